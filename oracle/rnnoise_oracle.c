@@ -1,0 +1,1350 @@
+/*
+ * oracle/rnnoise_oracle.c -- scalar f32 restatement of nnnoiseless 0.5.2 / xiph rnnoise.
+ * TEST INFRASTRUCTURE ONLY (see rnnoise_oracle.h).  PARITY UNPINNED (see header).
+ *
+ * Each function names the reference interface it stands behind and the upstream routine it
+ * restates.  The only in-tree citations possible are the call site `denoise.process_frame`
+ * at /root/reference/src-tauri/src/audio.rs:268 and the crate pin Cargo.lock:2825-2838; the
+ * upstream file names (nnnoiseless src/{denoise,features,pitch,rnn,util}.rs == rnnoise
+ * src/{denoise,pitch,celt_lpc,rnn}.c) are given per function.
+ *
+ * Build: gcc -O2 -ffp-contract=off (Rust never contracts a*b+c into an FMA, so neither do we).
+ */
+#include "rnnoise_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define FRAME_SIZE 480
+#define WINDOW_SIZE 960
+#define FREQ_SIZE 481
+#define PITCH_MIN_PERIOD 60
+#define PITCH_MAX_PERIOD 768
+#define PITCH_FRAME_SIZE 960
+#define PITCH_BUF_SIZE (PITCH_MAX_PERIOD + PITCH_FRAME_SIZE)
+#define NB_BANDS 22
+#define CEPS_MEM 8
+#define NB_DELTA_CEPS 6
+#define NB_FEATURES (NB_BANDS + 3 * NB_DELTA_CEPS + 2)
+#define FRAME_SIZE_SHIFT 2
+#define WEIGHTS_SCALE (1.f / 256)
+
+#define ACT_TANH 0
+#define ACT_SIGMOID 1
+#define ACT_RELU 2
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+typedef struct {
+  float r, i;
+} cpx;
+
+/* upstream: denoise.c `eband5ms` / nnnoiseless lib.rs EBAND_5MS */
+static const int eband5ms[NB_BANDS] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  10, 12,
+                                       14, 16, 20, 24, 28, 34, 40, 48, 60, 78, 100};
+
+/* ------------------------------------------------------------------------------------------ */
+/* tables                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+static float g_half_window[FRAME_SIZE];
+static float g_dct_table[NB_BANDS * NB_BANDS];
+static float g_tansig[201];
+static cpx g_tw480[480];  /* exp(-2 pi i k / 480) */
+static cpx g_tw960[481];  /* exp(-2 pi i k / 960), k <= 480 */
+static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+
+static void init_tables(void) {
+  int i, j;
+  /* upstream: denoise.c check_init(): half_window, dct_table */
+  for (i = 0; i < FRAME_SIZE; i++) {
+    double s = sin(.5 * M_PI * (i + .5) / FRAME_SIZE);
+    g_half_window[i] = (float)sin(.5 * M_PI * s * s);
+  }
+  for (i = 0; i < NB_BANDS; i++)
+    for (j = 0; j < NB_BANDS; j++) {
+      double v = cos((i + .5) * j * M_PI / NB_BANDS);
+      if (j == 0) v *= sqrt(.5);
+      g_dct_table[i * NB_BANDS + j] = (float)v;
+    }
+  /* upstream: tansig_table.h -- tanh(0.04 i) printed with 6 decimals */
+  for (i = 0; i <= 200; i++) g_tansig[i] = (float)(floor(tanh(.04 * i) * 1e6 + .5) / 1e6);
+  for (i = 0; i < 480; i++) {
+    g_tw480[i].r = (float)cos(2 * M_PI * i / 480);
+    g_tw480[i].i = (float)-sin(2 * M_PI * i / 480);
+  }
+  for (i = 0; i <= 480; i++) {
+    g_tw960[i].r = (float)cos(2 * M_PI * i / 960);
+    g_tw960[i].i = (float)-sin(2 * M_PI * i / 960);
+  }
+}
+static void ensure_tables(void) { pthread_once(&g_once, init_tables); }
+
+const float *rno_half_window(void) {
+  ensure_tables();
+  return g_half_window;
+}
+const float *rno_dct_table(void) {
+  ensure_tables();
+  return g_dct_table;
+}
+const float *rno_tansig_table(void) {
+  ensure_tables();
+  return g_tansig;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* FFT: 480-point complex mixed radix (2,3,5) in f32 + real packing.  Stands in for            */
+/* easyfft/realfft/rustfft (Cargo.lock:1200-1210, :3927-3933, :4199-4210), which compute the   */
+/* same DFT in f32; only rounding differs.                                                    */
+/* ------------------------------------------------------------------------------------------ */
+static cpx cmul(cpx a, cpx b) {
+  cpx c;
+  c.r = a.r * b.r - a.i * b.i;
+  c.i = a.r * b.i + a.i * b.r;
+  return c;
+}
+
+/* out[k] = sum_n in[n*stride] W_N^{nk}; recursive decimation in time over the smallest factor */
+static void fft_rec(cpx *out, const cpx *in, int n, int stride) {
+  int p, m, k, q, r;
+  cpx tmp[5];
+  if (n == 1) {
+    out[0] = in[0];
+    return;
+  }
+  p = (n % 2 == 0) ? 2 : (n % 3 == 0) ? 3 : 5;
+  m = n / p;
+  for (q = 0; q < p; q++) fft_rec(out + q * m, in + q * stride, m, stride * p);
+  for (k = 0; k < m; k++) {
+    for (q = 0; q < p; q++) tmp[q] = cmul(out[q * m + k], g_tw480[(q * k * (480 / n)) % 480]);
+    for (r = 0; r < p; r++) {
+      cpx acc = tmp[0];
+      for (q = 1; q < p; q++) {
+        cpx w = g_tw480[((q * r) % p) * (480 / p)];
+        cpx t = cmul(tmp[q], w);
+        acc.r += t.r;
+        acc.i += t.i;
+      }
+      out[r * m + k] = acc;
+    }
+  }
+}
+
+/* upstream: denoise.c forward_transform (kiss_fft scales by 1/N); nnnoiseless scales by
+ * 1/WINDOW_SIZE after an unscaled real FFT. */
+static void forward_transform(cpx *out, const float *in) {
+  cpx z[480], Z[480];
+  int k;
+  const float norm = 1.0f / WINDOW_SIZE;
+  for (k = 0; k < 480; k++) {
+    z[k].r = in[2 * k];
+    z[k].i = in[2 * k + 1];
+  }
+  fft_rec(Z, z, 480, 1);
+  for (k = 0; k <= 480; k++) {
+    cpx a = Z[k % 480], b = Z[(480 - k) % 480], e, o, t;
+    b.i = -b.i; /* conj(Z[N-k]) */
+    e.r = .5f * (a.r + b.r);
+    e.i = .5f * (a.i + b.i);
+    o.r = .5f * (a.r - b.r);
+    o.i = .5f * (a.i - b.i);
+    /* X[k] = E[k] - i W960^k O[k] */
+    t = cmul(o, g_tw960[k]);
+    out[k].r = (e.r + t.i) * norm;
+    out[k].i = (e.i - t.r) * norm;
+  }
+}
+
+/* upstream: denoise.c inverse_transform -- Hermitian extension, UNSCALED inverse DFT. */
+static void inverse_transform(float *out, const cpx *in) {
+  cpx z[480], Z[480];
+  int k;
+  /* x[n] = sum_{k<960} X[k] e^{+2 pi i k n/960};  with z[m] = x[2m] + i x[2m+1]:
+   * z = IDFT480( (X[k] + conj(X[480-k])) + i e^{+2 pi i k/960} (X[k] - conj(X[480-k])) ).
+   * IDFT480(Y)[m] = conj(DFT480(conj(Y)))[m]. */
+  for (k = 0; k < 480; k++) {
+    cpx a = in[k], b = in[480 - k], e, o, w, t;
+    b.i = -b.i;
+    e.r = a.r + b.r;
+    e.i = a.i + b.i;
+    o.r = a.r - b.r;
+    o.i = a.i - b.i;
+    w = g_tw960[k];
+    w.i = -w.i; /* e^{+...} */
+    t = cmul(o, w);
+    /* e + i t, then conjugate for the forward-FFT trick */
+    Z[k].r = e.r - t.i;
+    Z[k].i = -(e.i + t.r);
+  }
+  fft_rec(z, Z, 480, 1);
+  for (k = 0; k < 480; k++) {
+    out[2 * k] = z[k].r;
+    out[2 * k + 1] = -z[k].i;
+  }
+}
+
+void rno_forward_transform(float *out, const float *in) {
+  ensure_tables();
+  forward_transform((cpx *)out, in);
+}
+void rno_inverse_transform(float *out, const float *in) {
+  ensure_tables();
+  inverse_transform(out, (const cpx *)in);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* model                                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int nb_inputs, nb_neurons, activation;
+  int8_t *weights; /* [in][out] */
+  int8_t *bias;    /* [out] */
+} dense_layer;
+typedef struct {
+  int nb_inputs, nb_neurons, activation;
+  int8_t *input_weights;     /* [in][3N] */
+  int8_t *recurrent_weights; /* [N][3N] */
+  int8_t *bias;              /* [3N] */
+} gru_layer;
+
+struct rno_model {
+  dense_layer input_dense;
+  gru_layer vad_gru;
+  dense_layer vad_output;
+  gru_layer noise_gru;
+  gru_layer denoise_gru;
+  dense_layer denoise_output;
+};
+
+static void dense_alloc(dense_layer *l, int in, int out, int act) {
+  l->nb_inputs = in;
+  l->nb_neurons = out;
+  l->activation = act;
+  l->weights = (int8_t *)calloc((size_t)in * out, 1);
+  l->bias = (int8_t *)calloc((size_t)out, 1);
+}
+static void gru_alloc(gru_layer *l, int in, int n, int act) {
+  l->nb_inputs = in;
+  l->nb_neurons = n;
+  l->activation = act;
+  l->input_weights = (int8_t *)calloc((size_t)in * 3 * n, 1);
+  l->recurrent_weights = (int8_t *)calloc((size_t)n * 3 * n, 1);
+  l->bias = (int8_t *)calloc((size_t)3 * n, 1);
+}
+
+void rno_model_free(rno_model *m) {
+  if (!m) return;
+  free(m->input_dense.weights);
+  free(m->input_dense.bias);
+  free(m->vad_output.weights);
+  free(m->vad_output.bias);
+  free(m->denoise_output.weights);
+  free(m->denoise_output.bias);
+  free(m->vad_gru.input_weights);
+  free(m->vad_gru.recurrent_weights);
+  free(m->vad_gru.bias);
+  free(m->noise_gru.input_weights);
+  free(m->noise_gru.recurrent_weights);
+  free(m->noise_gru.bias);
+  free(m->denoise_gru.input_weights);
+  free(m->denoise_gru.recurrent_weights);
+  free(m->denoise_gru.bias);
+  free(m);
+}
+
+static rno_model *model_alloc_default_shapes(void) {
+  /* SURVEY.md Appendix A.6 topology (rnnoise rnn_data.c) */
+  rno_model *m = (rno_model *)calloc(1, sizeof(*m));
+  dense_alloc(&m->input_dense, 42, 24, ACT_TANH);
+  gru_alloc(&m->vad_gru, 24, 24, ACT_RELU);
+  dense_alloc(&m->vad_output, 24, 1, ACT_SIGMOID);
+  gru_alloc(&m->noise_gru, 90, 48, ACT_RELU);
+  gru_alloc(&m->denoise_gru, 114, 96, ACT_RELU);
+  dense_alloc(&m->denoise_output, 96, 22, ACT_SIGMOID);
+  return m;
+}
+
+/* Seeded synthetic int8 weights (the real nnnoiseless weights are not available offline).
+ * The generator is specified in DESIGN.md "Synthetic model" and implemented twice on purpose:
+ * here and in crispy_b200/csrc/model.cpp; tests assert both emit identical bytes. */
+static uint64_t splitmix64(uint64_t *s) {
+  uint64_t z = (*s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static void fill_q(int8_t *dst, size_t n, uint64_t *s, int amp, int offset) {
+  size_t i;
+  for (i = 0; i < n; i++) {
+    uint64_t u = splitmix64(s);
+    int a = (int)(u & 0xFFFF), b = (int)((u >> 16) & 0xFFFF), c = (int)((u >> 32) & 0xFFFF),
+        d = (int)((u >> 48) & 0xFFFF);
+    int t = a + b + c + d - 131070; /* ~N(0, 37837^2), Irwin-Hall n=4 */
+    int w = (t * amp) / 131072 + offset;
+    if (w > 127) w = 127;
+    if (w < -127) w = -127;
+    dst[i] = (int8_t)w;
+  }
+}
+
+rno_model *rno_model_synthetic(uint64_t seed) {
+  rno_model *m = model_alloc_default_shapes();
+  uint64_t s = seed ^ 0xC215B200C215B200ull;
+  fill_q(m->input_dense.weights, 42 * 24, &s, 80, 0);
+  fill_q(m->input_dense.bias, 24, &s, 80, 0);
+  fill_q(m->vad_gru.input_weights, 24 * 72, &s, 250, 0);
+  fill_q(m->vad_gru.recurrent_weights, 24 * 72, &s, 110, 0);
+  fill_q(m->vad_gru.bias, 72, &s, 100, 0);
+  fill_q(m->vad_output.weights, 24, &s, 500, 0);
+  fill_q(m->vad_output.bias, 1, &s, 40, 0);
+  fill_q(m->noise_gru.input_weights, 90 * 144, &s, 160, 0);
+  fill_q(m->noise_gru.recurrent_weights, 48 * 144, &s, 80, 0);
+  fill_q(m->noise_gru.bias, 144, &s, 100, 0);
+  fill_q(m->denoise_gru.input_weights, 114 * 288, &s, 160, 0);
+  fill_q(m->denoise_gru.recurrent_weights, 96 * 288, &s, 60, 0);
+  fill_q(m->denoise_gru.bias, 288, &s, 100, 0);
+  fill_q(m->denoise_output.weights, 96 * 22, &s, 400, 0);
+  fill_q(m->denoise_output.bias, 22, &s, 120, 40);
+  return m;
+}
+
+/* binary blob "CRNSMDL1": magic[8]; then 6 layers in A.6 order, each
+ * u32 kind(0 dense,1 gru) | u32 nb_inputs | u32 nb_neurons | u32 activation | int8 arrays */
+static const char kMagic[8] = {'C', 'R', 'N', 'S', 'M', 'D', 'L', '1'};
+
+static size_t put_u32(uint8_t *p, size_t off, size_t cap, uint32_t v) {
+  if (p && off + 4 <= cap) {
+    p[off] = (uint8_t)v;
+    p[off + 1] = (uint8_t)(v >> 8);
+    p[off + 2] = (uint8_t)(v >> 16);
+    p[off + 3] = (uint8_t)(v >> 24);
+  }
+  return off + 4;
+}
+static size_t put_bytes(uint8_t *p, size_t off, size_t cap, const void *src, size_t n) {
+  if (p && off + n <= cap) memcpy(p + off, src, n);
+  return off + n;
+}
+static size_t put_dense(uint8_t *p, size_t off, size_t cap, const dense_layer *l) {
+  off = put_u32(p, off, cap, 0);
+  off = put_u32(p, off, cap, (uint32_t)l->nb_inputs);
+  off = put_u32(p, off, cap, (uint32_t)l->nb_neurons);
+  off = put_u32(p, off, cap, (uint32_t)l->activation);
+  off = put_bytes(p, off, cap, l->weights, (size_t)l->nb_inputs * l->nb_neurons);
+  off = put_bytes(p, off, cap, l->bias, (size_t)l->nb_neurons);
+  return off;
+}
+static size_t put_gru(uint8_t *p, size_t off, size_t cap, const gru_layer *l) {
+  size_t n3 = 3 * (size_t)l->nb_neurons;
+  off = put_u32(p, off, cap, 1);
+  off = put_u32(p, off, cap, (uint32_t)l->nb_inputs);
+  off = put_u32(p, off, cap, (uint32_t)l->nb_neurons);
+  off = put_u32(p, off, cap, (uint32_t)l->activation);
+  off = put_bytes(p, off, cap, l->input_weights, (size_t)l->nb_inputs * n3);
+  off = put_bytes(p, off, cap, l->recurrent_weights, (size_t)l->nb_neurons * n3);
+  off = put_bytes(p, off, cap, l->bias, n3);
+  return off;
+}
+
+size_t rno_model_to_bytes(const rno_model *m, void *buf, size_t cap) {
+  uint8_t *p = (uint8_t *)buf;
+  size_t off = put_bytes(p, 0, cap, kMagic, 8);
+  off = put_dense(p, off, cap, &m->input_dense);
+  off = put_gru(p, off, cap, &m->vad_gru);
+  off = put_dense(p, off, cap, &m->vad_output);
+  off = put_gru(p, off, cap, &m->noise_gru);
+  off = put_gru(p, off, cap, &m->denoise_gru);
+  off = put_dense(p, off, cap, &m->denoise_output);
+  return off;
+}
+
+typedef struct {
+  const uint8_t *p;
+  size_t len, off;
+  int err;
+} rd;
+static uint32_t get_u32(rd *r) {
+  uint32_t v;
+  if (r->off + 4 > r->len) {
+    r->err = 1;
+    return 0;
+  }
+  v = (uint32_t)r->p[r->off] | ((uint32_t)r->p[r->off + 1] << 8) |
+      ((uint32_t)r->p[r->off + 2] << 16) | ((uint32_t)r->p[r->off + 3] << 24);
+  r->off += 4;
+  return v;
+}
+static void get_bytes(rd *r, void *dst, size_t n) {
+  if (r->off + n > r->len) {
+    r->err = 1;
+    return;
+  }
+  memcpy(dst, r->p + r->off, n);
+  r->off += n;
+}
+static void get_dense(rd *r, dense_layer *l) {
+  uint32_t kind = get_u32(r), in = get_u32(r), out = get_u32(r), act = get_u32(r);
+  if (r->err || kind != 0 || (int)in != l->nb_inputs || (int)out != l->nb_neurons || act > 2) {
+    r->err = 1;
+    return;
+  }
+  l->activation = (int)act;
+  get_bytes(r, l->weights, (size_t)in * out);
+  get_bytes(r, l->bias, out);
+}
+static void get_gru(rd *r, gru_layer *l) {
+  uint32_t kind = get_u32(r), in = get_u32(r), n = get_u32(r), act = get_u32(r);
+  if (r->err || kind != 1 || (int)in != l->nb_inputs || (int)n != l->nb_neurons || act > 2) {
+    r->err = 1;
+    return;
+  }
+  l->activation = (int)act;
+  get_bytes(r, l->input_weights, (size_t)in * 3 * n);
+  get_bytes(r, l->recurrent_weights, (size_t)n * 3 * n);
+  get_bytes(r, l->bias, (size_t)3 * n);
+}
+
+/* rnnoise-nu text model: "rnnoise-nu model file version 1", then per layer a header line
+ * (dense: in out act; gru: in out act) followed by whitespace-separated integers.  Layer order in
+ * that format: input_dense, vad_gru, noise_gru, denoise_gru, denoise_output, vad_output. */
+typedef struct {
+  const char *p, *end;
+  int err;
+} trd;
+static long text_int(trd *t) {
+  char *e;
+  long v;
+  while (t->p < t->end && (*t->p == ' ' || *t->p == '\n' || *t->p == '\r' || *t->p == '\t')) t->p++;
+  if (t->p >= t->end) {
+    t->err = 1;
+    return 0;
+  }
+  v = strtol(t->p, &e, 10);
+  if (e == t->p) {
+    t->err = 1;
+    return 0;
+  }
+  t->p = e;
+  return v;
+}
+static void text_arr(trd *t, int8_t *dst, size_t n) {
+  size_t i;
+  for (i = 0; i < n && !t->err; i++) {
+    long v = text_int(t);
+    if (v > 127) v = 127;
+    if (v < -128) v = -128;
+    dst[i] = (int8_t)v;
+  }
+}
+static void text_dense(trd *t, dense_layer *l) {
+  long in = text_int(t), out = text_int(t), act = text_int(t);
+  if (t->err || in != l->nb_inputs || out != l->nb_neurons || act < 0 || act > 2) {
+    t->err = 1;
+    return;
+  }
+  l->activation = (int)act;
+  text_arr(t, l->weights, (size_t)in * out);
+  text_arr(t, l->bias, (size_t)out);
+}
+static void text_gru(trd *t, gru_layer *l) {
+  long in = text_int(t), n = text_int(t), act = text_int(t);
+  if (t->err || in != l->nb_inputs || n != l->nb_neurons || act < 0 || act > 2) {
+    t->err = 1;
+    return;
+  }
+  l->activation = (int)act;
+  text_arr(t, l->input_weights, (size_t)in * 3 * n);
+  text_arr(t, l->recurrent_weights, (size_t)n * 3 * n);
+  text_arr(t, l->bias, (size_t)3 * n);
+}
+
+rno_model *rno_model_from_bytes(const void *blob, size_t len) {
+  static const char kText[] = "rnnoise-nu model file version 1";
+  rno_model *m;
+  if (!blob) return NULL;
+  m = model_alloc_default_shapes();
+  if (len >= 8 && memcmp(blob, kMagic, 8) == 0) {
+    rd r;
+    r.p = (const uint8_t *)blob;
+    r.len = len;
+    r.off = 8;
+    r.err = 0;
+    get_dense(&r, &m->input_dense);
+    get_gru(&r, &m->vad_gru);
+    get_dense(&r, &m->vad_output);
+    get_gru(&r, &m->noise_gru);
+    get_gru(&r, &m->denoise_gru);
+    get_dense(&r, &m->denoise_output);
+    if (r.err || r.off != len) {
+      rno_model_free(m);
+      return NULL;
+    }
+    return m;
+  }
+  if (len >= sizeof(kText) - 1 && memcmp(blob, kText, sizeof(kText) - 1) == 0) {
+    trd t;
+    t.p = (const char *)blob + sizeof(kText) - 1;
+    t.end = (const char *)blob + len;
+    t.err = 0;
+    text_dense(&t, &m->input_dense);
+    text_gru(&t, &m->vad_gru);
+    text_gru(&t, &m->noise_gru);
+    text_gru(&t, &m->denoise_gru);
+    text_dense(&t, &m->denoise_output);
+    text_dense(&t, &m->vad_output);
+    if (t.err) {
+      rno_model_free(m);
+      return NULL;
+    }
+    return m;
+  }
+  rno_model_free(m);
+  return NULL;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* state (nnnoiseless DenoiseState; reference type at audio.rs:203)                            */
+/* ------------------------------------------------------------------------------------------ */
+struct rno_state {
+  const rno_model *model;
+  float analysis_mem[FRAME_SIZE];
+  float cepstral_mem[CEPS_MEM][NB_BANDS];
+  int memid;
+  float synthesis_mem[FRAME_SIZE];
+  float pitch_buf[PITCH_BUF_SIZE];
+  float last_gain;
+  int last_period;
+  float mem_hp_x[2];
+  float lastg[NB_BANDS];
+  float vad_gru_state[24];
+  float noise_gru_state[48];
+  float denoise_gru_state[96];
+  rno_debug dbg;
+};
+
+rno_state *rno_create(const rno_model *m) {
+  rno_state *st;
+  ensure_tables();
+  st = (rno_state *)calloc(1, sizeof(*st));
+  st->model = m;
+  return st;
+}
+void rno_reset(rno_state *st) {
+  const rno_model *m = st->model;
+  memset(st, 0, sizeof(*st));
+  st->model = m;
+}
+void rno_destroy(rno_state *st) { free(st); }
+void rno_get_debug(const rno_state *st, rno_debug *dbg) { *dbg = st->dbg; }
+
+/* ------------------------------------------------------------------------------------------ */
+/* a6: biquad high-pass.  upstream denoise.c biquad() (double intermediates, f32 memory).      */
+/* ------------------------------------------------------------------------------------------ */
+static void biquad(float *y, float mem[2], const float *x, const float *b, const float *a, int N) {
+  int i;
+  for (i = 0; i < N; i++) {
+    float xi = x[i];
+    float yi = x[i] + mem[0];
+    mem[0] = (float)(mem[1] + (b[0] * (double)xi - a[0] * (double)yi));
+    mem[1] = (float)(b[1] * (double)xi - a[1] * (double)yi);
+    y[i] = yi;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a7/a8: window, band energy / correlation, interpolation, DCT (denoise.c)                   */
+/* ------------------------------------------------------------------------------------------ */
+static void apply_window(float *x) {
+  int i;
+  for (i = 0; i < FRAME_SIZE; i++) {
+    x[i] *= g_half_window[i];
+    x[WINDOW_SIZE - 1 - i] *= g_half_window[i];
+  }
+}
+
+static void compute_band_energy(float *bandE, const cpx *X) {
+  int i, j;
+  float sum[NB_BANDS] = {0};
+  for (i = 0; i < NB_BANDS - 1; i++) {
+    int band_size = (eband5ms[i + 1] - eband5ms[i]) << FRAME_SIZE_SHIFT;
+    for (j = 0; j < band_size; j++) {
+      float frac = (float)j / band_size;
+      int k = (eband5ms[i] << FRAME_SIZE_SHIFT) + j;
+      float tmp = X[k].r * X[k].r + X[k].i * X[k].i;
+      sum[i] += (1 - frac) * tmp;
+      sum[i + 1] += frac * tmp;
+    }
+  }
+  sum[0] *= 2;
+  sum[NB_BANDS - 1] *= 2;
+  for (i = 0; i < NB_BANDS; i++) bandE[i] = sum[i];
+}
+
+static void compute_band_corr(float *bandE, const cpx *X, const cpx *P) {
+  int i, j;
+  float sum[NB_BANDS] = {0};
+  for (i = 0; i < NB_BANDS - 1; i++) {
+    int band_size = (eband5ms[i + 1] - eband5ms[i]) << FRAME_SIZE_SHIFT;
+    for (j = 0; j < band_size; j++) {
+      float frac = (float)j / band_size;
+      int k = (eband5ms[i] << FRAME_SIZE_SHIFT) + j;
+      float tmp = X[k].r * P[k].r + X[k].i * P[k].i;
+      sum[i] += (1 - frac) * tmp;
+      sum[i + 1] += frac * tmp;
+    }
+  }
+  sum[0] *= 2;
+  sum[NB_BANDS - 1] *= 2;
+  for (i = 0; i < NB_BANDS; i++) bandE[i] = sum[i];
+}
+
+static void interp_band_gain(float *g, const float *bandE) {
+  int i, j;
+  memset(g, 0, FREQ_SIZE * sizeof(float));
+  for (i = 0; i < NB_BANDS - 1; i++) {
+    int band_size = (eband5ms[i + 1] - eband5ms[i]) << FRAME_SIZE_SHIFT;
+    for (j = 0; j < band_size; j++) {
+      float frac = (float)j / band_size;
+      g[(eband5ms[i] << FRAME_SIZE_SHIFT) + j] = (1 - frac) * bandE[i] + frac * bandE[i + 1];
+    }
+  }
+}
+
+static void dct(float *out, const float *in) {
+  int i, j;
+  const float scale = (float)sqrt(2. / 22);
+  for (i = 0; i < NB_BANDS; i++) {
+    float sum = 0;
+    for (j = 0; j < NB_BANDS; j++) sum += in[j] * g_dct_table[j * NB_BANDS + i];
+    out[i] = sum * scale;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a9: pitch_downsample (pitch.c) + _celt_autocorr/_celt_lpc (celt_lpc.c) + celt_fir5          */
+/* ------------------------------------------------------------------------------------------ */
+static void celt_pitch_xcorr(const float *x, const float *y, float *xcorr, int len, int max_pitch) {
+  int i, j;
+  for (i = 0; i < max_pitch; i++) {
+    float sum = 0;
+    for (j = 0; j < len; j++) sum += x[j] * y[i + j];
+    xcorr[i] = sum;
+  }
+}
+static float celt_inner_prod(const float *x, const float *y, int N) {
+  int i;
+  float xy = 0;
+  for (i = 0; i < N; i++) xy += x[i] * y[i];
+  return xy;
+}
+static void dual_inner_prod(const float *x, const float *y01, const float *y02, int N, float *xy1,
+                            float *xy2) {
+  int i;
+  float a = 0, b = 0;
+  for (i = 0; i < N; i++) {
+    a += x[i] * y01[i];
+    b += x[i] * y02[i];
+  }
+  *xy1 = a;
+  *xy2 = b;
+}
+
+static void celt_autocorr(const float *x, float *ac, int lag, int n) {
+  int i, k;
+  int fastN = n - lag;
+  celt_pitch_xcorr(x, x, ac, fastN, lag + 1);
+  for (k = 0; k <= lag; k++) {
+    float d = 0;
+    for (i = k + fastN; i < n; i++) d += x[i] * x[i - k];
+    ac[k] += d;
+  }
+}
+
+static void celt_lpc(float *lpc, const float *ac, int p) {
+  int i, j;
+  float error = ac[0];
+  for (i = 0; i < p; i++) lpc[i] = 0;
+  if (ac[0] != 0) {
+    for (i = 0; i < p; i++) {
+      float rr = 0, r;
+      for (j = 0; j < i; j++) rr += lpc[j] * ac[i - j];
+      rr += ac[i + 1];
+      r = -rr / error;
+      lpc[i] = r;
+      for (j = 0; j < (i + 1) >> 1; j++) {
+        float tmp1 = lpc[j], tmp2 = lpc[i - 1 - j];
+        lpc[j] = tmp1 + r * tmp2;
+        lpc[i - 1 - j] = tmp2 + r * tmp1;
+      }
+      error = error - r * r * error;
+      if (error < .001f * ac[0]) break;
+    }
+  }
+}
+
+static void celt_fir5(const float *x, const float *num, float *y, int N, float *mem) {
+  int i;
+  float num0 = num[0], num1 = num[1], num2 = num[2], num3 = num[3], num4 = num[4];
+  float mem0 = mem[0], mem1 = mem[1], mem2 = mem[2], mem3 = mem[3], mem4 = mem[4];
+  for (i = 0; i < N; i++) {
+    float sum = x[i];
+    sum += num0 * mem0;
+    sum += num1 * mem1;
+    sum += num2 * mem2;
+    sum += num3 * mem3;
+    sum += num4 * mem4;
+    mem4 = mem3;
+    mem3 = mem2;
+    mem2 = mem1;
+    mem1 = mem0;
+    mem0 = x[i];
+    y[i] = sum;
+  }
+  mem[0] = mem0;
+  mem[1] = mem1;
+  mem[2] = mem2;
+  mem[3] = mem3;
+  mem[4] = mem4;
+}
+
+static void pitch_downsample(const float *x, float *x_lp, int len) {
+  int i;
+  float ac[5];
+  float tmp = 1.f;
+  float lpc[4], mem[5] = {0, 0, 0, 0, 0};
+  float lpc2[5];
+  float c1 = .8f;
+  for (i = 1; i < len >> 1; i++)
+    x_lp[i] = .5f * (.5f * (x[2 * i - 1] + x[2 * i + 1]) + x[2 * i]);
+  x_lp[0] = .5f * (.5f * x[1] + x[0]);
+  celt_autocorr(x_lp, ac, 4, len >> 1);
+  ac[0] *= 1.0001f;
+  for (i = 1; i <= 4; i++) ac[i] -= ac[i] * (.008f * i) * (.008f * i);
+  celt_lpc(lpc, ac, 4);
+  for (i = 0; i < 4; i++) {
+    tmp = .9f * tmp;
+    lpc[i] = lpc[i] * tmp;
+  }
+  lpc2[0] = lpc[0] + .8f;
+  lpc2[1] = lpc[1] + c1 * lpc[0];
+  lpc2[2] = lpc[2] + c1 * lpc[1];
+  lpc2[3] = lpc[3] + c1 * lpc[2];
+  lpc2[4] = c1 * lpc[3];
+  celt_fir5(x_lp, lpc2, x_lp, len >> 1, mem);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a10: pitch_search / find_best_pitch (pitch.c)                                              */
+/* ------------------------------------------------------------------------------------------ */
+static void find_best_pitch(const float *xcorr, const float *y, int len, int max_pitch,
+                            int *best_pitch) {
+  int i, j;
+  float Syy = 1;
+  float best_num[2] = {-1, -1};
+  float best_den[2] = {0, 0};
+  best_pitch[0] = 0;
+  best_pitch[1] = 1;
+  for (j = 0; j < len; j++) Syy += y[j] * y[j];
+  for (i = 0; i < max_pitch; i++) {
+    if (xcorr[i] > 0) {
+      float num;
+      float xcorr16 = xcorr[i];
+      xcorr16 *= 1e-12f;
+      num = xcorr16 * xcorr16;
+      if (num * best_den[1] > best_num[1] * Syy) {
+        if (num * best_den[0] > best_num[0] * Syy) {
+          best_num[1] = best_num[0];
+          best_den[1] = best_den[0];
+          best_pitch[1] = best_pitch[0];
+          best_num[0] = num;
+          best_den[0] = Syy;
+          best_pitch[0] = i;
+        } else {
+          best_num[1] = num;
+          best_den[1] = Syy;
+          best_pitch[1] = i;
+        }
+      }
+    }
+    Syy += y[i + len] * y[i + len] - y[i] * y[i];
+    if (Syy < 1) Syy = 1;
+  }
+}
+
+static void pitch_search(const float *x_lp, const float *y, int len, int max_pitch, int *pitch) {
+  int i, j;
+  int lag = len + max_pitch;
+  int best_pitch[2] = {0, 0};
+  int offset;
+  float x_lp4[PITCH_FRAME_SIZE >> 2];
+  float y_lp4[(PITCH_FRAME_SIZE + PITCH_MAX_PERIOD) >> 2];
+  float xcorr[PITCH_MAX_PERIOD >> 1];
+  for (j = 0; j < len >> 2; j++) x_lp4[j] = x_lp[2 * j];
+  for (j = 0; j < lag >> 2; j++) y_lp4[j] = y[2 * j];
+  celt_pitch_xcorr(x_lp4, y_lp4, xcorr, len >> 2, max_pitch >> 2);
+  find_best_pitch(xcorr, y_lp4, len >> 2, max_pitch >> 2, best_pitch);
+  for (i = 0; i < max_pitch >> 1; i++) {
+    float sum;
+    xcorr[i] = 0;
+    if (abs(i - 2 * best_pitch[0]) > 2 && abs(i - 2 * best_pitch[1]) > 2) continue;
+    sum = celt_inner_prod(x_lp, y + i, len >> 1);
+    xcorr[i] = sum < -1 ? -1 : sum;
+  }
+  find_best_pitch(xcorr, y, len >> 1, max_pitch >> 1, best_pitch);
+  if (best_pitch[0] > 0 && best_pitch[0] < (max_pitch >> 1) - 1) {
+    float a = xcorr[best_pitch[0] - 1], b = xcorr[best_pitch[0]], c = xcorr[best_pitch[0] + 1];
+    if ((c - a) > .7f * (b - a))
+      offset = 1;
+    else if ((a - c) > .7f * (b - c))
+      offset = -1;
+    else
+      offset = 0;
+  } else {
+    offset = 0;
+  }
+  *pitch = 2 * best_pitch[0] - offset;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a11: remove_doubling (pitch.c)                                                             */
+/* ------------------------------------------------------------------------------------------ */
+static float compute_pitch_gain(float xy, float xx, float yy) {
+  return xy / (float)sqrt(1 + xx * yy);
+}
+static const int second_check[16] = {0, 0, 3, 2, 3, 2, 5, 2, 3, 2, 3, 2, 5, 2, 3, 2};
+
+static float remove_doubling(const float *x, int maxperiod, int minperiod, int N, int *T0_,
+                             int prev_period, float prev_gain) {
+  int k, i, T, T0;
+  float g, g0, pg;
+  float xy, xx, yy, xy2;
+  float xcorr[3];
+  float best_xy, best_yy;
+  int offset;
+  int minperiod0 = minperiod;
+  float yy_lookup[(PITCH_MAX_PERIOD >> 1) + 1];
+  maxperiod /= 2;
+  minperiod /= 2;
+  *T0_ /= 2;
+  prev_period /= 2;
+  N /= 2;
+  x += maxperiod;
+  if (*T0_ >= maxperiod) *T0_ = maxperiod - 1;
+  T = T0 = *T0_;
+  dual_inner_prod(x, x, x - T0, N, &xx, &xy);
+  yy_lookup[0] = xx;
+  yy = xx;
+  for (i = 1; i <= maxperiod; i++) {
+    yy = yy + x[-i] * x[-i] - x[N - i] * x[N - i];
+    yy_lookup[i] = yy < 0 ? 0 : yy;
+  }
+  yy = yy_lookup[T0];
+  best_xy = xy;
+  best_yy = yy;
+  g = g0 = compute_pitch_gain(xy, xx, yy);
+  for (k = 2; k <= 15; k++) {
+    int T1, T1b;
+    float g1, cont = 0, thresh;
+    T1 = (2 * T0 + k) / (2 * k);
+    if (T1 < minperiod) break;
+    if (k == 2) {
+      if (T1 + T0 > maxperiod)
+        T1b = T0;
+      else
+        T1b = T0 + T1;
+    } else {
+      T1b = (2 * second_check[k] * T0 + k) / (2 * k);
+    }
+    dual_inner_prod(x, &x[-T1], &x[-T1b], N, &xy, &xy2);
+    xy = .5f * (xy + xy2);
+    yy = .5f * (yy_lookup[T1] + yy_lookup[T1b]);
+    g1 = compute_pitch_gain(xy, xx, yy);
+    if (abs(T1 - prev_period) <= 1)
+      cont = prev_gain;
+    else if (abs(T1 - prev_period) <= 2 && 5 * k * k < T0)
+      cont = .5f * prev_gain;
+    else
+      cont = 0;
+    thresh = .7f * g0 - cont;
+    if (thresh < .3f) thresh = .3f;
+    if (T1 < 3 * minperiod) {
+      thresh = .85f * g0 - cont;
+      if (thresh < .4f) thresh = .4f;
+    } else if (T1 < 2 * minperiod) {
+      thresh = .9f * g0 - cont;
+      if (thresh < .5f) thresh = .5f;
+    }
+    if (g1 > thresh) {
+      best_xy = xy;
+      best_yy = yy;
+      T = T1;
+      g = g1;
+    }
+  }
+  if (best_xy < 0) best_xy = 0;
+  if (best_yy <= best_xy)
+    pg = 1.f;
+  else
+    pg = best_xy / (best_yy + 1);
+  for (k = 0; k < 3; k++) xcorr[k] = celt_inner_prod(x, x - (T + k - 1), N);
+  if ((xcorr[2] - xcorr[0]) > .7f * (xcorr[1] - xcorr[0]))
+    offset = 1;
+  else if ((xcorr[0] - xcorr[2]) > .7f * (xcorr[1] - xcorr[2]))
+    offset = -1;
+  else
+    offset = 0;
+  if (pg > g) pg = g;
+  *T0_ = 2 * T + offset;
+  if (*T0_ < minperiod0) *T0_ = minperiod0;
+  return pg;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a7, a12, a13: frame_analysis + compute_frame_features (denoise.c / nnnoiseless features.rs) */
+/* ------------------------------------------------------------------------------------------ */
+static void frame_analysis(rno_state *st, cpx *X, float *Ex, const float *in) {
+  float x[WINDOW_SIZE];
+  memcpy(x, st->analysis_mem, FRAME_SIZE * sizeof(float));
+  memcpy(x + FRAME_SIZE, in, FRAME_SIZE * sizeof(float));
+  memcpy(st->analysis_mem, in, FRAME_SIZE * sizeof(float));
+  apply_window(x);
+  forward_transform(X, x);
+  compute_band_energy(Ex, X);
+}
+
+static int compute_frame_features(rno_state *st, cpx *X, cpx *P, float *Ex, float *Ep, float *Exp,
+                                  float *features, const float *in) {
+  int i, j, k;
+  float E = 0;
+  float *ceps_0, *ceps_1, *ceps_2;
+  float spec_variability = 0;
+  float Ly[NB_BANDS];
+  float p[WINDOW_SIZE];
+  float pitch_buf[PITCH_BUF_SIZE >> 1];
+  int pitch_index;
+  float gain;
+  float tmp[NB_BANDS];
+  float follow, logMax;
+  frame_analysis(st, X, Ex, in);
+  memmove(st->pitch_buf, &st->pitch_buf[FRAME_SIZE], (PITCH_BUF_SIZE - FRAME_SIZE) * sizeof(float));
+  memcpy(&st->pitch_buf[PITCH_BUF_SIZE - FRAME_SIZE], in, FRAME_SIZE * sizeof(float));
+  pitch_downsample(st->pitch_buf, pitch_buf, PITCH_BUF_SIZE);
+  pitch_search(pitch_buf + (PITCH_MAX_PERIOD >> 1), pitch_buf, PITCH_FRAME_SIZE,
+               PITCH_MAX_PERIOD - 3 * PITCH_MIN_PERIOD, &pitch_index);
+  pitch_index = PITCH_MAX_PERIOD - pitch_index;
+  gain = remove_doubling(pitch_buf, PITCH_MAX_PERIOD, PITCH_MIN_PERIOD, PITCH_FRAME_SIZE,
+                         &pitch_index, st->last_period, st->last_gain);
+  st->last_period = pitch_index;
+  st->last_gain = gain;
+  st->dbg.pitch_index = pitch_index;
+  st->dbg.pitch_gain = gain;
+  for (i = 0; i < WINDOW_SIZE; i++)
+    p[i] = st->pitch_buf[PITCH_BUF_SIZE - WINDOW_SIZE - pitch_index + i];
+  apply_window(p);
+  forward_transform(P, p);
+  compute_band_energy(Ep, P);
+  compute_band_corr(Exp, X, P);
+  for (i = 0; i < NB_BANDS; i++) Exp[i] = Exp[i] / (float)sqrt(.001 + Ex[i] * Ep[i]);
+  dct(tmp, Exp);
+  for (i = 0; i < NB_DELTA_CEPS; i++) features[NB_BANDS + 2 * NB_DELTA_CEPS + i] = tmp[i];
+  features[NB_BANDS + 2 * NB_DELTA_CEPS] -= 1.3f;
+  features[NB_BANDS + 2 * NB_DELTA_CEPS + 1] -= 0.9f;
+  features[NB_BANDS + 3 * NB_DELTA_CEPS] = .01f * (pitch_index - 300);
+  logMax = -2;
+  follow = -2;
+  for (i = 0; i < NB_BANDS; i++) {
+    Ly[i] = (float)log10(1e-2 + Ex[i]);
+    Ly[i] = fmaxf(logMax - 7, fmaxf(follow - 1.5f, Ly[i]));
+    logMax = fmaxf(logMax, Ly[i]);
+    follow = fmaxf(follow - 1.5f, Ly[i]);
+    E += Ex[i];
+  }
+  if (E < 0.04f) {
+    /* silence: features zeroed, cepstral history / RNN state untouched */
+    memset(features, 0, NB_FEATURES * sizeof(float));
+    return 1;
+  }
+  dct(features, Ly);
+  features[0] -= 12;
+  features[1] -= 4;
+  ceps_0 = st->cepstral_mem[st->memid];
+  ceps_1 = (st->memid < 1) ? st->cepstral_mem[CEPS_MEM + st->memid - 1] : st->cepstral_mem[st->memid - 1];
+  ceps_2 = (st->memid < 2) ? st->cepstral_mem[CEPS_MEM + st->memid - 2] : st->cepstral_mem[st->memid - 2];
+  for (i = 0; i < NB_BANDS; i++) ceps_0[i] = features[i];
+  st->memid++;
+  for (i = 0; i < NB_DELTA_CEPS; i++) {
+    features[i] = ceps_0[i] + ceps_1[i] + ceps_2[i];
+    features[NB_BANDS + i] = ceps_0[i] - ceps_2[i];
+    features[NB_BANDS + NB_DELTA_CEPS + i] = ceps_0[i] - 2 * ceps_1[i] + ceps_2[i];
+  }
+  if (st->memid == CEPS_MEM) st->memid = 0;
+  for (i = 0; i < CEPS_MEM; i++) {
+    float mindist = 1e15f;
+    for (j = 0; j < CEPS_MEM; j++) {
+      float dist = 0;
+      for (k = 0; k < NB_BANDS; k++) {
+        float t = st->cepstral_mem[i][k] - st->cepstral_mem[j][k];
+        dist += t * t;
+      }
+      if (j != i) mindist = fminf(mindist, dist);
+    }
+    spec_variability += mindist;
+  }
+  features[NB_BANDS + 3 * NB_DELTA_CEPS + 1] = spec_variability / CEPS_MEM - 2.1f;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a14: RNN (rnn.c / nnnoiseless rnn.rs)                                                      */
+/* ------------------------------------------------------------------------------------------ */
+float rno_tansig_approx(float x) {
+  int i;
+  float y, dy;
+  float sign = 1;
+  ensure_tables();
+  if (!(x < 8)) return 1;
+  if (!(x > -8)) return -1;
+  if (x < 0) {
+    x = -x;
+    sign = -1;
+  }
+  i = (int)floor(.5f + 25 * x);
+  x -= .04f * i;
+  y = g_tansig[i];
+  dy = 1 - y * y;
+  y = y + x * dy * (1 - y * x);
+  return sign * y;
+}
+float rno_sigmoid_approx(float x) { return .5f + .5f * rno_tansig_approx(.5f * x); }
+static float relu(float x) { return x < 0 ? 0 : x; }
+static float activate(int act, float x) {
+  if (act == ACT_SIGMOID) return rno_sigmoid_approx(x);
+  if (act == ACT_TANH) return rno_tansig_approx(x);
+  return relu(x);
+}
+
+static void compute_dense(const dense_layer *layer, float *output, const float *input) {
+  int i, j;
+  int M = layer->nb_inputs, N = layer->nb_neurons, stride = N;
+  for (i = 0; i < N; i++) {
+    float sum = layer->bias[i];
+    for (j = 0; j < M; j++) sum += layer->weights[j * stride + i] * input[j];
+    output[i] = activate(layer->activation, WEIGHTS_SCALE * sum);
+  }
+}
+
+static void compute_gru(const gru_layer *gru, float *state, const float *input) {
+  int i, j;
+  float z[96], r[96], h[96];
+  int M = gru->nb_inputs, N = gru->nb_neurons, stride = 3 * N;
+  for (i = 0; i < N; i++) {
+    float sum = gru->bias[i];
+    for (j = 0; j < M; j++) sum += gru->input_weights[j * stride + i] * input[j];
+    for (j = 0; j < N; j++) sum += gru->recurrent_weights[j * stride + i] * state[j];
+    z[i] = rno_sigmoid_approx(WEIGHTS_SCALE * sum);
+  }
+  for (i = 0; i < N; i++) {
+    float sum = gru->bias[N + i];
+    for (j = 0; j < M; j++) sum += gru->input_weights[N + j * stride + i] * input[j];
+    for (j = 0; j < N; j++) sum += gru->recurrent_weights[N + j * stride + i] * state[j];
+    r[i] = rno_sigmoid_approx(WEIGHTS_SCALE * sum);
+  }
+  for (i = 0; i < N; i++) {
+    float sum = gru->bias[2 * N + i];
+    for (j = 0; j < M; j++) sum += gru->input_weights[2 * N + j * stride + i] * input[j];
+    for (j = 0; j < N; j++) sum += gru->recurrent_weights[2 * N + j * stride + i] * state[j] * r[j];
+    sum = activate(gru->activation, WEIGHTS_SCALE * sum);
+    h[i] = z[i] * state[i] + (1 - z[i]) * sum;
+  }
+  for (i = 0; i < N; i++) state[i] = h[i];
+}
+
+static void compute_rnn(rno_state *st, float *gains, float *vad, const float *input) {
+  int i;
+  const rno_model *m = st->model;
+  float dense_out[24];
+  float noise_input[90];
+  float denoise_input[114];
+  compute_dense(&m->input_dense, dense_out, input);
+  compute_gru(&m->vad_gru, st->vad_gru_state, dense_out);
+  compute_dense(&m->vad_output, vad, st->vad_gru_state);
+  for (i = 0; i < 24; i++) noise_input[i] = dense_out[i];
+  for (i = 0; i < 24; i++) noise_input[i + 24] = st->vad_gru_state[i];
+  for (i = 0; i < 42; i++) noise_input[i + 48] = input[i];
+  compute_gru(&m->noise_gru, st->noise_gru_state, noise_input);
+  for (i = 0; i < 24; i++) denoise_input[i] = st->vad_gru_state[i];
+  for (i = 0; i < 48; i++) denoise_input[i + 24] = st->noise_gru_state[i];
+  for (i = 0; i < 42; i++) denoise_input[i + 72] = input[i];
+  compute_gru(&m->denoise_gru, st->denoise_gru_state, denoise_input);
+  compute_dense(&m->denoise_output, gains, st->denoise_gru_state);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a15/a16: pitch_filter, frame_synthesis, process_frame (denoise.c / nnnoiseless denoise.rs)  */
+/* ------------------------------------------------------------------------------------------ */
+static void pitch_filter(cpx *X, const cpx *P, const float *Ex, const float *Ep, const float *Exp,
+                         const float *g) {
+  int i;
+  float r[NB_BANDS];
+  float rf[FREQ_SIZE];
+  float newE[NB_BANDS];
+  float norm[NB_BANDS];
+  float normf[FREQ_SIZE];
+  for (i = 0; i < NB_BANDS; i++) {
+    if (Exp[i] > g[i])
+      r[i] = 1;
+    else
+      r[i] = (Exp[i] * Exp[i]) * (1 - g[i] * g[i]) / (.001f + (g[i] * g[i]) * (1 - Exp[i] * Exp[i]));
+    r[i] = (float)sqrt(fminf(1, fmaxf(0, r[i])));
+    r[i] *= (float)sqrt(Ex[i] / (1e-8 + Ep[i]));
+  }
+  interp_band_gain(rf, r);
+  for (i = 0; i < FREQ_SIZE; i++) {
+    X[i].r += rf[i] * P[i].r;
+    X[i].i += rf[i] * P[i].i;
+  }
+  compute_band_energy(newE, X);
+  for (i = 0; i < NB_BANDS; i++) norm[i] = (float)sqrt(Ex[i] / (1e-8 + newE[i]));
+  interp_band_gain(normf, norm);
+  for (i = 0; i < FREQ_SIZE; i++) {
+    X[i].r *= normf[i];
+    X[i].i *= normf[i];
+  }
+}
+
+static void frame_synthesis(rno_state *st, float *out, const cpx *y) {
+  float x[WINDOW_SIZE];
+  int i;
+  inverse_transform(x, y);
+  apply_window(x);
+  for (i = 0; i < FRAME_SIZE; i++) out[i] = x[i] + st->synthesis_mem[i];
+  memcpy(st->synthesis_mem, &x[FRAME_SIZE], FRAME_SIZE * sizeof(float));
+}
+
+float rno_process_frame(rno_state *st, float *out, const float *in) {
+  int i;
+  cpx X[FREQ_SIZE];
+  cpx P[WINDOW_SIZE];
+  float x[FRAME_SIZE];
+  float Ex[NB_BANDS], Ep[NB_BANDS];
+  float Exp[NB_BANDS];
+  float features[NB_FEATURES];
+  float g[NB_BANDS];
+  float gf[FREQ_SIZE];
+  float vad_prob = 0;
+  int silence;
+  static const float a_hp[2] = {-1.99599f, 0.99600f};
+  static const float b_hp[2] = {-2, 1};
+  for (i = 0; i < NB_BANDS; i++) g[i] = 0;
+  biquad(x, st->mem_hp_x, in, b_hp, a_hp, FRAME_SIZE);
+  silence = compute_frame_features(st, X, P, Ex, Ep, Exp, features, x);
+  if (!silence) {
+    compute_rnn(st, g, &vad_prob, features);
+    pitch_filter(X, P, Ex, Ep, Exp, g);
+    for (i = 0; i < NB_BANDS; i++) {
+      float alpha = .6f;
+      g[i] = fmaxf(g[i], alpha * st->lastg[i]);
+      st->lastg[i] = g[i];
+    }
+    interp_band_gain(gf, g);
+    for (i = 0; i < FREQ_SIZE; i++) {
+      X[i].r *= gf[i];
+      X[i].i *= gf[i];
+    }
+  }
+  frame_synthesis(st, out, X);
+  memcpy(st->dbg.features, features, sizeof(features));
+  memcpy(st->dbg.gains, g, sizeof(g));
+  memcpy(st->dbg.Ex, Ex, sizeof(Ex));
+  memcpy(st->dbg.Ep, Ep, sizeof(Ep));
+  memcpy(st->dbg.Exp, Exp, sizeof(Exp));
+  st->dbg.vad = vad_prob;
+  st->dbg.silence = silence;
+  return vad_prob;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* batch helper (CPU baseline): pthreads over streams                                          */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const rno_model *m;
+  const float *in;
+  float *out, *vad;
+  int n_streams, n_frames, tid, n_threads;
+  long in_stride, out_stride;
+  unsigned flags;
+  float volume;
+} job;
+
+static void *worker(void *arg) {
+  job *j = (job *)arg;
+  int s, t, i;
+  float fin[FRAME_SIZE], fout[FRAME_SIZE];
+  for (s = j->tid; s < j->n_streams; s += j->n_threads) {
+    rno_state *st = rno_create(j->m);
+    const float *src = j->in + (size_t)s * j->in_stride;
+    float *dst = j->out + (size_t)s * j->out_stride;
+    for (t = 0; t < j->n_frames; t++) {
+      float v;
+      if (j->flags & 1u) {
+        /* wrapper arithmetic: audio.rs:261-273 */
+        for (i = 0; i < FRAME_SIZE; i++) fin[i] = src[(size_t)t * FRAME_SIZE + i] * 32768.0f;
+        v = rno_process_frame(st, fout, fin);
+        for (i = 0; i < FRAME_SIZE; i++) {
+          float o = fout[i] / 32768.0f;
+          o = o < -1.f ? -1.f : (o > 1.f ? 1.f : o);
+          dst[(size_t)t * FRAME_SIZE + i] = o * j->volume;
+        }
+      } else {
+        v = rno_process_frame(st, dst + (size_t)t * FRAME_SIZE, src + (size_t)t * FRAME_SIZE);
+      }
+      if (j->vad) j->vad[(size_t)s * j->n_frames + t] = v;
+    }
+    rno_destroy(st);
+  }
+  return NULL;
+}
+
+int rno_process_streams(const rno_model *m, const float *in, float *out, float *vad, int n_streams,
+                        int n_frames, long in_stride, long out_stride, unsigned flags, float volume,
+                        int n_threads) {
+  int t;
+  pthread_t *th;
+  job *jobs;
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n_streams) n_threads = n_streams > 0 ? n_streams : 1;
+  ensure_tables();
+  th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+  jobs = (job *)malloc(sizeof(job) * (size_t)n_threads);
+  for (t = 0; t < n_threads; t++) {
+    job j;
+    j.m = m;
+    j.in = in;
+    j.out = out;
+    j.vad = vad;
+    j.n_streams = n_streams;
+    j.n_frames = n_frames;
+    j.tid = t;
+    j.n_threads = n_threads;
+    j.in_stride = in_stride;
+    j.out_stride = out_stride;
+    j.flags = flags;
+    j.volume = volume;
+    jobs[t] = j;
+    pthread_create(&th[t], NULL, worker, &jobs[t]);
+  }
+  for (t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  free(th);
+  free(jobs);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a4: LinearResampler::process_sample (audio.rs:108-133)                                      */
+/* ------------------------------------------------------------------------------------------ */
+void rno_linres_init(rno_linres *r, float input_rate, float output_rate) {
+  r->input_rate = input_rate;
+  r->output_rate = output_rate;
+  r->last_sample = 0.f;
+  r->has_last = 0;
+  r->input_pos = 0.0;
+  r->next_output_pos = 0.0;
+}
+
+size_t rno_linres_process(rno_linres *r, const float *in, size_t n_in, float *out, size_t out_cap) {
+  size_t n, k = 0;
+  for (n = 0; n < n_in; n++) {
+    float sample = in[n];
+    double step;
+    if (fabsf(r->input_rate - r->output_rate) < 1.0f) { /* audio.rs:109-112 */
+      if (k < out_cap) out[k] = sample;
+      k++;
+      continue;
+    }
+    if (!r->has_last) { /* audio.rs:114-120: the first sample only primes the state */
+      r->last_sample = sample;
+      r->has_last = 1;
+      r->input_pos = 0.0;
+      r->next_output_pos = 0.0;
+      continue;
+    }
+    r->input_pos += 1.0;
+    step = (double)(r->input_rate / r->output_rate); /* f32 division, then widened (audio.rs:123) */
+    while (r->next_output_pos <= r->input_pos) {
+      float t = (float)(r->next_output_pos - (r->input_pos - 1.0));
+      float o;
+      t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+      o = r->last_sample + (sample - r->last_sample) * t;
+      if (k < out_cap) out[k] = o;
+      k++;
+      r->next_output_pos += step;
+    }
+    r->last_sample = sample;
+  }
+  return k;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a3: RnnNoiseProcessor::new + push_sample over a whole buffer (audio.rs:216-295)             */
+/* ------------------------------------------------------------------------------------------ */
+size_t rno_processor_run(const rno_model *m, float input_rate, float volume, const float *in,
+                         size_t n_in, float *out, size_t out_cap) {
+  rno_state *st = rno_create(m);
+  rno_linres rs;
+  int use_rs = fabsf(input_rate - 48000.0f) >= 1.0f; /* audio.rs:217 */
+  float frame_in[FRAME_SIZE], frame_out[FRAME_SIZE];
+  float tmp[8];
+  int fill = 0, first_frame = 1;
+  size_t n, k = 0;
+  if (volume < 0.f) volume = 0.f; /* audio.rs:236 */
+  if (volume > 1.f) volume = 1.f;
+  rno_linres_init(&rs, input_rate, 48000.0f);
+  for (n = 0; n < n_in; n++) {
+    size_t cnt, c;
+    if (use_rs) {
+      cnt = rno_linres_process(&rs, in + n, 1, tmp, 8);
+    } else {
+      tmp[0] = in[n];
+      cnt = 1;
+    }
+    for (c = 0; c < cnt; c++) {
+      frame_in[fill++] = tmp[c] * 32768.0f; /* audio.rs:264 */
+      if (fill == FRAME_SIZE) {
+        int i;
+        fill = 0;
+        rno_process_frame(st, frame_out, frame_in); /* audio.rs:268 */
+        if (first_frame) {                          /* audio.rs:275-278 */
+          first_frame = 0;
+          continue;
+        }
+        for (i = 0; i < FRAME_SIZE; i++) {
+          float o = frame_out[i] / 32768.0f;
+          o = o < -1.f ? -1.f : (o > 1.f ? 1.f : o);
+          if (k < out_cap) out[k] = o * volume; /* audio.rs:272 */
+          k++;
+        }
+      }
+    }
+  }
+  rno_destroy(st);
+  return k;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* f1: mixer + PCM16 quantiser (commands/recording.rs:260-264; recording.rs:108-110)           */
+/* ------------------------------------------------------------------------------------------ */
+void rno_mix_dual_mono_i16(const float *mic, const float *app, size_t n, int16_t *out) {
+  size_t i;
+  for (i = 0; i < n; i++) {
+    float mixed = mic[i] + (app ? app[i] : 0.f);
+    float c = mixed < -1.f ? -1.f : (mixed > 1.f ? 1.f : mixed);
+    int16_t q = (int16_t)(c * 32767.0f); /* Rust `as i16`: truncation toward zero */
+    out[2 * i] = q;
+    out[2 * i + 1] = q;
+  }
+}

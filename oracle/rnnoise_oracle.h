@@ -1,0 +1,108 @@
+/*
+ * oracle/rnnoise_oracle.h -- CPU restatement of the RNNoise denoiser that sleep3r/crispy calls
+ * through `nnnoiseless::DenoiseState` (reference call sites: src-tauri/src/audio.rs:4, :203, :229,
+ * :268; crate pin nnnoiseless 0.5.2 at Cargo.lock:2825-2838).
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (crispy_b200/, libcrispy_ns.so) never links or calls anything in oracle/.
+ *
+ * PARITY UNPINNED: the nnnoiseless crate (source + its embedded ~87.5K int8 weights) is not
+ * vendored under /root/reference, no Rust toolchain exists in this image, and the reference tree
+ * holds no golden vectors for this path.  This file restates the
+ * published algorithm of nnnoiseless 0.5.2 == xiph/rnnoise (denoise.c, pitch.c, celt_lpc.c, rnn.c)
+ * in scalar f32 with the upstream summation order.  It is anchored on (a) the reference's call
+ * sites and wrapper arithmetic (audio.rs:242-295), (b) the reference's own unit tests for the
+ * neighbouring rows (LinearResampler audio.rs:1040-1096, WavWriter recording.rs:454-504), and
+ * (c) algorithm-level known answers (window power-complementarity, DCT orthonormality, tanh
+ * table, analysis/synthesis perfect reconstruction on the silence path).
+ */
+#ifndef RNNOISE_ORACLE_H
+#define RNNOISE_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNO_FRAME_SIZE 480
+#define RNO_WINDOW_SIZE 960
+#define RNO_FREQ_SIZE 481
+#define RNO_NB_BANDS 22
+#define RNO_NB_FEATURES 42
+#define RNO_PITCH_BUF_SIZE 1728
+
+typedef struct rno_model rno_model;
+typedef struct rno_state rno_state;
+
+/* Intermediate taps of the most recent process_frame call (for stage-by-stage parity tests). */
+typedef struct rno_debug {
+  float features[RNO_NB_FEATURES];
+  float gains[RNO_NB_BANDS];
+  float Ex[RNO_NB_BANDS];
+  float Ep[RNO_NB_BANDS];
+  float Exp[RNO_NB_BANDS];
+  float pitch_gain;
+  float vad;
+  int32_t pitch_index;
+  int32_t silence;
+} rno_debug;
+
+/* ---- model (the six layers of SURVEY.md Appendix A.6) ---- */
+rno_model *rno_model_synthetic(uint64_t seed);
+rno_model *rno_model_from_bytes(const void *blob, size_t len); /* "CRNSMDL1" binary or rnnoise-nu text */
+size_t rno_model_to_bytes(const rno_model *m, void *buf, size_t cap);
+void rno_model_free(rno_model *m);
+
+/* ---- DenoiseState::new / process_frame (audio.rs:229, :268) ---- */
+rno_state *rno_create(const rno_model *m);
+void rno_destroy(rno_state *st);
+void rno_reset(rno_state *st);
+/* in/out: 480 f32 in 16-bit scale (audio.rs:264 multiplies by 32768 first). Returns VAD prob. */
+float rno_process_frame(rno_state *st, float *out, const float *in);
+void rno_get_debug(const rno_state *st, rno_debug *dbg);
+
+/* ---- batch helper: n_streams independent DenoiseStates over n_frames frames, n_threads pthreads
+ *      over streams (the CPU baseline of SURVEY.md 8d).  flags: bit0 = unit-scale wrapper
+ *      arithmetic of audio.rs:261-273 (x32768 in, /32768 + clamp + *volume out).  Output frame t
+ *      is written at out + s*out_stride + t*480 (no first-frame drop here). ---- */
+int rno_process_streams(const rno_model *m, const float *in, float *out, float *vad, int n_streams,
+                        int n_frames, long in_stride, long out_stride, unsigned flags, float volume,
+                        int n_threads);
+
+/* ---- neighbouring rows ---- */
+/* a4: LinearResampler (audio.rs:73-134). Streaming; returns number of samples emitted. */
+typedef struct rno_linres {
+  float input_rate, output_rate, last_sample;
+  int has_last;
+  double input_pos, next_output_pos;
+} rno_linres;
+void rno_linres_init(rno_linres *r, float input_rate, float output_rate);
+size_t rno_linres_process(rno_linres *r, const float *in, size_t n_in, float *out, size_t out_cap);
+
+/* a3: RnnNoiseProcessor::push_sample semantics over a whole buffer (audio.rs:242-295):
+ * optional linear resample to 48k, frame assembly, x32768, process_frame, /32768, clamp, *volume,
+ * first frame dropped.  Returns samples written to out. */
+size_t rno_processor_run(const rno_model *m, float input_rate, float volume, const float *in,
+                         size_t n_in, float *out, size_t out_cap);
+
+/* f1: dual-mono mix + PCM16 quantiser (commands/recording.rs:260-264, recording.rs:101-121).
+ * out is interleaved stereo i16, both channels = trunc(clamp(mic+app,-1,1)*32767). */
+void rno_mix_dual_mono_i16(const float *mic, const float *app, size_t n, int16_t *out_interleaved);
+
+/* tables exposed for known-answer tests */
+const float *rno_half_window(void);  /* 480 */
+const float *rno_dct_table(void);    /* 22*22 */
+const float *rno_tansig_table(void); /* 201 */
+float rno_tansig_approx(float x);
+float rno_sigmoid_approx(float x);
+/* forward (scaled 1/960) and inverse (unscaled) 960-point real transforms as used on the path */
+void rno_forward_transform(float *out_re_im_481x2, const float *in960);
+void rno_inverse_transform(float *out960, const float *in_re_im_481x2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
