@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- stream-seconds of 48 kHz audio denoised per wall-second (BASELINE.json metric).
+
+  python bench.py [--gpus N --steps K --warmup W]           our arm: libcrispy_ns.so on N B200s
+  python bench.py --impl reference [...]                    reference arm: the CPU implementation
+                                                            (oracle port of nnnoiseless 0.5.2; the
+                                                            crate itself cannot be built offline)
+
+A "step" is one pass of the whole denoise path over one batch: configs[1] of BASELINE.json --
+1,024 independent 60 s 48 kHz mono streams per GPU (6.144 M frames), synthetic speech+noise.
+  value : device-resident throughput (inputs already in HBM), CUDA events, max over ranks
+  e2e   : same metric through the public host API (BatchDenoiser.process_streams_host): pinned
+          host buffers, H2D + kernel + D2H inside the timed region
+Streams are independent, so N GPUs each take their own 1,024 streams (weak scaling, no collective
+on the data path; torch.distributed is used only for the timing barrier / max).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME = 480
+ALG_BYTES_PER_FRAME = 3844          # 480*4 read + 480*4 written + 4 (VAD)
+RNN_FLOPS_PER_FRAME = 175006        # 2 * 87,503 MAC
+ALL_FLOPS_PER_FRAME = 390000        # SURVEY.md 8(a) whole-pipeline estimate
+FP32_PEAK_TFLOPS_NOMINAL = 74.5     # 148 SM * 128 lanes * 2 * 1.965 GHz (not in MEASURED_PEAKS.json)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=1024, help="streams per GPU")
+    ap.add_argument("--seconds", type=float, default=60.0, help="audio seconds per stream per step")
+    ap.add_argument("--e2e-seconds", type=float, default=None, help="override the e2e leg's length")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-streams", type=int, default=4)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_rate(target_seconds: float = 12.0, seed_streams: int = 0):
+    """stream-seconds per wall-second of the CPU implementation on all host cores, on a bounded
+    sample of the same synthetic workload (first streams of the batch, first seconds of each)."""
+    import numpy as np
+    from crispy_b200.synth import synth_chunk
+    from oracle import pyoracle as po
+    po.build_native()
+    cores = os.cpu_count() or 1
+    model = po.Model.synthetic(0)
+    # calibrate on one second per thread, then size the sample for ~target_seconds of wall time
+    x = synth_chunk(cores, 48000, first_stream=seed_streams).numpy()
+    t0 = time.perf_counter()
+    po.process_streams(model, x, unit_scale=True, n_threads=cores, native=True)
+    dt = time.perf_counter() - t0
+    rate = cores * 1.0 / dt
+    secs = max(2, min(60, int(target_seconds * rate / (cores * 4))))
+    n_streams = cores * 4
+    x = synth_chunk(n_streams, 48000 * secs, first_stream=seed_streams).numpy()
+    t0 = time.perf_counter()
+    po.process_streams(model, x, unit_scale=True, n_threads=cores, native=True)
+    dt = time.perf_counter() - t0
+    return {"value": n_streams * secs / dt, "unit": "stream-seconds/s", "cores": cores, "kind": "port",
+            "sample": f"{n_streams} streams x {secs} s of the same synthetic workload, {cores} pthreads over "
+                      f"streams, oracle C port (-O3 -march=native) of nnnoiseless 0.5.2; {dt:.2f} s wall"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    vals, last = [], None
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_rate(target_seconds=2.0)
+    for _ in range(steps):
+        last = cpu_reference_rate(target_seconds=max(4.0, min(20.0, 60.0 / steps)))
+        vals.append(last["value"])
+    v = sum(vals) / len(vals)
+    last["value"] = v
+    line = {
+        "impl": "reference", "metric": "stream-seconds of 48 kHz audio denoised per wall-second",
+        "value": v, "unit": "stream-seconds/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.streams} independent {args.seconds:g} s 48 kHz mono streams per GPU "
+                               "(BASELINE.json configs[1]); CPU arm times a bounded sample of it",
+                   "note": "nnnoiseless itself cannot be built offline (no Rust toolchain, crate not vendored): "
+                           "this is the in-repo C restatement, all host cores"},
+        "cpu_baseline": last,
+        "e2e": {"value": v, "unit": "stream-seconds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import crispy_b200 as cb
+    from crispy_b200.synth import synth_chunk
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    n_streams = args.streams
+    n_frames = int(round(args.seconds * 100))
+    first_stream = rank * n_streams  # global stream ids: each GPU denoises its own recordings
+
+    # ---- synthetic input, resident in HBM ------------------------------------------------------
+    x = torch.empty((n_streams, n_frames * FRAME), dtype=torch.float32, device=dev)
+    chunk = 100  # frames per generation chunk
+    for f0 in range(0, n_frames, chunk):
+        nf = min(chunk, n_frames - f0)
+        x[:, f0 * FRAME:(f0 + nf) * FRAME] = synth_chunk(n_streams, nf * FRAME, first_stream=first_stream,
+                                                         start_sample=f0 * FRAME, device=dev)
+    out = torch.empty_like(x)
+    vad = torch.empty((n_streams, n_frames), dtype=torch.float32, device=dev)
+    den = cb.BatchDenoiser(n_streams, device=local)
+    info0 = den.info
+
+    def step():
+        den.reset_async()
+        den.process_streams(x, unit_scale=True, out=out, vad=vad)
+
+    # ---- parity spot-check against the oracle (rank 0, a few streams, first 2 s) ----------------
+    parity = None
+    if rank == 0 and args.parity_streams > 0:
+        from oracle import pyoracle as po
+        ns_p, nf_p = min(args.parity_streams, n_streams), min(200, n_frames)
+        step()
+        torch.cuda.synchronize(dev)
+        got = out[:ns_p, :nf_p * FRAME].cpu().numpy()
+        gv = vad[:ns_p, :nf_p].cpu().numpy()
+        ref, rv = po.process_streams(po.Model.synthetic(0), x[:ns_p, :nf_p * FRAME].cpu().numpy(), unit_scale=True)
+        err = got.astype(np.float64) - ref
+        parity = {"streams": ns_p, "frames": nf_p, "max_abs_fs": float(np.abs(err).max()),
+                  "snr_db": float(10 * np.log10((ref.astype(np.float64) ** 2).mean() / max((err ** 2).mean(), 1e-30))),
+                  "vad_max": float(np.abs(gv - rv).max())}
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = den.info["launches"]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for e0, e1 in evs:
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = evs[0][0].elapsed_time(evs[-1][1])
+    launches = den.info["launches"] - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    stream_seconds_per_step = world * n_streams * n_frames / 100.0
+    value = stream_seconds_per_step * args.steps / (total_ms_max / 1e3)
+
+    # ---- end to end through the host API --------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        e2e_frames = n_frames if args.e2e_seconds is None else int(round(args.e2e_seconds * 100))
+        need = 2 * n_streams * e2e_frames * FRAME * 4
+        avail = psutil.virtual_memory().available / max(1, world)
+        while need > 0.35 * avail and e2e_frames > 100:
+            e2e_frames //= 2
+            need = 2 * n_streams * e2e_frames * FRAME * 4
+        hx = torch.empty((n_streams, e2e_frames * FRAME), dtype=torch.float32).pin_memory()
+        hx.copy_(x[:, :e2e_frames * FRAME])
+        hout = torch.empty_like(hx).pin_memory()
+        hvad = torch.empty((n_streams, e2e_frames), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            den.reset_async()
+            den.process_streams_host(hx, unit_scale=True, out=hout, vad=hvad)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * n_streams * e2e_frames / 100.0 * args.steps / dt, "unit": "stream-seconds/s",
+               "h2d_bytes_per_step": n_streams * e2e_frames * FRAME * 4,
+               "d2h_bytes_per_step": n_streams * e2e_frames * (FRAME * 4 + 4),
+               "seconds_per_stream": e2e_frames / 100.0,
+               "api": "BatchDenoiser.process_streams_host -> crispy_ns_process_streams_host (pinned host buffers)"}
+        if rank == 0:
+            e2e["matches_device_path"] = bool(torch.equal(hout[:4], out[:4, :e2e_frames * FRAME].cpu()))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline for the dominant (only) kernel ------------------------------------------------
+    hbm_peak, peak_src = measured_peaks()
+    frames_per_launch = n_streams * n_frames
+    avg_launch_s = (sum(kernel_ms) / len(kernel_ms)) / 1e3 / max(1, launches // args.steps)
+    achieved_gbs = ALG_BYTES_PER_FRAME * frames_per_launch / avg_launch_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel": "ns_stream_kernel (analysis + recurrent + synthesis fused)",
+                "algorithmic_bytes_per_launch": ALG_BYTES_PER_FRAME * frames_per_launch,
+                "note": "the fused kernel is FP32-issue bound, not HBM bound: see roofline_fp32"}
+    tf_all = ALL_FLOPS_PER_FRAME * frames_per_launch / avg_launch_s / 1e12
+    tf_rnn = RNN_FLOPS_PER_FRAME * frames_per_launch / avg_launch_s / 1e12
+    roofline_fp32 = {"achieved_tflops_whole_pipeline": tf_all, "achieved_tflops_rnn_only": tf_rnn,
+                     "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL, "frac_whole_pipeline": tf_all / FP32_PEAK_TFLOPS_NOMINAL}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cpu_baseline = cpu_reference_rate(target_seconds=12.0)
+
+    line = {
+        "metric": "stream-seconds of 48 kHz audio denoised per wall-second",
+        "value": value, "unit": "stream-seconds/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{n_streams} independent {args.seconds:g} s 48 kHz mono streams per GPU "
+                               "(BASELINE.json configs[1]), f32 unit-scale in/out + VAD",
+                   "streams_per_gpu": n_streams, "frames_per_stream": n_frames, "parallelism": f"streams/{world}gpu",
+                   "streams_per_cta": info0["streams_per_cta"], "ctas": info0["n_ctas"],
+                   "l2": f"inputs {x.numel() * 4 / 1e9:.1f} GB + outputs per step >> 126 MB L2 (no flush needed)",
+                   "weights": "synthetic seed 0 (nnnoiseless weights are not available offline)"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_fp32": roofline_fp32, "cpu_baseline": cpu_baseline,
+        "parity_vs_oracle": parity, "wall_s_timed_region": t_wall,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

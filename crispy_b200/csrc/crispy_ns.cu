@@ -1,0 +1,710 @@
+// crispy_ns.cu -- libcrispy_ns.so: the sm_100a kernels' entry points and the C ABI declared in
+// include/crispy_ns.h.  No CPU fallback: every compute call needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/crispy_ns.h"
+#include "ns_host.h"
+#include "ns_kernel.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(S *ns::kGroupThreads, (S <= 4) ? 2 : 1)
+    ns_stream_kernel(const __grid_constant__ ns::Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ns::CtaSmem<S> &sm = *reinterpret_cast<ns::CtaSmem<S> *>(smem_raw);
+  ns::stream_kernel_body<S>(p, sm);
+}
+
+// a4/f2: out[s][n] = in[s][idx[n]-1] + (in[s][idx[n]] - in[s][idx[n]-1]) * frac[n], no FMA
+// contraction so the result is bit-identical to LinearResampler::process_sample (audio.rs:125-129).
+__global__ void ns_linear_resample_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                          const int32_t *__restrict__ idx, const float *__restrict__ frac,
+                                          long long n_out, long long in_stride, long long out_stride) {
+  const int s = blockIdx.y;
+  const float *src = in + (long long)s * in_stride;
+  float *dst = out + (long long)s * out_stride;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n_out;
+       n += (long long)gridDim.x * blockDim.x) {
+    const int i = idx[n];
+    const float last = src[i - 1], cur = src[i];
+    dst[n] = __fadd_rn(last, __fmul_rn(__fsub_rn(cur, last), frac[n]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define NS_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(CRISPY_NS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
+  } while (0)
+
+struct crispy_ns_model {
+  ns::Model m;
+};
+
+struct crispy_ns_batch {
+  int device = 0;
+  int n_streams = 0;
+  int S = 1;
+  int n_ctas = 0;
+  int64_t launches = 0;
+  int64_t frames_done = 0;
+  ns::Tables *d_tables = nullptr;
+  ns::RnnHeader *d_hdr = nullptr;
+  uint32_t *d_words = nullptr;
+  float *d_bias = nullptr;
+  float *d_state = nullptr;
+  // host-pointer path
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  cudaEvent_t e_in[2] = {nullptr, nullptr}, e_k[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
+  void *d_in[2] = {nullptr, nullptr};
+  void *d_out[2] = {nullptr, nullptr};
+  float *d_vad[2] = {nullptr, nullptr};
+  float *d_app[2] = {nullptr, nullptr};
+  size_t cap_in = 0, cap_out = 0, cap_vad = 0, cap_app = 0;
+};
+
+struct crispy_ns_state {
+  crispy_ns_batch *b = nullptr;
+  float *h_pin = nullptr;  // 480 in + 480 out + 1 vad, pinned
+  float *d_io = nullptr;   // same on device
+};
+
+// ------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------
+template <int S>
+static cudaError_t launch_S(const ns::Params &p, int n_ctas, cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<int, bool> configured;
+  const size_t smem = sizeof(ns::CtaSmem<S>);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(ns_stream_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured[dev] = true;
+    }
+  }
+  ns_stream_kernel<S><<<n_ctas, S * ns::kGroupThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_stream_kernel(int S, const ns::Params &p, int n_ctas, cudaStream_t st) {
+  switch (S) {
+    case 1: return launch_S<1>(p, n_ctas, st);
+    case 2: return launch_S<2>(p, n_ctas, st);
+    case 3: return launch_S<3>(p, n_ctas, st);
+    case 4: return launch_S<4>(p, n_ctas, st);
+    case 5: return launch_S<5>(p, n_ctas, st);
+    case 6: return launch_S<6>(p, n_ctas, st);
+    case 7: return launch_S<7>(p, n_ctas, st);
+    case 8: return launch_S<8>(p, n_ctas, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// streams per CTA: fewest scheduling rounds over the SMs, then the smaller CTA
+static int choose_streams_per_cta(int n_streams, int n_sms) {
+  const char *env = getenv("CRISPY_NS_STREAMS_PER_CTA");
+  if (env) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= ns::kMaxStreamsPerCta) return v;
+  }
+  if (n_streams <= n_sms) return 1;
+  int best = 8;
+  double best_cost = 1e30;
+  for (int S = 2; S <= 8; S++) {
+    const int ctas = (n_streams + S - 1) / S;
+    const int per_sm = (S <= 4) ? 2 : 1;  // resident CTAs per SM (shared memory bound)
+    const int rounds = (ctas + n_sms * per_sm - 1) / (n_sms * per_sm);
+    const double cost = rounds * (2.0 + S) * per_sm;
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = S;
+    }
+  }
+  return best;
+}
+
+static size_t in_elem(uint32_t flags) { return (flags & CRISPY_NS_IN_I16) ? 2 : 4; }
+static size_t out_elem(uint32_t flags) {
+  if (flags & CRISPY_NS_MIX_STEREO_I16) return 4;
+  return (flags & CRISPY_NS_OUT_I16) ? 2 : 4;
+}
+
+static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad, const float *d_app,
+                      float *d_taps, int n_frames, int64_t in_stride, int64_t out_stride,
+                      int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume, cudaStream_t st) {
+  if (!b || !d_in || !d_out || n_frames < 0) return fail(CRISPY_NS_EINVAL, "process_streams: bad argument");
+  if (n_frames == 0) return CRISPY_NS_OK;
+  ns::Params p;
+  memset(&p, 0, sizeof(p));
+  p.in = d_in;
+  p.out = d_out;
+  p.vad = d_vad;
+  p.app = d_app;
+  p.state = b->d_state;
+  p.dbg = d_taps;
+  p.tables = b->d_tables;
+  p.rnn_hdr = b->d_hdr;
+  p.rnn_words = b->d_words;
+  p.rnn_bias = b->d_bias;
+  p.in_stride = in_stride;
+  p.out_stride = out_stride;
+  p.vad_stride = vad_stride;
+  p.app_stride = app_stride;
+  p.n_streams = b->n_streams;
+  p.n_frames = n_frames;
+  p.out_frame_offset = ((flags & CRISPY_NS_DROP_FIRST_FRAME) && b->frames_done == 0) ? -1 : 0;
+  p.flags = flags & 0xFFu;
+  p.volume = volume;
+  NS_CUDA(cudaSetDevice(b->device));
+  NS_CUDA(launch_stream_kernel(b->S, p, b->n_ctas, st));
+  b->launches += 1;
+  b->frames_done += n_frames;
+  return CRISPY_NS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int crispy_ns_frame_size(void) { return ns::kFrame; }
+const char *crispy_ns_last_error(void) { return g_err.c_str(); }
+int crispy_ns_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int crispy_ns_debug_floats(void) { return ns::kDbgFloats; }
+
+int crispy_ns_model_synthetic(uint64_t seed, crispy_ns_model **out) {
+  if (!out) return fail(CRISPY_NS_EINVAL, "model_synthetic: out is null");
+  crispy_ns_model *m = new (std::nothrow) crispy_ns_model();
+  if (!m) return fail(CRISPY_NS_ENOMEM, "out of memory");
+  ns::model_synthetic(m->m, seed);
+  *out = m;
+  return CRISPY_NS_OK;
+}
+int crispy_ns_model_from_bytes(const void *blob, size_t len, crispy_ns_model **out) {
+  if (!out) return fail(CRISPY_NS_EINVAL, "model_from_bytes: out is null");
+  crispy_ns_model *m = new (std::nothrow) crispy_ns_model();
+  if (!m) return fail(CRISPY_NS_ENOMEM, "out of memory");
+  std::string err;
+  if (!ns::model_from_bytes(m->m, blob, len, err)) {
+    delete m;
+    return fail(CRISPY_NS_EMODEL, err);
+  }
+  *out = m;
+  return CRISPY_NS_OK;
+}
+int crispy_ns_model_to_bytes(const crispy_ns_model *m, void *buf, size_t cap, size_t *needed) {
+  if (!m) return fail(CRISPY_NS_EINVAL, "model_to_bytes: model is null");
+  const std::vector<uint8_t> b = ns::model_to_bytes(m->m);
+  if (needed) *needed = b.size();
+  if (buf && cap >= b.size()) memcpy(buf, b.data(), b.size());
+  return CRISPY_NS_OK;
+}
+void crispy_ns_model_destroy(crispy_ns_model *m) { delete m; }
+
+static int default_model(ns::Model &m) {
+  const char *path = getenv("CRISPY_NS_WEIGHTS");
+  if (path && *path) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(CRISPY_NS_EIO, std::string("cannot open $CRISPY_NS_WEIGHTS: ") + path);
+    std::vector<uint8_t> buf;
+    uint8_t tmp[65536];
+    size_t n;
+    while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+    fclose(f);
+    std::string err;
+    if (!ns::model_from_bytes(m, buf.data(), buf.size(), err)) return fail(CRISPY_NS_EMODEL, err);
+    return CRISPY_NS_OK;
+  }
+  ns::model_synthetic(m, 0);
+  return CRISPY_NS_OK;
+}
+
+void crispy_ns_batch_destroy(crispy_ns_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  cudaFree(b->d_tables);
+  cudaFree(b->d_hdr);
+  cudaFree(b->d_words);
+  cudaFree(b->d_bias);
+  cudaFree(b->d_state);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(b->d_in[i]);
+    cudaFree(b->d_out[i]);
+    cudaFree(b->d_vad[i]);
+    cudaFree(b->d_app[i]);
+    if (b->e_in[i]) cudaEventDestroy(b->e_in[i]);
+    if (b->e_k[i]) cudaEventDestroy(b->e_k[i]);
+    if (b->e_out[i]) cudaEventDestroy(b->e_out[i]);
+  }
+  if (b->s_in) cudaStreamDestroy(b->s_in);
+  if (b->s_k) cudaStreamDestroy(b->s_k);
+  if (b->s_out) cudaStreamDestroy(b->s_out);
+  delete b;
+}
+
+int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_streams, crispy_ns_batch **out) {
+  if (!out || n_streams < 1) return fail(CRISPY_NS_EINVAL, "batch_create: bad argument");
+  const int ndev = crispy_ns_device_count();
+  if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
+  ns::Model local;
+  const ns::Model *m = nullptr;
+  if (model) {
+    m = &model->m;
+  } else {
+    const int rc = default_model(local);
+    if (rc != CRISPY_NS_OK) return rc;
+    m = &local;
+  }
+  NS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  NS_CUDA(cudaGetDeviceProperties(&prop, device));
+  crispy_ns_batch *b = new (std::nothrow) crispy_ns_batch();
+  if (!b) return fail(CRISPY_NS_ENOMEM, "out of memory");
+  b->device = device;
+  b->n_streams = n_streams;
+  b->S = choose_streams_per_cta(n_streams, prop.multiProcessorCount);
+  b->n_ctas = (n_streams + b->S - 1) / b->S;
+  ns::PackedRnn pk;
+  ns::pack_rnn(*m, pk);
+  static ns::Tables tab;
+  static std::once_flag once;
+  std::call_once(once, [] { ns::make_tables(tab); });
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void **dst, const void *src, size_t bytes) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc(dst, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  up((void **)&b->d_tables, &tab, sizeof(tab));
+  up((void **)&b->d_hdr, &pk.hdr, sizeof(pk.hdr));
+  up((void **)&b->d_words, pk.words.data(), pk.words.size() * sizeof(uint32_t));
+  up((void **)&b->d_bias, pk.bias.data(), pk.bias.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_state, (size_t)n_streams * ns::kStateFloats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(b->d_state, 0, (size_t)n_streams * ns::kStateFloats * sizeof(float));
+  if (e != cudaSuccess) {
+    crispy_ns_batch_destroy(b);
+    return fail(CRISPY_NS_ECUDA, std::string("batch_create: ") + cudaGetErrorString(e));
+  }
+  *out = b;
+  return CRISPY_NS_OK;
+}
+
+int crispy_ns_batch_reset(crispy_ns_batch *b) {
+  if (!b) return fail(CRISPY_NS_EINVAL, "batch_reset: null handle");
+  NS_CUDA(cudaSetDevice(b->device));
+  NS_CUDA(cudaDeviceSynchronize());
+  NS_CUDA(cudaMemset(b->d_state, 0, (size_t)b->n_streams * ns::kStateFloats * sizeof(float)));
+  b->frames_done = 0;
+  return CRISPY_NS_OK;
+}
+int crispy_ns_batch_reset_async(crispy_ns_batch *b, void *cuda_stream) {
+  if (!b) return fail(CRISPY_NS_EINVAL, "batch_reset_async: null handle");
+  NS_CUDA(cudaSetDevice(b->device));
+  NS_CUDA(cudaMemsetAsync(b->d_state, 0, (size_t)b->n_streams * ns::kStateFloats * sizeof(float), (cudaStream_t)cuda_stream));
+  b->frames_done = 0;
+  return CRISPY_NS_OK;
+}
+int crispy_ns_batch_n_streams(const crispy_ns_batch *b) { return b ? b->n_streams : 0; }
+
+int crispy_ns_process_streams(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad,
+                              const float *d_app, int n_frames, int64_t in_stride, int64_t out_stride,
+                              int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume,
+                              void *cuda_stream) {
+  return run_device(b, d_in, d_out, d_vad, d_app, nullptr, n_frames, in_stride, out_stride, vad_stride,
+                    app_stride, flags, volume, (cudaStream_t)cuda_stream);
+}
+
+int crispy_ns_process_streams_debug(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad,
+                                    float *d_taps, int n_frames, int64_t in_stride, int64_t out_stride,
+                                    uint32_t flags, float volume, void *cuda_stream) {
+  return run_device(b, d_in, d_out, d_vad, nullptr, d_taps, n_frames, in_stride, out_stride, n_frames, 0,
+                    flags, volume, (cudaStream_t)cuda_stream);
+}
+
+int crispy_ns_process_streams_host(crispy_ns_batch *b, const void *h_in, void *h_out, float *h_vad,
+                                   const float *h_app, int n_frames, int64_t in_stride,
+                                   int64_t out_stride, int64_t vad_stride, int64_t app_stride,
+                                   uint32_t flags, float volume) {
+  if (!b || !h_in || !h_out || n_frames < 0) return fail(CRISPY_NS_EINVAL, "process_streams_host: bad argument");
+  if (n_frames == 0) return CRISPY_NS_OK;
+  NS_CUDA(cudaSetDevice(b->device));
+  if (!b->s_in) {
+    NS_CUDA(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
+    NS_CUDA(cudaStreamCreateWithFlags(&b->s_k, cudaStreamNonBlocking));
+    NS_CUDA(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      NS_CUDA(cudaEventCreateWithFlags(&b->e_in[i], cudaEventDisableTiming));
+      NS_CUDA(cudaEventCreateWithFlags(&b->e_k[i], cudaEventDisableTiming));
+      NS_CUDA(cudaEventCreateWithFlags(&b->e_out[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t ie = in_elem(flags), oe = out_elem(flags);
+  const int n = b->n_streams;
+  // chunk length in frames: ~64 MiB of input per chunk, at least 8 chunks when the job is long
+  long long ch = (64ll << 20) / ((long long)n * ns::kFrame * (long long)ie);
+  if (ch < 1) ch = 1;
+  if (ch > n_frames) ch = n_frames;
+  const char *env = getenv("CRISPY_NS_CHUNK_FRAMES");
+  if (env && atoi(env) > 0) ch = atoi(env) < n_frames ? atoi(env) : n_frames;
+  const size_t in_bytes = (size_t)n * ch * ns::kFrame * ie, out_bytes = (size_t)n * ch * ns::kFrame * oe;
+  const bool use_app = (flags & CRISPY_NS_MIX_STEREO_I16) && h_app;
+  // (re)allocate double buffers
+  if (b->cap_in < in_bytes) {
+    for (int i = 0; i < 2; i++) {
+      if (b->d_in[i]) cudaFree(b->d_in[i]);
+      b->d_in[i] = nullptr;
+    }
+    NS_CUDA(cudaMalloc(&b->d_in[0], in_bytes));
+    NS_CUDA(cudaMalloc(&b->d_in[1], in_bytes));
+    b->cap_in = in_bytes;
+  }
+  if (b->cap_out < out_bytes) {
+    for (int i = 0; i < 2; i++) {
+      if (b->d_out[i]) cudaFree(b->d_out[i]);
+      b->d_out[i] = nullptr;
+    }
+    NS_CUDA(cudaMalloc(&b->d_out[0], out_bytes));
+    NS_CUDA(cudaMalloc(&b->d_out[1], out_bytes));
+    b->cap_out = out_bytes;
+  }
+  const size_t vad_bytes = (size_t)n * ch * sizeof(float);
+  if (h_vad && b->cap_vad < vad_bytes) {
+    for (int i = 0; i < 2; i++) {
+      if (b->d_vad[i]) cudaFree(b->d_vad[i]);
+      b->d_vad[i] = nullptr;
+    }
+    NS_CUDA(cudaMalloc((void **)&b->d_vad[0], vad_bytes));
+    NS_CUDA(cudaMalloc((void **)&b->d_vad[1], vad_bytes));
+    b->cap_vad = vad_bytes;
+  }
+  const size_t app_bytes = (size_t)n * ch * ns::kFrame * sizeof(float);
+  if (use_app && b->cap_app < app_bytes) {
+    for (int i = 0; i < 2; i++) {
+      if (b->d_app[i]) cudaFree(b->d_app[i]);
+      b->d_app[i] = nullptr;
+    }
+    NS_CUDA(cudaMalloc((void **)&b->d_app[0], app_bytes));
+    NS_CUDA(cudaMalloc((void **)&b->d_app[1], app_bytes));
+    b->cap_app = app_bytes;
+  }
+  const bool drop = (flags & CRISPY_NS_DROP_FIRST_FRAME) && b->frames_done == 0;
+  int c = 0;
+  for (long long f0 = 0; f0 < n_frames; f0 += ch, c++) {
+    const int k = c & 1;
+    const long long nf = (f0 + ch <= n_frames) ? ch : (n_frames - f0);
+    // the in buffer k was last read by kernel c-2; the out buffer k was last drained by copy c-2
+    if (c >= 2) {
+      NS_CUDA(cudaStreamWaitEvent(b->s_in, b->e_k[k], 0));
+      NS_CUDA(cudaStreamWaitEvent(b->s_k, b->e_out[k], 0));
+    }
+    const long long row = nf * ns::kFrame;
+    NS_CUDA(cudaMemcpy2DAsync(b->d_in[k], (size_t)row * ie, (const char *)h_in + (size_t)f0 * ns::kFrame * ie,
+                              (size_t)in_stride * ie, (size_t)row * ie, n, cudaMemcpyHostToDevice, b->s_in));
+    // frames the chunk emits and where they land in the caller's output
+    const int off = (drop && f0 == 0) ? -1 : 0;
+    const long long nf_out = nf + off;
+    const long long out_f0 = f0 + ((drop && f0 > 0) ? -1 : 0);
+    if (use_app && nf_out > 0)
+      NS_CUDA(cudaMemcpy2DAsync(b->d_app[k], (size_t)row * 4, (const char *)h_app + (size_t)out_f0 * ns::kFrame * 4,
+                                (size_t)app_stride * 4, (size_t)nf_out * ns::kFrame * 4, n,
+                                cudaMemcpyHostToDevice, b->s_in));
+    NS_CUDA(cudaEventRecord(b->e_in[k], b->s_in));
+    NS_CUDA(cudaStreamWaitEvent(b->s_k, b->e_in[k], 0));
+    const int rc = run_device(b, b->d_in[k], b->d_out[k], h_vad ? b->d_vad[k] : nullptr,
+                              use_app ? b->d_app[k] : nullptr, nullptr, (int)nf, row, row, nf, row, flags,
+                              volume, b->s_k);
+    if (rc != CRISPY_NS_OK) return rc;
+    NS_CUDA(cudaEventRecord(b->e_k[k], b->s_k));
+    NS_CUDA(cudaStreamWaitEvent(b->s_out, b->e_k[k], 0));
+    if (nf_out > 0)
+      NS_CUDA(cudaMemcpy2DAsync((char *)h_out + (size_t)out_f0 * ns::kFrame * oe, (size_t)out_stride * oe,
+                                b->d_out[k], (size_t)row * oe, (size_t)nf_out * ns::kFrame * oe, n,
+                                cudaMemcpyDeviceToHost, b->s_out));
+    if (h_vad)
+      NS_CUDA(cudaMemcpy2DAsync(h_vad + f0, (size_t)vad_stride * 4, b->d_vad[k], (size_t)nf * 4, (size_t)nf * 4, n,
+                                cudaMemcpyDeviceToHost, b->s_out));
+    NS_CUDA(cudaEventRecord(b->e_out[k], b->s_out));
+  }
+  NS_CUDA(cudaStreamSynchronize(b->s_out));
+  NS_CUDA(cudaStreamSynchronize(b->s_k));
+  NS_CUDA(cudaStreamSynchronize(b->s_in));
+  return CRISPY_NS_OK;
+}
+
+size_t crispy_ns_batch_state_size(const crispy_ns_batch *b) {
+  return b ? (size_t)b->n_streams * ns::kStateFloats * sizeof(float) + 16 : 0;
+}
+int crispy_ns_batch_save_state(crispy_ns_batch *b, void *buf, size_t len) {
+  if (!b || !buf || len < crispy_ns_batch_state_size(b)) return fail(CRISPY_NS_EINVAL, "save_state: bad argument");
+  NS_CUDA(cudaSetDevice(b->device));
+  NS_CUDA(cudaDeviceSynchronize());
+  int64_t hdr[2] = {b->n_streams, b->frames_done};
+  memcpy(buf, hdr, 16);
+  NS_CUDA(cudaMemcpy((char *)buf + 16, b->d_state, len - 16 < crispy_ns_batch_state_size(b) - 16 ? len - 16 : crispy_ns_batch_state_size(b) - 16,
+                     cudaMemcpyDeviceToHost));
+  return CRISPY_NS_OK;
+}
+int crispy_ns_batch_load_state(crispy_ns_batch *b, const void *buf, size_t len) {
+  if (!b || !buf || len < crispy_ns_batch_state_size(b)) return fail(CRISPY_NS_EINVAL, "load_state: bad argument");
+  int64_t hdr[2];
+  memcpy(hdr, buf, 16);
+  if (hdr[0] != b->n_streams) return fail(CRISPY_NS_EINVAL, "load_state: stream count mismatch");
+  NS_CUDA(cudaSetDevice(b->device));
+  NS_CUDA(cudaDeviceSynchronize());
+  NS_CUDA(cudaMemcpy(b->d_state, (const char *)buf + 16, crispy_ns_batch_state_size(b) - 16, cudaMemcpyHostToDevice));
+  b->frames_done = hdr[1];
+  return CRISPY_NS_OK;
+}
+int crispy_ns_batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_ctas, int64_t *launches,
+                         int64_t *frames_done) {
+  if (!b) return fail(CRISPY_NS_EINVAL, "batch_info: null handle");
+  if (streams_per_cta) *streams_per_cta = b->S;
+  if (n_ctas) *n_ctas = b->n_ctas;
+  if (launches) *launches = b->launches;
+  if (frames_done) *frames_done = b->frames_done;
+  return CRISPY_NS_OK;
+}
+
+int crispy_ns_host_alloc(void **ptr, size_t bytes) {
+  if (!ptr) return fail(CRISPY_NS_EINVAL, "host_alloc: null");
+  NS_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return CRISPY_NS_OK;
+}
+void crispy_ns_host_free(void *ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+// ---- single stream: DenoiseState ------------------------------------------------------------------
+void crispy_ns_destroy(crispy_ns_state *st) {
+  if (!st) return;
+  if (st->b) cudaSetDevice(st->b->device);
+  if (st->h_pin) cudaFreeHost(st->h_pin);
+  if (st->d_io) cudaFree(st->d_io);
+  crispy_ns_batch_destroy(st->b);
+  delete st;
+}
+int crispy_ns_create(const crispy_ns_model *model, int device, crispy_ns_state **out) {
+  if (!out) return fail(CRISPY_NS_EINVAL, "create: out is null");
+  crispy_ns_state *st = new (std::nothrow) crispy_ns_state();
+  if (!st) return fail(CRISPY_NS_ENOMEM, "out of memory");
+  int rc = crispy_ns_batch_create(model, device, 1, &st->b);
+  if (rc != CRISPY_NS_OK) {
+    delete st;
+    return rc;
+  }
+  cudaError_t e = cudaHostAlloc((void **)&st->h_pin, 964 * sizeof(float), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_io, 964 * sizeof(float));
+  if (e != cudaSuccess) {
+    crispy_ns_destroy(st);
+    return fail(CRISPY_NS_ECUDA, std::string("create: ") + cudaGetErrorString(e));
+  }
+  *out = st;
+  return CRISPY_NS_OK;
+}
+int crispy_ns_process_frame(crispy_ns_state *st, float *out480, const float *in480, float *vad) {
+  if (!st || !out480 || !in480) return fail(CRISPY_NS_EINVAL, "process_frame: bad argument");
+  NS_CUDA(cudaSetDevice(st->b->device));
+  memcpy(st->h_pin, in480, ns::kFrame * sizeof(float));
+  NS_CUDA(cudaMemcpyAsync(st->d_io, st->h_pin, ns::kFrame * sizeof(float), cudaMemcpyHostToDevice, 0));
+  const int rc = run_device(st->b, st->d_io, st->d_io + 480, st->d_io + 960, nullptr, nullptr, 1, 480, 480, 1, 0, 0, 1.0f, 0);
+  if (rc != CRISPY_NS_OK) return rc;
+  NS_CUDA(cudaMemcpyAsync(st->h_pin + 480, st->d_io + 480, 481 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  NS_CUDA(cudaStreamSynchronize(0));
+  memcpy(out480, st->h_pin + 480, ns::kFrame * sizeof(float));
+  if (vad) *vad = st->h_pin[960];
+  return CRISPY_NS_OK;
+}
+int crispy_ns_reset(crispy_ns_state *st) {
+  if (!st) return fail(CRISPY_NS_EINVAL, "reset: null handle");
+  return crispy_ns_batch_reset(st->b);
+}
+
+// ---- a4 / f2: LinearResampler -------------------------------------------------------------------
+struct ResampleTable {
+  std::vector<int32_t> idx;
+  std::vector<float> frac;
+};
+// Replays LinearResampler::process_sample's position arithmetic (audio.rs:108-133) for n_in input
+// samples and records, for each emitted sample, the index of the "current" input and t.
+static void build_resample_table(float input_rate, float output_rate, int64_t n_in, ResampleTable &t) {
+  t.idx.clear();
+  t.frac.clear();
+  double input_pos = 0.0, next_output_pos = 0.0;
+  const double step = (double)(input_rate / output_rate);
+  for (int64_t i = 1; i < n_in; i++) {  // sample 0 only primes the state
+    input_pos += 1.0;
+    while (next_output_pos <= input_pos) {
+      float f = (float)(next_output_pos - (input_pos - 1.0));
+      f = f < 0.f ? 0.f : (f > 1.f ? 1.f : f);
+      t.idx.push_back((int32_t)i);
+      t.frac.push_back(f);
+      next_output_pos += step;
+    }
+  }
+}
+int64_t crispy_ns_linear_resample_count(float input_rate, float output_rate, int64_t n_in) {
+  if (n_in <= 0) return 0;
+  const float d = input_rate - output_rate;
+  if ((d < 0 ? -d : d) < 1.0f) return n_in;
+  ResampleTable t;
+  build_resample_table(input_rate, output_rate, n_in, t);
+  return (int64_t)t.idx.size();
+}
+int crispy_ns_linear_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
+                              int64_t in_stride, int64_t out_stride, float input_rate,
+                              float output_rate, void *cuda_stream) {
+  if (!d_in || !d_out || n_streams < 1 || n_in < 0) return fail(CRISPY_NS_EINVAL, "linear_resample: bad argument");
+  if (n_in >= (1ll << 31)) return fail(CRISPY_NS_EINVAL, "linear_resample: n_in too large for one call");
+  const int ndev = crispy_ns_device_count();
+  if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
+  NS_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const float d = input_rate - output_rate;
+  if ((d < 0 ? -d : d) < 1.0f) {  // audio.rs:109-112 passthrough
+    NS_CUDA(cudaMemcpy2DAsync(d_out, (size_t)out_stride * 4, d_in, (size_t)in_stride * 4, (size_t)n_in * 4,
+                              n_streams, cudaMemcpyDeviceToDevice, st));
+    return CRISPY_NS_OK;
+  }
+  ResampleTable t;
+  build_resample_table(input_rate, output_rate, n_in, t);
+  const int64_t n_out = (int64_t)t.idx.size();
+  if (n_out == 0) return CRISPY_NS_OK;
+  int32_t *d_idx = nullptr;
+  float *d_frac = nullptr;
+  NS_CUDA(cudaMallocAsync((void **)&d_idx, (size_t)n_out * 4, st));
+  NS_CUDA(cudaMallocAsync((void **)&d_frac, (size_t)n_out * 4, st));
+  NS_CUDA(cudaMemcpyAsync(d_idx, t.idx.data(), (size_t)n_out * 4, cudaMemcpyHostToDevice, st));
+  NS_CUDA(cudaMemcpyAsync(d_frac, t.frac.data(), (size_t)n_out * 4, cudaMemcpyHostToDevice, st));
+  NS_CUDA(cudaStreamSynchronize(st));  // the host table goes out of scope below
+  int gx = (int)((n_out + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  dim3 grid(gx, n_streams);
+  ns_linear_resample_kernel<<<grid, 256, 0, st>>>(d_in, d_out, d_idx, d_frac, n_out, in_stride, out_stride);
+  NS_CUDA(cudaGetLastError());
+  NS_CUDA(cudaFreeAsync(d_idx, st));
+  NS_CUDA(cudaFreeAsync(d_frac, st));
+  return CRISPY_NS_OK;
+}
+
+// ---- f3: WAV PCM16 -------------------------------------------------------------------------------
+static void le16(uint8_t *p, uint32_t v) {
+  p[0] = (uint8_t)v;
+  p[1] = (uint8_t)(v >> 8);
+}
+static void le32(uint8_t *p, uint32_t v) {
+  p[0] = (uint8_t)v;
+  p[1] = (uint8_t)(v >> 8);
+  p[2] = (uint8_t)(v >> 16);
+  p[3] = (uint8_t)(v >> 24);
+}
+int crispy_ns_wav_write_pcm16(const char *path, const int16_t *interleaved, int64_t n_frames, int channels,
+                              int sample_rate) {
+  if (!path || (!interleaved && n_frames > 0) || n_frames < 0 || channels < 1 || sample_rate < 1)
+    return fail(CRISPY_NS_EINVAL, "wav_write: bad argument");
+  const uint64_t data_bytes = (uint64_t)n_frames * channels * 2;
+  if (data_bytes > 0xFFFFFFFFull - 36) return fail(CRISPY_NS_EINVAL, "wav_write: too large for RIFF");
+  FILE *f = fopen(path, "wb");
+  if (!f) return fail(CRISPY_NS_EIO, std::string("wav_write: cannot open ") + path);
+  uint8_t h[44];
+  memcpy(h, "RIFF", 4);
+  le32(h + 4, (uint32_t)(36 + data_bytes));
+  memcpy(h + 8, "WAVEfmt ", 8);
+  le32(h + 16, 16);
+  le16(h + 20, 1);
+  le16(h + 22, (uint32_t)channels);
+  le32(h + 24, (uint32_t)sample_rate);
+  le32(h + 28, (uint32_t)(sample_rate * channels * 2));
+  le16(h + 32, (uint32_t)(channels * 2));
+  le16(h + 34, 16);
+  memcpy(h + 36, "data", 4);
+  le32(h + 40, (uint32_t)data_bytes);
+  bool ok = fwrite(h, 1, 44, f) == 44;
+  if (ok && data_bytes) ok = fwrite(interleaved, 1, data_bytes, f) == data_bytes;
+  ok = (fclose(f) == 0) && ok;
+  return ok ? CRISPY_NS_OK : fail(CRISPY_NS_EIO, "wav_write: short write");
+}
+int crispy_ns_wav_read_pcm16(const char *path, int16_t *interleaved, int64_t cap_samples, int64_t *n_frames,
+                             int *channels, int *sample_rate) {
+  if (!path) return fail(CRISPY_NS_EINVAL, "wav_read: bad argument");
+  FILE *f = fopen(path, "rb");
+  if (!f) return fail(CRISPY_NS_EIO, std::string("wav_read: cannot open ") + path);
+  uint8_t h[12];
+  if (fread(h, 1, 12, f) != 12 || memcmp(h, "RIFF", 4) != 0 || memcmp(h + 8, "WAVE", 4) != 0) {
+    fclose(f);
+    return fail(CRISPY_NS_EIO, "wav_read: not a RIFF/WAVE file");
+  }
+  int ch = 0, sr = 0, bits = 0, fmt = 0;
+  bool have_fmt = false;
+  for (;;) {  // chunk walk, as get_wav_duration does (commands/recording.rs:385-460)
+    uint8_t c[8];
+    if (fread(c, 1, 8, f) != 8) break;
+    const uint32_t sz = (uint32_t)c[4] | ((uint32_t)c[5] << 8) | ((uint32_t)c[6] << 16) | ((uint32_t)c[7] << 24);
+    if (memcmp(c, "fmt ", 4) == 0) {
+      uint8_t fm[16];
+      if (sz < 16 || fread(fm, 1, 16, f) != 16) break;
+      fmt = fm[0] | (fm[1] << 8);
+      ch = fm[2] | (fm[3] << 8);
+      sr = (int)((uint32_t)fm[4] | ((uint32_t)fm[5] << 8) | ((uint32_t)fm[6] << 16) | ((uint32_t)fm[7] << 24));
+      bits = fm[14] | (fm[15] << 8);
+      have_fmt = true;
+      if (sz > 16) fseek(f, (long)(sz - 16 + (sz & 1)), SEEK_CUR);
+    } else if (memcmp(c, "data", 4) == 0) {
+      if (!have_fmt || fmt != 1 || bits != 16 || ch < 1) {
+        fclose(f);
+        return fail(CRISPY_NS_EIO, "wav_read: only PCM16 is supported");
+      }
+      const int64_t total = (int64_t)sz / 2;
+      if (n_frames) *n_frames = total / ch;
+      if (channels) *channels = ch;
+      if (sample_rate) *sample_rate = sr;
+      if (interleaved) {
+        const int64_t want = total < cap_samples ? total : cap_samples;
+        if ((int64_t)fread(interleaved, 2, (size_t)want, f) != want) {
+          fclose(f);
+          return fail(CRISPY_NS_EIO, "wav_read: truncated data chunk");
+        }
+      }
+      fclose(f);
+      return CRISPY_NS_OK;
+    } else {
+      fseek(f, (long)(sz + (sz & 1)), SEEK_CUR);
+    }
+  }
+  fclose(f);
+  return fail(CRISPY_NS_EIO, "wav_read: no fmt/data chunk");
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+// ns_common.h -- constants, table and parameter structs shared by the sm_100a kernels, the host
+// library and the host-side SIMT emulation used by the CPU tests.
+//
+// Domain vocabulary follows the reference path (nnnoiseless::DenoiseState behind
+// /root/reference/src-tauri/src/audio.rs:268): frames of 480 samples at 48 kHz, a 960-sample
+// analysis window, 481 frequency bins, 22 bands, 42 features, a 1728-sample pitch buffer.
+#pragma once
+#include <stdint.h>
+
+namespace ns {
+
+constexpr int kFrame = 480;
+constexpr int kWindow = 960;
+constexpr int kFreq = 481;
+constexpr int kBands = 22;
+constexpr int kFeatures = 42;
+constexpr int kCepsMem = 8;
+constexpr int kDeltaCeps = 6;
+constexpr int kPitchMin = 60;
+constexpr int kPitchMax = 768;
+constexpr int kPitchBuf = 1728;
+constexpr int kRing = 1920;          // 4 frame slots; the 1728-sample pitch buffer lives inside it
+constexpr int kGroupThreads = 128;   // threads cooperating on one stream
+constexpr int kMaxStreamsPerCta = 8;
+
+struct alignas(8) cf {
+  float x, y;
+};
+struct alignas(16) f4 {
+  float x, y, z, w;
+};
+
+// ---- per-stream persistent state (the fields of nnnoiseless::DenoiseState), one block of
+// kStateFloats f32 per stream in HBM; loaded into shared memory for the duration of a launch.
+constexpr int kStRing = 0;                        // 1920: biquad output history (pitch_buf + analysis_mem)
+constexpr int kStSynth = kStRing + kRing;         // 480 : synthesis_mem
+constexpr int kStCeps = kStSynth + kFrame;        // 176 : cepstral_mem[8][22]
+constexpr int kStLastG = kStCeps + 176;           // 22  : lastg
+constexpr int kStHVad = kStLastG + 22;            // 24  : vad_gru_state
+constexpr int kStHNoise = kStHVad + 24;           // 48  : noise_gru_state
+constexpr int kStHDen = kStHNoise + 48;           // 96  : denoise_gru_state
+constexpr int kStHp = kStHDen + 96;               // 4   : biquad memory, two f64 (8B aligned: 2766*4 % 8 == 0)
+constexpr int kStLastGain = kStHp + 4;            // 1
+constexpr int kStLastPeriod = kStLastGain + 1;    // 1 (int bits)
+constexpr int kStMemId = kStLastPeriod + 1;       // 1 (int bits)
+constexpr int kStRingSlot = kStMemId + 1;         // 1 (int bits): slot the NEXT frame is written to
+constexpr int kStFrameCount = kStRingSlot + 1;    // 2 (int64 bits): frames processed so far
+constexpr int kStateFloats = 2784;                // padded to a multiple of 32 floats
+static_assert(kStFrameCount + 2 <= kStateFloats, "state layout overflow");
+static_assert((kStHp % 2) == 0, "f64 biquad memory must be 8-byte aligned");
+
+// ---- per-frame debug taps (optional), mirrors oracle rno_debug
+constexpr int kDbgFeatures = 0;
+constexpr int kDbgGains = 42;
+constexpr int kDbgEx = 64;
+constexpr int kDbgEp = 86;
+constexpr int kDbgExp = 108;
+constexpr int kDbgPitchGain = 130;
+constexpr int kDbgVad = 131;
+constexpr int kDbgPitchIndex = 132;  // stored as float
+constexpr int kDbgSilence = 133;
+constexpr int kDbgFloats = 136;
+
+// ---- constant tables, generated on the host in f64 and copied to shared memory per CTA
+struct Tables {
+  cf w480[480];          // exp(-2 pi i k/480)
+  cf w960[244];          // exp(-2 pi i k/960), k <= 240
+  float win[480];        // Vorbis power-complementary half window
+  float dct[484];        // dct_table[j*22+i] = cos((j+.5) i pi/22) (* sqrt(.5) for i == 0)
+  float tansig[204];     // tanh(0.04 i) rounded to 6 decimals, i <= 200
+  float bin_frac[400];   // j / band_size for bin k inside band interval bin_band[k]
+  int32_t bin_band[400]; // band interval index (0..20) of bin k
+  int32_t eband[24];     // band edges in bins (eband5ms * 4), 22 used
+  double hp_pow[5][4];   // (A^15)^(2^d), d = 0..4, row-major 2x2: biquad state transition powers
+  double hp_a[4];        // A (2x2) and
+  double hp_b[2];        // B of the biquad state recursion s' = A s + B x
+};
+
+// ---- RNN weights repacked for the kernel: per job, uint32 words hold four consecutive input rows
+// of one output column (int8 each); words are stored [k4][n_out] so a warp reads them coalesced.
+constexpr int kNumJobs = 9;
+constexpr int kMaxSegs = 4;
+enum Seg : int32_t { kSegFeat = 0, kSegDense = 1, kSegHVad = 2, kSegHNoise = 3, kSegHDen = 4, kSegRH = 5 };
+struct JobDesc {
+  int32_t n_out;
+  int32_t activation;     // 0 tanh, 1 sigmoid, 2 relu (of the layer; ZR jobs are always sigmoid)
+  int32_t w_off;          // offset (in uint32 words) into RnnWeights::words
+  int32_t b_off;          // offset into RnnWeights::bias
+  int32_t n_segs;
+  int32_t seg_id[kMaxSegs];
+  int32_t seg_k4[kMaxSegs];  // ceil(len/4)
+};
+struct RnnHeader {
+  JobDesc jobs[kNumJobs];
+  int32_t n_words;
+  int32_t n_bias;
+};
+
+// ---- launch parameters
+enum Flags : uint32_t {
+  kFlagInI16 = 1u << 0,       // input samples are int16 (16-bit scale)
+  kFlagOutI16 = 1u << 1,      // output samples are int16 (round to nearest, saturate)
+  kFlagUnitScale = 1u << 2,   // audio.rs:261-273 wrapper arithmetic: x32768 in, /32768 + clamp + *volume out
+  kFlagMixStereoI16 = 1u << 3 // f1: out = interleaved stereo i16 of clamp(dn + app) * 32767 (trunc)
+};
+
+struct Params {
+  const void *in;
+  void *out;
+  float *vad;             // [n_streams][vad_stride] or null
+  const float *app;       // f1: app audio, unit scale, same geometry as out frames; may be null
+  float *state;           // [n_streams][kStateFloats]
+  float *dbg;             // [n_streams][n_frames][kDbgFloats] or null
+  const Tables *tables;
+  const RnnHeader *rnn_hdr;
+  const uint32_t *rnn_words;
+  const float *rnn_bias;
+  const int32_t *rs_idx;  // f2: linear resampler tables (null = no resampling)
+  const float *rs_frac;
+  long long in_stride;    // samples between streams
+  long long out_stride;   // samples (mono) or stereo pairs between streams
+  long long vad_stride;
+  long long app_stride;
+  int n_streams;
+  int n_frames;
+  int out_frame_offset;   // output frame t is stored at frame slot t + out_frame_offset (skipped if < 0)
+  uint32_t flags;
+  float volume;
+};
+
+}  // namespace ns

@@ -1,0 +1,357 @@
+// ns_host.cpp -- tables, model blobs, weight repacking (host only; see ns_host.h)
+#include "ns_host.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <functional>
+
+namespace ns {
+
+static const int kEband5ms[kBands] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  10, 12,
+                                      14, 16, 20, 24, 28, 34, 40, 48, 60, 78, 100};
+
+static void mat2_mul(const long double a[4], const long double b[4], long double c[4]) {
+  long double r[4] = {a[0] * b[0] + a[1] * b[2], a[0] * b[1] + a[1] * b[3], a[2] * b[0] + a[3] * b[2],
+                      a[2] * b[1] + a[3] * b[3]};
+  memcpy(c, r, sizeof(r));
+}
+
+void make_tables(Tables &t) {
+  memset(&t, 0, sizeof(t));
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int k = 0; k < 480; k++) {
+    t.w480[k].x = (float)cosl(2 * pi * k / 480);
+    t.w480[k].y = (float)-sinl(2 * pi * k / 480);
+  }
+  for (int k = 0; k <= 240; k++) {
+    t.w960[k].x = (float)cosl(2 * pi * k / 960);
+    t.w960[k].y = (float)-sinl(2 * pi * k / 960);
+  }
+  for (int i = 0; i < kFrame; i++) {
+    const long double s = sinl(.5L * pi * (i + .5L) / kFrame);
+    t.win[i] = (float)sinl(.5L * pi * s * s);
+  }
+  for (int i = 0; i < kBands; i++)
+    for (int j = 0; j < kBands; j++) {
+      long double v = cosl((i + .5L) * j * pi / kBands);
+      if (j == 0) v *= sqrtl(.5L);
+      t.dct[i * kBands + j] = (float)v;
+    }
+  for (int i = 0; i <= 200; i++) t.tansig[i] = (float)(floor(tanh(.04 * i) * 1e6 + .5) / 1e6);
+  for (int i = 0; i < kBands; i++) t.eband[i] = kEband5ms[i] * 4;
+  for (int i = 0; i < kBands - 1; i++) {
+    const int lo = t.eband[i], n = t.eband[i + 1] - lo;
+    for (int j = 0; j < n; j++) {
+      t.bin_band[lo + j] = i;
+      t.bin_frac[lo + j] = (float)j / (float)n;
+    }
+  }
+  // biquad (a6): y = x + m0; m0' = m1 + (b0 x - a0 y); m1' = b1 x - a1 y
+  //   =>  s' = A s + B x,  A = [[-a0, 1], [-a1, 0]],  B = [b0 - a0, b1 - a1]
+  const double a0 = (double)-1.99599f, a1 = (double)0.99600f, b0 = -2.0, b1 = 1.0;
+  t.hp_a[0] = -a0;
+  t.hp_a[1] = 1.0;
+  t.hp_a[2] = -a1;
+  t.hp_a[3] = 0.0;
+  t.hp_b[0] = b0 - a0;
+  t.hp_b[1] = b1 - a1;
+  long double A[4] = {(long double)-a0, 1.0L, (long double)-a1, 0.0L};
+  long double P[4] = {1, 0, 0, 1};
+  for (int i = 0; i < 15; i++) mat2_mul(P, A, P);  // A^15
+  for (int d = 0; d < 5; d++) {
+    for (int e = 0; e < 4; e++) t.hp_pow[d][e] = (double)P[e];
+    mat2_mul(P, P, P);
+  }
+}
+
+// ---- synthetic weights: specified in DESIGN.md; an independent copy lives in the oracle ----------
+static uint64_t splitmix64(uint64_t &s) {
+  uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static void fill_q(std::vector<int8_t> &dst, size_t n, uint64_t &s, int amp, int offset) {
+  dst.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    const uint64_t u = splitmix64(s);
+    const int t = (int)(u & 0xFFFF) + (int)((u >> 16) & 0xFFFF) + (int)((u >> 32) & 0xFFFF) +
+                  (int)((u >> 48) & 0xFFFF) - 131070;
+    int w = (t * amp) / 131072 + offset;
+    if (w > 127) w = 127;
+    if (w < -127) w = -127;
+    dst[i] = (int8_t)w;
+  }
+}
+
+static void shape_default(Model &m) {
+  m.input_dense.nb_inputs = 42, m.input_dense.nb_neurons = 24, m.input_dense.activation = 0;
+  m.vad_gru.nb_inputs = 24, m.vad_gru.nb_neurons = 24, m.vad_gru.activation = 2;
+  m.vad_output.nb_inputs = 24, m.vad_output.nb_neurons = 1, m.vad_output.activation = 1;
+  m.noise_gru.nb_inputs = 90, m.noise_gru.nb_neurons = 48, m.noise_gru.activation = 2;
+  m.denoise_gru.nb_inputs = 114, m.denoise_gru.nb_neurons = 96, m.denoise_gru.activation = 2;
+  m.denoise_output.nb_inputs = 96, m.denoise_output.nb_neurons = 22, m.denoise_output.activation = 1;
+}
+
+void model_synthetic(Model &m, uint64_t seed) {
+  shape_default(m);
+  uint64_t s = seed ^ 0xC215B200C215B200ull;
+  fill_q(m.input_dense.weights, 42 * 24, s, 80, 0);
+  fill_q(m.input_dense.bias, 24, s, 80, 0);
+  fill_q(m.vad_gru.input_weights, 24 * 72, s, 250, 0);
+  fill_q(m.vad_gru.recurrent_weights, 24 * 72, s, 110, 0);
+  fill_q(m.vad_gru.bias, 72, s, 100, 0);
+  fill_q(m.vad_output.weights, 24, s, 500, 0);
+  fill_q(m.vad_output.bias, 1, s, 40, 0);
+  fill_q(m.noise_gru.input_weights, 90 * 144, s, 160, 0);
+  fill_q(m.noise_gru.recurrent_weights, 48 * 144, s, 80, 0);
+  fill_q(m.noise_gru.bias, 144, s, 100, 0);
+  fill_q(m.denoise_gru.input_weights, 114 * 288, s, 160, 0);
+  fill_q(m.denoise_gru.recurrent_weights, 96 * 288, s, 60, 0);
+  fill_q(m.denoise_gru.bias, 288, s, 100, 0);
+  fill_q(m.denoise_output.weights, 96 * 22, s, 400, 0);
+  fill_q(m.denoise_output.bias, 22, s, 120, 40);
+}
+
+// ---- blobs ---------------------------------------------------------------------------------------
+static const char kMagic[8] = {'C', 'R', 'N', 'S', 'M', 'D', 'L', '1'};
+static const char kTextMagic[] = "rnnoise-nu model file version 1";
+
+static void put_u32(std::vector<uint8_t> &b, uint32_t v) {
+  for (int i = 0; i < 4; i++) b.push_back((uint8_t)(v >> (8 * i)));
+}
+static void put_arr(std::vector<uint8_t> &b, const std::vector<int8_t> &a) {
+  b.insert(b.end(), reinterpret_cast<const uint8_t *>(a.data()), reinterpret_cast<const uint8_t *>(a.data()) + a.size());
+}
+static void put_dense(std::vector<uint8_t> &b, const DenseLayer &l) {
+  put_u32(b, 0), put_u32(b, (uint32_t)l.nb_inputs), put_u32(b, (uint32_t)l.nb_neurons), put_u32(b, (uint32_t)l.activation);
+  put_arr(b, l.weights), put_arr(b, l.bias);
+}
+static void put_gru(std::vector<uint8_t> &b, const GruLayer &l) {
+  put_u32(b, 1), put_u32(b, (uint32_t)l.nb_inputs), put_u32(b, (uint32_t)l.nb_neurons), put_u32(b, (uint32_t)l.activation);
+  put_arr(b, l.input_weights), put_arr(b, l.recurrent_weights), put_arr(b, l.bias);
+}
+std::vector<uint8_t> model_to_bytes(const Model &m) {
+  std::vector<uint8_t> b(kMagic, kMagic + 8);
+  put_dense(b, m.input_dense);
+  put_gru(b, m.vad_gru);
+  put_dense(b, m.vad_output);
+  put_gru(b, m.noise_gru);
+  put_gru(b, m.denoise_gru);
+  put_dense(b, m.denoise_output);
+  return b;
+}
+
+struct Reader {
+  const uint8_t *p;
+  size_t len, off;
+  bool ok;
+  uint32_t u32() {
+    if (off + 4 > len) {
+      ok = false;
+      return 0;
+    }
+    uint32_t v = (uint32_t)p[off] | ((uint32_t)p[off + 1] << 8) | ((uint32_t)p[off + 2] << 16) | ((uint32_t)p[off + 3] << 24);
+    off += 4;
+    return v;
+  }
+  void arr(std::vector<int8_t> &a, size_t n) {
+    if (off + n > len) {
+      ok = false;
+      return;
+    }
+    a.assign(reinterpret_cast<const int8_t *>(p + off), reinterpret_cast<const int8_t *>(p + off) + n);
+    off += n;
+  }
+};
+static void get_dense(Reader &r, DenseLayer &l) {
+  const uint32_t kind = r.u32(), in = r.u32(), out = r.u32(), act = r.u32();
+  if (!r.ok || kind != 0 || (int)in != l.nb_inputs || (int)out != l.nb_neurons || act > 2) {
+    r.ok = false;
+    return;
+  }
+  l.activation = (int)act;
+  r.arr(l.weights, (size_t)in * out);
+  r.arr(l.bias, out);
+}
+static void get_gru(Reader &r, GruLayer &l) {
+  const uint32_t kind = r.u32(), in = r.u32(), n = r.u32(), act = r.u32();
+  if (!r.ok || kind != 1 || (int)in != l.nb_inputs || (int)n != l.nb_neurons || act > 2) {
+    r.ok = false;
+    return;
+  }
+  l.activation = (int)act;
+  r.arr(l.input_weights, (size_t)in * 3 * n);
+  r.arr(l.recurrent_weights, (size_t)n * 3 * n);
+  r.arr(l.bias, (size_t)3 * n);
+}
+
+struct TextReader {
+  const char *p, *end;
+  bool ok;
+  long next() {
+    while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) p++;
+    if (p >= end) {
+      ok = false;
+      return 0;
+    }
+    char *e = nullptr;
+    const long v = strtol(p, &e, 10);
+    if (e == p) {
+      ok = false;
+      return 0;
+    }
+    p = e;
+    return v;
+  }
+  void arr(std::vector<int8_t> &a, size_t n) {
+    a.resize(n);
+    for (size_t i = 0; i < n && ok; i++) {
+      long v = next();
+      if (v > 127) v = 127;
+      if (v < -128) v = -128;
+      a[i] = (int8_t)v;
+    }
+  }
+};
+static void text_dense(TextReader &t, DenseLayer &l) {
+  const long in = t.next(), out = t.next(), act = t.next();
+  if (!t.ok || in != l.nb_inputs || out != l.nb_neurons || act < 0 || act > 2) {
+    t.ok = false;
+    return;
+  }
+  l.activation = (int)act;
+  t.arr(l.weights, (size_t)in * out);
+  t.arr(l.bias, (size_t)out);
+}
+static void text_gru(TextReader &t, GruLayer &l) {
+  const long in = t.next(), n = t.next(), act = t.next();
+  if (!t.ok || in != l.nb_inputs || n != l.nb_neurons || act < 0 || act > 2) {
+    t.ok = false;
+    return;
+  }
+  l.activation = (int)act;
+  t.arr(l.input_weights, (size_t)in * 3 * n);
+  t.arr(l.recurrent_weights, (size_t)n * 3 * n);
+  t.arr(l.bias, (size_t)3 * n);
+}
+
+bool model_from_bytes(Model &m, const void *blob, size_t len, std::string &err) {
+  shape_default(m);
+  if (!blob) {
+    err = "null model blob";
+    return false;
+  }
+  if (len >= 8 && memcmp(blob, kMagic, 8) == 0) {
+    Reader r{reinterpret_cast<const uint8_t *>(blob), len, 8, true};
+    get_dense(r, m.input_dense);
+    get_gru(r, m.vad_gru);
+    get_dense(r, m.vad_output);
+    get_gru(r, m.noise_gru);
+    get_gru(r, m.denoise_gru);
+    get_dense(r, m.denoise_output);
+    if (!r.ok || r.off != len) {
+      err = "malformed CRNSMDL1 model blob (layer shape/length mismatch)";
+      return false;
+    }
+    return true;
+  }
+  const size_t tl = sizeof(kTextMagic) - 1;
+  if (len >= tl && memcmp(blob, kTextMagic, tl) == 0) {
+    TextReader t{reinterpret_cast<const char *>(blob) + tl, reinterpret_cast<const char *>(blob) + len, true};
+    text_dense(t, m.input_dense);
+    text_gru(t, m.vad_gru);
+    text_gru(t, m.noise_gru);
+    text_gru(t, m.denoise_gru);
+    text_dense(t, m.denoise_output);
+    text_dense(t, m.vad_output);
+    if (!t.ok) {
+      err = "malformed rnnoise-nu text model";
+      return false;
+    }
+    return true;
+  }
+  err = "unknown model blob format (expected CRNSMDL1 or rnnoise-nu text)";
+  return false;
+}
+
+// ---- repacking -----------------------------------------------------------------------------------
+struct SegSrc {
+  int seg_id;
+  int len;
+  std::function<int8_t(int row, int col)> w;
+};
+
+static void add_job(PackedRnn &out, int job, int n_out, int act, const std::vector<SegSrc> &segs,
+                    const std::function<int8_t(int col)> &bias) {
+  JobDesc &jd = out.hdr.jobs[job];
+  memset(&jd, 0, sizeof(jd));
+  jd.n_out = n_out;
+  jd.activation = act;
+  jd.w_off = (int32_t)out.words.size();
+  jd.b_off = (int32_t)out.bias.size();
+  jd.n_segs = (int32_t)segs.size();
+  for (size_t s = 0; s < segs.size(); s++) {
+    const int k4 = (segs[s].len + 3) / 4;
+    jd.seg_id[s] = segs[s].seg_id;
+    jd.seg_k4[s] = k4;
+    for (int kk = 0; kk < k4; kk++)
+      for (int col = 0; col < n_out; col++) {
+        uint32_t word = 0;
+        for (int b = 0; b < 4; b++) {
+          const int row = kk * 4 + b;
+          const int8_t v = row < segs[s].len ? segs[s].w(row, col) : (int8_t)0;
+          word |= (uint32_t)(uint8_t)v << (8 * b);
+        }
+        out.words.push_back(word);
+      }
+  }
+  for (int col = 0; col < n_out; col++) out.bias.push_back((float)bias(col));
+}
+
+void pack_rnn(const Model &m, PackedRnn &out) {
+  out.words.clear();
+  out.bias.clear();
+  memset(&out.hdr, 0, sizeof(out.hdr));
+  const DenseLayer &d0 = m.input_dense, &dv = m.vad_output, &dg = m.denoise_output;
+  const GruLayer &gv = m.vad_gru, &gn = m.noise_gru, &gd = m.denoise_gru;
+  auto gi = [](const GruLayer &g, int row0, int col0) {
+    const int st = 3 * g.nb_neurons;
+    return [&g, row0, col0, st](int row, int col) { return g.input_weights[(size_t)(row0 + row) * st + col0 + col]; };
+  };
+  auto gr = [](const GruLayer &g, int col0) {
+    const int st = 3 * g.nb_neurons;
+    return [&g, col0, st](int row, int col) { return g.recurrent_weights[(size_t)row * st + col0 + col]; };
+  };
+  auto gb = [](const GruLayer &g, int col0) { return [&g, col0](int col) { return g.bias[col0 + col]; }; };
+  auto dw = [](const DenseLayer &d) {
+    return [&d](int row, int col) { return d.weights[(size_t)row * d.nb_neurons + col]; };
+  };
+  auto db = [](const DenseLayer &d) { return [&d](int col) { return d.bias[col]; }; };
+
+  add_job(out, 0, 24, d0.activation, {{kSegFeat, 42, dw(d0)}}, db(d0));
+  add_job(out, 1, 48, 1, {{kSegDense, 24, gi(gv, 0, 0)}, {kSegHVad, 24, gr(gv, 0)}}, gb(gv, 0));
+  add_job(out, 2, 24, gv.activation, {{kSegDense, 24, gi(gv, 0, 48)}, {kSegRH, 24, gr(gv, 48)}}, gb(gv, 48));
+  add_job(out, 3, 1, dv.activation, {{kSegHVad, 24, dw(dv)}}, db(dv));
+  // noise_gru input = [dense_out(24) | vad_gru_state(24) | features(42)]
+  add_job(out, 4, 96, 1,
+          {{kSegDense, 24, gi(gn, 0, 0)}, {kSegHVad, 24, gi(gn, 24, 0)}, {kSegFeat, 42, gi(gn, 48, 0)}, {kSegHNoise, 48, gr(gn, 0)}},
+          gb(gn, 0));
+  add_job(out, 5, 48, gn.activation,
+          {{kSegDense, 24, gi(gn, 0, 96)}, {kSegHVad, 24, gi(gn, 24, 96)}, {kSegFeat, 42, gi(gn, 48, 96)}, {kSegRH, 48, gr(gn, 96)}},
+          gb(gn, 96));
+  // denoise_gru input = [vad_gru_state(24) | noise_gru_state(48) | features(42)]
+  add_job(out, 6, 192, 1,
+          {{kSegHVad, 24, gi(gd, 0, 0)}, {kSegHNoise, 48, gi(gd, 24, 0)}, {kSegFeat, 42, gi(gd, 72, 0)}, {kSegHDen, 96, gr(gd, 0)}},
+          gb(gd, 0));
+  add_job(out, 7, 96, gd.activation,
+          {{kSegHVad, 24, gi(gd, 0, 192)}, {kSegHNoise, 48, gi(gd, 24, 192)}, {kSegFeat, 42, gi(gd, 72, 192)}, {kSegRH, 96, gr(gd, 192)}},
+          gb(gd, 192));
+  add_job(out, 8, 22, dg.activation, {{kSegHDen, 96, dw(dg)}}, db(dg));
+  out.hdr.n_words = (int32_t)out.words.size();
+  out.hdr.n_bias = (int32_t)out.bias.size();
+}
+
+}  // namespace ns

@@ -1,0 +1,96 @@
+// ns_simt.h -- the handful of SIMT primitives the stream kernel uses, in two spellings:
+//  * device build (nvcc, sm_100a): thin wrappers over threadIdx, named barriers (bar.sync id, n)
+//    and warp shuffles;
+//  * NS_HOST_EMU build (g++): one OS thread per CUDA thread, pthread barriers for bar.sync and a
+//    per-warp exchange buffer for shuffles.  The emulation exists so the CPU test-suite can run the
+//    kernel's exact control flow against the oracle without a GPU.  It is test plumbing: the
+//    product library never contains it.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(NS_HOST_EMU)
+
+#define NS_DEV __device__ __forceinline__
+#define NS_DEV_NOINLINE __device__ __noinline__
+
+namespace ns {
+struct Simt {
+  static NS_DEV int tid() { return (int)threadIdx.x; }
+  static NS_DEV int cta() { return (int)blockIdx.x; }
+  static NS_DEV void cta_sync() { __syncthreads(); }
+  // bar.sync with an explicit id and thread count: only the `n` threads of one stream group meet.
+  static NS_DEV void group_sync(int id, int n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+  }
+  static NS_DEV void warp_sync() { __syncwarp(); }
+  static NS_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+  static NS_DEV float shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+  static NS_DEV float shfl_up(float v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+  static NS_DEV float shfl(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  static NS_DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+  static NS_DEV int shfl_down(int v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+  static NS_DEV int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  static NS_DEV double shfl_up(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+  static NS_DEV double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+};
+}  // namespace ns
+
+#else  // ---------------------------------------------------------------- host emulation
+
+#include <pthread.h>
+#include <string.h>
+
+#define NS_DEV inline
+#define NS_DEV_NOINLINE inline
+
+namespace ns {
+struct EmuWarp {
+  pthread_barrier_t bar;
+  uint64_t xch[32];
+};
+struct EmuCta {
+  pthread_barrier_t cta_bar;
+  pthread_barrier_t group_bar[16];
+  EmuWarp *warps;
+  int cta_index;
+};
+struct EmuThread {
+  EmuCta *cta;
+  int tid;
+};
+extern thread_local EmuThread g_emu;
+
+struct Simt {
+  static int tid() { return g_emu.tid; }
+  static int cta() { return g_emu.cta->cta_index; }
+  static void cta_sync() { pthread_barrier_wait(&g_emu.cta->cta_bar); }
+  static void group_sync(int id, int) { pthread_barrier_wait(&g_emu.cta->group_bar[id]); }
+  static void warp_sync() { pthread_barrier_wait(&g_emu.cta->warps[g_emu.tid >> 5].bar); }
+  template <class T>
+  static T xchg(T v, int src_lane) {
+    EmuWarp &w = g_emu.cta->warps[g_emu.tid >> 5];
+    int lane = g_emu.tid & 31;
+    uint64_t bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    w.xch[lane] = bits;
+    pthread_barrier_wait(&w.bar);
+    T r = v;
+    if (src_lane >= 0 && src_lane < 32) memcpy(&r, &w.xch[src_lane], sizeof(T));
+    pthread_barrier_wait(&w.bar);
+    return r;
+  }
+  static int lane() { return g_emu.tid & 31; }
+  static float shfl_xor(float v, int m) { return xchg(v, lane() ^ m); }
+  static float shfl_down(float v, int d) { return xchg(v, lane() + d); }
+  static float shfl_up(float v, int d) { return xchg(v, lane() - d); }
+  static float shfl(float v, int src) { return xchg(v, src); }
+  static int shfl_xor(int v, int m) { return xchg(v, lane() ^ m); }
+  static int shfl_down(int v, int d) { return xchg(v, lane() + d); }
+  static int shfl(int v, int src) { return xchg(v, src); }
+  static double shfl_up(double v, int d) { return xchg(v, lane() - d); }
+  static double shfl(double v, int src) { return xchg(v, src); }
+};
+}  // namespace ns
+
+#endif

@@ -1,0 +1,147 @@
+/*
+ * crispy_ns.h -- C ABI of libcrispy_ns.so: a B200-native (sm_100a) drop-in for the RNNoise
+ * noise-suppression path of sleep3r/crispy.
+ *
+ * What it replaces in the reference (/root/reference/src-tauri/src/...):
+ *   - `use nnnoiseless::{DenoiseState, FRAME_SIZE}`                      audio.rs:4
+ *   - `DenoiseState::new() -> Box<DenoiseState<'static>>`               audio.rs:203, :229
+ *   - `denoise.process_frame(&mut out[..], &in[..]) -> f32 (VAD)`        audio.rs:268
+ *   - the wrapper arithmetic around it (x32768, /32768, clamp, volume,
+ *     first frame dropped)                                               audio.rs:261-278
+ *   - LinearResampler in front of it when the input is not 48 kHz        audio.rs:73-134, :217-221
+ *   - the recorder's dual-mono mix + PCM16 quantiser                     commands/recording.rs:260-264,
+ *                                                                        recording.rs:101-121
+ * plus the batched `process_streams` surface BASELINE.json's north_star adds (many independent
+ * recordings at once; streams are independent, so batches shard over GPUs with no exchange).
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative CRISPY_NS_E* code; it never throws or
+ *     unwinds across the boundary (the reference builds with panic = "abort", Cargo.toml:10-20).
+ *     crispy_ns_last_error() returns a thread-local message for the last failure.
+ *   - Plain pointers and sizes only.  `void *cuda_stream` is a cudaStream_t (NULL = the legacy
+ *     default stream).  Device-pointer entry points are asynchronous on that stream; host-pointer
+ *     entry points are synchronous.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     CRISPY_NS_ENODEV.
+ *   - A handle is not thread-safe (the reference guards its DenoiseState with a Mutex,
+ *     audio.rs:693); distinct handles are independent.
+ */
+#ifndef CRISPY_NS_H
+#define CRISPY_NS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRISPY_NS_FRAME_SIZE 480 /* nnnoiseless::FRAME_SIZE (audio.rs:4) */
+
+enum {
+  CRISPY_NS_OK = 0,
+  CRISPY_NS_EINVAL = -1, /* bad argument */
+  CRISPY_NS_ENODEV = -2, /* no CUDA device / device index out of range */
+  CRISPY_NS_ECUDA = -3,  /* CUDA runtime error (message in crispy_ns_last_error) */
+  CRISPY_NS_EMODEL = -4, /* malformed model blob */
+  CRISPY_NS_ENOMEM = -5,
+  CRISPY_NS_EIO = -6
+};
+
+/* flags for the batched calls */
+enum {
+  CRISPY_NS_IN_I16 = 1u << 0,     /* input samples are int16 (16-bit scale) instead of f32 */
+  CRISPY_NS_OUT_I16 = 1u << 1,    /* output samples are int16 (round-to-nearest, saturating) */
+  CRISPY_NS_UNIT_SCALE = 1u << 2, /* f32 I/O in [-1,1]: x32768 on load, /32768 + clamp(-1,1) + *volume
+                                     on store -- RnnNoiseProcessor::push_sample, audio.rs:261-273.
+                                     Without it f32 I/O is in 16-bit scale, as process_frame itself. */
+  CRISPY_NS_MIX_STEREO_I16 = 1u << 3, /* output = interleaved stereo PCM16 of clamp(denoised + app):
+                                         commands/recording.rs:260-264 + recording.rs:108-110 */
+  CRISPY_NS_DROP_FIRST_FRAME = 1u << 8 /* discard the very first output frame of each stream
+                                          (audio.rs:275-278); the first call then yields n_frames-1 */
+};
+
+typedef struct crispy_ns_model crispy_ns_model; /* the six RNN layers (int8 weights) */
+typedef struct crispy_ns_state crispy_ns_state; /* one stream: mirrors nnnoiseless::DenoiseState */
+typedef struct crispy_ns_batch crispy_ns_batch; /* n independent streams on one GPU */
+
+int crispy_ns_frame_size(void); /* 480 */
+const char *crispy_ns_last_error(void);
+int crispy_ns_device_count(void); /* number of CUDA devices, 0 if none */
+
+/* ---- model: nnnoiseless embeds its weights in the crate; they are not redistributable here, so
+ * the model is an explicit object.  Blob formats: "CRNSMDL1" binary or the rnnoise-nu
+ * text format.  crispy_ns_model_synthetic gives seeded int8 weights of the same topology. ---- */
+int crispy_ns_model_synthetic(uint64_t seed, crispy_ns_model **out);
+int crispy_ns_model_from_bytes(const void *blob, size_t len, crispy_ns_model **out);
+int crispy_ns_model_to_bytes(const crispy_ns_model *m, void *buf, size_t cap, size_t *needed);
+void crispy_ns_model_destroy(crispy_ns_model *m);
+
+/* ---- DenoiseState::new (audio.rs:229).  model == NULL selects the built-in default: the blob
+ * named by $CRISPY_NS_WEIGHTS if set, else synthetic seed 0. ---- */
+int crispy_ns_create(const crispy_ns_model *model, int device, crispy_ns_state **out);
+/* ---- DenoiseState::process_frame (audio.rs:268): 480 f32 in 16-bit scale in and out (host
+ * pointers); *vad receives the voice-activity probability the reference discards. ---- */
+int crispy_ns_process_frame(crispy_ns_state *st, float *out480, const float *in480, float *vad);
+int crispy_ns_reset(crispy_ns_state *st); /* fresh DenoiseState (audio.rs:955-965 model switch) */
+void crispy_ns_destroy(crispy_ns_state *st);
+
+/* ---- batched process_streams (north_star).  Geometry: stream s, frame t, sample i lives at
+ * base + s*stride + t*480 + i (strides in samples; for MIX_STEREO_I16 output, in stereo pairs).
+ * State (all of DenoiseState) persists across calls, so a long recording can be fed in chunks. ---- */
+int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_streams, crispy_ns_batch **out);
+int crispy_ns_batch_reset(crispy_ns_batch *b);
+/* same, as an asynchronous memset on cuda_stream (no device synchronisation) */
+int crispy_ns_batch_reset_async(crispy_ns_batch *b, void *cuda_stream);
+int crispy_ns_batch_n_streams(const crispy_ns_batch *b);
+/* device pointers, asynchronous on cuda_stream.  vad may be NULL.  app (unit-scale f32, same
+ * geometry as the output frames) is only read with CRISPY_NS_MIX_STEREO_I16 and may be NULL. */
+int crispy_ns_process_streams(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad,
+                              const float *d_app, int n_frames, int64_t in_stride, int64_t out_stride,
+                              int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume,
+                              void *cuda_stream);
+/* host pointers, synchronous; copies are chunked in time and overlapped with the kernel.  Pinned
+ * host memory (crispy_ns_host_alloc) is needed for the overlap to materialise. */
+int crispy_ns_process_streams_host(crispy_ns_batch *b, const void *h_in, void *h_out, float *h_vad,
+                                   const float *h_app, int n_frames, int64_t in_stride,
+                                   int64_t out_stride, int64_t vad_stride, int64_t app_stride,
+                                   uint32_t flags, float volume);
+/* test hook: as crispy_ns_process_streams, additionally writing per-frame taps
+ * ([n_streams][n_frames][crispy_ns_debug_floats()] f32, device pointer). */
+int crispy_ns_process_streams_debug(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad,
+                                    float *d_taps, int n_frames, int64_t in_stride, int64_t out_stride,
+                                    uint32_t flags, float volume, void *cuda_stream);
+int crispy_ns_debug_floats(void);
+
+/* checkpoint / resume of every stream's DenoiseState (host buffers) */
+size_t crispy_ns_batch_state_size(const crispy_ns_batch *b);
+int crispy_ns_batch_save_state(crispy_ns_batch *b, void *buf, size_t len);
+int crispy_ns_batch_load_state(crispy_ns_batch *b, const void *buf, size_t len);
+/* launch geometry + bookkeeping: streams per CTA, CTAs, kernels launched, frames processed per stream */
+int crispy_ns_batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_ctas, int64_t *launches,
+                         int64_t *frames_done);
+void crispy_ns_batch_destroy(crispy_ns_batch *b);
+
+/* pinned host memory for the host-pointer path */
+int crispy_ns_host_alloc(void **ptr, size_t bytes);
+void crispy_ns_host_free(void *ptr);
+
+/* ---- a4 / f2: LinearResampler (audio.rs:73-134), data-parallel on the device.  The output
+ * positions depend only on the two rates, so they are tabulated once on the host in f64 exactly as
+ * the reference accumulates them; the device then interpolates every (stream, sample) at once and
+ * is bit-identical to LinearResampler::process_sample.  n_out = crispy_ns_linear_resample_count. */
+int64_t crispy_ns_linear_resample_count(float input_rate, float output_rate, int64_t n_in);
+int crispy_ns_linear_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
+                              int64_t in_stride, int64_t out_stride, float input_rate,
+                              float output_rate, void *cuda_stream);
+
+/* ---- f3: RIFF/WAVE PCM16 I/O (recording.rs:83-121 writer; commands/recording.rs:385-460 parser) */
+int crispy_ns_wav_write_pcm16(const char *path, const int16_t *interleaved, int64_t n_frames,
+                              int channels, int sample_rate);
+int crispy_ns_wav_read_pcm16(const char *path, int16_t *interleaved, int64_t cap_samples,
+                             int64_t *n_frames, int *channels, int *sample_rate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRISPY_NS_H */

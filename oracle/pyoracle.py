@@ -59,15 +59,38 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+_NATIVE_PATH = os.path.join(_HERE, "librnnoise_oracle_native.so")
+
+
+def build_native() -> str:
+    """-O3 -march=native build of the same source for the CPU baseline.  Always rebuilt on the
+    machine that runs it (an -march=native object must not travel between hosts)."""
+    src = os.path.join(_HERE, "rnnoise_oracle.c")
+    subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-ffp-contract=off", "-fno-fast-math",
+                           "-std=c11", "-shared", "-o", _NATIVE_PATH, src, "-lm", "-lpthread"])
+    return _NATIVE_PATH
+
+
 _lib = None
+_libs = {}
 
 
-def lib() -> C.CDLL:
+def lib(native: bool = False) -> C.CDLL:
     global _lib
+    if native:
+        if "native" not in _libs:
+            if not os.path.exists(_NATIVE_PATH):
+                build_native()
+            _libs["native"] = _declare(C.CDLL(_NATIVE_PATH))
+        return _libs["native"]
     if _lib is not None:
         return _lib
     build()
-    L = C.CDLL(_LIB_PATH)
+    _lib = _declare(C.CDLL(_LIB_PATH))
+    return _lib
+
+
+def _declare(L: C.CDLL) -> C.CDLL:
     vp, f32p = C.c_void_p, C.POINTER(C.c_float)
     L.rno_model_synthetic.restype = vp
     L.rno_model_synthetic.argtypes = [C.c_uint64]
@@ -100,7 +123,6 @@ def lib() -> C.CDLL:
     L.rno_sigmoid_approx.argtypes = [C.c_float]
     L.rno_forward_transform.argtypes = [f32p, f32p]
     L.rno_inverse_transform.argtypes = [f32p, f32p]
-    _lib = L
     return L
 
 
@@ -175,14 +197,14 @@ class DenoiseState:
 
 
 def process_streams(model: Model, x: np.ndarray, unit_scale: bool = False, volume: float = 1.0,
-                    n_threads: int = 1):
+                    n_threads: int = 1, native: bool = False):
     """x: [n_streams, n_frames*480] f32 -> (out same shape, vad [n_streams, n_frames])."""
     x = np.ascontiguousarray(x, dtype=np.float32)
     n_streams, n = x.shape
     n_frames = n // FRAME_SIZE
     out = np.zeros_like(x)
     vad = np.zeros((n_streams, n_frames), dtype=np.float32)
-    lib().rno_process_streams(model.h, _fp(x), _fp(out), _fp(vad), n_streams, n_frames, n, n,
+    lib(native).rno_process_streams(model.h, _fp(x), _fp(out), _fp(vad), n_streams, n_frames, n, n,
                               1 if unit_scale else 0, volume, n_threads)
     return out, vad
 

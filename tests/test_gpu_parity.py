@@ -1,0 +1,197 @@
+"""GPU: the CUDA path through the C ABI (libcrispy_ns.so) against the oracle -- the parity tests proper.
+Tolerances are BASELINE.json north_star's: max abs <= 1e-3 of full scale, SNR >= 60 dB, VAD within 1e-3."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import crispy_b200 as cb  # noqa: E402
+from crispy_b200.synth import synth_chunk  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+from tests.util import TOL_MAX_ABS, assert_parity, make_signal, snr_db  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def model():
+    return cb.Model.synthetic(0)
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def test_c1_single_stream_process_frame(oracle_model):
+    """configs[0]: one 10 s clip through DenoiseState.new / process_frame (audio.rs:229, :268)."""
+    x = make_signal(1, 1000)[0]
+    st = cb.DenoiseState.new()
+    out = np.zeros_like(x)
+    vad = np.zeros(1000, np.float32)
+    for t in range(1000):
+        vad[t] = st.process_frame(out[t * 480:(t + 1) * 480], x[t * 480:(t + 1) * 480])
+    ref, rvad = po.process_streams(oracle_model, x[None, :])
+    r = assert_parity(ref[0], out, rvad[0], vad, "C1")
+    print("C1 parity", r)
+    with pytest.raises(AssertionError):
+        st.process_frame(np.zeros(479, np.float32), np.zeros(479, np.float32))
+
+
+def test_batch_matches_oracle_with_taps(oracle_model, model):
+    n_streams, n_frames = 37, 120
+    x = make_signal(n_streams, n_frames)
+    den = cb.BatchDenoiser(n_streams, model)
+    out, vad, taps = den.process_streams(_dev(x), unit_scale=False, return_taps=True)
+    out, vad, taps = out.cpu().numpy(), vad.cpu().numpy(), taps.cpu().numpy()
+    ref, rvad = po.process_streams(oracle_model, x, n_threads=8)
+    r = assert_parity(ref, out, rvad, vad, "batch")
+    print("batch parity", r)
+    flips, frames = 0, 0
+    for s in (0, 1, 17, 36):
+        _, t = po.debug_trace(oracle_model, x[s])
+        pi = np.array([a["pitch_index"] for a in t])
+        flips += int((pi != taps[s, :, 132].astype(int)).sum())
+        frames += len(pi)
+        assert np.array_equal(taps[s, :, 133].astype(int), np.array([a["silence"] for a in t]))
+        gains = np.array([a["gains"] for a in t])
+        assert np.max(np.abs(taps[s, :, 42:64] - gains)) < 5e-3
+    print(f"pitch decision flips vs oracle: {flips}/{frames}")
+    assert flips <= frames // 50
+
+
+def test_golden_fixture(oracle_model, model):
+    g = np.load(os.path.join(GOLDEN, "c1_head.npz"))
+    x = g["x_i16"][None, :]
+    den = cb.BatchDenoiser(1, model)
+    out, vad = den.process_streams(_dev(x), unit_scale=False)  # int16 in, f32 (16-bit scale) out
+    assert_parity(g["out"][None, :], out.cpu().numpy(), g["vad"][None, :], vad.cpu().numpy(), "golden")
+
+
+@pytest.mark.parametrize("spc", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_streams_per_cta_variants_agree(model, spc, monkeypatch):
+    x = _dev(make_signal(19, 30))
+    monkeypatch.setenv("CRISPY_NS_STREAMS_PER_CTA", "1")
+    a, va = cb.BatchDenoiser(19, model).process_streams(x, unit_scale=False)
+    monkeypatch.setenv("CRISPY_NS_STREAMS_PER_CTA", str(spc))
+    den = cb.BatchDenoiser(19, model)
+    assert den.info["streams_per_cta"] == spc
+    b, vb = den.process_streams(x, unit_scale=False)
+    assert torch.equal(a, b) and torch.equal(va, vb)
+
+
+def test_chunking_save_load_and_reset_are_bit_exact(model):
+    x = _dev(make_signal(11, 64))
+    den = cb.BatchDenoiser(11, model)
+    full, vfull = den.process_streams(x, unit_scale=False)
+    den.reset()
+    a, va = den.process_streams(x[:, : 20 * 480].contiguous(), unit_scale=False)
+    blob = den.save_state()
+    b, vb = den.process_streams(x[:, 20 * 480:].contiguous(), unit_scale=False)
+    assert torch.equal(torch.cat([a, b], 1), full) and torch.equal(torch.cat([va, vb], 1), vfull)
+    other = cb.BatchDenoiser(11, model)
+    other.load_state(blob)
+    assert other.frames_done == 20
+    b2, _ = other.process_streams(x[:, 20 * 480:].contiguous(), unit_scale=False)
+    assert torch.equal(b2, b)
+    # strided input (rows longer than the processed span)
+    den.reset()
+    c, _ = den.process_streams(x[:, : 20 * 480], unit_scale=False)
+    assert torch.equal(c, a)
+
+
+def test_wrapper_semantics_unit_scale_volume_drop_first(oracle_model, model):
+    xu = (make_signal(5, 40) / 32768.0).astype(np.float32)
+    den = cb.BatchDenoiser(5, model)
+    out, vad = den.process_streams(_dev(xu), unit_scale=True, volume=0.5, drop_first_frame=True)
+    assert out.shape[1] == 39 * 480
+    for s in range(5):
+        ref = po.processor_run(oracle_model, xu[s], 48000.0, 0.5)  # RnnNoiseProcessor::push_sample
+        assert len(ref) == 39 * 480
+        assert np.max(np.abs(out[s].cpu().numpy() - ref)) <= 1e-3 and snr_db(ref, out[s].cpu().numpy()) >= 60
+    # a second chunk continues without dropping anything
+    more, _ = den.process_streams(_dev(xu[:, : 4 * 480]), unit_scale=True, volume=0.5, drop_first_frame=True)
+    assert more.shape[1] == 4 * 480
+
+
+def test_host_path_equals_device_path(model, monkeypatch):
+    x = make_signal(13, 90)
+    xu = (x / 32768.0).astype(np.float32)
+    den = cb.BatchDenoiser(13, model)
+    d_out, d_vad = den.process_streams(_dev(xu), unit_scale=True)
+    monkeypatch.setenv("CRISPY_NS_CHUNK_FRAMES", "17")  # force several pipelined chunks
+    den.reset()
+    hx = torch.from_numpy(xu).pin_memory()
+    h_out, h_vad = den.process_streams_host(hx, unit_scale=True)
+    assert torch.equal(h_out, d_out.cpu()) and torch.equal(h_vad, d_vad.cpu())
+    den.reset()
+    h2, _ = den.process_streams_host(hx, unit_scale=True, drop_first_frame=True)
+    assert torch.equal(h2, d_out.cpu()[:, 480:])
+
+
+def test_i16_io_and_dual_mono_mix(oracle_model, model):
+    x = make_signal(6, 50)
+    xi = np.clip(np.rint(x), -32768, 32767).astype(np.int16)
+    den = cb.BatchDenoiser(6, model)
+    o16, _ = den.process_streams(_dev(xi), unit_scale=False, out_i16=True)
+    ref, _ = po.process_streams(oracle_model, xi.astype(np.float32))
+    assert np.max(np.abs(o16.cpu().numpy().astype(np.float64) - np.rint(ref))) <= TOL_MAX_ABS + 1
+    # f1: mic denoised + app raw -> clamp -> PCM16 dual mono (commands/recording.rs:260-264)
+    xu = (x / 32768.0).astype(np.float32)
+    app = (np.random.default_rng(5).standard_normal(xu.shape) * 0.2).astype(np.float32)
+    den.reset()
+    mix, _ = den.process_streams(_dev(xu), unit_scale=True, app=_dev(app), mix_stereo_i16=True)
+    mix = mix.cpu().numpy()
+    refd, _ = po.process_streams(oracle_model, xu, unit_scale=True)
+    for s in range(6):
+        want = po.mix_dual_mono_i16(refd[s], app[s]).reshape(-1, 2)
+        assert np.max(np.abs(mix[s].astype(np.int32) - want.astype(np.int32))) <= 34
+        assert np.array_equal(mix[s][:, 0], mix[s][:, 1])
+
+
+def test_linear_resample_is_bit_exact():  # audio.rs:73-134
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((3, 44100)).astype(np.float32)
+    for rin, rout in ((44100.0, 48000.0), (48000.0, 16000.0), (16000.0, 48000.0), (48000.0, 48000.0)):
+        y = cb.linear_resample(_dev(x), rin, rout).cpu().numpy()
+        for s in range(3):
+            assert np.array_equal(y[s], po.linear_resample(x[s], rin, rout))
+
+
+def test_config3_441k_front_end(oracle_model, model):
+    """configs[2]: 44.1 kHz input, linear resample to 48 kHz ahead of the denoiser (audio.rs:217-221)."""
+    x44 = (synth_chunk(4, 44100 * 2).numpy()).astype(np.float32)
+    y = cb.linear_resample(_dev(x44), 44100.0, 48000.0)
+    nfr = y.shape[1] // 480
+    den = cb.BatchDenoiser(4, model)
+    out, _ = den.process_streams(y[:, : nfr * 480], unit_scale=True, drop_first_frame=True)
+    for s in range(4):
+        ref = po.processor_run(oracle_model, x44[s], 44100.0, 1.0)
+        assert len(ref) == out.shape[1]
+        assert np.max(np.abs(out[s].cpu().numpy() - ref)) <= 1e-3
+
+
+def test_full_size_properties(model):
+    """configs[1] geometry (1,024 streams) on a 6 s slice: results must not depend on how streams are
+    packed into CTAs or on chunking, silence must reconstruct exactly, and nothing may be NaN."""
+    n_streams, n_frames = 1024, 600
+    x = torch.cat([synth_chunk(n_streams, 100 * 480, start_sample=f * 480, device="cuda") for f in range(0, n_frames, 100)], 1)
+    den = cb.BatchDenoiser(n_streams, model)
+    out, vad = den.process_streams(x, unit_scale=True)
+    assert torch.isfinite(out).all() and torch.isfinite(vad).all()
+    assert float(vad.min()) >= 0.0 and float(vad.max()) <= 1.0
+    den.reset()
+    o1, _ = den.process_streams(x[:, : 250 * 480], unit_scale=True)
+    o2, _ = den.process_streams(x[:, 250 * 480:], unit_scale=True)
+    assert torch.equal(torch.cat([o1, o2], 1), out)
+    os.environ["CRISPY_NS_STREAMS_PER_CTA"] = "4"
+    try:
+        alt, _ = cb.BatchDenoiser(n_streams, model).process_streams(x, unit_scale=True)
+    finally:
+        del os.environ["CRISPY_NS_STREAMS_PER_CTA"]
+    assert torch.equal(alt, out)
+    # muted stretches (stream % 16 == 3, second half of every 4 s) come out as exact zeros after ring-out
+    assert float(out[3, 350 * 480:400 * 480].abs().max()) < 1e-3

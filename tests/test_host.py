@@ -1,0 +1,92 @@
+"""CPU: host logic and the C-ABI boundary (no compute calls -- there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import crispy_b200 as cb
+from crispy_b200 import _lib, build
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    build.build()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "crispy_ns.h")).read()
+    declared = set(re.findall(r"\b(crispy_ns_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "header parse failed"
+    L = C.CDLL(_lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, f"libcrispy_ns.so lacks {missing}"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert L.crispy_ns_frame_size() == 480
+
+
+def test_library_contains_sm_100a_code():
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_models_match_oracle_generator_and_loader():
+    for seed in (0, 1, 12345):
+        assert cb.Model.synthetic(seed).to_bytes() == po.Model.synthetic(seed).to_bytes()
+    blob = cb.Model.synthetic(3).to_bytes()
+    assert cb.Model.from_bytes(blob).to_bytes() == blob
+    with pytest.raises(cb.CrispyNsError):
+        cb.Model.from_bytes(b"not a model")
+    with pytest.raises(cb.CrispyNsError):
+        cb.Model.from_bytes(blob[:-5])
+
+
+@pytest.mark.skipif(cb.device_count() > 0, reason="checks the no-device behaviour")
+def test_no_cpu_fallback_without_a_device():
+    with pytest.raises(cb.CrispyNsError, match="no CPU fallback"):
+        cb.DenoiseState.new()
+    with pytest.raises(cb.CrispyNsError, match="no CPU fallback"):
+        cb.BatchDenoiser(4)
+
+
+def test_python_linear_resampler_matches_oracle():  # audio.rs:73-134
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(2000).astype(np.float32)
+    for rin, rout in ((44100.0, 48000.0), (48000.0, 16000.0), (16000.0, 48000.0), (48000.0, 48000.0)):
+        r = cb.LinearResampler(rin, rout)
+        got = []
+        for s in x:
+            r.process_sample(s, got.append)
+        want = po.linear_resample(x, rin, rout)
+        assert np.array_equal(np.array(got, np.float32), want)
+        n = _lib.lib().crispy_ns_linear_resample_count(rin, rout, len(x))
+        assert n == len(want)
+    r = cb.LinearResampler(44100.0, 48000.0)  # audio.rs:1083-1096
+    assert abs(r.rates()[0] - 44100.0) < 0.1 and abs(r.rates()[1] - 48000.0) < 0.1
+    r.set_rates(44100.0, 16000.0)
+    assert abs(r.rates()[1] - 16000.0) < 0.1
+
+
+def test_wav_roundtrip_and_header(tmp_path):  # recording.rs:406-480
+    p = str(tmp_path / "t.wav")
+    left = np.full(100, (np.float32(0.5) * np.float32(32767.0)).astype(np.int16))
+    right = np.full(100, -left[0])
+    inter = np.stack([left, right], axis=1).astype(np.int16)
+    cb.wav_write_pcm16(p, inter, channels=2, sample_rate=48000)
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and len(raw) == 44 + 400
+    assert int.from_bytes(raw[22:24], "little") == 2 and int.from_bytes(raw[24:28], "little") == 48000
+    assert int.from_bytes(raw[34:36], "little") == 16
+    data, sr = cb.wav_read_pcm16(p)
+    assert sr == 48000 and np.array_equal(data, inter)
+    with pytest.raises(cb.CrispyNsError, match="length mismatch"):  # recording.rs:102-104
+        cb.wav_write_pcm16(p, np.zeros(3, np.int16), channels=2)
+    with pytest.raises(cb.CrispyNsError):
+        cb.wav_read_pcm16(str(tmp_path / "missing.wav"))

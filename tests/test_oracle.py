@@ -1,0 +1,174 @@
+"""CPU tests of the oracle (oracle/rnnoise_oracle.c) against algorithm-level known answers and the
+reference's own unit tests for the neighbouring rows.  PARITY UNPINNED vs nnnoiseless itself: the
+crate is not in /root/reference and no Rust toolchain exists."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_half_window_power_complementary():
+    # Vorbis window: w[i]^2 + w[479-i]^2 == 1 makes analysis+synthesis with 50% overlap an identity
+    w = np.ctypeslib.as_array(po.lib().rno_half_window(), shape=(480,)).astype(np.float64)
+    assert np.allclose(w ** 2 + w[::-1] ** 2, 1.0, atol=2e-7)
+    assert np.all(np.diff(w) >= 0) and w[0] > 0 and w[-1] <= 1.0
+
+
+def test_dct_table_orthonormal():
+    d = np.ctypeslib.as_array(po.lib().rno_dct_table(), shape=(22, 22)).astype(np.float64)
+    m = d * np.sqrt(2.0 / 22)
+    assert np.allclose(m.T @ m, np.eye(22), atol=1e-6)
+
+
+def test_tansig_table_and_approx():
+    t = np.ctypeslib.as_array(po.lib().rno_tansig_table(), shape=(201,))
+    ref = np.tanh(0.04 * np.arange(201))
+    assert np.max(np.abs(t - ref)) <= 5.7e-7  # 6 printed decimals, then f32
+    assert t[0] == 0.0 and abs(t[25] - 0.761594) < 1e-6
+    xs = np.linspace(-9, 9, 2001).astype(np.float32)
+    y = np.array([po.lib().rno_tansig_approx(float(x)) for x in xs])
+    assert np.max(np.abs(y - np.tanh(xs))) < 3e-4
+    s = np.array([po.lib().rno_sigmoid_approx(float(x)) for x in xs])
+    assert np.max(np.abs(s - 1 / (1 + np.exp(-xs.astype(np.float64))))) < 2e-4
+    assert po.lib().rno_tansig_approx(8.0) == 1.0 and po.lib().rno_tansig_approx(-8.0) == -1.0
+
+
+def test_transforms_match_numpy():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(960).astype(np.float32) * 1000
+    X = po.forward_transform(x)
+    ref = np.fft.rfft(x.astype(np.float64)) / 960  # forward carries 1/960
+    assert np.max(np.abs(X - ref)) < 2e-6 * np.max(np.abs(ref))
+    xi = po.inverse_transform(X)  # inverse carries no scaling -> identity overall
+    assert np.max(np.abs(xi - x)) < 1e-3
+
+
+def _biquad_f64(x):
+    a0, a1 = float(np.float32(-1.99599)), float(np.float32(0.99600))
+    m0 = m1 = 0.0
+    y = np.empty_like(x, dtype=np.float64)
+    for i, xi in enumerate(x.astype(np.float64)):
+        yi = xi + m0
+        m0 = m1 + (-2.0 * xi - a0 * yi)
+        m1 = xi - a1 * yi
+        y[i] = yi
+    return y
+
+
+def test_silence_path_is_delayed_highpass(oracle_model):
+    # E < 0.04: no gains, no pitch filter -> out = biquad(in) delayed by one frame (perfect
+    # reconstruction of the windowed overlap-add), VAD = 0, RNN state untouched.
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal(480 * 12) * 0.02).astype(np.float32)
+    out, vad = po.process_streams(oracle_model, x[None, :])
+    assert np.all(vad == 0.0)
+    hp = _biquad_f64(x)
+    # upstream keeps the biquad memory in f32, which drifts ~1e-4 relative against an f64 recursion
+    assert np.max(np.abs(out[0, 480:] - hp[:-480])) < 2e-5
+    assert np.max(np.abs(out[0, :480])) < 1e-6
+
+
+def test_model_blob_roundtrip_and_text_format(oracle_model):
+    blob = oracle_model.to_bytes()
+    assert blob[:8] == b"CRNSMDL1" and len(blob) == 8 + 6 * 16 + 87503
+    again = po.Model.from_bytes(blob)
+    assert again.to_bytes() == blob
+    with pytest.raises(ValueError):
+        po.Model.from_bytes(blob[:-1])
+    # rnnoise-nu text format: header, then per layer "in out act" + integers; layer order
+    # input_dense, vad_gru, noise_gru, denoise_gru, denoise_output, vad_output
+    def layers(b):
+        off, out = 8, []
+        for _ in range(6):
+            kind, i, n, act = np.frombuffer(b[off:off + 16], dtype="<u4")
+            off += 16
+            cnt = i * n + n if kind == 0 else i * 3 * n + n * 3 * n + 3 * n
+            out.append((int(i), int(n), int(act), np.frombuffer(b[off:off + cnt], dtype=np.int8)))
+            off += int(cnt)
+        return out
+    L = layers(blob)
+    order = [0, 1, 3, 4, 5, 2]
+    text = "rnnoise-nu model file version 1\n"
+    for k in order:
+        i, n, act, w = L[k]
+        text += f"{i} {n} {act}\n" + " ".join(str(int(v)) for v in w) + "\n"
+    assert po.Model.from_bytes(text.encode()).to_bytes() == blob
+
+
+def test_chunk_invariance_and_determinism(oracle_model):
+    from tests.util import make_signal
+    x = make_signal(1, 40)[0]
+    full, _ = po.process_streams(oracle_model, x[None, :])
+    st = po.DenoiseState(oracle_model)
+    pieces = [st.process_frame(x[t * 480:(t + 1) * 480])[0] for t in range(40)]
+    assert np.array_equal(np.concatenate(pieces), full[0])
+
+
+# ---- the reference's own unit tests for the neighbouring rows ------------------------------------
+def test_linear_resampler_same_rate_passthrough():  # audio.rs:1041-1053
+    x = (np.arange(10) * 0.1).astype(np.float32)
+    y = po.linear_resample(x, 48000.0, 48000.0)
+    assert len(y) == 10 and np.max(np.abs(y - x)) < 0.001
+
+
+def test_linear_resampler_downsample_produces_fewer():  # audio.rs:1055-1067
+    y = po.linear_resample(np.full(300, 0.5, np.float32), 48000.0, 16000.0)
+    assert 80 < len(y) < 120
+
+
+def test_linear_resampler_upsample_produces_more():  # audio.rs:1069-1081
+    y = po.linear_resample(np.full(100, 0.5, np.float32), 16000.0, 48000.0)
+    assert 250 < len(y) < 350
+    assert np.all(y == 0.5)
+
+
+def test_linear_resampler_441_to_48_is_linear_interp():
+    n = 4410
+    x = np.sin(2 * np.pi * 440 * np.arange(n) / 44100).astype(np.float32)
+    y = po.linear_resample(x, 44100.0, 48000.0)
+    step = float(np.float32(44100.0) / np.float32(48000.0))
+    pos = np.arange(len(y)) * step
+    ref = np.interp(pos, np.arange(n), x.astype(np.float64))
+    assert abs(len(y) - round((n - 1) / step)) <= 1
+    assert np.max(np.abs(y - ref)) < 1e-5
+
+
+def test_mixer_quantiser_matches_wavwriter_tests():  # recording.rs:454-504
+    q = po.mix_dual_mono_i16(np.array([0.5, -0.5], np.float32), None)
+    assert q.tolist() == [16383, 16383, -16383, -16383]  # (0.5*32767) as i16 truncates
+    q = po.mix_dual_mono_i16(np.array([2.0, -3.0, 1.5, -1.5], np.float32), None)
+    assert q.tolist() == [32767, 32767, -32767, -32767, 32767, 32767, -32767, -32767]
+    q = po.mix_dual_mono_i16(np.array([0.25], np.float32), np.array([0.5], np.float32))
+    assert q.tolist() == [int(0.75 * 32767)] * 2  # commands/recording.rs:260-264: mixed to both channels
+
+
+def test_processor_wrapper_matches_manual_composition(oracle_model):  # audio.rs:242-295
+    from tests.util import make_signal
+    x = make_signal(1, 12)[0] / 32768.0
+    y = po.processor_run(oracle_model, x.astype(np.float32), 48000.0, 0.8)
+    assert len(y) == 11 * 480  # first frame dropped (audio.rs:275-278)
+    ref, _ = po.process_streams(oracle_model, x[None, :].astype(np.float32), unit_scale=True, volume=0.8)
+    assert np.array_equal(y, ref[0, 480:])
+    # 44.1 kHz input goes through LinearResampler first (audio.rs:217-221)
+    x44 = x[: 441 * 10].astype(np.float32)
+    y44 = po.processor_run(oracle_model, x44, 44100.0, 1.0)
+    rs = po.linear_resample(x44, 44100.0, 48000.0)
+    nfr = len(rs) // 480
+    ref, _ = po.process_streams(oracle_model, rs[None, : nfr * 480], unit_scale=True)
+    assert np.array_equal(y44, ref[0, 480:])
+
+
+def test_golden_regression(oracle_model):
+    """The committed fixture was produced by this oracle (tests/golden/make_golden.py); it pins the
+    oracle against accidental change -- it is NOT an nnnoiseless output (none can be made here)."""
+    g = np.load(os.path.join(GOLDEN, "c1_head.npz"))
+    x = g["x_i16"].astype(np.float32)
+    out, vad = po.process_streams(oracle_model, x[None, :])
+    assert np.array_equal(out[0], g["out"])
+    assert np.array_equal(vad[0], g["vad"])
+    _, taps = po.debug_trace(oracle_model, x)
+    assert [t["pitch_index"] for t in taps] == g["pitch_index"].tolist()
