@@ -340,7 +340,7 @@ def run_b200(args):
         "config": {"workload": f"{n_streams} independent {args.seconds:g} s 48 kHz mono streams per GPU "
                                "(BASELINE.json configs[1]), f32 unit-scale in/out + VAD",
                    "streams_per_gpu": n_streams, "frames_per_stream": n_frames, "parallelism": f"streams/{world}gpu",
-                   "streams_per_cta": info0["streams_per_cta"], "ctas": info0["n_ctas"],
+                   "chunk_frames": info0["chunk_frames"], "rnn_streams_per_cta": info0["rnn_streams_per_cta"],
                    "l2": f"inputs {x.numel() * 4 / 1e9:.1f} GB + outputs per step >> 126 MB L2 (no flush needed)",
                    "weights": "synthetic seed 0 (nnnoiseless weights are not available offline)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcrispy_ns.so")
 SOURCES = ["crispy_ns.cu", "ns_host.cpp"]
-HEADERS = ["ns_common.h", "ns_simt.h", "ns_kernel.cuh", "ns_host.h", os.path.join("..", "..", "include", "crispy_ns.h")]
+HEADERS = ["ns_common.h", "ns_simt.h", "ns_pipe.cuh", "ns_host.h", os.path.join("..", "..", "include", "crispy_ns.h")]
 
 
 def nvcc_path() -> str:
@@ -33,6 +33,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [
         nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        # exactness contract (ns_pipe.cuh): no implicit a*b+c contraction; fmaf() is spelled out where allowed
+        "-fmad=false",
         "-Xcompiler", "-fPIC", "-shared", "-o", LIB,
     ] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:

@@ -12,17 +12,38 @@
 
 #include "../../include/crispy_ns.h"
 #include "ns_host.h"
-#include "ns_kernel.cuh"
+#include "ns_pipe.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// kernels
+// kernels (bodies in ns_pipe.cuh)
 // ------------------------------------------------------------------------------------------------
-template <int S>
-__global__ void __launch_bounds__(S *ns::kGroupThreads, (S <= 4) ? 2 : 1)
-    ns_stream_kernel(const __grid_constant__ ns::Params p) {
+constexpr int kPitchRun = 8;        // frames of one stream per pitch CTA
+constexpr int kPitchThreads = 320;  // 37 lag-quads x 8 frames = 296 lanes in the coarse search
+constexpr int kRnnThreads = 256;
+constexpr int kScanWarps = 4;
+
+__global__ void __launch_bounds__(32) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
+  __shared__ ns::HpSmem sm;
+  ns::highpass_body(p, sm);
+}
+__global__ void __launch_bounds__(kPitchThreads) ns_pitch_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ns::CtaSmem<S> &sm = *reinterpret_cast<ns::CtaSmem<S> *>(smem_raw);
-  ns::stream_kernel_body<S>(p, sm);
+  ns::pitch_body<kPitchRun, kPitchThreads>(p, *reinterpret_cast<ns::PitchSmem<kPitchRun> *>(smem_raw));
+}
+__global__ void __launch_bounds__(32 * kScanWarps) ns_pitchscan_kernel(const __grid_constant__ ns::Params p) {
+  ns::pitchscan_body(p, kScanWarps);
+}
+__global__ void __launch_bounds__(ns::kGroupThreads) ns_spectrum_kernel(const __grid_constant__ ns::Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ns::spectrum_body(p, *reinterpret_cast<ns::SpecSmem *>(smem_raw));
+}
+__global__ void __launch_bounds__(kRnnThreads) ns_rnn_kernel(const __grid_constant__ ns::Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ns::rnn_body<kRnnThreads>(p, *reinterpret_cast<ns::RnnSmem *>(smem_raw));
+}
+__global__ void __launch_bounds__(ns::kGroupThreads) ns_synthesis_kernel(const __grid_constant__ ns::Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ns::synthesis_body(p, *reinterpret_cast<ns::SpecSmem *>(smem_raw));
 }
 
 // a4/f2: out[s][n] = in[s][idx[n]-1] + (in[s][idx[n]] - in[s][idx[n]-1]) * frac[n], no FMA
@@ -60,18 +81,29 @@ struct crispy_ns_model {
   ns::Model m;
 };
 
+constexpr int kSlots = 3;  // workspace slots: chunk c uses slot c % kSlots
+
 struct crispy_ns_batch {
   int device = 0;
   int n_streams = 0;
-  int S = 1;
-  int n_ctas = 0;
+  int n_sms = 148;
+  int chunk_cap = 0;  // frames per chunk
   int64_t launches = 0;
   int64_t frames_done = 0;
+  int64_t chunks_done = 0;
   ns::Tables *d_tables = nullptr;
   ns::RnnHeader *d_hdr = nullptr;
   uint32_t *d_words = nullptr;
   float *d_bias = nullptr;
   float *d_state = nullptr;
+  // pipeline workspace + plumbing
+  float *d_hp[kSlots] = {nullptr, nullptr, nullptr};
+  uint32_t *d_tab[kSlots] = {nullptr, nullptr, nullptr};
+  float *d_rec[kSlots] = {nullptr, nullptr, nullptr};
+  cudaStream_t s_hp = nullptr, s_an = nullptr, s_syn = nullptr;
+  cudaEvent_t e_start = nullptr;
+  cudaEvent_t e_hp[kSlots] = {nullptr, nullptr, nullptr}, e_an[kSlots] = {nullptr, nullptr, nullptr},
+              e_syn[kSlots] = {nullptr, nullptr, nullptr};
   // host-pointer path
   cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
   cudaEvent_t e_in[2] = {nullptr, nullptr}, e_k[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
@@ -89,62 +121,22 @@ struct crispy_ns_state {
 };
 
 // ------------------------------------------------------------------------------------------------
-// launch
+// launch: one call = a train of chunks, each chunk = six kernels on three internal streams
+//   s_hp : K0                (serial biquad; runs ahead of the rest)
+//   s_an : K1, K2, K3        (pitch analysis, pitch decision scan, spectra)
+//   s_syn: K4, K5            (recurrent core, synthesis)
+// Events chain hp -> an -> syn per workspace slot, so chunk c+1's analysis overlaps chunk c's
+// recurrent core and synthesis.
 // ------------------------------------------------------------------------------------------------
-template <int S>
-static cudaError_t launch_S(const ns::Params &p, int n_ctas, cudaStream_t st) {
-  static std::mutex mu;
-  static std::map<int, bool> configured;
-  const size_t smem = sizeof(ns::CtaSmem<S>);
-  int dev = 0;
-  cudaGetDevice(&dev);
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (!configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(ns_stream_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured[dev] = true;
-    }
-  }
-  ns_stream_kernel<S><<<n_ctas, S * ns::kGroupThreads, smem, st>>>(p);
-  return cudaGetLastError();
-}
-
-static cudaError_t launch_stream_kernel(int S, const ns::Params &p, int n_ctas, cudaStream_t st) {
-  switch (S) {
-    case 1: return launch_S<1>(p, n_ctas, st);
-    case 2: return launch_S<2>(p, n_ctas, st);
-    case 3: return launch_S<3>(p, n_ctas, st);
-    case 4: return launch_S<4>(p, n_ctas, st);
-    case 5: return launch_S<5>(p, n_ctas, st);
-    case 6: return launch_S<6>(p, n_ctas, st);
-    case 7: return launch_S<7>(p, n_ctas, st);
-    case 8: return launch_S<8>(p, n_ctas, st);
-    default: return cudaErrorInvalidValue;
-  }
-}
-
-// streams per CTA: fewest scheduling rounds over the SMs, then the smaller CTA
-static int choose_streams_per_cta(int n_streams, int n_sms) {
-  const char *env = getenv("CRISPY_NS_STREAMS_PER_CTA");
-  if (env) {
-    const int v = atoi(env);
-    if (v >= 1 && v <= ns::kMaxStreamsPerCta) return v;
-  }
-  if (n_streams <= n_sms) return 1;
-  int best = 8;
-  double best_cost = 1e30;
-  for (int S = 2; S <= 8; S++) {
-    const int ctas = (n_streams + S - 1) / S;
-    const int per_sm = (S <= 4) ? 2 : 1;  // resident CTAs per SM (shared memory bound)
-    const int rounds = (ctas + n_sms * per_sm - 1) / (n_sms * per_sm);
-    const double cost = rounds * (2.0 + S) * per_sm;
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = S;
-    }
-  }
-  return best;
+static int default_chunk_cap(int n_streams) {
+  const char *env = getenv("CRISPY_NS_CHUNK_FRAMES");
+  if (env && atoi(env) > 0) return atoi(env) > 4096 ? 4096 : atoi(env);
+  const long long per_frame = (long long)n_streams * (ns::kFrame * 4 + ns::kTabWords * 4 + ns::kRecFloats * 4);
+  long long cap = (64ll << 20) / per_frame;
+  cap = (cap / kPitchRun) * kPitchRun;
+  if (cap < kPitchRun) cap = kPitchRun;
+  if (cap > 256) cap = 256;
+  return (int)cap;
 }
 
 static size_t in_elem(uint32_t flags) { return (flags & CRISPY_NS_IN_I16) ? 2 : 4; }
@@ -153,19 +145,38 @@ static size_t out_elem(uint32_t flags) {
   return (flags & CRISPY_NS_OUT_I16) ? 2 : 4;
 }
 
+static cudaError_t configure_kernels(int dev) {
+  static std::mutex mu;
+  static std::map<int, bool> configured;
+  std::lock_guard<std::mutex> lk(mu);
+  if (configured[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(ns_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ns::PitchSmem<kPitchRun>));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(ns_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::SpecSmem));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(ns_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::SpecSmem));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(ns_rnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::RnnSmem));
+  if (e == cudaSuccess) configured[dev] = true;
+  return e;
+}
+
 static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad, const float *d_app,
                       float *d_taps, int n_frames, int64_t in_stride, int64_t out_stride,
                       int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume, cudaStream_t st) {
   if (!b || !d_in || !d_out || n_frames < 0) return fail(CRISPY_NS_EINVAL, "process_streams: bad argument");
   if (n_frames == 0) return CRISPY_NS_OK;
+  NS_CUDA(cudaSetDevice(b->device));
+  NS_CUDA(configure_kernels(b->device));
   ns::Params p;
   memset(&p, 0, sizeof(p));
   p.in = d_in;
   p.out = d_out;
   p.vad = d_vad;
   p.app = d_app;
-  p.state = b->d_state;
   p.dbg = d_taps;
+  p.state = b->d_state;
   p.tables = b->d_tables;
   p.rnn_hdr = b->d_hdr;
   p.rnn_words = b->d_words;
@@ -174,14 +185,51 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
   p.out_stride = out_stride;
   p.vad_stride = vad_stride;
   p.app_stride = app_stride;
+  p.hp_stride = ns::kHist + (long long)b->chunk_cap * ns::kFrame;
   p.n_streams = b->n_streams;
-  p.n_frames = n_frames;
+  p.n_frames_call = n_frames;
+  p.chunk_cap = b->chunk_cap;
   p.out_frame_offset = ((flags & CRISPY_NS_DROP_FIRST_FRAME) && b->frames_done == 0) ? -1 : 0;
   p.flags = flags & 0xFFu;
   p.volume = volume;
-  NS_CUDA(cudaSetDevice(b->device));
-  NS_CUDA(launch_stream_kernel(b->S, p, b->n_ctas, st));
-  b->launches += 1;
+  const int n = b->n_streams;
+  NS_CUDA(cudaEventRecord(b->e_start, st));
+  NS_CUDA(cudaStreamWaitEvent(b->s_hp, b->e_start, 0));
+  int last_slot = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += b->chunk_cap) {
+    const int slot = (int)(b->chunks_done % kSlots);
+    const int nf = (n_frames - f0) < b->chunk_cap ? (n_frames - f0) : b->chunk_cap;
+    p.frame0 = f0;
+    p.n_frames = nf;
+    p.hp = b->d_hp[slot];
+    p.tab = b->d_tab[slot];
+    p.rec = b->d_rec[slot];
+    if (b->chunks_done >= kSlots) NS_CUDA(cudaStreamWaitEvent(b->s_hp, b->e_syn[slot], 0));
+    ns_highpass_kernel<<<(n + 31) / 32, 32, 0, b->s_hp>>>(p);
+    NS_CUDA(cudaGetLastError());
+    NS_CUDA(cudaEventRecord(b->e_hp[slot], b->s_hp));
+    NS_CUDA(cudaStreamWaitEvent(b->s_an, b->e_hp[slot], 0));
+    const int runs = (nf + kPitchRun - 1) / kPitchRun;
+    ns_pitch_kernel<<<n * runs, kPitchThreads, sizeof(ns::PitchSmem<kPitchRun>), b->s_an>>>(p);
+    NS_CUDA(cudaGetLastError());
+    ns_pitchscan_kernel<<<(n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, b->s_an>>>(p);
+    NS_CUDA(cudaGetLastError());
+    long long spec_ctas = (long long)n * nf;
+    if (spec_ctas > (long long)b->n_sms * 8) spec_ctas = (long long)b->n_sms * 8;
+    ns_spectrum_kernel<<<(int)spec_ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), b->s_an>>>(p);
+    NS_CUDA(cudaGetLastError());
+    NS_CUDA(cudaEventRecord(b->e_an[slot], b->s_an));
+    NS_CUDA(cudaStreamWaitEvent(b->s_syn, b->e_an[slot], 0));
+    ns_rnn_kernel<<<(n + ns::kRnnStreams - 1) / ns::kRnnStreams, kRnnThreads, sizeof(ns::RnnSmem), b->s_syn>>>(p);
+    NS_CUDA(cudaGetLastError());
+    ns_synthesis_kernel<<<n, ns::kGroupThreads, sizeof(ns::SpecSmem), b->s_syn>>>(p);
+    NS_CUDA(cudaGetLastError());
+    NS_CUDA(cudaEventRecord(b->e_syn[slot], b->s_syn));
+    b->launches += 6;
+    b->chunks_done += 1;
+    last_slot = slot;
+  }
+  NS_CUDA(cudaStreamWaitEvent(st, b->e_syn[last_slot], 0));
   b->frames_done += n_frames;
   return CRISPY_NS_OK;
 }
@@ -258,6 +306,18 @@ void crispy_ns_batch_destroy(crispy_ns_batch *b) {
   cudaFree(b->d_words);
   cudaFree(b->d_bias);
   cudaFree(b->d_state);
+  for (int i = 0; i < kSlots; i++) {
+    cudaFree(b->d_hp[i]);
+    cudaFree(b->d_tab[i]);
+    cudaFree(b->d_rec[i]);
+    if (b->e_hp[i]) cudaEventDestroy(b->e_hp[i]);
+    if (b->e_an[i]) cudaEventDestroy(b->e_an[i]);
+    if (b->e_syn[i]) cudaEventDestroy(b->e_syn[i]);
+  }
+  if (b->e_start) cudaEventDestroy(b->e_start);
+  if (b->s_hp) cudaStreamDestroy(b->s_hp);
+  if (b->s_an) cudaStreamDestroy(b->s_an);
+  if (b->s_syn) cudaStreamDestroy(b->s_syn);
   for (int i = 0; i < 2; i++) {
     cudaFree(b->d_in[i]);
     cudaFree(b->d_out[i]);
@@ -294,8 +354,8 @@ int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_strea
   if (!b) return fail(CRISPY_NS_ENOMEM, "out of memory");
   b->device = device;
   b->n_streams = n_streams;
-  b->S = choose_streams_per_cta(n_streams, prop.multiProcessorCount);
-  b->n_ctas = (n_streams + b->S - 1) / b->S;
+  b->n_sms = prop.multiProcessorCount;
+  b->chunk_cap = default_chunk_cap(n_streams);
   ns::PackedRnn pk;
   ns::pack_rnn(*m, pk);
   static ns::Tables tab;
@@ -313,6 +373,19 @@ int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_strea
   up((void **)&b->d_bias, pk.bias.data(), pk.bias.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_state, (size_t)n_streams * ns::kStateFloats * sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(b->d_state, 0, (size_t)n_streams * ns::kStateFloats * sizeof(float));
+  for (int i = 0; i < kSlots && e == cudaSuccess; i++) {
+    const size_t nf = (size_t)n_streams * b->chunk_cap;
+    e = cudaMalloc((void **)&b->d_hp[i], (size_t)n_streams * (ns::kHist + (size_t)b->chunk_cap * ns::kFrame) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_tab[i], nf * ns::kTabWords * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_rec[i], nf * ns::kRecFloats * sizeof(float));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_hp[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_an[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_syn[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_start, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->s_hp, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->s_an, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->s_syn, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     crispy_ns_batch_destroy(b);
     return fail(CRISPY_NS_ECUDA, std::string("batch_create: ") + cudaGetErrorString(e));
@@ -376,7 +449,7 @@ int crispy_ns_process_streams_host(crispy_ns_batch *b, const void *h_in, void *h
   long long ch = (64ll << 20) / ((long long)n * ns::kFrame * (long long)ie);
   if (ch < 1) ch = 1;
   if (ch > n_frames) ch = n_frames;
-  const char *env = getenv("CRISPY_NS_CHUNK_FRAMES");
+  const char *env = getenv("CRISPY_NS_HOST_CHUNK_FRAMES");
   if (env && atoi(env) > 0) ch = atoi(env) < n_frames ? atoi(env) : n_frames;
   const size_t in_bytes = (size_t)n * ch * ns::kFrame * ie, out_bytes = (size_t)n * ch * ns::kFrame * oe;
   const bool use_app = (flags & CRISPY_NS_MIX_STEREO_I16) && h_app;
@@ -488,10 +561,10 @@ int crispy_ns_batch_load_state(crispy_ns_batch *b, const void *buf, size_t len) 
   return CRISPY_NS_OK;
 }
 int crispy_ns_batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_ctas, int64_t *launches,
-                         int64_t *frames_done) {
+                         int64_t *frames_done) {  // (rnn_streams_per_cta, chunk_frames, ...)
   if (!b) return fail(CRISPY_NS_EINVAL, "batch_info: null handle");
-  if (streams_per_cta) *streams_per_cta = b->S;
-  if (n_ctas) *n_ctas = b->n_ctas;
+  if (streams_per_cta) *streams_per_cta = ns::kRnnStreams;
+  if (n_ctas) *n_ctas = b->chunk_cap;
   if (launches) *launches = b->launches;
   if (frames_done) *frames_done = b->frames_done;
   return CRISPY_NS_OK;

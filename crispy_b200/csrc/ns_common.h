@@ -19,9 +19,32 @@ constexpr int kDeltaCeps = 6;
 constexpr int kPitchMin = 60;
 constexpr int kPitchMax = 768;
 constexpr int kPitchBuf = 1728;
-constexpr int kRing = 1920;          // 4 frame slots; the 1728-sample pitch buffer lives inside it
-constexpr int kGroupThreads = 128;   // threads cooperating on one stream
-constexpr int kMaxStreamsPerCta = 8;
+constexpr int kGroupThreads = 128;   // threads cooperating on one frame's spectra
+
+// ---- pipeline geometry ---------------------------------------------------------------------------
+// A call is cut into chunks of <= chunk_cap frames.  Per chunk and stream the engine keeps, in HBM:
+//   hp  : the high-passed signal, kHist samples of history + chunk*480 new samples (f32)
+//   tab : per frame, the pitch candidate table remove_doubling's serial decision walks (kTabWords)
+//   rec : per frame, the small record passed between phases (kRecFloats)
+constexpr int kHist = 1440;          // >= 1248 (pitch_buf history) and a multiple of 480
+constexpr int kLpLen = 864;          // pitch_buf downsampled by 2
+constexpr int kLpStride = 872;       // padded row of the per-frame downsampled buffers
+constexpr int kMaxK = 15;            // remove_doubling examines T0/k for k = 1..15
+constexpr int kTabWords = 48;
+//   word 0      : T0 | n_k << 16      (n_k = candidates present, k = 1..n_k)
+//   word 1      : unused
+//   word 2+3(k-1): T_k | pitch_index_k << 16 ; g_k (f32 bits) ; pitch_gain_k (f32 bits)
+constexpr int kRecFloats = 128;
+constexpr int kRecPitchIndex = 0;    // int bits
+constexpr int kRecSilence = 1;       // int bits
+constexpr int kRecPitchGain = 2;
+constexpr int kRecVad = 3;
+constexpr int kRecExp = 4;           // 22 (normalised band correlation)
+constexpr int kRecCeps = 26;         // 22 (DCT of log band energy, offsets applied)
+constexpr int kRecTail = 48;         // 7: features[34..40]
+constexpr int kRecGRaw = 56;         // 22: band gains as the RNN emits them (the pitch filter uses these)
+constexpr int kRecG = 78;            // 22: band gains after the 0.6*lastg smoothing
+static_assert(kRecG + kBands <= kRecFloats, "record overflow");
 
 struct alignas(8) cf {
   float x, y;
@@ -31,23 +54,21 @@ struct alignas(16) f4 {
 };
 
 // ---- per-stream persistent state (the fields of nnnoiseless::DenoiseState), one block of
-// kStateFloats f32 per stream in HBM; loaded into shared memory for the duration of a launch.
-constexpr int kStRing = 0;                        // 1920: biquad output history (pitch_buf + analysis_mem)
-constexpr int kStSynth = kStRing + kRing;         // 480 : synthesis_mem
+// kStateFloats f32 per stream in HBM.
+constexpr int kStHist = 0;                        // 1440: last high-passed samples (pitch_buf + analysis_mem)
+constexpr int kStSynth = kStHist + kHist;         // 480 : synthesis_mem
 constexpr int kStCeps = kStSynth + kFrame;        // 176 : cepstral_mem[8][22]
 constexpr int kStLastG = kStCeps + 176;           // 22  : lastg
 constexpr int kStHVad = kStLastG + 22;            // 24  : vad_gru_state
 constexpr int kStHNoise = kStHVad + 24;           // 48  : noise_gru_state
 constexpr int kStHDen = kStHNoise + 48;           // 96  : denoise_gru_state
-constexpr int kStHp = kStHDen + 96;               // 4   : biquad memory, two f64 (8B aligned: 2766*4 % 8 == 0)
-constexpr int kStLastGain = kStHp + 4;            // 1
+constexpr int kStHp = kStHDen + 96;               // 2   : mem_hp_x (f32, as upstream)
+constexpr int kStLastGain = kStHp + 2;            // 1
 constexpr int kStLastPeriod = kStLastGain + 1;    // 1 (int bits)
 constexpr int kStMemId = kStLastPeriod + 1;       // 1 (int bits)
-constexpr int kStRingSlot = kStMemId + 1;         // 1 (int bits): slot the NEXT frame is written to
-constexpr int kStFrameCount = kStRingSlot + 1;    // 2 (int64 bits): frames processed so far
-constexpr int kStateFloats = 2784;                // padded to a multiple of 32 floats
-static_assert(kStFrameCount + 2 <= kStateFloats, "state layout overflow");
-static_assert((kStHp % 2) == 0, "f64 biquad memory must be 8-byte aligned");
+constexpr int kStFrameCount = kStMemId + 1;       // 1 (int bits, informational)
+constexpr int kStateFloats = 2304;                // padded to a multiple of 32 floats
+static_assert(kStFrameCount + 1 <= kStateFloats, "state layout overflow");
 
 // ---- per-frame debug taps (optional), mirrors oracle rno_debug
 constexpr int kDbgFeatures = 0;
@@ -71,9 +92,6 @@ struct Tables {
   float bin_frac[400];   // j / band_size for bin k inside band interval bin_band[k]
   int32_t bin_band[400]; // band interval index (0..20) of bin k
   int32_t eband[24];     // band edges in bins (eband5ms * 4), 22 used
-  double hp_pow[5][4];   // (A^15)^(2^d), d = 0..4, row-major 2x2: biquad state transition powers
-  double hp_a[4];        // A (2x2) and
-  double hp_b[2];        // B of the biquad state recursion s' = A s + B x
 };
 
 // ---- RNN weights repacked for the kernel: per job, uint32 words hold four consecutive input rows
@@ -104,25 +122,32 @@ enum Flags : uint32_t {
   kFlagMixStereoI16 = 1u << 3 // f1: out = interleaved stereo i16 of clamp(dn + app) * 32767 (trunc)
 };
 
+// One chunk of one call.  Caller pointers (in/out/vad/app/dbg) address frame 0 of the CALL; the
+// kernels add frame0.  Engine pointers (hp/tab/rec) address the chunk's workspace slot.
 struct Params {
   const void *in;
   void *out;
   float *vad;             // [n_streams][vad_stride] or null
   const float *app;       // f1: app audio, unit scale, same geometry as out frames; may be null
+  float *dbg;             // [n_streams][n_frames_call][kDbgFloats] or null
   float *state;           // [n_streams][kStateFloats]
-  float *dbg;             // [n_streams][n_frames][kDbgFloats] or null
+  float *hp;              // [n_streams][hp_stride]
+  uint32_t *tab;          // [n_streams][chunk_cap][kTabWords]
+  float *rec;             // [n_streams][chunk_cap][kRecFloats]
   const Tables *tables;
   const RnnHeader *rnn_hdr;
   const uint32_t *rnn_words;
   const float *rnn_bias;
-  const int32_t *rs_idx;  // f2: linear resampler tables (null = no resampling)
-  const float *rs_frac;
   long long in_stride;    // samples between streams
   long long out_stride;   // samples (mono) or stereo pairs between streams
   long long vad_stride;
   long long app_stride;
+  long long hp_stride;    // kHist + chunk_cap*480
   int n_streams;
-  int n_frames;
+  int n_frames;           // frames in this chunk
+  int frame0;             // index of the chunk's first frame within the call
+  int n_frames_call;      // frames in the whole call (debug tap geometry)
+  int chunk_cap;
   int out_frame_offset;   // output frame t is stored at frame slot t + out_frame_offset (skipped if < 0)
   uint32_t flags;
   float volume;

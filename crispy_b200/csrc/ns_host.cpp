@@ -12,12 +12,6 @@ namespace ns {
 static const int kEband5ms[kBands] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  10, 12,
                                       14, 16, 20, 24, 28, 34, 40, 48, 60, 78, 100};
 
-static void mat2_mul(const long double a[4], const long double b[4], long double c[4]) {
-  long double r[4] = {a[0] * b[0] + a[1] * b[2], a[0] * b[1] + a[1] * b[3], a[2] * b[0] + a[3] * b[2],
-                      a[2] * b[1] + a[3] * b[3]};
-  memcpy(c, r, sizeof(r));
-}
-
 void make_tables(Tables &t) {
   memset(&t, 0, sizeof(t));
   const long double pi = 3.14159265358979323846264338327950288L;
@@ -47,22 +41,6 @@ void make_tables(Tables &t) {
       t.bin_band[lo + j] = i;
       t.bin_frac[lo + j] = (float)j / (float)n;
     }
-  }
-  // biquad (a6): y = x + m0; m0' = m1 + (b0 x - a0 y); m1' = b1 x - a1 y
-  //   =>  s' = A s + B x,  A = [[-a0, 1], [-a1, 0]],  B = [b0 - a0, b1 - a1]
-  const double a0 = (double)-1.99599f, a1 = (double)0.99600f, b0 = -2.0, b1 = 1.0;
-  t.hp_a[0] = -a0;
-  t.hp_a[1] = 1.0;
-  t.hp_a[2] = -a1;
-  t.hp_a[3] = 0.0;
-  t.hp_b[0] = b0 - a0;
-  t.hp_b[1] = b1 - a1;
-  long double A[4] = {(long double)-a0, 1.0L, (long double)-a1, 0.0L};
-  long double P[4] = {1, 0, 0, 1};
-  for (int i = 0; i < 15; i++) mat2_mul(P, A, P);  // A^15
-  for (int d = 0; d < 5; d++) {
-    for (int e = 0; e < 4; e++) t.hp_pow[d][e] = (double)P[e];
-    mat2_mul(P, P, P);
   }
 }
 

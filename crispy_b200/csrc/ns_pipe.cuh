@@ -1,0 +1,1253 @@
+// ns_pipe.cuh -- device code of the phased RNNoise pipeline behind
+// nnnoiseless::DenoiseState::process_frame (/root/reference/src-tauri/src/audio.rs:268).
+//
+// One chunk of frames of every stream goes through six kernels (DESIGN.md has the data flow):
+//   K0 highpass   serial-in-time biquad, one lane per stream (f32 state, f64 intermediates: a6)
+//   K1 pitch      parallel over (stream, run of R frames): pitch_downsample, pitch_search and every
+//                 inner product remove_doubling can ask for (a9-a11) -> candidate table
+//   K2 pitchscan  serial-in-time threshold walk of remove_doubling (last_period / last_gain), one
+//                 warp per stream, one lane per candidate
+//   K3 spectrum   parallel over (stream, frame): windowed rFFT960 of the frame and of the
+//                 pitch-lagged window, band energies / correlation, cepstrum (a7, a8, a12, a13)
+//   K4 rnn        serial-in-time recurrent core, 8 streams per CTA: cepstral ring + delta features,
+//                 dense -> 3 GRUs -> dense, gain smoothing (a13, a14)
+//   K5 synthesis  per stream: pitch filter, gain interpolation, inverse FFT, overlap-add (a15, a16)
+//
+// EXACTNESS CONTRACT.  Everything that feeds a discrete pitch decision (K0, K1, K2) is computed
+// with the oracle's operation order and roundings: this translation unit is compiled with
+// -fmad=false (nvcc) / -ffp-contract=off (host emulation), so a*b+c is a rounded product followed by
+// a rounded sum unless fmaf() is spelled out; fmaf() appears only in K3-K5 (spectra, RNN), whose
+// results are continuous in their inputs.  Pitch indices therefore match the oracle bit for bit.
+//
+// The same source compiles for sm_100a (nvcc) and for the host SIMT emulation (NS_HOST_EMU, tests).
+#pragma once
+#include "ns_common.h"
+#include "ns_simt.h"
+
+namespace ns {
+
+NS_DEV f4 ld4(const float *p) { return *reinterpret_cast<const f4 *>(p); }
+
+// =================================================================================================
+// K0: a6 biquad high-pass.  upstream denoise.c biquad(): y = x + mem0 (f32);
+// mem0 = (f32)(mem1 + (b0 x - a0 y)), mem1 = (f32)(b1 x - a1 y) with f64 intermediates.  The f32
+// rounding of the state makes the recursion non-linear, so it is run serially, one lane per stream;
+// a warp moves 32-sample x 32-stream tiles through shared memory so HBM sees 128-byte rows.
+// =================================================================================================
+struct HpSmem {
+  float tile[32][33];
+};
+
+NS_DEV float load_sample(const Params &p, int stream, long long idx) {
+  const long long off = (long long)stream * p.in_stride + idx;
+  if (p.flags & kFlagInI16) return (float)reinterpret_cast<const int16_t *>(p.in)[off];
+  const float v = reinterpret_cast<const float *>(p.in)[off];
+  return (p.flags & kFlagUnitScale) ? v * 32768.0f : v;  // audio.rs:264
+}
+
+NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
+  const int lane = Simt::tid() & 31;
+  const int s0 = Simt::cta() * 32;
+  const int nrows = (p.n_streams - s0) < 32 ? (p.n_streams - s0) : 32;
+  for (int r = 0; r < nrows; r++) {  // history -> front of the slot row
+    const float *src = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
+    float *dst = p.hp + (long long)(s0 + r) * p.hp_stride;
+    for (int i = lane; i < kHist; i += 32) dst[i] = src[i];
+  }
+  const bool valid = lane < nrows;
+  float *st = p.state + (long long)(s0 + (valid ? lane : 0)) * kStateFloats;
+  float m0 = valid ? st[kStHp] : 0.f, m1 = valid ? st[kStHp + 1] : 0.f;
+  const double a0 = (double)-1.99599f, a1 = (double)0.99600f;
+  const int nsamp = p.n_frames * kFrame;
+  const long long in0 = (long long)p.frame0 * kFrame;
+  float nxt[32];
+#pragma unroll
+  for (int r = 0; r < 32; r++) nxt[r] = (r < nrows) ? load_sample(p, s0 + r, in0 + lane) : 0.f;
+  for (int base = 0; base < nsamp; base += 32) {
+#pragma unroll
+    for (int r = 0; r < 32; r++) sm.tile[r][lane] = nxt[r];
+    Simt::warp_sync();
+    if (base + 32 < nsamp) {
+#pragma unroll
+      for (int r = 0; r < 32; r++) nxt[r] = (r < nrows) ? load_sample(p, s0 + r, in0 + base + 32 + lane) : 0.f;
+    }
+    if (valid) {
+#pragma unroll 8
+      for (int i = 0; i < 32; i++) {
+        const float xi = sm.tile[lane][i];
+        const float yi = xi + m0;
+        const double xd = (double)xi, yd = (double)yi;
+        m0 = (float)((double)m1 + (-2.0 * xd - a0 * yd));
+        m1 = (float)(xd - a1 * yd);
+        sm.tile[lane][i] = yi;
+      }
+    }
+    Simt::warp_sync();
+    for (int r = 0; r < nrows; r++) p.hp[(long long)(s0 + r) * p.hp_stride + kHist + base + lane] = sm.tile[r][lane];
+    Simt::warp_sync();
+  }
+  if (valid) {
+    st[kStHp] = m0;
+    st[kStHp + 1] = m1;
+  }
+  for (int r = 0; r < nrows; r++) {  // last kHist samples of [history | chunk] -> state
+    const float *src = p.hp + (long long)(s0 + r) * p.hp_stride + nsamp;
+    float *dst = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
+    for (int i = lane; i < kHist; i += 32) dst[i] = src[i];
+  }
+}
+
+// =================================================================================================
+// K1: pitch analysis of R consecutive frames of one stream.  Every sum below is accumulated in the
+// oracle's order (ascending index, rounded product then rounded add), one lane per sum.
+// =================================================================================================
+template <int R>
+struct PitchSmem {
+  static constexpr int kHLen = R * kFrame + 1248;
+  static constexpr int kXlpFloats = (R * kLpStride > kHLen) ? R * kLpStride : kHLen;
+  float xr[R * kLpStride];  // raw downsampled rows; after the FIR each row holds y4[432] | yy_lookup[388]
+  float xlp[kXlpFloats];    // first the high-passed window, then the whitened rows x_lp
+  float xc[R][148];
+  float ac[R][8];
+  float lpc2[R][8];
+  float fx[R][12];
+  int fi[R][12];
+  float xx[R], xy0[R];
+  int best0[R], best1[R], T0[R], nk[R];
+  int n_tasks;
+  int task[R * 64];    // frame | lag << 4 | dst << 16
+  float dots[R][64];   // 0: T0-1, 1: T0+1; for k >= 2 at 2+4(k-2): T1-1, T1, T1+1, T1b
+};
+
+struct Best2 {
+  float n0, d0, n1, d1;
+  int p0, p1;
+};
+NS_DEV void best_init(Best2 &b) {
+  b.n0 = b.n1 = -1.f;
+  b.d0 = b.d1 = 0.f;
+  b.p0 = 0;
+  b.p1 = 1;
+}
+NS_DEV void best_insert(Best2 &b, float num, float syy, int i) {  // pitch.c find_best_pitch
+  if (num * b.d1 > b.n1 * syy) {
+    if (num * b.d0 > b.n0 * syy) {
+      b.n1 = b.n0;
+      b.d1 = b.d0;
+      b.p1 = b.p0;
+      b.n0 = num;
+      b.d0 = syy;
+      b.p0 = i;
+    } else {
+      b.n1 = num;
+      b.d1 = syy;
+      b.p1 = i;
+    }
+  }
+}
+
+NS_DEV int rd_T1(int k, int T0) { return (2 * T0 + k) / (2 * k); }
+NS_DEV int rd_T1b(int k, int T0, int T1) {
+  if (k == 2) return (T1 + T0 > 384) ? T0 : T0 + T1;
+  const int sc = (k == 6 || k == 12) ? 5 : ((k & 1) ? 2 : 3);  // second_check[k]
+  return (2 * sc * T0 + k) / (2 * k);
+}
+NS_DEV float pitch_gain_f(float xy, float xx, float yy) { return xy / sqrtf(1.f + xx * yy); }
+
+template <int R, int NT>
+NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
+  const int tid = Simt::tid();
+  const int runs_per_stream = (p.n_frames + R - 1) / R;
+  const int stream = Simt::cta() / runs_per_stream;
+  const int t0 = (Simt::cta() % runs_per_stream) * R;
+  const int nfr = (p.n_frames - t0) < R ? (p.n_frames - t0) : R;
+  const float *row = p.hp + (long long)stream * p.hp_stride + 192 + (long long)t0 * kFrame;
+  float *h = sm.xlp;
+
+  // P0: the window of high-passed samples these frames' pitch buffers cover
+  {
+    const int n4 = (nfr * kFrame + 1248) / 4;
+    const f4 *src = reinterpret_cast<const f4 *>(row);
+    f4 *dst = reinterpret_cast<f4 *>(h);
+    for (int i = tid; i < n4; i += NT) dst[i] = src[i];
+  }
+  Simt::cta_sync();
+  // P1: a9 2x downsample, pitch_buf[j] of frame f = h[480 f + j]
+  for (int it = tid; it < nfr * kLpLen; it += NT) {
+    const int f = it / kLpLen, i = it - f * kLpLen;
+    const float *x = h + f * kFrame;
+    float v;
+    if (i == 0)
+      v = .5f * (.5f * x[1] + x[0]);
+    else
+      v = .5f * (.5f * (x[2 * i - 1] + x[2 * i + 1]) + x[2 * i]);
+    sm.xr[f * kLpStride + i] = v;
+  }
+  Simt::cta_sync();
+  // P2: _celt_autocorr, lags 0..4
+  for (int it = tid; it < nfr * 5; it += NT) {
+    const int f = it / 5, k = it - f * 5;
+    const float *x = sm.xr + f * kLpStride;
+    float sum = 0.f;
+    for (int j = 0; j < kLpLen - 4; j++) sum += x[j] * x[j + k];
+    float d = 0.f;
+    for (int i = k + kLpLen - 4; i < kLpLen; i++) d += x[i] * x[i - k];
+    sm.ac[f][k] = sum + d;
+  }
+  Simt::cta_sync();
+  // P3: lag window, _celt_lpc (order 4), bandwidth expansion, the extra zero
+  if (tid < nfr) {
+    const int f = tid;
+    float ac[5], lpc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 5; k++) ac[k] = sm.ac[f][k];
+    ac[0] *= 1.0001f;
+#pragma unroll
+    for (int i = 1; i <= 4; i++) ac[i] -= ac[i] * (.008f * i) * (.008f * i);
+    float error = ac[0];
+    if (ac[0] != 0.f) {
+      for (int i = 0; i < 4; i++) {
+        float rr = 0.f;
+        for (int j = 0; j < i; j++) rr += lpc[j] * ac[i - j];
+        rr += ac[i + 1];
+        const float r = -rr / error;
+        lpc[i] = r;
+        for (int j = 0; j < ((i + 1) >> 1); j++) {
+          const float t1 = lpc[j], t2 = lpc[i - 1 - j];
+          lpc[j] = t1 + r * t2;
+          lpc[i - 1 - j] = t2 + r * t1;
+        }
+        error = error - r * r * error;
+        if (error < .001f * ac[0]) break;
+      }
+    }
+    float tmp = 1.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      tmp = .9f * tmp;
+      lpc[i] = lpc[i] * tmp;
+    }
+    sm.lpc2[f][0] = lpc[0] + .8f;
+    sm.lpc2[f][1] = lpc[1] + .8f * lpc[0];
+    sm.lpc2[f][2] = lpc[2] + .8f * lpc[1];
+    sm.lpc2[f][3] = lpc[3] + .8f * lpc[2];
+    sm.lpc2[f][4] = .8f * lpc[3];
+  }
+  Simt::cta_sync();
+  // P4: celt_fir5 with zero initial memory -> x_lp (overwrites the window h, which is dead now)
+  for (int it = tid; it < nfr * kLpLen; it += NT) {
+    const int f = it / kLpLen, i = it - f * kLpLen;
+    const float *x = sm.xr + f * kLpStride;
+    const float *n = sm.lpc2[f];
+    float sum = x[i];
+    sum += n[0] * (i >= 1 ? x[i - 1] : 0.f);
+    sum += n[1] * (i >= 2 ? x[i - 2] : 0.f);
+    sum += n[2] * (i >= 3 ? x[i - 3] : 0.f);
+    sum += n[3] * (i >= 4 ? x[i - 4] : 0.f);
+    sum += n[4] * (i >= 5 ? x[i - 5] : 0.f);
+    sm.xlp[f * kLpStride + i] = sum;
+  }
+  Simt::cta_sync();
+  // P4b: 4x-decimated copy y4[m] = x_lp[2m] (x4[j] = y4[192 + j]); zero pad to 432+8
+  for (int it = tid; it < nfr * 440; it += NT) {
+    const int f = it / 440, m = it - f * 440;
+    sm.xr[f * kLpStride + m] = (m < 432) ? sm.xlp[f * kLpStride + 2 * m] : 0.f;
+  }
+  Simt::cta_sync();
+  // P5: a10 coarse cross-correlation, 147 lags x 240 taps, four lags per lane
+  for (int it = tid; it < nfr * 37; it += NT) {
+    const int f = it / 37, q = it - f * 37;
+    const float *y4 = sm.xr + f * kLpStride;
+    const float *x4 = y4 + 192;
+    const float *yb = y4 + 4 * q;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int j = 0; j < 240; j += 4) {
+      const f4 xv = ld4(x4 + j), ya = ld4(yb + j), yc = ld4(yb + j + 4);
+      a0 += xv.x * ya.x; a1 += xv.x * ya.y; a2 += xv.x * ya.z; a3 += xv.x * ya.w;
+      a0 += xv.y * ya.y; a1 += xv.y * ya.z; a2 += xv.y * ya.w; a3 += xv.y * yc.x;
+      a0 += xv.z * ya.z; a1 += xv.z * ya.w; a2 += xv.z * yc.x; a3 += xv.z * yc.y;
+      a0 += xv.w * ya.w; a1 += xv.w * yc.x; a2 += xv.w * yc.y; a3 += xv.w * yc.z;
+    }
+    float *dst = sm.xc[f] + 4 * q;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+  }
+  Simt::cta_sync();
+  // P6: find_best_pitch on the coarse correlation (one lane per frame; Syy is a running sum)
+  if (tid < nfr) {
+    const int f = tid;
+    const float *y4 = sm.xr + f * kLpStride;
+    Best2 b;
+    best_init(b);
+    float syy = 1.f;
+    for (int j = 0; j < 240; j++) syy += y4[j] * y4[j];
+    for (int i = 0; i < 147; i++) {
+      const float xc = sm.xc[f][i];
+      if (xc > 0.f) {
+        const float x16 = xc * 1e-12f;
+        best_insert(b, x16 * x16, syy, i);
+      }
+      syy += y4[i + 240] * y4[i + 240] - y4[i] * y4[i];
+      syy = syy < 1.f ? 1.f : syy;
+    }
+    sm.best0[f] = b.p0;
+    sm.best1[f] = b.p1;
+  }
+  Simt::cta_sync();
+  // P7: fine search, at most ten lags around 2*best0 and 2*best1
+  for (int it = tid; it < nfr * 10; it += NT) {
+    const int f = it / 10, c = it - f * 10;
+    const float *lp = sm.xlp + f * kLpStride;
+    const int c0 = 2 * sm.best0[f], c1 = 2 * sm.best1[f];
+    const int i = (c < 5) ? (c0 - 2 + c) : (c1 - 2 + (c - 5));
+    const int dd = i - c0;
+    const bool ok = (i >= 0) && (i < 294) && (c < 5 || dd > 2 || dd < -2);
+    float sum = 0.f;
+    if (ok) {
+      const float *x = lp + 384, *y = lp + i;
+      for (int j = 0; j < 480; j++) sum += x[j] * y[j];
+    }
+    sm.fi[f][c] = ok ? i : -1;
+    sm.fx[f][c] = sum < -1.f ? -1.f : sum;
+  }
+  Simt::cta_sync();
+  // P8: find_best_pitch on the fine correlation (zero outside the candidates), pseudo-interpolation
+  if (tid < nfr) {
+    const int f = tid;
+    const float *y = sm.xlp + f * kLpStride;
+    const int lo0 = 2 * sm.best0[f] - 2, lo1 = 2 * sm.best1[f] - 2;
+    auto xcorr_at = [&](int i) -> float {
+      const int d0 = i - lo0, d1 = i - lo1;
+      if (d0 >= 0 && d0 < 5 && sm.fi[f][d0] == i) return sm.fx[f][d0];
+      if (d1 >= 0 && d1 < 5 && sm.fi[f][5 + d1] == i) return sm.fx[f][5 + d1];
+      return 0.f;
+    };
+    Best2 b;
+    best_init(b);
+    float syy = 1.f;
+    for (int j = 0; j < 480; j++) syy += y[j] * y[j];
+    for (int i = 0; i < 294; i++) {
+      const int d0 = i - lo0, d1 = i - lo1;
+      if ((d0 >= 0 && d0 < 5) || (d1 >= 0 && d1 < 5)) {
+        const float xc = xcorr_at(i);
+        if (xc > 0.f) {
+          const float x16 = xc * 1e-12f;
+          best_insert(b, x16 * x16, syy, i);
+        }
+      }
+      syy += y[i + 480] * y[i + 480] - y[i] * y[i];
+      syy = syy < 1.f ? 1.f : syy;
+    }
+    const int bp = b.p0;
+    int offset = 0;
+    if (bp > 0 && bp < 293) {
+      const float a = xcorr_at(bp - 1), bb = xcorr_at(bp), cc = xcorr_at(bp + 1);
+      if ((cc - a) > .7f * (bb - a))
+        offset = 1;
+      else if ((a - cc) > .7f * (bb - cc))
+        offset = -1;
+    }
+    const int pitch_index = kPitchMax - (2 * bp - offset);
+    int T0 = pitch_index / 2;
+    if (T0 >= 384) T0 = 383;
+    sm.T0[f] = T0;
+  }
+  Simt::cta_sync();
+  // P9: a11 remove_doubling: xx and xy(T0) (dual_inner_prod), then the candidate work list
+  for (int it = tid; it < nfr * 2; it += NT) {
+    const int f = it >> 1;
+    const float *x = sm.xlp + f * kLpStride + 384;
+    const float *y = (it & 1) ? x - sm.T0[f] : x;
+    float sum = 0.f;
+    for (int j = 0; j < 480; j++) sum += x[j] * y[j];
+    if (it & 1)
+      sm.xy0[f] = sum;
+    else
+      sm.xx[f] = sum;
+  }
+  if (tid == 0) sm.n_tasks = 0;
+  Simt::cta_sync();
+  if (tid < nfr) {
+    const int f = tid;
+    const float *x = sm.xlp + f * kLpStride + 384;
+    float *yyl = sm.xr + f * kLpStride + 432;  // yy_lookup[0..384]
+    float yy = sm.xx[f];
+    yyl[0] = yy;
+    for (int i = 1; i <= 384; i++) {
+      yy = yy + x[-i] * x[-i] - x[480 - i] * x[480 - i];
+      yyl[i] = yy < 0.f ? 0.f : yy;
+    }
+    const int T0 = sm.T0[f];
+    int nk = 1;
+    for (int k = 2; k <= kMaxK; k++) {
+      if (rd_T1(k, T0) < 30) break;
+      nk = k;
+    }
+    sm.nk[f] = nk;
+    const int n = 2 + 4 * (nk - 1);
+    const int base = Simt::atomic_add_shared(&sm.n_tasks, n);
+    int *tk = sm.task + base;
+    tk[0] = f | ((T0 - 1) << 4) | (0 << 16);
+    tk[1] = f | ((T0 + 1) << 4) | (1 << 16);
+    for (int k = 2; k <= nk; k++) {
+      const int T1 = rd_T1(k, T0), T1b = rd_T1b(k, T0, T1);
+      const int d = 2 + 4 * (k - 2);
+      int *e = tk + d;
+      e[0] = f | ((T1 - 1) << 4) | ((d + 0) << 16);
+      e[1] = f | (T1 << 4) | ((d + 1) << 16);
+      e[2] = f | ((T1 + 1) << 4) | ((d + 2) << 16);
+      e[3] = f | (T1b << 4) | ((d + 3) << 16);
+    }
+  }
+  Simt::cta_sync();
+  // P11: one 480-tap inner product per work item
+  {
+    const int n = sm.n_tasks;
+    for (int it = tid; it < n; it += NT) {
+      const int e = sm.task[it];
+      const int f = e & 15, lag = (e >> 4) & 0xFFF, dst = e >> 16;
+      const float *x = sm.xlp + f * kLpStride + 384;
+      const float *y = x - lag;
+      float sum = 0.f;
+      for (int j = 0; j < 480; j++) sum += x[j] * y[j];
+      sm.dots[f][dst] = sum;
+    }
+  }
+  Simt::cta_sync();
+  // P12: per candidate k: gain, the pitch gain it would report, refined pitch index -> table
+  for (int it = tid; it < nfr * 16; it += NT) {
+    const int f = it >> 4, k = it & 15;  // k == 0 writes the header
+    uint32_t *tab = p.tab + ((long long)stream * p.chunk_cap + (t0 + f)) * kTabWords;
+    const int T0 = sm.T0[f], nk = sm.nk[f];
+    if (k == 0) {
+      tab[0] = (uint32_t)T0 | ((uint32_t)nk << 16);
+      tab[1] = 0u;
+      continue;
+    }
+    if (k > nk) continue;
+    const float *yyl = sm.xr + f * kLpStride + 432;
+    const float xx = sm.xx[f];
+    float xy, yy, c0, c1, c2;
+    int T;
+    if (k == 1) {
+      T = T0;
+      xy = sm.xy0[f];
+      yy = yyl[T0];
+      c0 = sm.dots[f][0];
+      c1 = xy;
+      c2 = sm.dots[f][1];
+    } else {
+      const int d = 2 + 4 * (k - 2);
+      T = rd_T1(k, T0);
+      const int T1b = rd_T1b(k, T0, T);
+      c0 = sm.dots[f][d];
+      c1 = sm.dots[f][d + 1];
+      c2 = sm.dots[f][d + 2];
+      xy = .5f * (c1 + sm.dots[f][d + 3]);
+      yy = .5f * (yyl[T] + yyl[T1b]);
+    }
+    const float g = pitch_gain_f(xy, xx, yy);
+    const float bxy = xy < 0.f ? 0.f : xy;
+    float pg = (yy <= bxy) ? 1.f : bxy / (yy + 1.f);
+    if (pg > g) pg = g;
+    int offset = 0;
+    if ((c2 - c0) > .7f * (c1 - c0))
+      offset = 1;
+    else if ((c0 - c2) > .7f * (c1 - c2))
+      offset = -1;
+    int pi = 2 * T + offset;
+    if (pi < kPitchMin) pi = kPitchMin;
+    uint32_t *e = tab + 2 + 3 * (k - 1);
+    e[0] = (uint32_t)T | ((uint32_t)pi << 16);
+    e[1] = f2u(g);
+    e[2] = f2u(pg);
+  }
+}
+
+// =================================================================================================
+// K2: the serial part of remove_doubling.  One warp per stream; lane k-1 judges candidate k against
+// the threshold that depends on the previous frame's period and gain; the last passing k wins.
+// =================================================================================================
+NS_DEV void pitchscan_body(const Params &p, int warps_per_cta) {
+  const int lane = Simt::tid() & 31;
+  const int stream = Simt::cta() * warps_per_cta + (Simt::tid() >> 5);
+  if (stream >= p.n_streams) return;
+  float *st = p.state + (long long)stream * kStateFloats;
+  int last_period = reinterpret_cast<int *>(st)[kStLastPeriod];
+  float last_gain = st[kStLastGain];
+  const uint32_t *tab = p.tab + (long long)stream * p.chunk_cap * kTabWords;
+  float *rec = p.rec + (long long)stream * p.chunk_cap * kRecFloats;
+  const int k = lane + 1;
+  for (int t = 0; t < p.n_frames; t++, tab += kTabWords, rec += kRecFloats) {
+    const uint32_t hdr = tab[0];
+    const int T0 = (int)(hdr & 0xFFFFu), nk = (int)(hdr >> 16);
+    uint32_t w0 = 0u;
+    float g1 = 0.f, pg = 0.f;
+    if (k <= nk) {
+      w0 = tab[2 + 3 * lane];
+      g1 = u2f(tab[3 + 3 * lane]);
+      pg = u2f(tab[4 + 3 * lane]);
+    }
+    const float g0 = Simt::shfl(g1, 0);
+    const int T1 = (int)(w0 & 0xFFFFu);
+    const int prev_period = last_period / 2;
+    bool pass = (k == 1);
+    if (k >= 2 && k <= nk) {
+      const int dT = T1 > prev_period ? T1 - prev_period : prev_period - T1;
+      float cont;
+      if (dT <= 1)
+        cont = last_gain;
+      else if (dT <= 2 && 5 * k * k < T0)
+        cont = .5f * last_gain;
+      else
+        cont = 0.f;
+      float thresh = .7f * g0 - cont;
+      if (thresh < .3f) thresh = .3f;
+      if (T1 < 90) {
+        thresh = .85f * g0 - cont;
+        if (thresh < .4f) thresh = .4f;
+      } else if (T1 < 60) {
+        thresh = .9f * g0 - cont;
+        if (thresh < .5f) thresh = .5f;
+      }
+      pass = g1 > thresh;
+    }
+    const unsigned m = Simt::ballot(pass);
+    int win = 0;
+    for (int b = 14; b > 0; b--)
+      if (m & (1u << b)) {
+        win = b;
+        break;
+      }
+    const int pi = (int)(Simt::shfl((int)w0, win) >> 16) & 0xFFFF;
+    const float gain = Simt::shfl(pg, win);
+    last_period = pi;
+    last_gain = gain;
+    if (lane == 0) {
+      reinterpret_cast<int *>(rec)[kRecPitchIndex] = pi;
+      rec[kRecPitchGain] = gain;
+    }
+  }
+  if (lane == 0) {
+    reinterpret_cast<int *>(st)[kStLastPeriod] = last_period;
+    st[kStLastGain] = last_gain;
+  }
+}
+
+// =================================================================================================
+// spectra: 480-point complex FFT (forward), Stockham radices 4,4,5,6 through registers, by a
+// 128-thread group that meets on its own named barrier
+// =================================================================================================
+struct Grp {
+  int tid, lane, warp, bar;
+};
+NS_DEV void gsync(const Grp &g) { Simt::group_sync(g.bar, kGroupThreads); }
+NS_DEV cf cmul(cf a, cf b) {
+  cf c;
+  c.x = fmaf(a.x, b.x, -(a.y * b.y));
+  c.y = fmaf(a.x, b.y, a.y * b.x);
+  return c;
+}
+NS_DEV cf cadd(cf a, cf b) { return cf{a.x + b.x, a.y + b.y}; }
+NS_DEV cf csub(cf a, cf b) { return cf{a.x - b.x, a.y - b.y}; }
+NS_DEV cf mul_neg_i(cf a) { return cf{a.y, -a.x}; }  // a * (-i)
+NS_DEV cf mul_pos_i(cf a) { return cf{-a.y, a.x}; }  // a * (+i)
+
+template <int R>
+struct Dft;
+template <>
+struct Dft<3> {
+  static NS_DEV void run(cf *v) {
+    const float s = 0.86602540378443864676f;
+    cf a = cadd(v[1], v[2]), b = csub(v[1], v[2]);
+    cf m = cf{fmaf(-0.5f, a.x, v[0].x), fmaf(-0.5f, a.y, v[0].y)};
+    cf n = cf{s * b.x, s * b.y};
+    v[0] = cadd(v[0], a);
+    v[1] = cadd(m, mul_neg_i(n));
+    v[2] = cadd(m, mul_pos_i(n));
+  }
+};
+template <>
+struct Dft<4> {
+  static NS_DEV void run(cf *v) {
+    cf t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    cf t2 = cadd(v[1], v[3]), t3 = mul_neg_i(csub(v[1], v[3]));
+    v[0] = cadd(t0, t2);
+    v[2] = csub(t0, t2);
+    v[1] = cadd(t1, t3);
+    v[3] = csub(t1, t3);
+  }
+};
+template <>
+struct Dft<5> {
+  static NS_DEV void run(cf *v) {
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    cf a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
+    cf b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+    cf m1 = cf{fmaf(c2, a2.x, fmaf(c1, a1.x, v[0].x)), fmaf(c2, a2.y, fmaf(c1, a1.y, v[0].y))};
+    cf m2 = cf{fmaf(c1, a2.x, fmaf(c2, a1.x, v[0].x)), fmaf(c1, a2.y, fmaf(c2, a1.y, v[0].y))};
+    cf n1 = cf{fmaf(s2, b2.x, s1 * b1.x), fmaf(s2, b2.y, s1 * b1.y)};
+    cf n2 = cf{fmaf(-s1, b2.x, s2 * b1.x), fmaf(-s1, b2.y, s2 * b1.y)};
+    v[0] = cf{v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y};
+    v[1] = cadd(m1, mul_neg_i(n1));
+    v[4] = cadd(m1, mul_pos_i(n1));
+    v[2] = cadd(m2, mul_neg_i(n2));
+    v[3] = cadd(m2, mul_pos_i(n2));
+  }
+};
+template <>
+struct Dft<6> {
+  static NS_DEV void run(cf *v) {
+    cf e[3] = {v[0], v[2], v[4]};
+    cf o[3] = {v[1], v[3], v[5]};
+    Dft<3>::run(e);
+    Dft<3>::run(o);
+    const cf w1 = cf{0.5f, -0.86602540378443864676f};   // W6
+    const cf w2 = cf{-0.5f, -0.86602540378443864676f};  // W6^2
+    o[1] = cmul(o[1], w1);
+    o[2] = cmul(o[2], w2);
+    v[0] = cadd(e[0], o[0]);
+    v[1] = cadd(e[1], o[1]);
+    v[2] = cadd(e[2], o[2]);
+    v[3] = csub(e[0], o[0]);
+    v[4] = csub(e[1], o[1]);
+    v[5] = csub(e[2], o[2]);
+  }
+};
+
+template <int R, int NS_, class Load>
+NS_DEV void fft_stage(const Grp &g, const Tables &T, cf *buf, Load load) {
+  constexpr int M = 480 / R;
+  constexpr int TSTEP = 480 / (NS_ * R);
+  cf v[R];
+  const int j = g.tid;
+  const bool act = j < M;
+  int k = 0;
+  if (act) {
+    k = j % NS_;
+    v[0] = load(j);
+#pragma unroll
+    for (int r = 1; r < R; r++) {
+      cf x = load(j + r * M);
+      v[r] = (NS_ == 1) ? x : cmul(x, T.w480[r * k * TSTEP]);
+    }
+    Dft<R>::run(v);
+  }
+  gsync(g);
+  if (act) {
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; r++) buf[j0 + r * NS_] = v[r];
+  }
+  gsync(g);
+}
+
+template <class LoadFirst>
+NS_DEV void fft480(const Grp &g, const Tables &T, cf *buf, LoadFirst load_first) {
+  auto from_buf = [&](int n) -> cf { return buf[n]; };
+  fft_stage<4, 1>(g, T, buf, load_first);
+  fft_stage<4, 4>(g, T, buf, from_buf);
+  fft_stage<5, 16>(g, T, buf, from_buf);
+  fft_stage<6, 80>(g, T, buf, from_buf);
+}
+
+// a7 / a12: X <- rFFT960(window . src[0..960)) / 960   (bins 0..480); src is in HBM/L2
+NS_DEV void rfft960_windowed(const Grp &g, const Tables &T, const float *__restrict__ src, cf *X) {
+  auto load = [&](int n) -> cf {
+    const int i0 = 2 * n;
+    const float w0 = (i0 < kFrame) ? T.win[i0] : T.win[kWindow - 1 - i0];
+    const float w1 = (i0 + 1 < kFrame) ? T.win[i0 + 1] : T.win[kWindow - 2 - i0];
+    return cf{src[i0] * w0, src[i0 + 1] * w1};
+  };
+  fft480(g, T, X, load);
+  const float norm = 1.0f / kWindow;
+  for (int k = g.tid; k <= 240; k += kGroupThreads) {
+    const cf a = X[k], b = X[k == 0 ? 0 : 480 - k], w = T.w960[k];
+    const float er = .5f * (a.x + b.x), ei = .5f * (a.y - b.y);
+    const float orr = .5f * (a.x - b.x), oi = .5f * (a.y + b.y);
+    const float tr = fmaf(orr, w.x, -(oi * w.y)), ti = fmaf(orr, w.y, oi * w.x);
+    X[k] = cf{(er + ti) * norm, (ei - tr) * norm};
+    X[480 - k] = cf{(er - ti) * norm, (-ei - tr) * norm};
+  }
+  gsync(g);
+}
+
+// a16: unscaled inverse of the Hermitian spectrum X[0..480]; result left in X as 480 complex
+// z[m] with x[2m] = z[m].x and x[2m+1] = -z[m].y (the conjugate of a forward FFT).
+NS_DEV void irfft960_inplace(const Grp &g, const Tables &T, cf *X) {
+  for (int k = g.tid; k <= 240; k += kGroupThreads) {
+    const cf a = X[k], b = X[480 - k], w = T.w960[k];
+    const float ex = a.x + b.x, ey = a.y - b.y;
+    const float ox = a.x - b.x, oy = a.y + b.y;
+    const float tr = fmaf(ox, w.x, oy * w.y), ti = fmaf(-ox, w.y, oy * w.x);
+    X[k] = cf{ex - ti, -(ey + tr)};
+    if (k != 0) X[480 - k] = cf{ex + ti, ey - tr};
+  }
+  gsync(g);
+  auto from_buf = [&](int n) -> cf { return X[n]; };
+  fft480(g, T, X, from_buf);
+}
+
+// a8: 22 triangular bands over bins 0..400.  88 threads: band = tid/4, four lanes split the bins.
+template <class BinVal>
+NS_DEV float band_accumulate(const Grp &g, const Tables &T, BinVal val) {
+  float acc = 0.f;
+  const int b = g.tid >> 2, sub = g.tid & 3;
+  if (g.tid < 4 * kBands) {
+    if (b >= 1) {
+      const int lo = T.eband[b - 1], n = T.eband[b] - lo;
+      for (int j = sub; j < n; j += 4) acc = fmaf((float)j / (float)n, val(lo + j), acc);
+    }
+    if (b <= kBands - 2) {
+      const int lo = T.eband[b], n = T.eband[b + 1] - lo;
+      for (int j = sub; j < n; j += 4) acc = fmaf(1.f - (float)j / (float)n, val(lo + j), acc);
+    }
+  }
+  acc += Simt::shfl_xor(acc, 1);
+  acc += Simt::shfl_xor(acc, 2);
+  if (b == 0 || b == kBands - 1) acc *= 2.f;
+  return acc;  // valid in lanes with sub == 0 and tid < 88
+}
+
+struct SpecSmem {
+  Tables tab;
+  cf X[482];
+  cf P[482];
+  float Ex[24], Ep[24], Exp[24], Ly[24], g[24], graw[24], r[24], nrm[24], newE[24];
+  float synth[kFrame];
+  int pitch_index, silence;
+};
+
+NS_DEV void load_tables(const Params &p, Tables &dst, int tid, int nthr) {
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(p.tables);
+  uint32_t *d = reinterpret_cast<uint32_t *>(&dst);
+  for (int i = tid; i < (int)(sizeof(Tables) / 4); i += nthr) d[i] = src[i];
+}
+
+// spectra of frame t: X of [prev | cur], P of the window lagged by pitch_index, Ex / Ep / raw Exp
+NS_DEV void frame_spectra(const Grp &g, const Tables &T, SpecSmem &s, const float *hp_row, int t, int pitch_index,
+                          bool want_p) {
+  const float *cur = hp_row + kHist - kFrame + (long long)t * kFrame;  // [analysis_mem | frame]
+  rfft960_windowed(g, T, cur, s.X);
+  if (want_p) rfft960_windowed(g, T, cur - pitch_index, s.P);
+  const float ex = band_accumulate(g, T, [&](int k) { return fmaf(s.X[k].x, s.X[k].x, s.X[k].y * s.X[k].y); });
+  float ep = 0.f, exp_ = 0.f;
+  if (want_p) {
+    ep = band_accumulate(g, T, [&](int k) { return fmaf(s.P[k].x, s.P[k].x, s.P[k].y * s.P[k].y); });
+    exp_ = band_accumulate(g, T, [&](int k) { return fmaf(s.X[k].x, s.P[k].x, s.X[k].y * s.P[k].y); });
+  }
+  if (g.tid < 4 * kBands && (g.tid & 3) == 0) {
+    s.Ex[g.tid >> 2] = ex;
+    s.Ep[g.tid >> 2] = ep;
+    s.Exp[g.tid >> 2] = exp_;
+  }
+  gsync(g);
+}
+
+// =================================================================================================
+// K3: per (stream, frame): spectra -> band features that do not depend on recurrent state
+// =================================================================================================
+NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
+  Grp g;
+  g.tid = Simt::tid();
+  g.lane = g.tid & 31;
+  g.warp = g.tid >> 5;
+  g.bar = 1;
+  load_tables(p, s.tab, g.tid, kGroupThreads);
+  Simt::cta_sync();
+  const Tables &T = s.tab;
+  const float dct_scale = 0.30151134457776363f;  // sqrt(2/22)
+  const long long n_tasks = (long long)p.n_streams * p.n_frames;
+  for (long long task = Simt::cta(); task < n_tasks; task += Simt::n_ctas()) {
+    const int stream = (int)(task / p.n_frames), t = (int)(task - (long long)stream * p.n_frames);
+    float *rec = p.rec + ((long long)stream * p.chunk_cap + t) * kRecFloats;
+    const int pitch_index = reinterpret_cast<const int *>(rec)[kRecPitchIndex];
+    frame_spectra(g, T, s, p.hp + (long long)stream * p.hp_stride, t, pitch_index, true);
+    if (g.tid < kBands) {
+      const int i = g.tid;
+      s.Exp[i] = s.Exp[i] / (float)sqrt(.001 + (double)(s.Ex[i] * s.Ep[i]));
+    } else if (g.tid == 32) {
+      float logMax = -2.f, follow = -2.f, E = 0.f;
+      for (int i = 0; i < kBands; i++) {
+        float ly = (float)log10(1e-2 + (double)s.Ex[i]);
+        ly = fmaxf(logMax - 7.f, fmaxf(follow - 1.5f, ly));
+        logMax = fmaxf(logMax, ly);
+        follow = fmaxf(follow - 1.5f, ly);
+        s.Ly[i] = ly;
+        E += s.Ex[i];
+      }
+      s.silence = (E < 0.04f) ? 1 : 0;
+    }
+    gsync(g);
+    if (g.tid < kBands) {
+      const int i = g.tid;
+      float sum = 0.f;
+      for (int j = 0; j < kBands; j++) sum += s.Ly[j] * T.dct[j * kBands + i];
+      float c = sum * dct_scale;
+      if (i == 0) c -= 12.f;
+      if (i == 1) c -= 4.f;
+      rec[kRecCeps + i] = c;
+      rec[kRecExp + i] = s.Exp[i];
+      if (p.dbg) {
+        float *d = p.dbg + ((long long)stream * p.n_frames_call + p.frame0 + t) * kDbgFloats;
+        d[kDbgEx + i] = s.Ex[i];
+        d[kDbgEp + i] = s.Ep[i];
+        d[kDbgExp + i] = s.Exp[i];
+      }
+    } else if (g.tid >= 32 && g.tid < 32 + kDeltaCeps) {
+      const int i = g.tid - 32;
+      float sum = 0.f;
+      for (int j = 0; j < kBands; j++) sum += s.Exp[j] * T.dct[j * kBands + i];
+      float c = sum * dct_scale;
+      if (i == 0) c -= 1.3f;
+      if (i == 1) c -= 0.9f;
+      rec[kRecTail + i] = c;
+    } else if (g.tid == 40) {
+      rec[kRecTail + kDeltaCeps] = .01f * (float)(pitch_index - 300);
+      reinterpret_cast<int *>(rec)[kRecSilence] = s.silence;
+    }
+    gsync(g);
+  }
+}
+
+// =================================================================================================
+// K4: the recurrent core, 8 streams per CTA, serial over the chunk's frames
+// =================================================================================================
+constexpr int kRnnStreams = 8;
+struct RnnSmem {
+  float tansig[204];
+  float feat[44 * 8];  // [row][stream]
+  float dense[24 * 8];
+  float hvad[24 * 8];
+  float hnoise[48 * 8];
+  float hden[96 * 8];
+  float rh[96 * 8];
+  float z[96 * 8];
+  float gains[24 * 8];
+  float vad[8];
+  int silent[8];
+  int memid[8];
+  float ring[8][kCepsMem][kBands];
+  float lastg[8][kBands];
+  float cin[8][32];     // ceps[22] | tail[7] of the current frame
+  float fstage[8][44];  // features being assembled
+  float dist[8][64];
+};
+
+NS_DEV float tansig_approx(const float *tab, float x) {
+  if (!(x < 8.f)) return 1.f;
+  if (!(x > -8.f)) return -1.f;
+  float sign = 1.f;
+  if (x < 0.f) {
+    x = -x;
+    sign = -1.f;
+  }
+  const int i = (int)floorf(.5f + 25.f * x);
+  x -= .04f * i;
+  float y = tab[i];
+  const float dy = 1.f - y * y;
+  y = y + x * dy * (1.f - y * x);
+  return sign * y;
+}
+NS_DEV float sigmoid_approx(const float *tab, float x) { return .5f + .5f * tansig_approx(tab, .5f * x); }
+NS_DEV float activate(const float *tab, int act, float x) {
+  if (act == 1) return sigmoid_approx(tab, x);
+  if (act == 0) return tansig_approx(tab, x);
+  return x < 0.f ? 0.f : x;
+}
+
+NS_DEV float *rnn_seg_ptr(RnnSmem &r, int id) {
+  switch (id) {
+    case kSegFeat: return r.feat;
+    case kSegDense: return r.dense;
+    case kSegHVad: return r.hvad;
+    case kSegHNoise: return r.hnoise;
+    case kSegHDen: return r.hden;
+    default: return r.rh;
+  }
+}
+
+// acc[s] = bias[col] + sum_rows W[row][col] * act[row][s]   for one output column `col`
+NS_DEV void rnn_matvec(const JobDesc &jd, const uint32_t *__restrict__ words, const float *__restrict__ bias,
+                       RnnSmem &r, int col, float (&acc)[8]) {
+  const float b = bias[jd.b_off + col];
+#pragma unroll
+  for (int s = 0; s < 8; s++) acc[s] = b;
+  const uint32_t *w = words + jd.w_off + col;
+  const int n_out = jd.n_out;
+  for (int sg = 0; sg < jd.n_segs; sg++) {
+    const float *a = rnn_seg_ptr(r, jd.seg_id[sg]);
+    const int k4 = jd.seg_k4[sg];
+    for (int kk = 0; kk < k4; kk++) {
+      const uint32_t wv = *w;
+      w += n_out;
+#pragma unroll
+      for (int bb = 0; bb < 4; bb++) {
+        const float wf = (float)(int)(int8_t)((wv >> (8 * bb)) & 0xFFu);
+        const f4 lo = ld4(a), hi = ld4(a + 4);
+        a += 8;
+        acc[0] = fmaf(wf, lo.x, acc[0]);
+        acc[1] = fmaf(wf, lo.y, acc[1]);
+        acc[2] = fmaf(wf, lo.z, acc[2]);
+        acc[3] = fmaf(wf, lo.w, acc[3]);
+        acc[4] = fmaf(wf, hi.x, acc[4]);
+        acc[5] = fmaf(wf, hi.y, acc[5]);
+        acc[6] = fmaf(wf, hi.z, acc[6]);
+        acc[7] = fmaf(wf, hi.w, acc[7]);
+      }
+    }
+  }
+}
+
+NS_DEV void rnn_dense(const RnnHeader &H, int job, const Params &p, RnnSmem &r, int tid, int nthr, float *dst) {
+  const JobDesc &jd = H.jobs[job];
+  for (int col = tid; col < jd.n_out; col += nthr) {
+    float acc[8];
+    rnn_matvec(jd, p.rnn_words, p.rnn_bias, r, col, acc);
+#pragma unroll
+    for (int s = 0; s < 8; s++) dst[col * 8 + s] = activate(r.tansig, jd.activation, acc[s] * (1.f / 256));
+  }
+}
+// z and r gates of a GRU with N neurons: columns [0,N) -> z, [N,2N) -> r*h into rh
+NS_DEV void rnn_gru_zr(const RnnHeader &H, int job, const Params &p, RnnSmem &r, int tid, int nthr, const float *h) {
+  const JobDesc &jd = H.jobs[job];
+  const int N = jd.n_out >> 1;
+  for (int col = tid; col < jd.n_out; col += nthr) {
+    float acc[8];
+    rnn_matvec(jd, p.rnn_words, p.rnn_bias, r, col, acc);
+    if (col < N) {
+#pragma unroll
+      for (int s = 0; s < 8; s++) r.z[col * 8 + s] = sigmoid_approx(r.tansig, acc[s] * (1.f / 256));
+    } else {
+      const int i = col - N;
+#pragma unroll
+      for (int s = 0; s < 8; s++) r.rh[i * 8 + s] = h[i * 8 + s] * sigmoid_approx(r.tansig, acc[s] * (1.f / 256));
+    }
+  }
+}
+NS_DEV void rnn_gru_c(const RnnHeader &H, int job, const Params &p, RnnSmem &r, int tid, int nthr, float *h) {
+  const JobDesc &jd = H.jobs[job];
+  for (int col = tid; col < jd.n_out; col += nthr) {
+    float acc[8];
+    rnn_matvec(jd, p.rnn_words, p.rnn_bias, r, col, acc);
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const float c = activate(r.tansig, jd.activation, acc[s] * (1.f / 256));
+      const float z = r.z[col * 8 + s], ho = h[col * 8 + s];
+      const float hn = z * ho + (1.f - z) * c;
+      h[col * 8 + s] = r.silent[s] ? ho : hn;
+    }
+  }
+}
+
+NS_DEV void rnn_phase(const Params &p, RnnSmem &r, int tid, int nthr) {
+  const RnnHeader &H = *p.rnn_hdr;
+  rnn_dense(H, 0, p, r, tid, nthr, r.dense);
+  Simt::cta_sync();
+  rnn_gru_zr(H, 1, p, r, tid, nthr, r.hvad);
+  Simt::cta_sync();
+  rnn_gru_c(H, 2, p, r, tid, nthr, r.hvad);
+  Simt::cta_sync();
+  rnn_gru_zr(H, 4, p, r, tid, nthr, r.hnoise);
+  if (tid == nthr - 1) {  // vad_output rides along on the last thread
+    float acc[8];
+    rnn_matvec(H.jobs[3], p.rnn_words, p.rnn_bias, r, 0, acc);
+#pragma unroll
+    for (int s = 0; s < 8; s++) r.vad[s] = activate(r.tansig, H.jobs[3].activation, acc[s] * (1.f / 256));
+  }
+  Simt::cta_sync();
+  rnn_gru_c(H, 5, p, r, tid, nthr, r.hnoise);
+  Simt::cta_sync();
+  rnn_gru_zr(H, 6, p, r, tid, nthr, r.hden);
+  Simt::cta_sync();
+  rnn_gru_c(H, 7, p, r, tid, nthr, r.hden);
+  Simt::cta_sync();
+  rnn_dense(H, 8, p, r, tid, nthr, r.gains);
+  Simt::cta_sync();
+}
+
+template <int NT>
+NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
+  const int tid = Simt::tid();
+  const int s0 = Simt::cta() * kRnnStreams;
+  {
+    float *rz = reinterpret_cast<float *>(&r);
+    for (int i = tid; i < (int)(sizeof(RnnSmem) / 4); i += NT) rz[i] = 0.f;
+  }
+  Simt::cta_sync();
+  for (int i = tid; i < 204; i += NT) r.tansig[i] = p.tables->tansig[i];
+  for (int it = tid; it < kRnnStreams * 384; it += NT) {  // recurrent state -> shared memory
+    const int s = it / 384, j = it - s * 384;
+    if (s0 + s >= p.n_streams) continue;
+    const float *st = p.state + (long long)(s0 + s) * kStateFloats;
+    if (j < 176)
+      r.ring[s][j / kBands][j % kBands] = st[kStCeps + j];
+    else if (j < 198)
+      r.lastg[s][j - 176] = st[kStLastG + j - 176];
+    else if (j < 222)
+      r.hvad[(j - 198) * 8 + s] = st[kStHVad + j - 198];
+    else if (j < 270)
+      r.hnoise[(j - 222) * 8 + s] = st[kStHNoise + j - 222];
+    else if (j < 366)
+      r.hden[(j - 270) * 8 + s] = st[kStHDen + j - 270];
+    else if (j == 366)
+      r.memid[s] = reinterpret_cast<const int *>(st)[kStMemId];
+  }
+  Simt::cta_sync();
+  for (int t = 0; t < p.n_frames; t++) {
+    for (int it = tid; it < kRnnStreams * 32; it += NT) {
+      const int s = it >> 5, j = it & 31;
+      const bool act = s0 + s < p.n_streams;
+      const float *rec = p.rec + ((long long)(s0 + (act ? s : 0)) * p.chunk_cap + t) * kRecFloats;
+      if (j < kBands)
+        r.cin[s][j] = act ? rec[kRecCeps + j] : 0.f;
+      else if (j < kBands + 7)
+        r.cin[s][j] = act ? rec[kRecTail + j - kBands] : 0.f;
+      else if (j == 29)
+        r.silent[s] = act ? reinterpret_cast<const int *>(rec)[kRecSilence] : 1;
+    }
+    Simt::cta_sync();
+    for (int it = tid; it < kRnnStreams * kBands; it += NT) {  // a13: cepstral ring update
+      const int s = it / kBands, i = it - s * kBands;
+      if (!r.silent[s]) r.ring[s][r.memid[s]][i] = r.cin[s][i];
+    }
+    Simt::cta_sync();
+    for (int it = tid; it < kRnnStreams * 64; it += NT) {  // a13: pairwise cepstral distances
+      const int s = it >> 6, a = (it >> 3) & 7, b = it & 7;
+      if (r.silent[s]) continue;
+      float dist = 0.f;
+      for (int k = 0; k < kBands; k++) {
+        const float tt = r.ring[s][a][k] - r.ring[s][b][k];
+        dist += tt * tt;
+      }
+      r.dist[s][(a << 3) + b] = dist;
+    }
+    for (int it = tid; it < kRnnStreams * 44; it += NT) {  // a13: features[0..41]
+      const int s = it / 44, i = it - s * 44;
+      float v = 0.f;
+      if (!r.silent[s] && i < 41) {
+        const int m0 = r.memid[s], m1 = (m0 + 7) & 7, m2 = (m0 + 6) & 7;
+        if (i < kDeltaCeps) {
+          v = r.ring[s][m0][i] + r.ring[s][m1][i] + r.ring[s][m2][i];
+        } else if (i < kBands) {
+          v = r.cin[s][i];
+        } else if (i < kBands + kDeltaCeps) {
+          const int j = i - kBands;
+          v = r.ring[s][m0][j] - r.ring[s][m2][j];
+        } else if (i < kBands + 2 * kDeltaCeps) {
+          const int j = i - kBands - kDeltaCeps;
+          v = r.ring[s][m0][j] - 2.f * r.ring[s][m1][j] + r.ring[s][m2][j];
+        } else {
+          v = r.cin[s][kBands + (i - kBands - 2 * kDeltaCeps)];
+        }
+      }
+      if (i != 41) r.fstage[s][i] = v;
+    }
+    Simt::cta_sync();
+    if (tid < kRnnStreams) {
+      const int s = tid;
+      float v = 0.f;
+      if (!r.silent[s]) {
+        float sv = 0.f;
+        for (int a = 0; a < kCepsMem; a++) {
+          float mind = 1e15f;
+          for (int b = 0; b < kCepsMem; b++)
+            if (b != a) mind = fminf(mind, r.dist[s][(a << 3) + b]);
+          sv += mind;
+        }
+        v = sv / kCepsMem - 2.1f;
+        r.memid[s] = (r.memid[s] + 1) & 7;
+      }
+      r.fstage[s][41] = v;
+    }
+    Simt::cta_sync();
+    for (int it = tid; it < kRnnStreams * 44; it += NT) {
+      const int s = it & 7, row = it >> 3;
+      r.feat[row * 8 + s] = (row < kFeatures) ? r.fstage[s][row] : 0.f;
+    }
+    Simt::cta_sync();
+    rnn_phase(p, r, tid, NT);
+    for (int it = tid; it < kRnnStreams * 32; it += NT) {
+      const int s = it >> 5, i = it & 31;
+      if (s0 + s >= p.n_streams) continue;
+      const bool silent = r.silent[s] != 0;
+      float *rec = p.rec + ((long long)(s0 + s) * p.chunk_cap + t) * kRecFloats;
+      if (i < kBands) {
+        float gi = 0.f, graw = 0.f;
+        if (!silent) {
+          graw = r.gains[i * 8 + s];
+          gi = fmaxf(graw, .6f * r.lastg[s][i]);
+          r.lastg[s][i] = gi;
+        }
+        rec[kRecGRaw + i] = graw;
+        rec[kRecG + i] = gi;
+      } else if (i == 22) {
+        const float v = silent ? 0.f : r.vad[s];
+        rec[kRecVad] = v;
+        if (p.vad) p.vad[(long long)(s0 + s) * p.vad_stride + p.frame0 + t] = v;
+      }
+    }
+    if (p.dbg) {
+      for (int it = tid; it < kRnnStreams * kFeatures; it += NT) {
+        const int s = it / kFeatures, i = it - s * kFeatures;
+        if (s0 + s >= p.n_streams) continue;
+        p.dbg[((long long)(s0 + s) * p.n_frames_call + p.frame0 + t) * kDbgFloats + kDbgFeatures + i] = r.fstage[s][i];
+      }
+    }
+    Simt::cta_sync();
+  }
+  for (int it = tid; it < kRnnStreams * 384; it += NT) {  // recurrent state -> HBM
+    const int s = it / 384, j = it - s * 384;
+    if (s0 + s >= p.n_streams) continue;
+    float *st = p.state + (long long)(s0 + s) * kStateFloats;
+    if (j < 176)
+      st[kStCeps + j] = r.ring[s][j / kBands][j % kBands];
+    else if (j < 198)
+      st[kStLastG + j - 176] = r.lastg[s][j - 176];
+    else if (j < 222)
+      st[kStHVad + j - 198] = r.hvad[(j - 198) * 8 + s];
+    else if (j < 270)
+      st[kStHNoise + j - 222] = r.hnoise[(j - 222) * 8 + s];
+    else if (j < 366)
+      st[kStHDen + j - 270] = r.hden[(j - 270) * 8 + s];
+    else if (j == 366)
+      reinterpret_cast<int *>(st)[kStMemId] = r.memid[s];
+  }
+}
+
+// =================================================================================================
+// K5: a15 pitch filter + gain interpolation, a16 synthesis; one 128-thread group per stream walks
+// the chunk's frames carrying synthesis_mem in shared memory
+// =================================================================================================
+NS_DEV float interp_band(const Tables &T, const float *v, int k) {  // k < 400
+  const int b = T.bin_band[k];
+  const float f = T.bin_frac[k];
+  return (1.f - f) * v[b] + f * v[b + 1];
+}
+
+NS_DEV void pitch_filter_and_gains(const Grp &g, const Tables &T, SpecSmem &s) {
+  if (g.tid < kBands) {
+    const int i = g.tid;
+    const float e = s.Exp[i], gi = s.graw[i];
+    float r;
+    if (e > gi)
+      r = 1.f;
+    else
+      r = (e * e) * (1.f - gi * gi) / (.001f + (gi * gi) * (1.f - e * e));
+    r = sqrtf(fminf(1.f, fmaxf(0.f, r)));
+    r *= (float)sqrt((double)s.Ex[i] / (1e-8 + (double)s.Ep[i]));
+    s.r[i] = r;
+  }
+  gsync(g);
+  for (int k = g.tid; k < 400; k += kGroupThreads) {
+    const float rf = interp_band(T, s.r, k);
+    s.X[k].x += rf * s.P[k].x;
+    s.X[k].y += rf * s.P[k].y;
+  }
+  gsync(g);
+  {
+    const float e = band_accumulate(g, T, [&](int k) { return fmaf(s.X[k].x, s.X[k].x, s.X[k].y * s.X[k].y); });
+    if (g.tid < 4 * kBands && (g.tid & 3) == 0) s.newE[g.tid >> 2] = e;
+  }
+  gsync(g);
+  if (g.tid < kBands) {
+    const int i = g.tid;
+    s.nrm[i] = (float)sqrt((double)s.Ex[i] / (1e-8 + (double)s.newE[i]));
+  }
+  gsync(g);
+  for (int k = g.tid; k < kFreq; k += kGroupThreads) {
+    if (k < 400) {
+      const float nf = interp_band(T, s.nrm, k), gf = interp_band(T, s.g, k);
+      s.X[k].x = (s.X[k].x * nf) * gf;
+      s.X[k].y = (s.X[k].y * nf) * gf;
+    } else {
+      s.X[k] = cf{0.f, 0.f};
+    }
+  }
+  gsync(g);
+}
+
+NS_DEV void store_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem &s, int stream, int t_call) {
+  // X holds z[m] with x[2m] = z.x, x[2m+1] = -z.y.  out[i] = x[i] w[i] + synth[i]; synth = x[480+i] w[479-i]
+  const int slot = t_call + p.out_frame_offset;
+  const float *zb = reinterpret_cast<const float *>(s.X);
+  for (int i = g.tid; i < kFrame; i += kGroupThreads) {
+    const float x0 = (i & 1) ? -zb[i] : zb[i];
+    const float x1 = (i & 1) ? -zb[kFrame + i] : zb[kFrame + i];
+    const float o = x0 * T.win[i] + s.synth[i];
+    s.synth[i] = x1 * T.win[kFrame - 1 - i];
+    if (slot >= 0) {
+      const long long o_off = (long long)stream * p.out_stride + (long long)slot * kFrame + i;
+      if (p.flags & kFlagMixStereoI16) {
+        float dn = o / 32768.0f;
+        dn = fminf(1.f, fmaxf(-1.f, dn)) * p.volume;
+        float mixed = dn;
+        if (p.app) mixed += p.app[(long long)stream * p.app_stride + (long long)slot * kFrame + i];
+        mixed = fminf(1.f, fmaxf(-1.f, mixed));
+        const int16_t q = (int16_t)(int)(mixed * 32767.0f);  // truncation toward zero, as Rust `as i16`
+        int16_t *dst = reinterpret_cast<int16_t *>(p.out) + 2 * o_off;
+        dst[0] = q;
+        dst[1] = q;
+      } else if (p.flags & kFlagOutI16) {
+        float v = rintf(o);
+        v = fminf(32767.f, fmaxf(-32768.f, v));
+        reinterpret_cast<int16_t *>(p.out)[o_off] = (int16_t)(int)v;
+      } else {
+        float v = o;
+        if (p.flags & kFlagUnitScale) v = fminf(1.f, fmaxf(-1.f, o / 32768.0f)) * p.volume;
+        reinterpret_cast<float *>(p.out)[o_off] = v;
+      }
+    }
+  }
+}
+
+NS_DEV void synthesis_body(const Params &p, SpecSmem &s) {
+  Grp g;
+  g.tid = Simt::tid();
+  g.lane = g.tid & 31;
+  g.warp = g.tid >> 5;
+  g.bar = 1;
+  const int stream = Simt::cta();
+  load_tables(p, s.tab, g.tid, kGroupThreads);
+  float *st = p.state + (long long)stream * kStateFloats;
+  for (int i = g.tid; i < kFrame; i += kGroupThreads) s.synth[i] = st[kStSynth + i];
+  Simt::cta_sync();
+  const Tables &T = s.tab;
+  const float *hp_row = p.hp + (long long)stream * p.hp_stride;
+  for (int t = 0; t < p.n_frames; t++) {
+    const float *rec = p.rec + ((long long)stream * p.chunk_cap + t) * kRecFloats;
+    const int pitch_index = reinterpret_cast<const int *>(rec)[kRecPitchIndex];
+    const bool silent = reinterpret_cast<const int *>(rec)[kRecSilence] != 0;
+    if (g.tid < kBands) {
+      s.g[g.tid] = rec[kRecG + g.tid];
+      s.graw[g.tid] = rec[kRecGRaw + g.tid];
+    }
+    frame_spectra(g, T, s, hp_row, t, pitch_index, !silent);
+    if (!silent) {
+      // the band energies K3 stored are bit-identical to the ones just recomputed; Exp is the
+      // normalised correlation K3 derived from them
+      if (g.tid < kBands) s.Exp[g.tid] = rec[kRecExp + g.tid];
+      gsync(g);
+      pitch_filter_and_gains(g, T, s);
+    }
+    if (p.dbg) {
+      float *d = p.dbg + ((long long)stream * p.n_frames_call + p.frame0 + t) * kDbgFloats;
+      if (g.tid < kBands) {
+        d[kDbgGains + g.tid] = s.g[g.tid];
+      }
+      if (g.tid == 0) {
+        d[kDbgPitchGain] = rec[kRecPitchGain];
+        d[kDbgVad] = rec[kRecVad];
+        d[kDbgPitchIndex] = (float)pitch_index;
+        d[kDbgSilence] = silent ? 1.f : 0.f;
+      }
+    }
+    irfft960_inplace(g, T, s.X);
+    store_frame(g, T, p, s, stream, p.frame0 + t);
+    gsync(g);
+  }
+  for (int i = g.tid; i < kFrame; i += kGroupThreads) st[kStSynth + i] = s.synth[i];
+  if (g.tid == 0) reinterpret_cast<int *>(st)[kStFrameCount] += p.n_frames;
+}
+
+}  // namespace ns

@@ -13,6 +13,10 @@
 
 #define NS_DEV __device__ __forceinline__
 #define NS_DEV_NOINLINE __device__ __noinline__
+namespace ns {
+NS_DEV uint32_t f2u(float v) { return __float_as_uint(v); }
+NS_DEV float u2f(uint32_t v) { return __uint_as_float(v); }
+}  // namespace ns
 
 namespace ns {
 struct Simt {
@@ -33,6 +37,9 @@ struct Simt {
   static NS_DEV int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
   static NS_DEV double shfl_up(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
   static NS_DEV double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  static NS_DEV unsigned ballot(bool pred) { return __ballot_sync(0xffffffffu, pred); }
+  static NS_DEV int atomic_add_shared(int *p, int v) { return atomicAdd(p, v); }
+  static NS_DEV int n_ctas() { return (int)gridDim.x; }
 };
 }  // namespace ns
 
@@ -43,6 +50,18 @@ struct Simt {
 
 #define NS_DEV inline
 #define NS_DEV_NOINLINE inline
+namespace ns {
+inline uint32_t f2u(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  return u;
+}
+inline float u2f(uint32_t u) {
+  float v;
+  memcpy(&v, &u, 4);
+  return v;
+}
+}  // namespace ns
 
 namespace ns {
 struct EmuWarp {
@@ -54,6 +73,7 @@ struct EmuCta {
   pthread_barrier_t group_bar[16];
   EmuWarp *warps;
   int cta_index;
+  int n_ctas;
 };
 struct EmuThread {
   EmuCta *cta;
@@ -90,6 +110,17 @@ struct Simt {
   static int shfl(int v, int src) { return xchg(v, src); }
   static double shfl_up(double v, int d) { return xchg(v, lane() - d); }
   static double shfl(double v, int src) { return xchg(v, src); }
+  static unsigned ballot(bool pred) {
+    EmuWarp &w = g_emu.cta->warps[g_emu.tid >> 5];
+    w.xch[lane()] = pred ? 1u : 0u;
+    pthread_barrier_wait(&w.bar);
+    unsigned m = 0;
+    for (int i = 0; i < 32; i++) m |= (unsigned)(w.xch[i] & 1u) << i;
+    pthread_barrier_wait(&w.bar);
+    return m;
+  }
+  static int atomic_add_shared(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+  static int n_ctas() { return g_emu.cta->n_ctas; }
 };
 }  // namespace ns
 

@@ -274,7 +274,7 @@ class BatchDenoiser:
     def info(self) -> dict:
         s, c, l, f = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
         check(_lib.lib().crispy_ns_batch_info(self._h, C.byref(s), C.byref(c), C.byref(l), C.byref(f)))
-        return {"streams_per_cta": s.value, "n_ctas": c.value, "launches": l.value, "frames_done": f.value}
+        return {"rnn_streams_per_cta": s.value, "chunk_frames": c.value, "launches": l.value, "frames_done": f.value}
 
     @property
     def frames_done(self) -> int:

@@ -117,9 +117,11 @@ int crispy_ns_debug_floats(void);
 size_t crispy_ns_batch_state_size(const crispy_ns_batch *b);
 int crispy_ns_batch_save_state(crispy_ns_batch *b, void *buf, size_t len);
 int crispy_ns_batch_load_state(crispy_ns_batch *b, const void *buf, size_t len);
-/* launch geometry + bookkeeping: streams per CTA, CTAs, kernels launched, frames processed per stream */
-int crispy_ns_batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_ctas, int64_t *launches,
-                         int64_t *frames_done);
+/* launch geometry + bookkeeping: streams per recurrent-core CTA, frames per engine chunk
+ * ($CRISPY_NS_CHUNK_FRAMES overrides the default at batch_create), kernels launched so far,
+ * frames processed per stream */
+int crispy_ns_batch_info(const crispy_ns_batch *b, int *rnn_streams_per_cta, int *chunk_frames,
+                         int64_t *launches, int64_t *frames_done);
 void crispy_ns_batch_destroy(crispy_ns_batch *b);
 
 /* pinned host memory for the host-pointer path */

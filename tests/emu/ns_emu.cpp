@@ -1,76 +1,79 @@
-// ns_emu.cpp -- host SIMT emulation of the stream kernel (TEST PLUMBING, never shipped).
-// Compiles crispy_b200/csrc/ns_kernel.cuh with NS_HOST_EMU: one OS thread per CUDA thread,
+// ns_emu.cpp -- host SIMT emulation of the pipeline kernels (TEST PLUMBING, never shipped).
+// Compiles crispy_b200/csrc/ns_pipe.cuh with NS_HOST_EMU: one OS thread per CUDA thread,
 // pthread barriers for bar.sync / __syncthreads, a per-warp exchange buffer for shuffles.
-// Lets `pytest -m "not gpu"` run the kernel's exact control flow against the oracle.
+// Lets `pytest -m "not gpu"` run the kernels' exact control flow against the oracle.
+// Build with -ffp-contract=off: the kernels' exactness contract (ns_pipe.cuh) relies on it.
 #define NS_HOST_EMU 1
 #include <pthread.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
 #include "../../crispy_b200/csrc/ns_host.h"
-#include "../../crispy_b200/csrc/ns_kernel.cuh"
+#include "../../crispy_b200/csrc/ns_pipe.cuh"
 
 namespace ns {
 thread_local EmuThread g_emu;
 }
 
 namespace {
-template <int S>
-struct Launch {
-  ns::Params p;
-  ns::CtaSmem<S> *sm;
-  ns::EmuCta *cta;
-};
-template <int S>
 struct ThreadArg {
-  Launch<S> *l;
+  ns::EmuCta *cta;
   int tid;
+  const std::function<void()> *body;
 };
-template <int S>
 void *thread_main(void *a) {
-  ThreadArg<S> *ta = (ThreadArg<S> *)a;
-  ns::g_emu.cta = ta->l->cta;
+  ThreadArg *ta = (ThreadArg *)a;
+  ns::g_emu.cta = ta->cta;
   ns::g_emu.tid = ta->tid;
-  ns::stream_kernel_body<S>(ta->l->p, *ta->l->sm);
+  (*ta->body)();
   return nullptr;
 }
 
-template <int S>
-int run(const ns::Params &p) {
-  const int n_threads = S * ns::kGroupThreads;
-  const int n_ctas = (p.n_streams + S - 1) / S;
+// run `n_ctas` CTAs of `n_threads` threads one after another; `body(smem)` is the kernel body
+int launch(int n_ctas, int n_threads, size_t smem_bytes, const std::function<void(void *)> &kernel) {
+  std::vector<unsigned char> smem(smem_bytes + 64);
+  void *sm = (void *)(((uintptr_t)smem.data() + 63) & ~(uintptr_t)63);
   for (int c = 0; c < n_ctas; c++) {
     ns::EmuCta cta;
-    std::vector<ns::EmuWarp> warps(n_threads / 32);
+    std::vector<ns::EmuWarp> warps((n_threads + 31) / 32);
     cta.warps = warps.data();
     cta.cta_index = c;
+    cta.n_ctas = n_ctas;
     pthread_barrier_init(&cta.cta_bar, nullptr, n_threads);
     for (int i = 0; i < 16; i++) pthread_barrier_init(&cta.group_bar[i], nullptr, ns::kGroupThreads);
-    for (auto &w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
-    ns::CtaSmem<S> *sm = new ns::CtaSmem<S>();
-    memset((void *)sm, 0xCD, sizeof(*sm));  // shared memory is not zeroed on a GPU either
-    Launch<S> l{p, sm, &cta};
+    for (size_t w = 0; w < warps.size(); w++) {
+      const int in_warp = (n_threads - (int)w * 32) < 32 ? (n_threads - (int)w * 32) : 32;
+      pthread_barrier_init(&warps[w].bar, nullptr, in_warp);
+    }
+    memset(sm, 0xCD, smem_bytes);  // shared memory is not zeroed on a GPU either
+    const std::function<void()> body = [&]() { kernel(sm); };
     std::vector<pthread_t> th(n_threads);
-    std::vector<ThreadArg<S>> args(n_threads);
+    std::vector<ThreadArg> args(n_threads);
     pthread_attr_t attr;
     pthread_attr_init(&attr);
     pthread_attr_setstacksize(&attr, 256 * 1024);
     for (int t = 0; t < n_threads; t++) {
-      args[t] = ThreadArg<S>{&l, t};
-      if (pthread_create(&th[t], &attr, thread_main<S>, &args[t]) != 0) return -2;
+      args[t] = ThreadArg{&cta, t, &body};
+      if (pthread_create(&th[t], &attr, thread_main, &args[t]) != 0) return -2;
     }
     for (int t = 0; t < n_threads; t++) pthread_join(th[t], nullptr);
     pthread_attr_destroy(&attr);
-    delete sm;
     pthread_barrier_destroy(&cta.cta_bar);
     for (int i = 0; i < 16; i++) pthread_barrier_destroy(&cta.group_bar[i]);
     for (auto &w : warps) pthread_barrier_destroy(&w.bar);
   }
   return 0;
 }
+
+constexpr int kPitchRun = 8;
+constexpr int kPitchThreads = 64;  // any thread count gives the same result; fewer OS threads run faster
+constexpr int kRnnThreads = 64;
+constexpr int kScanWarps = 1;
 }  // namespace
 
 extern "C" {
@@ -78,9 +81,10 @@ int ns_emu_state_floats(void) { return ns::kStateFloats; }
 int ns_emu_dbg_floats(void) { return ns::kDbgFloats; }
 
 // in/out/app use the same strides the device path uses; state is in/out ([n_streams][kStateFloats]).
+// The call is cut into chunks of `chunk_cap` frames exactly as libcrispy_ns.so does.
 int ns_emu_process(const void *model_blob, size_t model_len, const void *in, void *out, float *vad,
                    const float *app, float *state, float *dbg, int n_streams, int n_frames,
-                   long long in_stride, long long out_stride, long long app_stride, int streams_per_cta,
+                   long long in_stride, long long out_stride, long long app_stride, int chunk_cap,
                    unsigned flags, float volume, int out_frame_offset) {
   ns::Model m;
   std::string err;
@@ -92,14 +96,22 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
   ns::pack_rnn(m, pk);
   static ns::Tables tab;
   ns::make_tables(tab);
+  if (chunk_cap < 1) chunk_cap = 8;
   ns::Params p;
   memset(&p, 0, sizeof(p));
+  const long long hp_stride = ns::kHist + (long long)chunk_cap * ns::kFrame;
+  std::vector<float> hp((size_t)n_streams * hp_stride, 0.f);
+  std::vector<uint32_t> tabw((size_t)n_streams * chunk_cap * ns::kTabWords, 0u);
+  std::vector<float> rec((size_t)n_streams * chunk_cap * ns::kRecFloats, 0.f);
   p.in = in;
   p.out = out;
   p.vad = vad;
   p.app = app;
-  p.state = state;
   p.dbg = dbg;
+  p.state = state;
+  p.hp = hp.data();
+  p.tab = tabw.data();
+  p.rec = rec.data();
   p.tables = &tab;
   p.rnn_hdr = &pk.hdr;
   p.rnn_words = pk.words.data();
@@ -108,16 +120,39 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
   p.out_stride = out_stride;
   p.vad_stride = n_frames;
   p.app_stride = app_stride;
+  p.hp_stride = hp_stride;
   p.n_streams = n_streams;
-  p.n_frames = n_frames;
+  p.n_frames_call = n_frames;
+  p.chunk_cap = chunk_cap;
   p.out_frame_offset = out_frame_offset;
   p.flags = flags;
   p.volume = volume;
-  switch (streams_per_cta) {
-    case 1: return run<1>(p);
-    case 2: return run<2>(p);
-    case 4: return run<4>(p);
-    default: return -3;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk_cap) {
+    const int nf = (n_frames - f0) < chunk_cap ? (n_frames - f0) : chunk_cap;
+    p.frame0 = f0;
+    p.n_frames = nf;
+    int rc = launch((n_streams + 31) / 32, 32, sizeof(ns::HpSmem),
+                    [&](void *sm) { ns::highpass_body(p, *(ns::HpSmem *)sm); });
+    if (rc) return rc;
+    const int runs = (nf + kPitchRun - 1) / kPitchRun;
+    rc = launch(n_streams * runs, kPitchThreads, sizeof(ns::PitchSmem<kPitchRun>), [&](void *sm) {
+      ns::pitch_body<kPitchRun, kPitchThreads>(p, *(ns::PitchSmem<kPitchRun> *)sm);
+    });
+    if (rc) return rc;
+    rc = launch((n_streams + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 16,
+                [&](void *) { ns::pitchscan_body(p, kScanWarps); });
+    if (rc) return rc;
+    const int spec_ctas = n_streams * nf < 4 ? n_streams * nf : 4;
+    rc = launch(spec_ctas, ns::kGroupThreads, sizeof(ns::SpecSmem),
+                [&](void *sm) { ns::spectrum_body(p, *(ns::SpecSmem *)sm); });
+    if (rc) return rc;
+    rc = launch((n_streams + ns::kRnnStreams - 1) / ns::kRnnStreams, kRnnThreads, sizeof(ns::RnnSmem),
+                [&](void *sm) { ns::rnn_body<kRnnThreads>(p, *(ns::RnnSmem *)sm); });
+    if (rc) return rc;
+    rc = launch(n_streams, ns::kGroupThreads, sizeof(ns::SpecSmem),
+                [&](void *sm) { ns::synthesis_body(p, *(ns::SpecSmem *)sm); });
+    if (rc) return rc;
   }
+  return 0;
 }
 }

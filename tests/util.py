@@ -20,9 +20,9 @@ TOL_VAD = 1e-3
 
 def build_emu() -> str:
     srcs = [os.path.join(EMU_DIR, "ns_emu.cpp"), os.path.join(CSRC, "ns_host.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("ns_kernel.cuh", "ns_common.h", "ns_simt.h", "ns_host.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("ns_pipe.cuh", "ns_common.h", "ns_simt.h", "ns_host.h")]
     if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread",
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
                                "-Wno-unknown-pragmas", "-o", EMU_LIB] + srcs)
     return EMU_LIB
 
@@ -41,7 +41,7 @@ def emu_lib():
     return _emu
 
 
-def emu_process(blob: bytes, x: np.ndarray, S: int = 1, flags: int = 0, volume: float = 1.0, state=None,
+def emu_process(blob: bytes, x: np.ndarray, chunk: int = 16, flags: int = 0, volume: float = 1.0, state=None,
                 out_dtype=np.float32, out_cols=None, app=None, out_frame_offset: int = 0):
     """Run the kernel body under the host SIMT emulation.  x: [n_streams, n_frames*480]."""
     L = emu_lib()
@@ -59,7 +59,7 @@ def emu_process(blob: bytes, x: np.ndarray, S: int = 1, flags: int = 0, volume: 
         app_p, app_stride = app.ctypes.data, app.shape[1]
     out_stride = out.shape[1] if not (flags & 8) else out.shape[1] // 2
     rc = L.ns_emu_process(blob, len(blob), x.ctypes.data, out.ctypes.data, vad.ctypes.data, app_p,
-                          state.ctypes.data, dbg.ctypes.data, ns, nf, n, out_stride, app_stride, S, flags,
+                          state.ctypes.data, dbg.ctypes.data, ns, nf, n, out_stride, app_stride, chunk, flags,
                           volume, out_frame_offset)
     assert rc == 0, f"ns_emu_process failed: {rc}"
     return out, vad, dbg, state
