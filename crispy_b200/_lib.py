@@ -26,6 +26,7 @@ SYMBOLS = [
     "crispy_ns_batch_load_state", "crispy_ns_batch_info", "crispy_ns_batch_destroy",
     "crispy_ns_host_alloc", "crispy_ns_host_free", "crispy_ns_linear_resample_count",
     "crispy_ns_linear_resample", "crispy_ns_wav_write_pcm16", "crispy_ns_wav_read_pcm16",
+    "crispy_ns_kernel_count", "crispy_ns_kernel_name", "crispy_ns_batch_profile", "crispy_ns_batch_profile_read",
 ]
 
 
@@ -73,6 +74,11 @@ def lib() -> C.CDLL:
     L.crispy_ns_batch_save_state.argtypes = [vp, vp, C.c_size_t]
     L.crispy_ns_batch_load_state.argtypes = [vp, vp, C.c_size_t]
     L.crispy_ns_batch_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64), C.POINTER(i64)]
+    L.crispy_ns_kernel_count.restype = C.c_int
+    L.crispy_ns_kernel_name.argtypes = [C.c_int]
+    L.crispy_ns_kernel_name.restype = C.c_char_p
+    L.crispy_ns_batch_profile.argtypes = [vp, C.c_int]
+    L.crispy_ns_batch_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.c_int]
     L.crispy_ns_batch_destroy.argtypes = [vp]
     L.crispy_ns_batch_destroy.restype = None
     L.crispy_ns_host_alloc.argtypes = [vpp, C.c_size_t]

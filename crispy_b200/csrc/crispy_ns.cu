@@ -19,10 +19,9 @@
 // ------------------------------------------------------------------------------------------------
 constexpr int kPitchRun = 8;        // frames of one stream per pitch CTA
 constexpr int kPitchThreads = 320;  // 37 lag-quads x 8 frames = 296 lanes in the coarse search
-constexpr int kRnnThreads = 256;
 constexpr int kScanWarps = 4;
 
-__global__ void __launch_bounds__(32) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
+__global__ void __launch_bounds__(ns::kHpThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
   __shared__ ns::HpSmem sm;
   ns::highpass_body(p, sm);
 }
@@ -37,9 +36,9 @@ __global__ void __launch_bounds__(ns::kGroupThreads) ns_spectrum_kernel(const __
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ns::spectrum_body(p, *reinterpret_cast<ns::SpecSmem *>(smem_raw));
 }
-__global__ void __launch_bounds__(kRnnThreads) ns_rnn_kernel(const __grid_constant__ ns::Params p) {
+__global__ void __launch_bounds__(ns::kRnnThreads, 1) ns_rnn_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ns::rnn_body<kRnnThreads>(p, *reinterpret_cast<ns::RnnSmem *>(smem_raw));
+  ns::rnn_body<ns::kRnnThreads>(p, *reinterpret_cast<ns::RnnSmem *>(smem_raw));
 }
 __global__ void __launch_bounds__(ns::kGroupThreads) ns_synthesis_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -100,10 +99,19 @@ struct crispy_ns_batch {
   float *d_hp[kSlots] = {nullptr, nullptr, nullptr};
   uint32_t *d_tab[kSlots] = {nullptr, nullptr, nullptr};
   float *d_rec[kSlots] = {nullptr, nullptr, nullptr};
+  ns::cf *d_spec[kSlots] = {nullptr, nullptr, nullptr};
   cudaStream_t s_hp = nullptr, s_an = nullptr, s_syn = nullptr;
   cudaEvent_t e_start = nullptr;
   cudaEvent_t e_hp[kSlots] = {nullptr, nullptr, nullptr}, e_an[kSlots] = {nullptr, nullptr, nullptr},
               e_syn[kSlots] = {nullptr, nullptr, nullptr};
+  // optional per-kernel timing (crispy_ns_batch_profile): CUDA events around every launch, each on
+  // the stream the kernel is launched on
+  bool prof_on = false;
+  struct ProfRec {
+    cudaEvent_t a, b;
+    int kernel;
+  };
+  std::vector<ProfRec> prof;
   // host-pointer path
   cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
   cudaEvent_t e_in[2] = {nullptr, nullptr}, e_k[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
@@ -131,7 +139,7 @@ struct crispy_ns_state {
 static int default_chunk_cap(int n_streams) {
   const char *env = getenv("CRISPY_NS_CHUNK_FRAMES");
   if (env && atoi(env) > 0) return atoi(env) > 4096 ? 4096 : atoi(env);
-  const long long per_frame = (long long)n_streams * (ns::kFrame * 4 + ns::kTabWords * 4 + ns::kRecFloats * 4);
+  const long long per_frame = (long long)n_streams * (ns::kFrame * 4 + ns::kTabWords * 4 + ns::kRecFloats * 4 + 2 * ns::kSpecStride * 8);
   long long cap = (64ll << 20) / per_frame;
   cap = (cap / kPitchRun) * kPitchRun;
   if (cap < kPitchRun) cap = kPitchRun;
@@ -160,6 +168,28 @@ static cudaError_t configure_kernels(int dev) {
     e = cudaFuncSetAttribute(ns_rnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::RnnSmem));
   if (e == cudaSuccess) configured[dev] = true;
   return e;
+}
+
+static cudaError_t prof_begin(crispy_ns_batch *b, int kernel, cudaStream_t s) {
+  if (!b->prof_on) return cudaSuccess;
+  crispy_ns_batch::ProfRec r;
+  r.kernel = kernel;
+  cudaError_t e = cudaEventCreate(&r.a);
+  if (e == cudaSuccess) e = cudaEventCreate(&r.b);
+  if (e == cudaSuccess) e = cudaEventRecord(r.a, s);
+  if (e == cudaSuccess) b->prof.push_back(r);
+  return e;
+}
+static cudaError_t prof_end(crispy_ns_batch *b, cudaStream_t s) {
+  if (!b->prof_on) return cudaSuccess;
+  return cudaEventRecord(b->prof.back().b, s);
+}
+static void prof_clear(crispy_ns_batch *b) {
+  for (auto &r : b->prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  b->prof.clear();
 }
 
 static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad, const float *d_app,
@@ -204,26 +234,42 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
     p.hp = b->d_hp[slot];
     p.tab = b->d_tab[slot];
     p.rec = b->d_rec[slot];
+    p.spec = b->d_spec[slot];
+    p.synth_sel = (int)(b->chunks_done & 1);
     if (b->chunks_done >= kSlots) NS_CUDA(cudaStreamWaitEvent(b->s_hp, b->e_syn[slot], 0));
-    ns_highpass_kernel<<<(n + 31) / 32, 32, 0, b->s_hp>>>(p);
+    NS_CUDA(prof_begin(b, 0, b->s_hp));
+    ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, 0, b->s_hp>>>(p);
     NS_CUDA(cudaGetLastError());
+    NS_CUDA(prof_end(b, b->s_hp));
     NS_CUDA(cudaEventRecord(b->e_hp[slot], b->s_hp));
     NS_CUDA(cudaStreamWaitEvent(b->s_an, b->e_hp[slot], 0));
     const int runs = (nf + kPitchRun - 1) / kPitchRun;
+    NS_CUDA(prof_begin(b, 1, b->s_an));
     ns_pitch_kernel<<<n * runs, kPitchThreads, sizeof(ns::PitchSmem<kPitchRun>), b->s_an>>>(p);
     NS_CUDA(cudaGetLastError());
+    NS_CUDA(prof_end(b, b->s_an));
+    NS_CUDA(prof_begin(b, 2, b->s_an));
     ns_pitchscan_kernel<<<(n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, b->s_an>>>(p);
     NS_CUDA(cudaGetLastError());
+    NS_CUDA(prof_end(b, b->s_an));
     long long spec_ctas = (long long)n * nf;
     if (spec_ctas > (long long)b->n_sms * 8) spec_ctas = (long long)b->n_sms * 8;
+    NS_CUDA(prof_begin(b, 3, b->s_an));
     ns_spectrum_kernel<<<(int)spec_ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), b->s_an>>>(p);
     NS_CUDA(cudaGetLastError());
+    NS_CUDA(prof_end(b, b->s_an));
     NS_CUDA(cudaEventRecord(b->e_an[slot], b->s_an));
     NS_CUDA(cudaStreamWaitEvent(b->s_syn, b->e_an[slot], 0));
-    ns_rnn_kernel<<<(n + ns::kRnnStreams - 1) / ns::kRnnStreams, kRnnThreads, sizeof(ns::RnnSmem), b->s_syn>>>(p);
+    NS_CUDA(prof_begin(b, 4, b->s_syn));
+    ns_rnn_kernel<<<(n + ns::kRnnStreams - 1) / ns::kRnnStreams, ns::kRnnThreads, sizeof(ns::RnnSmem), b->s_syn>>>(p);
     NS_CUDA(cudaGetLastError());
-    ns_synthesis_kernel<<<n, ns::kGroupThreads, sizeof(ns::SpecSmem), b->s_syn>>>(p);
+    NS_CUDA(prof_end(b, b->s_syn));
+    NS_CUDA(prof_begin(b, 5, b->s_syn));
+    long long syn_ctas = (long long)n * ((nf + ns::kSynRun - 1) / ns::kSynRun);
+    if (syn_ctas > (long long)b->n_sms * 8) syn_ctas = (long long)b->n_sms * 8;
+    ns_synthesis_kernel<<<(int)syn_ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), b->s_syn>>>(p);
     NS_CUDA(cudaGetLastError());
+    NS_CUDA(prof_end(b, b->s_syn));
     NS_CUDA(cudaEventRecord(b->e_syn[slot], b->s_syn));
     b->launches += 6;
     b->chunks_done += 1;
@@ -301,6 +347,7 @@ static int default_model(ns::Model &m) {
 void crispy_ns_batch_destroy(crispy_ns_batch *b) {
   if (!b) return;
   cudaSetDevice(b->device);
+  prof_clear(b);
   cudaFree(b->d_tables);
   cudaFree(b->d_hdr);
   cudaFree(b->d_words);
@@ -310,6 +357,7 @@ void crispy_ns_batch_destroy(crispy_ns_batch *b) {
     cudaFree(b->d_hp[i]);
     cudaFree(b->d_tab[i]);
     cudaFree(b->d_rec[i]);
+    cudaFree(b->d_spec[i]);
     if (b->e_hp[i]) cudaEventDestroy(b->e_hp[i]);
     if (b->e_an[i]) cudaEventDestroy(b->e_an[i]);
     if (b->e_syn[i]) cudaEventDestroy(b->e_syn[i]);
@@ -378,6 +426,7 @@ int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_strea
     e = cudaMalloc((void **)&b->d_hp[i], (size_t)n_streams * (ns::kHist + (size_t)b->chunk_cap * ns::kFrame) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_tab[i], nf * ns::kTabWords * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_rec[i], nf * ns::kRecFloats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_spec[i], nf * 2 * ns::kSpecStride * sizeof(ns::cf));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_hp[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_an[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_syn[i], cudaEventDisableTiming);
@@ -543,7 +592,7 @@ int crispy_ns_batch_save_state(crispy_ns_batch *b, void *buf, size_t len) {
   if (!b || !buf || len < crispy_ns_batch_state_size(b)) return fail(CRISPY_NS_EINVAL, "save_state: bad argument");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(cudaDeviceSynchronize());
-  int64_t hdr[2] = {b->n_streams, b->frames_done};
+  int64_t hdr[2] = {b->n_streams | (b->chunks_done & 1) << 40, b->frames_done};
   memcpy(buf, hdr, 16);
   NS_CUDA(cudaMemcpy((char *)buf + 16, b->d_state, len - 16 < crispy_ns_batch_state_size(b) - 16 ? len - 16 : crispy_ns_batch_state_size(b) - 16,
                      cudaMemcpyDeviceToHost));
@@ -553,11 +602,14 @@ int crispy_ns_batch_load_state(crispy_ns_batch *b, const void *buf, size_t len) 
   if (!b || !buf || len < crispy_ns_batch_state_size(b)) return fail(CRISPY_NS_EINVAL, "load_state: bad argument");
   int64_t hdr[2];
   memcpy(hdr, buf, 16);
+  const int64_t sel = (hdr[0] >> 40) & 1;
+  hdr[0] &= ((int64_t)1 << 40) - 1;
   if (hdr[0] != b->n_streams) return fail(CRISPY_NS_EINVAL, "load_state: stream count mismatch");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(cudaDeviceSynchronize());
   NS_CUDA(cudaMemcpy(b->d_state, (const char *)buf + 16, crispy_ns_batch_state_size(b) - 16, cudaMemcpyHostToDevice));
   b->frames_done = hdr[1];
+  if ((b->chunks_done & 1) != sel) b->chunks_done += 1;  // synthesis_mem double buffer parity (ns_common.h kStSynth)
   return CRISPY_NS_OK;
 }
 int crispy_ns_batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_ctas, int64_t *launches,
@@ -567,6 +619,38 @@ int crispy_ns_batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_
   if (n_ctas) *n_ctas = b->chunk_cap;
   if (launches) *launches = b->launches;
   if (frames_done) *frames_done = b->frames_done;
+  return CRISPY_NS_OK;
+}
+
+int crispy_ns_kernel_count(void) { return 6; }
+const char *crispy_ns_kernel_name(int k) {
+  static const char *names[6] = {"ns_highpass_kernel", "ns_pitch_kernel", "ns_pitchscan_kernel",
+                                 "ns_spectrum_kernel", "ns_rnn_kernel", "ns_synthesis_kernel"};
+  return (k >= 0 && k < 6) ? names[k] : "";
+}
+int crispy_ns_batch_profile(crispy_ns_batch *b, int enable) {
+  if (!b) return fail(CRISPY_NS_EINVAL, "batch_profile: null handle");
+  NS_CUDA(cudaSetDevice(b->device));
+  NS_CUDA(cudaDeviceSynchronize());
+  prof_clear(b);
+  b->prof_on = enable != 0;
+  return CRISPY_NS_OK;
+}
+int crispy_ns_batch_profile_read(crispy_ns_batch *b, double *ms_total, int64_t *n_launches, int n_kernels) {
+  if (!b || !ms_total || !n_launches || n_kernels < 6) return fail(CRISPY_NS_EINVAL, "batch_profile_read: bad argument");
+  NS_CUDA(cudaSetDevice(b->device));
+  NS_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < n_kernels; k++) {
+    ms_total[k] = 0.0;
+    n_launches[k] = 0;
+  }
+  for (auto &r : b->prof) {
+    float ms = 0.f;
+    NS_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_total[r.kernel] += ms;
+    n_launches[r.kernel] += 1;
+  }
+  prof_clear(b);
   return CRISPY_NS_OK;
 }
 

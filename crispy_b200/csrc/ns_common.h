@@ -26,6 +26,7 @@ constexpr int kGroupThreads = 128;   // threads cooperating on one frame's spect
 //   hp  : the high-passed signal, kHist samples of history + chunk*480 new samples (f32)
 //   tab : per frame, the pitch candidate table remove_doubling's serial decision walks (kTabWords)
 //   rec : per frame, the small record passed between phases (kRecFloats)
+//   spec: per frame, the spectra X and P (K3 -> K5)
 constexpr int kHist = 1440;          // >= 1248 (pitch_buf history) and a multiple of 480
 constexpr int kLpLen = 864;          // pitch_buf downsampled by 2
 constexpr int kLpStride = 872;       // padded row of the per-frame downsampled buffers
@@ -34,7 +35,7 @@ constexpr int kTabWords = 48;
 //   word 0      : T0 | n_k << 16      (n_k = candidates present, k = 1..n_k)
 //   word 1      : unused
 //   word 2+3(k-1): T_k | pitch_index_k << 16 ; g_k (f32 bits) ; pitch_gain_k (f32 bits)
-constexpr int kRecFloats = 128;
+constexpr int kRecFloats = 144;
 constexpr int kRecPitchIndex = 0;    // int bits
 constexpr int kRecSilence = 1;       // int bits
 constexpr int kRecPitchGain = 2;
@@ -44,7 +45,10 @@ constexpr int kRecCeps = 26;         // 22 (DCT of log band energy, offsets appl
 constexpr int kRecTail = 48;         // 7: features[34..40]
 constexpr int kRecGRaw = 56;         // 22: band gains as the RNN emits them (the pitch filter uses these)
 constexpr int kRecG = 78;            // 22: band gains after the 0.6*lastg smoothing
-static_assert(kRecG + kBands <= kRecFloats, "record overflow");
+constexpr int kRecEx = 100;          // 22: band energy of the frame
+constexpr int kRecEp = 122;          // 22: band energy of the pitch-lagged window
+static_assert(kRecEp + kBands <= kRecFloats, "record overflow");
+constexpr int kSpecStride = 482;     // complex bins per stored spectrum (481 used); per frame: X then P
 
 struct alignas(8) cf {
   float x, y;
@@ -56,8 +60,9 @@ struct alignas(16) f4 {
 // ---- per-stream persistent state (the fields of nnnoiseless::DenoiseState), one block of
 // kStateFloats f32 per stream in HBM.
 constexpr int kStHist = 0;                        // 1440: last high-passed samples (pitch_buf + analysis_mem)
-constexpr int kStSynth = kStHist + kHist;         // 480 : synthesis_mem
-constexpr int kStCeps = kStSynth + kFrame;        // 176 : cepstral_mem[8][22]
+constexpr int kStSynth = kStHist + kHist;         // 2x480: synthesis_mem, double buffered: a chunk reads copy
+                                                  //        synth_sel and writes the other (its runs are concurrent)
+constexpr int kStCeps = kStSynth + 2 * kFrame;    // 176 : cepstral_mem[8][22]
 constexpr int kStLastG = kStCeps + 176;           // 22  : lastg
 constexpr int kStHVad = kStLastG + 22;            // 24  : vad_gru_state
 constexpr int kStHNoise = kStHVad + 24;           // 48  : noise_gru_state
@@ -67,7 +72,7 @@ constexpr int kStLastGain = kStHp + 2;            // 1
 constexpr int kStLastPeriod = kStLastGain + 1;    // 1 (int bits)
 constexpr int kStMemId = kStLastPeriod + 1;       // 1 (int bits)
 constexpr int kStFrameCount = kStMemId + 1;       // 1 (int bits, informational)
-constexpr int kStateFloats = 2304;                // padded to a multiple of 32 floats
+constexpr int kStateFloats = 2784;                // padded to a multiple of 32 floats
 static_assert(kStFrameCount + 1 <= kStateFloats, "state layout overflow");
 
 // ---- per-frame debug taps (optional), mirrors oracle rno_debug
@@ -94,22 +99,37 @@ struct Tables {
   int32_t eband[24];     // band edges in bins (eband5ms * 4), 22 used
 };
 
-// ---- RNN weights repacked for the kernel: per job, uint32 words hold four consecutive input rows
-// of one output column (int8 each); words are stored [k4][n_out] so a warp reads them coalesced.
-constexpr int kNumJobs = 9;
-constexpr int kMaxSegs = 4;
-enum Seg : int32_t { kSegFeat = 0, kSegDense = 1, kSegHVad = 2, kSegHNoise = 3, kSegHDen = 4, kSegRH = 5 };
+// ---- RNN weights repacked for the recurrent-core kernel (K4).
+// Activations of the 8 streams of a CTA live in shared memory as two f32 arrays of rows [k][8]:
+//   A: dense(24) | vad_gru_state(24) | features(42) | noise_gru_state(48) | denoise_gru_state(96)
+//   R: r*h of the three GRUs: vad(24) | noise(48) | denoise(96)
+// so that every matrix-vector job reads one contiguous range of A plus, for the candidate-gate jobs,
+// one contiguous range of R.  A job with N outputs is worked by cp = ceil(N/2) column pairs x ksplit
+// slices of its K inputs; thread tj = ks*cp + pair keeps 2 x 8 accumulators and reads its weights
+// as packed bf16 pairs (int8 values are exact in bf16) from words[w_off + i*(cp*ksplit) + tj].
+constexpr int kRnnThreads = 256;
+constexpr int kActDense = 0, kActHVad = 24, kActFeat = 48, kActHNoise = 90, kActHDen = 138, kActRows = 234;
+constexpr int kRhVad = 0, kRhNoise = 24, kRhDen = 72, kRhRows = 168;
+constexpr int kNumJobs = 8;
+enum JobKind : int32_t { kJobDense = 0, kJobZR = 1, kJobC = 2 };
 struct JobDesc {
-  int32_t n_out;
-  int32_t activation;     // 0 tanh, 1 sigmoid, 2 relu (of the layer; ZR jobs are always sigmoid)
-  int32_t w_off;          // offset (in uint32 words) into RnnWeights::words
-  int32_t b_off;          // offset into RnnWeights::bias
-  int32_t n_segs;
-  int32_t seg_id[kMaxSegs];
-  int32_t seg_k4[kMaxSegs];  // ceil(len/4)
+  int32_t n_out;       // N
+  int32_t activation;  // 0 tanh, 1 sigmoid, 2 relu (of the layer; ZR jobs are always sigmoid)
+  int32_t kind;        // JobKind
+  int32_t cp, ksplit, len;  // column pairs, K slices, slice length
+  int32_t k_total;     // K = len1 + len2
+  int32_t off1, len1;  // rows of A
+  int32_t off2, len2;  // rows of R (candidate-gate jobs), len2 == 0 otherwise
+  int32_t w_off;       // offset (uint32 words) into words
+  int32_t b_off;       // offset into bias
+  int32_t out_off;     // Dense: row of A (or -1: gains); ZR / C: row of A holding this GRU's state
+  int32_t rh_off;      // ZR: row of R receiving r*h
+  int32_t pad;
 };
 struct RnnHeader {
   JobDesc jobs[kNumJobs];
+  int32_t vad_w_off;   // vad_output: 24 f32 weights + bias at bias[vad_w_off .. +25)
+  int32_t vad_activation;
   int32_t n_words;
   int32_t n_bias;
 };
@@ -134,6 +154,7 @@ struct Params {
   float *hp;              // [n_streams][hp_stride]
   uint32_t *tab;          // [n_streams][chunk_cap][kTabWords]
   float *rec;             // [n_streams][chunk_cap][kRecFloats]
+  cf *spec;               // [n_streams][chunk_cap][2][kSpecStride]: X and P of every frame
   const Tables *tables;
   const RnnHeader *rnn_hdr;
   const uint32_t *rnn_words;
@@ -148,6 +169,7 @@ struct Params {
   int frame0;             // index of the chunk's first frame within the call
   int n_frames_call;      // frames in the whole call (debug tap geometry)
   int chunk_cap;
+  int synth_sel;          // which synthesis_mem copy this chunk reads (chunk counter & 1)
   int out_frame_offset;   // output frame t is stored at frame slot t + out_frame_offset (skipped if < 0)
   uint32_t flags;
   float volume;

@@ -256,36 +256,53 @@ bool model_from_bytes(Model &m, const void *blob, size_t len, std::string &err) 
 }
 
 // ---- repacking -----------------------------------------------------------------------------------
-struct SegSrc {
-  int seg_id;
-  int len;
-  std::function<int8_t(int row, int col)> w;
+// One matrix-vector job: rows = its K inputs in the order of the kernel's activation layout
+// (ns_common.h), each row naming where the weight of (row, col) lives in the model.
+struct RowSrc {
+  std::function<int8_t(int col)> w;
 };
 
-static void add_job(PackedRnn &out, int job, int n_out, int act, const std::vector<SegSrc> &segs,
+static uint32_t bf16_bits(int v) {  // int8 value -> bf16 bit pattern (exact)
+  float f = (float)v;
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u >> 16;
+}
+
+static void add_job(PackedRnn &out, int job, int kind, int n_out, int act, int off1, int len1, int off2,
+                    int len2, int out_off, int rh_off, const std::vector<RowSrc> &rows,
                     const std::function<int8_t(int col)> &bias) {
   JobDesc &jd = out.hdr.jobs[job];
   memset(&jd, 0, sizeof(jd));
+  const int K = (int)rows.size();
   jd.n_out = n_out;
   jd.activation = act;
+  jd.kind = kind;
+  jd.cp = (n_out + 1) / 2;
+  jd.ksplit = kRnnThreads / jd.cp;
+  if (jd.ksplit > K) jd.ksplit = K;
+  jd.len = (K + jd.ksplit - 1) / jd.ksplit;
+  jd.k_total = K;
+  jd.off1 = off1;
+  jd.len1 = len1;
+  jd.off2 = off2;
+  jd.len2 = len2;
   jd.w_off = (int32_t)out.words.size();
   jd.b_off = (int32_t)out.bias.size();
-  jd.n_segs = (int32_t)segs.size();
-  for (size_t s = 0; s < segs.size(); s++) {
-    const int k4 = (segs[s].len + 3) / 4;
-    jd.seg_id[s] = segs[s].seg_id;
-    jd.seg_k4[s] = k4;
-    for (int kk = 0; kk < k4; kk++)
-      for (int col = 0; col < n_out; col++) {
-        uint32_t word = 0;
-        for (int b = 0; b < 4; b++) {
-          const int row = kk * 4 + b;
-          const int8_t v = row < segs[s].len ? segs[s].w(row, col) : (int8_t)0;
-          word |= (uint32_t)(uint8_t)v << (8 * b);
-        }
-        out.words.push_back(word);
+  jd.out_off = out_off;
+  jd.rh_off = rh_off;
+  const int stride = jd.cp * jd.ksplit;
+  for (int i = 0; i < jd.len; i++)
+    for (int tj = 0; tj < stride; tj++) {
+      const int pair = tj % jd.cp, ks = tj / jd.cp, k = ks * jd.len + i;
+      uint32_t lo = 0, hi = 0;
+      if (k < K) {
+        const int c0 = 2 * pair, c1 = 2 * pair + 1;
+        lo = bf16_bits(rows[k].w(c0));
+        if (c1 < n_out) hi = bf16_bits(rows[k].w(c1));
       }
-  }
+      out.words.push_back(lo | (hi << 16));
+    }
   for (int col = 0; col < n_out; col++) out.bias.push_back((float)bias(col));
 }
 
@@ -295,39 +312,66 @@ void pack_rnn(const Model &m, PackedRnn &out) {
   memset(&out.hdr, 0, sizeof(out.hdr));
   const DenseLayer &d0 = m.input_dense, &dv = m.vad_output, &dg = m.denoise_output;
   const GruLayer &gv = m.vad_gru, &gn = m.noise_gru, &gd = m.denoise_gru;
-  auto gi = [](const GruLayer &g, int row0, int col0) {
+  // weight of input row `row` / recurrent row `row` of a GRU at gate column col0 + col
+  auto gi = [](const GruLayer &g, int row, int col0) {
     const int st = 3 * g.nb_neurons;
-    return [&g, row0, col0, st](int row, int col) { return g.input_weights[(size_t)(row0 + row) * st + col0 + col]; };
+    return RowSrc{[&g, row, col0, st](int col) { return g.input_weights[(size_t)row * st + col0 + col]; }};
   };
-  auto gr = [](const GruLayer &g, int col0) {
+  auto gr = [](const GruLayer &g, int row, int col0) {
     const int st = 3 * g.nb_neurons;
-    return [&g, col0, st](int row, int col) { return g.recurrent_weights[(size_t)row * st + col0 + col]; };
+    return RowSrc{[&g, row, col0, st](int col) { return g.recurrent_weights[(size_t)row * st + col0 + col]; }};
   };
   auto gb = [](const GruLayer &g, int col0) { return [&g, col0](int col) { return g.bias[col0 + col]; }; };
-  auto dw = [](const DenseLayer &d) {
-    return [&d](int row, int col) { return d.weights[(size_t)row * d.nb_neurons + col]; };
+  auto dw = [](const DenseLayer &d, int row) {
+    return RowSrc{[&d, row](int col) { return d.weights[(size_t)row * d.nb_neurons + col]; }};
   };
   auto db = [](const DenseLayer &d) { return [&d](int col) { return d.bias[col]; }; };
+  std::vector<RowSrc> rows;
 
-  add_job(out, 0, 24, d0.activation, {{kSegFeat, 42, dw(d0)}}, db(d0));
-  add_job(out, 1, 48, 1, {{kSegDense, 24, gi(gv, 0, 0)}, {kSegHVad, 24, gr(gv, 0)}}, gb(gv, 0));
-  add_job(out, 2, 24, gv.activation, {{kSegDense, 24, gi(gv, 0, 48)}, {kSegRH, 24, gr(gv, 48)}}, gb(gv, 48));
-  add_job(out, 3, 1, dv.activation, {{kSegHVad, 24, dw(dv)}}, db(dv));
-  // noise_gru input = [dense_out(24) | vad_gru_state(24) | features(42)]
-  add_job(out, 4, 96, 1,
-          {{kSegDense, 24, gi(gn, 0, 0)}, {kSegHVad, 24, gi(gn, 24, 0)}, {kSegFeat, 42, gi(gn, 48, 0)}, {kSegHNoise, 48, gr(gn, 0)}},
-          gb(gn, 0));
-  add_job(out, 5, 48, gn.activation,
-          {{kSegDense, 24, gi(gn, 0, 96)}, {kSegHVad, 24, gi(gn, 24, 96)}, {kSegFeat, 42, gi(gn, 48, 96)}, {kSegRH, 48, gr(gn, 96)}},
-          gb(gn, 96));
-  // denoise_gru input = [vad_gru_state(24) | noise_gru_state(48) | features(42)]
-  add_job(out, 6, 192, 1,
-          {{kSegHVad, 24, gi(gd, 0, 0)}, {kSegHNoise, 48, gi(gd, 24, 0)}, {kSegFeat, 42, gi(gd, 72, 0)}, {kSegHDen, 96, gr(gd, 0)}},
-          gb(gd, 0));
-  add_job(out, 7, 96, gd.activation,
-          {{kSegHVad, 24, gi(gd, 0, 192)}, {kSegHNoise, 48, gi(gd, 24, 192)}, {kSegFeat, 42, gi(gd, 72, 192)}, {kSegRH, 96, gr(gd, 192)}},
-          gb(gd, 192));
-  add_job(out, 8, 22, dg.activation, {{kSegHDen, 96, dw(dg)}}, db(dg));
+  // job 0: input_dense, reads features = A[48:90)
+  rows.clear();
+  for (int k = 0; k < 42; k++) rows.push_back(dw(d0, k));
+  add_job(out, 0, kJobDense, 24, d0.activation, kActFeat, 42, 0, 0, kActDense, 0, rows, db(d0));
+  // vad_gru: input = dense(24); z,r read A[0:48) = dense | vad state
+  rows.clear();
+  for (int k = 0; k < 24; k++) rows.push_back(gi(gv, k, 0));
+  for (int k = 0; k < 24; k++) rows.push_back(gr(gv, k, 0));
+  add_job(out, 1, kJobZR, 48, 1, kActDense, 48, 0, 0, kActHVad, kRhVad, rows, gb(gv, 0));
+  rows.clear();
+  for (int k = 0; k < 24; k++) rows.push_back(gi(gv, k, 48));
+  for (int k = 0; k < 24; k++) rows.push_back(gr(gv, k, 48));
+  add_job(out, 2, kJobC, 24, gv.activation, kActDense, 24, kRhVad, 24, kActHVad, 0, rows, gb(gv, 48));
+  // noise_gru: input = [dense(24) | vad state(24) | features(42)] = A[0:90), recurrent = A[90:138)
+  rows.clear();
+  for (int k = 0; k < 90; k++) rows.push_back(gi(gn, k, 0));
+  for (int k = 0; k < 48; k++) rows.push_back(gr(gn, k, 0));
+  add_job(out, 3, kJobZR, 96, 1, kActDense, 138, 0, 0, kActHNoise, kRhNoise, rows, gb(gn, 0));
+  rows.clear();
+  for (int k = 0; k < 90; k++) rows.push_back(gi(gn, k, 96));
+  for (int k = 0; k < 48; k++) rows.push_back(gr(gn, k, 96));
+  add_job(out, 4, kJobC, 48, gn.activation, kActDense, 90, kRhNoise, 48, kActHNoise, 0, rows, gb(gn, 96));
+  // denoise_gru: input = [vad state(24) | noise state(48) | features(42)]; in A's order the rows are
+  // vad state (input 0..23), features (input 72..113), noise state (input 24..71), then the recurrent rows
+  auto den_rows = [&](int col0) {
+    rows.clear();
+    for (int k = 0; k < 24; k++) rows.push_back(gi(gd, k, col0));
+    for (int k = 0; k < 42; k++) rows.push_back(gi(gd, 72 + k, col0));
+    for (int k = 0; k < 48; k++) rows.push_back(gi(gd, 24 + k, col0));
+    for (int k = 0; k < 96; k++) rows.push_back(gr(gd, k, col0));
+  };
+  den_rows(0);
+  add_job(out, 5, kJobZR, 192, 1, kActHVad, 210, 0, 0, kActHDen, kRhDen, rows, gb(gd, 0));
+  den_rows(192);
+  add_job(out, 6, kJobC, 96, gd.activation, kActHVad, 114, kRhDen, 96, kActHDen, 0, rows, gb(gd, 192));
+  // denoise_output reads the denoise state A[138:234)
+  rows.clear();
+  for (int k = 0; k < 96; k++) rows.push_back(dw(dg, k));
+  add_job(out, 7, kJobDense, 22, dg.activation, kActHDen, 96, 0, 0, -1, 0, rows, db(dg));
+  // vad_output: 24 weights + bias as f32 (one lane per stream works it)
+  out.hdr.vad_w_off = (int32_t)out.bias.size();
+  out.hdr.vad_activation = dv.activation;
+  for (int k = 0; k < 24; k++) out.bias.push_back((float)dv.weights[k]);
+  out.bias.push_back((float)dv.bias[0]);
   out.hdr.n_words = (int32_t)out.words.size();
   out.hdr.n_bias = (int32_t)out.bias.size();
 }

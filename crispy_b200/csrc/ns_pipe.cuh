@@ -34,8 +34,14 @@ NS_DEV f4 ld4(const float *p) { return *reinterpret_cast<const f4 *>(p); }
 // rounding of the state makes the recursion non-linear, so it is run serially, one lane per stream;
 // a warp moves 32-sample x 32-stream tiles through shared memory so HBM sees 128-byte rows.
 // =================================================================================================
+// Roles inside the 128-thread CTA (32 streams): warp 0 runs the recursion on the tile in ring slot
+// n%4; warp 1 loads tile n+3 from HBM into registers and parks tile n+1 in the ring (two register
+// sets, so a load has two iterations to land); warp 2 writes tile n-1 to the hp workspace (and the
+// last kHist samples to the state block); warp 3 copies the stream history into the workspace
+// front.  One __syncthreads per 32-sample tile.
+constexpr int kHpThreads = 128;
 struct HpSmem {
-  float tile[32][33];
+  float tile[4][32][33];
 };
 
 NS_DEV float load_sample(const Params &p, int stream, long long idx) {
@@ -45,55 +51,103 @@ NS_DEV float load_sample(const Params &p, int stream, long long idx) {
   return (p.flags & kFlagUnitScale) ? v * 32768.0f : v;  // audio.rs:264
 }
 
+NS_DEV void hp_load_tile(const Params &p, int s0, int nrows, long long idx, float (&regs)[32]) {
+#pragma unroll
+  for (int r = 0; r < 32; r++) regs[r] = (r < nrows) ? load_sample(p, s0 + r, idx) : 0.f;
+}
+
 NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
-  const int lane = Simt::tid() & 31;
+  const int tid = Simt::tid();
+  const int lane = tid & 31, warp = tid >> 5;
   const int s0 = Simt::cta() * 32;
   const int nrows = (p.n_streams - s0) < 32 ? (p.n_streams - s0) : 32;
-  for (int r = 0; r < nrows; r++) {  // history -> front of the slot row
-    const float *src = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
-    float *dst = p.hp + (long long)(s0 + r) * p.hp_stride;
-    for (int i = lane; i < kHist; i += 32) dst[i] = src[i];
-  }
+  const int nsamp = p.n_frames * kFrame;
+  const int ntiles = nsamp / 32;
+  const long long in0 = (long long)p.frame0 * kFrame;
   const bool valid = lane < nrows;
   float *st = p.state + (long long)(s0 + (valid ? lane : 0)) * kStateFloats;
-  float m0 = valid ? st[kStHp] : 0.f, m1 = valid ? st[kStHp + 1] : 0.f;
-  const double a0 = (double)-1.99599f, a1 = (double)0.99600f;
-  const int nsamp = p.n_frames * kFrame;
-  const long long in0 = (long long)p.frame0 * kFrame;
-  float nxt[32];
+  float m0 = 0.f, m1 = 0.f;
+  float regs[2][32];
+  if (warp == 0 && valid) {
+    m0 = st[kStHp];
+    m1 = st[kStHp + 1];
+  } else if (warp == 1) {  // prologue: tile 0 straight into the ring, tiles 1 and 2 in flight
+    hp_load_tile(p, s0, nrows, in0 + lane, regs[0]);
 #pragma unroll
-  for (int r = 0; r < 32; r++) nxt[r] = (r < nrows) ? load_sample(p, s0 + r, in0 + lane) : 0.f;
-  for (int base = 0; base < nsamp; base += 32) {
+    for (int r = 0; r < 32; r++) sm.tile[0][r][lane] = regs[0][r];
+    if (ntiles > 1) hp_load_tile(p, s0, nrows, in0 + 32 + lane, regs[1]);
+    if (ntiles > 2) hp_load_tile(p, s0, nrows, in0 + 64 + lane, regs[0]);
+  } else if (warp == 3) {  // history -> front of the workspace rows
+    for (int r = 0; r < nrows; r++) {
+      const float *__restrict__ src = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
+      float *__restrict__ dst = p.hp + (long long)(s0 + r) * p.hp_stride;
+      float v[15];
+      for (int i0 = 0; i0 < kHist; i0 += 15 * 32) {
 #pragma unroll
-    for (int r = 0; r < 32; r++) sm.tile[r][lane] = nxt[r];
-    Simt::warp_sync();
-    if (base + 32 < nsamp) {
+        for (int u = 0; u < 15; u++) v[u] = src[i0 + u * 32 + lane];
 #pragma unroll
-      for (int r = 0; r < 32; r++) nxt[r] = (r < nrows) ? load_sample(p, s0 + r, in0 + base + 32 + lane) : 0.f;
-    }
-    if (valid) {
-#pragma unroll 8
-      for (int i = 0; i < 32; i++) {
-        const float xi = sm.tile[lane][i];
-        const float yi = xi + m0;
-        const double xd = (double)xi, yd = (double)yi;
-        m0 = (float)((double)m1 + (-2.0 * xd - a0 * yd));
-        m1 = (float)(xd - a1 * yd);
-        sm.tile[lane][i] = yi;
+        for (int u = 0; u < 15; u++) dst[i0 + u * 32 + lane] = v[u];
       }
     }
-    Simt::warp_sync();
-    for (int r = 0; r < nrows; r++) p.hp[(long long)(s0 + r) * p.hp_stride + kHist + base + lane] = sm.tile[r][lane];
-    Simt::warp_sync();
   }
-  if (valid) {
+  Simt::cta_sync();
+  const double a0 = (double)-1.99599f, a1 = (double)0.99600f;
+  const bool tail_direct = nsamp >= kHist;  // the new history is the chunk's own tail
+  for (int n = 0; n <= ntiles; n++) {
+    if (warp == 0) {
+      if (n < ntiles && valid) {
+        float *row = sm.tile[n & 3][lane];
+#pragma unroll 8
+        for (int i = 0; i < 32; i++) {
+          const float xi = row[i];
+          const float yi = xi + m0;
+          const double xd = (double)xi, yd = (double)yi;
+          m0 = (float)((double)m1 + (-2.0 * xd - a0 * yd));
+          m1 = (float)(xd - a1 * yd);
+          row[i] = yi;
+        }
+      }
+    } else if (warp == 1) {
+      if (n + 1 < ntiles) {
+        if ((n + 1) & 1) {
+#pragma unroll
+          for (int r = 0; r < 32; r++) sm.tile[(n + 1) & 3][r][lane] = regs[1][r];
+          if (n + 3 < ntiles) hp_load_tile(p, s0, nrows, in0 + (long long)(n + 3) * 32 + lane, regs[1]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 32; r++) sm.tile[(n + 1) & 3][r][lane] = regs[0][r];
+          if (n + 3 < ntiles) hp_load_tile(p, s0, nrows, in0 + (long long)(n + 3) * 32 + lane, regs[0]);
+        }
+      }
+    } else if (warp == 2) {
+      if (n >= 1) {
+        const int base = (n - 1) * 32;
+        const int hidx = base + lane - (nsamp - kHist);
+        for (int r = 0; r < nrows; r++) {
+          const float v = sm.tile[(n - 1) & 3][r][lane];
+          p.hp[(long long)(s0 + r) * p.hp_stride + kHist + base + lane] = v;
+          if (tail_direct && hidx >= 0) p.state[(long long)(s0 + r) * kStateFloats + kStHist + hidx] = v;
+        }
+      }
+    }
+    Simt::cta_sync();
+  }
+  if (warp == 0 && valid) {
     st[kStHp] = m0;
     st[kStHp + 1] = m1;
   }
-  for (int r = 0; r < nrows; r++) {  // last kHist samples of [history | chunk] -> state
-    const float *src = p.hp + (long long)(s0 + r) * p.hp_stride + nsamp;
-    float *dst = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
-    for (int i = lane; i < kHist; i += 32) dst[i] = src[i];
+  if (!tail_direct && warp == 3) {  // short chunk: last kHist samples of [history | chunk] -> state
+    for (int r = 0; r < nrows; r++) {
+      const float *src = p.hp + (long long)(s0 + r) * p.hp_stride + nsamp;
+      float *dst = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
+      float v[15];
+      for (int i0 = 0; i0 < kHist; i0 += 15 * 32) {  // read everything before overwriting (src may alias dst's source)
+#pragma unroll
+        for (int u = 0; u < 15; u++) v[u] = src[i0 + u * 32 + lane];
+#pragma unroll
+        for (int u = 0; u < 15; u++) dst[i0 + u * 32 + lane] = v[u];
+      }
+    }
   }
 }
 
@@ -688,25 +742,33 @@ NS_DEV void irfft960_inplace(const Grp &g, const Tables &T, cf *X) {
   fft480(g, T, X, from_buf);
 }
 
-// a8: 22 triangular bands over bins 0..400.  88 threads: band = tid/4, four lanes split the bins.
-template <class BinVal>
-NS_DEV float band_accumulate(const Grp &g, const Tables &T, BinVal val) {
-  float acc = 0.f;
+// a8: 22 triangular bands over bins 0..400.  88 threads: band = tid/4, four lanes split the bins of
+// the two intervals that touch the band; triangular weights come from the bin_frac table.  NQ
+// quantities are accumulated in one pass.  Results are valid in lanes with (tid & 3) == 0, tid < 88.
+template <int NQ, class BinVal>
+NS_DEV void band_accumulate(const Grp &g, const Tables &T, BinVal val, float (&acc)[NQ]) {
+#pragma unroll
+  for (int q = 0; q < NQ; q++) acc[q] = 0.f;
   const int b = g.tid >> 2, sub = g.tid & 3;
   if (g.tid < 4 * kBands) {
-    if (b >= 1) {
-      const int lo = T.eband[b - 1], n = T.eband[b] - lo;
-      for (int j = sub; j < n; j += 4) acc = fmaf((float)j / (float)n, val(lo + j), acc);
-    }
-    if (b <= kBands - 2) {
-      const int lo = T.eband[b], n = T.eband[b + 1] - lo;
-      for (int j = sub; j < n; j += 4) acc = fmaf(1.f - (float)j / (float)n, val(lo + j), acc);
+    const int lo = (b >= 1) ? T.eband[b - 1] : 0;
+    const int mid = T.eband[b];
+    const int hi = (b <= kBands - 2) ? T.eband[b + 1] : mid;
+    for (int k = lo + sub; k < hi; k += 4) {
+      const float f = T.bin_frac[k];
+      const float w = (k < mid) ? f : 1.f - f;
+      float v[NQ];
+      val(k, v);
+#pragma unroll
+      for (int q = 0; q < NQ; q++) acc[q] = fmaf(w, v[q], acc[q]);
     }
   }
-  acc += Simt::shfl_xor(acc, 1);
-  acc += Simt::shfl_xor(acc, 2);
-  if (b == 0 || b == kBands - 1) acc *= 2.f;
-  return acc;  // valid in lanes with sub == 0 and tid < 88
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    acc[q] += Simt::shfl_xor(acc[q], 1);
+    acc[q] += Simt::shfl_xor(acc[q], 2);
+    if (b == 0 || b == kBands - 1) acc[q] *= 2.f;
+  }
 }
 
 struct SpecSmem {
@@ -725,21 +787,21 @@ NS_DEV void load_tables(const Params &p, Tables &dst, int tid, int nthr) {
 }
 
 // spectra of frame t: X of [prev | cur], P of the window lagged by pitch_index, Ex / Ep / raw Exp
-NS_DEV void frame_spectra(const Grp &g, const Tables &T, SpecSmem &s, const float *hp_row, int t, int pitch_index,
-                          bool want_p) {
+NS_DEV void frame_spectra(const Grp &g, const Tables &T, SpecSmem &s, const float *hp_row, int t, int pitch_index) {
   const float *cur = hp_row + kHist - kFrame + (long long)t * kFrame;  // [analysis_mem | frame]
   rfft960_windowed(g, T, cur, s.X);
-  if (want_p) rfft960_windowed(g, T, cur - pitch_index, s.P);
-  const float ex = band_accumulate(g, T, [&](int k) { return fmaf(s.X[k].x, s.X[k].x, s.X[k].y * s.X[k].y); });
-  float ep = 0.f, exp_ = 0.f;
-  if (want_p) {
-    ep = band_accumulate(g, T, [&](int k) { return fmaf(s.P[k].x, s.P[k].x, s.P[k].y * s.P[k].y); });
-    exp_ = band_accumulate(g, T, [&](int k) { return fmaf(s.X[k].x, s.P[k].x, s.X[k].y * s.P[k].y); });
-  }
+  rfft960_windowed(g, T, cur - pitch_index, s.P);
+  float acc[3];
+  band_accumulate<3>(g, T, [&](int k, float (&v)[3]) {
+    const cf x = s.X[k], p = s.P[k];
+    v[0] = fmaf(x.x, x.x, x.y * x.y);
+    v[1] = fmaf(p.x, p.x, p.y * p.y);
+    v[2] = fmaf(x.x, p.x, x.y * p.y);
+  }, acc);
   if (g.tid < 4 * kBands && (g.tid & 3) == 0) {
-    s.Ex[g.tid >> 2] = ex;
-    s.Ep[g.tid >> 2] = ep;
-    s.Exp[g.tid >> 2] = exp_;
+    s.Ex[g.tid >> 2] = acc[0];
+    s.Ep[g.tid >> 2] = acc[1];
+    s.Exp[g.tid >> 2] = acc[2];
   }
   gsync(g);
 }
@@ -760,16 +822,27 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
   const long long n_tasks = (long long)p.n_streams * p.n_frames;
   for (long long task = Simt::cta(); task < n_tasks; task += Simt::n_ctas()) {
     const int stream = (int)(task / p.n_frames), t = (int)(task - (long long)stream * p.n_frames);
-    float *rec = p.rec + ((long long)stream * p.chunk_cap + t) * kRecFloats;
+    const long long fidx = (long long)stream * p.chunk_cap + t;
+    float *rec = p.rec + fidx * kRecFloats;
     const int pitch_index = reinterpret_cast<const int *>(rec)[kRecPitchIndex];
-    frame_spectra(g, T, s, p.hp + (long long)stream * p.hp_stride, t, pitch_index, true);
+    frame_spectra(g, T, s, p.hp + (long long)stream * p.hp_stride, t, pitch_index);
+    {  // spectra -> workspace (K5 reads them back instead of redoing two FFTs)
+      cf *dst = p.spec + fidx * (2 * kSpecStride);
+      for (int k = g.tid; k < kFreq; k += kGroupThreads) {
+        dst[k] = s.X[k];
+        dst[kSpecStride + k] = s.P[k];
+      }
+    }
     if (g.tid < kBands) {
       const int i = g.tid;
       s.Exp[i] = s.Exp[i] / (float)sqrt(.001 + (double)(s.Ex[i] * s.Ep[i]));
-    } else if (g.tid == 32) {
+      s.Ly[i] = (float)log10(1e-2 + (double)s.Ex[i]);
+    }
+    gsync(g);
+    if (g.tid == 0) {
       float logMax = -2.f, follow = -2.f, E = 0.f;
       for (int i = 0; i < kBands; i++) {
-        float ly = (float)log10(1e-2 + (double)s.Ex[i]);
+        float ly = s.Ly[i];
         ly = fmaxf(logMax - 7.f, fmaxf(follow - 1.5f, ly));
         logMax = fmaxf(logMax, ly);
         follow = fmaxf(follow - 1.5f, ly);
@@ -788,6 +861,8 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
       if (i == 1) c -= 4.f;
       rec[kRecCeps + i] = c;
       rec[kRecExp + i] = s.Exp[i];
+      rec[kRecEx + i] = s.Ex[i];
+      rec[kRecEp + i] = s.Ep[i];
       if (p.dbg) {
         float *d = p.dbg + ((long long)stream * p.n_frames_call + p.frame0 + t) * kDbgFloats;
         d[kDbgEx + i] = s.Ex[i];
@@ -811,28 +886,35 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
 }
 
 // =================================================================================================
-// K4: the recurrent core, 8 streams per CTA, serial over the chunk's frames
+// K4: the recurrent core, 8 streams per CTA, serial over the chunk's frames.  All weights stay in
+// shared memory as packed bf16 pairs for the whole launch; activations and GRU states of the 8
+// streams are f32 rows [k][8] (layout in ns_common.h).  Each matrix-vector job is split over
+// column pairs x K slices so that all 256 threads carry 2 x 8 FP32 FMA accumulators; partial sums
+// meet in shared memory, where bias, activation and the GRU algebra are applied.
 // =================================================================================================
 constexpr int kRnnStreams = 8;
+constexpr int kRnnWordsMax = 44544;  // packed weight words (pack_rnn emits 44,093 for the RNNoise topology)
+constexpr int kRnnBiasMax = 608;
 struct RnnSmem {
-  float tansig[204];
-  float feat[44 * 8];  // [row][stream]
-  float dense[24 * 8];
-  float hvad[24 * 8];
-  float hnoise[48 * 8];
-  float hden[96 * 8];
-  float rh[96 * 8];
+  uint32_t w[kRnnWordsMax];
+  float bias[kRnnBiasMax];
+  float A[kActRows * 8];
+  float R[kRhRows * 8];
   float z[96 * 8];
+  float psum[4096];  // [ks][half][col][4]
   float gains[24 * 8];
+  float tansig[204];
   float vad[8];
   int silent[8];
   int memid[8];
+  int any_active;
   float ring[8][kCepsMem][kBands];
   float lastg[8][kBands];
-  float cin[8][32];     // ceps[22] | tail[7] of the current frame
-  float fstage[8][44];  // features being assembled
+  float cin[8][32];  // ceps[22] | tail[7] | silence flag of the current frame
   float dist[8][64];
+  JobDesc jobs[kNumJobs];
 };
+static_assert(sizeof(RnnSmem) <= 232448, "recurrent-core shared memory exceeds the 227 KB a CTA may use");
 
 NS_DEV float tansig_approx(const float *tab, float x) {
   if (!(x < 8.f)) return 1.f;
@@ -856,126 +938,123 @@ NS_DEV float activate(const float *tab, int act, float x) {
   return x < 0.f ? 0.f : x;
 }
 
-NS_DEV float *rnn_seg_ptr(RnnSmem &r, int id) {
-  switch (id) {
-    case kSegFeat: return r.feat;
-    case kSegDense: return r.dense;
-    case kSegHVad: return r.hvad;
-    case kSegHNoise: return r.hnoise;
-    case kSegHDen: return r.hden;
-    default: return r.rh;
+#define NS_RNN_FMA16(w0, w1, lo, hi)                                  \
+  acc0[0] = fmaf(w0, lo.x, acc0[0]); acc0[1] = fmaf(w0, lo.y, acc0[1]); \
+  acc0[2] = fmaf(w0, lo.z, acc0[2]); acc0[3] = fmaf(w0, lo.w, acc0[3]); \
+  acc0[4] = fmaf(w0, hi.x, acc0[4]); acc0[5] = fmaf(w0, hi.y, acc0[5]); \
+  acc0[6] = fmaf(w0, hi.z, acc0[6]); acc0[7] = fmaf(w0, hi.w, acc0[7]); \
+  acc1[0] = fmaf(w1, lo.x, acc1[0]); acc1[1] = fmaf(w1, lo.y, acc1[1]); \
+  acc1[2] = fmaf(w1, lo.z, acc1[2]); acc1[3] = fmaf(w1, lo.w, acc1[3]); \
+  acc1[4] = fmaf(w1, hi.x, acc1[4]); acc1[5] = fmaf(w1, hi.y, acc1[5]); \
+  acc1[6] = fmaf(w1, hi.z, acc1[6]); acc1[7] = fmaf(w1, hi.w, acc1[7]);
+
+// partial sums of one job: thread tj = ks*cp + pair covers columns 2*pair, 2*pair+1 over K slice ks
+NS_DEV void rnn_job_partial(const JobDesc &jd, RnnSmem &r, int tid) {
+  const int stride = jd.cp * jd.ksplit;
+  if (tid >= stride) return;
+  const int ks = tid / jd.cp, pair = tid - ks * jd.cp;
+  float acc0[8], acc1[8];
+#pragma unroll
+  for (int s = 0; s < 8; s++) acc0[s] = acc1[s] = 0.f;
+  const uint32_t *w = r.w + jd.w_off + tid;
+  int k = ks * jd.len;
+  int kend = k + jd.len;
+  if (kend > jd.k_total) kend = jd.k_total;
+  const int k1 = kend < jd.len1 ? kend : jd.len1;
+  {
+    const float *a = r.A + (jd.off1 + k) * 8;
+#pragma unroll 2
+    for (; k < k1; k++, w += stride, a += 8) {
+      const uint32_t wv = *w;
+      const float w0 = u2f(wv << 16), w1 = u2f(wv & 0xFFFF0000u);
+      const f4 lo = ld4(a), hi = ld4(a + 4);
+      NS_RNN_FMA16(w0, w1, lo, hi)
+    }
+  }
+  if (k < kend) {
+    const float *a = r.R + (jd.off2 + k - jd.len1) * 8;
+#pragma unroll 2
+    for (; k < kend; k++, w += stride, a += 8) {
+      const uint32_t wv = *w;
+      const float w0 = u2f(wv << 16), w1 = u2f(wv & 0xFFFF0000u);
+      const f4 lo = ld4(a), hi = ld4(a + 4);
+      NS_RNN_FMA16(w0, w1, lo, hi)
+    }
+  }
+  const int N = jd.n_out, c0 = 2 * pair;
+  f4 *p0 = reinterpret_cast<f4 *>(r.psum + ((ks * 2 + 0) * N + c0) * 4);
+  f4 *p1 = reinterpret_cast<f4 *>(r.psum + ((ks * 2 + 1) * N + c0) * 4);
+  p0[0] = f4{acc0[0], acc0[1], acc0[2], acc0[3]};
+  p1[0] = f4{acc0[4], acc0[5], acc0[6], acc0[7]};
+  if (c0 + 1 < N) {
+    p0[1] = f4{acc1[0], acc1[1], acc1[2], acc1[3]};
+    p1[1] = f4{acc1[4], acc1[5], acc1[6], acc1[7]};
   }
 }
 
-// acc[s] = bias[col] + sum_rows W[row][col] * act[row][s]   for one output column `col`
-NS_DEV void rnn_matvec(const JobDesc &jd, const uint32_t *__restrict__ words, const float *__restrict__ bias,
-                       RnnSmem &r, int col, float (&acc)[8]) {
-  const float b = bias[jd.b_off + col];
+// sum the K slices, add the bias, apply the activation and the job's algebra
+template <int NT>
+NS_DEV void rnn_job_finish(const JobDesc &jd, RnnSmem &r, int tid) {
+  const int N = jd.n_out;
+  for (int it = tid; it < 2 * N; it += NT) {
+    const int half = it / N, col = it - half * N;
+    const float b = r.bias[jd.b_off + col];
+    float v[4] = {b, b, b, b};
+    for (int ks = 0; ks < jd.ksplit; ks++) {
+      const f4 q = ld4(r.psum + ((ks * 2 + half) * N + col) * 4);
+      v[0] += q.x;
+      v[1] += q.y;
+      v[2] += q.z;
+      v[3] += q.w;
+    }
 #pragma unroll
-  for (int s = 0; s < 8; s++) acc[s] = b;
-  const uint32_t *w = words + jd.w_off + col;
-  const int n_out = jd.n_out;
-  for (int sg = 0; sg < jd.n_segs; sg++) {
-    const float *a = rnn_seg_ptr(r, jd.seg_id[sg]);
-    const int k4 = jd.seg_k4[sg];
-    for (int kk = 0; kk < k4; kk++) {
-      const uint32_t wv = *w;
-      w += n_out;
-#pragma unroll
-      for (int bb = 0; bb < 4; bb++) {
-        const float wf = (float)(int)(int8_t)((wv >> (8 * bb)) & 0xFFu);
-        const f4 lo = ld4(a), hi = ld4(a + 4);
-        a += 8;
-        acc[0] = fmaf(wf, lo.x, acc[0]);
-        acc[1] = fmaf(wf, lo.y, acc[1]);
-        acc[2] = fmaf(wf, lo.z, acc[2]);
-        acc[3] = fmaf(wf, lo.w, acc[3]);
-        acc[4] = fmaf(wf, hi.x, acc[4]);
-        acc[5] = fmaf(wf, hi.y, acc[5]);
-        acc[6] = fmaf(wf, hi.z, acc[6]);
-        acc[7] = fmaf(wf, hi.w, acc[7]);
+    for (int j = 0; j < 4; j++) {
+      const int s = 4 * half + j;
+      const float x = v[j] * (1.f / 256);
+      if (jd.kind == kJobDense) {
+        const float y = activate(r.tansig, jd.activation, x);
+        if (jd.out_off >= 0)
+          r.A[(jd.out_off + col) * 8 + s] = y;
+        else
+          r.gains[col * 8 + s] = y;
+      } else if (jd.kind == kJobZR) {
+        const int Ng = N >> 1;
+        const float y = sigmoid_approx(r.tansig, x);
+        if (col < Ng)
+          r.z[col * 8 + s] = y;
+        else
+          r.R[(jd.rh_off + col - Ng) * 8 + s] = r.A[(jd.out_off + col - Ng) * 8 + s] * y;
+      } else {
+        const float c = activate(r.tansig, jd.activation, x);
+        const float zz = r.z[col * 8 + s], ho = r.A[(jd.out_off + col) * 8 + s];
+        const float hn = zz * ho + (1.f - zz) * c;
+        if (!r.silent[s]) r.A[(jd.out_off + col) * 8 + s] = hn;
       }
     }
   }
-}
-
-NS_DEV void rnn_dense(const RnnHeader &H, int job, const Params &p, RnnSmem &r, int tid, int nthr, float *dst) {
-  const JobDesc &jd = H.jobs[job];
-  for (int col = tid; col < jd.n_out; col += nthr) {
-    float acc[8];
-    rnn_matvec(jd, p.rnn_words, p.rnn_bias, r, col, acc);
-#pragma unroll
-    for (int s = 0; s < 8; s++) dst[col * 8 + s] = activate(r.tansig, jd.activation, acc[s] * (1.f / 256));
-  }
-}
-// z and r gates of a GRU with N neurons: columns [0,N) -> z, [N,2N) -> r*h into rh
-NS_DEV void rnn_gru_zr(const RnnHeader &H, int job, const Params &p, RnnSmem &r, int tid, int nthr, const float *h) {
-  const JobDesc &jd = H.jobs[job];
-  const int N = jd.n_out >> 1;
-  for (int col = tid; col < jd.n_out; col += nthr) {
-    float acc[8];
-    rnn_matvec(jd, p.rnn_words, p.rnn_bias, r, col, acc);
-    if (col < N) {
-#pragma unroll
-      for (int s = 0; s < 8; s++) r.z[col * 8 + s] = sigmoid_approx(r.tansig, acc[s] * (1.f / 256));
-    } else {
-      const int i = col - N;
-#pragma unroll
-      for (int s = 0; s < 8; s++) r.rh[i * 8 + s] = h[i * 8 + s] * sigmoid_approx(r.tansig, acc[s] * (1.f / 256));
-    }
-  }
-}
-NS_DEV void rnn_gru_c(const RnnHeader &H, int job, const Params &p, RnnSmem &r, int tid, int nthr, float *h) {
-  const JobDesc &jd = H.jobs[job];
-  for (int col = tid; col < jd.n_out; col += nthr) {
-    float acc[8];
-    rnn_matvec(jd, p.rnn_words, p.rnn_bias, r, col, acc);
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-      const float c = activate(r.tansig, jd.activation, acc[s] * (1.f / 256));
-      const float z = r.z[col * 8 + s], ho = h[col * 8 + s];
-      const float hn = z * ho + (1.f - z) * c;
-      h[col * 8 + s] = r.silent[s] ? ho : hn;
-    }
-  }
-}
-
-NS_DEV void rnn_phase(const Params &p, RnnSmem &r, int tid, int nthr) {
-  const RnnHeader &H = *p.rnn_hdr;
-  rnn_dense(H, 0, p, r, tid, nthr, r.dense);
-  Simt::cta_sync();
-  rnn_gru_zr(H, 1, p, r, tid, nthr, r.hvad);
-  Simt::cta_sync();
-  rnn_gru_c(H, 2, p, r, tid, nthr, r.hvad);
-  Simt::cta_sync();
-  rnn_gru_zr(H, 4, p, r, tid, nthr, r.hnoise);
-  if (tid == nthr - 1) {  // vad_output rides along on the last thread
-    float acc[8];
-    rnn_matvec(H.jobs[3], p.rnn_words, p.rnn_bias, r, 0, acc);
-#pragma unroll
-    for (int s = 0; s < 8; s++) r.vad[s] = activate(r.tansig, H.jobs[3].activation, acc[s] * (1.f / 256));
-  }
-  Simt::cta_sync();
-  rnn_gru_c(H, 5, p, r, tid, nthr, r.hnoise);
-  Simt::cta_sync();
-  rnn_gru_zr(H, 6, p, r, tid, nthr, r.hden);
-  Simt::cta_sync();
-  rnn_gru_c(H, 7, p, r, tid, nthr, r.hden);
-  Simt::cta_sync();
-  rnn_dense(H, 8, p, r, tid, nthr, r.gains);
-  Simt::cta_sync();
 }
 
 template <int NT>
 NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
   const int tid = Simt::tid();
   const int s0 = Simt::cta() * kRnnStreams;
-  {
-    float *rz = reinterpret_cast<float *>(&r);
-    for (int i = tid; i < (int)(sizeof(RnnSmem) / 4); i += NT) rz[i] = 0.f;
+  {  // weights, biases, tables, job descriptors -> shared memory; activations cleared
+    const RnnHeader &H = *p.rnn_hdr;
+    for (int i = tid; i < H.n_words; i += NT) r.w[i] = p.rnn_words[i];
+    for (int i = tid; i < H.n_bias; i += NT) r.bias[i] = p.rnn_bias[i];
+    for (int i = tid; i < 204; i += NT) r.tansig[i] = p.tables->tansig[i];
+    const int32_t *js = reinterpret_cast<const int32_t *>(H.jobs);
+    int32_t *jd = reinterpret_cast<int32_t *>(r.jobs);
+    for (int i = tid; i < (int)(sizeof(JobDesc) * kNumJobs / 4); i += NT) jd[i] = js[i];
+    for (int i = tid; i < kActRows * 8; i += NT) r.A[i] = 0.f;
+    for (int i = tid; i < kRhRows * 8; i += NT) r.R[i] = 0.f;
+    for (int i = tid; i < 96 * 8; i += NT) r.z[i] = 0.f;
+    for (int i = tid; i < 8 * kCepsMem * kBands; i += NT) (&r.ring[0][0][0])[i] = 0.f;
+    for (int i = tid; i < 8 * kBands; i += NT) (&r.lastg[0][0])[i] = 0.f;
+    if (tid < 8) r.memid[tid] = 0;
   }
+  const int vad_w_off = p.rnn_hdr->vad_w_off, vad_act = p.rnn_hdr->vad_activation;
   Simt::cta_sync();
-  for (int i = tid; i < 204; i += NT) r.tansig[i] = p.tables->tansig[i];
   for (int it = tid; it < kRnnStreams * 384; it += NT) {  // recurrent state -> shared memory
     const int s = it / 384, j = it - s * 384;
     if (s0 + s >= p.n_streams) continue;
@@ -985,88 +1064,131 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
     else if (j < 198)
       r.lastg[s][j - 176] = st[kStLastG + j - 176];
     else if (j < 222)
-      r.hvad[(j - 198) * 8 + s] = st[kStHVad + j - 198];
+      r.A[(kActHVad + j - 198) * 8 + s] = st[kStHVad + j - 198];
     else if (j < 270)
-      r.hnoise[(j - 222) * 8 + s] = st[kStHNoise + j - 222];
+      r.A[(kActHNoise + j - 222) * 8 + s] = st[kStHNoise + j - 222];
     else if (j < 366)
-      r.hden[(j - 270) * 8 + s] = st[kStHDen + j - 270];
+      r.A[(kActHDen + j - 270) * 8 + s] = st[kStHDen + j - 270];
     else if (j == 366)
       r.memid[s] = reinterpret_cast<const int *>(st)[kStMemId];
   }
   Simt::cta_sync();
-  for (int t = 0; t < p.n_frames; t++) {
-    for (int it = tid; it < kRnnStreams * 32; it += NT) {
-      const int s = it >> 5, j = it & 31;
-      const bool act = s0 + s < p.n_streams;
-      const float *rec = p.rec + ((long long)(s0 + (act ? s : 0)) * p.chunk_cap + t) * kRecFloats;
-      if (j < kBands)
-        r.cin[s][j] = act ? rec[kRecCeps + j] : 0.f;
-      else if (j < kBands + 7)
-        r.cin[s][j] = act ? rec[kRecTail + j - kBands] : 0.f;
-      else if (j == 29)
-        r.silent[s] = act ? reinterpret_cast<const int *>(rec)[kRecSilence] : 1;
+  for (int it = tid; it < kRnnStreams * 64; it += NT) {  // pairwise cepstral distances of the ring
+    const int s = it >> 6, a = (it >> 3) & 7, b = it & 7;
+    float dist = 0.f;
+    for (int k = 0; k < kBands; k++) {
+      const float tt = r.ring[s][a][k] - r.ring[s][b][k];
+      dist += tt * tt;
     }
+    r.dist[s][(a << 3) + b] = dist;
+  }
+  // per-thread slice of the next frame's record (ceps | tail | silence), fetched one frame ahead
+  const int ps = tid / 30, pj = tid - ps * 30;
+  const bool pact = tid < kRnnStreams * 30 && s0 + ps < p.n_streams;
+  auto fetch = [&](int t) -> float {
+    if (!pact) return (pj == 29) ? 1.f : 0.f;
+    const float *rec = p.rec + ((long long)(s0 + ps) * p.chunk_cap + t) * kRecFloats;
+    if (pj < kBands) return rec[kRecCeps + pj];
+    if (pj < 29) return rec[kRecTail + pj - kBands];
+    return reinterpret_cast<const int *>(rec)[kRecSilence] ? 1.f : 0.f;
+  };
+  float nxt = (p.n_frames > 0) ? fetch(0) : 0.f;
+  Simt::cta_sync();
+  for (int t = 0; t < p.n_frames; t++) {
+    if (tid < kRnnStreams * 30) {
+      r.cin[ps][pj] = nxt;
+      if (pj == 29) r.silent[ps] = nxt != 0.f;
+    }
+    if (t + 1 < p.n_frames) nxt = fetch(t + 1);
+    if (tid == 0) r.any_active = 0;
     Simt::cta_sync();
     for (int it = tid; it < kRnnStreams * kBands; it += NT) {  // a13: cepstral ring update
       const int s = it / kBands, i = it - s * kBands;
-      if (!r.silent[s]) r.ring[s][r.memid[s]][i] = r.cin[s][i];
-    }
-    Simt::cta_sync();
-    for (int it = tid; it < kRnnStreams * 64; it += NT) {  // a13: pairwise cepstral distances
-      const int s = it >> 6, a = (it >> 3) & 7, b = it & 7;
-      if (r.silent[s]) continue;
-      float dist = 0.f;
-      for (int k = 0; k < kBands; k++) {
-        const float tt = r.ring[s][a][k] - r.ring[s][b][k];
-        dist += tt * tt;
-      }
-      r.dist[s][(a << 3) + b] = dist;
-    }
-    for (int it = tid; it < kRnnStreams * 44; it += NT) {  // a13: features[0..41]
-      const int s = it / 44, i = it - s * 44;
-      float v = 0.f;
-      if (!r.silent[s] && i < 41) {
-        const int m0 = r.memid[s], m1 = (m0 + 7) & 7, m2 = (m0 + 6) & 7;
-        if (i < kDeltaCeps) {
-          v = r.ring[s][m0][i] + r.ring[s][m1][i] + r.ring[s][m2][i];
-        } else if (i < kBands) {
-          v = r.cin[s][i];
-        } else if (i < kBands + kDeltaCeps) {
-          const int j = i - kBands;
-          v = r.ring[s][m0][j] - r.ring[s][m2][j];
-        } else if (i < kBands + 2 * kDeltaCeps) {
-          const int j = i - kBands - kDeltaCeps;
-          v = r.ring[s][m0][j] - 2.f * r.ring[s][m1][j] + r.ring[s][m2][j];
-        } else {
-          v = r.cin[s][kBands + (i - kBands - 2 * kDeltaCeps)];
-        }
-      }
-      if (i != 41) r.fstage[s][i] = v;
-    }
-    Simt::cta_sync();
-    if (tid < kRnnStreams) {
-      const int s = tid;
-      float v = 0.f;
       if (!r.silent[s]) {
-        float sv = 0.f;
-        for (int a = 0; a < kCepsMem; a++) {
-          float mind = 1e15f;
-          for (int b = 0; b < kCepsMem; b++)
-            if (b != a) mind = fminf(mind, r.dist[s][(a << 3) + b]);
-          sv += mind;
-        }
-        v = sv / kCepsMem - 2.1f;
-        r.memid[s] = (r.memid[s] + 1) & 7;
+        r.ring[s][r.memid[s]][i] = r.cin[s][i];
+        if (i == 0) r.any_active = 1;
       }
-      r.fstage[s][41] = v;
     }
     Simt::cta_sync();
-    for (int it = tid; it < kRnnStreams * 44; it += NT) {
-      const int s = it & 7, row = it >> 3;
-      r.feat[row * 8 + s] = (row < kFeatures) ? r.fstage[s][row] : 0.f;
+    if (r.any_active) {
+      for (int it = tid; it < kRnnStreams * 8; it += NT) {  // a13: distances to the new ring row
+        const int s = it >> 3, b = it & 7;
+        if (r.silent[s]) continue;
+        const int a = r.memid[s];
+        float dist = 0.f;
+        for (int k = 0; k < kBands; k++) {
+          const float tt = r.ring[s][a][k] - r.ring[s][b][k];
+          dist += tt * tt;
+        }
+        r.dist[s][(a << 3) + b] = dist;
+        r.dist[s][(b << 3) + a] = dist;
+      }
+      for (int it = tid; it < kRnnStreams * 41; it += NT) {  // a13: features[0..40] -> A[feat]
+        const int s = it / 41, i = it - s * 41;
+        float v = 0.f;
+        if (!r.silent[s]) {
+          const int m0 = r.memid[s], m1 = (m0 + 7) & 7, m2 = (m0 + 6) & 7;
+          if (i < kDeltaCeps) {
+            v = r.ring[s][m0][i] + r.ring[s][m1][i] + r.ring[s][m2][i];
+          } else if (i < kBands) {
+            v = r.cin[s][i];
+          } else if (i < kBands + kDeltaCeps) {
+            const int j = i - kBands;
+            v = r.ring[s][m0][j] - r.ring[s][m2][j];
+          } else if (i < kBands + 2 * kDeltaCeps) {
+            const int j = i - kBands - kDeltaCeps;
+            v = r.ring[s][m0][j] - 2.f * r.ring[s][m1][j] + r.ring[s][m2][j];
+          } else {
+            v = r.cin[s][kBands + (i - kBands - 2 * kDeltaCeps)];
+          }
+        }
+        r.A[(kActFeat + i) * 8 + s] = v;
+      }
+      Simt::cta_sync();
+      if (tid < kRnnStreams) {  // a13: spectral variability, ring index
+        const int s = tid;
+        float v = 0.f;
+        if (!r.silent[s]) {
+          float sv = 0.f;
+          for (int a = 0; a < kCepsMem; a++) {
+            float mind = 1e15f;
+            for (int b = 0; b < kCepsMem; b++)
+              if (b != a) mind = fminf(mind, r.dist[s][(a << 3) + b]);
+            sv += mind;
+          }
+          v = sv / kCepsMem - 2.1f;
+          r.memid[s] = (r.memid[s] + 1) & 7;
+        }
+        r.A[(kActFeat + 41) * 8 + s] = v;
+      }
+      Simt::cta_sync();
+      if (p.dbg) {
+        for (int it = tid; it < kRnnStreams * kFeatures; it += NT) {
+          const int s = it / kFeatures, i = it - s * kFeatures;
+          if (s0 + s >= p.n_streams) continue;
+          p.dbg[((long long)(s0 + s) * p.n_frames_call + p.frame0 + t) * kDbgFloats + kDbgFeatures + i] =
+              r.A[(kActFeat + i) * 8 + s];
+        }
+      }
+      for (int j = 0; j < kNumJobs; j++) {
+        rnn_job_partial(r.jobs[j], r, tid);
+        if (j == 3 && tid >= NT - 8) {  // vad_output on the settled vad state (threads idle in this job)
+          const int s = tid - (NT - 8);
+          float sum = r.bias[vad_w_off + 24];
+          for (int k = 0; k < 24; k++) sum = fmaf(r.bias[vad_w_off + k], r.A[(kActHVad + k) * 8 + s], sum);
+          r.vad[s] = activate(r.tansig, vad_act, sum * (1.f / 256));
+        }
+        Simt::cta_sync();
+        rnn_job_finish<NT>(r.jobs[j], r, tid);
+        Simt::cta_sync();
+      }
+    } else if (p.dbg) {
+      for (int it = tid; it < kRnnStreams * kFeatures; it += NT) {
+        const int s = it / kFeatures, i = it - s * kFeatures;
+        if (s0 + s >= p.n_streams) continue;
+        p.dbg[((long long)(s0 + s) * p.n_frames_call + p.frame0 + t) * kDbgFloats + kDbgFeatures + i] = 0.f;
+      }
     }
-    Simt::cta_sync();
-    rnn_phase(p, r, tid, NT);
     for (int it = tid; it < kRnnStreams * 32; it += NT) {
       const int s = it >> 5, i = it & 31;
       if (s0 + s >= p.n_streams) continue;
@@ -1087,13 +1209,6 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
         if (p.vad) p.vad[(long long)(s0 + s) * p.vad_stride + p.frame0 + t] = v;
       }
     }
-    if (p.dbg) {
-      for (int it = tid; it < kRnnStreams * kFeatures; it += NT) {
-        const int s = it / kFeatures, i = it - s * kFeatures;
-        if (s0 + s >= p.n_streams) continue;
-        p.dbg[((long long)(s0 + s) * p.n_frames_call + p.frame0 + t) * kDbgFloats + kDbgFeatures + i] = r.fstage[s][i];
-      }
-    }
     Simt::cta_sync();
   }
   for (int it = tid; it < kRnnStreams * 384; it += NT) {  // recurrent state -> HBM
@@ -1105,11 +1220,11 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
     else if (j < 198)
       st[kStLastG + j - 176] = r.lastg[s][j - 176];
     else if (j < 222)
-      st[kStHVad + j - 198] = r.hvad[(j - 198) * 8 + s];
+      st[kStHVad + j - 198] = r.A[(kActHVad + j - 198) * 8 + s];
     else if (j < 270)
-      st[kStHNoise + j - 222] = r.hnoise[(j - 222) * 8 + s];
+      st[kStHNoise + j - 222] = r.A[(kActHNoise + j - 222) * 8 + s];
     else if (j < 366)
-      st[kStHDen + j - 270] = r.hden[(j - 270) * 8 + s];
+      st[kStHDen + j - 270] = r.A[(kActHDen + j - 270) * 8 + s];
     else if (j == 366)
       reinterpret_cast<int *>(st)[kStMemId] = r.memid[s];
   }
@@ -1146,8 +1261,9 @@ NS_DEV void pitch_filter_and_gains(const Grp &g, const Tables &T, SpecSmem &s) {
   }
   gsync(g);
   {
-    const float e = band_accumulate(g, T, [&](int k) { return fmaf(s.X[k].x, s.X[k].x, s.X[k].y * s.X[k].y); });
-    if (g.tid < 4 * kBands && (g.tid & 3) == 0) s.newE[g.tid >> 2] = e;
+    float e[1];
+    band_accumulate<1>(g, T, [&](int k, float (&v)[1]) { v[0] = fmaf(s.X[k].x, s.X[k].x, s.X[k].y * s.X[k].y); }, e);
+    if (g.tid < 4 * kBands && (g.tid & 3) == 0) s.newE[g.tid >> 2] = e[0];
   }
   gsync(g);
   if (g.tid < kBands) {
@@ -1201,53 +1317,79 @@ NS_DEV void store_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem
   }
 }
 
+// One task = kSynRun consecutive frames of one stream.  A run that does not start the chunk first
+// re-synthesises the frame before it to recover synthesis_mem (the overlap-add halo).
+constexpr int kSynRun = 8;
+
+NS_DEV void synth_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem &s, int stream, int t, bool halo) {
+  const long long fidx = (long long)stream * p.chunk_cap + t;
+  const float *rec = p.rec + fidx * kRecFloats;
+  const bool silent = reinterpret_cast<const int *>(rec)[kRecSilence] != 0;
+  const cf *src = p.spec + fidx * (2 * kSpecStride);
+  for (int k = g.tid; k < kFreq; k += kGroupThreads) {
+    s.X[k] = src[k];
+    if (!silent) s.P[k] = src[kSpecStride + k];
+  }
+  if (g.tid < kBands) {
+    s.g[g.tid] = rec[kRecG + g.tid];
+    s.graw[g.tid] = rec[kRecGRaw + g.tid];
+    s.Exp[g.tid] = rec[kRecExp + g.tid];
+    s.Ex[g.tid] = rec[kRecEx + g.tid];
+    s.Ep[g.tid] = rec[kRecEp + g.tid];
+  }
+  gsync(g);
+  if (!silent) pitch_filter_and_gains(g, T, s);
+  if (p.dbg && !halo) {
+    float *d = p.dbg + ((long long)stream * p.n_frames_call + p.frame0 + t) * kDbgFloats;
+    if (g.tid < kBands) d[kDbgGains + g.tid] = s.g[g.tid];
+    if (g.tid == 0) {
+      d[kDbgPitchGain] = rec[kRecPitchGain];
+      d[kDbgVad] = rec[kRecVad];
+      d[kDbgPitchIndex] = (float)reinterpret_cast<const int *>(rec)[kRecPitchIndex];
+      d[kDbgSilence] = silent ? 1.f : 0.f;
+    }
+  }
+  irfft960_inplace(g, T, s.X);
+  if (halo) {
+    const float *zb = reinterpret_cast<const float *>(s.X);
+    for (int i = g.tid; i < kFrame; i += kGroupThreads) {
+      const float x1 = (i & 1) ? -zb[kFrame + i] : zb[kFrame + i];
+      s.synth[i] = x1 * T.win[kFrame - 1 - i];
+    }
+  } else {
+    store_frame(g, T, p, s, stream, p.frame0 + t);
+  }
+  gsync(g);
+}
+
 NS_DEV void synthesis_body(const Params &p, SpecSmem &s) {
   Grp g;
   g.tid = Simt::tid();
   g.lane = g.tid & 31;
   g.warp = g.tid >> 5;
   g.bar = 1;
-  const int stream = Simt::cta();
   load_tables(p, s.tab, g.tid, kGroupThreads);
-  float *st = p.state + (long long)stream * kStateFloats;
-  for (int i = g.tid; i < kFrame; i += kGroupThreads) s.synth[i] = st[kStSynth + i];
   Simt::cta_sync();
   const Tables &T = s.tab;
-  const float *hp_row = p.hp + (long long)stream * p.hp_stride;
-  for (int t = 0; t < p.n_frames; t++) {
-    const float *rec = p.rec + ((long long)stream * p.chunk_cap + t) * kRecFloats;
-    const int pitch_index = reinterpret_cast<const int *>(rec)[kRecPitchIndex];
-    const bool silent = reinterpret_cast<const int *>(rec)[kRecSilence] != 0;
-    if (g.tid < kBands) {
-      s.g[g.tid] = rec[kRecG + g.tid];
-      s.graw[g.tid] = rec[kRecGRaw + g.tid];
-    }
-    frame_spectra(g, T, s, hp_row, t, pitch_index, !silent);
-    if (!silent) {
-      // the band energies K3 stored are bit-identical to the ones just recomputed; Exp is the
-      // normalised correlation K3 derived from them
-      if (g.tid < kBands) s.Exp[g.tid] = rec[kRecExp + g.tid];
+  const int runs = (p.n_frames + kSynRun - 1) / kSynRun;
+  const long long n_tasks = (long long)p.n_streams * runs;
+  for (long long task = Simt::cta(); task < n_tasks; task += Simt::n_ctas()) {
+    const int stream = (int)(task / runs), t0 = (int)(task - (long long)stream * runs) * kSynRun;
+    const int t1 = (t0 + kSynRun < p.n_frames) ? t0 + kSynRun : p.n_frames;
+    float *st = p.state + (long long)stream * kStateFloats;
+    if (t0 == 0) {
+      for (int i = g.tid; i < kFrame; i += kGroupThreads) s.synth[i] = st[kStSynth + p.synth_sel * kFrame + i];
       gsync(g);
-      pitch_filter_and_gains(g, T, s);
+    } else {
+      synth_frame(g, T, p, s, stream, t0 - 1, true);
     }
-    if (p.dbg) {
-      float *d = p.dbg + ((long long)stream * p.n_frames_call + p.frame0 + t) * kDbgFloats;
-      if (g.tid < kBands) {
-        d[kDbgGains + g.tid] = s.g[g.tid];
-      }
-      if (g.tid == 0) {
-        d[kDbgPitchGain] = rec[kRecPitchGain];
-        d[kDbgVad] = rec[kRecVad];
-        d[kDbgPitchIndex] = (float)pitch_index;
-        d[kDbgSilence] = silent ? 1.f : 0.f;
-      }
+    for (int t = t0; t < t1; t++) synth_frame(g, T, p, s, stream, t, false);
+    if (t1 == p.n_frames) {
+      for (int i = g.tid; i < kFrame; i += kGroupThreads) st[kStSynth + (1 - p.synth_sel) * kFrame + i] = s.synth[i];
+      if (g.tid == 0) reinterpret_cast<int *>(st)[kStFrameCount] += p.n_frames;
     }
-    irfft960_inplace(g, T, s.X);
-    store_frame(g, T, p, s, stream, p.frame0 + t);
     gsync(g);
   }
-  for (int i = g.tid; i < kFrame; i += kGroupThreads) st[kStSynth + i] = s.synth[i];
-  if (g.tid == 0) reinterpret_cast<int *>(st)[kStFrameCount] += p.n_frames;
 }
 
 }  // namespace ns

@@ -280,6 +280,19 @@ class BatchDenoiser:
     def frames_done(self) -> int:
         return self.info["frames_done"]
 
+    def profile(self, enable: bool = True) -> None:
+        """Bracket every kernel launch with CUDA events on its own stream (measurement aid)."""
+        check(_lib.lib().crispy_ns_batch_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self) -> dict:
+        """{kernel name: (summed device ms, launches)} since the last read; synchronises."""
+        L = _lib.lib()
+        n = L.crispy_ns_kernel_count()
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        check(L.crispy_ns_batch_profile_read(self._h, ms, cnt, n))
+        return {L.crispy_ns_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}
+
     def save_state(self) -> bytes:
         n = _lib.lib().crispy_ns_batch_state_size(self._h)
         buf = C.create_string_buffer(n)

@@ -122,6 +122,13 @@ int crispy_ns_batch_load_state(crispy_ns_batch *b, const void *buf, size_t len);
  * frames processed per stream */
 int crispy_ns_batch_info(const crispy_ns_batch *b, int *rnn_streams_per_cta, int *chunk_frames,
                          int64_t *launches, int64_t *frames_done);
+/* measurement aid: with profiling enabled every kernel launch is bracketed by CUDA events on the
+ * stream it is launched on; profile_read synchronises, returns the summed device time (ms) and the
+ * launch count per kernel (index < crispy_ns_kernel_count()) since the last read, and clears them. */
+int crispy_ns_kernel_count(void);
+const char *crispy_ns_kernel_name(int k);
+int crispy_ns_batch_profile(crispy_ns_batch *b, int enable);
+int crispy_ns_batch_profile_read(crispy_ns_batch *b, double *ms_total, int64_t *n_launches, int n_kernels);
 void crispy_ns_batch_destroy(crispy_ns_batch *b);
 
 /* pinned host memory for the host-pointer path */

@@ -1,0 +1,79 @@
+// micro-benchmark: latency of the exact biquad recursion variants on one warp (B200)
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ double f2d_manual(float f) {  // exact for normal floats and zero
+  const uint32_t u = __float_as_uint(f);
+  const uint32_t e = (u >> 23) & 0xFF;
+  if (e == 0 || e == 255) return (double)f;
+  const uint32_t hi = (u & 0x80000000u) | (((u >> 3) & 0x0FFFFFFFu) + 0x38000000u);
+  const uint32_t lo = u << 29;
+  return __hiloint2double((int)hi, (int)lo);
+}
+
+template <int V>
+__global__ void k(const float *x, float *y, int n, long long *cycles, float *mout) {
+  __shared__ float sx[4096];
+  for (int i = threadIdx.x; i < 4096; i += 32) sx[i] = x[i];
+  __syncwarp();
+  float m0 = 0.f, m1 = 0.f;
+  const double a0 = (double)-1.99599f, a1 = (double)0.99600f;
+  float acc = 0.f;
+  long long t0 = clock64();
+  for (int i = 0; i < n; i++) {
+    const float xi = sx[(i + threadIdx.x) & 4095];
+    const float yi = xi + m0;
+    if (V == 0) {
+      const double xd = (double)xi, yd = (double)yi;
+      m0 = (float)((double)m1 + (-2.0 * xd - a0 * yd));
+      m1 = (float)(xd - a1 * yd);
+    } else if (V == 1) {
+      const double xd = (double)xi, yd = (double)yi;
+      m0 = (float)((double)m1 + fma(-a0, yd, -2.0 * xd));
+      m1 = (float)fma(-a1, yd, xd);
+    } else if (V == 2) {
+      const double xd = f2d_manual(xi), yd = f2d_manual(yi);
+      m0 = (float)(f2d_manual(m1) + fma(-a0, yd, -2.0 * xd));
+      m1 = (float)fma(-a1, yd, xd);
+    } else if (V == 3) {  // f32 only (NOT exact; latency reference)
+      m0 = m1 + (-2.0f * xi - -1.99599f * yi);
+      m1 = xi - 0.99600f * yi;
+    } else if (V == 4) {  // pure double state (not exact either): how slow is a DFMA chain
+      static double d0, d1;
+      const double xd = (double)xi;
+      double yd = xd + (double)m0;
+      m0 = (float)(0.0 + fma(-a0, yd, -2.0 * xd));
+      m1 = 0.f;
+    }
+    acc += yi;
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) {
+    cycles[0] = t1 - t0;
+  }
+  y[threadIdx.x] = acc;
+  mout[threadIdx.x] = m0 + m1;
+}
+
+int main() {
+  float *x, *y, *m;
+  long long *c;
+  cudaMalloc(&x, 4096 * 4);
+  cudaMalloc(&y, 32 * 4);
+  cudaMalloc(&m, 32 * 4);
+  cudaMalloc(&c, 8);
+  float hx[4096];
+  for (int i = 0; i < 4096; i++) hx[i] = 1000.f * sinf(0.01f * i) + 13.f * ((i * 7919) % 101);
+  cudaMemcpy(x, hx, sizeof(hx), cudaMemcpyHostToDevice);
+  const int n = 100000;
+  long long hc;
+#define RUN(V)                                                   \
+  k<V><<<1, 32>>>(x, y, n, c, m);                                \
+  k<V><<<1, 32>>>(x, y, n, c, m);                                \
+  cudaDeviceSynchronize();                                       \
+  cudaMemcpy(&hc, c, 8, cudaMemcpyDeviceToHost);                 \
+  printf("variant %d: %.1f cycles/sample (%s)\n", V, (double)hc / n, cudaGetErrorString(cudaGetLastError()));
+  RUN(0) RUN(1) RUN(2) RUN(3) RUN(4)
+  return 0;
+}

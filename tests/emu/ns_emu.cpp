@@ -72,7 +72,6 @@ int launch(int n_ctas, int n_threads, size_t smem_bytes, const std::function<voi
 
 constexpr int kPitchRun = 8;
 constexpr int kPitchThreads = 64;  // any thread count gives the same result; fewer OS threads run faster
-constexpr int kRnnThreads = 64;
 constexpr int kScanWarps = 1;
 }  // namespace
 
@@ -103,6 +102,7 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
   std::vector<float> hp((size_t)n_streams * hp_stride, 0.f);
   std::vector<uint32_t> tabw((size_t)n_streams * chunk_cap * ns::kTabWords, 0u);
   std::vector<float> rec((size_t)n_streams * chunk_cap * ns::kRecFloats, 0.f);
+  std::vector<ns::cf> spec((size_t)n_streams * chunk_cap * 2 * ns::kSpecStride);
   p.in = in;
   p.out = out;
   p.vad = vad;
@@ -112,6 +112,7 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
   p.hp = hp.data();
   p.tab = tabw.data();
   p.rec = rec.data();
+  p.spec = spec.data();
   p.tables = &tab;
   p.rnn_hdr = &pk.hdr;
   p.rnn_words = pk.words.data();
@@ -131,7 +132,12 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
     const int nf = (n_frames - f0) < chunk_cap ? (n_frames - f0) : chunk_cap;
     p.frame0 = f0;
     p.n_frames = nf;
-    int rc = launch((n_streams + 31) / 32, 32, sizeof(ns::HpSmem),
+    // the library keeps its chunk counter in the batch handle; the emulation keeps it in stream 0's
+    // state block (host side) so that chained calls see the same synthesis_mem buffer parity
+    int *chunk_counter = reinterpret_cast<int *>(state) + ns::kStateFloats - 1;
+    p.synth_sel = *chunk_counter & 1;
+    *chunk_counter += 1;
+    int rc = launch((n_streams + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem),
                     [&](void *sm) { ns::highpass_body(p, *(ns::HpSmem *)sm); });
     if (rc) return rc;
     const int runs = (nf + kPitchRun - 1) / kPitchRun;
@@ -146,10 +152,11 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
     rc = launch(spec_ctas, ns::kGroupThreads, sizeof(ns::SpecSmem),
                 [&](void *sm) { ns::spectrum_body(p, *(ns::SpecSmem *)sm); });
     if (rc) return rc;
-    rc = launch((n_streams + ns::kRnnStreams - 1) / ns::kRnnStreams, kRnnThreads, sizeof(ns::RnnSmem),
-                [&](void *sm) { ns::rnn_body<kRnnThreads>(p, *(ns::RnnSmem *)sm); });
+    rc = launch((n_streams + ns::kRnnStreams - 1) / ns::kRnnStreams, ns::kRnnThreads, sizeof(ns::RnnSmem),
+                [&](void *sm) { ns::rnn_body<ns::kRnnThreads>(p, *(ns::RnnSmem *)sm); });
     if (rc) return rc;
-    rc = launch(n_streams, ns::kGroupThreads, sizeof(ns::SpecSmem),
+    const int syn_tasks = n_streams * ((nf + ns::kSynRun - 1) / ns::kSynRun);
+    rc = launch(syn_tasks < 3 ? syn_tasks : 3, ns::kGroupThreads, sizeof(ns::SpecSmem),
                 [&](void *sm) { ns::synthesis_body(p, *(ns::SpecSmem *)sm); });
     if (rc) return rc;
   }

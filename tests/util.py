@@ -104,3 +104,20 @@ def make_signal(n_streams: int, n_frames: int, seed: int = 0xC0FFEE, first_strea
         if n_frames >= 60:
             x[1, 20 * 480:45 * 480] = 0.0
     return x
+
+
+ST_SYNTH = 1440  # ns_common.h kStSynth: two 480-float copies of synthesis_mem
+
+
+def canonical_state(state: np.ndarray) -> np.ndarray:
+    """The emulation keeps its chunk counter in the last word of stream 0's state block and
+    synthesis_mem is double buffered on that counter's parity (ns_common.h kStSynth).  Return the
+    state with the live synthesis_mem copy in slot 0, the stale copy and the counter cleared, so
+    that states reached through different chunkings compare equal."""
+    st = state.copy()
+    sel = int(st.view(np.int32)[0, -1]) & 1
+    live = st[:, ST_SYNTH + sel * 480: ST_SYNTH + (sel + 1) * 480].copy()
+    st[:, ST_SYNTH: ST_SYNTH + 480] = live
+    st[:, ST_SYNTH + 480: ST_SYNTH + 960] = 0.0
+    st.view(np.int32)[0, -1] = 0
+    return st
