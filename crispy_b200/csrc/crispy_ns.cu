@@ -22,8 +22,8 @@ constexpr int kPitchThreads = 320;  // 37 lag-quads x 8 frames = 296 lanes in th
 constexpr int kScanWarps = 4;
 
 __global__ void __launch_bounds__(ns::kHpThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
-  __shared__ ns::HpSmem sm;
-  ns::highpass_body(p, sm);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ns::highpass_body(p, *reinterpret_cast<ns::HpSmem *>(smem_raw));
 }
 __global__ void __launch_bounds__(kPitchThreads) ns_pitch_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -158,7 +158,8 @@ static cudaError_t configure_kernels(int dev) {
   static std::map<int, bool> configured;
   std::lock_guard<std::mutex> lk(mu);
   if (configured[dev]) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(ns_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(ns_highpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::HpSmem));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ns_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ns::PitchSmem<kPitchRun>));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(ns_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::SpecSmem));
@@ -238,7 +239,7 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
     p.synth_sel = (int)(b->chunks_done & 1);
     if (b->chunks_done >= kSlots) NS_CUDA(cudaStreamWaitEvent(b->s_hp, b->e_syn[slot], 0));
     NS_CUDA(prof_begin(b, 0, b->s_hp));
-    ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, 0, b->s_hp>>>(p);
+    ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem), b->s_hp>>>(p);
     NS_CUDA(cudaGetLastError());
     NS_CUDA(prof_end(b, b->s_hp));
     NS_CUDA(cudaEventRecord(b->e_hp[slot], b->s_hp));

@@ -34,26 +34,58 @@ NS_DEV f4 ld4(const float *p) { return *reinterpret_cast<const f4 *>(p); }
 // rounding of the state makes the recursion non-linear, so it is run serially, one lane per stream;
 // a warp moves 32-sample x 32-stream tiles through shared memory so HBM sees 128-byte rows.
 // =================================================================================================
-// Roles inside the 128-thread CTA (32 streams): warp 0 runs the recursion on the tile in ring slot
-// n%4; warp 1 loads tile n+3 from HBM into registers and parks tile n+1 in the ring (two register
-// sets, so a load has two iterations to land); warp 2 writes tile n-1 to the hp workspace (and the
-// last kHist samples to the state block); warp 3 copies the stream history into the workspace
-// front.  One __syncthreads per 32-sample tile.
-constexpr int kHpThreads = 128;
+// One CTA = 32 streams = two warps.  Warp 0, one lane per stream, walks the chunk in tiles of 96
+// samples: cp.async (LDGSTS) keeps three tiles of PCM in flight into a 4-slot shared-memory ring,
+// the lane runs the recursion over its row with 128-bit shared-memory accesses, then the warp
+// writes the tile to the hp workspace with 512-byte row segments.  There is no block barrier in the
+// loop (a bar.sync would wait for the global stores to drain).  Warp 1 copies the stream history
+// to the front of the workspace rows meanwhile.
+constexpr int kHpThreads = 64;
+constexpr int kHpTile = 96;        // samples per tile; 480 = 5 tiles
+constexpr int kHpPitch = 100;      // floats per row in shared memory: 4*lane banks apart for LDS.128
+constexpr int kHpStages = 4;
 struct HpSmem {
-  float tile[4][32][33];
+  float tile[kHpStages][32][kHpPitch];
 };
 
 NS_DEV float load_sample(const Params &p, int stream, long long idx) {
   const long long off = (long long)stream * p.in_stride + idx;
   if (p.flags & kFlagInI16) return (float)reinterpret_cast<const int16_t *>(p.in)[off];
-  const float v = reinterpret_cast<const float *>(p.in)[off];
-  return (p.flags & kFlagUnitScale) ? v * 32768.0f : v;  // audio.rs:264
+  return reinterpret_cast<const float *>(p.in)[off];
 }
 
-NS_DEV void hp_load_tile(const Params &p, int s0, int nrows, long long idx, float (&regs)[32]) {
+// tile `n` of the chunk -> ring slot; fast path: 16-byte cp.async, else plain loads
+NS_DEV void hp_fetch_tile(const Params &p, HpSmem &sm, int s0, int nrows, long long in0, int n, bool fast, int lane) {
+  float(*dst)[kHpPitch] = sm.tile[n & (kHpStages - 1)];
+  const long long idx0 = in0 + (long long)n * kHpTile;
+  if (fast) {
+    const float *in = reinterpret_cast<const float *>(p.in);
+    for (int q = lane; q < 32 * (kHpTile / 4); q += 32) {
+      const int r = q / (kHpTile / 4), c = (q - r * (kHpTile / 4)) * 4;
+      if (r < nrows) Simt::cp_async16(&dst[r][c], in + (long long)(s0 + r) * p.in_stride + idx0 + c);
+    }
+  } else {
+    for (int q = lane; q < 32 * kHpTile; q += 32) {
+      const int r = q / kHpTile, c = q - r * kHpTile;
+      dst[r][c] = (r < nrows) ? load_sample(p, s0 + r, idx0 + c) : 0.f;
+    }
+  }
+}
+
+NS_DEV void hp_copy_rows(const float *src, long long src_stride, float *dst, long long dst_stride, int nrows, int lane) {
+  for (int r = 0; r < nrows; r++) {  // kHist floats per row, batched so the loads overlap
+    const f4 *__restrict__ s = reinterpret_cast<const f4 *>(src + (long long)r * src_stride);
+    f4 *__restrict__ d = reinterpret_cast<f4 *>(dst + (long long)r * dst_stride);
+    f4 v[6];
+    for (int i0 = 0; i0 < kHist / 4; i0 += 6 * 32) {
 #pragma unroll
-  for (int r = 0; r < 32; r++) regs[r] = (r < nrows) ? load_sample(p, s0 + r, idx) : 0.f;
+      for (int u = 0; u < 6; u++)
+        if (i0 + u * 32 + lane < kHist / 4) v[u] = s[i0 + u * 32 + lane];
+#pragma unroll
+      for (int u = 0; u < 6; u++)
+        if (i0 + u * 32 + lane < kHist / 4) d[i0 + u * 32 + lane] = v[u];
+    }
+  }
 }
 
 NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
@@ -62,90 +94,83 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
   const int s0 = Simt::cta() * 32;
   const int nrows = (p.n_streams - s0) < 32 ? (p.n_streams - s0) : 32;
   const int nsamp = p.n_frames * kFrame;
-  const int ntiles = nsamp / 32;
-  const long long in0 = (long long)p.frame0 * kFrame;
-  const bool valid = lane < nrows;
-  float *st = p.state + (long long)(s0 + (valid ? lane : 0)) * kStateFloats;
-  float m0 = 0.f, m1 = 0.f;
-  float regs[2][32];
-  if (warp == 0 && valid) {
-    m0 = st[kStHp];
-    m1 = st[kStHp + 1];
-  } else if (warp == 1) {  // prologue: tile 0 straight into the ring, tiles 1 and 2 in flight
-    hp_load_tile(p, s0, nrows, in0 + lane, regs[0]);
-#pragma unroll
-    for (int r = 0; r < 32; r++) sm.tile[0][r][lane] = regs[0][r];
-    if (ntiles > 1) hp_load_tile(p, s0, nrows, in0 + 32 + lane, regs[1]);
-    if (ntiles > 2) hp_load_tile(p, s0, nrows, in0 + 64 + lane, regs[0]);
-  } else if (warp == 3) {  // history -> front of the workspace rows
-    for (int r = 0; r < nrows; r++) {
-      const float *__restrict__ src = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
-      float *__restrict__ dst = p.hp + (long long)(s0 + r) * p.hp_stride;
-      float v[15];
-      for (int i0 = 0; i0 < kHist; i0 += 15 * 32) {
-#pragma unroll
-        for (int u = 0; u < 15; u++) v[u] = src[i0 + u * 32 + lane];
-#pragma unroll
-        for (int u = 0; u < 15; u++) dst[i0 + u * 32 + lane] = v[u];
-      }
-    }
-  }
-  Simt::cta_sync();
-  const double a0 = (double)-1.99599f, a1 = (double)0.99600f;
+  const int ntiles = nsamp / kHpTile;
   const bool tail_direct = nsamp >= kHist;  // the new history is the chunk's own tail
-  for (int n = 0; n <= ntiles; n++) {
-    if (warp == 0) {
-      if (n < ntiles && valid) {
-        float *row = sm.tile[n & 3][lane];
-#pragma unroll 8
-        for (int i = 0; i < 32; i++) {
-          const float xi = row[i];
-          const float yi = xi + m0;
-          const double xd = (double)xi, yd = (double)yi;
-          m0 = (float)((double)m1 + (-2.0 * xd - a0 * yd));
-          m1 = (float)(xd - a1 * yd);
-          row[i] = yi;
-        }
-      }
-    } else if (warp == 1) {
-      if (n + 1 < ntiles) {
-        if ((n + 1) & 1) {
-#pragma unroll
-          for (int r = 0; r < 32; r++) sm.tile[(n + 1) & 3][r][lane] = regs[1][r];
-          if (n + 3 < ntiles) hp_load_tile(p, s0, nrows, in0 + (long long)(n + 3) * 32 + lane, regs[1]);
-        } else {
-#pragma unroll
-          for (int r = 0; r < 32; r++) sm.tile[(n + 1) & 3][r][lane] = regs[0][r];
-          if (n + 3 < ntiles) hp_load_tile(p, s0, nrows, in0 + (long long)(n + 3) * 32 + lane, regs[0]);
-        }
-      }
-    } else if (warp == 2) {
-      if (n >= 1) {
-        const int base = (n - 1) * 32;
-        const int hidx = base + lane - (nsamp - kHist);
-        for (int r = 0; r < nrows; r++) {
-          const float v = sm.tile[(n - 1) & 3][r][lane];
-          p.hp[(long long)(s0 + r) * p.hp_stride + kHist + base + lane] = v;
-          if (tail_direct && hidx >= 0) p.state[(long long)(s0 + r) * kStateFloats + kStHist + hidx] = v;
-        }
-      }
+  if (warp == 1) {
+    hp_copy_rows(p.state + (long long)s0 * kStateFloats + kStHist, kStateFloats, p.hp + (long long)s0 * p.hp_stride,
+                 p.hp_stride, nrows, lane);
+    if (tail_direct) Simt::cta_sync();  // the old history has been read: warp 0 may overwrite it from here on
+  } else {
+    const long long in0 = (long long)p.frame0 * kFrame;
+    const bool fast = !(p.flags & kFlagInI16) && (p.in_stride & 3) == 0 && (in0 & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
+    const float scale = ((p.flags & kFlagUnitScale) && !(p.flags & kFlagInI16)) ? 32768.0f : 1.0f;  // audio.rs:264
+    const bool valid = lane < nrows;
+    float *st = p.state + (long long)(s0 + (valid ? lane : 0)) * kStateFloats;
+    float m0 = valid ? st[kStHp] : 0.f, m1 = valid ? st[kStHp + 1] : 0.f;
+    const double a0 = (double)-1.99599f, a1 = (double)0.99600f;
+    for (int n = 0; n < kHpStages - 1; n++) {
+      if (n < ntiles) hp_fetch_tile(p, sm, s0, nrows, in0, n, fast, lane);
+      Simt::cp_async_commit();
     }
+    for (int n = 0; n < ntiles; n++) {
+      Simt::cp_async_wait<kHpStages - 2>();
+      Simt::warp_sync();
+      float(*tile)[kHpPitch] = sm.tile[n & (kHpStages - 1)];
+      if (valid) {
+        float *row = tile[lane];
+#pragma unroll 2
+        for (int c = 0; c < kHpTile; c += 4) {
+          const f4 xv = ld4(row + c);
+          const float x[4] = {xv.x * scale, xv.y * scale, xv.z * scale, xv.w * scale};
+          float y[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float xi = x[i];
+            const float yi = xi + m0;
+            const double xd = (double)xi, yd = (double)yi;
+            m0 = (float)((double)m1 + (-2.0 * xd - a0 * yd));
+            m1 = (float)(xd - a1 * yd);
+            y[i] = yi;
+          }
+          *reinterpret_cast<f4 *>(row + c) = f4{y[0], y[1], y[2], y[3]};
+        }
+      }
+      Simt::warp_sync();
+      const int base = n * kHpTile;
+      if (tail_direct && base + kHpTile > nsamp - kHist && base <= nsamp - kHist) Simt::cta_sync();  // see warp 1
+      for (int q = lane; q < 32 * (kHpTile / 4); q += 32) {
+        const int r = q / (kHpTile / 4), c = (q - r * (kHpTile / 4)) * 4;
+        if (r < nrows) {
+          const f4 v = ld4(&tile[r][c]);
+          *reinterpret_cast<f4 *>(p.hp + (long long)(s0 + r) * p.hp_stride + kHist + base + c) = v;
+          const int hidx = base + c - (nsamp - kHist);
+          if (tail_direct && hidx >= 0)
+            *reinterpret_cast<f4 *>(p.state + (long long)(s0 + r) * kStateFloats + kStHist + hidx) = v;
+        }
+      }
+      Simt::warp_sync();
+      if (n + kHpStages - 1 < ntiles) hp_fetch_tile(p, sm, s0, nrows, in0, n + kHpStages - 1, fast, lane);
+      Simt::cp_async_commit();
+    }
+    Simt::cp_async_wait<0>();
+    if (valid) {
+      st[kStHp] = m0;
+      st[kStHp + 1] = m1;
+    }
+  }
+  if (!tail_direct) {  // short chunk: last kHist samples of [history | chunk] -> state
     Simt::cta_sync();
-  }
-  if (warp == 0 && valid) {
-    st[kStHp] = m0;
-    st[kStHp + 1] = m1;
-  }
-  if (!tail_direct && warp == 3) {  // short chunk: last kHist samples of [history | chunk] -> state
-    for (int r = 0; r < nrows; r++) {
-      const float *src = p.hp + (long long)(s0 + r) * p.hp_stride + nsamp;
-      float *dst = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
-      float v[15];
-      for (int i0 = 0; i0 < kHist; i0 += 15 * 32) {  // read everything before overwriting (src may alias dst's source)
-#pragma unroll
-        for (int u = 0; u < 15; u++) v[u] = src[i0 + u * 32 + lane];
-#pragma unroll
-        for (int u = 0; u < 15; u++) dst[i0 + u * 32 + lane] = v[u];
+    if (warp == 1) {
+      // every row is read in full into registers? no: kHist floats do not fit; stage through the (now idle) ring
+      float *stage = &sm.tile[0][0][0];
+      for (int r = 0; r < nrows; r++) {
+        const float *src = p.hp + (long long)(s0 + r) * p.hp_stride + nsamp;
+        float *dst = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
+        for (int i = lane; i < kHist; i += 32) stage[i] = src[i];
+        Simt::warp_sync();
+        for (int i = lane; i < kHist; i += 32) dst[i] = stage[i];
+        Simt::warp_sync();
       }
     }
   }

@@ -40,6 +40,16 @@ struct Simt {
   static NS_DEV unsigned ballot(bool pred) { return __ballot_sync(0xffffffffu, pred); }
   static NS_DEV int atomic_add_shared(int *p, int v) { return atomicAdd(p, v); }
   static NS_DEV int n_ctas() { return (int)gridDim.x; }
+  // 16-byte asynchronous global -> shared copy (LDGSTS), grouped with commit / wait<N pending groups>
+  static NS_DEV void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+  }
+  static NS_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  template <int N>
+  static NS_DEV void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+  }
 };
 }  // namespace ns
 
@@ -121,6 +131,10 @@ struct Simt {
   }
   static int atomic_add_shared(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
   static int n_ctas() { return g_emu.cta->n_ctas; }
+  static void cp_async16(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+  static void cp_async_commit() {}
+  template <int N>
+  static void cp_async_wait() {}
 };
 }  // namespace ns
 
