@@ -140,7 +140,7 @@ static int default_chunk_cap(int n_streams) {
   const char *env = getenv("CRISPY_NS_CHUNK_FRAMES");
   if (env && atoi(env) > 0) return atoi(env) > 4096 ? 4096 : atoi(env);
   const long long per_frame = (long long)n_streams * (ns::kFrame * 4 + ns::kTabWords * 4 + ns::kRecFloats * 4 + 2 * ns::kSpecStride * 8);
-  long long cap = (64ll << 20) / per_frame;
+  long long cap = (384ll << 20) / per_frame;  // ~1 GB of workspace over the three slots
   cap = (cap / kPitchRun) * kPitchRun;
   if (cap < kPitchRun) cap = kPitchRun;
   if (cap > 256) cap = 256;
