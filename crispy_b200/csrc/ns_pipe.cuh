@@ -54,15 +54,17 @@ NS_DEV float load_sample(const Params &p, int stream, long long idx) {
   return reinterpret_cast<const float *>(p.in)[off];
 }
 
-// tile `n` of the chunk -> ring slot; fast path: 16-byte cp.async, else plain loads
+// tile `n` of the chunk -> ring slot; fast path: 16-byte cp.async (lanes 0..23 cover one 384-byte row
+// segment per instruction), else plain loads
 NS_DEV void hp_fetch_tile(const Params &p, HpSmem &sm, int s0, int nrows, long long in0, int n, bool fast, int lane) {
   float(*dst)[kHpPitch] = sm.tile[n & (kHpStages - 1)];
   const long long idx0 = in0 + (long long)n * kHpTile;
   if (fast) {
-    const float *in = reinterpret_cast<const float *>(p.in);
-    for (int q = lane; q < 32 * (kHpTile / 4); q += 32) {
-      const int r = q / (kHpTile / 4), c = (q - r * (kHpTile / 4)) * 4;
-      if (r < nrows) Simt::cp_async16(&dst[r][c], in + (long long)(s0 + r) * p.in_stride + idx0 + c);
+    if (lane < kHpTile / 4) {
+      const float *src = reinterpret_cast<const float *>(p.in) + (long long)s0 * p.in_stride + idx0 + 4 * lane;
+      float *d = &dst[0][4 * lane];
+#pragma unroll 8
+      for (int r = 0; r < nrows; r++, src += p.in_stride, d += kHpPitch) Simt::cp_async16(d, src);
     }
   } else {
     for (int q = lane; q < 32 * kHpTile; q += 32) {
@@ -139,14 +141,20 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
       Simt::warp_sync();
       const int base = n * kHpTile;
       if (tail_direct && base + kHpTile > nsamp - kHist && base <= nsamp - kHist) Simt::cta_sync();  // see warp 1
-      for (int q = lane; q < 32 * (kHpTile / 4); q += 32) {
-        const int r = q / (kHpTile / 4), c = (q - r * (kHpTile / 4)) * 4;
-        if (r < nrows) {
-          const f4 v = ld4(&tile[r][c]);
-          *reinterpret_cast<f4 *>(p.hp + (long long)(s0 + r) * p.hp_stride + kHist + base + c) = v;
-          const int hidx = base + c - (nsamp - kHist);
-          if (tail_direct && hidx >= 0)
-            *reinterpret_cast<f4 *>(p.state + (long long)(s0 + r) * kStateFloats + kStHist + hidx) = v;
+      if (lane < kHpTile / 4) {
+        const int c = 4 * lane;
+        float *dsth = p.hp + (long long)s0 * p.hp_stride + kHist + base + c;
+        const int hidx = base + c - (nsamp - kHist);
+        if (tail_direct && hidx >= 0) {
+          float *dsts = p.state + (long long)s0 * kStateFloats + kStHist + hidx;
+          for (int r = 0; r < nrows; r++, dsth += p.hp_stride, dsts += kStateFloats) {
+            const f4 v = ld4(&tile[r][c]);
+            *reinterpret_cast<f4 *>(dsth) = v;
+            *reinterpret_cast<f4 *>(dsts) = v;
+          }
+        } else {
+#pragma unroll 8
+          for (int r = 0; r < nrows; r++, dsth += p.hp_stride) *reinterpret_cast<f4 *>(dsth) = ld4(&tile[r][c]);
         }
       }
       Simt::warp_sync();
