@@ -36,9 +36,13 @@ __global__ void __launch_bounds__(ns::kGroupThreads) ns_spectrum_kernel(const __
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ns::spectrum_body(p, *reinterpret_cast<ns::SpecSmem *>(smem_raw));
 }
-__global__ void __launch_bounds__(ns::kRnnThreads, 1) ns_rnn_kernel(const __grid_constant__ ns::Params p) {
+__global__ void __launch_bounds__(32 * ns::kFeatWarps) ns_features_kernel(const __grid_constant__ ns::Params p) {
+  __shared__ ns::FeatSmem sm;
+  ns::features_body(p, sm);
+}
+__global__ void __launch_bounds__(ns::kMmaThreads, 1) ns_rnn_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ns::rnn_body<ns::kRnnThreads>(p, *reinterpret_cast<ns::RnnSmem *>(smem_raw));
+  ns::rnn_body(p, *reinterpret_cast<ns::RnnSmem *>(smem_raw));
 }
 __global__ void __launch_bounds__(ns::kGroupThreads) ns_synthesis_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -100,6 +104,7 @@ struct crispy_ns_batch {
   uint32_t *d_tab[kSlots] = {nullptr, nullptr, nullptr};
   float *d_rec[kSlots] = {nullptr, nullptr, nullptr};
   ns::cf *d_spec[kSlots] = {nullptr, nullptr, nullptr};
+  uint32_t *d_featq[kSlots] = {nullptr, nullptr, nullptr};
   cudaStream_t s_hp = nullptr, s_an = nullptr, s_syn = nullptr;
   cudaEvent_t e_start = nullptr;
   cudaEvent_t e_hp[kSlots] = {nullptr, nullptr, nullptr}, e_an[kSlots] = {nullptr, nullptr, nullptr},
@@ -236,6 +241,7 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
     p.tab = b->d_tab[slot];
     p.rec = b->d_rec[slot];
     p.spec = b->d_spec[slot];
+    p.featq = b->d_featq[slot];
     p.synth_sel = (int)(b->chunks_done & 1);
     if (b->chunks_done >= kSlots) NS_CUDA(cudaStreamWaitEvent(b->s_hp, b->e_syn[slot], 0));
     NS_CUDA(prof_begin(b, 0, b->s_hp));
@@ -259,20 +265,25 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
     ns_spectrum_kernel<<<(int)spec_ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), b->s_an>>>(p);
     NS_CUDA(cudaGetLastError());
     NS_CUDA(prof_end(b, b->s_an));
+    const int groups = (n + ns::kMmaStreams - 1) / ns::kMmaStreams;
+    NS_CUDA(prof_begin(b, 4, b->s_an));
+    ns_features_kernel<<<(groups * ns::kMmaStreams + ns::kFeatWarps - 1) / ns::kFeatWarps, 32 * ns::kFeatWarps, 0, b->s_an>>>(p);
+    NS_CUDA(cudaGetLastError());
+    NS_CUDA(prof_end(b, b->s_an));
     NS_CUDA(cudaEventRecord(b->e_an[slot], b->s_an));
     NS_CUDA(cudaStreamWaitEvent(b->s_syn, b->e_an[slot], 0));
-    NS_CUDA(prof_begin(b, 4, b->s_syn));
-    ns_rnn_kernel<<<(n + ns::kRnnStreams - 1) / ns::kRnnStreams, ns::kRnnThreads, sizeof(ns::RnnSmem), b->s_syn>>>(p);
+    NS_CUDA(prof_begin(b, 5, b->s_syn));
+    ns_rnn_kernel<<<groups, ns::kMmaThreads, sizeof(ns::RnnSmem), b->s_syn>>>(p);
     NS_CUDA(cudaGetLastError());
     NS_CUDA(prof_end(b, b->s_syn));
-    NS_CUDA(prof_begin(b, 5, b->s_syn));
+    NS_CUDA(prof_begin(b, 6, b->s_syn));
     long long syn_ctas = (long long)n * ((nf + ns::kSynRun - 1) / ns::kSynRun);
     if (syn_ctas > (long long)b->n_sms * 8) syn_ctas = (long long)b->n_sms * 8;
     ns_synthesis_kernel<<<(int)syn_ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), b->s_syn>>>(p);
     NS_CUDA(cudaGetLastError());
     NS_CUDA(prof_end(b, b->s_syn));
     NS_CUDA(cudaEventRecord(b->e_syn[slot], b->s_syn));
-    b->launches += 6;
+    b->launches += 7;
     b->chunks_done += 1;
     last_slot = slot;
   }
@@ -359,6 +370,7 @@ void crispy_ns_batch_destroy(crispy_ns_batch *b) {
     cudaFree(b->d_tab[i]);
     cudaFree(b->d_rec[i]);
     cudaFree(b->d_spec[i]);
+    cudaFree(b->d_featq[i]);
     if (b->e_hp[i]) cudaEventDestroy(b->e_hp[i]);
     if (b->e_an[i]) cudaEventDestroy(b->e_an[i]);
     if (b->e_syn[i]) cudaEventDestroy(b->e_syn[i]);
@@ -428,6 +440,9 @@ int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_strea
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_tab[i], nf * ns::kTabWords * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_rec[i], nf * ns::kRecFloats * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_spec[i], nf * 2 * ns::kSpecStride * sizeof(ns::cf));
+    if (e == cudaSuccess)
+      e = cudaMalloc((void **)&b->d_featq[i], (size_t)((n_streams + ns::kMmaStreams - 1) / ns::kMmaStreams) * b->chunk_cap *
+                                                  ns::kFeatBlockWords * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_hp[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_an[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_syn[i], cudaEventDisableTiming);
@@ -616,18 +631,19 @@ int crispy_ns_batch_load_state(crispy_ns_batch *b, const void *buf, size_t len) 
 int crispy_ns_batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_ctas, int64_t *launches,
                          int64_t *frames_done) {  // (rnn_streams_per_cta, chunk_frames, ...)
   if (!b) return fail(CRISPY_NS_EINVAL, "batch_info: null handle");
-  if (streams_per_cta) *streams_per_cta = ns::kRnnStreams;
+  if (streams_per_cta) *streams_per_cta = ns::kMmaStreams;
   if (n_ctas) *n_ctas = b->chunk_cap;
   if (launches) *launches = b->launches;
   if (frames_done) *frames_done = b->frames_done;
   return CRISPY_NS_OK;
 }
 
-int crispy_ns_kernel_count(void) { return 6; }
+constexpr int kNumKernels = 7;
+int crispy_ns_kernel_count(void) { return kNumKernels; }
 const char *crispy_ns_kernel_name(int k) {
-  static const char *names[6] = {"ns_highpass_kernel", "ns_pitch_kernel", "ns_pitchscan_kernel",
-                                 "ns_spectrum_kernel", "ns_rnn_kernel", "ns_synthesis_kernel"};
-  return (k >= 0 && k < 6) ? names[k] : "";
+  static const char *names[kNumKernels] = {"ns_highpass_kernel", "ns_pitch_kernel",    "ns_pitchscan_kernel", "ns_spectrum_kernel",
+                                           "ns_features_kernel", "ns_rnn_kernel",      "ns_synthesis_kernel"};
+  return (k >= 0 && k < kNumKernels) ? names[k] : "";
 }
 int crispy_ns_batch_profile(crispy_ns_batch *b, int enable) {
   if (!b) return fail(CRISPY_NS_EINVAL, "batch_profile: null handle");
@@ -638,7 +654,7 @@ int crispy_ns_batch_profile(crispy_ns_batch *b, int enable) {
   return CRISPY_NS_OK;
 }
 int crispy_ns_batch_profile_read(crispy_ns_batch *b, double *ms_total, int64_t *n_launches, int n_kernels) {
-  if (!b || !ms_total || !n_launches || n_kernels < 6) return fail(CRISPY_NS_EINVAL, "batch_profile_read: bad argument");
+  if (!b || !ms_total || !n_launches || n_kernels < kNumKernels) return fail(CRISPY_NS_EINVAL, "batch_profile_read: bad argument");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(cudaDeviceSynchronize());
   for (int k = 0; k < n_kernels; k++) {

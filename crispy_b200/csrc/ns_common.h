@@ -27,6 +27,7 @@ constexpr int kGroupThreads = 128;   // threads cooperating on one frame's spect
 //   tab : per frame, the pitch candidate table remove_doubling's serial decision walks (kTabWords)
 //   rec : per frame, the small record passed between phases (kRecFloats)
 //   spec: per frame, the spectra X and P (K3 -> K5)
+//   featq: per (16-stream group, frame), the 42 features pre-split for the tensor pipe (K3b -> K4)
 constexpr int kHist = 1440;          // >= 1248 (pitch_buf history) and a multiple of 480
 constexpr int kLpLen = 864;          // pitch_buf downsampled by 2
 constexpr int kLpStride = 872;       // padded row of the per-frame downsampled buffers
@@ -99,40 +100,61 @@ struct Tables {
   int32_t eband[24];     // band edges in bins (eband5ms * 4), 22 used
 };
 
-// ---- RNN weights repacked for the recurrent-core kernel (K4).
-// Activations of the 8 streams of a CTA live in shared memory as two f32 arrays of rows [k][8]:
-//   A: dense(24) | vad_gru_state(24) | features(42) | noise_gru_state(48) | denoise_gru_state(96)
-//   R: r*h of the three GRUs: vad(24) | noise(48) | denoise(96)
-// so that every matrix-vector job reads one contiguous range of A plus, for the candidate-gate jobs,
-// one contiguous range of R.  A job with N outputs is worked by cp = ceil(N/2) column pairs x ksplit
-// slices of its K inputs; thread tj = ks*cp + pair keeps 2 x 8 accumulators and reads its weights
-// as packed bf16 pairs (int8 values are exact in bf16) from words[w_off + i*(cp*ksplit) + tj].
-constexpr int kRnnThreads = 256;
-constexpr int kActDense = 0, kActHVad = 24, kActFeat = 48, kActHNoise = 90, kActHDen = 138, kActRows = 234;
-constexpr int kRhVad = 0, kRhNoise = 24, kRhDen = 72, kRhRows = 168;
-constexpr int kNumJobs = 8;
-enum JobKind : int32_t { kJobDense = 0, kJobZR = 1, kJobC = 2 };
-struct JobDesc {
-  int32_t n_out;       // N
-  int32_t activation;  // 0 tanh, 1 sigmoid, 2 relu (of the layer; ZR jobs are always sigmoid)
-  int32_t kind;        // JobKind
-  int32_t cp, ksplit, len;  // column pairs, K slices, slice length
-  int32_t k_total;     // K = len1 + len2
-  int32_t off1, len1;  // rows of A
-  int32_t off2, len2;  // rows of R (candidate-gate jobs), len2 == 0 otherwise
-  int32_t w_off;       // offset (uint32 words) into words
-  int32_t b_off;       // offset into bias
-  int32_t out_off;     // Dense: row of A (or -1: gains); ZR / C: row of A holding this GRU's state
-  int32_t rh_off;      // ZR: row of R receiving r*h
+// ---- recurrent core (K4) on the tensor pipe: mma.sync m16n8k16, bf16 x bf16 -> f32.
+// One CTA carries 16 streams (the M dimension of one MMA tile).  Every activation vector lives in
+// shared memory already split into bf16 hi + bf16 lo (x = hi + lo to 2^-17 relative) and already in
+// the MMA A-fragment order, one "k-tile" = 16 consecutive inputs x 16 streams = 32 lanes x 4 words:
+//   element (stream row r, input kk) of a k-tile -> lane (r%8)*4 + (kk%8)/2, word (r/8) + 2*(kk/8),
+//   halfword kk%2.
+// The accumulator (C) fragment of an n-tile of 8 outputs has the same lane/word pattern as half a
+// k-tile, so an epilogue lane writes its own activations straight back as the next job's A operand.
+// Weights (int8, exact in bf16) are packed on the host as B fragments per (job, k-tile, n-tile):
+// 32 lanes x 2 words, lane = n*4 + (kk%8)/2, word kk/8, halfword kk%2.
+constexpr int kMmaStreams = 16;
+constexpr int kMmaWarps = 8;
+constexpr int kMmaThreads = 32 * kMmaWarps;
+constexpr int kKtWords = 128;            // 32 lanes x 4 words per k-tile (per hi / lo plane)
+// resident k-tiles (segments); the feature k-tiles are double buffered separately
+constexpr int kKtDV = 0;                 // [dense 24 | vad state 24]            3 k-tiles
+constexpr int kKtDVR = 3;                // [dense 24 | r*h of the vad GRU 24]   3
+constexpr int kKtNH = 6;                 // noise state 48                        3
+constexpr int kKtNR = 9;                 // r*h of the noise GRU                  3
+constexpr int kKtDH = 12;                // denoise state 96                      6
+constexpr int kKtDR = 18;                // r*h of the denoise GRU                6
+constexpr int kKtResident = 24;
+constexpr int kKtF = 24;                 // virtual index of the 3 feature k-tiles (42 features + 6 zeros)
+constexpr int kFeatKt = 3;
+// per (16-stream group, frame) block K3b hands to K4: hi plane, lo plane, 16 silence flags
+constexpr int kFeatBlockWords = 2 * kFeatKt * kKtWords + kMmaStreams;  // 784 words = 3136 B
+enum MmaJob : int32_t {
+  kJDense = 0,   // input_dense            K = F            N = 24
+  kJVadZR = 1,   // vad_gru z | r          K = DV           N = 48
+  kJVadC = 2,    // vad_gru candidate      K = DVR          N = 24
+  kJNoiseZR = 3, // noise_gru z | r        K = DV, F, NH    N = 96
+  kJNoiseC = 4,  // noise_gru candidate    K = DV, F, NR    N = 48
+  kJDenZR = 5,   // denoise_gru z | r      K = DV[1..2], NH, F, DH   N = 192
+  kJDenC = 6,    // denoise_gru candidate  K = DV[1..2], NH, F, DR   N = 96
+  kJOut = 7,     // denoise_output         K = DH           N = 22 (24)
+  kJVadOut = 8,  // vad_output             K = DV           N = 1 (8)
+  kNumMmaJobs = 9
+};
+constexpr int kMmaMaxKt = 14;
+struct MmaJobDesc {
+  int32_t nkt;               // k-tiles in this job's K list
+  int32_t nnt;               // n-tiles (8 outputs each)
+  int32_t w_off;             // offset (uint32 words) of the job's B fragments: [i][nt][32][2]
+  int32_t b_off;             // offset into bias (nnt*8 f32, zero padded)
+  int32_t activation;        // 0 tanh, 1 sigmoid, 2 relu (of the layer)
+  int32_t kt[kMmaMaxKt];     // virtual k-tile index of list position i
   int32_t pad;
 };
 struct RnnHeader {
-  JobDesc jobs[kNumJobs];
-  int32_t vad_w_off;   // vad_output: 24 f32 weights + bias at bias[vad_w_off .. +25)
-  int32_t vad_activation;
+  MmaJobDesc jobs[kNumMmaJobs];
   int32_t n_words;
   int32_t n_bias;
 };
+constexpr int kMmaWordsMax = 46272;      // 723 B-fragment tiles x 64 words for the RNNoise topology
+constexpr int kMmaBiasMax = 576;
 
 // ---- launch parameters
 enum Flags : uint32_t {
@@ -155,6 +177,7 @@ struct Params {
   uint32_t *tab;          // [n_streams][chunk_cap][kTabWords]
   float *rec;             // [n_streams][chunk_cap][kRecFloats]
   cf *spec;               // [n_streams][chunk_cap][2][kSpecStride]: X and P of every frame
+  uint32_t *featq;        // [ceil(n_streams/16)][chunk_cap][kFeatBlockWords]: features as bf16 hi/lo A fragments
   const Tables *tables;
   const RnnHeader *rnn_hdr;
   const uint32_t *rnn_words;

@@ -255,13 +255,7 @@ bool model_from_bytes(Model &m, const void *blob, size_t len, std::string &err) 
   return false;
 }
 
-// ---- repacking -----------------------------------------------------------------------------------
-// One matrix-vector job: rows = its K inputs in the order of the kernel's activation layout
-// (ns_common.h), each row naming where the weight of (row, col) lives in the model.
-struct RowSrc {
-  std::function<int8_t(int col)> w;
-};
-
+// ---- repacking for the tensor-pipe recurrent core (ns_common.h "recurrent core (K4)") ---------------
 static uint32_t bf16_bits(int v) {  // int8 value -> bf16 bit pattern (exact)
   float f = (float)v;
   uint32_t u;
@@ -269,41 +263,52 @@ static uint32_t bf16_bits(int v) {  // int8 value -> bf16 bit pattern (exact)
   return u >> 16;
 }
 
-static void add_job(PackedRnn &out, int job, int kind, int n_out, int act, int off1, int len1, int off2,
-                    int len2, int out_off, int rh_off, const std::vector<RowSrc> &rows,
-                    const std::function<int8_t(int col)> &bias) {
-  JobDesc &jd = out.hdr.jobs[job];
+namespace {
+enum Src { kSrcNone = 0, kSrcDense, kSrcVadH, kSrcFeat, kSrcNoiseH, kSrcDenH };
+struct SrcIdx {
+  Src src;
+  int idx;
+};
+// which activation sits at input kk of virtual k-tile vkt (ns_common.h kKt*)
+SrcIdx seg_src(int vkt, int kk) {
+  if (vkt < kKtNH) {  // DV and DVR: [dense 24 | vad state (or r*h) 24]
+    const int pos = (vkt % 3) * 16 + kk;
+    return pos < 24 ? SrcIdx{kSrcDense, pos} : SrcIdx{kSrcVadH, pos - 24};
+  }
+  if (vkt < kKtDH) return SrcIdx{kSrcNoiseH, ((vkt - kKtNH) % 3) * 16 + kk};
+  if (vkt < kKtResident) return SrcIdx{kSrcDenH, ((vkt - kKtDH) % 6) * 16 + kk};
+  const int f = (vkt - kKtF) * 16 + kk;
+  return f < kFeatures ? SrcIdx{kSrcFeat, f} : SrcIdx{kSrcNone, 0};
+}
+}  // namespace
+
+// weight(src, idx, col) of one job; 0 where the job does not read that input / column
+using WeightFn = std::function<int(SrcIdx, int col)>;
+
+static void add_mma_job(PackedRnn &out, int job, const std::vector<int> &kts, int n_out, int act, const WeightFn &w,
+                        const std::function<int(int col)> &bias) {
+  MmaJobDesc &jd = out.hdr.jobs[job];
   memset(&jd, 0, sizeof(jd));
-  const int K = (int)rows.size();
-  jd.n_out = n_out;
-  jd.activation = act;
-  jd.kind = kind;
-  jd.cp = (n_out + 1) / 2;
-  jd.ksplit = kRnnThreads / jd.cp;
-  if (jd.ksplit > K) jd.ksplit = K;
-  jd.len = (K + jd.ksplit - 1) / jd.ksplit;
-  jd.k_total = K;
-  jd.off1 = off1;
-  jd.len1 = len1;
-  jd.off2 = off2;
-  jd.len2 = len2;
+  jd.nkt = (int32_t)kts.size();
+  jd.nnt = (n_out + 7) / 8;
   jd.w_off = (int32_t)out.words.size();
   jd.b_off = (int32_t)out.bias.size();
-  jd.out_off = out_off;
-  jd.rh_off = rh_off;
-  const int stride = jd.cp * jd.ksplit;
-  for (int i = 0; i < jd.len; i++)
-    for (int tj = 0; tj < stride; tj++) {
-      const int pair = tj % jd.cp, ks = tj / jd.cp, k = ks * jd.len + i;
-      uint32_t lo = 0, hi = 0;
-      if (k < K) {
-        const int c0 = 2 * pair, c1 = 2 * pair + 1;
-        lo = bf16_bits(rows[k].w(c0));
-        if (c1 < n_out) hi = bf16_bits(rows[k].w(c1));
-      }
-      out.words.push_back(lo | (hi << 16));
-    }
-  for (int col = 0; col < n_out; col++) out.bias.push_back((float)bias(col));
+  jd.activation = act;
+  for (int i = 0; i < jd.nkt; i++) jd.kt[i] = kts[i];
+  for (int i = 0; i < jd.nkt; i++)
+    for (int nt = 0; nt < jd.nnt; nt++)
+      for (int lane = 0; lane < 32; lane++)
+        for (int r = 0; r < 2; r++) {
+          const int n = nt * 8 + lane / 4;
+          uint32_t word = 0;
+          for (int h = 0; h < 2; h++) {
+            const int kk = (lane % 4) * 2 + 8 * r + h;
+            const int v = (n < n_out) ? w(seg_src(kts[i], kk), n) : 0;
+            word |= bf16_bits(v) << (16 * h);
+          }
+          out.words.push_back(word);
+        }
+  for (int col = 0; col < jd.nnt * 8; col++) out.bias.push_back(col < n_out ? (float)bias(col) : 0.f);
 }
 
 void pack_rnn(const Model &m, PackedRnn &out) {
@@ -312,66 +317,71 @@ void pack_rnn(const Model &m, PackedRnn &out) {
   memset(&out.hdr, 0, sizeof(out.hdr));
   const DenseLayer &d0 = m.input_dense, &dv = m.vad_output, &dg = m.denoise_output;
   const GruLayer &gv = m.vad_gru, &gn = m.noise_gru, &gd = m.denoise_gru;
-  // weight of input row `row` / recurrent row `row` of a GRU at gate column col0 + col
-  auto gi = [](const GruLayer &g, int row, int col0) {
-    const int st = 3 * g.nb_neurons;
-    return RowSrc{[&g, row, col0, st](int col) { return g.input_weights[(size_t)row * st + col0 + col]; }};
+  auto gin = [](const GruLayer &g, int row, int col) { return (int)g.input_weights[(size_t)row * 3 * g.nb_neurons + col]; };
+  auto grec = [](const GruLayer &g, int row, int col) { return (int)g.recurrent_weights[(size_t)row * 3 * g.nb_neurons + col]; };
+  const std::vector<int> kDV = {kKtDV, kKtDV + 1, kKtDV + 2}, kDVR = {kKtDVR, kKtDVR + 1, kKtDVR + 2};
+  const std::vector<int> kF = {kKtF, kKtF + 1, kKtF + 2};
+  auto cat = [](std::initializer_list<std::vector<int>> parts) {
+    std::vector<int> v;
+    for (const auto &p : parts) v.insert(v.end(), p.begin(), p.end());
+    return v;
   };
-  auto gr = [](const GruLayer &g, int row, int col0) {
-    const int st = 3 * g.nb_neurons;
-    return RowSrc{[&g, row, col0, st](int col) { return g.recurrent_weights[(size_t)row * st + col0 + col]; }};
+  auto range = [](int k0, int n) {
+    std::vector<int> v;
+    for (int i = 0; i < n; i++) v.push_back(k0 + i);
+    return v;
   };
-  auto gb = [](const GruLayer &g, int col0) { return [&g, col0](int col) { return g.bias[col0 + col]; }; };
-  auto dw = [](const DenseLayer &d, int row) {
-    return RowSrc{[&d, row](int col) { return d.weights[(size_t)row * d.nb_neurons + col]; }};
+  // input_dense: features -> 24
+  add_mma_job(out, kJDense, kF, 24, d0.activation,
+              [&](SrcIdx s, int col) { return s.src == kSrcFeat ? (int)d0.weights[(size_t)s.idx * 24 + col] : 0; },
+              [&](int col) { return (int)d0.bias[col]; });
+  // vad_gru: input dense(24), state 24
+  auto vad_w = [&](int col0) {
+    return [&, col0](SrcIdx s, int col) {
+      if (s.src == kSrcDense) return gin(gv, s.idx, col0 + col);
+      if (s.src == kSrcVadH) return grec(gv, s.idx, col0 + col);
+      return 0;
+    };
   };
-  auto db = [](const DenseLayer &d) { return [&d](int col) { return d.bias[col]; }; };
-  std::vector<RowSrc> rows;
-
-  // job 0: input_dense, reads features = A[48:90)
-  rows.clear();
-  for (int k = 0; k < 42; k++) rows.push_back(dw(d0, k));
-  add_job(out, 0, kJobDense, 24, d0.activation, kActFeat, 42, 0, 0, kActDense, 0, rows, db(d0));
-  // vad_gru: input = dense(24); z,r read A[0:48) = dense | vad state
-  rows.clear();
-  for (int k = 0; k < 24; k++) rows.push_back(gi(gv, k, 0));
-  for (int k = 0; k < 24; k++) rows.push_back(gr(gv, k, 0));
-  add_job(out, 1, kJobZR, 48, 1, kActDense, 48, 0, 0, kActHVad, kRhVad, rows, gb(gv, 0));
-  rows.clear();
-  for (int k = 0; k < 24; k++) rows.push_back(gi(gv, k, 48));
-  for (int k = 0; k < 24; k++) rows.push_back(gr(gv, k, 48));
-  add_job(out, 2, kJobC, 24, gv.activation, kActDense, 24, kRhVad, 24, kActHVad, 0, rows, gb(gv, 48));
-  // noise_gru: input = [dense(24) | vad state(24) | features(42)] = A[0:90), recurrent = A[90:138)
-  rows.clear();
-  for (int k = 0; k < 90; k++) rows.push_back(gi(gn, k, 0));
-  for (int k = 0; k < 48; k++) rows.push_back(gr(gn, k, 0));
-  add_job(out, 3, kJobZR, 96, 1, kActDense, 138, 0, 0, kActHNoise, kRhNoise, rows, gb(gn, 0));
-  rows.clear();
-  for (int k = 0; k < 90; k++) rows.push_back(gi(gn, k, 96));
-  for (int k = 0; k < 48; k++) rows.push_back(gr(gn, k, 96));
-  add_job(out, 4, kJobC, 48, gn.activation, kActDense, 90, kRhNoise, 48, kActHNoise, 0, rows, gb(gn, 96));
-  // denoise_gru: input = [vad state(24) | noise state(48) | features(42)]; in A's order the rows are
-  // vad state (input 0..23), features (input 72..113), noise state (input 24..71), then the recurrent rows
-  auto den_rows = [&](int col0) {
-    rows.clear();
-    for (int k = 0; k < 24; k++) rows.push_back(gi(gd, k, col0));
-    for (int k = 0; k < 42; k++) rows.push_back(gi(gd, 72 + k, col0));
-    for (int k = 0; k < 48; k++) rows.push_back(gi(gd, 24 + k, col0));
-    for (int k = 0; k < 96; k++) rows.push_back(gr(gd, k, col0));
+  add_mma_job(out, kJVadZR, kDV, 48, 1, vad_w(0), [&](int col) { return (int)gv.bias[col]; });
+  add_mma_job(out, kJVadC, kDVR, 24, gv.activation, vad_w(48), [&](int col) { return (int)gv.bias[48 + col]; });
+  // noise_gru: input [dense 24 | vad state 24 | features 42], state 48
+  auto noise_w = [&](int col0) {
+    return [&, col0](SrcIdx s, int col) {
+      if (s.src == kSrcDense) return gin(gn, s.idx, col0 + col);
+      if (s.src == kSrcVadH) return gin(gn, 24 + s.idx, col0 + col);
+      if (s.src == kSrcFeat) return gin(gn, 48 + s.idx, col0 + col);
+      if (s.src == kSrcNoiseH) return grec(gn, s.idx, col0 + col);
+      return 0;
+    };
   };
-  den_rows(0);
-  add_job(out, 5, kJobZR, 192, 1, kActHVad, 210, 0, 0, kActHDen, kRhDen, rows, gb(gd, 0));
-  den_rows(192);
-  add_job(out, 6, kJobC, 96, gd.activation, kActHVad, 114, kRhDen, 96, kActHDen, 0, rows, gb(gd, 192));
-  // denoise_output reads the denoise state A[138:234)
-  rows.clear();
-  for (int k = 0; k < 96; k++) rows.push_back(dw(dg, k));
-  add_job(out, 7, kJobDense, 22, dg.activation, kActHDen, 96, 0, 0, -1, 0, rows, db(dg));
-  // vad_output: 24 weights + bias as f32 (one lane per stream works it)
-  out.hdr.vad_w_off = (int32_t)out.bias.size();
-  out.hdr.vad_activation = dv.activation;
-  for (int k = 0; k < 24; k++) out.bias.push_back((float)dv.weights[k]);
-  out.bias.push_back((float)dv.bias[0]);
+  add_mma_job(out, kJNoiseZR, cat({kDV, kF, range(kKtNH, 3)}), 96, 1, noise_w(0), [&](int col) { return (int)gn.bias[col]; });
+  add_mma_job(out, kJNoiseC, cat({kDV, kF, range(kKtNR, 3)}), 48, gn.activation, noise_w(96),
+              [&](int col) { return (int)gn.bias[96 + col]; });
+  // denoise_gru: input [vad state 24 | noise state 48 | features 42], state 96.  DV k-tile 1 also
+  // holds dense[16..24): zero weights.
+  auto den_w = [&](int col0) {
+    return [&, col0](SrcIdx s, int col) {
+      if (s.src == kSrcVadH) return gin(gd, s.idx, col0 + col);
+      if (s.src == kSrcNoiseH) return gin(gd, 24 + s.idx, col0 + col);
+      if (s.src == kSrcFeat) return gin(gd, 72 + s.idx, col0 + col);
+      if (s.src == kSrcDenH) return grec(gd, s.idx, col0 + col);
+      return 0;
+    };
+  };
+  const std::vector<int> kDV12 = {kKtDV + 1, kKtDV + 2};
+  add_mma_job(out, kJDenZR, cat({kDV12, range(kKtNH, 3), kF, range(kKtDH, 6)}), 192, 1, den_w(0),
+              [&](int col) { return (int)gd.bias[col]; });
+  add_mma_job(out, kJDenC, cat({kDV12, range(kKtNH, 3), kF, range(kKtDR, 6)}), 96, gd.activation, den_w(192),
+              [&](int col) { return (int)gd.bias[192 + col]; });
+  // denoise_output: denoise state -> 22 band gains
+  add_mma_job(out, kJOut, range(kKtDH, 6), 22, dg.activation,
+              [&](SrcIdx s, int col) { return s.src == kSrcDenH ? (int)dg.weights[(size_t)s.idx * 22 + col] : 0; },
+              [&](int col) { return (int)dg.bias[col]; });
+  // vad_output: vad state -> 1 (column 0 of one n-tile)
+  add_mma_job(out, kJVadOut, kDV, 1, dv.activation,
+              [&](SrcIdx s, int col) { return (s.src == kSrcVadH && col == 0) ? (int)dv.weights[s.idx] : 0; },
+              [&](int col) { return (int)dv.bias[col]; });
   out.hdr.n_words = (int32_t)out.words.size();
   out.hdr.n_bias = (int32_t)out.bias.size();
 }

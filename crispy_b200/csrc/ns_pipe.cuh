@@ -919,36 +919,8 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
 }
 
 // =================================================================================================
-// K4: the recurrent core, 8 streams per CTA, serial over the chunk's frames.  All weights stay in
-// shared memory as packed bf16 pairs for the whole launch; activations and GRU states of the 8
-// streams are f32 rows [k][8] (layout in ns_common.h).  Each matrix-vector job is split over
-// column pairs x K slices so that all 256 threads carry 2 x 8 FP32 FMA accumulators; partial sums
-// meet in shared memory, where bias, activation and the GRU algebra are applied.
+// activations (rnn.c tansig_approx / sigmoid_approx / relu)
 // =================================================================================================
-constexpr int kRnnStreams = 8;
-constexpr int kRnnWordsMax = 44544;  // packed weight words (pack_rnn emits 44,093 for the RNNoise topology)
-constexpr int kRnnBiasMax = 608;
-struct RnnSmem {
-  uint32_t w[kRnnWordsMax];
-  float bias[kRnnBiasMax];
-  float A[kActRows * 8];
-  float R[kRhRows * 8];
-  float z[96 * 8];
-  float psum[4096];  // [ks][half][col][4]
-  float gains[24 * 8];
-  float tansig[204];
-  float vad[8];
-  int silent[8];
-  int memid[8];
-  int any_active;
-  float ring[8][kCepsMem][kBands];
-  float lastg[8][kBands];
-  float cin[8][32];  // ceps[22] | tail[7] | silence flag of the current frame
-  float dist[8][64];
-  JobDesc jobs[kNumJobs];
-};
-static_assert(sizeof(RnnSmem) <= 232448, "recurrent-core shared memory exceeds the 227 KB a CTA may use");
-
 NS_DEV float tansig_approx(const float *tab, float x) {
   if (!(x < 8.f)) return 1.f;
   if (!(x > -8.f)) return -1.f;
@@ -971,296 +943,452 @@ NS_DEV float activate(const float *tab, int act, float x) {
   return x < 0.f ? 0.f : x;
 }
 
-#define NS_RNN_FMA16(w0, w1, lo, hi)                                  \
-  acc0[0] = fmaf(w0, lo.x, acc0[0]); acc0[1] = fmaf(w0, lo.y, acc0[1]); \
-  acc0[2] = fmaf(w0, lo.z, acc0[2]); acc0[3] = fmaf(w0, lo.w, acc0[3]); \
-  acc0[4] = fmaf(w0, hi.x, acc0[4]); acc0[5] = fmaf(w0, hi.y, acc0[5]); \
-  acc0[6] = fmaf(w0, hi.z, acc0[6]); acc0[7] = fmaf(w0, hi.w, acc0[7]); \
-  acc1[0] = fmaf(w1, lo.x, acc1[0]); acc1[1] = fmaf(w1, lo.y, acc1[1]); \
-  acc1[2] = fmaf(w1, lo.z, acc1[2]); acc1[3] = fmaf(w1, lo.w, acc1[3]); \
-  acc1[4] = fmaf(w1, hi.x, acc1[4]); acc1[5] = fmaf(w1, hi.y, acc1[5]); \
-  acc1[6] = fmaf(w1, hi.z, acc1[6]); acc1[7] = fmaf(w1, hi.w, acc1[7]);
+// bf16 (round to nearest even) bit pattern of a finite float, and the hi + lo split of an activation
+NS_DEV uint32_t bf16_rn_bits(float x) {
+  const uint32_t u = f2u(x);
+  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+}
+NS_DEV void bf16_split(float x, uint32_t &hi, uint32_t &lo) {
+  hi = bf16_rn_bits(x);
+  lo = bf16_rn_bits(x - u2f(hi << 16));
+}
+struct alignas(16) u4 {
+  uint32_t x, y, z, w;
+};
+struct alignas(8) u2 {
+  uint32_t x, y;
+};
 
-// partial sums of one job: thread tj = ks*cp + pair covers columns 2*pair, 2*pair+1 over K slice ks
-NS_DEV void rnn_job_partial(const JobDesc &jd, RnnSmem &r, int tid) {
-  const int stride = jd.cp * jd.ksplit;
-  if (tid >= stride) return;
-  const int ks = tid / jd.cp, pair = tid - ks * jd.cp;
-  float acc0[8], acc1[8];
-#pragma unroll
-  for (int s = 0; s < 8; s++) acc0[s] = acc1[s] = 0.f;
-  const uint32_t *w = r.w + jd.w_off + tid;
-  int k = ks * jd.len;
-  int kend = k + jd.len;
-  if (kend > jd.k_total) kend = jd.k_total;
-  const int k1 = kend < jd.len1 ? kend : jd.len1;
-  {
-    const float *a = r.A + (jd.off1 + k) * 8;
-#pragma unroll 2
-    for (; k < k1; k++, w += stride, a += 8) {
-      const uint32_t wv = *w;
-      const float w0 = u2f(wv << 16), w1 = u2f(wv & 0xFFFF0000u);
-      const f4 lo = ld4(a), hi = ld4(a + 4);
-      NS_RNN_FMA16(w0, w1, lo, hi)
+// =================================================================================================
+// K3b: a13 cepstral ring, delta features, spectral variability.  One warp per stream walks the
+// chunk's frames (the ring only advances on non-silent frames) and emits the 42 features already
+// split into bf16 hi + lo and laid out as the recurrent core's A fragments (ns_common.h).
+// =================================================================================================
+constexpr int kFeatWarps = 4;
+struct FeatSmem {
+  float ring[kFeatWarps][kCepsMem][24];
+  float dist[kFeatWarps][64];
+  float cin[kFeatWarps][32];
+  float feat[kFeatWarps][48];
+};
+
+NS_DEV void features_body(const Params &p, FeatSmem &sm) {
+  const int lane = Simt::tid() & 31, warp = Simt::tid() >> 5;
+  const int stream = Simt::cta() * kFeatWarps + warp;
+  const int n_pad = (p.n_streams + kMmaStreams - 1) / kMmaStreams * kMmaStreams;
+  if (stream >= n_pad) return;
+  const int group = stream / kMmaStreams, row = stream % kMmaStreams;
+  uint32_t *blk = p.featq + (long long)group * p.chunk_cap * kFeatBlockWords;
+  // feature pair q = lane (features 2q, 2q+1) of this stream's row lands in this word of a plane
+  const int q = lane;
+  const int widx = ((q >> 3) * 32 + (row & 7) * 4 + (q & 3)) * 4 + (row >> 3) + 2 * ((q & 7) >> 2);
+  if (stream >= p.n_streams) {  // padding rows of the last group: zero features, flagged silent
+    for (int t = 0; t < p.n_frames; t++) {
+      uint32_t *b = blk + (long long)t * kFeatBlockWords;
+      if (lane < 24) {
+        b[widx] = 0u;
+        b[kFeatKt * kKtWords + widx] = 0u;
+      }
+      if (lane == 24) b[2 * kFeatKt * kKtWords + row] = 1u;
     }
+    return;
   }
-  if (k < kend) {
-    const float *a = r.R + (jd.off2 + k - jd.len1) * 8;
-#pragma unroll 2
-    for (; k < kend; k++, w += stride, a += 8) {
-      const uint32_t wv = *w;
-      const float w0 = u2f(wv << 16), w1 = u2f(wv & 0xFFFF0000u);
-      const f4 lo = ld4(a), hi = ld4(a + 4);
-      NS_RNN_FMA16(w0, w1, lo, hi)
+  float(*ring)[24] = sm.ring[warp];
+  float *dist = sm.dist[warp], *cin = sm.cin[warp], *feat = sm.feat[warp];
+  float *st = p.state + (long long)stream * kStateFloats;
+  for (int i = lane; i < kCepsMem * kBands; i += 32) ring[i / kBands][i % kBands] = st[kStCeps + i];
+  int memid = reinterpret_cast<const int *>(st)[kStMemId];
+  for (int i = lane; i < 48; i += 32) feat[i] = 0.f;
+  Simt::warp_sync();
+  for (int it = lane; it < 64; it += 32) {  // pairwise cepstral distances of the ring
+    const int a = it >> 3, b = it & 7;
+    float d = 0.f;
+    for (int k = 0; k < kBands; k++) {
+      const float tt = ring[a][k] - ring[b][k];
+      d += tt * tt;
     }
+    dist[it] = d;
   }
-  const int N = jd.n_out, c0 = 2 * pair;
-  f4 *p0 = reinterpret_cast<f4 *>(r.psum + ((ks * 2 + 0) * N + c0) * 4);
-  f4 *p1 = reinterpret_cast<f4 *>(r.psum + ((ks * 2 + 1) * N + c0) * 4);
-  p0[0] = f4{acc0[0], acc0[1], acc0[2], acc0[3]};
-  p1[0] = f4{acc0[4], acc0[5], acc0[6], acc0[7]};
-  if (c0 + 1 < N) {
-    p0[1] = f4{acc1[0], acc1[1], acc1[2], acc1[3]};
-    p1[1] = f4{acc1[4], acc1[5], acc1[6], acc1[7]};
+  Simt::warp_sync();
+  for (int t = 0; t < p.n_frames; t++) {
+    const float *rec = p.rec + ((long long)stream * p.chunk_cap + t) * kRecFloats;
+    const bool silent = reinterpret_cast<const int *>(rec)[kRecSilence] != 0;
+    uint32_t *b = blk + (long long)t * kFeatBlockWords;
+    if (!silent) {
+      if (lane < kBands) {
+        const float c = rec[kRecCeps + lane];
+        ring[memid][lane] = c;
+        cin[lane] = c;
+      } else if (lane < 29) {
+        cin[lane] = rec[kRecTail + lane - kBands];
+      }
+      Simt::warp_sync();
+      if (lane < kCepsMem) {  // distances to the new ring row
+        const int a = memid, bb = lane;
+        float d = 0.f;
+        for (int k = 0; k < kBands; k++) {
+          const float tt = ring[a][k] - ring[bb][k];
+          d += tt * tt;
+        }
+        dist[(a << 3) + bb] = d;
+        dist[(bb << 3) + a] = d;
+      }
+      const int m0 = memid, m1 = (m0 + 7) & 7, m2 = (m0 + 6) & 7;
+      for (int i = lane; i < 41; i += 32) {  // features[0..40]
+        float v;
+        if (i < kDeltaCeps) {
+          v = ring[m0][i] + ring[m1][i] + ring[m2][i];
+        } else if (i < kBands) {
+          v = cin[i];
+        } else if (i < kBands + kDeltaCeps) {
+          const int j = i - kBands;
+          v = ring[m0][j] - ring[m2][j];
+        } else if (i < kBands + 2 * kDeltaCeps) {
+          const int j = i - kBands - kDeltaCeps;
+          v = ring[m0][j] - 2.f * ring[m1][j] + ring[m2][j];
+        } else {
+          v = cin[kBands + (i - kBands - 2 * kDeltaCeps)];
+        }
+        feat[i] = v;
+      }
+      Simt::warp_sync();
+      float mind = 1e15f;  // spectral variability: sum over ring rows of the distance to the nearest other row
+      if (lane < kCepsMem)
+        for (int bb = 0; bb < kCepsMem; bb++)
+          if (bb != lane) mind = fminf(mind, dist[(lane << 3) + bb]);
+      float sv = 0.f;
+      for (int a = 0; a < kCepsMem; a++) sv += Simt::shfl(mind, a);
+      if (lane == 0) feat[41] = sv / kCepsMem - 2.1f;
+      memid = (memid + 1) & 7;
+      Simt::warp_sync();
+    }
+    if (lane < 24) {
+      uint32_t h0 = 0u, l0 = 0u, h1 = 0u, l1 = 0u;
+      if (!silent) {
+        bf16_split(feat[2 * q], h0, l0);
+        bf16_split(feat[2 * q + 1], h1, l1);
+      }
+      b[widx] = h0 | (h1 << 16);
+      b[kFeatKt * kKtWords + widx] = l0 | (l1 << 16);
+    }
+    if (lane == 24) b[2 * kFeatKt * kKtWords + row] = silent ? 1u : 0u;
+    if (p.dbg) {
+      float *d = p.dbg + ((long long)stream * p.n_frames_call + p.frame0 + t) * kDbgFloats + kDbgFeatures;
+      for (int i = lane; i < kFeatures; i += 32) d[i] = silent ? 0.f : feat[i];
+    }
+    Simt::warp_sync();
   }
+  for (int i = lane; i < kCepsMem * kBands; i += 32) st[kStCeps + i] = ring[i / kBands][i % kBands];
+  if (lane == 0) reinterpret_cast<int *>(st)[kStMemId] = memid;
 }
 
-// sum the K slices, add the bias, apply the activation and the job's algebra
-template <int NT>
-NS_DEV void rnn_job_finish(const JobDesc &jd, RnnSmem &r, int tid) {
-  const int N = jd.n_out;
-  for (int it = tid; it < 2 * N; it += NT) {
-    const int half = it / N, col = it - half * N;
-    const float b = r.bias[jd.b_off + col];
-    float v[4] = {b, b, b, b};
-    for (int ks = 0; ks < jd.ksplit; ks++) {
-      const f4 q = ld4(r.psum + ((ks * 2 + half) * N + col) * 4);
-      v[0] += q.x;
-      v[1] += q.y;
-      v[2] += q.z;
-      v[3] += q.w;
-    }
+// =================================================================================================
+// K4: a14 the recurrent core on the tensor pipe, 16 streams per CTA, serial over the chunk's frames.
+// All weights stay in shared memory as bf16 B fragments for the whole launch; every activation
+// vector lives in shared memory as bf16 hi + lo A fragments; the GRU states, update gates and
+// lastg stay in the registers of the lanes whose accumulator fragments own them.  Each of the
+// eight matrix products of a frame is one pass of mma.sync.m16n8k16 over its k-tiles (twice: hi and
+// lo plane) followed by an in-register epilogue (bias, activation, GRU algebra) that writes the
+// next products' A fragments; one block barrier separates consecutive products.
+// Neuron tile j (8 neurons) of a GRU belongs to warp j % 8 in both its z|r and candidate products.
+// =================================================================================================
+struct RnnSmem {
+  uint32_t w[kMmaWordsMax];
+  uint32_t ahi[kKtResident * kKtWords];
+  uint32_t alo[kKtResident * kKtWords];
+  uint32_t fq[2][kFeatBlockWords];
+  float bias[kMmaBiasMax];
+  float tansig[204];
+  MmaJobDesc jobs[kNumMmaJobs];
+};
+static_assert(sizeof(RnnSmem) <= 232448, "recurrent-core shared memory exceeds the 227 KB a CTA may use");
+
+// one product: this warp's `nact` (<= NACC) n-tiles `tiles[]`, all k-tiles of the job; hi and lo planes
+// accumulate separately (two independent MMA chains per n-tile)
+template <int NACC>
+NS_DEV void mma_run(const RnnSmem &r, const MmaJobDesc &jd, const uint32_t *fcur, const int (&tiles)[NACC], int nact,
+                    int lane, float (&acc)[NACC][2][4]) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int s = 4 * half + j;
-      const float x = v[j] * (1.f / 256);
-      if (jd.kind == kJobDense) {
-        const float y = activate(r.tansig, jd.activation, x);
-        if (jd.out_off >= 0)
-          r.A[(jd.out_off + col) * 8 + s] = y;
-        else
-          r.gains[col * 8 + s] = y;
-      } else if (jd.kind == kJobZR) {
-        const int Ng = N >> 1;
-        const float y = sigmoid_approx(r.tansig, x);
-        if (col < Ng)
-          r.z[col * 8 + s] = y;
-        else
-          r.R[(jd.rh_off + col - Ng) * 8 + s] = r.A[(jd.out_off + col - Ng) * 8 + s] * y;
-      } else {
-        const float c = activate(r.tansig, jd.activation, x);
-        const float zz = r.z[col * 8 + s], ho = r.A[(jd.out_off + col) * 8 + s];
-        const float hn = zz * ho + (1.f - zz) * c;
-        if (!r.silent[s]) r.A[(jd.out_off + col) * 8 + s] = hn;
+  for (int n = 0; n < NACC; n++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) acc[n][0][e] = acc[n][1][e] = 0.f;
+  const uint32_t *wj = r.w + jd.w_off + lane * 2;
+  const int nkt = jd.nkt, nnt = jd.nnt;
+  for (int i = 0; i < nkt; i++) {
+    const int v = jd.kt[i];
+    const uint32_t *ph = (v < kKtResident) ? r.ahi + v * kKtWords : fcur + (v - kKtF) * kKtWords;
+    const uint32_t *pl = (v < kKtResident) ? r.alo + v * kKtWords : fcur + (kFeatKt + v - kKtF) * kKtWords;
+    const u4 ah4 = *reinterpret_cast<const u4 *>(ph + lane * 4), al4 = *reinterpret_cast<const u4 *>(pl + lane * 4);
+    const uint32_t ah[4] = {ah4.x, ah4.y, ah4.z, ah4.w}, al[4] = {al4.x, al4.y, al4.z, al4.w};
+#pragma unroll
+    for (int n = 0; n < NACC; n++) {
+      if (n < nact) {
+        const u2 b2 = *reinterpret_cast<const u2 *>(wj + (i * nnt + tiles[n]) * 64);
+        const uint32_t b[2] = {b2.x, b2.y};
+        Simt::mma_bf16_16816(acc[n][0], ah, b);
+        Simt::mma_bf16_16816(acc[n][1], al, b);
       }
     }
   }
 }
 
-template <int NT>
+// S * (bias + sum) of accumulator element e of n-tile `tile`: rows lane/4 (e < 2) and lane/4 + 8,
+// output column tile*8 + 2*(lane%4) + (e & 1)
+NS_DEV float mma_pre(const RnnSmem &r, const MmaJobDesc &jd, const float (&acc)[2][4], int tile, int lane, int e) {
+  const float b = r.bias[jd.b_off + tile * 8 + 2 * (lane & 3) + (e & 1)];
+  return ((acc[0][e] + acc[1][e]) + b) * (1.f / 256);
+}
+
+// write this lane's four values (rows lane/4 and lane/4+8, inputs k0 + 2*(lane%4) + {0,1}) of the
+// 8 inputs starting at resident position k0 (a multiple of 8) as hi/lo A fragments
+NS_DEV void store_frag(RnnSmem &r, int k0, int lane, const float (&v)[4]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) bf16_split(v[e], h[e], l[e]);
+  const int off = ((k0 >> 4) * 32 + lane) * 4 + ((k0 >> 3) & 1) * 2;
+  *reinterpret_cast<u2 *>(r.ahi + off) = u2{h[0] | (h[1] << 16), h[2] | (h[3] << 16)};
+  *reinterpret_cast<u2 *>(r.alo + off) = u2{l[0] | (l[1] << 16), l[2] | (l[3] << 16)};
+}
+
+// resident positions (k index = k-tile * 16 + kk) of the activation vectors
+constexpr int kPosDense = kKtDV * 16, kPosVadH = kKtDV * 16 + 24, kPosDense2 = kKtDVR * 16,
+              kPosVadR = kKtDVR * 16 + 24, kPosNoiseH = kKtNH * 16, kPosNoiseR = kKtNR * 16,
+              kPosDenH = kKtDH * 16, kPosDenR = kKtDR * 16;
+
 NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
-  const int tid = Simt::tid();
-  const int s0 = Simt::cta() * kRnnStreams;
+  const int tid = Simt::tid(), lane = tid & 31, warp = tid >> 5;
+  const int NT = kMmaThreads;
+  const int g = lane >> 2, c2 = 2 * (lane & 3);
+  const int s0 = Simt::cta() * kMmaStreams;
+  const int srow[2] = {s0 + g, s0 + g + 8};
+  const bool live[2] = {srow[0] < p.n_streams, srow[1] < p.n_streams};
   {  // weights, biases, tables, job descriptors -> shared memory; activations cleared
     const RnnHeader &H = *p.rnn_hdr;
-    for (int i = tid; i < H.n_words; i += NT) r.w[i] = p.rnn_words[i];
+    const u4 *src = reinterpret_cast<const u4 *>(p.rnn_words);
+    u4 *dst = reinterpret_cast<u4 *>(r.w);
+    for (int i = tid; i < H.n_words / 4; i += NT) dst[i] = src[i];
     for (int i = tid; i < H.n_bias; i += NT) r.bias[i] = p.rnn_bias[i];
     for (int i = tid; i < 204; i += NT) r.tansig[i] = p.tables->tansig[i];
     const int32_t *js = reinterpret_cast<const int32_t *>(H.jobs);
     int32_t *jd = reinterpret_cast<int32_t *>(r.jobs);
-    for (int i = tid; i < (int)(sizeof(JobDesc) * kNumJobs / 4); i += NT) jd[i] = js[i];
-    for (int i = tid; i < kActRows * 8; i += NT) r.A[i] = 0.f;
-    for (int i = tid; i < kRhRows * 8; i += NT) r.R[i] = 0.f;
-    for (int i = tid; i < 96 * 8; i += NT) r.z[i] = 0.f;
-    for (int i = tid; i < 8 * kCepsMem * kBands; i += NT) (&r.ring[0][0][0])[i] = 0.f;
-    for (int i = tid; i < 8 * kBands; i += NT) (&r.lastg[0][0])[i] = 0.f;
-    if (tid < 8) r.memid[tid] = 0;
+    for (int i = tid; i < (int)(sizeof(MmaJobDesc) * kNumMmaJobs / 4); i += NT) jd[i] = js[i];
+    for (int i = tid; i < kKtResident * kKtWords; i += NT) r.ahi[i] = r.alo[i] = 0u;
   }
-  const int vad_w_off = p.rnn_hdr->vad_w_off, vad_act = p.rnn_hdr->vad_activation;
-  Simt::cta_sync();
-  for (int it = tid; it < kRnnStreams * 384; it += NT) {  // recurrent state -> shared memory
-    const int s = it / 384, j = it - s * 384;
-    if (s0 + s >= p.n_streams) continue;
-    const float *st = p.state + (long long)(s0 + s) * kStateFloats;
-    if (j < 176)
-      r.ring[s][j / kBands][j % kBands] = st[kStCeps + j];
-    else if (j < 198)
-      r.lastg[s][j - 176] = st[kStLastG + j - 176];
-    else if (j < 222)
-      r.A[(kActHVad + j - 198) * 8 + s] = st[kStHVad + j - 198];
-    else if (j < 270)
-      r.A[(kActHNoise + j - 222) * 8 + s] = st[kStHNoise + j - 222];
-    else if (j < 366)
-      r.A[(kActHDen + j - 270) * 8 + s] = st[kStHDen + j - 270];
-    else if (j == 366)
-      r.memid[s] = reinterpret_cast<const int *>(st)[kStMemId];
-  }
-  Simt::cta_sync();
-  for (int it = tid; it < kRnnStreams * 64; it += NT) {  // pairwise cepstral distances of the ring
-    const int s = it >> 6, a = (it >> 3) & 7, b = it & 7;
-    float dist = 0.f;
-    for (int k = 0; k < kBands; k++) {
-      const float tt = r.ring[s][a][k] - r.ring[s][b][k];
-      dist += tt * tt;
-    }
-    r.dist[s][(a << 3) + b] = dist;
-  }
-  // per-thread slice of the next frame's record (ceps | tail | silence), fetched one frame ahead
-  const int ps = tid / 30, pj = tid - ps * 30;
-  const bool pact = tid < kRnnStreams * 30 && s0 + ps < p.n_streams;
-  auto fetch = [&](int t) -> float {
-    if (!pact) return (pj == 29) ? 1.f : 0.f;
-    const float *rec = p.rec + ((long long)(s0 + ps) * p.chunk_cap + t) * kRecFloats;
-    if (pj < kBands) return rec[kRecCeps + pj];
-    if (pj < 29) return rec[kRecTail + pj - kBands];
-    return reinterpret_cast<const int *>(rec)[kRecSilence] ? 1.f : 0.f;
+  const uint32_t *fq_src = p.featq + (long long)Simt::cta() * p.chunk_cap * kFeatBlockWords;
+  auto fetch = [&](int t) {  // feature block of frame t -> fq[t & 1]
+    if (tid < kFeatBlockWords / 4) Simt::cp_async16(&r.fq[t & 1][tid * 4], fq_src + (long long)t * kFeatBlockWords + tid * 4);
+    Simt::cp_async_commit();
   };
-  float nxt = (p.n_frames > 0) ? fetch(0) : 0.f;
+  if (p.n_frames > 0) fetch(0);
+  // recurrent state -> registers of the owning lanes.  hv: vad (warps 0-2), hn: noise (warps 0-5),
+  // hd[0]: denoise tile `warp`, hd[1]: denoise tile warp + 8 (warps 0-3); lastg: warps 0-2
+  float hv[4], hn[4], hd[2][4], lastg[4];
+  auto load4 = [&](float (&h)[4], int st_off, int n0, int n_max) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int n = n0 + (e & 1);
+      h[e] = (live[e >> 1] && n < n_max) ? p.state[(long long)srow[e >> 1] * kStateFloats + st_off + n] : 0.f;
+    }
+  };
+  auto save4 = [&](const float (&h)[4], int st_off, int n0, int n_max) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int n = n0 + (e & 1);
+      if (live[e >> 1] && n < n_max) p.state[(long long)srow[e >> 1] * kStateFloats + st_off + n] = h[e];
+    }
+  };
+  load4(hv, kStHVad, warp * 8 + c2, warp < 3 ? 24 : 0);
+  load4(hn, kStHNoise, warp * 8 + c2, warp < 6 ? 48 : 0);
+  load4(hd[0], kStHDen, warp * 8 + c2, 96);
+  load4(hd[1], kStHDen, (warp + 8) * 8 + c2, warp < 4 ? 96 : 0);
+  load4(lastg, kStLastG, warp * 8 + c2, warp < 3 ? kBands : 0);
+  Simt::cta_sync();  // the fragments were cleared
+  if (warp < 3) store_frag(r, kPosVadH + warp * 8, lane, hv);
+  if (warp < 6) store_frag(r, kPosNoiseH + warp * 8, lane, hn);
+  store_frag(r, kPosDenH + warp * 8, lane, hd[0]);
+  if (warp < 4) store_frag(r, kPosDenH + (warp + 8) * 8, lane, hd[1]);
+  Simt::cp_async_wait<0>();
   Simt::cta_sync();
+  const float *tab = r.tansig;
   for (int t = 0; t < p.n_frames; t++) {
-    if (tid < kRnnStreams * 30) {
-      r.cin[ps][pj] = nxt;
-      if (pj == 29) r.silent[ps] = nxt != 0.f;
-    }
-    if (t + 1 < p.n_frames) nxt = fetch(t + 1);
-    if (tid == 0) r.any_active = 0;
-    Simt::cta_sync();
-    for (int it = tid; it < kRnnStreams * kBands; it += NT) {  // a13: cepstral ring update
-      const int s = it / kBands, i = it - s * kBands;
-      if (!r.silent[s]) {
-        r.ring[s][r.memid[s]][i] = r.cin[s][i];
-        if (i == 0) r.any_active = 1;
-      }
-    }
-    Simt::cta_sync();
-    if (r.any_active) {
-      for (int it = tid; it < kRnnStreams * 8; it += NT) {  // a13: distances to the new ring row
-        const int s = it >> 3, b = it & 7;
-        if (r.silent[s]) continue;
-        const int a = r.memid[s];
-        float dist = 0.f;
-        for (int k = 0; k < kBands; k++) {
-          const float tt = r.ring[s][a][k] - r.ring[s][b][k];
-          dist += tt * tt;
-        }
-        r.dist[s][(a << 3) + b] = dist;
-        r.dist[s][(b << 3) + a] = dist;
-      }
-      for (int it = tid; it < kRnnStreams * 41; it += NT) {  // a13: features[0..40] -> A[feat]
-        const int s = it / 41, i = it - s * 41;
-        float v = 0.f;
-        if (!r.silent[s]) {
-          const int m0 = r.memid[s], m1 = (m0 + 7) & 7, m2 = (m0 + 6) & 7;
-          if (i < kDeltaCeps) {
-            v = r.ring[s][m0][i] + r.ring[s][m1][i] + r.ring[s][m2][i];
-          } else if (i < kBands) {
-            v = r.cin[s][i];
-          } else if (i < kBands + kDeltaCeps) {
-            const int j = i - kBands;
-            v = r.ring[s][m0][j] - r.ring[s][m2][j];
-          } else if (i < kBands + 2 * kDeltaCeps) {
-            const int j = i - kBands - kDeltaCeps;
-            v = r.ring[s][m0][j] - 2.f * r.ring[s][m1][j] + r.ring[s][m2][j];
-          } else {
-            v = r.cin[s][kBands + (i - kBands - 2 * kDeltaCeps)];
-          }
-        }
-        r.A[(kActFeat + i) * 8 + s] = v;
-      }
-      Simt::cta_sync();
-      if (tid < kRnnStreams) {  // a13: spectral variability, ring index
-        const int s = tid;
-        float v = 0.f;
-        if (!r.silent[s]) {
-          float sv = 0.f;
-          for (int a = 0; a < kCepsMem; a++) {
-            float mind = 1e15f;
-            for (int b = 0; b < kCepsMem; b++)
-              if (b != a) mind = fminf(mind, r.dist[s][(a << 3) + b]);
-            sv += mind;
-          }
-          v = sv / kCepsMem - 2.1f;
-          r.memid[s] = (r.memid[s] + 1) & 7;
-        }
-        r.A[(kActFeat + 41) * 8 + s] = v;
-      }
-      Simt::cta_sync();
-      if (p.dbg) {
-        for (int it = tid; it < kRnnStreams * kFeatures; it += NT) {
-          const int s = it / kFeatures, i = it - s * kFeatures;
-          if (s0 + s >= p.n_streams) continue;
-          p.dbg[((long long)(s0 + s) * p.n_frames_call + p.frame0 + t) * kDbgFloats + kDbgFeatures + i] =
-              r.A[(kActFeat + i) * 8 + s];
-        }
-      }
-      for (int j = 0; j < kNumJobs; j++) {
-        rnn_job_partial(r.jobs[j], r, tid);
-        if (j == 3 && tid >= NT - 8) {  // vad_output on the settled vad state (threads idle in this job)
-          const int s = tid - (NT - 8);
-          float sum = r.bias[vad_w_off + 24];
-          for (int k = 0; k < 24; k++) sum = fmaf(r.bias[vad_w_off + k], r.A[(kActHVad + k) * 8 + s], sum);
-          r.vad[s] = activate(r.tansig, vad_act, sum * (1.f / 256));
+    const uint32_t *fcur = r.fq[t & 1];
+    if (t + 1 < p.n_frames) fetch(t + 1);
+    const uint32_t *flags = fcur + 2 * kFeatKt * kKtWords;
+    bool any_active = false;
+#pragma unroll
+    for (int i = 0; i < kMmaStreams; i++) any_active = any_active || (flags[i] == 0u);
+    const bool sil[2] = {flags[g] != 0u, flags[g + 8] != 0u};
+    float vad[2] = {0.f, 0.f};
+    float gout[4] = {0.f, 0.f, 0.f, 0.f}, graw[4] = {0.f, 0.f, 0.f, 0.f};
+    if (any_active) {
+      {  // input_dense: features -> dense (both copies)
+        if (warp < 3) {
+          const MmaJobDesc &jd = r.jobs[kJDense];
+          float acc[1][2][4];
+          const int tiles[1] = {warp};
+          mma_run<1>(r, jd, fcur, tiles, 1, lane, acc);
+          float y[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) y[e] = activate(tab, jd.activation, mma_pre(r, jd, acc[0], warp, lane, e));
+          store_frag(r, kPosDense + warp * 8, lane, y);
+          store_frag(r, kPosDense2 + warp * 8, lane, y);
         }
         Simt::cta_sync();
-        rnn_job_finish<NT>(r.jobs[j], r, tid);
+      }
+      float z[2][4];
+      {  // vad_gru
+        if (warp < 3) {
+          const MmaJobDesc &jd = r.jobs[kJVadZR];
+          float acc[2][2][4];
+          const int tiles[2] = {warp, 3 + warp};
+          mma_run<2>(r, jd, fcur, tiles, 2, lane, acc);
+          float rh[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            z[0][e] = sigmoid_approx(tab, mma_pre(r, jd, acc[0], tiles[0], lane, e));
+            rh[e] = hv[e] * sigmoid_approx(tab, mma_pre(r, jd, acc[1], tiles[1], lane, e));
+          }
+          store_frag(r, kPosVadR + warp * 8, lane, rh);
+        }
+        Simt::cta_sync();
+        if (warp < 3) {
+          const MmaJobDesc &jd = r.jobs[kJVadC];
+          float acc[1][2][4];
+          const int tiles[1] = {warp};
+          mma_run<1>(r, jd, fcur, tiles, 1, lane, acc);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float cnd = activate(tab, jd.activation, mma_pre(r, jd, acc[0], warp, lane, e));
+            const float hnew = z[0][e] * hv[e] + (1.f - z[0][e]) * cnd;
+            if (!sil[e >> 1]) hv[e] = hnew;
+          }
+          store_frag(r, kPosVadH + warp * 8, lane, hv);
+        }
         Simt::cta_sync();
       }
-    } else if (p.dbg) {
-      for (int it = tid; it < kRnnStreams * kFeatures; it += NT) {
-        const int s = it / kFeatures, i = it - s * kFeatures;
-        if (s0 + s >= p.n_streams) continue;
-        p.dbg[((long long)(s0 + s) * p.n_frames_call + p.frame0 + t) * kDbgFloats + kDbgFeatures + i] = 0.f;
-      }
-    }
-    for (int it = tid; it < kRnnStreams * 32; it += NT) {
-      const int s = it >> 5, i = it & 31;
-      if (s0 + s >= p.n_streams) continue;
-      const bool silent = r.silent[s] != 0;
-      float *rec = p.rec + ((long long)(s0 + s) * p.chunk_cap + t) * kRecFloats;
-      if (i < kBands) {
-        float gi = 0.f, graw = 0.f;
-        if (!silent) {
-          graw = r.gains[i * 8 + s];
-          gi = fmaxf(graw, .6f * r.lastg[s][i]);
-          r.lastg[s][i] = gi;
+      {  // noise_gru (warps 0-5); vad_output on the settled vad state (warp 7)
+        if (warp < 6) {
+          const MmaJobDesc &jd = r.jobs[kJNoiseZR];
+          float acc[2][2][4];
+          const int tiles[2] = {warp, 6 + warp};
+          mma_run<2>(r, jd, fcur, tiles, 2, lane, acc);
+          float rh[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            z[0][e] = sigmoid_approx(tab, mma_pre(r, jd, acc[0], tiles[0], lane, e));
+            rh[e] = hn[e] * sigmoid_approx(tab, mma_pre(r, jd, acc[1], tiles[1], lane, e));
+          }
+          store_frag(r, kPosNoiseR + warp * 8, lane, rh);
+        } else if (warp == 7) {
+          const MmaJobDesc &jd = r.jobs[kJVadOut];
+          float acc[1][2][4];
+          const int tiles[1] = {0};
+          mma_run<1>(r, jd, fcur, tiles, 1, lane, acc);
+          vad[0] = activate(tab, jd.activation, mma_pre(r, jd, acc[0], 0, lane, 0));  // column 0 lives in lanes with lane%4 == 0
+          vad[1] = activate(tab, jd.activation, mma_pre(r, jd, acc[0], 0, lane, 2));
         }
-        rec[kRecGRaw + i] = graw;
-        rec[kRecG + i] = gi;
-      } else if (i == 22) {
-        const float v = silent ? 0.f : r.vad[s];
-        rec[kRecVad] = v;
-        if (p.vad) p.vad[(long long)(s0 + s) * p.vad_stride + p.frame0 + t] = v;
+        Simt::cta_sync();
+        if (warp < 6) {
+          const MmaJobDesc &jd = r.jobs[kJNoiseC];
+          float acc[1][2][4];
+          const int tiles[1] = {warp};
+          mma_run<1>(r, jd, fcur, tiles, 1, lane, acc);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float cnd = activate(tab, jd.activation, mma_pre(r, jd, acc[0], warp, lane, e));
+            const float hnew = z[0][e] * hn[e] + (1.f - z[0][e]) * cnd;
+            if (!sil[e >> 1]) hn[e] = hnew;
+          }
+          store_frag(r, kPosNoiseH + warp * 8, lane, hn);
+        }
+        Simt::cta_sync();
+      }
+      {  // denoise_gru: warp w owns neuron tiles w and (w < 4) w + 8
+        const int nown = warp < 4 ? 2 : 1;
+        {
+          const MmaJobDesc &jd = r.jobs[kJDenZR];
+          float acc[4][2][4];
+          const int tiles[4] = {warp, 12 + warp, warp + 8, 12 + warp + 8};
+          mma_run<4>(r, jd, fcur, tiles, 2 * nown, lane, acc);
+#pragma unroll
+          for (int o = 0; o < 2; o++) {
+            if (o < nown) {
+              float rh[4];
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                z[o][e] = sigmoid_approx(tab, mma_pre(r, jd, acc[2 * o], tiles[2 * o], lane, e));
+                rh[e] = hd[o][e] * sigmoid_approx(tab, mma_pre(r, jd, acc[2 * o + 1], tiles[2 * o + 1], lane, e));
+              }
+              store_frag(r, kPosDenR + tiles[2 * o] * 8, lane, rh);
+            }
+          }
+        }
+        Simt::cta_sync();
+        {
+          const MmaJobDesc &jd = r.jobs[kJDenC];
+          float acc[2][2][4];
+          const int tiles[2] = {warp, warp + 8};
+          mma_run<2>(r, jd, fcur, tiles, nown, lane, acc);
+#pragma unroll
+          for (int o = 0; o < 2; o++) {
+            if (o < nown) {
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const float cnd = activate(tab, jd.activation, mma_pre(r, jd, acc[o], tiles[o], lane, e));
+                const float hnew = z[o][e] * hd[o][e] + (1.f - z[o][e]) * cnd;
+                if (!sil[e >> 1]) hd[o][e] = hnew;
+              }
+              store_frag(r, kPosDenH + tiles[o] * 8, lane, hd[o]);
+            }
+          }
+        }
+        Simt::cta_sync();
+      }
+      if (warp < 3) {  // denoise_output -> band gains; g = max(g, 0.6 lastg)
+        const MmaJobDesc &jd = r.jobs[kJOut];
+        float acc[1][2][4];
+        const int tiles[1] = {warp};
+        mma_run<1>(r, jd, fcur, tiles, 1, lane, acc);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          if (!sil[e >> 1]) {
+            graw[e] = activate(tab, jd.activation, mma_pre(r, jd, acc[0], warp, lane, e));
+            gout[e] = fmaxf(graw[e], .6f * lastg[e]);
+            lastg[e] = gout[e];
+          }
+        }
       }
     }
+    if (warp < 3) {  // band gains of this frame -> record (zeros on silent frames)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int band = warp * 8 + c2;
+        if (live[h] && band < kBands) {
+          float *rec = p.rec + ((long long)srow[h] * p.chunk_cap + t) * kRecFloats;
+          rec[kRecGRaw + band] = graw[2 * h];
+          rec[kRecGRaw + band + 1] = graw[2 * h + 1];
+          rec[kRecG + band] = gout[2 * h];
+          rec[kRecG + band + 1] = gout[2 * h + 1];
+        }
+      }
+    } else if (warp == 7 && (lane & 3) == 0) {
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        if (live[h]) {
+          const float v = sil[h] ? 0.f : vad[h];
+          p.rec[((long long)srow[h] * p.chunk_cap + t) * kRecFloats + kRecVad] = v;
+          if (p.vad) p.vad[(long long)srow[h] * p.vad_stride + p.frame0 + t] = v;
+        }
+      }
+    }
+    Simt::cp_async_wait<0>();
     Simt::cta_sync();
   }
-  for (int it = tid; it < kRnnStreams * 384; it += NT) {  // recurrent state -> HBM
-    const int s = it / 384, j = it - s * 384;
-    if (s0 + s >= p.n_streams) continue;
-    float *st = p.state + (long long)(s0 + s) * kStateFloats;
-    if (j < 176)
-      st[kStCeps + j] = r.ring[s][j / kBands][j % kBands];
-    else if (j < 198)
-      st[kStLastG + j - 176] = r.lastg[s][j - 176];
-    else if (j < 222)
-      st[kStHVad + j - 198] = r.A[(kActHVad + j - 198) * 8 + s];
-    else if (j < 270)
-      st[kStHNoise + j - 222] = r.A[(kActHNoise + j - 222) * 8 + s];
-    else if (j < 366)
-      st[kStHDen + j - 270] = r.A[(kActHDen + j - 270) * 8 + s];
-    else if (j == 366)
-      reinterpret_cast<int *>(st)[kStMemId] = r.memid[s];
-  }
+  save4(hv, kStHVad, warp * 8 + c2, warp < 3 ? 24 : 0);
+  save4(hn, kStHNoise, warp * 8 + c2, warp < 6 ? 48 : 0);
+  save4(hd[0], kStHDen, warp * 8 + c2, 96);
+  save4(hd[1], kStHDen, (warp + 8) * 8 + c2, warp < 4 ? 96 : 0);
+  save4(lastg, kStLastG, warp * 8 + c2, warp < 3 ? kBands : 0);
 }
 
 // =================================================================================================

@@ -50,6 +50,14 @@ struct Simt {
   static NS_DEV void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
   }
+  // warp-wide tensor-pipe MMA (HMMA): D[16x8] += A[16x16] . B[16x8], bf16 inputs, f32 accumulate.
+  // Fragment layouts are the PTX m16n8k16 ones (ns_common.h restates them).
+  static NS_DEV void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
 };
 }  // namespace ns
 
@@ -77,6 +85,7 @@ namespace ns {
 struct EmuWarp {
   pthread_barrier_t bar;
   uint64_t xch[32];
+  uint32_t frag[32][6];  // mma emulation: every lane's A (4 words) and B (2 words) fragments
 };
 struct EmuCta {
   pthread_barrier_t cta_bar;
@@ -135,6 +144,28 @@ struct Simt {
   static void cp_async_commit() {}
   template <int N>
   static void cp_async_wait() {}
+  // mma.sync.m16n8k16 (bf16 x bf16 -> f32) emulated from the lanes' fragments: A element (row, k)
+  // sits in lane (row%8)*4 + (k%8)/2, word row/8 + 2*(k/8), halfword k%2; B element (k, col) in
+  // lane col*4 + (k%8)/2, word k/8, halfword k%2; this lane owns D (lane/4 [+8], 2*(lane%4) [+1]).
+  static void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    EmuWarp &w = g_emu.cta->warps[g_emu.tid >> 5];
+    const int ln = lane();
+    for (int i = 0; i < 4; i++) w.frag[ln][i] = a[i];
+    for (int i = 0; i < 2; i++) w.frag[ln][4 + i] = b[i];
+    pthread_barrier_wait(&w.bar);
+    auto bf = [](uint32_t word, int half) { return u2f(((word >> (16 * half)) & 0xFFFFu) << 16); };
+    for (int e = 0; e < 4; e++) {
+      const int row = (ln >> 2) + 8 * (e >> 1), col = 2 * (ln & 3) + (e & 1);
+      double sum = 0.0;
+      for (int k = 0; k < 16; k++) {
+        const float av = bf(w.frag[(row & 7) * 4 + ((k & 7) >> 1)][(row >> 3) + 2 * (k >> 3)], k & 1);
+        const float bv = bf(w.frag[col * 4 + ((k & 7) >> 1)][4 + (k >> 3)], k & 1);
+        sum += (double)av * (double)bv;
+      }
+      d[e] = (float)((double)d[e] + sum);
+    }
+    pthread_barrier_wait(&w.bar);
+  }
 };
 }  // namespace ns
 

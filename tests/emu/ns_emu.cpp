@@ -103,6 +103,8 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
   std::vector<uint32_t> tabw((size_t)n_streams * chunk_cap * ns::kTabWords, 0u);
   std::vector<float> rec((size_t)n_streams * chunk_cap * ns::kRecFloats, 0.f);
   std::vector<ns::cf> spec((size_t)n_streams * chunk_cap * 2 * ns::kSpecStride);
+  const int groups = (n_streams + ns::kMmaStreams - 1) / ns::kMmaStreams;
+  std::vector<uint32_t> featq((size_t)groups * chunk_cap * ns::kFeatBlockWords, 0xCDCDCDCDu);
   p.in = in;
   p.out = out;
   p.vad = vad;
@@ -113,6 +115,7 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
   p.tab = tabw.data();
   p.rec = rec.data();
   p.spec = spec.data();
+  p.featq = featq.data();
   p.tables = &tab;
   p.rnn_hdr = &pk.hdr;
   p.rnn_words = pk.words.data();
@@ -152,8 +155,10 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
     rc = launch(spec_ctas, ns::kGroupThreads, sizeof(ns::SpecSmem),
                 [&](void *sm) { ns::spectrum_body(p, *(ns::SpecSmem *)sm); });
     if (rc) return rc;
-    rc = launch((n_streams + ns::kRnnStreams - 1) / ns::kRnnStreams, ns::kRnnThreads, sizeof(ns::RnnSmem),
-                [&](void *sm) { ns::rnn_body<ns::kRnnThreads>(p, *(ns::RnnSmem *)sm); });
+    rc = launch((groups * ns::kMmaStreams + ns::kFeatWarps - 1) / ns::kFeatWarps, 32 * ns::kFeatWarps, sizeof(ns::FeatSmem),
+                [&](void *sm) { ns::features_body(p, *(ns::FeatSmem *)sm); });
+    if (rc) return rc;
+    rc = launch(groups, ns::kMmaThreads, sizeof(ns::RnnSmem), [&](void *sm) { ns::rnn_body(p, *(ns::RnnSmem *)sm); });
     if (rc) return rc;
     const int syn_tasks = n_streams * ((nf + ns::kSynRun - 1) / ns::kSynRun);
     rc = launch(syn_tasks < 3 ? syn_tasks : 3, ns::kGroupThreads, sizeof(ns::SpecSmem),
