@@ -138,23 +138,47 @@ enum MmaJob : int32_t {
   kJVadOut = 8,  // vad_output             K = DV           N = 1 (8)
   kNumMmaJobs = 9
 };
-constexpr int kMmaMaxKt = 14;
-struct MmaJobDesc {
-  int32_t nkt;               // k-tiles in this job's K list
-  int32_t nnt;               // n-tiles (8 outputs each)
-  int32_t w_off;             // offset (uint32 words) of the job's B fragments: [i][nt][32][2]
-  int32_t b_off;             // offset into bias (nnt*8 f32, zero padded)
-  int32_t activation;        // 0 tanh, 1 sigmoid, 2 relu (of the layer)
-  int32_t kt[kMmaMaxKt];     // virtual k-tile index of list position i
-  int32_t pad;
+// compile-time shape of every product: its k-tile list (virtual k-tile indices) and n-tile count.
+// The kernel unrolls over it (every shared-memory offset becomes an immediate); the host packer
+// (ns_host.cpp pack_rnn) walks the same lists.
+template <int V>
+struct IntC {
+  static constexpr int value = V;
+};
+template <int... KT>
+struct KtList {
+  static constexpr int n = (int)sizeof...(KT);
+};
+template <int J>
+struct MmaShape;
+template <> struct MmaShape<kJDense>   { using Kt = KtList<24, 25, 26>; static constexpr int nnt = 3; };
+template <> struct MmaShape<kJVadZR>   { using Kt = KtList<0, 1, 2>; static constexpr int nnt = 6; };
+template <> struct MmaShape<kJVadC>    { using Kt = KtList<3, 4, 5>; static constexpr int nnt = 3; };
+template <> struct MmaShape<kJNoiseZR> { using Kt = KtList<0, 1, 2, 24, 25, 26, 6, 7, 8>; static constexpr int nnt = 12; };
+template <> struct MmaShape<kJNoiseC>  { using Kt = KtList<0, 1, 2, 24, 25, 26, 9, 10, 11>; static constexpr int nnt = 6; };
+template <> struct MmaShape<kJDenZR>   { using Kt = KtList<1, 2, 6, 7, 8, 24, 25, 26, 12, 13, 14, 15, 16, 17>; static constexpr int nnt = 24; };
+template <> struct MmaShape<kJDenC>    { using Kt = KtList<1, 2, 6, 7, 8, 24, 25, 26, 18, 19, 20, 21, 22, 23>; static constexpr int nnt = 12; };
+template <> struct MmaShape<kJOut>     { using Kt = KtList<12, 13, 14, 15, 16, 17>; static constexpr int nnt = 3; };
+template <> struct MmaShape<kJVadOut>  { using Kt = KtList<0, 1, 2>; static constexpr int nnt = 1; };
+// B fragments of job J start at word MmaOff<J>::w ([i][nt][32 lanes][2 words]); its nnt*8 biases at MmaOff<J>::b
+template <int J>
+struct MmaOff {
+  static constexpr int w = MmaOff<J - 1>::w + MmaShape<J - 1>::Kt::n * MmaShape<J - 1>::nnt * 64;
+  static constexpr int b = MmaOff<J - 1>::b + MmaShape<J - 1>::nnt * 8;
+};
+template <>
+struct MmaOff<0> {
+  static constexpr int w = 0, b = 0;
 };
 struct RnnHeader {
-  MmaJobDesc jobs[kNumMmaJobs];
+  int32_t activation[kNumMmaJobs];  // 0 tanh, 1 sigmoid, 2 relu (of the layer behind each product)
   int32_t n_words;
   int32_t n_bias;
+  int32_t pad;
 };
-constexpr int kMmaWordsMax = 46272;      // 723 B-fragment tiles x 64 words for the RNNoise topology
-constexpr int kMmaBiasMax = 576;
+constexpr int kMmaWords = MmaOff<kNumMmaJobs>::w;  // 723 B-fragment tiles x 64 words = 46,272
+constexpr int kMmaBias = MmaOff<kNumMmaJobs>::b;   // 560
+static_assert(kMmaWords == 46272 && kMmaBias == 560, "RNNoise topology");
 
 // ---- launch parameters
 enum Flags : uint32_t {

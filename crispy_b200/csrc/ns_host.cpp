@@ -285,18 +285,20 @@ SrcIdx seg_src(int vkt, int kk) {
 // weight(src, idx, col) of one job; 0 where the job does not read that input / column
 using WeightFn = std::function<int(SrcIdx, int col)>;
 
-static void add_mma_job(PackedRnn &out, int job, const std::vector<int> &kts, int n_out, int act, const WeightFn &w,
-                        const std::function<int(int col)> &bias) {
-  MmaJobDesc &jd = out.hdr.jobs[job];
-  memset(&jd, 0, sizeof(jd));
-  jd.nkt = (int32_t)kts.size();
-  jd.nnt = (n_out + 7) / 8;
-  jd.w_off = (int32_t)out.words.size();
-  jd.b_off = (int32_t)out.bias.size();
-  jd.activation = act;
-  for (int i = 0; i < jd.nkt; i++) jd.kt[i] = kts[i];
-  for (int i = 0; i < jd.nkt; i++)
-    for (int nt = 0; nt < jd.nnt; nt++)
+template <int... KT>
+static std::vector<int> kt_vec(KtList<KT...>) {
+  return std::vector<int>{KT...};
+}
+
+// B fragments + biases of product J, in the compile-time shape the kernel unrolls over (ns_common.h MmaShape)
+template <int J>
+static void add_mma_job(PackedRnn &out, int n_out, int act, const WeightFn &w, const std::function<int(int col)> &bias) {
+  const std::vector<int> kts = kt_vec(typename MmaShape<J>::Kt{});
+  const int nnt = MmaShape<J>::nnt;
+  if ((int)out.words.size() != MmaOff<J>::w || (int)out.bias.size() != MmaOff<J>::b || (n_out + 7) / 8 != nnt) abort();
+  out.hdr.activation[J] = act;
+  for (size_t i = 0; i < kts.size(); i++)
+    for (int nt = 0; nt < nnt; nt++)
       for (int lane = 0; lane < 32; lane++)
         for (int r = 0; r < 2; r++) {
           const int n = nt * 8 + lane / 4;
@@ -308,7 +310,7 @@ static void add_mma_job(PackedRnn &out, int job, const std::vector<int> &kts, in
           }
           out.words.push_back(word);
         }
-  for (int col = 0; col < jd.nnt * 8; col++) out.bias.push_back(col < n_out ? (float)bias(col) : 0.f);
+  for (int col = 0; col < nnt * 8; col++) out.bias.push_back(col < n_out ? (float)bias(col) : 0.f);
 }
 
 void pack_rnn(const Model &m, PackedRnn &out) {
@@ -319,20 +321,8 @@ void pack_rnn(const Model &m, PackedRnn &out) {
   const GruLayer &gv = m.vad_gru, &gn = m.noise_gru, &gd = m.denoise_gru;
   auto gin = [](const GruLayer &g, int row, int col) { return (int)g.input_weights[(size_t)row * 3 * g.nb_neurons + col]; };
   auto grec = [](const GruLayer &g, int row, int col) { return (int)g.recurrent_weights[(size_t)row * 3 * g.nb_neurons + col]; };
-  const std::vector<int> kDV = {kKtDV, kKtDV + 1, kKtDV + 2}, kDVR = {kKtDVR, kKtDVR + 1, kKtDVR + 2};
-  const std::vector<int> kF = {kKtF, kKtF + 1, kKtF + 2};
-  auto cat = [](std::initializer_list<std::vector<int>> parts) {
-    std::vector<int> v;
-    for (const auto &p : parts) v.insert(v.end(), p.begin(), p.end());
-    return v;
-  };
-  auto range = [](int k0, int n) {
-    std::vector<int> v;
-    for (int i = 0; i < n; i++) v.push_back(k0 + i);
-    return v;
-  };
   // input_dense: features -> 24
-  add_mma_job(out, kJDense, kF, 24, d0.activation,
+  add_mma_job<kJDense>(out, 24, d0.activation,
               [&](SrcIdx s, int col) { return s.src == kSrcFeat ? (int)d0.weights[(size_t)s.idx * 24 + col] : 0; },
               [&](int col) { return (int)d0.bias[col]; });
   // vad_gru: input dense(24), state 24
@@ -343,8 +333,8 @@ void pack_rnn(const Model &m, PackedRnn &out) {
       return 0;
     };
   };
-  add_mma_job(out, kJVadZR, kDV, 48, 1, vad_w(0), [&](int col) { return (int)gv.bias[col]; });
-  add_mma_job(out, kJVadC, kDVR, 24, gv.activation, vad_w(48), [&](int col) { return (int)gv.bias[48 + col]; });
+  add_mma_job<kJVadZR>(out, 48, 1, vad_w(0), [&](int col) { return (int)gv.bias[col]; });
+  add_mma_job<kJVadC>(out, 24, gv.activation, vad_w(48), [&](int col) { return (int)gv.bias[48 + col]; });
   // noise_gru: input [dense 24 | vad state 24 | features 42], state 48
   auto noise_w = [&](int col0) {
     return [&, col0](SrcIdx s, int col) {
@@ -355,8 +345,8 @@ void pack_rnn(const Model &m, PackedRnn &out) {
       return 0;
     };
   };
-  add_mma_job(out, kJNoiseZR, cat({kDV, kF, range(kKtNH, 3)}), 96, 1, noise_w(0), [&](int col) { return (int)gn.bias[col]; });
-  add_mma_job(out, kJNoiseC, cat({kDV, kF, range(kKtNR, 3)}), 48, gn.activation, noise_w(96),
+  add_mma_job<kJNoiseZR>(out, 96, 1, noise_w(0), [&](int col) { return (int)gn.bias[col]; });
+  add_mma_job<kJNoiseC>(out, 48, gn.activation, noise_w(96),
               [&](int col) { return (int)gn.bias[96 + col]; });
   // denoise_gru: input [vad state 24 | noise state 48 | features 42], state 96.  DV k-tile 1 also
   // holds dense[16..24): zero weights.
@@ -369,17 +359,16 @@ void pack_rnn(const Model &m, PackedRnn &out) {
       return 0;
     };
   };
-  const std::vector<int> kDV12 = {kKtDV + 1, kKtDV + 2};
-  add_mma_job(out, kJDenZR, cat({kDV12, range(kKtNH, 3), kF, range(kKtDH, 6)}), 192, 1, den_w(0),
+  add_mma_job<kJDenZR>(out, 192, 1, den_w(0),
               [&](int col) { return (int)gd.bias[col]; });
-  add_mma_job(out, kJDenC, cat({kDV12, range(kKtNH, 3), kF, range(kKtDR, 6)}), 96, gd.activation, den_w(192),
+  add_mma_job<kJDenC>(out, 96, gd.activation, den_w(192),
               [&](int col) { return (int)gd.bias[192 + col]; });
   // denoise_output: denoise state -> 22 band gains
-  add_mma_job(out, kJOut, range(kKtDH, 6), 22, dg.activation,
+  add_mma_job<kJOut>(out, 22, dg.activation,
               [&](SrcIdx s, int col) { return s.src == kSrcDenH ? (int)dg.weights[(size_t)s.idx * 22 + col] : 0; },
               [&](int col) { return (int)dg.bias[col]; });
   // vad_output: vad state -> 1 (column 0 of one n-tile)
-  add_mma_job(out, kJVadOut, kDV, 1, dv.activation,
+  add_mma_job<kJVadOut>(out, 1, dv.activation,
               [&](SrcIdx s, int col) { return (s.src == kSrcVadH && col == 0) ? (int)dv.weights[s.idx] : 0; },
               [&](int col) { return (int)dv.bias[col]; });
   out.hdr.n_words = (int32_t)out.words.size();

@@ -31,21 +31,26 @@ NS_DEV f4 ld4(const float *p) { return *reinterpret_cast<const f4 *>(p); }
 // =================================================================================================
 // K0: a6 biquad high-pass.  upstream denoise.c biquad(): y = x + mem0 (f32);
 // mem0 = (f32)(mem1 + (b0 x - a0 y)), mem1 = (f32)(b1 x - a1 y) with f64 intermediates.  The f32
-// rounding of the state makes the recursion non-linear, so it is run serially, one lane per stream;
-// a warp moves 32-sample x 32-stream tiles through shared memory so HBM sees 128-byte rows.
+// rounding of the state makes the recursion non-linear (two trajectories a few ulps apart never
+// merge: measured, scripts/micro), so it runs serially, one lane per stream, and nothing else may
+// sit on that lane's critical path.
 // =================================================================================================
-// One CTA = 32 streams = two warps.  Warp 0, one lane per stream, walks the chunk in tiles of 96
-// samples: cp.async (LDGSTS) keeps three tiles of PCM in flight into a 4-slot shared-memory ring,
-// the lane runs the recursion over its row with 128-bit shared-memory accesses, then the warp
-// writes the tile to the hp workspace with 512-byte row segments.  There is no block barrier in the
-// loop (a bar.sync would wait for the global stores to drain).  Warp 1 copies the stream history
-// to the front of the workspace rows meanwhile.
-constexpr int kHpThreads = 64;
+// One CTA = 32 streams = three specialised warps that meet only through shared-memory flags (a
+// bar.sync would make the recursion wait for the other warps' global memory traffic):
+//   warp 1 (loader)   : cp.async (LDGSTS) tiles of 96 samples x 32 streams into a ring, two tiles ahead
+//   warp 0 (recursion): one lane per stream runs the biquad over its row of the tile in place
+//   warp 2 (storer)   : copies the stream history to the front of the hp rows, then writes every
+//                       finished tile to the hp workspace (and the chunk's tail to the state's history)
+// Flags hold "tile index + 1" per ring slot: landed (loader -> recursion), done (recursion ->
+// storer), freed (storer -> loader).
+constexpr int kHpThreads = 96;
 constexpr int kHpTile = 96;        // samples per tile; 480 = 5 tiles
 constexpr int kHpPitch = 100;      // floats per row in shared memory: 4*lane banks apart for LDS.128
 constexpr int kHpStages = 4;
+constexpr int kHpAhead = 2;        // tiles the loader keeps in flight beyond the one it is publishing
 struct HpSmem {
   float tile[kHpStages][32][kHpPitch];
+  int landed[kHpStages], done[kHpStages], freed[kHpStages];
 };
 
 NS_DEV float load_sample(const Params &p, int stream, long long idx) {
@@ -57,7 +62,7 @@ NS_DEV float load_sample(const Params &p, int stream, long long idx) {
 // tile `n` of the chunk -> ring slot; fast path: 16-byte cp.async (lanes 0..23 cover one 384-byte row
 // segment per instruction), else plain loads
 NS_DEV void hp_fetch_tile(const Params &p, HpSmem &sm, int s0, int nrows, long long in0, int n, bool fast, int lane) {
-  float(*dst)[kHpPitch] = sm.tile[n & (kHpStages - 1)];
+  float(*dst)[kHpPitch] = sm.tile[n % kHpStages];
   const long long idx0 = in0 + (long long)n * kHpTile;
   if (fast) {
     if (lane < kHpTile / 4) {
@@ -98,29 +103,36 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
   const int nsamp = p.n_frames * kFrame;
   const int ntiles = nsamp / kHpTile;
   const bool tail_direct = nsamp >= kHist;  // the new history is the chunk's own tail
-  if (warp == 1) {
-    hp_copy_rows(p.state + (long long)s0 * kStateFloats + kStHist, kStateFloats, p.hp + (long long)s0 * p.hp_stride,
-                 p.hp_stride, nrows, lane);
-    if (tail_direct) Simt::cta_sync();  // the old history has been read: warp 0 may overwrite it from here on
-  } else {
+  if (tid < kHpStages) sm.landed[tid] = sm.done[tid] = sm.freed[tid] = 0;
+  Simt::cta_sync();
+  if (warp == 1) {  // ---- loader
     const long long in0 = (long long)p.frame0 * kFrame;
     const bool fast = !(p.flags & kFlagInI16) && (p.in_stride & 3) == 0 && (in0 & 3) == 0 &&
                       (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
+    for (int n = 0; n < ntiles + kHpAhead; n++) {
+      if (n < ntiles) {
+        if (n >= kHpStages) Simt::flag_wait(&sm.freed[n % kHpStages], n - kHpStages + 1, true);
+        hp_fetch_tile(p, sm, s0, nrows, in0, n, fast, lane);
+      }
+      Simt::cp_async_commit();
+      if (n >= kHpAhead) {  // tile n - kHpAhead has landed in every lane's view: publish it
+        Simt::cp_async_wait<kHpAhead>();
+        Simt::fence_cta();
+        Simt::warp_sync();
+        if (lane == 0) Simt::flag_set(&sm.landed[(n - kHpAhead) % kHpStages], n - kHpAhead + 1);
+      }
+    }
+  } else if (warp == 0) {  // ---- recursion
     const float scale = ((p.flags & kFlagUnitScale) && !(p.flags & kFlagInI16)) ? 32768.0f : 1.0f;  // audio.rs:264
     const bool valid = lane < nrows;
     float *st = p.state + (long long)(s0 + (valid ? lane : 0)) * kStateFloats;
     float m0 = valid ? st[kStHp] : 0.f, m1 = valid ? st[kStHp + 1] : 0.f;
-    const double a0 = (double)-1.99599f, a1 = (double)0.99600f;
-    for (int n = 0; n < kHpStages - 1; n++) {
-      if (n < ntiles) hp_fetch_tile(p, sm, s0, nrows, in0, n, fast, lane);
-      Simt::cp_async_commit();
-    }
+    const double na0 = -(double)-1.99599f, na1 = -(double)0.99600f;
     for (int n = 0; n < ntiles; n++) {
-      Simt::cp_async_wait<kHpStages - 2>();
-      Simt::warp_sync();
-      float(*tile)[kHpPitch] = sm.tile[n & (kHpStages - 1)];
+      const int slot = n % kHpStages;
+      Simt::flag_wait(&sm.landed[slot], n + 1, false);
       if (valid) {
-        float *row = tile[lane];
+        float *row = sm.tile[slot][lane];
 #pragma unroll 2
         for (int c = 0; c < kHpTile; c += 4) {
           const f4 xv = ld4(row + c);
@@ -131,16 +143,32 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
             const float xi = x[i];
             const float yi = xi + m0;
             const double xd = (double)xi, yd = (double)yi;
-            m0 = (float)((double)m1 + (-2.0 * xd - a0 * yd));
-            m1 = (float)(xd - a1 * yd);
+            // a0*y and a1*y are exact in f64 (24 x 24 bit), so the fused forms round exactly like
+            // upstream's  mem1 + (b0*x - a0*y)  and  b1*x - a1*y
+            m0 = (float)((double)m1 + fma(na0, yd, -2.0 * xd));
+            m1 = (float)fma(na1, yd, xd);
             y[i] = yi;
           }
           *reinterpret_cast<f4 *>(row + c) = f4{y[0], y[1], y[2], y[3]};
         }
       }
+      Simt::fence_cta();
       Simt::warp_sync();
+      if (lane == 0) Simt::flag_set(&sm.done[slot], n + 1);
+    }
+    if (valid) {
+      st[kStHp] = m0;
+      st[kStHp + 1] = m1;
+    }
+  } else {  // ---- storer
+    hp_copy_rows(p.state + (long long)s0 * kStateFloats + kStHist, kStateFloats, p.hp + (long long)s0 * p.hp_stride,
+                 p.hp_stride, nrows, lane);
+    Simt::warp_sync();  // the old history has been read: the tail tiles may overwrite it
+    for (int n = 0; n < ntiles; n++) {
+      const int slot = n % kHpStages;
+      Simt::flag_wait(&sm.done[slot], n + 1, true);
+      float(*tile)[kHpPitch] = sm.tile[slot];
       const int base = n * kHpTile;
-      if (tail_direct && base + kHpTile > nsamp - kHist && base <= nsamp - kHist) Simt::cta_sync();  // see warp 1
       if (lane < kHpTile / 4) {
         const int c = 4 * lane;
         float *dsth = p.hp + (long long)s0 * p.hp_stride + kHist + base + c;
@@ -158,27 +186,19 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
         }
       }
       Simt::warp_sync();
-      if (n + kHpStages - 1 < ntiles) hp_fetch_tile(p, sm, s0, nrows, in0, n + kHpStages - 1, fast, lane);
-      Simt::cp_async_commit();
+      if (lane == 0) Simt::flag_set(&sm.freed[slot], n + 1);
     }
-    Simt::cp_async_wait<0>();
-    if (valid) {
-      st[kStHp] = m0;
-      st[kStHp + 1] = m1;
-    }
-  }
-  if (!tail_direct) {  // short chunk: last kHist samples of [history | chunk] -> state
-    Simt::cta_sync();
-    if (warp == 1) {
-      // every row is read in full into registers? no: kHist floats do not fit; stage through the (now idle) ring
-      float *stage = &sm.tile[0][0][0];
+    if (!tail_direct) {  // short chunk: last kHist samples of [history | chunk] -> state, staged through registers
+      Simt::fence_cta();
+      Simt::warp_sync();
       for (int r = 0; r < nrows; r++) {
         const float *src = p.hp + (long long)(s0 + r) * p.hp_stride + nsamp;
         float *dst = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
-        for (int i = lane; i < kHist; i += 32) stage[i] = src[i];
-        Simt::warp_sync();
-        for (int i = lane; i < kHist; i += 32) dst[i] = stage[i];
-        Simt::warp_sync();
+        float v[kHist / 32];
+#pragma unroll
+        for (int i = 0; i < kHist / 32; i++) v[i] = src[lane + 32 * i];
+#pragma unroll
+        for (int i = 0; i < kHist / 32; i++) dst[lane + 32 * i] = v[i];
       }
     }
   }
@@ -921,20 +941,16 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
 // =================================================================================================
 // activations (rnn.c tansig_approx / sigmoid_approx / relu)
 // =================================================================================================
+// tansig_approx without branches: |x| is clamped to 8, where the table ends at exactly 1.0 with zero
+// slope, so x >= 8 (and NaN) give +-1 as upstream's early returns do; floor(.5 + 25|x|) is a truncation.
 NS_DEV float tansig_approx(const float *tab, float x) {
-  if (!(x < 8.f)) return 1.f;
-  if (!(x > -8.f)) return -1.f;
-  float sign = 1.f;
-  if (x < 0.f) {
-    x = -x;
-    sign = -1.f;
-  }
-  const int i = (int)floorf(.5f + 25.f * x);
-  x -= .04f * i;
+  const float ax = fminf(fabsf(x), 8.f);
+  const int i = (int)(.5f + 25.f * ax);
+  const float d = ax - .04f * i;
   float y = tab[i];
   const float dy = 1.f - y * y;
-  y = y + x * dy * (1.f - y * x);
-  return sign * y;
+  y = y + d * dy * (1.f - y * d);
+  return copysignf(y, x);
 }
 NS_DEV float sigmoid_approx(const float *tab, float x) { return .5f + .5f * tansig_approx(tab, .5f * x); }
 NS_DEV float activate(const float *tab, int act, float x) {
@@ -951,6 +967,11 @@ NS_DEV uint32_t bf16_rn_bits(float x) {
 NS_DEV void bf16_split(float x, uint32_t &hi, uint32_t &lo) {
   hi = bf16_rn_bits(x);
   lo = bf16_rn_bits(x - u2f(hi << 16));
+}
+// two activations -> one word of the hi plane and one of the lo plane (v0 in the low halfword)
+NS_DEV void bf16_split2(float v0, float v1, uint32_t &hi, uint32_t &lo) {
+  hi = Simt::bf16x2_rn(v0, v1);
+  lo = Simt::bf16x2_rn(v0 - u2f(hi << 16), v1 - u2f(hi & 0xFFFF0000u));
 }
 struct alignas(16) u4 {
   uint32_t x, y, z, w;
@@ -1093,61 +1114,78 @@ NS_DEV void features_body(const Params &p, FeatSmem &sm) {
 // Neuron tile j (8 neurons) of a GRU belongs to warp j % 8 in both its z|r and candidate products.
 // =================================================================================================
 struct RnnSmem {
-  uint32_t w[kMmaWordsMax];
+  uint32_t w[kMmaWords];
   uint32_t ahi[kKtResident * kKtWords];
   uint32_t alo[kKtResident * kKtWords];
   uint32_t fq[2][kFeatBlockWords];
-  float bias[kMmaBiasMax];
+  float bias[kMmaBias];
   float tansig[204];
-  MmaJobDesc jobs[kNumMmaJobs];
+  int act[kNumMmaJobs];
 };
 static_assert(sizeof(RnnSmem) <= 232448, "recurrent-core shared memory exceeds the 227 KB a CTA may use");
 
-// one product: this warp's `nact` (<= NACC) n-tiles `tiles[]`, all k-tiles of the job; hi and lo planes
-// accumulate separately (two independent MMA chains per n-tile)
-template <int NACC>
-NS_DEV void mma_run(const RnnSmem &r, const MmaJobDesc &jd, const uint32_t *fcur, const int (&tiles)[NACC], int nact,
-                    int lane, float (&acc)[NACC][2][4]) {
+// product J for this warp's `nact` (<= NACC) n-tiles `tiles[]`: every k-tile of the job's compile-time
+// list, hi and lo planes into separate accumulators (two independent MMA chains per n-tile).  All
+// shared-memory offsets except the warp's tile bases are immediates.
+template <int J, int NACC, int... KT>
+NS_DEV void mma_run_list(const RnnSmem &r, const uint32_t *fcur, const int (&tiles)[NACC], int nact, int lane,
+                         float (&acc)[NACC][2][4], KtList<KT...>) {
+  constexpr int NNT = MmaShape<J>::nnt;
 #pragma unroll
   for (int n = 0; n < NACC; n++)
 #pragma unroll
     for (int e = 0; e < 4; e++) acc[n][0][e] = acc[n][1][e] = 0.f;
-  const uint32_t *wj = r.w + jd.w_off + lane * 2;
-  const int nkt = jd.nkt, nnt = jd.nnt;
-  for (int i = 0; i < nkt; i++) {
-    const int v = jd.kt[i];
-    const uint32_t *ph = (v < kKtResident) ? r.ahi + v * kKtWords : fcur + (v - kKtF) * kKtWords;
-    const uint32_t *pl = (v < kKtResident) ? r.alo + v * kKtWords : fcur + (kFeatKt + v - kKtF) * kKtWords;
-    const u4 ah4 = *reinterpret_cast<const u4 *>(ph + lane * 4), al4 = *reinterpret_cast<const u4 *>(pl + lane * 4);
+  const uint32_t *wb[NACC];
+#pragma unroll
+  for (int n = 0; n < NACC; n++) wb[n] = r.w + MmaOff<J>::w + tiles[n] * 64 + lane * 2;
+  const uint32_t *res_hi = r.ahi + lane * 4, *res_lo = r.alo + lane * 4, *f_hi = fcur + lane * 4;
+  int i = 0;
+  auto step = [&](auto vt) {
+    constexpr int v = decltype(vt)::value;
+    const uint32_t *ph = (v < kKtResident) ? res_hi + v * kKtWords : f_hi + (v - kKtF) * kKtWords;
+    const uint32_t *pl = (v < kKtResident) ? res_lo + v * kKtWords : f_hi + (kFeatKt + v - kKtF) * kKtWords;
+    const u4 ah4 = *reinterpret_cast<const u4 *>(ph), al4 = *reinterpret_cast<const u4 *>(pl);
     const uint32_t ah[4] = {ah4.x, ah4.y, ah4.z, ah4.w}, al[4] = {al4.x, al4.y, al4.z, al4.w};
 #pragma unroll
     for (int n = 0; n < NACC; n++) {
       if (n < nact) {
-        const u2 b2 = *reinterpret_cast<const u2 *>(wj + (i * nnt + tiles[n]) * 64);
+        const u2 b2 = *reinterpret_cast<const u2 *>(wb[n] + i * NNT * 64);
         const uint32_t b[2] = {b2.x, b2.y};
         Simt::mma_bf16_16816(acc[n][0], ah, b);
         Simt::mma_bf16_16816(acc[n][1], al, b);
       }
     }
-  }
+    i++;
+  };
+  (step(IntC<KT>{}), ...);
+}
+template <int J, int NACC>
+NS_DEV void mma_run(const RnnSmem &r, const uint32_t *fcur, const int (&tiles)[NACC], int nact, int lane,
+                    float (&acc)[NACC][2][4]) {
+  mma_run_list<J, NACC>(r, fcur, tiles, nact, lane, acc, typename MmaShape<J>::Kt{});
 }
 
-// S * (bias + sum) of accumulator element e of n-tile `tile`: rows lane/4 (e < 2) and lane/4 + 8,
-// output column tile*8 + 2*(lane%4) + (e & 1)
-NS_DEV float mma_pre(const RnnSmem &r, const MmaJobDesc &jd, const float (&acc)[2][4], int tile, int lane, int e) {
-  const float b = r.bias[jd.b_off + tile * 8 + 2 * (lane & 3) + (e & 1)];
-  return ((acc[0][e] + acc[1][e]) + b) * (1.f / 256);
+// S * (bias + sum) of the four accumulator elements of n-tile `tile`: rows lane/4 (e < 2) and
+// lane/4 + 8, output columns tile*8 + 2*(lane%4) + (e & 1)
+template <int J>
+NS_DEV void mma_pre(const RnnSmem &r, const float (&acc)[2][4], int tile, int lane, float (&x)[4]) {
+  const float *b = r.bias + MmaOff<J>::b + tile * 8 + 2 * (lane & 3);
+  const float b0 = b[0], b1 = b[1];
+  x[0] = ((acc[0][0] + acc[1][0]) + b0) * (1.f / 256);
+  x[1] = ((acc[0][1] + acc[1][1]) + b1) * (1.f / 256);
+  x[2] = ((acc[0][2] + acc[1][2]) + b0) * (1.f / 256);
+  x[3] = ((acc[0][3] + acc[1][3]) + b1) * (1.f / 256);
 }
 
 // write this lane's four values (rows lane/4 and lane/4+8, inputs k0 + 2*(lane%4) + {0,1}) of the
 // 8 inputs starting at resident position k0 (a multiple of 8) as hi/lo A fragments
 NS_DEV void store_frag(RnnSmem &r, int k0, int lane, const float (&v)[4]) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int e = 0; e < 4; e++) bf16_split(v[e], h[e], l[e]);
+  uint32_t h0, l0, h1, l1;
+  bf16_split2(v[0], v[1], h0, l0);
+  bf16_split2(v[2], v[3], h1, l1);
   const int off = ((k0 >> 4) * 32 + lane) * 4 + ((k0 >> 3) & 1) * 2;
-  *reinterpret_cast<u2 *>(r.ahi + off) = u2{h[0] | (h[1] << 16), h[2] | (h[3] << 16)};
-  *reinterpret_cast<u2 *>(r.alo + off) = u2{l[0] | (l[1] << 16), l[2] | (l[3] << 16)};
+  *reinterpret_cast<u2 *>(r.ahi + off) = u2{h0, h1};
+  *reinterpret_cast<u2 *>(r.alo + off) = u2{l0, l1};
 }
 
 // resident positions (k index = k-tile * 16 + kk) of the activation vectors
@@ -1162,16 +1200,14 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
   const int s0 = Simt::cta() * kMmaStreams;
   const int srow[2] = {s0 + g, s0 + g + 8};
   const bool live[2] = {srow[0] < p.n_streams, srow[1] < p.n_streams};
-  {  // weights, biases, tables, job descriptors -> shared memory; activations cleared
+  {  // weights, biases, tables -> shared memory; activation fragments cleared
     const RnnHeader &H = *p.rnn_hdr;
     const u4 *src = reinterpret_cast<const u4 *>(p.rnn_words);
     u4 *dst = reinterpret_cast<u4 *>(r.w);
-    for (int i = tid; i < H.n_words / 4; i += NT) dst[i] = src[i];
-    for (int i = tid; i < H.n_bias; i += NT) r.bias[i] = p.rnn_bias[i];
+    for (int i = tid; i < kMmaWords / 4; i += NT) dst[i] = src[i];
+    for (int i = tid; i < kMmaBias; i += NT) r.bias[i] = p.rnn_bias[i];
     for (int i = tid; i < 204; i += NT) r.tansig[i] = p.tables->tansig[i];
-    const int32_t *js = reinterpret_cast<const int32_t *>(H.jobs);
-    int32_t *jd = reinterpret_cast<int32_t *>(r.jobs);
-    for (int i = tid; i < (int)(sizeof(MmaJobDesc) * kNumMmaJobs / 4); i += NT) jd[i] = js[i];
+    if (tid < kNumMmaJobs) r.act[tid] = H.activation[tid];
     for (int i = tid; i < kKtResident * kKtWords; i += NT) r.ahi[i] = r.alo[i] = 0u;
   }
   const uint32_t *fq_src = p.featq + (long long)Simt::cta() * p.chunk_cap * kFeatBlockWords;
@@ -1210,149 +1246,141 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
   Simt::cp_async_wait<0>();
   Simt::cta_sync();
   const float *tab = r.tansig;
+  const int act_dense = r.act[kJDense], act_vad = r.act[kJVadC], act_noise = r.act[kJNoiseC], act_den = r.act[kJDenC],
+            act_out = r.act[kJOut], act_vadout = r.act[kJVadOut];
+  // GRU update of the four (row, neuron) elements this lane owns
+  auto gru_update = [&](float (&h)[4], const float (&z)[4], const float (&x)[4], int act, const bool (&sil)[2]) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float cnd = activate(tab, act, x[e]);
+      const float hnew = z[e] * h[e] + (1.f - z[e]) * cnd;
+      if (!sil[e >> 1]) h[e] = hnew;
+    }
+  };
   for (int t = 0; t < p.n_frames; t++) {
     const uint32_t *fcur = r.fq[t & 1];
     if (t + 1 < p.n_frames) fetch(t + 1);
-    const uint32_t *flags = fcur + 2 * kFeatKt * kKtWords;
-    bool any_active = false;
+    const u4 *flags4 = reinterpret_cast<const u4 *>(fcur + 2 * kFeatKt * kKtWords);
+    uint32_t all_silent = 1u;
 #pragma unroll
-    for (int i = 0; i < kMmaStreams; i++) any_active = any_active || (flags[i] == 0u);
+    for (int i = 0; i < kMmaStreams / 4; i++) {
+      const u4 f = flags4[i];
+      all_silent &= f.x & f.y & f.z & f.w;
+    }
+    const uint32_t *flags = fcur + 2 * kFeatKt * kKtWords;
     const bool sil[2] = {flags[g] != 0u, flags[g + 8] != 0u};
     float vad[2] = {0.f, 0.f};
     float gout[4] = {0.f, 0.f, 0.f, 0.f}, graw[4] = {0.f, 0.f, 0.f, 0.f};
-    if (any_active) {
-      {  // input_dense: features -> dense (both copies)
-        if (warp < 3) {
-          const MmaJobDesc &jd = r.jobs[kJDense];
-          float acc[1][2][4];
-          const int tiles[1] = {warp};
-          mma_run<1>(r, jd, fcur, tiles, 1, lane, acc);
-          float y[4];
-#pragma unroll
-          for (int e = 0; e < 4; e++) y[e] = activate(tab, jd.activation, mma_pre(r, jd, acc[0], warp, lane, e));
-          store_frag(r, kPosDense + warp * 8, lane, y);
-          store_frag(r, kPosDense2 + warp * 8, lane, y);
-        }
-        Simt::cta_sync();
-      }
-      float z[2][4];
-      {  // vad_gru
-        if (warp < 3) {
-          const MmaJobDesc &jd = r.jobs[kJVadZR];
-          float acc[2][2][4];
-          const int tiles[2] = {warp, 3 + warp};
-          mma_run<2>(r, jd, fcur, tiles, 2, lane, acc);
-          float rh[4];
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            z[0][e] = sigmoid_approx(tab, mma_pre(r, jd, acc[0], tiles[0], lane, e));
-            rh[e] = hv[e] * sigmoid_approx(tab, mma_pre(r, jd, acc[1], tiles[1], lane, e));
-          }
-          store_frag(r, kPosVadR + warp * 8, lane, rh);
-        }
-        Simt::cta_sync();
-        if (warp < 3) {
-          const MmaJobDesc &jd = r.jobs[kJVadC];
-          float acc[1][2][4];
-          const int tiles[1] = {warp};
-          mma_run<1>(r, jd, fcur, tiles, 1, lane, acc);
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const float cnd = activate(tab, jd.activation, mma_pre(r, jd, acc[0], warp, lane, e));
-            const float hnew = z[0][e] * hv[e] + (1.f - z[0][e]) * cnd;
-            if (!sil[e >> 1]) hv[e] = hnew;
-          }
-          store_frag(r, kPosVadH + warp * 8, lane, hv);
-        }
-        Simt::cta_sync();
-      }
-      {  // noise_gru (warps 0-5); vad_output on the settled vad state (warp 7)
-        if (warp < 6) {
-          const MmaJobDesc &jd = r.jobs[kJNoiseZR];
-          float acc[2][2][4];
-          const int tiles[2] = {warp, 6 + warp};
-          mma_run<2>(r, jd, fcur, tiles, 2, lane, acc);
-          float rh[4];
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            z[0][e] = sigmoid_approx(tab, mma_pre(r, jd, acc[0], tiles[0], lane, e));
-            rh[e] = hn[e] * sigmoid_approx(tab, mma_pre(r, jd, acc[1], tiles[1], lane, e));
-          }
-          store_frag(r, kPosNoiseR + warp * 8, lane, rh);
-        } else if (warp == 7) {
-          const MmaJobDesc &jd = r.jobs[kJVadOut];
-          float acc[1][2][4];
-          const int tiles[1] = {0};
-          mma_run<1>(r, jd, fcur, tiles, 1, lane, acc);
-          vad[0] = activate(tab, jd.activation, mma_pre(r, jd, acc[0], 0, lane, 0));  // column 0 lives in lanes with lane%4 == 0
-          vad[1] = activate(tab, jd.activation, mma_pre(r, jd, acc[0], 0, lane, 2));
-        }
-        Simt::cta_sync();
-        if (warp < 6) {
-          const MmaJobDesc &jd = r.jobs[kJNoiseC];
-          float acc[1][2][4];
-          const int tiles[1] = {warp};
-          mma_run<1>(r, jd, fcur, tiles, 1, lane, acc);
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const float cnd = activate(tab, jd.activation, mma_pre(r, jd, acc[0], warp, lane, e));
-            const float hnew = z[0][e] * hn[e] + (1.f - z[0][e]) * cnd;
-            if (!sil[e >> 1]) hn[e] = hnew;
-          }
-          store_frag(r, kPosNoiseH + warp * 8, lane, hn);
-        }
-        Simt::cta_sync();
-      }
-      {  // denoise_gru: warp w owns neuron tiles w and (w < 4) w + 8
-        const int nown = warp < 4 ? 2 : 1;
-        {
-          const MmaJobDesc &jd = r.jobs[kJDenZR];
-          float acc[4][2][4];
-          const int tiles[4] = {warp, 12 + warp, warp + 8, 12 + warp + 8};
-          mma_run<4>(r, jd, fcur, tiles, 2 * nown, lane, acc);
-#pragma unroll
-          for (int o = 0; o < 2; o++) {
-            if (o < nown) {
-              float rh[4];
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                z[o][e] = sigmoid_approx(tab, mma_pre(r, jd, acc[2 * o], tiles[2 * o], lane, e));
-                rh[e] = hd[o][e] * sigmoid_approx(tab, mma_pre(r, jd, acc[2 * o + 1], tiles[2 * o + 1], lane, e));
-              }
-              store_frag(r, kPosDenR + tiles[2 * o] * 8, lane, rh);
-            }
-          }
-        }
-        Simt::cta_sync();
-        {
-          const MmaJobDesc &jd = r.jobs[kJDenC];
-          float acc[2][2][4];
-          const int tiles[2] = {warp, warp + 8};
-          mma_run<2>(r, jd, fcur, tiles, nown, lane, acc);
-#pragma unroll
-          for (int o = 0; o < 2; o++) {
-            if (o < nown) {
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const float cnd = activate(tab, jd.activation, mma_pre(r, jd, acc[o], tiles[o], lane, e));
-                const float hnew = z[o][e] * hd[o][e] + (1.f - z[o][e]) * cnd;
-                if (!sil[e >> 1]) hd[o][e] = hnew;
-              }
-              store_frag(r, kPosDenH + tiles[o] * 8, lane, hd[o]);
-            }
-          }
-        }
-        Simt::cta_sync();
-      }
-      if (warp < 3) {  // denoise_output -> band gains; g = max(g, 0.6 lastg)
-        const MmaJobDesc &jd = r.jobs[kJOut];
+    if (!all_silent) {
+      float x[4], z[2][4];
+      if (warp < 3) {  // input_dense: features -> dense (both copies)
         float acc[1][2][4];
         const int tiles[1] = {warp};
-        mma_run<1>(r, jd, fcur, tiles, 1, lane, acc);
+        mma_run<kJDense, 1>(r, fcur, tiles, 1, lane, acc);
+        mma_pre<kJDense>(r, acc[0], warp, lane, x);
+        float y[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) y[e] = activate(tab, act_dense, x[e]);
+        store_frag(r, kPosDense + warp * 8, lane, y);
+        store_frag(r, kPosDense2 + warp * 8, lane, y);
+      }
+      Simt::cta_sync();
+      if (warp < 3) {  // vad_gru z | r
+        float acc[2][2][4];
+        const int tiles[2] = {warp, 3 + warp};
+        mma_run<kJVadZR, 2>(r, fcur, tiles, 2, lane, acc);
+        float rh[4];
+        mma_pre<kJVadZR>(r, acc[0], tiles[0], lane, x);
+#pragma unroll
+        for (int e = 0; e < 4; e++) z[0][e] = sigmoid_approx(tab, x[e]);
+        mma_pre<kJVadZR>(r, acc[1], tiles[1], lane, x);
+#pragma unroll
+        for (int e = 0; e < 4; e++) rh[e] = hv[e] * sigmoid_approx(tab, x[e]);
+        store_frag(r, kPosVadR + warp * 8, lane, rh);
+      }
+      Simt::cta_sync();
+      if (warp < 3) {  // vad_gru candidate
+        float acc[1][2][4];
+        const int tiles[1] = {warp};
+        mma_run<kJVadC, 1>(r, fcur, tiles, 1, lane, acc);
+        mma_pre<kJVadC>(r, acc[0], warp, lane, x);
+        gru_update(hv, z[0], x, act_vad, sil);
+        store_frag(r, kPosVadH + warp * 8, lane, hv);
+      }
+      Simt::cta_sync();
+      if (warp < 6) {  // noise_gru z | r (warps 0-5); vad_output on the settled vad state (warp 7)
+        float acc[2][2][4];
+        const int tiles[2] = {warp, 6 + warp};
+        mma_run<kJNoiseZR, 2>(r, fcur, tiles, 2, lane, acc);
+        float rh[4];
+        mma_pre<kJNoiseZR>(r, acc[0], tiles[0], lane, x);
+#pragma unroll
+        for (int e = 0; e < 4; e++) z[0][e] = sigmoid_approx(tab, x[e]);
+        mma_pre<kJNoiseZR>(r, acc[1], tiles[1], lane, x);
+#pragma unroll
+        for (int e = 0; e < 4; e++) rh[e] = hn[e] * sigmoid_approx(tab, x[e]);
+        store_frag(r, kPosNoiseR + warp * 8, lane, rh);
+      } else if (warp == 7) {
+        float acc[1][2][4];
+        const int tiles[1] = {0};
+        mma_run<kJVadOut, 1>(r, fcur, tiles, 1, lane, acc);
+        mma_pre<kJVadOut>(r, acc[0], 0, lane, x);  // column 0 lives in the lanes with lane % 4 == 0
+        vad[0] = activate(tab, act_vadout, x[0]);
+        vad[1] = activate(tab, act_vadout, x[2]);
+      }
+      Simt::cta_sync();
+      if (warp < 6) {  // noise_gru candidate
+        float acc[1][2][4];
+        const int tiles[1] = {warp};
+        mma_run<kJNoiseC, 1>(r, fcur, tiles, 1, lane, acc);
+        mma_pre<kJNoiseC>(r, acc[0], warp, lane, x);
+        gru_update(hn, z[0], x, act_noise, sil);
+        store_frag(r, kPosNoiseH + warp * 8, lane, hn);
+      }
+      Simt::cta_sync();
+      const int nown = warp < 4 ? 2 : 1;  // denoise_gru: warp w owns neuron tiles w and (w < 4) w + 8
+      {
+        float acc[4][2][4];
+        const int tiles[4] = {warp, 12 + warp, warp + 8, 12 + warp + 8};
+        mma_run<kJDenZR, 4>(r, fcur, tiles, 2 * nown, lane, acc);
+#pragma unroll
+        for (int o = 0; o < 2; o++) {
+          if (o < nown) {
+            float rh[4];
+            mma_pre<kJDenZR>(r, acc[2 * o], tiles[2 * o], lane, x);
+#pragma unroll
+            for (int e = 0; e < 4; e++) z[o][e] = sigmoid_approx(tab, x[e]);
+            mma_pre<kJDenZR>(r, acc[2 * o + 1], tiles[2 * o + 1], lane, x);
+#pragma unroll
+            for (int e = 0; e < 4; e++) rh[e] = hd[o][e] * sigmoid_approx(tab, x[e]);
+            store_frag(r, kPosDenR + tiles[2 * o] * 8, lane, rh);
+          }
+        }
+      }
+      Simt::cta_sync();
+      {
+        float acc[2][2][4];
+        const int tiles[2] = {warp, warp + 8};
+        mma_run<kJDenC, 2>(r, fcur, tiles, nown, lane, acc);
+#pragma unroll
+        for (int o = 0; o < 2; o++) {
+          if (o < nown) {
+            mma_pre<kJDenC>(r, acc[o], tiles[o], lane, x);
+            gru_update(hd[o], z[o], x, act_den, sil);
+            store_frag(r, kPosDenH + tiles[o] * 8, lane, hd[o]);
+          }
+        }
+      }
+      Simt::cta_sync();
+      if (warp < 3) {  // denoise_output -> band gains; g = max(g, 0.6 lastg)
+        float acc[1][2][4];
+        const int tiles[1] = {warp};
+        mma_run<kJOut, 1>(r, fcur, tiles, 1, lane, acc);
+        mma_pre<kJOut>(r, acc[0], warp, lane, x);
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           if (!sil[e >> 1]) {
-            graw[e] = activate(tab, jd.activation, mma_pre(r, jd, acc[0], warp, lane, e));
+            graw[e] = activate(tab, act_out, x[e]);
             gout[e] = fmaxf(graw[e], .6f * lastg[e]);
             lastg[e] = gout[e];
           }
@@ -1360,15 +1388,13 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
       }
     }
     if (warp < 3) {  // band gains of this frame -> record (zeros on silent frames)
+      const int band = warp * 8 + c2;
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        const int band = warp * 8 + c2;
         if (live[h] && band < kBands) {
           float *rec = p.rec + ((long long)srow[h] * p.chunk_cap + t) * kRecFloats;
-          rec[kRecGRaw + band] = graw[2 * h];
-          rec[kRecGRaw + band + 1] = graw[2 * h + 1];
-          rec[kRecG + band] = gout[2 * h];
-          rec[kRecG + band + 1] = gout[2 * h + 1];
+          *reinterpret_cast<cf *>(rec + kRecGRaw + band) = cf{graw[2 * h], graw[2 * h + 1]};
+          *reinterpret_cast<cf *>(rec + kRecG + band) = cf{gout[2 * h], gout[2 * h + 1]};
         }
       }
     } else if (warp == 7 && (lane & 3) == 0) {

@@ -50,6 +50,24 @@ struct Simt {
   static NS_DEV void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
   }
+  // shared-memory flags between the specialised warps of one CTA (no bar.sync): values only grow
+  static NS_DEV void fence_cta() { __threadfence_block(); }
+  static NS_DEV void flag_set(int *f, int v) {
+    __threadfence_block();
+    *reinterpret_cast<volatile int *>(f) = v;
+  }
+  static NS_DEV void flag_wait(const int *f, int v, bool relaxed) {
+    while (*reinterpret_cast<const volatile int *>(f) < v) {
+      if (relaxed) __nanosleep(200);
+    }
+    __threadfence_block();
+  }
+  // two floats -> packed bf16 pair, round to nearest even; `lo` lands in the low halfword
+  static NS_DEV uint32_t bf16x2_rn(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+  }
   // warp-wide tensor-pipe MMA (HMMA): D[16x8] += A[16x16] . B[16x8], bf16 inputs, f32 accumulate.
   // Fragment layouts are the PTX m16n8k16 ones (ns_common.h restates them).
   static NS_DEV void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -64,6 +82,7 @@ struct Simt {
 #else  // ---------------------------------------------------------------- host emulation
 
 #include <pthread.h>
+#include <sched.h>
 #include <string.h>
 
 #define NS_DEV inline
@@ -144,6 +163,18 @@ struct Simt {
   static void cp_async_commit() {}
   template <int N>
   static void cp_async_wait() {}
+  static uint32_t bf16x2_rn(float lo, float hi) {
+    auto rn = [](float x) {
+      const uint32_t u = f2u(x);
+      return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+    };
+    return rn(lo) | (rn(hi) << 16);
+  }
+  static void fence_cta() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+  static void flag_set(int *f, int v) { __atomic_store_n(f, v, __ATOMIC_SEQ_CST); }
+  static void flag_wait(const int *f, int v, bool) {
+    while (__atomic_load_n(f, __ATOMIC_SEQ_CST) < v) sched_yield();
+  }
   // mma.sync.m16n8k16 (bf16 x bf16 -> f32) emulated from the lanes' fragments: A element (row, k)
   // sits in lane (row%8)*4 + (k%8)/2, word row/8 + 2*(k/8), halfword k%2; B element (k, col) in
   // lane col*4 + (k%8)/2, word k/8, halfword k%2; this lane owns D (lane/4 [+8], 2*(lane%4) [+1]).

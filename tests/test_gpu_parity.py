@@ -58,7 +58,7 @@ def test_batch_matches_oracle_with_taps(oracle_model, model):
         frames += len(pi)
         assert np.array_equal(taps[s, :, 133].astype(int), np.array([a["silence"] for a in t]))
         gains = np.array([a["gains"] for a in t])
-        assert np.max(np.abs(taps[s, :, 42:64] - gains)) < 1e-4
+        assert np.max(np.abs(taps[s, :, 42:64] - gains)) < 5e-4  # band gains; bf16 hi+lo activations on the tensor pipe
         assert np.array_equal(taps[s, :, 130], np.array([a["pitch_gain"] for a in t], dtype=np.float32))
     print(f"pitch decision flips vs oracle: {flips}/{frames}")
     assert flips == 0, "the pitch decision chain is computed bit-exactly (ns_pipe.cuh exactness contract)"
