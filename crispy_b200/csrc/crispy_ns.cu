@@ -84,7 +84,8 @@ struct crispy_ns_model {
   ns::Model m;
 };
 
-constexpr int kSlots = 3;  // workspace slots: chunk c uses slot c % kSlots
+constexpr int kSlots = 8;    // workspace slots: chunk c uses slot c % kSlots
+constexpr int kNumKernels = 7;  // K0 highpass, K1 pitch, K2 pitchscan, K3 spectrum, K3b features, K4 rnn, K5 synthesis
 
 struct crispy_ns_batch {
   int device = 0;
@@ -100,15 +101,16 @@ struct crispy_ns_batch {
   float *d_bias = nullptr;
   float *d_state = nullptr;
   // pipeline workspace + plumbing
-  float *d_hp[kSlots] = {nullptr, nullptr, nullptr};
-  uint32_t *d_tab[kSlots] = {nullptr, nullptr, nullptr};
-  float *d_rec[kSlots] = {nullptr, nullptr, nullptr};
-  ns::cf *d_spec[kSlots] = {nullptr, nullptr, nullptr};
-  uint32_t *d_featq[kSlots] = {nullptr, nullptr, nullptr};
-  cudaStream_t s_hp = nullptr, s_an = nullptr, s_syn = nullptr;
+  float *d_hp[kSlots] = {};
+  uint32_t *d_tab[kSlots] = {};
+  float *d_rec[kSlots] = {};
+  ns::cf *d_spec[kSlots] = {};
+  uint32_t *d_featq[kSlots] = {};
+  cudaStream_t s_k[kNumKernels] = {};         // one internal stream per kernel of the pipeline
   cudaEvent_t e_start = nullptr;
-  cudaEvent_t e_hp[kSlots] = {nullptr, nullptr, nullptr}, e_an[kSlots] = {nullptr, nullptr, nullptr},
-              e_syn[kSlots] = {nullptr, nullptr, nullptr};
+  cudaEvent_t e_reset = nullptr;  // recorded by batch_reset_async; every internal stream waits for it once
+  bool reset_pending = false;
+  cudaEvent_t e_k[kSlots][kNumKernels] = {};  // "kernel k of the chunk in this slot has finished"
   // optional per-kernel timing (crispy_ns_batch_profile): CUDA events around every launch, each on
   // the stream the kernel is launched on
   bool prof_on = false;
@@ -118,8 +120,9 @@ struct crispy_ns_batch {
   };
   std::vector<ProfRec> prof;
   // host-pointer path
-  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-  cudaEvent_t e_in[2] = {nullptr, nullptr}, e_k[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t e_in[2] = {nullptr, nullptr}, e_run[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr},
+              e_k0[2] = {nullptr, nullptr};
   void *d_in[2] = {nullptr, nullptr};
   void *d_out[2] = {nullptr, nullptr};
   float *d_vad[2] = {nullptr, nullptr};
@@ -134,18 +137,17 @@ struct crispy_ns_state {
 };
 
 // ------------------------------------------------------------------------------------------------
-// launch: one call = a train of chunks, each chunk = six kernels on three internal streams
-//   s_hp : K0                (serial biquad; runs ahead of the rest)
-//   s_an : K1, K2, K3        (pitch analysis, pitch decision scan, spectra)
-//   s_syn: K4, K5            (recurrent core, synthesis)
-// Events chain hp -> an -> syn per workspace slot, so chunk c+1's analysis overlaps chunk c's
-// recurrent core and synthesis.
+// launch: one call = a train of chunks; every chunk goes through the seven kernels, each kernel on
+// its own internal stream.  Kernel k of chunk c waits for kernel k-1 of chunk c (event) and, by stream
+// order, for kernel k of chunk c-1 (the serial-in-time kernels carry per-stream state from chunk to
+// chunk).  With kSlots workspace slots the seven kernels work on up to seven different chunks at
+// once, so the latency-bound serial kernels (K0, K2, K3b, K4) hide behind the parallel ones.
 // ------------------------------------------------------------------------------------------------
 static int default_chunk_cap(int n_streams) {
   const char *env = getenv("CRISPY_NS_CHUNK_FRAMES");
   if (env && atoi(env) > 0) return atoi(env) > 4096 ? 4096 : atoi(env);
   const long long per_frame = (long long)n_streams * (ns::kFrame * 4 + ns::kTabWords * 4 + ns::kRecFloats * 4 + 2 * ns::kSpecStride * 8);
-  long long cap = (384ll << 20) / per_frame;  // ~1 GB of workspace over the three slots
+  long long cap = (384ll << 20) / per_frame;  // ~384 MB of workspace per slot
   cap = (cap / kPitchRun) * kPitchRun;
   if (cap < kPitchRun) cap = kPitchRun;
   if (cap > 256) cap = 256;
@@ -198,9 +200,21 @@ static void prof_clear(crispy_ns_batch *b) {
   b->prof.clear();
 }
 
+// Optional stream plumbing of one run_device call (host-pointer path): instead of fencing the whole
+// pipeline on the caller's stream at both ends, the first kernel waits for the input copy, the
+// output-writing kernels wait for the buffer to be drained, and completion is published as events, so
+// consecutive calls keep all seven kernels busy across the call boundary.
+struct RunHooks {
+  cudaEvent_t in_ready = nullptr;  // K0 waits for it (d_in filled)
+  cudaEvent_t out_free = nullptr;  // K4 / K5 wait for it (d_vad / d_out / d_app reusable), may be null
+  cudaEvent_t k0_done = nullptr;   // recorded after the call's last K0 (d_in may be overwritten)
+  cudaEvent_t all_done = nullptr;  // recorded after the call's last K5
+};
+
 static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad, const float *d_app,
                       float *d_taps, int n_frames, int64_t in_stride, int64_t out_stride,
-                      int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume, cudaStream_t st) {
+                      int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume, cudaStream_t st,
+                      const RunHooks *hooks = nullptr) {
   if (!b || !d_in || !d_out || n_frames < 0) return fail(CRISPY_NS_EINVAL, "process_streams: bad argument");
   if (n_frames == 0) return CRISPY_NS_OK;
   NS_CUDA(cudaSetDevice(b->device));
@@ -229,8 +243,21 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
   p.flags = flags & 0xFFu;
   p.volume = volume;
   const int n = b->n_streams;
-  NS_CUDA(cudaEventRecord(b->e_start, st));
-  NS_CUDA(cudaStreamWaitEvent(b->s_hp, b->e_start, 0));
+  const int groups = (n + ns::kMmaStreams - 1) / ns::kMmaStreams;
+  if (b->reset_pending) {  // an asynchronous reset of the per-stream state is in flight on some caller stream
+    for (int k = 0; k < kNumKernels; k++) NS_CUDA(cudaStreamWaitEvent(b->s_k[k], b->e_reset, 0));
+    b->reset_pending = false;
+  }
+  if (hooks) {
+    NS_CUDA(cudaStreamWaitEvent(b->s_k[0], hooks->in_ready, 0));
+    if (hooks->out_free) {
+      NS_CUDA(cudaStreamWaitEvent(b->s_k[kNumKernels - 2], hooks->out_free, 0));
+      NS_CUDA(cudaStreamWaitEvent(b->s_k[kNumKernels - 1], hooks->out_free, 0));
+    }
+  } else {
+    NS_CUDA(cudaEventRecord(b->e_start, st));
+    NS_CUDA(cudaStreamWaitEvent(b->s_k[0], b->e_start, 0));
+  }
   int last_slot = 0;
   for (int f0 = 0; f0 < n_frames; f0 += b->chunk_cap) {
     const int slot = (int)(b->chunks_done % kSlots);
@@ -243,51 +270,55 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
     p.spec = b->d_spec[slot];
     p.featq = b->d_featq[slot];
     p.synth_sel = (int)(b->chunks_done & 1);
-    if (b->chunks_done >= kSlots) NS_CUDA(cudaStreamWaitEvent(b->s_hp, b->e_syn[slot], 0));
-    NS_CUDA(prof_begin(b, 0, b->s_hp));
-    ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem), b->s_hp>>>(p);
-    NS_CUDA(cudaGetLastError());
-    NS_CUDA(prof_end(b, b->s_hp));
-    NS_CUDA(cudaEventRecord(b->e_hp[slot], b->s_hp));
-    NS_CUDA(cudaStreamWaitEvent(b->s_an, b->e_hp[slot], 0));
-    const int runs = (nf + kPitchRun - 1) / kPitchRun;
-    NS_CUDA(prof_begin(b, 1, b->s_an));
-    ns_pitch_kernel<<<n * runs, kPitchThreads, sizeof(ns::PitchSmem<kPitchRun>), b->s_an>>>(p);
-    NS_CUDA(cudaGetLastError());
-    NS_CUDA(prof_end(b, b->s_an));
-    NS_CUDA(prof_begin(b, 2, b->s_an));
-    ns_pitchscan_kernel<<<(n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, b->s_an>>>(p);
-    NS_CUDA(cudaGetLastError());
-    NS_CUDA(prof_end(b, b->s_an));
-    long long spec_ctas = (long long)n * nf;
-    if (spec_ctas > (long long)b->n_sms * 8) spec_ctas = (long long)b->n_sms * 8;
-    NS_CUDA(prof_begin(b, 3, b->s_an));
-    ns_spectrum_kernel<<<(int)spec_ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), b->s_an>>>(p);
-    NS_CUDA(cudaGetLastError());
-    NS_CUDA(prof_end(b, b->s_an));
-    const int groups = (n + ns::kMmaStreams - 1) / ns::kMmaStreams;
-    NS_CUDA(prof_begin(b, 4, b->s_an));
-    ns_features_kernel<<<(groups * ns::kMmaStreams + ns::kFeatWarps - 1) / ns::kFeatWarps, 32 * ns::kFeatWarps, 0, b->s_an>>>(p);
-    NS_CUDA(cudaGetLastError());
-    NS_CUDA(prof_end(b, b->s_an));
-    NS_CUDA(cudaEventRecord(b->e_an[slot], b->s_an));
-    NS_CUDA(cudaStreamWaitEvent(b->s_syn, b->e_an[slot], 0));
-    NS_CUDA(prof_begin(b, 5, b->s_syn));
-    ns_rnn_kernel<<<groups, ns::kMmaThreads, sizeof(ns::RnnSmem), b->s_syn>>>(p);
-    NS_CUDA(cudaGetLastError());
-    NS_CUDA(prof_end(b, b->s_syn));
-    NS_CUDA(prof_begin(b, 6, b->s_syn));
-    long long syn_ctas = (long long)n * ((nf + ns::kSynRun - 1) / ns::kSynRun);
-    if (syn_ctas > (long long)b->n_sms * 8) syn_ctas = (long long)b->n_sms * 8;
-    ns_synthesis_kernel<<<(int)syn_ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), b->s_syn>>>(p);
-    NS_CUDA(cudaGetLastError());
-    NS_CUDA(prof_end(b, b->s_syn));
-    NS_CUDA(cudaEventRecord(b->e_syn[slot], b->s_syn));
-    b->launches += 7;
+    // the slot's previous chunk must have left the pipeline before K0 overwrites its workspace
+    if (b->chunks_done >= kSlots) NS_CUDA(cudaStreamWaitEvent(b->s_k[0], b->e_k[slot][kNumKernels - 1], 0));
+    for (int k = 0; k < kNumKernels; k++) {
+      cudaStream_t sk = b->s_k[k];
+      if (k > 0) NS_CUDA(cudaStreamWaitEvent(sk, b->e_k[slot][k - 1], 0));
+      NS_CUDA(prof_begin(b, k, sk));
+      switch (k) {
+        case 0:
+          ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem), sk>>>(p);
+          break;
+        case 1:
+          ns_pitch_kernel<<<n * ((nf + kPitchRun - 1) / kPitchRun), kPitchThreads, sizeof(ns::PitchSmem<kPitchRun>), sk>>>(p);
+          break;
+        case 2:
+          ns_pitchscan_kernel<<<(n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, sk>>>(p);
+          break;
+        case 3: {
+          long long ctas = (long long)n * nf;
+          if (ctas > (long long)b->n_sms * 8) ctas = (long long)b->n_sms * 8;
+          ns_spectrum_kernel<<<(int)ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), sk>>>(p);
+          break;
+        }
+        case 4:
+          ns_features_kernel<<<(groups * ns::kMmaStreams + ns::kFeatWarps - 1) / ns::kFeatWarps, 32 * ns::kFeatWarps, 0, sk>>>(p);
+          break;
+        case 5:
+          ns_rnn_kernel<<<groups, ns::kMmaThreads, sizeof(ns::RnnSmem), sk>>>(p);
+          break;
+        default: {
+          long long ctas = (long long)n * ((nf + ns::kSynRun - 1) / ns::kSynRun);
+          if (ctas > (long long)b->n_sms * 8) ctas = (long long)b->n_sms * 8;
+          ns_synthesis_kernel<<<(int)ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), sk>>>(p);
+          break;
+        }
+      }
+      NS_CUDA(cudaGetLastError());
+      NS_CUDA(prof_end(b, sk));
+      NS_CUDA(cudaEventRecord(b->e_k[slot][k], sk));
+    }
+    b->launches += kNumKernels;
     b->chunks_done += 1;
     last_slot = slot;
   }
-  NS_CUDA(cudaStreamWaitEvent(st, b->e_syn[last_slot], 0));
+  if (hooks) {
+    NS_CUDA(cudaEventRecord(hooks->k0_done, b->s_k[0]));
+    NS_CUDA(cudaEventRecord(hooks->all_done, b->s_k[kNumKernels - 1]));
+  } else {
+    NS_CUDA(cudaStreamWaitEvent(st, b->e_k[last_slot][kNumKernels - 1], 0));
+  }
   b->frames_done += n_frames;
   return CRISPY_NS_OK;
 }
@@ -371,25 +402,24 @@ void crispy_ns_batch_destroy(crispy_ns_batch *b) {
     cudaFree(b->d_rec[i]);
     cudaFree(b->d_spec[i]);
     cudaFree(b->d_featq[i]);
-    if (b->e_hp[i]) cudaEventDestroy(b->e_hp[i]);
-    if (b->e_an[i]) cudaEventDestroy(b->e_an[i]);
-    if (b->e_syn[i]) cudaEventDestroy(b->e_syn[i]);
+    for (int k = 0; k < kNumKernels; k++)
+      if (b->e_k[i][k]) cudaEventDestroy(b->e_k[i][k]);
   }
   if (b->e_start) cudaEventDestroy(b->e_start);
-  if (b->s_hp) cudaStreamDestroy(b->s_hp);
-  if (b->s_an) cudaStreamDestroy(b->s_an);
-  if (b->s_syn) cudaStreamDestroy(b->s_syn);
+  if (b->e_reset) cudaEventDestroy(b->e_reset);
+  for (int k = 0; k < kNumKernels; k++)
+    if (b->s_k[k]) cudaStreamDestroy(b->s_k[k]);
   for (int i = 0; i < 2; i++) {
     cudaFree(b->d_in[i]);
     cudaFree(b->d_out[i]);
     cudaFree(b->d_vad[i]);
     cudaFree(b->d_app[i]);
     if (b->e_in[i]) cudaEventDestroy(b->e_in[i]);
-    if (b->e_k[i]) cudaEventDestroy(b->e_k[i]);
+    if (b->e_run[i]) cudaEventDestroy(b->e_run[i]);
     if (b->e_out[i]) cudaEventDestroy(b->e_out[i]);
+    if (b->e_k0[i]) cudaEventDestroy(b->e_k0[i]);
   }
   if (b->s_in) cudaStreamDestroy(b->s_in);
-  if (b->s_k) cudaStreamDestroy(b->s_k);
   if (b->s_out) cudaStreamDestroy(b->s_out);
   delete b;
 }
@@ -443,14 +473,17 @@ int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_strea
     if (e == cudaSuccess)
       e = cudaMalloc((void **)&b->d_featq[i], (size_t)((n_streams + ns::kMmaStreams - 1) / ns::kMmaStreams) * b->chunk_cap *
                                                   ns::kFeatBlockWords * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_hp[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_an[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_syn[i], cudaEventDisableTiming);
+    for (int k = 0; k < kNumKernels && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&b->e_k[i][k], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_start, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->s_hp, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->s_an, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->s_syn, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->e_reset, cudaEventDisableTiming);
+  {  // the serial-in-time kernels (few warps, latency bound) get the higher block-scheduling priority
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    static const bool serial[kNumKernels] = {true, false, true, false, true, true, false};
+    for (int k = 0; k < kNumKernels && e == cudaSuccess; k++)
+      e = cudaStreamCreateWithPriority(&b->s_k[k], cudaStreamNonBlocking, serial[k] ? prio_hi : prio_lo);
+  }
   if (e != cudaSuccess) {
     crispy_ns_batch_destroy(b);
     return fail(CRISPY_NS_ECUDA, std::string("batch_create: ") + cudaGetErrorString(e));
@@ -471,6 +504,8 @@ int crispy_ns_batch_reset_async(crispy_ns_batch *b, void *cuda_stream) {
   if (!b) return fail(CRISPY_NS_EINVAL, "batch_reset_async: null handle");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(cudaMemsetAsync(b->d_state, 0, (size_t)b->n_streams * ns::kStateFloats * sizeof(float), (cudaStream_t)cuda_stream));
+  NS_CUDA(cudaEventRecord(b->e_reset, (cudaStream_t)cuda_stream));
+  b->reset_pending = true;
   b->frames_done = 0;
   return CRISPY_NS_OK;
 }
@@ -500,19 +535,19 @@ int crispy_ns_process_streams_host(crispy_ns_batch *b, const void *h_in, void *h
   NS_CUDA(cudaSetDevice(b->device));
   if (!b->s_in) {
     NS_CUDA(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
-    NS_CUDA(cudaStreamCreateWithFlags(&b->s_k, cudaStreamNonBlocking));
     NS_CUDA(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
       NS_CUDA(cudaEventCreateWithFlags(&b->e_in[i], cudaEventDisableTiming));
-      NS_CUDA(cudaEventCreateWithFlags(&b->e_k[i], cudaEventDisableTiming));
+      NS_CUDA(cudaEventCreateWithFlags(&b->e_run[i], cudaEventDisableTiming));
       NS_CUDA(cudaEventCreateWithFlags(&b->e_out[i], cudaEventDisableTiming));
+      NS_CUDA(cudaEventCreateWithFlags(&b->e_k0[i], cudaEventDisableTiming));
     }
   }
   const size_t ie = in_elem(flags), oe = out_elem(flags);
   const int n = b->n_streams;
-  // chunk length in frames: ~64 MiB of input per chunk, at least 8 chunks when the job is long
-  long long ch = (64ll << 20) / ((long long)n * ns::kFrame * (long long)ie);
-  if (ch < 1) ch = 1;
+  // host chunk length in frames: a whole number of engine chunks, ~128 MiB of input per buffer
+  long long ch = (128ll << 20) / ((long long)n * ns::kFrame * (long long)ie) / b->chunk_cap * b->chunk_cap;
+  if (ch < b->chunk_cap) ch = b->chunk_cap;
   if (ch > n_frames) ch = n_frames;
   const char *env = getenv("CRISPY_NS_HOST_CHUNK_FRAMES");
   if (env && atoi(env) > 0) ch = atoi(env) < n_frames ? atoi(env) : n_frames;
@@ -562,10 +597,11 @@ int crispy_ns_process_streams_host(crispy_ns_batch *b, const void *h_in, void *h
   for (long long f0 = 0; f0 < n_frames; f0 += ch, c++) {
     const int k = c & 1;
     const long long nf = (f0 + ch <= n_frames) ? ch : (n_frames - f0);
-    // the in buffer k was last read by kernel c-2; the out buffer k was last drained by copy c-2
+    // the in buffer k was last read by the biquad of host chunk c-2; the out buffer k was last
+    // drained by copy c-2 (the output-writing kernels wait for that through the hooks)
     if (c >= 2) {
-      NS_CUDA(cudaStreamWaitEvent(b->s_in, b->e_k[k], 0));
-      NS_CUDA(cudaStreamWaitEvent(b->s_k, b->e_out[k], 0));
+      NS_CUDA(cudaStreamWaitEvent(b->s_in, b->e_k0[k], 0));
+      if (use_app) NS_CUDA(cudaStreamWaitEvent(b->s_in, b->e_run[k], 0));  // K5 of host chunk c-2 read d_app[k]
     }
     const long long row = nf * ns::kFrame;
     NS_CUDA(cudaMemcpy2DAsync(b->d_in[k], (size_t)row * ie, (const char *)h_in + (size_t)f0 * ns::kFrame * ie,
@@ -579,13 +615,16 @@ int crispy_ns_process_streams_host(crispy_ns_batch *b, const void *h_in, void *h
                                 (size_t)app_stride * 4, (size_t)nf_out * ns::kFrame * 4, n,
                                 cudaMemcpyHostToDevice, b->s_in));
     NS_CUDA(cudaEventRecord(b->e_in[k], b->s_in));
-    NS_CUDA(cudaStreamWaitEvent(b->s_k, b->e_in[k], 0));
+    RunHooks hooks;
+    hooks.in_ready = b->e_in[k];
+    hooks.out_free = (c >= 2) ? b->e_out[k] : nullptr;
+    hooks.k0_done = b->e_k0[k];
+    hooks.all_done = b->e_run[k];
     const int rc = run_device(b, b->d_in[k], b->d_out[k], h_vad ? b->d_vad[k] : nullptr,
                               use_app ? b->d_app[k] : nullptr, nullptr, (int)nf, row, row, nf, row, flags,
-                              volume, b->s_k);
+                              volume, nullptr, &hooks);
     if (rc != CRISPY_NS_OK) return rc;
-    NS_CUDA(cudaEventRecord(b->e_k[k], b->s_k));
-    NS_CUDA(cudaStreamWaitEvent(b->s_out, b->e_k[k], 0));
+    NS_CUDA(cudaStreamWaitEvent(b->s_out, b->e_run[k], 0));
     if (nf_out > 0)
       NS_CUDA(cudaMemcpy2DAsync((char *)h_out + (size_t)out_f0 * ns::kFrame * oe, (size_t)out_stride * oe,
                                 b->d_out[k], (size_t)row * oe, (size_t)nf_out * ns::kFrame * oe, n,
@@ -596,7 +635,6 @@ int crispy_ns_process_streams_host(crispy_ns_batch *b, const void *h_in, void *h
     NS_CUDA(cudaEventRecord(b->e_out[k], b->s_out));
   }
   NS_CUDA(cudaStreamSynchronize(b->s_out));
-  NS_CUDA(cudaStreamSynchronize(b->s_k));
   NS_CUDA(cudaStreamSynchronize(b->s_in));
   return CRISPY_NS_OK;
 }
@@ -638,7 +676,6 @@ int crispy_ns_batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_
   return CRISPY_NS_OK;
 }
 
-constexpr int kNumKernels = 7;
 int crispy_ns_kernel_count(void) { return kNumKernels; }
 const char *crispy_ns_kernel_name(int k) {
   static const char *names[kNumKernels] = {"ns_highpass_kernel", "ns_pitch_kernel",    "ns_pitchscan_kernel", "ns_spectrum_kernel",

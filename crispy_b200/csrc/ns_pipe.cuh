@@ -261,6 +261,34 @@ NS_DEV int rd_T1b(int k, int T0, int T1) {
 }
 NS_DEV float pitch_gain_f(float xy, float xx, float yy) { return xy / sqrtf(1.f + xx * yy); }
 
+// sum_{j<480} x[j] * y[j] with x = row + 384 and y = row + yoff, accumulated in ascending j as a rounded
+// product followed by a rounded add (the oracle's order).  y has arbitrary alignment: the lane walks
+// 16-byte aligned float4s and shifts a two-vector window in registers, so one LDS.128 feeds four
+// taps (scalar loads of y cost ~3.5 shared-memory wavefronts per tap from bank conflicts between
+// lanes with different lags; shared-memory bandwidth is what bounds this kernel).  Reads up to 3
+// floats before y[0] and 4 past y[479]: inside the row's padding / the neighbouring rows.
+NS_DEV float dot480_shifted(const float *row, int yoff) {
+  const float *x = row + 384;
+  const float *ya = row + (yoff & ~3);
+  const bool p1 = (yoff & 1) != 0, p2 = (yoff & 2) != 0;
+  f4 lo = ld4(ya);
+  float sum = 0.f;
+#pragma unroll 2
+  for (int j = 0; j < 480; j += 4) {
+    const f4 hi = ld4(ya + j + 4);
+    const f4 xv = ld4(x + j);
+    const float a0 = p1 ? lo.y : lo.x, a1 = p1 ? lo.z : lo.y, a2 = p1 ? lo.w : lo.z, a3 = p1 ? hi.x : lo.w,
+                a4 = p1 ? hi.y : hi.x, a5 = p1 ? hi.z : hi.y;
+    const float y0 = p2 ? a2 : a0, y1 = p2 ? a3 : a1, y2 = p2 ? a4 : a2, y3 = p2 ? a5 : a3;
+    sum += xv.x * y0;
+    sum += xv.y * y1;
+    sum += xv.z * y2;
+    sum += xv.w * y3;
+    lo = hi;
+  }
+  return sum;
+}
+
 template <int R, int NT>
 NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   const int tid = Simt::tid();
@@ -409,10 +437,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     const int dd = i - c0;
     const bool ok = (i >= 0) && (i < 294) && (c < 5 || dd > 2 || dd < -2);
     float sum = 0.f;
-    if (ok) {
-      const float *x = lp + 384, *y = lp + i;
-      for (int j = 0; j < 480; j++) sum += x[j] * y[j];
-    }
+    if (ok) sum = dot480_shifted(lp, i);
     sm.fi[f][c] = ok ? i : -1;
     sm.fx[f][c] = sum < -1.f ? -1.f : sum;
   }
@@ -462,10 +487,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   // P9: a11 remove_doubling: xx and xy(T0) (dual_inner_prod), then the candidate work list
   for (int it = tid; it < nfr * 2; it += NT) {
     const int f = it >> 1;
-    const float *x = sm.xlp + f * kLpStride + 384;
-    const float *y = (it & 1) ? x - sm.T0[f] : x;
-    float sum = 0.f;
-    for (int j = 0; j < 480; j++) sum += x[j] * y[j];
+    const float sum = dot480_shifted(sm.xlp + f * kLpStride, (it & 1) ? 384 - sm.T0[f] : 384);
     if (it & 1)
       sm.xy0[f] = sum;
     else
@@ -512,11 +534,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     for (int it = tid; it < n; it += NT) {
       const int e = sm.task[it];
       const int f = e & 15, lag = (e >> 4) & 0xFFF, dst = e >> 16;
-      const float *x = sm.xlp + f * kLpStride + 384;
-      const float *y = x - lag;
-      float sum = 0.f;
-      for (int j = 0; j < 480; j++) sum += x[j] * y[j];
-      sm.dots[f][dst] = sum;
+      sm.dots[f][dst] = dot480_shifted(sm.xlp + f * kLpStride, 384 - lag);
     }
   }
   Simt::cta_sync();
