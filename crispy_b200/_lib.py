@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcrispy_ns.so")
+# $CRISPY_NS_LIB selects another build of the same library (kernel tuning experiments, scripts/variants.sh)
+LIB_PATH = os.environ.get("CRISPY_NS_LIB") or os.path.join(HERE, "libcrispy_ns.so")
 
 # flags (include/crispy_ns.h)
 IN_I16 = 1 << 0

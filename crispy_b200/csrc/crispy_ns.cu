@@ -17,8 +17,11 @@
 // ------------------------------------------------------------------------------------------------
 // kernels (bodies in ns_pipe.cuh)
 // ------------------------------------------------------------------------------------------------
-constexpr int kPitchRun = 8;        // frames of one stream per pitch CTA
-constexpr int kPitchThreads = 320;  // 37 lag-quads x 8 frames = 296 lanes in the coarse search
+#ifndef NS_PITCH_RUN
+#define NS_PITCH_RUN 8
+#endif
+constexpr int kPitchRun = NS_PITCH_RUN;  // frames of one stream per pitch CTA
+constexpr int kPitchThreads = (37 * kPitchRun + 31) / 32 * 32;  // 37 lag-quads per frame in the coarse search
 constexpr int kScanWarps = 4;
 
 __global__ void __launch_bounds__(ns::kHpThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {

@@ -261,20 +261,21 @@ NS_DEV int rd_T1b(int k, int T0, int T1) {
 }
 NS_DEV float pitch_gain_f(float xy, float xx, float yy) { return xy / sqrtf(1.f + xx * yy); }
 
-// sum_{j<480} x[j] * y[j] with x = row + 384 and y = row + yoff, accumulated in ascending j as a rounded
-// product followed by a rounded add (the oracle's order).  y has arbitrary alignment: the lane walks
-// 16-byte aligned float4s and shifts a two-vector window in registers, so one LDS.128 feeds four
-// taps (scalar loads of y cost ~3.5 shared-memory wavefronts per tap from bank conflicts between
-// lanes with different lags; shared-memory bandwidth is what bounds this kernel).  Reads up to 3
-// floats before y[0] and 4 past y[479]: inside the row's padding / the neighbouring rows.
-NS_DEV float dot480_shifted(const float *row, int yoff) {
-  const float *x = row + 384;
-  const float *ya = row + (yoff & ~3);
+// sum_{j<N} x[j] * y[j] with y = yrow + yoff, accumulated in ascending j as a rounded product followed
+// by a rounded add (the oracle's order).  x and yrow are 16-byte aligned, y has arbitrary alignment:
+// the lane walks aligned float4s and shifts a two-vector window in registers, so one LDS.128 feeds
+// four taps and the only serial dependency is the chain of adds (a scalar loop pays the ~29-cycle
+// shared-memory latency on every tap and ~3.5 bank-conflict wavefronts between lanes with different
+// lags).  Reads up to 3 floats before y[0] and 4 past y[N-1]: row padding / neighbouring rows.
+template <int N>
+NS_DEV float dot_shifted(const float *x, const float *yrow, int yoff) {
+  static_assert(N % 4 == 0, "whole float4s");
+  const float *ya = yrow + (yoff & ~3);
   const bool p1 = (yoff & 1) != 0, p2 = (yoff & 2) != 0;
   f4 lo = ld4(ya);
   float sum = 0.f;
 #pragma unroll 2
-  for (int j = 0; j < 480; j += 4) {
+  for (int j = 0; j < N; j += 4) {
     const f4 hi = ld4(ya + j + 4);
     const f4 xv = ld4(x + j);
     const float a0 = p1 ? lo.y : lo.x, a1 = p1 ? lo.z : lo.y, a2 = p1 ? lo.w : lo.z, a3 = p1 ? hi.x : lo.w,
@@ -287,6 +288,22 @@ NS_DEV float dot480_shifted(const float *row, int yoff) {
     lo = hi;
   }
   return sum;
+}
+NS_DEV float dot480_shifted(const float *row, int yoff) { return dot_shifted<480>(row + 384, row, yoff); }
+
+// acc + sum_{j<N} y[j]^2 in ascending j (y 16-byte aligned), loads batched four taps at a time
+template <int N>
+NS_DEV float sumsq_from(float acc, const float *y) {
+  static_assert(N % 4 == 0, "whole float4s");
+#pragma unroll 4
+  for (int j = 0; j < N; j += 4) {
+    const f4 v = ld4(y + j);
+    acc += v.x * v.x;
+    acc += v.y * v.y;
+    acc += v.z * v.z;
+    acc += v.w * v.w;
+  }
+  return acc;
 }
 
 template <int R, int NT>
@@ -323,8 +340,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   for (int it = tid; it < nfr * 5; it += NT) {
     const int f = it / 5, k = it - f * 5;
     const float *x = sm.xr + f * kLpStride;
-    float sum = 0.f;
-    for (int j = 0; j < kLpLen - 4; j++) sum += x[j] * x[j + k];
+    const float sum = dot_shifted<kLpLen - 4>(x, x, k);
     float d = 0.f;
     for (int i = k + kLpLen - 4; i < kLpLen; i++) d += x[i] * x[i - k];
     sm.ac[f][k] = sum + d;
@@ -413,16 +429,23 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     const float *y4 = sm.xr + f * kLpStride;
     Best2 b;
     best_init(b);
-    float syy = 1.f;
-    for (int j = 0; j < 240; j++) syy += y4[j] * y4[j];
-    for (int i = 0; i < 147; i++) {
-      const float xc = sm.xc[f][i];
-      if (xc > 0.f) {
-        const float x16 = xc * 1e-12f;
-        best_insert(b, x16 * x16, syy, i);
+    float syy = sumsq_from<240>(1.f, y4);
+    for (int i0 = 0; i0 < 147; i0 += 4) {  // four lags per trip: the loads are off the running sum's chain
+      const f4 xc4 = ld4(sm.xc[f] + i0), ya = ld4(y4 + i0 + 240), yb = ld4(y4 + i0);
+      const float xcv[4] = {xc4.x, xc4.y, xc4.z, xc4.w};
+      const float dl[4] = {ya.x * ya.x - yb.x * yb.x, ya.y * ya.y - yb.y * yb.y, ya.z * ya.z - yb.z * yb.z,
+                           ya.w * ya.w - yb.w * yb.w};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (i0 + u < 147) {
+          if (xcv[u] > 0.f) {
+            const float x16 = xcv[u] * 1e-12f;
+            best_insert(b, x16 * x16, syy, i0 + u);
+          }
+          syy += dl[u];
+          syy = syy < 1.f ? 1.f : syy;
+        }
       }
-      syy += y4[i + 240] * y4[i + 240] - y4[i] * y4[i];
-      syy = syy < 1.f ? 1.f : syy;
     }
     sm.best0[f] = b.p0;
     sm.best1[f] = b.p1;
@@ -455,19 +478,30 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     };
     Best2 b;
     best_init(b);
-    float syy = 1.f;
-    for (int j = 0; j < 480; j++) syy += y[j] * y[j];
-    for (int i = 0; i < 294; i++) {
-      const int d0 = i - lo0, d1 = i - lo1;
-      if ((d0 >= 0 && d0 < 5) || (d1 >= 0 && d1 < 5)) {
-        const float xc = xcorr_at(i);
-        if (xc > 0.f) {
-          const float x16 = xc * 1e-12f;
-          best_insert(b, x16 * x16, syy, i);
+    float syy = sumsq_from<480>(1.f, y);
+    // the running Syy only matters up to the last candidate lag; four lags per trip, loads off the chain
+    int iend = (lo0 > lo1 ? lo0 : lo1) + 5;
+    if (iend > 294) iend = 294;
+    for (int i0 = 0; i0 < iend; i0 += 4) {
+      const f4 ya = ld4(y + i0 + 480), yb = ld4(y + i0);
+      const float dl[4] = {ya.x * ya.x - yb.x * yb.x, ya.y * ya.y - yb.y * yb.y, ya.z * ya.z - yb.z * yb.z,
+                           ya.w * ya.w - yb.w * yb.w};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u;
+        if (i < iend) {
+          const int d0 = i - lo0, d1 = i - lo1;
+          if ((d0 >= 0 && d0 < 5) || (d1 >= 0 && d1 < 5)) {
+            const float xc = xcorr_at(i);
+            if (xc > 0.f) {
+              const float x16 = xc * 1e-12f;
+              best_insert(b, x16 * x16, syy, i);
+            }
+          }
+          syy += dl[u];
+          syy = syy < 1.f ? 1.f : syy;
         }
       }
-      syy += y[i + 480] * y[i + 480] - y[i] * y[i];
-      syy = syy < 1.f ? 1.f : syy;
     }
     const int bp = b.p0;
     int offset = 0;
@@ -501,9 +535,15 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     float *yyl = sm.xr + f * kLpStride + 432;  // yy_lookup[0..384]
     float yy = sm.xx[f];
     yyl[0] = yy;
-    for (int i = 1; i <= 384; i++) {
-      yy = yy + x[-i] * x[-i] - x[480 - i] * x[480 - i];
-      yyl[i] = yy < 0.f ? 0.f : yy;
+    for (int i0 = 1; i0 <= 384; i0 += 4) {  // lags i0..i0+3: x[-i] and x[480-i] come as two aligned float4s
+      const f4 a = ld4(x - i0 - 3), c = ld4(x + 477 - i0);
+      const float av[4] = {a.w * a.w, a.z * a.z, a.y * a.y, a.x * a.x};
+      const float cv[4] = {c.w * c.w, c.z * c.z, c.y * c.y, c.x * c.x};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        yy = yy + av[u] - cv[u];
+        yyl[i0 + u] = yy < 0.f ? 0.f : yy;
+      }
     }
     const int T0 = sm.T0[f];
     int nk = 1;
@@ -740,6 +780,21 @@ struct Dft<6> {
   }
 };
 
+// Stockham scatter of one butterfly's outputs; the first stage writes R consecutive bins per thread
+// and uses 16-byte stores (the 8-byte scatter is 4-way bank conflicted there)
+template <int R, int NS_>
+NS_DEV void fft_store(cf *buf, int j, int k, const cf (&v)[R]) {
+  const int j0 = (j - k) * R + k;
+  if (NS_ == 1 && (R & 1) == 0) {
+    f4 *d = reinterpret_cast<f4 *>(buf + j0);
+#pragma unroll
+    for (int r = 0; r < R; r += 2) d[r >> 1] = f4{v[r].x, v[r].y, v[r + 1].x, v[r + 1].y};
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; r++) buf[j0 + r * NS_] = v[r];
+  }
+}
+
 template <int R, int NS_, class Load>
 NS_DEV void fft_stage(const Grp &g, const Tables &T, cf *buf, Load load) {
   constexpr int M = 480 / R;
@@ -759,10 +814,38 @@ NS_DEV void fft_stage(const Grp &g, const Tables &T, cf *buf, Load load) {
     Dft<R>::run(v);
   }
   gsync(g);
+  if (act) fft_store<R, NS_>(buf, j, k, v);
+  gsync(g);
+}
+
+// two independent transforms side by side (same twiddles, same barriers): K3's frame and pitch-lag spectra
+template <int R, int NS_, class Load2>
+NS_DEV void fft_stage2(const Grp &g, const Tables &T, cf *bufA, cf *bufB, Load2 load2) {
+  constexpr int M = 480 / R;
+  constexpr int TSTEP = 480 / (NS_ * R);
+  cf va[R], vb[R];
+  const int j = g.tid;
+  const bool act = j < M;
+  int k = 0;
   if (act) {
-    const int j0 = (j - k) * R + k;
+    k = j % NS_;
+    load2(j, va[0], vb[0]);
 #pragma unroll
-    for (int r = 0; r < R; r++) buf[j0 + r * NS_] = v[r];
+    for (int r = 1; r < R; r++) {
+      load2(j + r * M, va[r], vb[r]);
+      if (NS_ != 1) {
+        const cf w = T.w480[r * k * TSTEP];
+        va[r] = cmul(va[r], w);
+        vb[r] = cmul(vb[r], w);
+      }
+    }
+    Dft<R>::run(va);
+    Dft<R>::run(vb);
+  }
+  gsync(g);
+  if (act) {
+    fft_store<R, NS_>(bufA, j, k, va);
+    fft_store<R, NS_>(bufB, j, k, vb);
   }
   gsync(g);
 }
@@ -793,6 +876,42 @@ NS_DEV void rfft960_windowed(const Grp &g, const Tables &T, const float *__restr
     const float tr = fmaf(orr, w.x, -(oi * w.y)), ti = fmaf(orr, w.y, oi * w.x);
     X[k] = cf{(er + ti) * norm, (ei - tr) * norm};
     X[480 - k] = cf{(er - ti) * norm, (-ei - tr) * norm};
+  }
+  gsync(g);
+}
+
+// the same for two windows at once (X of the frame, P of the pitch-lagged window): shared window,
+// twiddle and barrier traffic
+NS_DEV void rfft960_windowed2(const Grp &g, const Tables &T, const float *__restrict__ srcA, const float *__restrict__ srcB,
+                              cf *XA, cf *XB) {
+  auto load = [&](int n, cf &a, cf &b) {
+    const int i0 = 2 * n;
+    const float w0 = (i0 < kFrame) ? T.win[i0] : T.win[kWindow - 1 - i0];
+    const float w1 = (i0 + 1 < kFrame) ? T.win[i0 + 1] : T.win[kWindow - 2 - i0];
+    a = cf{srcA[i0] * w0, srcA[i0 + 1] * w1};
+    b = cf{srcB[i0] * w0, srcB[i0 + 1] * w1};
+  };
+  auto from_buf = [&](int n, cf &a, cf &b) {
+    a = XA[n];
+    b = XB[n];
+  };
+  fft_stage2<4, 1>(g, T, XA, XB, load);
+  fft_stage2<4, 4>(g, T, XA, XB, from_buf);
+  fft_stage2<5, 16>(g, T, XA, XB, from_buf);
+  fft_stage2<6, 80>(g, T, XA, XB, from_buf);
+  const float norm = 1.0f / kWindow;
+  for (int k = g.tid; k <= 240; k += kGroupThreads) {
+    const cf w = T.w960[k];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      cf *X = q ? XB : XA;
+      const cf a = X[k], b = X[k == 0 ? 0 : 480 - k];
+      const float er = .5f * (a.x + b.x), ei = .5f * (a.y - b.y);
+      const float orr = .5f * (a.x - b.x), oi = .5f * (a.y + b.y);
+      const float tr = fmaf(orr, w.x, -(oi * w.y)), ti = fmaf(orr, w.y, oi * w.x);
+      X[k] = cf{(er + ti) * norm, (ei - tr) * norm};
+      X[480 - k] = cf{(er - ti) * norm, (-ei - tr) * norm};
+    }
   }
   gsync(g);
 }
@@ -860,8 +979,7 @@ NS_DEV void load_tables(const Params &p, Tables &dst, int tid, int nthr) {
 // spectra of frame t: X of [prev | cur], P of the window lagged by pitch_index, Ex / Ep / raw Exp
 NS_DEV void frame_spectra(const Grp &g, const Tables &T, SpecSmem &s, const float *hp_row, int t, int pitch_index) {
   const float *cur = hp_row + kHist - kFrame + (long long)t * kFrame;  // [analysis_mem | frame]
-  rfft960_windowed(g, T, cur, s.X);
-  rfft960_windowed(g, T, cur - pitch_index, s.P);
+  rfft960_windowed2(g, T, cur, cur - pitch_index, s.X, s.P);
   float acc[3];
   band_accumulate<3>(g, T, [&](int k, float (&v)[3]) {
     const cf x = s.X[k], p = s.P[k];
