@@ -21,7 +21,7 @@
 #define NS_PITCH_RUN 8
 #endif
 constexpr int kPitchRun = NS_PITCH_RUN;  // frames of one stream per pitch CTA
-constexpr int kPitchThreads = (37 * kPitchRun + 31) / 32 * 32;  // 37 lag-quads per frame in the coarse search
+constexpr int kPitchThreads = (37 * kPitchRun + 31) / 32 * 32 + 32;  // 37 lag-quads per frame in the coarse search + one helper warp
 constexpr int kScanWarps = 4;
 
 __global__ void __launch_bounds__(ns::kHpThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
@@ -35,7 +35,13 @@ __global__ void __launch_bounds__(kPitchThreads) ns_pitch_kernel(const __grid_co
 __global__ void __launch_bounds__(32 * kScanWarps) ns_pitchscan_kernel(const __grid_constant__ ns::Params p) {
   ns::pitchscan_body(p, kScanWarps);
 }
-__global__ void __launch_bounds__(ns::kGroupThreads) ns_spectrum_kernel(const __grid_constant__ ns::Params p) {
+#ifndef NS_SPEC_MINB
+#define NS_SPEC_MINB 8  // as NS_SYN_MINB: one resident wave of 8 CTAs per SM
+#endif
+#ifndef NS_SYN_MINB
+#define NS_SYN_MINB 8  // measured on B200: 64 registers + 168 B of spill beat 4 resident CTAs at 119 registers
+#endif
+__global__ void __launch_bounds__(ns::kGroupThreads, NS_SPEC_MINB) ns_spectrum_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ns::spectrum_body(p, *reinterpret_cast<ns::SpecSmem *>(smem_raw));
 }
@@ -47,7 +53,7 @@ __global__ void __launch_bounds__(ns::kMmaThreads, 1) ns_rnn_kernel(const __grid
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ns::rnn_body(p, *reinterpret_cast<ns::RnnSmem *>(smem_raw));
 }
-__global__ void __launch_bounds__(ns::kGroupThreads) ns_synthesis_kernel(const __grid_constant__ ns::Params p) {
+__global__ void __launch_bounds__(ns::kGroupThreads, NS_SYN_MINB) ns_synthesis_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ns::synthesis_body(p, *reinterpret_cast<ns::SpecSmem *>(smem_raw));
 }
@@ -94,6 +100,7 @@ struct crispy_ns_batch {
   int device = 0;
   int n_streams = 0;
   int n_sms = 148;
+  int spec_ctas_per_sm = 4, syn_ctas_per_sm = 4;  // resident CTAs of the two persistent task-loop kernels
   int chunk_cap = 0;  // frames per chunk
   int64_t launches = 0;
   int64_t frames_done = 0;
@@ -290,8 +297,8 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
           ns_pitchscan_kernel<<<(n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, sk>>>(p);
           break;
         case 3: {
-          long long ctas = (long long)n * nf;
-          if (ctas > (long long)b->n_sms * 8) ctas = (long long)b->n_sms * 8;
+          long long ctas = (long long)n * nf;  // persistent task loop: exactly one resident wave
+          if (ctas > (long long)b->n_sms * b->spec_ctas_per_sm) ctas = (long long)b->n_sms * b->spec_ctas_per_sm;
           ns_spectrum_kernel<<<(int)ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), sk>>>(p);
           break;
         }
@@ -303,7 +310,7 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
           break;
         default: {
           long long ctas = (long long)n * ((nf + ns::kSynRun - 1) / ns::kSynRun);
-          if (ctas > (long long)b->n_sms * 8) ctas = (long long)b->n_sms * 8;
+          if (ctas > (long long)b->n_sms * b->syn_ctas_per_sm) ctas = (long long)b->n_sms * b->syn_ctas_per_sm;
           ns_synthesis_kernel<<<(int)ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), sk>>>(p);
           break;
         }
@@ -450,6 +457,19 @@ int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_strea
   b->n_streams = n_streams;
   b->n_sms = prop.multiProcessorCount;
   b->chunk_cap = default_chunk_cap(n_streams);
+  if (cudaError_t ce = configure_kernels(device); ce != cudaSuccess) {
+    delete b;
+    return fail(CRISPY_NS_ECUDA, std::string("batch_create: ") + cudaGetErrorString(ce));
+  }
+  {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ns_spectrum_kernel, ns::kGroupThreads, sizeof(ns::SpecSmem)) == cudaSuccess && occ > 0)
+      b->spec_ctas_per_sm = occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ns_synthesis_kernel, ns::kGroupThreads, sizeof(ns::SpecSmem)) == cudaSuccess && occ > 0)
+      b->syn_ctas_per_sm = occ;
+    if (getenv("CRISPY_NS_SPEC_CTAS") && atoi(getenv("CRISPY_NS_SPEC_CTAS")) > 0) b->spec_ctas_per_sm = atoi(getenv("CRISPY_NS_SPEC_CTAS"));
+    if (getenv("CRISPY_NS_SYN_CTAS") && atoi(getenv("CRISPY_NS_SYN_CTAS")) > 0) b->syn_ctas_per_sm = atoi(getenv("CRISPY_NS_SYN_CTAS"));
+  }
   ns::PackedRnn pk;
   ns::pack_rnn(*m, pk);
   static ns::Tables tab;

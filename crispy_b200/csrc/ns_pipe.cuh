@@ -220,6 +220,7 @@ struct PitchSmem {
   float fx[R][12];
   int fi[R][12];
   float xx[R], xy0[R];
+  float syy6[R], syy8[R];  // 1 + sum of squares the two find_best_pitch passes start from
   int best0[R], best1[R], T0[R], nk[R];
   int n_tasks;
   int task[R * 64];    // frame | lag << 4 | dst << 16
@@ -251,6 +252,18 @@ NS_DEV void best_insert(Best2 &b, float num, float syy, int i) {  // pitch.c fin
       b.p1 = i;
     }
   }
+}
+
+// the same update without branches (the serial search lanes run it on every lag): `valid` gates it
+NS_DEV void best_insert_sel(Best2 &b, bool valid, float num, float syy, int i) {
+  const bool c1 = valid && (num * b.d1 > b.n1 * syy);
+  const bool c0 = c1 && (num * b.d0 > b.n0 * syy);
+  b.n1 = c0 ? b.n0 : (c1 ? num : b.n1);
+  b.d1 = c0 ? b.d0 : (c1 ? syy : b.d1);
+  b.p1 = c0 ? b.p0 : (c1 ? i : b.p1);
+  b.n0 = c0 ? num : b.n0;
+  b.d0 = c0 ? syy : b.d0;
+  b.p0 = c0 ? i : b.p0;
 }
 
 NS_DEV int rd_T1(int k, int T0) { return (2 * T0 + k) / (2 * k); }
@@ -285,6 +298,24 @@ NS_DEV float dot_shifted(const float *x, const float *yrow, int yoff) {
     sum += xv.y * y1;
     sum += xv.z * y2;
     sum += xv.w * y3;
+    lo = hi;
+  }
+  return sum;
+}
+// the same with the shift S = (y - ya) known at compile time: no selects (used where a whole warp shares it)
+template <int N, int S>
+NS_DEV float dot_fixed_shift(const float *x, const float *ya) {
+  f4 lo = ld4(ya);
+  float sum = 0.f;
+#pragma unroll 2
+  for (int j = 0; j < N; j += 4) {
+    const f4 hi = ld4(ya + j + 4);
+    const f4 xv = ld4(x + j);
+    const float w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    sum += xv.x * w[S];
+    sum += xv.y * w[S + 1];
+    sum += xv.z * w[S + 2];
+    sum += xv.w * w[S + 3];
     lo = hi;
   }
   return sum;
@@ -336,14 +367,33 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     sm.xr[f * kLpStride + i] = v;
   }
   Simt::cta_sync();
-  // P2: _celt_autocorr, lags 0..4
-  for (int it = tid; it < nfr * 5; it += NT) {
-    const int f = it / 5, k = it - f * 5;
-    const float *x = sm.xr + f * kLpStride;
-    const float sum = dot_shifted<kLpLen - 4>(x, x, k);
-    float d = 0.f;
-    for (int i = k + kLpLen - 4; i < kLpLen; i++) d += x[i] * x[i - k];
-    sm.ac[f][k] = sum + d;
+  // P2: _celt_autocorr, lags 0..4.  Warp k works lag k for every frame, so the window shift is a
+  // compile-time constant per warp (no selects on the 860-step serial chain).
+  if (NT >= 5 * 32 && R <= 32) {
+    const int k = tid >> 5, f = tid & 31;
+    if (k < 5 && f < nfr) {
+      const float *x = sm.xr + f * kLpStride;
+      float sum;
+      switch (k) {
+        case 0: sum = dot_fixed_shift<kLpLen - 4, 0>(x, x); break;
+        case 1: sum = dot_fixed_shift<kLpLen - 4, 1>(x, x); break;
+        case 2: sum = dot_fixed_shift<kLpLen - 4, 2>(x, x); break;
+        case 3: sum = dot_fixed_shift<kLpLen - 4, 3>(x, x); break;
+        default: sum = dot_fixed_shift<kLpLen - 4, 0>(x, x + 4); break;
+      }
+      float d = 0.f;
+      for (int i = k + kLpLen - 4; i < kLpLen; i++) d += x[i] * x[i - k];
+      sm.ac[f][k] = sum + d;
+    }
+  } else {
+    for (int it = tid; it < nfr * 5; it += NT) {
+      const int f = it / 5, k = it - f * 5;
+      const float *x = sm.xr + f * kLpStride;
+      const float sum = dot_shifted<kLpLen - 4>(x, x, k);
+      float d = 0.f;
+      for (int i = k + kLpLen - 4; i < kLpLen; i++) d += x[i] * x[i - k];
+      sm.ac[f][k] = sum + d;
+    }
   }
   Simt::cta_sync();
   // P3: lag window, _celt_lpc (order 4), bandwidth expansion, the extra zero
@@ -405,7 +455,15 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     sm.xr[f * kLpStride + m] = (m < 432) ? sm.xlp[f * kLpStride + 2 * m] : 0.f;
   }
   Simt::cta_sync();
-  // P5: a10 coarse cross-correlation, 147 lags x 240 taps, four lags per lane
+  // P5: a10 coarse cross-correlation, 147 lags x 240 taps, four lags per lane.  In its shadow the
+  // last warp (idle when NT > 37 R) prepares the sums of squares both find_best_pitch passes start from.
+  if (tid >= NT - 32) {
+    const int l = tid - (NT - 32);
+    if (l < nfr)
+      sm.syy6[l] = sumsq_from<240>(1.f, sm.xr + l * kLpStride);
+    else if (l >= 16 && l - 16 < nfr)
+      sm.syy8[l - 16] = sumsq_from<480>(1.f, sm.xlp + (l - 16) * kLpStride);
+  }
   for (int it = tid; it < nfr * 37; it += NT) {
     const int f = it / 37, q = it - f * 37;
     const float *y4 = sm.xr + f * kLpStride;
@@ -429,7 +487,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     const float *y4 = sm.xr + f * kLpStride;
     Best2 b;
     best_init(b);
-    float syy = sumsq_from<240>(1.f, y4);
+    float syy = sm.syy6[f];
     for (int i0 = 0; i0 < 147; i0 += 4) {  // four lags per trip: the loads are off the running sum's chain
       const f4 xc4 = ld4(sm.xc[f] + i0), ya = ld4(y4 + i0 + 240), yb = ld4(y4 + i0);
       const float xcv[4] = {xc4.x, xc4.y, xc4.z, xc4.w};
@@ -438,10 +496,8 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         if (i0 + u < 147) {
-          if (xcv[u] > 0.f) {
-            const float x16 = xcv[u] * 1e-12f;
-            best_insert(b, x16 * x16, syy, i0 + u);
-          }
+          const float x16 = xcv[u] * 1e-12f;
+          best_insert_sel(b, xcv[u] > 0.f, x16 * x16, syy, i0 + u);
           syy += dl[u];
           syy = syy < 1.f ? 1.f : syy;
         }
@@ -478,31 +534,32 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     };
     Best2 b;
     best_init(b);
-    float syy = sumsq_from<480>(1.f, y);
-    // the running Syy only matters up to the last candidate lag; four lags per trip, loads off the chain
-    int iend = (lo0 > lo1 ? lo0 : lo1) + 5;
-    if (iend > 294) iend = 294;
-    for (int i0 = 0; i0 < iend; i0 += 4) {
-      const f4 ya = ld4(y + i0 + 480), yb = ld4(y + i0);
-      const float dl[4] = {ya.x * ya.x - yb.x * yb.x, ya.y * ya.y - yb.y * yb.y, ya.z * ya.z - yb.z * yb.z,
-                           ya.w * ya.w - yb.w * yb.w};
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int i = i0 + u;
-        if (i < iend) {
-          const int d0 = i - lo0, d1 = i - lo1;
-          if ((d0 >= 0 && d0 < 5) || (d1 >= 0 && d1 < 5)) {
-            const float xc = xcorr_at(i);
-            if (xc > 0.f) {
-              const float x16 = xc * 1e-12f;
-              best_insert(b, x16 * x16, syy, i);
-            }
-          }
-          syy += dl[u];
-          syy = syy < 1.f ? 1.f : syy;
-        }
+    float syy = sm.syy8[f];
+    // Syy runs over every lag up to the last candidate, but the comparison only happens inside the two
+    // runs of five candidates: plain recurrence up to each run, straight-line checks inside it
+    const int r1 = lo0 < lo1 ? lo0 : lo1, r2 = lo0 < lo1 ? lo1 : lo0;
+    auto clampi = [](int v) { return v < 0 ? 0 : (v > 294 ? 294 : v); };
+    const int a0 = clampi(r1), a1 = clampi(r1 + 5), b0 = clampi(r2 > r1 + 5 ? r2 : r1 + 5), b1 = clampi(r2 + 5);
+    auto advance = [&](int from, int to) {
+#pragma unroll 4
+      for (int i = from; i < to; i++) {
+        syy += y[i + 480] * y[i + 480] - y[i] * y[i];
+        syy = syy < 1.f ? 1.f : syy;
       }
-    }
+    };
+    auto checked = [&](int from, int to) {
+      for (int i = from; i < to; i++) {
+        const float xc = xcorr_at(i);
+        const float x16 = xc * 1e-12f;
+        best_insert_sel(b, xc > 0.f, x16 * x16, syy, i);
+        syy += y[i + 480] * y[i + 480] - y[i] * y[i];
+        syy = syy < 1.f ? 1.f : syy;
+      }
+    };
+    advance(0, a0);
+    checked(a0, a1);
+    advance(a1, b0);
+    checked(b0, b1);
     const int bp = b.p0;
     int offset = 0;
     if (bp > 0 && bp < 293) {

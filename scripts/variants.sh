@@ -10,6 +10,14 @@ for spec in "$@"; do
      -o $so crispy_b200/csrc/crispy_ns.cu crispy_b200/csrc/ns_host.cpp > gpurun_out/${TAG}_${name}_build.log 2>&1 || { echo "build $name failed"; tail -5 gpurun_out/${TAG}_${name}_build.log; continue; }
   echo "=== variant $name ($flags)"
   CRISPY_NS_LIB=$so timeout 300 python scripts/prof_kernels.py 1024 512 2>&1 | tee gpurun_out/${TAG}_${name}_kernels.txt
+  # isolated (serialised, cold) duration of each kernel of one chunk
+  CRISPY_NS_LIB=$so timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ns_ -s 14 -c 7 --csv \
+     --log-file gpurun_out/${TAG}_${name}_iso.csv python scripts/prof_kernels.py 1024 64 > /dev/null 2>&1
+  python - <<PY
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/${TAG}_${name}_iso.csv')) if len(r)>5 and r[0].isdigit()]
+print('  isolated us:', ', '.join(f"{r[4].split('(')[0].replace('ns_','').replace('_kernel','')}={float(r[-1].replace(',',''))/1000:.0f}" for r in rows))
+PY
 done
 if [ -n "$CHUNKS" ]; then
   for ch in $CHUNKS; do

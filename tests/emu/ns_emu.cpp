@@ -71,7 +71,7 @@ int launch(int n_ctas, int n_threads, size_t smem_bytes, const std::function<voi
 }
 
 constexpr int kPitchRun = 8;
-constexpr int kPitchThreads = 64;  // any thread count gives the same result; fewer OS threads run faster
+constexpr int kPitchThreads = 160;  // any multiple of 32 gives the same result; >= 160 takes the per-warp-lag autocorrelation path
 constexpr int kScanWarps = 1;
 }  // namespace
 
