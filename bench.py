@@ -32,6 +32,8 @@ ALG_BYTES_PER_FRAME = 3844          # 480*4 read + 480*4 written
 RNN_FLOPS_PER_FRAME = 175006        # 2 * 87,503 MAC
 ALL_FLOPS_PER_FRAME = 390000        # SURVEY.md 8(a) whole-pipeline estimate
 FP32_PEAK_TFLOPS_NOMINAL = 74.5     # 148 SM * 128 lanes * 2 * 1.965 GHz (not in MEASURED_PEAKS.json)
+# the recurrent core (K4) runs on the tensor pipe: 723 bf16 m16n8k16 tiles per 16-stream step, twice (hi + lo plane)
+RNN_MMA_FLOPS_PER_FRAME = 2 * 723 * (16 * 8 * 16 * 2) // 16   # executed flops per (stream, frame), padding included
 
 
 def parse_args():
@@ -58,6 +60,18 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    """dense bf16 TFLOP/s, sustained figure (the kernel is timed inside a long step)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]), "measured sustained (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 1400.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -265,6 +279,29 @@ def run_b200(args):
     stream_seconds_per_step = world * n_streams * n_frames / 100.0
     value = stream_seconds_per_step * args.steps / (total_ms_max / 1e3)
 
+    # ---- the same kernels one at a time (one stream): isolated durations, comparable with the ncu
+    # launch list under profiles/ (inside the timed region above they overlap 7 deep and share SMs) ----
+    kernels_isolated = None
+    if rank == 0:
+        os.environ["CRISPY_NS_SERIAL"] = "1"
+        try:
+            den_s = cb.BatchDenoiser(n_streams, device=local)
+        finally:
+            del os.environ["CRISPY_NS_SERIAL"]
+        nf_s = min(n_frames, 8 * info0["chunk_frames"])
+        den_s.process_streams(x[:, :nf_s * FRAME], unit_scale=True, out=out[:, :nf_s * FRAME], vad=vad[:, :nf_s])
+        torch.cuda.synchronize(dev)
+        den_s.reset()
+        den_s.profile(True)
+        den_s.process_streams(x[:, :nf_s * FRAME], unit_scale=True, out=out[:, :nf_s * FRAME], vad=vad[:, :nf_s])
+        prof_s = den_s.profile_read()
+        den_s.profile(False)
+        tot_s = sum(ms for ms, _ in prof_s.values()) or 1.0
+        kernels_isolated = {"frames_per_stream": nf_s, "note": "CRISPY_NS_SERIAL=1: all kernels on one stream",
+                            "kernels": [{"kernel": k, "launches": n, "avg_launch_us": ms / max(n, 1) * 1e3,
+                                         "share_of_kernel_time": ms / tot_s} for k, (ms, n) in prof_s.items()]}
+        del den_s
+
     # ---- end to end through the host API --------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -330,8 +367,12 @@ def run_b200(args):
                "avg_launch_us": avg_s * 1e6, "frames_per_launch": frames_per_launch,
                "hbm_algorithmic_gbs": ALG_BYTES_PER_FRAME * frames_per_launch / avg_s / 1e9}
         if name == "ns_rnn_kernel":
-            ent["fp32_tflops"] = RNN_FLOPS_PER_FRAME * frames_per_launch / avg_s / 1e12
-            ent["fp32_frac_of_nominal"] = ent["fp32_tflops"] / FP32_PEAK_TFLOPS_NOMINAL
+            tpeak, tsrc = measured_tensor_peak()
+            ent["tensor"] = {"bound": "tensor (latency: 8 dependent products per frame step)",
+                             "algorithmic_tflops": RNN_FLOPS_PER_FRAME * frames_per_launch / avg_s / 1e12,
+                             "executed_tflops_bf16_hi_lo": RNN_MMA_FLOPS_PER_FRAME * frames_per_launch / avg_s / 1e12,
+                             "peak": tpeak, "unit": "TFLOP/s", "peak_source": tsrc}
+            ent["tensor"]["frac"] = ent["tensor"]["algorithmic_tflops"] / tpeak
         tr = traffic_tab.get(name)
         if tr and tr.get("streams") == n_streams:
             ent["dram_bytes_per_launch_ncu"] = tr["dram_bytes_per_launch"] * frames_per_launch / tr["frames_per_launch"]
@@ -368,7 +409,8 @@ def run_b200(args):
                          "(no flush needed)",
                    "weights": "synthetic seed 0 (nnnoiseless weights are not available offline)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "kernels": kernels, "roofline_fp32": roofline_fp32, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "kernels": kernels, "kernels_isolated": kernels_isolated, "roofline_fp32": roofline_fp32,
+        "cpu_baseline": cpu_baseline,
         "parity_vs_oracle": parity, "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line), flush=True)

@@ -418,7 +418,7 @@ void crispy_ns_batch_destroy(crispy_ns_batch *b) {
   if (b->e_start) cudaEventDestroy(b->e_start);
   if (b->e_reset) cudaEventDestroy(b->e_reset);
   for (int k = 0; k < kNumKernels; k++)
-    if (b->s_k[k]) cudaStreamDestroy(b->s_k[k]);
+    if (b->s_k[k] && (k == 0 || b->s_k[k] != b->s_k[0])) cudaStreamDestroy(b->s_k[k]);
   for (int i = 0; i < 2; i++) {
     cudaFree(b->d_in[i]);
     cudaFree(b->d_out[i]);
@@ -504,8 +504,15 @@ int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_strea
     int prio_lo = 0, prio_hi = 0;
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     static const bool serial[kNumKernels] = {true, false, true, false, true, true, false};
-    for (int k = 0; k < kNumKernels && e == cudaSuccess; k++)
-      e = cudaStreamCreateWithPriority(&b->s_k[k], cudaStreamNonBlocking, serial[k] ? prio_hi : prio_lo);
+    // $CRISPY_NS_SERIAL=1 (measurement aid): every kernel on one stream, so per-kernel event times are
+    // isolated durations comparable with an ncu launch list
+    const bool one_stream = getenv("CRISPY_NS_SERIAL") && atoi(getenv("CRISPY_NS_SERIAL")) > 0;
+    for (int k = 0; k < kNumKernels && e == cudaSuccess; k++) {
+      if (one_stream && k > 0)
+        b->s_k[k] = b->s_k[0];
+      else
+        e = cudaStreamCreateWithPriority(&b->s_k[k], cudaStreamNonBlocking, serial[k] ? prio_hi : prio_lo);
+    }
   }
   if (e != cudaSuccess) {
     crispy_ns_batch_destroy(b);

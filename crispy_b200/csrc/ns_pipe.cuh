@@ -1701,7 +1701,8 @@ NS_DEV void store_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem
 // re-synthesises the frame before it to recover synthesis_mem (the overlap-add halo).
 constexpr int kSynRun = 8;
 
-NS_DEV void synth_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem &s, int stream, int t, bool halo) {
+NS_DEV void synth_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem &s, int stream, int t, bool halo,
+                        bool prefetch_next) {
   const long long fidx = (long long)stream * p.chunk_cap + t;
   const float *rec = p.rec + fidx * kRecFloats;
   const bool silent = reinterpret_cast<const int *>(rec)[kRecSilence] != 0;
@@ -1710,6 +1711,9 @@ NS_DEV void synth_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem
     s.X[k] = src[k];
     if (!silent) s.P[k] = src[kSpecStride + k];
   }
+  // the run's next frame is the next 7.7 KB of the same array: pull it into L2 while this one is worked on
+  if (prefetch_next && g.tid * 128 < (int)(2 * kSpecStride * sizeof(cf)))
+    Simt::prefetch_l2(reinterpret_cast<const char *>(src + 2 * kSpecStride) + g.tid * 128);
   if (g.tid < kBands) {
     s.g[g.tid] = rec[kRecG + g.tid];
     s.graw[g.tid] = rec[kRecGRaw + g.tid];
@@ -1761,9 +1765,9 @@ NS_DEV void synthesis_body(const Params &p, SpecSmem &s) {
       for (int i = g.tid; i < kFrame; i += kGroupThreads) s.synth[i] = st[kStSynth + p.synth_sel * kFrame + i];
       gsync(g);
     } else {
-      synth_frame(g, T, p, s, stream, t0 - 1, true);
+      synth_frame(g, T, p, s, stream, t0 - 1, true, true);
     }
-    for (int t = t0; t < t1; t++) synth_frame(g, T, p, s, stream, t, false);
+    for (int t = t0; t < t1; t++) synth_frame(g, T, p, s, stream, t, false, t + 1 < t1);
     if (t1 == p.n_frames) {
       for (int i = g.tid; i < kFrame; i += kGroupThreads) st[kStSynth + (1 - p.synth_sel) * kFrame + i] = s.synth[i];
       if (g.tid == 0) reinterpret_cast<int *>(st)[kStFrameCount] += p.n_frames;

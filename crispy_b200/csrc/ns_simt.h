@@ -50,6 +50,7 @@ struct Simt {
   static NS_DEV void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
   }
+  static NS_DEV void prefetch_l2(const void *gmem) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem)); }
   // shared-memory flags between the specialised warps of one CTA (no bar.sync): values only grow
   static NS_DEV void fence_cta() { __threadfence_block(); }
   static NS_DEV void flag_set(int *f, int v) {
@@ -170,6 +171,7 @@ struct Simt {
     };
     return rn(lo) | (rn(hi) << 16);
   }
+  static void prefetch_l2(const void *) {}
   static void fence_cta() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
   static void flag_set(int *f, int v) { __atomic_store_n(f, v, __ATOMIC_SEQ_CST); }
   static void flag_wait(const int *f, int v, bool) {
