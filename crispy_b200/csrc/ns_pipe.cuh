@@ -219,11 +219,11 @@ struct PitchSmem {
   float lpc2[R][8];
   float fx[R][12];
   int fi[R][12];
-  float xx[R], xy0[R];
+  float xx[R];
   float syy6[R], syy8[R];  // 1 + sum of squares the two find_best_pitch passes start from
   int best0[R], best1[R], T0[R], nk[R];
-  int n_tasks;
-  int task[R * 64];    // frame | lag << 4 | dst << 16
+  int n_tasks4[4];
+  int task4[4][R * 64];  // per alignment bucket: frame | lag << 4 | dst << 16
   float dots[R][64];   // 0: T0-1, 1: T0+1; for k >= 2 at 2+4(k-2): T1-1, T1, T1+1, T1b
 };
 
@@ -266,6 +266,7 @@ NS_DEV void best_insert_sel(Best2 &b, bool valid, float num, float syy, int i) {
   b.p0 = c0 ? i : b.p0;
 }
 
+constexpr int kDotXy0 = 62;  // slot of xy(T0) in PitchSmem::dots (candidates use 0..57)
 NS_DEV int rd_T1(int k, int T0) { return (2 * T0 + k) / (2 * k); }
 NS_DEV int rd_T1b(int k, int T0, int T1) {
   if (k == 2) return (T1 + T0 > 384) ? T0 : T0 + T1;
@@ -348,6 +349,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   float *h = sm.xlp;
 
   // P0: the window of high-passed samples these frames' pitch buffers cover
+  if (tid < 4) sm.n_tasks4[tid] = 0;
   {
     const int n4 = (nfr * kFrame + 1248) / 4;
     const f4 *src = reinterpret_cast<const f4 *>(row);
@@ -456,13 +458,10 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   }
   Simt::cta_sync();
   // P5: a10 coarse cross-correlation, 147 lags x 240 taps, four lags per lane.  In its shadow the
-  // last warp (idle when NT > 37 R) prepares the sums of squares both find_best_pitch passes start from.
+  // last warp (idle when NT > 37 R) prepares the sum of squares the coarse find_best_pitch starts from.
   if (tid >= NT - 32) {
     const int l = tid - (NT - 32);
-    if (l < nfr)
-      sm.syy6[l] = sumsq_from<240>(1.f, sm.xr + l * kLpStride);
-    else if (l >= 16 && l - 16 < nfr)
-      sm.syy8[l - 16] = sumsq_from<480>(1.f, sm.xlp + (l - 16) * kLpStride);
+    if (l < nfr) sm.syy6[l] = sumsq_from<240>(1.f, sm.xr + l * kLpStride);
   }
   for (int it = tid; it < nfr * 37; it += NT) {
     const int f = it / 37, q = it - f * 37;
@@ -507,7 +506,16 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     sm.best1[f] = b.p1;
   }
   Simt::cta_sync();
-  // P7: fine search, at most ten lags around 2*best0 and 2*best1
+  // P7: fine search, at most ten lags around 2*best0 and 2*best1.  In its shadow the last warp prepares
+  // the fine pass's starting Syy and remove_doubling's xx (= sum x[j]^2, the same products and order as
+  // the inner product of x with itself).
+  if (tid >= NT - 32) {
+    const int l = tid - (NT - 32);
+    if (l < nfr)
+      sm.syy8[l] = sumsq_from<480>(1.f, sm.xlp + l * kLpStride);
+    else if (l >= 16 && l - 16 < nfr)
+      sm.xx[l - 16] = sumsq_from<480>(0.f, sm.xlp + (l - 16) * kLpStride + 384);
+  }
   for (int it = tid; it < nfr * 10; it += NT) {
     const int f = it / 10, c = it - f * 10;
     const float *lp = sm.xlp + f * kLpStride;
@@ -575,63 +583,75 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     sm.T0[f] = T0;
   }
   Simt::cta_sync();
-  // P9: a11 remove_doubling: xx and xy(T0) (dual_inner_prod), then the candidate work list
-  for (int it = tid; it < nfr * 2; it += NT) {
-    const int f = it >> 1;
-    const float sum = dot480_shifted(sm.xlp + f * kLpStride, (it & 1) ? 384 - sm.T0[f] : 384);
-    if (it & 1)
-      sm.xy0[f] = sum;
-    else
-      sm.xx[f] = sum;
-  }
-  if (tid == 0) sm.n_tasks = 0;
-  Simt::cta_sync();
-  if (tid < nfr) {
-    const int f = tid;
-    const float *x = sm.xlp + f * kLpStride + 384;
-    float *yyl = sm.xr + f * kLpStride + 432;  // yy_lookup[0..384]
-    float yy = sm.xx[f];
-    yyl[0] = yy;
-    for (int i0 = 1; i0 <= 384; i0 += 4) {  // lags i0..i0+3: x[-i] and x[480-i] come as two aligned float4s
-      const f4 a = ld4(x - i0 - 3), c = ld4(x + 477 - i0);
-      const float av[4] = {a.w * a.w, a.z * a.z, a.y * a.y, a.x * a.x};
-      const float cv[4] = {c.w * c.w, c.z * c.z, c.y * c.y, c.x * c.x};
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        yy = yy + av[u] - cv[u];
-        yyl[i0 + u] = yy < 0.f ? 0.f : yy;
-      }
-    }
+  // P9 (a11 remove_doubling): xx came from the helper warp above; xy(T0) is one more item of the work list
+  // P10: the candidate work list, one lane per (frame, k).  k is examined iff T0/k stays >= 30 (T1 is
+  // non-increasing in k, so this equals upstream's break).  Inner products are bucketed by the
+  // alignment of their lagged window, so that a whole warp shares a compile-time shift in P11.
+  for (int it = tid; it < nfr * 16; it += NT) {
+    const int f = it >> 4, k = it & 15;
+    if (k == 0) continue;
     const int T0 = sm.T0[f];
-    int nk = 1;
-    for (int k = 2; k <= kMaxK; k++) {
-      if (rd_T1(k, T0) < 30) break;
-      nk = k;
-    }
-    sm.nk[f] = nk;
-    const int n = 2 + 4 * (nk - 1);
-    const int base = Simt::atomic_add_shared(&sm.n_tasks, n);
-    int *tk = sm.task + base;
-    tk[0] = f | ((T0 - 1) << 4) | (0 << 16);
-    tk[1] = f | ((T0 + 1) << 4) | (1 << 16);
-    for (int k = 2; k <= nk; k++) {
+    if (k > 1 && rd_T1(k, T0) < 30) continue;
+    if (k == kMaxK || rd_T1(k + 1, T0) < 30) sm.nk[f] = k;
+    auto push = [&](int lag, int dst) {
+      const int bkt = (384 - lag) & 3;
+      const int idx = Simt::atomic_add_shared(&sm.n_tasks4[bkt], 1);
+      sm.task4[bkt][idx] = f | (lag << 4) | (dst << 16);
+    };
+    if (k == 1) {
+      push(T0 - 1, 0);
+      push(T0 + 1, 1);
+      push(T0, kDotXy0);
+    } else {
       const int T1 = rd_T1(k, T0), T1b = rd_T1b(k, T0, T1);
       const int d = 2 + 4 * (k - 2);
-      int *e = tk + d;
-      e[0] = f | ((T1 - 1) << 4) | ((d + 0) << 16);
-      e[1] = f | (T1 << 4) | ((d + 1) << 16);
-      e[2] = f | ((T1 + 1) << 4) | ((d + 2) << 16);
-      e[3] = f | (T1b << 4) | ((d + 3) << 16);
+      push(T1 - 1, d);
+      push(T1, d + 1);
+      push(T1 + 1, d + 2);
+      push(T1b, d + 3);
     }
   }
   Simt::cta_sync();
-  // P11: one 480-tap inner product per work item
+  // P11: one 480-tap inner product per work item on the worker warps (warp w serves bucket w % 4);
+  // meanwhile the last warp runs the serial yy_lookup recurrence, which only P12 needs
   {
-    const int n = sm.n_tasks;
-    for (int it = tid; it < n; it += NT) {
-      const int e = sm.task[it];
-      const int f = e & 15, lag = (e >> 4) & 0xFFF, dst = e >> 16;
-      sm.dots[f][dst] = dot480_shifted(sm.xlp + f * kLpStride, 384 - lag);
+    static_assert(NT >= 160, "four worker warps + the helper warp");
+    const int nwork = NT / 32 - 1, w = tid >> 5, lane = tid & 31;
+    if (w == nwork) {
+      if (lane < nfr) {
+        const int f = lane;
+        const float *x = sm.xlp + f * kLpStride + 384;
+        float *yyl = sm.xr + f * kLpStride + 432;  // yy_lookup[0..384]
+        float yy = sm.xx[f];
+        yyl[0] = yy;
+        for (int i0 = 1; i0 <= 384; i0 += 4) {  // lags i0..i0+3: x[-i] and x[480-i] come as two aligned float4s
+          const f4 a = ld4(x - i0 - 3), c = ld4(x + 477 - i0);
+          const float av[4] = {a.w * a.w, a.z * a.z, a.y * a.y, a.x * a.x};
+          const float cv[4] = {c.w * c.w, c.z * c.z, c.y * c.y, c.x * c.x};
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            yy = yy + av[u] - cv[u];
+            yyl[i0 + u] = yy < 0.f ? 0.f : yy;
+          }
+        }
+      }
+    } else {
+      const int bkt = w & 3, wb = w >> 2, nwb = (nwork - bkt + 3) >> 2;
+      const int n = sm.n_tasks4[bkt];
+      for (int it = wb * 32 + lane; it < n; it += nwb * 32) {
+        const int e = sm.task4[bkt][it];
+        const int f = e & 15, lag = (e >> 4) & 0xFFF, dst = e >> 16;
+        const float *row = sm.xlp + f * kLpStride;
+        const float *ya = row + ((384 - lag) & ~3);
+        float sum;
+        switch (bkt) {
+          case 0: sum = dot_fixed_shift<480, 0>(row + 384, ya); break;
+          case 1: sum = dot_fixed_shift<480, 1>(row + 384, ya); break;
+          case 2: sum = dot_fixed_shift<480, 2>(row + 384, ya); break;
+          default: sum = dot_fixed_shift<480, 3>(row + 384, ya); break;
+        }
+        sm.dots[f][dst] = sum;
+      }
     }
   }
   Simt::cta_sync();
@@ -652,7 +672,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     int T;
     if (k == 1) {
       T = T0;
-      xy = sm.xy0[f];
+      xy = sm.dots[f][kDotXy0];
       yy = yyl[T0];
       c0 = sm.dots[f][0];
       c1 = xy;
