@@ -279,29 +279,6 @@ def run_b200(args):
     stream_seconds_per_step = world * n_streams * n_frames / 100.0
     value = stream_seconds_per_step * args.steps / (total_ms_max / 1e3)
 
-    # ---- the same kernels one at a time (one stream): isolated durations, comparable with the ncu
-    # launch list under profiles/ (inside the timed region above they overlap 7 deep and share SMs) ----
-    kernels_isolated = None
-    if rank == 0:
-        os.environ["CRISPY_NS_SERIAL"] = "1"
-        try:
-            den_s = cb.BatchDenoiser(n_streams, device=local)
-        finally:
-            del os.environ["CRISPY_NS_SERIAL"]
-        nf_s = min(n_frames, 8 * info0["chunk_frames"])
-        den_s.process_streams(x[:, :nf_s * FRAME], unit_scale=True, out=out[:, :nf_s * FRAME], vad=vad[:, :nf_s])
-        torch.cuda.synchronize(dev)
-        den_s.reset()
-        den_s.profile(True)
-        den_s.process_streams(x[:, :nf_s * FRAME], unit_scale=True, out=out[:, :nf_s * FRAME], vad=vad[:, :nf_s])
-        prof_s = den_s.profile_read()
-        den_s.profile(False)
-        tot_s = sum(ms for ms, _ in prof_s.values()) or 1.0
-        kernels_isolated = {"frames_per_stream": nf_s, "note": "CRISPY_NS_SERIAL=1: all kernels on one stream",
-                            "kernels": [{"kernel": k, "launches": n, "avg_launch_us": ms / max(n, 1) * 1e3,
-                                         "share_of_kernel_time": ms / tot_s} for k, (ms, n) in prof_s.items()]}
-        del den_s
-
     # ---- end to end through the host API --------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -340,6 +317,29 @@ def run_b200(args):
                "api": "BatchDenoiser.process_streams_host -> crispy_ns_process_streams_host (pinned host buffers)"}
         if rank == 0:
             e2e["matches_device_path"] = bool(torch.equal(hout[:4], out[:4, :e2e_frames * FRAME].cpu()))
+
+    # ---- the same kernels one at a time (one stream): isolated durations, comparable with the ncu
+    # launch list under profiles/ (inside the timed region above they overlap 7 deep and share SMs) ----
+    kernels_isolated = None
+    if rank == 0:
+        os.environ["CRISPY_NS_SERIAL"] = "1"
+        try:
+            den_s = cb.BatchDenoiser(n_streams, device=local)
+        finally:
+            del os.environ["CRISPY_NS_SERIAL"]
+        nf_s = min(n_frames, 8 * info0["chunk_frames"])
+        den_s.process_streams(x[:, :nf_s * FRAME], unit_scale=True, out=out[:, :nf_s * FRAME], vad=vad[:, :nf_s])
+        torch.cuda.synchronize(dev)
+        den_s.reset()
+        den_s.profile(True)
+        den_s.process_streams(x[:, :nf_s * FRAME], unit_scale=True, out=out[:, :nf_s * FRAME], vad=vad[:, :nf_s])
+        prof_s = den_s.profile_read()
+        den_s.profile(False)
+        tot_s = sum(ms for ms, _ in prof_s.values()) or 1.0
+        kernels_isolated = {"frames_per_stream": nf_s, "note": "CRISPY_NS_SERIAL=1: all kernels on one stream",
+                            "kernels": [{"kernel": k, "launches": n, "avg_launch_us": ms / max(n, 1) * 1e3,
+                                         "share_of_kernel_time": ms / tot_s} for k, (ms, n) in prof_s.items()]}
+        del den_s
 
     if rank != 0:
         if world > 1:

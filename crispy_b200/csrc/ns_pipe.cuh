@@ -220,10 +220,11 @@ struct PitchSmem {
   float fx[R][12];
   int fi[R][12];
   float xx[R];
-  float syy6[R], syy8[R];  // 1 + sum of squares the two find_best_pitch passes start from
+  float sb6[R][148];  // Syy before every coarse lag (helper warp, in the coarse search's shadow)
   int best0[R], best1[R], T0[R], nk[R];
-  int n_tasks4[4];
-  int task4[4][R * 64];  // per alignment bucket: frame | lag << 4 | dst << 16
+  // work lists of remove_doubling's inner products per window-alignment bucket: frame | lag << 3 | k << 12
+  int n_tri[4], n_sgl[4];
+  uint16_t tri[4][R * 16], sgl[4][R * 16];  // <= 15 triples and <= 14 singles per frame
   float dots[R][64];   // 0: T0-1, 1: T0+1; for k >= 2 at 2+4(k-2): T1-1, T1, T1+1, T1b
 };
 
@@ -280,18 +281,24 @@ NS_DEV float pitch_gain_f(float xy, float xx, float yy) { return xy / sqrtf(1.f 
 // the lane walks aligned float4s and shifts a two-vector window in registers, so one LDS.128 feeds
 // four taps and the only serial dependency is the chain of adds (a scalar loop pays the ~29-cycle
 // shared-memory latency on every tap and ~3.5 bank-conflict wavefronts between lanes with different
-// lags).  Reads up to 3 floats before y[0] and 4 past y[N-1]: row padding / neighbouring rows.
+// lags).  Reads up to 3 floats before y[0] and 11 past y[N-1]: row padding / neighbouring rows.
+#ifndef NS_DOT_UNROLL
+#define NS_DOT_UNROLL 4
+#endif
+#define NS_PRAGMA(x) _Pragma(#x)
+#define NS_UNROLL(n) NS_PRAGMA(unroll n)
 template <int N>
 NS_DEV float dot_shifted(const float *x, const float *yrow, int yoff) {
   static_assert(N % 4 == 0, "whole float4s");
   const float *ya = yrow + (yoff & ~3);
   const bool p1 = (yoff & 1) != 0, p2 = (yoff & 2) != 0;
-  f4 lo = ld4(ya);
+  f4 lo = ld4(ya), hi = ld4(ya + 4), xv = ld4(x);
   float sum = 0.f;
-#pragma unroll 2
+  NS_UNROLL(NS_DOT_UNROLL)
   for (int j = 0; j < N; j += 4) {
-    const f4 hi = ld4(ya + j + 4);
-    const f4 xv = ld4(x + j);
+    // the next trip's operands are requested before this trip's chain of adds (the over-read of the
+    // last trip stays inside the shared-memory rows)
+    const f4 hi_n = ld4(ya + j + 8), xv_n = ld4(x + j + 4);
     const float a0 = p1 ? lo.y : lo.x, a1 = p1 ? lo.z : lo.y, a2 = p1 ? lo.w : lo.z, a3 = p1 ? hi.x : lo.w,
                 a4 = p1 ? hi.y : hi.x, a5 = p1 ? hi.z : hi.y;
     const float y0 = p2 ? a2 : a0, y1 = p2 ? a3 : a1, y2 = p2 ? a4 : a2, y3 = p2 ? a5 : a3;
@@ -300,28 +307,87 @@ NS_DEV float dot_shifted(const float *x, const float *yrow, int yoff) {
     sum += xv.z * y2;
     sum += xv.w * y3;
     lo = hi;
+    hi = hi_n;
+    xv = xv_n;
   }
   return sum;
 }
 // the same with the shift S = (y - ya) known at compile time: no selects (used where a whole warp shares it)
 template <int N, int S>
 NS_DEV float dot_fixed_shift(const float *x, const float *ya) {
-  f4 lo = ld4(ya);
+  f4 lo = ld4(ya), hi = ld4(ya + 4), xv = ld4(x);
   float sum = 0.f;
-#pragma unroll 2
+  NS_UNROLL(NS_DOT_UNROLL)
   for (int j = 0; j < N; j += 4) {
-    const f4 hi = ld4(ya + j + 4);
-    const f4 xv = ld4(x + j);
+    const f4 hi_n = ld4(ya + j + 8), xv_n = ld4(x + j + 4);
     const float w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     sum += xv.x * w[S];
     sum += xv.y * w[S + 1];
     sum += xv.z * w[S + 2];
     sum += xv.w * w[S + 3];
     lo = hi;
+    hi = hi_n;
+    xv = xv_n;
   }
   return sum;
 }
+// three inner products at once for the consecutive lags whose windows start at ya + S, ya + S + 1 and
+// ya + S + 2: one pass over x and one stream of y feed three independent chains of adds
+template <int N, int S>
+NS_DEV void dot3_fixed_shift(const float *x, const float *ya, float &s0, float &s1, float &s2) {
+  f4 w0 = ld4(ya), w1 = ld4(ya + 4), w2 = ld4(ya + 8), xv = ld4(x);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  NS_UNROLL(NS_DOT_UNROLL)
+  for (int j = 0; j < N; j += 4) {
+    const f4 w2_n = ld4(ya + j + 12), xv_n = ld4(x + j + 4);
+    const float w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+    a0 += xv.x * w[S];
+    a1 += xv.x * w[S + 1];
+    a2 += xv.x * w[S + 2];
+    a0 += xv.y * w[S + 1];
+    a1 += xv.y * w[S + 2];
+    a2 += xv.y * w[S + 3];
+    a0 += xv.z * w[S + 2];
+    a1 += xv.z * w[S + 3];
+    a2 += xv.z * w[S + 4];
+    a0 += xv.w * w[S + 3];
+    a1 += xv.w * w[S + 4];
+    a2 += xv.w * w[S + 5];
+    w0 = w1;
+    w1 = w2;
+    w2 = w2_n;
+    xv = xv_n;
+  }
+  s0 = a0;
+  s1 = a1;
+  s2 = a2;
+}
 NS_DEV float dot480_shifted(const float *row, int yoff) { return dot_shifted<480>(row + 384, row, yoff); }
+
+// find_best_pitch's running energy: out[i] = Syy before lag i, Syy <- max(1, Syy + y[i+len]^2 - y[i]^2), for
+// i < n (rounded up to 4).  y, out 16-byte aligned; out may alias y[0..n) (each y[i] is read before out[i]
+// is written and never again).  Four lags per trip: loads and products are off the chain of adds.
+NS_DEV void syy_recurrence(float syy, const float *y, int len, int n, float *out) {
+  for (int i0 = 0; i0 < n; i0 += 4) {
+    const f4 ya = ld4(y + i0 + len), yb = ld4(y + i0);
+    const float d0 = ya.x * ya.x - yb.x * yb.x, d1 = ya.y * ya.y - yb.y * yb.y, d2 = ya.z * ya.z - yb.z * yb.z,
+                d3 = ya.w * ya.w - yb.w * yb.w;
+    f4 o;
+    o.x = syy;
+    syy += d0;
+    syy = syy < 1.f ? 1.f : syy;
+    o.y = syy;
+    syy += d1;
+    syy = syy < 1.f ? 1.f : syy;
+    o.z = syy;
+    syy += d2;
+    syy = syy < 1.f ? 1.f : syy;
+    o.w = syy;
+    syy += d3;
+    syy = syy < 1.f ? 1.f : syy;
+    *reinterpret_cast<f4 *>(out + i0) = o;
+  }
+}
 
 // acc + sum_{j<N} y[j]^2 in ascending j (y 16-byte aligned), loads batched four taps at a time
 template <int N>
@@ -349,7 +415,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   float *h = sm.xlp;
 
   // P0: the window of high-passed samples these frames' pitch buffers cover
-  if (tid < 4) sm.n_tasks4[tid] = 0;
+  if (tid < 4) sm.n_tri[tid] = sm.n_sgl[tid] = 0;
   {
     const int n4 = (nfr * kFrame + 1248) / 4;
     const f4 *src = reinterpret_cast<const f4 *>(row);
@@ -458,10 +524,13 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   }
   Simt::cta_sync();
   // P5: a10 coarse cross-correlation, 147 lags x 240 taps, four lags per lane.  In its shadow the
-  // last warp (idle when NT > 37 R) prepares the sum of squares the coarse find_best_pitch starts from.
+  // last warp (idle when NT > 37 R) runs the coarse find_best_pitch's Syy recurrence (it only needs y4).
   if (tid >= NT - 32) {
     const int l = tid - (NT - 32);
-    if (l < nfr) sm.syy6[l] = sumsq_from<240>(1.f, sm.xr + l * kLpStride);
+    if (l < nfr) {
+      const float *y4 = sm.xr + l * kLpStride;
+      syy_recurrence(sumsq_from<240>(1.f, y4), y4, 240, 147, sm.sb6[l]);
+    }
   }
   for (int it = tid; it < nfr * 37; it += NT) {
     const int f = it / 37, q = it - f * 37;
@@ -480,25 +549,20 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
   }
   Simt::cta_sync();
-  // P6: find_best_pitch on the coarse correlation (one lane per frame; Syy is a running sum)
+  // P6: find_best_pitch on the coarse correlation (one lane per frame)
   if (tid < nfr) {
     const int f = tid;
     const float *y4 = sm.xr + f * kLpStride;
     Best2 b;
     best_init(b);
-    float syy = sm.syy6[f];
-    for (int i0 = 0; i0 < 147; i0 += 4) {  // four lags per trip: the loads are off the running sum's chain
-      const f4 xc4 = ld4(sm.xc[f] + i0), ya = ld4(y4 + i0 + 240), yb = ld4(y4 + i0);
-      const float xcv[4] = {xc4.x, xc4.y, xc4.z, xc4.w};
-      const float dl[4] = {ya.x * ya.x - yb.x * yb.x, ya.y * ya.y - yb.y * yb.y, ya.z * ya.z - yb.z * yb.z,
-                           ya.w * ya.w - yb.w * yb.w};
+    for (int i0 = 0; i0 < 147; i0 += 4) {  // Syy per lag comes from the helper warp
+      const f4 xc4 = ld4(sm.xc[f] + i0), sy4 = ld4(sm.sb6[f] + i0);
+      const float xcv[4] = {xc4.x, xc4.y, xc4.z, xc4.w}, syv[4] = {sy4.x, sy4.y, sy4.z, sy4.w};
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         if (i0 + u < 147) {
           const float x16 = xcv[u] * 1e-12f;
-          best_insert_sel(b, xcv[u] > 0.f, x16 * x16, syy, i0 + u);
-          syy += dl[u];
-          syy = syy < 1.f ? 1.f : syy;
+          best_insert_sel(b, xcv[u] > 0.f, x16 * x16, syv[u], i0 + u);
         }
       }
     }
@@ -506,14 +570,15 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     sm.best1[f] = b.p1;
   }
   Simt::cta_sync();
-  // P7: fine search, at most ten lags around 2*best0 and 2*best1.  In its shadow the last warp prepares
-  // the fine pass's starting Syy and remove_doubling's xx (= sum x[j]^2, the same products and order as
+  // P7: fine search, at most ten lags around 2*best0 and 2*best1.  In its shadow the last warp runs
+  // the fine pass's Syy recurrence and remove_doubling's xx (= sum x[j]^2, the same products and order as
   // the inner product of x with itself).
   if (tid >= NT - 32) {
     const int l = tid - (NT - 32);
-    if (l < nfr)
-      sm.syy8[l] = sumsq_from<480>(1.f, sm.xlp + l * kLpStride);
-    else if (l >= 16 && l - 16 < nfr)
+    if (l < nfr) {  // Syy before every fine lag -> the 4x-decimated row, dead since P6
+      const float *y = sm.xlp + l * kLpStride;
+      syy_recurrence(sumsq_from<480>(1.f, y), y, 480, 294, sm.xr + l * kLpStride);
+    } else if (l >= 16 && l - 16 < nfr)
       sm.xx[l - 16] = sumsq_from<480>(0.f, sm.xlp + (l - 16) * kLpStride + 384);
   }
   for (int it = tid; it < nfr * 10; it += NT) {
@@ -542,31 +607,19 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     };
     Best2 b;
     best_init(b);
-    float syy = sm.syy8[f];
-    // Syy runs over every lag up to the last candidate, but the comparison only happens inside the two
-    // runs of five candidates: plain recurrence up to each run, straight-line checks inside it
+    // only the two runs of five candidate lags are compared; Syy before each lag is in the scratch row
+    const float *sb = sm.xr + f * kLpStride;
     const int r1 = lo0 < lo1 ? lo0 : lo1, r2 = lo0 < lo1 ? lo1 : lo0;
     auto clampi = [](int v) { return v < 0 ? 0 : (v > 294 ? 294 : v); };
     const int a0 = clampi(r1), a1 = clampi(r1 + 5), b0 = clampi(r2 > r1 + 5 ? r2 : r1 + 5), b1 = clampi(r2 + 5);
-    auto advance = [&](int from, int to) {
-#pragma unroll 4
-      for (int i = from; i < to; i++) {
-        syy += y[i + 480] * y[i + 480] - y[i] * y[i];
-        syy = syy < 1.f ? 1.f : syy;
-      }
-    };
     auto checked = [&](int from, int to) {
       for (int i = from; i < to; i++) {
         const float xc = xcorr_at(i);
         const float x16 = xc * 1e-12f;
-        best_insert_sel(b, xc > 0.f, x16 * x16, syy, i);
-        syy += y[i + 480] * y[i + 480] - y[i] * y[i];
-        syy = syy < 1.f ? 1.f : syy;
+        best_insert_sel(b, xc > 0.f, x16 * x16, sb[i], i);
       }
     };
-    advance(0, a0);
     checked(a0, a1);
-    advance(a1, b0);
     checked(b0, b1);
     const int bp = b.p0;
     int offset = 0;
@@ -585,35 +638,33 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   Simt::cta_sync();
   // P9 (a11 remove_doubling): xx came from the helper warp above; xy(T0) is one more item of the work list
   // P10: the candidate work list, one lane per (frame, k).  k is examined iff T0/k stays >= 30 (T1 is
-  // non-increasing in k, so this equals upstream's break).  Inner products are bucketed by the
-  // alignment of their lagged window, so that a whole warp shares a compile-time shift in P11.
+  // non-increasing in k, so this equals upstream's break).  Every k contributes the three consecutive
+  // lags T-1, T, T+1 (one "triple": their lagged windows overlap, so one pass over x and y feeds all
+  // three sums) and, for k >= 2, the single lag T1b.  Items are bucketed by the alignment of their
+  // window so that a whole warp shares a compile-time shift in P11.
   for (int it = tid; it < nfr * 16; it += NT) {
     const int f = it >> 4, k = it & 15;
     if (k == 0) continue;
     const int T0 = sm.T0[f];
     if (k > 1 && rd_T1(k, T0) < 30) continue;
     if (k == kMaxK || rd_T1(k + 1, T0) < 30) sm.nk[f] = k;
-    auto push = [&](int lag, int dst) {
-      const int bkt = (384 - lag) & 3;
-      const int idx = Simt::atomic_add_shared(&sm.n_tasks4[bkt], 1);
-      sm.task4[bkt][idx] = f | (lag << 4) | (dst << 16);
-    };
-    if (k == 1) {
-      push(T0 - 1, 0);
-      push(T0 + 1, 1);
-      push(T0, kDotXy0);
-    } else {
-      const int T1 = rd_T1(k, T0), T1b = rd_T1b(k, T0, T1);
-      const int d = 2 + 4 * (k - 2);
-      push(T1 - 1, d);
-      push(T1, d + 1);
-      push(T1 + 1, d + 2);
-      push(T1b, d + 3);
+    const int Tc = (k == 1) ? T0 : rd_T1(k, T0);
+    {
+      const int bkt = (384 - Tc - 1) & 3;
+      const int idx = Simt::atomic_add_shared(&sm.n_tri[bkt], 1);
+      sm.tri[bkt][idx] = (uint16_t)(f | (Tc << 3) | (k << 12));
+    }
+    if (k > 1) {
+      const int T1b = rd_T1b(k, T0, Tc);
+      const int bkt = (384 - T1b) & 3;
+      const int idx = Simt::atomic_add_shared(&sm.n_sgl[bkt], 1);
+      sm.sgl[bkt][idx] = (uint16_t)(f | (T1b << 3) | (k << 12));
     }
   }
   Simt::cta_sync();
-  // P11: one 480-tap inner product per work item on the worker warps (warp w serves bucket w % 4);
-  // meanwhile the last warp runs the serial yy_lookup recurrence, which only P12 needs
+  // P11: the inner products on the worker warps; meanwhile the last warp runs the serial yy_lookup
+  // recurrence, which only P12 needs.  Jobs 0..7: triples of bucket j % 4, half j / 4; jobs 8..11:
+  // singles of bucket j - 8.  Worker warp w takes jobs w, w + nwork, ...
   {
     static_assert(NT >= 160, "four worker warps + the helper warp");
     const int nwork = NT / 32 - 1, w = tid >> 5, lane = tid & 31;
@@ -636,21 +687,43 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
         }
       }
     } else {
-      const int bkt = w & 3, wb = w >> 2, nwb = (nwork - bkt + 3) >> 2;
-      const int n = sm.n_tasks4[bkt];
-      for (int it = wb * 32 + lane; it < n; it += nwb * 32) {
-        const int e = sm.task4[bkt][it];
-        const int f = e & 15, lag = (e >> 4) & 0xFFF, dst = e >> 16;
-        const float *row = sm.xlp + f * kLpStride;
-        const float *ya = row + ((384 - lag) & ~3);
-        float sum;
-        switch (bkt) {
-          case 0: sum = dot_fixed_shift<480, 0>(row + 384, ya); break;
-          case 1: sum = dot_fixed_shift<480, 1>(row + 384, ya); break;
-          case 2: sum = dot_fixed_shift<480, 2>(row + 384, ya); break;
-          default: sum = dot_fixed_shift<480, 3>(row + 384, ya); break;
+      for (int job = w; job < 12; job += nwork) {
+        if (job < 8) {
+          const int bkt = job & 3, n = sm.n_tri[bkt];
+          for (int it = (job >> 2) * 32 + lane; it < n; it += 64) {
+            const int e = sm.tri[bkt][it];
+            const int f = e & 7, Tc = (e >> 3) & 0x1FF, k = e >> 12;
+            const float *row = sm.xlp + f * kLpStride;
+            const float *ya = row + ((384 - Tc - 1) & ~3);
+            float sp, sc, sm1;  // lags Tc+1, Tc, Tc-1
+            switch (bkt) {
+              case 0: dot3_fixed_shift<480, 0>(row + 384, ya, sp, sc, sm1); break;
+              case 1: dot3_fixed_shift<480, 1>(row + 384, ya, sp, sc, sm1); break;
+              case 2: dot3_fixed_shift<480, 2>(row + 384, ya, sp, sc, sm1); break;
+              default: dot3_fixed_shift<480, 3>(row + 384, ya, sp, sc, sm1); break;
+            }
+            const int d = 2 + 4 * (k - 2);
+            sm.dots[f][k == 1 ? 0 : d] = sm1;
+            sm.dots[f][k == 1 ? kDotXy0 : d + 1] = sc;
+            sm.dots[f][k == 1 ? 1 : d + 2] = sp;
+          }
+        } else {
+          const int bkt = job - 8, n = sm.n_sgl[bkt];
+          for (int it = lane; it < n; it += 32) {
+            const int e = sm.sgl[bkt][it];
+            const int f = e & 7, lag = (e >> 3) & 0x1FF, k = e >> 12;
+            const float *row = sm.xlp + f * kLpStride;
+            const float *ya = row + ((384 - lag) & ~3);
+            float sum;
+            switch (bkt) {
+              case 0: sum = dot_fixed_shift<480, 0>(row + 384, ya); break;
+              case 1: sum = dot_fixed_shift<480, 1>(row + 384, ya); break;
+              case 2: sum = dot_fixed_shift<480, 2>(row + 384, ya); break;
+              default: sum = dot_fixed_shift<480, 3>(row + 384, ya); break;
+            }
+            sm.dots[f][2 + 4 * (k - 2) + 3] = sum;
+          }
         }
-        sm.dots[f][dst] = sum;
       }
     }
   }
