@@ -214,7 +214,7 @@ struct PitchSmem {
   static constexpr int kXlpFloats = (R * kLpStride > kHLen) ? R * kLpStride : kHLen;
   float xr[R * kLpStride];  // raw downsampled rows; after the FIR each row holds y4[432] | yy_lookup[388]
   float xlp[kXlpFloats];    // first the high-passed window, then the whitened rows x_lp
-  float xc[R][148];
+  float xc[R][152];
   float ac[R][8];
   float lpc2[R][8];
   float fx[R][12];
@@ -424,15 +424,19 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   }
   Simt::cta_sync();
   // P1: a9 2x downsample, pitch_buf[j] of frame f = h[480 f + j]
-  for (int it = tid; it < nfr * kLpLen; it += NT) {
-    const int f = it / kLpLen, i = it - f * kLpLen;
-    const float *x = h + f * kFrame;
-    float v;
-    if (i == 0)
-      v = .5f * (.5f * x[1] + x[0]);
+  for (int it = tid; it < nfr * (kLpLen / 4); it += NT) {  // four outputs per lane from two float4s (+ one scalar)
+    const int f = it / (kLpLen / 4), i0 = 4 * (it - f * (kLpLen / 4));
+    const float *x = h + f * kFrame + 2 * i0;
+    const f4 b4 = ld4(x), c4 = ld4(x + 4);
+    f4 v;
+    if (i0 == 0)
+      v.x = .5f * (.5f * b4.y + b4.x);
     else
-      v = .5f * (.5f * (x[2 * i - 1] + x[2 * i + 1]) + x[2 * i]);
-    sm.xr[f * kLpStride + i] = v;
+      v.x = .5f * (.5f * (x[-1] + b4.y) + b4.x);
+    v.y = .5f * (.5f * (b4.y + b4.w) + b4.z);
+    v.z = .5f * (.5f * (b4.w + c4.y) + c4.x);
+    v.w = .5f * (.5f * (c4.y + c4.w) + c4.z);
+    *reinterpret_cast<f4 *>(sm.xr + f * kLpStride + i0) = v;
   }
   Simt::cta_sync();
   // P2: _celt_autocorr, lags 0..4.  Warp k works lag k for every frame, so the window shift is a
@@ -504,17 +508,26 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   }
   Simt::cta_sync();
   // P4: celt_fir5 with zero initial memory -> x_lp (overwrites the window h, which is dead now)
-  for (int it = tid; it < nfr * kLpLen; it += NT) {
-    const int f = it / kLpLen, i = it - f * kLpLen;
-    const float *x = sm.xr + f * kLpStride;
+  for (int it = tid; it < nfr * (kLpLen / 4); it += NT) {  // four outputs per lane from three float4s
+    const int f = it / (kLpLen / 4), i0 = 4 * (it - f * (kLpLen / 4));
+    const float *x = sm.xr + f * kLpStride + i0;
     const float *n = sm.lpc2[f];
-    float sum = x[i];
-    sum += n[0] * (i >= 1 ? x[i - 1] : 0.f);
-    sum += n[1] * (i >= 2 ? x[i - 2] : 0.f);
-    sum += n[2] * (i >= 3 ? x[i - 3] : 0.f);
-    sum += n[3] * (i >= 4 ? x[i - 4] : 0.f);
-    sum += n[4] * (i >= 5 ? x[i - 5] : 0.f);
-    sm.xlp[f * kLpStride + i] = sum;
+    const f4 z4 = f4{0.f, 0.f, 0.f, 0.f};
+    const f4 p4 = (i0 >= 8) ? ld4(x - 8) : z4, q4 = (i0 >= 4) ? ld4(x - 4) : z4, r4 = ld4(x);
+    const float w[9] = {p4.w, q4.x, q4.y, q4.z, q4.w, r4.x, r4.y, r4.z, r4.w};  // x[i0-5 .. i0+3]
+    const float n0 = n[0], n1 = n[1], n2 = n[2], n3 = n[3], n4 = n[4];
+    float o[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      float sum = w[5 + u];
+      sum += n0 * w[4 + u];
+      sum += n1 * w[3 + u];
+      sum += n2 * w[2 + u];
+      sum += n3 * w[1 + u];
+      sum += n4 * w[u];
+      o[u] = sum;
+    }
+    *reinterpret_cast<f4 *>(sm.xlp + f * kLpStride + i0) = f4{o[0], o[1], o[2], o[3]};
   }
   Simt::cta_sync();
   // P4b: 4x-decimated copy y4[m] = x_lp[2m] (x4[j] = y4[192 + j]); zero pad to 432+8
@@ -523,8 +536,8 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     sm.xr[f * kLpStride + m] = (m < 432) ? sm.xlp[f * kLpStride + 2 * m] : 0.f;
   }
   Simt::cta_sync();
-  // P5: a10 coarse cross-correlation, 147 lags x 240 taps, four lags per lane.  In its shadow the
-  // last warp (idle when NT > 37 R) runs the coarse find_best_pitch's Syy recurrence (it only needs y4).
+  // P5: a10 coarse cross-correlation, 147 lags x 240 taps, eight lags per lane.  In its shadow the
+  // last warp (idle when NT > 19 R + 32) runs the coarse find_best_pitch's Syy recurrence (it only needs y4).
   if (tid >= NT - 32) {
     const int l = tid - (NT - 32);
     if (l < nfr) {
@@ -532,21 +545,30 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
       syy_recurrence(sumsq_from<240>(1.f, y4), y4, 240, 147, sm.sb6[l]);
     }
   }
-  for (int it = tid; it < nfr * 37; it += NT) {
-    const int f = it / 37, q = it - f * 37;
+  for (int it = tid; it < nfr * 19; it += NT) {  // eight lags per lane: one new float4 of y and one of x feed 32 MACs
+    const int f = it / 19, q = it - f * 19;
     const float *y4 = sm.xr + f * kLpStride;
     const float *x4 = y4 + 192;
-    const float *yb = y4 + 4 * q;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float *yb = y4 + 8 * q;
+    float a[8];
+#pragma unroll
+    for (int l = 0; l < 8; l++) a[l] = 0.f;
+    f4 w0 = ld4(yb), w1 = ld4(yb + 4);
+#pragma unroll 2
     for (int j = 0; j < 240; j += 4) {
-      const f4 xv = ld4(x4 + j), ya = ld4(yb + j), yc = ld4(yb + j + 4);
-      a0 += xv.x * ya.x; a1 += xv.x * ya.y; a2 += xv.x * ya.z; a3 += xv.x * ya.w;
-      a0 += xv.y * ya.y; a1 += xv.y * ya.z; a2 += xv.y * ya.w; a3 += xv.y * yc.x;
-      a0 += xv.z * ya.z; a1 += xv.z * ya.w; a2 += xv.z * yc.x; a3 += xv.z * yc.y;
-      a0 += xv.w * ya.w; a1 += xv.w * yc.x; a2 += xv.w * yc.y; a3 += xv.w * yc.z;
+      const f4 xv = ld4(x4 + j), w2 = ld4(yb + j + 8);
+      const float w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+      const float xt[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int l = 0; l < 8; l++) a[l] += xt[t] * w[l + t];
+      w0 = w1;
+      w1 = w2;
     }
-    float *dst = sm.xc[f] + 4 * q;
-    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+    float *dst = sm.xc[f] + 8 * q;
+    *reinterpret_cast<f4 *>(dst) = f4{a[0], a[1], a[2], a[3]};
+    *reinterpret_cast<f4 *>(dst + 4) = f4{a[4], a[5], a[6], a[7]};
   }
   Simt::cta_sync();
   // P6: find_best_pitch on the coarse correlation (one lane per frame)
