@@ -206,6 +206,9 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL only carries the timing barrier / max here; keep its banner ("NCCL version ...") off stdout,
+        # which must hold exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
