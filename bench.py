@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--e2e-seconds", type=float, default=None, help="override the e2e leg's length")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-front-end", action="store_true")
     ap.add_argument("--parity-streams", type=int, default=4)
     return ap.parse_args()
 
@@ -344,6 +345,34 @@ def run_b200(args):
                                          "share_of_kernel_time": ms / tot_s} for k, (ms, n) in prof_s.items()]}
         del den_s
 
+    # ---- configs[2] front ends, timed alone (rank 0): 44.1 -> 48 kHz over n_streams x 10 s ----------
+    front_end = None
+    if rank == 0 and not args.no_front_end:
+        fe_secs = 10
+        x44 = torch.empty((n_streams, 44100 * fe_secs), dtype=torch.float32, device=dev)
+        x44.copy_(x[:, :44100 * fe_secs])  # any signal will do: the kernels are data-independent
+        front_end = {"input": f"{n_streams} streams x {fe_secs} s at 44.1 kHz -> 48 kHz, device-resident, kernel alone"}
+        for name, fn, flops in (("sinc256", lambda: cb.sinc_resample(x44, 44100, 48000), 2 * 256),
+                                ("linear", lambda: cb.linear_resample(x44, 44100.0, 48000.0), 3)):
+            for _ in range(3):
+                y48 = fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            e0.record()
+            for _ in range(reps):
+                y48 = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            sec = e0.elapsed_time(e1) / 1e3 / reps
+            n_out = y48.shape[1]
+            front_end[name] = {"ms_per_launch": sec * 1e3, "stream_seconds_per_s": n_streams * fe_secs / sec,
+                               "hbm_algorithmic_gbs": n_streams * (x44.shape[1] + n_out) * 4 / sec / 1e9,
+                               "fp32_tflops": n_streams * n_out * flops / sec / 1e12}
+        front_end["sinc256"]["frac_fp32_nominal"] = front_end["sinc256"]["fp32_tflops"] / FP32_PEAK_TFLOPS_NOMINAL
+        front_end["linear"]["frac_hbm"] = front_end["linear"]["hbm_algorithmic_gbs"] / measured_peaks()[0]
+        del x44, y48
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -413,6 +442,7 @@ def run_b200(args):
                    "weights": "synthetic seed 0 (nnnoiseless weights are not available offline)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "kernels": kernels, "kernels_isolated": kernels_isolated, "roofline_fp32": roofline_fp32,
+        "front_end": front_end,
         "cpu_baseline": cpu_baseline,
         "parity_vs_oracle": parity, "wall_s_timed_region": t_wall,
     }

@@ -1,6 +1,7 @@
 // crispy_ns.cu -- libcrispy_ns.so: the sm_100a kernels' entry points and the C ABI declared in
 // include/crispy_ns.h.  No CPU fallback: every compute call needs a CUDA device.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -8,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/crispy_ns.h"
@@ -71,6 +73,50 @@ __global__ void ns_linear_resample_kernel(const float *__restrict__ in, float *_
     const int i = idx[n];
     const float last = src[i - 1], cur = src[i];
     dst[n] = __fadd_rn(last, __fmul_rn(__fsub_rn(cur, last), frac[n]));
+  }
+}
+
+
+// f2 (north_star item 4): windowed-sinc polyphase resampler.  out[n] = sum_k h[(n*M)%L][k] *
+// in[floor(n*M/L) - half + 1 + k].  A CTA covers T*Q consecutive outputs of one stream (T a multiple
+// of L, so thread t keeps one phase for all of its Q outputs and holds the tap h[k][phase] in a
+// register across them); the input span is staged once in shared memory, zero-filled outside
+// [0, n_in).  One fmaf per tap in ascending k per output: bit-identical to the oracle's scalar loop.
+template <int Q>
+__global__ void __launch_bounds__(1024) ns_sinc_resample_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                                const float *__restrict__ hT,  // [sinc_len][L]
+                                                                long long n_in, long long n_out, long long in_stride,
+                                                                long long out_stride, int L, int M, int sinc_len,
+                                                                int span) {
+  extern __shared__ float xs[];
+  const int T = blockDim.x, t = threadIdx.x;
+  const long long n0 = (long long)blockIdx.x * T * Q;      // multiple of L
+  const long long base0 = n0 / L * M - sinc_len / 2 + 1;   // input index of xs[0]
+  const float *src = in + (long long)blockIdx.y * in_stride;
+  for (int i = t; i < span; i += T) {
+    const long long g = base0 + i;
+    xs[i] = (g >= 0 && g < n_in) ? __ldg(src + g) : 0.f;
+  }
+  __syncthreads();
+  const int pos = t * M;  // t < 1024, M < 2^20
+  const int phase = pos % L;
+  const int rb = pos / L, step = T / L * M;
+  float acc[Q];
+#pragma unroll
+  for (int q = 0; q < Q; q++) acc[q] = 0.f;
+  const float *hp = hT + phase;
+  const float *xp = xs + rb;
+#pragma unroll 4
+  for (int k = 0; k < sinc_len; k++) {
+    const float h = __ldg(hp + (long long)k * L);
+#pragma unroll
+    for (int q = 0; q < Q; q++) acc[q] = fmaf(h, xp[q * step + k], acc[q]);
+  }
+  float *dst = out + (long long)blockIdx.y * out_stride;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const long long n = n0 + t + (long long)q * T;
+    if (n < n_out) dst[n] = acc[q];
   }
 }
 
@@ -857,6 +903,131 @@ int crispy_ns_linear_resample(int device, const float *d_in, float *d_out, int n
   NS_CUDA(cudaGetLastError());
   NS_CUDA(cudaFreeAsync(d_idx, st));
   NS_CUDA(cudaFreeAsync(d_frac, st));
+  return CRISPY_NS_OK;
+}
+
+// ---- f2 (north_star item 4): windowed-sinc polyphase resampler -------------------------------------
+// rubato 0.16.2 (Cargo.lock:4166) synchronous sinc design -- make_sincs with the BlackmanHarris2
+// window, sinc_len taps, f_cutoff relative to Nyquist (scaled by the ratio when downsampling) --
+// with the oversampling factor equal to L of the reduced ratio L/M, so every output lands on a
+// tabulated phase.  Delay-compensated; zeros outside the input.
+namespace {
+struct SincKey {
+  int device, L, M, sinc_len;
+  float f_cutoff;
+  bool operator<(const SincKey &o) const {
+    return std::tie(device, L, M, sinc_len, f_cutoff) < std::tie(o.device, o.L, o.M, o.sinc_len, o.f_cutoff);
+  }
+};
+std::mutex g_sinc_mu;
+std::map<SincKey, float *> g_sinc_tables;  // device copies, [sinc_len][L]; live until process exit
+
+int reduce_ratio(int input_rate, int output_rate, int *L, int *M) {
+  if (input_rate < 1 || output_rate < 1) return 0;
+  int a = input_rate, b = output_rate;
+  while (b) {
+    const int t = a % b;
+    a = b;
+    b = t;
+  }
+  *L = output_rate / a;
+  *M = input_rate / a;
+  return *L <= 1024;
+}
+// taps[k*L + p]: the filter sampled (k - half + 1) - p/L input samples from the interpolation point
+void sinc_taps_transposed(int L, int M, int sinc_len, float f_cutoff, std::vector<float> &taps) {
+  const double kPi = 3.14159265358979323846;
+  double fc = (double)f_cutoff;
+  if (L < M) fc = fc * (double)L / (double)M;
+  const long tot = (long)sinc_len * L;
+  std::vector<double> y((size_t)tot);
+  double sum = 0.0;
+  for (long x = 0; x < tot; x++) {
+    const double t = ((double)x - (double)(tot / 2)) * fc / (double)L;
+    const double s = t == 0.0 ? 1.0 : sin(kPi * t) / (kPi * t);
+    const double a = 2.0 * kPi * (double)x / (double)tot;
+    const double w = 0.35875 - 0.48829 * cos(a) + 0.14128 * cos(2.0 * a) - 0.01168 * cos(3.0 * a);
+    y[(size_t)x] = w * w * s;
+    sum += y[(size_t)x];
+  }
+  sum /= (double)L;
+  taps.assign((size_t)tot, 0.f);
+  for (int k = 0; k < sinc_len; k++)
+    for (int p = 0; p < L; p++) {
+      const long x = (long)L * (k + 1) - p;
+      if (x < tot) taps[(size_t)k * L + p] = (float)(y[(size_t)x] / sum);
+    }
+}
+}  // namespace
+
+int64_t crispy_ns_sinc_resample_count(int input_rate, int output_rate, int64_t n_in) {
+  int L, M;
+  if (n_in <= 0 || !reduce_ratio(input_rate, output_rate, &L, &M)) return 0;
+  return (int64_t)(((unsigned long long)n_in * (unsigned)L + (unsigned)M - 1) / (unsigned)M);
+}
+int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
+                            int64_t in_stride, int64_t out_stride, int input_rate, int output_rate,
+                            int sinc_len, float f_cutoff, void *cuda_stream) {
+  if (!d_in || !d_out || n_streams < 1 || n_in < 0) return fail(CRISPY_NS_EINVAL, "sinc_resample: bad argument");
+  if (sinc_len == 0) sinc_len = 256;
+  if (f_cutoff == 0.f) f_cutoff = 0.95f;
+  if (sinc_len < 2 || sinc_len > 2048 || (sinc_len & 1) || !(f_cutoff > 0.f) || f_cutoff > 1.f)
+    return fail(CRISPY_NS_EINVAL, "sinc_resample: sinc_len must be even in [2, 2048], f_cutoff in (0, 1]");
+  int L, M;
+  if (!reduce_ratio(input_rate, output_rate, &L, &M))
+    return fail(CRISPY_NS_EINVAL, "sinc_resample: output_rate/input_rate must reduce to L/M with L <= 1024");
+  if (M >= (1 << 20)) return fail(CRISPY_NS_EINVAL, "sinc_resample: ratio too extreme");
+  const int ndev = crispy_ns_device_count();
+  if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
+  NS_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int64_t n_out = crispy_ns_sinc_resample_count(input_rate, output_rate, n_in);
+  if (n_out == 0) return CRISPY_NS_OK;
+  float *d_taps = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_sinc_mu);
+    const SincKey key{device, L, M, sinc_len, f_cutoff};
+    auto it = g_sinc_tables.find(key);
+    if (it == g_sinc_tables.end()) {
+      std::vector<float> taps;
+      sinc_taps_transposed(L, M, sinc_len, f_cutoff, taps);
+      NS_CUDA(cudaMalloc((void **)&d_taps, taps.size() * sizeof(float)));
+      NS_CUDA(cudaMemcpy(d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+      g_sinc_tables[key] = d_taps;
+    } else {
+      d_taps = it->second;
+    }
+  }
+  // threads: a multiple of L near 160-256; outputs per thread Q in {8, 4, 2, 1} so the staged span fits
+  int T = L * ((160 + L - 1) / L);
+  if (T > 1024) T = L;
+  const int per = T / L * M;  // input samples advanced per T outputs
+  int Q = 8;
+  auto span_of = [&](int q) { return (long long)per * q + sinc_len + 1; };
+  while (Q > 1 && span_of(Q) * 4 > 96 * 1024) Q >>= 1;
+  const long long span = span_of(Q);
+  if (span * 4 > 200 * 1024) return fail(CRISPY_NS_EINVAL, "sinc_resample: decimation ratio too large for one tile");
+  const size_t smem = (size_t)span * sizeof(float);
+  const long long tiles = (n_out + (long long)T * Q - 1) / ((long long)T * Q);
+  if (tiles > 0x7fffffffll || n_streams > 65535) return fail(CRISPY_NS_EINVAL, "sinc_resample: too large for one call");
+  dim3 grid((unsigned)tiles, (unsigned)n_streams);
+#define NS_SINC_LAUNCH(QQ)                                                                               \
+  do {                                                                                                   \
+    if (smem > 48 * 1024)                                                                                \
+      NS_CUDA(cudaFuncSetAttribute(ns_sinc_resample_kernel<QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)smem));                                                          \
+    ns_sinc_resample_kernel<QQ><<<grid, T, smem, st>>>(d_in, d_out, d_taps, n_in, n_out, in_stride,      \
+                                                       out_stride, L, M, sinc_len, (int)span);           \
+  } while (0)
+  switch (Q) {
+    case 8: NS_SINC_LAUNCH(8); break;
+    case 4: NS_SINC_LAUNCH(4); break;
+    case 2: NS_SINC_LAUNCH(2); break;
+    default: NS_SINC_LAUNCH(1); break;
+  }
+#undef NS_SINC_LAUNCH
+  NS_CUDA(cudaGetLastError());
   return CRISPY_NS_OK;
 }
 

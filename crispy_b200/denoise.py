@@ -155,6 +155,23 @@ def linear_resample(x, input_rate: float, output_rate: float):
     return out
 
 
+def sinc_resample(x, input_rate: int, output_rate: int, sinc_len: int = 256, f_cutoff: float = 0.95):
+    """Batched windowed-sinc resampler on the GPU (north_star item 4: the rubato-equivalent
+    44.1 -> 48 kHz front end; rubato 0.16.2 pinned at Cargo.lock:4166).  x is a CUDA f32 tensor
+    [n_streams, n_in]; returns [n_streams, ceil(n_in*L/M)].  Asynchronous on the current stream."""
+    import torch
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise CrispyNsError("sinc_resample needs a CUDA float32 [n_streams, n_in] tensor")
+    n_streams, n_in = x.shape
+    n_out = int(_lib.lib().crispy_ns_sinc_resample_count(int(input_rate), int(output_rate), n_in))
+    out = torch.empty((n_streams, n_out), dtype=torch.float32, device=x.device)
+    st = torch.cuda.current_stream(x.device).cuda_stream
+    check(_lib.lib().crispy_ns_sinc_resample(x.device.index or 0, x.data_ptr(), out.data_ptr(), n_streams,
+                                             n_in, x.stride(0), out.stride(0) if n_out else 0,
+                                             int(input_rate), int(output_rate), int(sinc_len), float(f_cutoff), st))
+    return out
+
+
 class BatchDenoiser:
     """n independent DenoiseStates on one GPU; state persists across calls (chunked recordings)."""
 
@@ -168,11 +185,21 @@ class BatchDenoiser:
     # ---- device-resident path -------------------------------------------------------------------
     def process_streams(self, x, *, unit_scale: bool = True, volume: float = 1.0,
                         drop_first_frame: bool = False, out=None, vad=None, out_i16: bool = False,
-                        app=None, mix_stereo_i16: bool = False, return_taps: bool = False):
+                        app=None, mix_stereo_i16: bool = False, return_taps: bool = False,
+                        input_rate: float = SAMPLE_RATE, front_end: str = "linear"):
         """x: CUDA tensor [n_streams, n_frames*480], f32 (unit scale by default, i.e. the
         RnnNoiseProcessor convention) or int16.  Returns (out, vad[, taps]).  Asynchronous on the
-        current torch CUDA stream."""
+        current torch CUDA stream.  With input_rate != 48 kHz (f32 only) the front end runs first on
+        the same stream: "linear" = the reference's LinearResampler (audio.rs:217-221), "sinc" = the
+        windowed-sinc kernel; a whole recording per call (the resamplers keep no state across calls)."""
         import torch
+        if abs(float(input_rate) - SAMPLE_RATE) >= 1.0:
+            if front_end == "sinc":
+                x = sinc_resample(x, int(round(input_rate)), int(SAMPLE_RATE))
+            elif front_end == "linear":
+                x = linear_resample(x, float(input_rate), float(SAMPLE_RATE))
+            else:
+                raise CrispyNsError("front_end must be 'linear' or 'sinc'")
         if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1 or x.shape[0] != self.n_streams:
             raise CrispyNsError("process_streams needs a CUDA [n_streams, n_samples] tensor")
         if x.dtype not in (torch.float32, torch.int16):

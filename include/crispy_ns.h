@@ -144,6 +144,20 @@ int crispy_ns_linear_resample(int device, const float *d_in, float *d_out, int n
                               int64_t in_stride, int64_t out_stride, float input_rate,
                               float output_rate, void *cuda_stream);
 
+/* ---- f2 (BASELINE.json north_star item 4, configs[2]): windowed-sinc 44.1 -> 48 kHz front end,
+ * "rubato-equivalent".  The reference's own front end on this path is the linear interpolator above;
+ * rubato 0.16.2 (Cargo.lock:4166) is in its tree ahead of transcription
+ * (commands/transcription.rs:201-207).  Polyphase form of rubato's synchronous sinc resampler:
+ * sinc_len taps (0 = 256), f_cutoff relative to Nyquist (0 = 0.95; scaled by the ratio when
+ * downsampling), BlackmanHarris2 window, one tabulated phase per L of the reduced ratio
+ * L/M = output_rate/input_rate (L <= 1024), delay-compensated, zeros outside [0, n_in):
+ *   out[s][n] = sum_k h[(n*M)%L][k] * in[s][floor(n*M/L) - sinc_len/2 + 1 + k],  n < ceil(n_in*L/M)
+ * 441 input samples give exactly one 480-sample frame.  Device pointers, asynchronous. */
+int64_t crispy_ns_sinc_resample_count(int input_rate, int output_rate, int64_t n_in);
+int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
+                            int64_t in_stride, int64_t out_stride, int input_rate, int output_rate,
+                            int sinc_len, float f_cutoff, void *cuda_stream);
+
 /* ---- f3: RIFF/WAVE PCM16 I/O (recording.rs:83-121 writer; commands/recording.rs:385-460 parser) */
 int crispy_ns_wav_write_pcm16(const char *path, const int16_t *interleaved, int64_t n_frames,
                               int channels, int sample_rate);

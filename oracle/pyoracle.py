@@ -112,6 +112,12 @@ def _declare(L: C.CDLL) -> C.CDLL:
     L.rno_linres_init.argtypes = [C.POINTER(LinRes), C.c_float, C.c_float]
     L.rno_linres_process.restype = C.c_size_t
     L.rno_linres_process.argtypes = [C.POINTER(LinRes), f32p, C.c_size_t, f32p, C.c_size_t]
+    L.rno_sinc_resample_count.restype = C.c_size_t
+    L.rno_sinc_resample_count.argtypes = [C.c_int, C.c_int, C.c_size_t]
+    L.rno_sinc_resample.restype = C.c_size_t
+    L.rno_sinc_resample.argtypes = [f32p, C.c_size_t, f32p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_float]
+    L.rno_sinc_table.restype = C.c_int
+    L.rno_sinc_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, f32p, C.c_size_t, C.POINTER(C.c_int)]
     L.rno_processor_run.restype = C.c_size_t
     L.rno_processor_run.argtypes = [vp, C.c_float, C.c_float, f32p, C.c_size_t, f32p, C.c_size_t]
     L.rno_mix_dual_mono_i16.argtypes = [f32p, f32p, C.c_size_t, C.POINTER(C.c_int16)]
@@ -229,6 +235,27 @@ def linear_resample(x: np.ndarray, input_rate: float, output_rate: float) -> np.
     out = np.empty(cap, dtype=np.float32)
     n = lib().rno_linres_process(C.byref(r), _fp(x), len(x), _fp(out), cap)
     return out[:n].copy()
+
+
+def sinc_resample(x: np.ndarray, input_rate: int, output_rate: int, sinc_len: int = 256,
+                  f_cutoff: float = 0.95) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n = lib().rno_sinc_resample_count(int(input_rate), int(output_rate), len(x))
+    out = np.empty(n, dtype=np.float32)
+    got = lib().rno_sinc_resample(_fp(x), len(x), _fp(out), n, int(input_rate), int(output_rate), int(sinc_len),
+                                  float(f_cutoff))
+    assert got == n, (got, n)
+    return out
+
+
+def sinc_table(input_rate: int, output_rate: int, sinc_len: int = 256, f_cutoff: float = 0.95):
+    """([L, sinc_len] f32 polyphase taps, M)"""
+    cap = 1024 * sinc_len
+    buf = np.empty(cap, dtype=np.float32)
+    M = C.c_int()
+    L = lib().rno_sinc_table(int(input_rate), int(output_rate), int(sinc_len), float(f_cutoff), _fp(buf), cap,
+                             C.byref(M))
+    return buf[:L * sinc_len].reshape(L, sinc_len).copy(), M.value
 
 
 def processor_run(model: Model, x: np.ndarray, input_rate: float = 48000.0, volume: float = 1.0):

@@ -1348,3 +1348,100 @@ void rno_mix_dual_mono_i16(const float *mic, const float *app, size_t n, int16_t
     out[2 * i + 1] = q;
   }
 }
+
+/* ---- f2 (north_star item 4): windowed-sinc polyphase resampler ----------------------------------
+ * Follows rubato 0.16.2 (Cargo.lock:4166; source not vendored, restated from its documentation):
+ * sinc.rs make_sincs -- y[x] = w[x] * sinc((x - tot/2) * f_cutoff / factor), tot = sinc_len * factor,
+ * normalised so that sum(y) == factor; windows.rs BlackmanHarris2 -- the square of the 4-term
+ * Blackman-Harris window; SincFixedIn -- f_cutoff scaled by the ratio when downsampling.
+ * factor = L, so sub-filter p holds y[L*k + (L-1-p)]... here indexed directly by the fractional
+ * position: h[p][k] = y at tau = (k - half + 1) - p/L input samples from the interpolation point. */
+static int gcd_i(int a, int b) {
+  while (b) {
+    int t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+static int sinc_ratio(int input_rate, int output_rate, int *L, int *M) {
+  if (input_rate < 1 || output_rate < 1) return 0;
+  int g = gcd_i(input_rate, output_rate);
+  *L = output_rate / g;
+  *M = input_rate / g;
+  return *L <= 1024;
+}
+static double bh2_window(double x, double tot) { /* x in [0, tot) */
+  const double PI = 3.14159265358979323846;
+  double a = 2.0 * PI * x / tot;
+  double w = 0.35875 - 0.48829 * cos(a) + 0.14128 * cos(2.0 * a) - 0.01168 * cos(3.0 * a);
+  return w * w;
+}
+static int sinc_build(int L, int M, int sinc_len, float f_cutoff, float *table) {
+  const double PI = 3.14159265358979323846;
+  double fc = (double)f_cutoff;
+  if (L < M) fc = fc * (double)L / (double)M;
+  const long tot = (long)sinc_len * L;
+  double *y = (double *)malloc(sizeof(double) * (size_t)tot);
+  if (!y) return 0;
+  double sum = 0.0;
+  for (long x = 0; x < tot; x++) {
+    double t = ((double)x - (double)(tot / 2)) * fc / (double)L;
+    double s = t == 0.0 ? 1.0 : sin(PI * t) / (PI * t);
+    y[x] = bh2_window((double)x, (double)tot) * s;
+    sum += y[x];
+  }
+  sum /= (double)L;
+  /* tau = (k - half + 1) - p/L  <=>  x = tot/2 + tau*L = L*(k + 1) - p   (x == tot -> tap is 0) */
+  for (int p = 0; p < L; p++)
+    for (int k = 0; k < sinc_len; k++) {
+      long x = (long)L * (k + 1) - p;
+      table[(size_t)p * sinc_len + k] = x < tot ? (float)(y[x] / sum) : 0.0f;
+    }
+  free(y);
+  return 1;
+}
+int rno_sinc_table(int input_rate, int output_rate, int sinc_len, float f_cutoff, float *table,
+                   size_t cap_floats, int *M_out) {
+  int L, M;
+  if (!sinc_ratio(input_rate, output_rate, &L, &M) || sinc_len < 2 || (sinc_len & 1)) return 0;
+  if (cap_floats < (size_t)L * sinc_len) return 0;
+  if (!sinc_build(L, M, sinc_len, f_cutoff, table)) return 0;
+  if (M_out) *M_out = M;
+  return L;
+}
+size_t rno_sinc_resample_count(int input_rate, int output_rate, size_t n_in) {
+  int L, M;
+  if (!sinc_ratio(input_rate, output_rate, &L, &M)) return 0;
+  /* every n with n*M/L < n_in */
+  return (size_t)(((unsigned long long)n_in * L + M - 1) / M);
+}
+size_t rno_sinc_resample(const float *in, size_t n_in, float *out, size_t out_cap, int input_rate,
+                         int output_rate, int sinc_len, float f_cutoff) {
+  int L, M;
+  if (!sinc_ratio(input_rate, output_rate, &L, &M) || sinc_len < 2 || (sinc_len & 1)) return 0;
+  size_t n_out = rno_sinc_resample_count(input_rate, output_rate, n_in);
+  if (!out) return n_out;
+  if (n_out > out_cap) n_out = out_cap;
+  float *h = (float *)malloc(sizeof(float) * (size_t)L * sinc_len);
+  if (!h || !sinc_build(L, M, sinc_len, f_cutoff, h)) {
+    free(h);
+    return 0;
+  }
+  const long half = sinc_len / 2;
+  for (size_t n = 0; n < n_out; n++) {
+    unsigned long long pos = (unsigned long long)n * M;
+    long base = (long)(pos / L);
+    int p = (int)(pos % L);
+    const float *hp = h + (size_t)p * sinc_len;
+    float acc = 0.f;
+    for (int k = 0; k < sinc_len; k++) {
+      long i = base - half + 1 + k;
+      float x = (i >= 0 && (size_t)i < n_in) ? in[i] : 0.f;
+      acc = fmaf(hp[k], x, acc);
+    }
+    out[n] = acc;
+  }
+  free(h);
+  return n_out;
+}

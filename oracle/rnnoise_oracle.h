@@ -92,6 +92,25 @@ size_t rno_processor_run(const rno_model *m, float input_rate, float volume, con
  * out is interleaved stereo i16, both channels = trunc(clamp(mic+app,-1,1)*32767). */
 void rno_mix_dual_mono_i16(const float *mic, const float *app, size_t n, int16_t *out_interleaved);
 
+/* f2 (north_star item 4): windowed-sinc polyphase resampler, "rubato-equivalent" front end.  The
+ * reference itself only uses a linear interpolator on this path (audio.rs:108-133); rubato 0.16.2
+ * (Cargo.lock:4166) appears in the tree as FftFixedIn ahead of transcription
+ * (commands/transcription.rs:201-207).  This restates rubato's published synchronous sinc design
+ * (SincFixedIn: make_sincs + BlackmanHarris2 window, sinc_len taps, f_cutoff relative to Nyquist,
+ * cutoff scaled by the ratio when downsampling) with the oversampling factor set to L of the
+ * reduced ratio L/M = output_rate/input_rate, so every output lands exactly on a tabulated phase
+ * and no inter-phase interpolation is needed; delay-compensated (zero-phase), zeros outside
+ * [0, n_in).  PARITY UNPINNED like the rest of this file: no rubato source or vectors are available.
+ *   out[n] = sum_{k<sinc_len} h[(n*M) % L][k] * in[floor(n*M/L) - sinc_len/2 + 1 + k]
+ * accumulated in f32 with fmaf in ascending k.  Returns samples written (<= out_cap); count only
+ * when out == NULL.  Returns 0 for unsupported ratios (L > 1024) or bad sinc_len. */
+size_t rno_sinc_resample_count(int input_rate, int output_rate, size_t n_in);
+size_t rno_sinc_resample(const float *in, size_t n_in, float *out, size_t out_cap, int input_rate,
+                         int output_rate, int sinc_len, float f_cutoff);
+/* the polyphase table itself ([L][sinc_len] f32) for known-answer tests; returns L, or 0 */
+int rno_sinc_table(int input_rate, int output_rate, int sinc_len, float f_cutoff, float *table,
+                   size_t cap_floats, int *M_out);
+
 /* tables exposed for known-answer tests */
 const float *rno_half_window(void);  /* 480 */
 const float *rno_dct_table(void);    /* 22*22 */

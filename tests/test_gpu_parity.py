@@ -176,6 +176,57 @@ def test_config3_441k_front_end(oracle_model, model):
         assert np.max(np.abs(out[s].cpu().numpy() - ref)) <= 1e-3
 
 
+def test_sinc_resample_is_bit_exact():  # north_star item 4; oracle: rno_sinc_resample
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((3, 44100 + 17)).astype(np.float32)
+    for rin, rout in ((44100, 48000), (48000, 44100), (16000, 48000), (48000, 16000), (22050, 48000), (48000, 8000)):
+        y = cb.sinc_resample(_dev(x), rin, rout).cpu().numpy()
+        for s in range(3):
+            want = po.sinc_resample(x[s], rin, rout)
+            assert y.shape[1] == len(want)
+            assert np.array_equal(y[s], want), (rin, rout, np.abs(y[s] - want).max())
+    # ragged edges: shorter than the filter, a single sample, other filter lengths, strided rows
+    for n_in in (1, 5, 127, 441, 442):
+        y = cb.sinc_resample(_dev(x[:, :n_in]), 44100, 48000).cpu().numpy()
+        assert np.array_equal(y[1], po.sinc_resample(x[1, :n_in], 44100, 48000))
+    y = cb.sinc_resample(_dev(x)[:, 100:5000], 44100, 48000, sinc_len=64, f_cutoff=0.9).cpu().numpy()
+    assert np.array_equal(y[2], po.sinc_resample(x[2, 100:5000], 44100, 48000, 64, 0.9))
+
+
+def test_sinc_resample_properties_at_full_size():
+    """configs[2] geometry (1,024 streams x 10 s at 44.1 kHz): linearity in the input, exactly one frame
+    per 441 samples, and time-shift invariance by whole periods (147 in -> 160 out)."""
+    n_streams, n_in = 1024, 441000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn((n_streams, n_in), device="cuda", generator=g)
+    b = torch.randn((n_streams, n_in), device="cuda", generator=g)
+    ya, yb, yab = (cb.sinc_resample(t, 44100, 48000) for t in (a, b, a + b))
+    assert ya.shape == (n_streams, 480000)
+    assert float((yab - (ya + yb)).abs().max()) < 2e-5
+    shifted = cb.sinc_resample(a[:, 147 * 5:], 44100, 48000)
+    assert torch.equal(shifted[:, 200:-200], ya[:, 160 * 5 + 200:-200])
+    # a 1 kHz tone comes out as a 1 kHz tone
+    t = torch.arange(n_in, device="cuda", dtype=torch.float64) / 44100.0
+    tone = (0.5 * torch.sin(2 * np.pi * 1000.0 * t)).float()[None, :].contiguous()
+    yt = cb.sinc_resample(tone, 44100, 48000)[0].double()
+    want = 0.5 * torch.sin(2 * np.pi * 1000.0 * torch.arange(480000, device="cuda", dtype=torch.float64) / 48000.0)
+    assert float((yt - want)[400:-400].abs().max()) < 2e-5
+
+
+def test_config3_441k_sinc_front_end(oracle_model, model):
+    """configs[2] as north_star words it: 44.1 kHz input, sinc resample to 48 kHz ahead of the analysis."""
+    x44 = (synth_chunk(4, 44100 * 2).numpy()).astype(np.float32)
+    den = cb.BatchDenoiser(4, model)
+    out, vad = den.process_streams(_dev(x44), unit_scale=True, input_rate=44100, front_end="sinc")
+    assert out.shape[1] == 200 * 480
+    for s in range(4):
+        y48 = po.sinc_resample(x44[s], 44100, 48000)
+        ref, rvad = po.process_streams(oracle_model, y48[None, :], unit_scale=True)
+        o = out[s].cpu().numpy()
+        assert np.max(np.abs(o - ref[0])) <= 1e-3 and snr_db(ref[0], o) >= 60, f"sinc front end, stream {s}"
+        assert np.max(np.abs(vad[s].cpu().numpy() - rvad[0])) <= 1e-3
+
+
 def test_full_size_properties(model):
     """configs[1] geometry (1,024 streams) on a 6 s slice: results must not depend on the
     engine's chunk size or on how the caller splits the recording, silence must reconstruct exactly, and nothing may be NaN."""

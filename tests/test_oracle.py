@@ -172,3 +172,67 @@ def test_golden_regression(oracle_model):
     assert np.array_equal(vad[0], g["vad"])
     _, taps = po.debug_trace(oracle_model, x)
     assert [t["pitch_index"] for t in taps] == g["pitch_index"].tolist()
+
+
+# ---- f2 / north_star item 4: windowed-sinc front end (rubato-equivalent; rubato 0.16.2, Cargo.lock:4166) ----
+def test_sinc_table_is_a_normalised_symmetric_lowpass():
+    h, M = po.sinc_table(44100, 48000)
+    assert h.shape == (160, 256) and M == 147
+    # make_sincs normalisation: all taps sum to the oversampling factor, every phase has ~unit DC gain
+    assert abs(float(h.astype(np.float64).sum()) - 160.0) < 1e-3
+    assert np.abs(h.astype(np.float64).sum(axis=1) - 1.0).max() < 1e-4
+    # phase 0 is symmetric about the interpolation point; phase p mirrors phase L-p
+    assert np.allclose(h[0, :255], h[0, :255][::-1], atol=1e-9)
+    assert np.allclose(h[1, :], h[159, ::-1], atol=1e-9)
+    # cutoff 0.95 x Nyquist of the input: the prototype passes 0.8 and stops 1.15 (units of input Nyquist)
+    proto = np.zeros(160 * 256)
+    for p in range(160):
+        proto[160 * (np.arange(256) + 1) - p - 1] = h[p]
+    w = np.fft.rfftfreq(1 << 18) * 2 * 160  # in units of the input Nyquist
+    H = np.abs(np.fft.rfft(proto, 1 << 18)) / 160.0
+    assert np.abs(H[w < 0.8] - 1.0).max() < 1e-3
+    assert H[(w > 1.15) & (w < 20)].max() < 1e-5
+
+
+def test_sinc_resample_counts_and_frame_alignment():
+    # 441 samples at 44.1 kHz are exactly one 480-sample frame at 48 kHz
+    for frames in (1, 2, 7):
+        assert len(po.sinc_resample(np.zeros(441 * frames, np.float32), 44100, 48000)) == 480 * frames
+    assert len(po.sinc_resample(np.zeros(300, np.float32), 48000, 16000)) == 100
+    assert len(po.sinc_resample(np.zeros(100, np.float32), 16000, 48000)) == 300
+    assert len(po.sinc_resample(np.zeros(0, np.float32), 44100, 48000)) == 0
+    assert len(po.sinc_resample(np.zeros(1, np.float32), 44100, 48000)) == 2
+
+
+def test_sinc_resample_matches_scipy_polyphase():
+    from scipy.signal import upfirdn
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(3000).astype(np.float32)
+    for rin, rout in ((44100, 48000), (48000, 44100), (16000, 48000), (48000, 16000)):
+        h, M = po.sinc_table(rin, rout)
+        L = h.shape[0]
+        proto = np.zeros(L * 256)
+        for p in range(L):
+            proto[L * (np.arange(256) + 1) - p - 1] = h[p]  # tap at x = L*(k+1) - p, stored from x = 1
+        # out[n] = sum_i x[i] * g(n*M - i*L) with g centred at x = L*128: upfirdn delay = L*128 - 1
+        full = upfirdn(proto, x.astype(np.float64), up=L, down=1)
+        y = po.sinc_resample(x, rin, rout)
+        ref = full[L * 128 - 1 + M * np.arange(len(y))]
+        assert np.abs(y - ref).max() < 2e-5 * max(1.0, np.abs(ref).max()), (rin, rout)
+
+
+def test_sinc_resample_reconstructs_a_tone_and_beats_linear():
+    n = 44100
+    t = np.arange(n) / 44100.0
+    x = (0.5 * np.sin(2 * np.pi * 5000.0 * t)).astype(np.float32)
+    y = po.sinc_resample(x, 44100, 48000)
+    want = 0.5 * np.sin(2 * np.pi * 5000.0 * np.arange(len(y)) / 48000.0)
+    mid = slice(400, len(y) - 400)
+    err_sinc = np.abs(y[mid] - want[mid]).max()
+    assert err_sinc < 2e-5  # f32 accumulation over 256 taps
+    lin = po.linear_resample(x, 44100.0, 48000.0)
+    k = min(len(lin), len(want)) - 400
+    # the reference's linear interpolator (audio.rs:108-133) starts one input sample late and smears a 5 kHz tone
+    best = min(np.abs(lin[400:k] - 0.5 * np.sin(2 * np.pi * 5000.0 * (np.arange(400, k) / 48000.0 + d / 44100.0))).max()
+               for d in (0.0, 1.0))
+    assert best > 100 * err_sinc
