@@ -349,8 +349,9 @@ def run_b200(args):
     front_end = None
     if rank == 0 and not args.no_front_end:
         fe_secs = 10
-        x44 = torch.empty((n_streams, 44100 * fe_secs), dtype=torch.float32, device=dev)
-        x44.copy_(x[:, :44100 * fe_secs])  # any signal will do: the kernels are data-independent
+        x44 = torch.zeros((n_streams, 44100 * fe_secs), dtype=torch.float32, device=dev)
+        n_cp = min(x.shape[1], x44.shape[1])
+        x44[:, :n_cp].copy_(x[:, :n_cp])  # any signal will do: the kernels are data-independent
         front_end = {"input": f"{n_streams} streams x {fe_secs} s at 44.1 kHz -> 48 kHz, device-resident, kernel alone"}
         for name, fn, flops in (("sinc256", lambda: cb.sinc_resample(x44, 44100, 48000), 2 * 256),
                                 ("linear", lambda: cb.linear_resample(x44, 44100.0, 48000.0), 3)):

@@ -503,6 +503,10 @@ int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_strea
   b->n_streams = n_streams;
   b->n_sms = prop.multiProcessorCount;
   b->chunk_cap = default_chunk_cap(n_streams);
+  if ((long long)n_streams * b->chunk_cap >= (1ll << 31)) {  // the task-loop kernels index (stream, frame) in 32 bits
+    delete b;
+    return fail(CRISPY_NS_EINVAL, "batch_create: n_streams x chunk frames must stay below 2^31");
+  }
   if (cudaError_t ce = configure_kernels(device); ce != cudaSuccess) {
     delete b;
     return fail(CRISPY_NS_ECUDA, std::string("batch_create: ") + cudaGetErrorString(ce));

@@ -1104,25 +1104,57 @@ NS_DEV void irfft960_inplace(const Grp &g, const Tables &T, cf *X) {
   fft480(g, T, X, from_buf);
 }
 
-// a8: 22 triangular bands over bins 0..400.  88 threads: band = tid/4, four lanes split the bins of
-// the two intervals that touch the band; triangular weights come from the bin_frac table.  NQ
-// quantities are accumulated in one pass.  Results are valid in lanes with (tid & 3) == 0, tid < 88.
+// a8: 22 triangular bands over bins 0..400.  Every band edge is a multiple of four bins, so bins
+// 4s..4s+3 ("slot" s < 100, = one eband5ms unit) lie in one interval between two band centres.
+// band_slots: thread s < 100 visits its four bins once, for NQ quantities at a time, and leaves the
+// interval's two triangular partial sums (weight 1-f towards the lower band, f towards the upper one)
+// in part[2q][s], part[2q+1][s].  band_reduce (after a group barrier): 88 threads, band = tid/4, four
+// lanes add the partials of the two intervals that touch the band in a fixed order; results are valid
+// in lanes with (tid & 3) == 0, tid < 88.
+constexpr int kSlots = 100;
+constexpr int kPartStride = 104;
 template <int NQ, class BinVal>
-NS_DEV void band_accumulate(const Grp &g, const Tables &T, BinVal val, float (&acc)[NQ]) {
+NS_DEV void band_slots(const Grp &g, const Tables &T, float *part, BinVal val) {
+  if (g.tid < kSlots) {
+    const int k0 = 4 * g.tid;
+    const f4 fr4 = ld4(T.bin_frac + k0);
+    const float fr[4] = {fr4.x, fr4.y, fr4.z, fr4.w};
+    float s0[NQ], s1[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) s0[q] = s1[q] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      float v[NQ];
+      val(k0 + u, v);
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        s0[q] += v[q];
+        s1[q] = fmaf(fr[u], v[q], s1[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      part[(2 * q) * kPartStride + g.tid] = s0[q] - s1[q];
+      part[(2 * q + 1) * kPartStride + g.tid] = s1[q];
+    }
+  }
+}
+template <int NQ>
+NS_DEV void band_reduce(const Grp &g, const Tables &T, const float *part, float (&acc)[NQ]) {
 #pragma unroll
   for (int q = 0; q < NQ; q++) acc[q] = 0.f;
   const int b = g.tid >> 2, sub = g.tid & 3;
   if (g.tid < 4 * kBands) {
-    const int lo = (b >= 1) ? T.eband[b - 1] : 0;
-    const int mid = T.eband[b];
-    const int hi = (b <= kBands - 2) ? T.eband[b + 1] : mid;
-    for (int k = lo + sub; k < hi; k += 4) {
-      const float f = T.bin_frac[k];
-      const float w = (k < mid) ? f : 1.f - f;
-      float v[NQ];
-      val(k, v);
+    const int lo = (b >= 1) ? (T.eband[b - 1] >> 2) : 0;  // slots
+    const int mid = T.eband[b] >> 2;
+    const int hi = (b <= kBands - 2) ? (T.eband[b + 1] >> 2) : mid;
+    for (int sl = mid + sub; sl < hi; sl += 4) {  // interval b: this band is its lower one
 #pragma unroll
-      for (int q = 0; q < NQ; q++) acc[q] = fmaf(w, v[q], acc[q]);
+      for (int q = 0; q < NQ; q++) acc[q] += part[(2 * q) * kPartStride + sl];
+    }
+    for (int sl = lo + sub; sl < mid; sl += 4) {  // interval b-1: this band is its upper one
+#pragma unroll
+      for (int q = 0; q < NQ; q++) acc[q] += part[(2 * q + 1) * kPartStride + sl];
     }
   }
 #pragma unroll
@@ -1139,6 +1171,7 @@ struct SpecSmem {
   cf P[482];
   float Ex[24], Ep[24], Exp[24], Ly[24], g[24], graw[24], r[24], nrm[24], newE[24];
   float synth[kFrame];
+  float part[6 * kPartStride];  // band_slots -> band_reduce
   int pitch_index, silence;
 };
 
@@ -1152,13 +1185,15 @@ NS_DEV void load_tables(const Params &p, Tables &dst, int tid, int nthr) {
 NS_DEV void frame_spectra(const Grp &g, const Tables &T, SpecSmem &s, const float *hp_row, int t, int pitch_index) {
   const float *cur = hp_row + kHist - kFrame + (long long)t * kFrame;  // [analysis_mem | frame]
   rfft960_windowed2(g, T, cur, cur - pitch_index, s.X, s.P);
-  float acc[3];
-  band_accumulate<3>(g, T, [&](int k, float (&v)[3]) {
+  band_slots<3>(g, T, s.part, [&](int k, float (&v)[3]) {
     const cf x = s.X[k], p = s.P[k];
     v[0] = fmaf(x.x, x.x, x.y * x.y);
     v[1] = fmaf(p.x, p.x, p.y * p.y);
     v[2] = fmaf(x.x, p.x, x.y * p.y);
-  }, acc);
+  });
+  gsync(g);
+  float acc[3];
+  band_reduce<3>(g, T, s.part, acc);
   if (g.tid < 4 * kBands && (g.tid & 3) == 0) {
     s.Ex[g.tid >> 2] = acc[0];
     s.Ep[g.tid >> 2] = acc[1];
@@ -1180,19 +1215,17 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
   Simt::cta_sync();
   const Tables &T = s.tab;
   const float dct_scale = 0.30151134457776363f;  // sqrt(2/22)
-  const long long n_tasks = (long long)p.n_streams * p.n_frames;
-  for (long long task = Simt::cta(); task < n_tasks; task += Simt::n_ctas()) {
-    const int stream = (int)(task / p.n_frames), t = (int)(task - (long long)stream * p.n_frames);
+  const int n_tasks = p.n_streams * p.n_frames;  // < 2^31: checked on the host
+  for (int task = Simt::cta(); task < n_tasks; task += Simt::n_ctas()) {
+    const int stream = task / p.n_frames, t = task - stream * p.n_frames;
     const long long fidx = (long long)stream * p.chunk_cap + t;
     float *rec = p.rec + fidx * kRecFloats;
     const int pitch_index = reinterpret_cast<const int *>(rec)[kRecPitchIndex];
     frame_spectra(g, T, s, p.hp + (long long)stream * p.hp_stride, t, pitch_index);
     {  // spectra -> workspace (K5 reads them back instead of redoing two FFTs)
-      cf *dst = p.spec + fidx * (2 * kSpecStride);
-      for (int k = g.tid; k < kFreq; k += kGroupThreads) {
-        dst[k] = s.X[k];
-        dst[kSpecStride + k] = s.P[k];
-      }
+      f4 *dst4 = reinterpret_cast<f4 *>(p.spec + fidx * (2 * kSpecStride));
+      const f4 *src4 = reinterpret_cast<const f4 *>(s.X);  // X[482] and P[482] are contiguous: 482 float4
+      for (int k = g.tid; k < kSpecStride; k += kGroupThreads) dst4[k] = src4[k];
     }
     if (g.tid < kBands) {
       const int i = g.tid;
@@ -1729,12 +1762,6 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
 // K5: a15 pitch filter + gain interpolation, a16 synthesis; one 128-thread group per stream walks
 // the chunk's frames carrying synthesis_mem in shared memory
 // =================================================================================================
-NS_DEV float interp_band(const Tables &T, const float *v, int k) {  // k < 400
-  const int b = T.bin_band[k];
-  const float f = T.bin_frac[k];
-  return (1.f - f) * v[b] + f * v[b + 1];
-}
-
 NS_DEV void pitch_filter_and_gains(const Grp &g, const Tables &T, SpecSmem &s) {
   if (g.tid < kBands) {
     const int i = g.tid;
@@ -1749,65 +1776,138 @@ NS_DEV void pitch_filter_and_gains(const Grp &g, const Tables &T, SpecSmem &s) {
     s.r[i] = r;
   }
   gsync(g);
-  for (int k = g.tid; k < 400; k += kGroupThreads) {
-    const float rf = interp_band(T, s.r, k);
-    s.X[k].x += rf * s.P[k].x;
-    s.X[k].y += rf * s.P[k].y;
+  // slot pass (four bins of one band interval per thread): X += rf P, and the filtered spectrum's band
+  // energy partials in the same sweep
+  if (g.tid < kSlots) {
+    const int k0 = 4 * g.tid, b = T.bin_band[k0];
+    const f4 fr4 = ld4(T.bin_frac + k0);
+    const float fr[4] = {fr4.x, fr4.y, fr4.z, fr4.w};
+    const float r0 = s.r[b], r1 = s.r[b + 1];
+    f4 *X4 = reinterpret_cast<f4 *>(s.X + k0);
+    const f4 *P4 = reinterpret_cast<const f4 *>(s.P + k0);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      f4 x = X4[h];
+      const f4 pp = P4[h];
+      const float rfa = (1.f - fr[2 * h]) * r0 + fr[2 * h] * r1, rfb = (1.f - fr[2 * h + 1]) * r0 + fr[2 * h + 1] * r1;
+      x.x += rfa * pp.x;
+      x.y += rfa * pp.y;
+      x.z += rfb * pp.z;
+      x.w += rfb * pp.w;
+      X4[h] = x;
+      const float va = fmaf(x.x, x.x, x.y * x.y), vb = fmaf(x.z, x.z, x.w * x.w);
+      s0 += va;
+      s1 = fmaf(fr[2 * h], va, s1);
+      s0 += vb;
+      s1 = fmaf(fr[2 * h + 1], vb, s1);
+    }
+    s.part[g.tid] = s0 - s1;
+    s.part[kPartStride + g.tid] = s1;
   }
   gsync(g);
   {
     float e[1];
-    band_accumulate<1>(g, T, [&](int k, float (&v)[1]) { v[0] = fmaf(s.X[k].x, s.X[k].x, s.X[k].y * s.X[k].y); }, e);
-    if (g.tid < 4 * kBands && (g.tid & 3) == 0) s.newE[g.tid >> 2] = e[0];
-  }
-  gsync(g);
-  if (g.tid < kBands) {
-    const int i = g.tid;
-    s.nrm[i] = (float)sqrt((double)s.Ex[i] / (1e-8 + (double)s.newE[i]));
-  }
-  gsync(g);
-  for (int k = g.tid; k < kFreq; k += kGroupThreads) {
-    if (k < 400) {
-      const float nf = interp_band(T, s.nrm, k), gf = interp_band(T, s.g, k);
-      s.X[k].x = (s.X[k].x * nf) * gf;
-      s.X[k].y = (s.X[k].y * nf) * gf;
-    } else {
-      s.X[k] = cf{0.f, 0.f};
+    band_reduce<1>(g, T, s.part, e);
+    if (g.tid < 4 * kBands && (g.tid & 3) == 0) {
+      const int i = g.tid >> 2;
+      s.nrm[i] = (float)sqrt((double)s.Ex[i] / (1e-8 + (double)e[0]));
     }
   }
   gsync(g);
+  if (g.tid < kSlots) {
+    const int k0 = 4 * g.tid, b = T.bin_band[k0];
+    const f4 fr4 = ld4(T.bin_frac + k0);
+    const float fr[4] = {fr4.x, fr4.y, fr4.z, fr4.w};
+    const float n0 = s.nrm[b], n1 = s.nrm[b + 1], g0 = s.g[b], g1 = s.g[b + 1];
+    f4 *X4 = reinterpret_cast<f4 *>(s.X + k0);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      f4 x = X4[h];
+      const float fa = fr[2 * h], fb = fr[2 * h + 1];
+      const float nfa = (1.f - fa) * n0 + fa * n1, gfa = (1.f - fa) * g0 + fa * g1;
+      const float nfb = (1.f - fb) * n0 + fb * n1, gfb = (1.f - fb) * g0 + fb * g1;
+      x.x = (x.x * nfa) * gfa;
+      x.y = (x.y * nfa) * gfa;
+      x.z = (x.z * nfb) * gfb;
+      x.w = (x.w * nfb) * gfb;
+      X4[h] = x;
+    }
+  } else {
+    for (int k = 400 + (g.tid - kSlots); k < kFreq; k += kGroupThreads - kSlots) s.X[k] = cf{0.f, 0.f};
+  }
+  gsync(g);
 }
+
+// a16 tail + the fused output conversions.  Thread i handles samples 4i..4i+3 (one 16-byte shared-memory
+// access per operand); the caller's buffers are written with 16 / 8-byte stores when their base and
+// stride allow it (any torch tensor does), else sample by sample.
+NS_DEV float out_unit(const Params &p, float o) { return fminf(1.f, fmaxf(-1.f, o / 32768.0f)) * p.volume; }
+NS_DEV int16_t out_i16(float o) {
+  float v = rintf(o);
+  v = fminf(32767.f, fmaxf(-32768.f, v));
+  return (int16_t)(int)v;
+}
+NS_DEV int16_t out_mix(const Params &p, float o, float app) {
+  float mixed = out_unit(p, o) + app;
+  mixed = fminf(1.f, fmaxf(-1.f, mixed));
+  return (int16_t)(int)(mixed * 32767.0f);  // truncation toward zero, as Rust `as i16`
+}
+NS_DEV uint32_t pack16(int16_t lo, int16_t hi) { return (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16); }
 
 NS_DEV void store_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem &s, int stream, int t_call) {
   // X holds z[m] with x[2m] = z.x, x[2m+1] = -z.y.  out[i] = x[i] w[i] + synth[i]; synth = x[480+i] w[479-i]
   const int slot = t_call + p.out_frame_offset;
   const float *zb = reinterpret_cast<const float *>(s.X);
-  for (int i = g.tid; i < kFrame; i += kGroupThreads) {
-    const float x0 = (i & 1) ? -zb[i] : zb[i];
-    const float x1 = (i & 1) ? -zb[kFrame + i] : zb[kFrame + i];
-    const float o = x0 * T.win[i] + s.synth[i];
-    s.synth[i] = x1 * T.win[kFrame - 1 - i];
-    if (slot >= 0) {
-      const long long o_off = (long long)stream * p.out_stride + (long long)slot * kFrame + i;
-      if (p.flags & kFlagMixStereoI16) {
-        float dn = o / 32768.0f;
-        dn = fminf(1.f, fmaxf(-1.f, dn)) * p.volume;
-        float mixed = dn;
-        if (p.app) mixed += p.app[(long long)stream * p.app_stride + (long long)slot * kFrame + i];
-        mixed = fminf(1.f, fmaxf(-1.f, mixed));
-        const int16_t q = (int16_t)(int)(mixed * 32767.0f);  // truncation toward zero, as Rust `as i16`
-        int16_t *dst = reinterpret_cast<int16_t *>(p.out) + 2 * o_off;
-        dst[0] = q;
-        dst[1] = q;
-      } else if (p.flags & kFlagOutI16) {
-        float v = rintf(o);
-        v = fminf(32767.f, fmaxf(-32768.f, v));
-        reinterpret_cast<int16_t *>(p.out)[o_off] = (int16_t)(int)v;
+  if (g.tid >= kFrame / 4) return;
+  const int i = 4 * g.tid;
+  const f4 za = ld4(zb + i), zc = ld4(zb + kFrame + i), wa = ld4(T.win + i), wr = ld4(T.win + kFrame - 4 - i);
+  const f4 sy = ld4(s.synth + i);
+  const float o[4] = {za.x * wa.x + sy.x, (-za.y) * wa.y + sy.y, za.z * wa.z + sy.z, (-za.w) * wa.w + sy.w};
+  *reinterpret_cast<f4 *>(s.synth + i) = f4{zc.x * wr.w, (-zc.y) * wr.z, zc.z * wr.y, (-zc.w) * wr.x};
+  if (slot < 0) return;
+  const long long o_off = (long long)stream * p.out_stride + (long long)slot * kFrame + i;
+  const bool vec_out = ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && ((p.out_stride & 3) == 0);
+  if (p.flags & kFlagMixStereoI16) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.app) {
+      const float *ap = p.app + (long long)stream * p.app_stride + (long long)slot * kFrame + i;
+      if (((reinterpret_cast<uintptr_t>(p.app) & 15) == 0) && ((p.app_stride & 3) == 0)) {
+        const f4 a4 = ld4(ap);
+        a[0] = a4.x, a[1] = a4.y, a[2] = a4.z, a[3] = a4.w;
       } else {
-        float v = o;
-        if (p.flags & kFlagUnitScale) v = fminf(1.f, fmaxf(-1.f, o / 32768.0f)) * p.volume;
-        reinterpret_cast<float *>(p.out)[o_off] = v;
+#pragma unroll
+        for (int u = 0; u < 4; u++) a[u] = ap[u];
       }
+    }
+    int16_t q[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) q[u] = out_mix(p, o[u], a[u]);
+    int16_t *dst = reinterpret_cast<int16_t *>(p.out) + 2 * o_off;
+    if (vec_out) {
+      *reinterpret_cast<u4 *>(dst) = u4{pack16(q[0], q[0]), pack16(q[1], q[1]), pack16(q[2], q[2]), pack16(q[3], q[3])};
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) dst[2 * u] = dst[2 * u + 1] = q[u];
+    }
+  } else if (p.flags & kFlagOutI16) {
+    int16_t *dst = reinterpret_cast<int16_t *>(p.out) + o_off;
+    if (vec_out) {
+      *reinterpret_cast<u2 *>(dst) = u2{pack16(out_i16(o[0]), out_i16(o[1])), pack16(out_i16(o[2]), out_i16(o[3]))};
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) dst[u] = out_i16(o[u]);
+    }
+  } else {
+    float *dst = reinterpret_cast<float *>(p.out) + o_off;
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = (p.flags & kFlagUnitScale) ? out_unit(p, o[u]) : o[u];
+    if (vec_out) {
+      *reinterpret_cast<f4 *>(dst) = f4{v[0], v[1], v[2], v[3]};
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) dst[u] = v[u];
     }
   }
 }
@@ -1822,9 +1922,12 @@ NS_DEV void synth_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem
   const float *rec = p.rec + fidx * kRecFloats;
   const bool silent = reinterpret_cast<const int *>(rec)[kRecSilence] != 0;
   const cf *src = p.spec + fidx * (2 * kSpecStride);
-  for (int k = g.tid; k < kFreq; k += kGroupThreads) {
-    s.X[k] = src[k];
-    if (!silent) s.P[k] = src[kSpecStride + k];
+  {  // X (and P unless silent) as 16-byte copies: kSpecStride cf = 241 float4 each, X and P contiguous on both sides
+    static_assert(kSpecStride % 2 == 0 && offsetof(SpecSmem, P) == offsetof(SpecSmem, X) + kSpecStride * sizeof(cf), "layout");
+    const f4 *src4 = reinterpret_cast<const f4 *>(src);
+    f4 *dst4 = reinterpret_cast<f4 *>(s.X);
+    const int n4 = silent ? kSpecStride / 2 : kSpecStride;
+    for (int k = g.tid; k < n4; k += kGroupThreads) dst4[k] = src4[k];
   }
   // the run's next frame is the next 7.7 KB of the same array: pull it into L2 while this one is worked on
   if (prefetch_next && g.tid * 128 < (int)(2 * kSpecStride * sizeof(cf)))
@@ -1871,9 +1974,9 @@ NS_DEV void synthesis_body(const Params &p, SpecSmem &s) {
   Simt::cta_sync();
   const Tables &T = s.tab;
   const int runs = (p.n_frames + kSynRun - 1) / kSynRun;
-  const long long n_tasks = (long long)p.n_streams * runs;
-  for (long long task = Simt::cta(); task < n_tasks; task += Simt::n_ctas()) {
-    const int stream = (int)(task / runs), t0 = (int)(task - (long long)stream * runs) * kSynRun;
+  const int n_tasks = p.n_streams * runs;  // < 2^31: checked on the host
+  for (int task = Simt::cta(); task < n_tasks; task += Simt::n_ctas()) {
+    const int stream = task / runs, t0 = (task - stream * runs) * kSynRun;
     const int t1 = (t0 + kSynRun < p.n_frames) ? t0 + kSynRun : p.n_frames;
     float *st = p.state + (long long)stream * kStateFloats;
     if (t0 == 0) {
