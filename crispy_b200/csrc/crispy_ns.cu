@@ -23,7 +23,12 @@
 #define NS_PITCH_RUN 8
 #endif
 constexpr int kPitchRun = NS_PITCH_RUN;  // frames of one stream per pitch CTA
-constexpr int kPitchThreads = (37 * kPitchRun + 31) / 32 * 32 + 32;  // 37 lag-quads per frame in the coarse search + one helper warp
+#ifdef NS_PITCH_THREADS
+constexpr int kPitchThreads = NS_PITCH_THREADS;
+#else
+constexpr int kPitchThreads = (37 * kPitchRun + 31) / 32 * 32 + 32;
+#endif
+//  // 37 lag-quads per frame in the coarse search + one helper warp
 constexpr int kScanWarps = 4;
 
 __global__ void __launch_bounds__(ns::kHpThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
@@ -148,6 +153,7 @@ struct crispy_ns_batch {
   int n_sms = 148;
   int spec_ctas_per_sm = 4, syn_ctas_per_sm = 4;  // resident CTAs of the two persistent task-loop kernels
   int chunk_cap = 0;  // frames per chunk
+  int syn_run_override = 0;  // $CRISPY_NS_SYN_RUN (tests: the result must not depend on it)
   int64_t launches = 0;
   int64_t frames_done = 0;
   int64_t chunks_done = 0;
@@ -355,8 +361,11 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
           ns_rnn_kernel<<<groups, ns::kMmaThreads, sizeof(ns::RnnSmem), sk>>>(p);
           break;
         default: {
-          long long ctas = (long long)n * ((nf + ns::kSynRun - 1) / ns::kSynRun);
-          if (ctas > (long long)b->n_sms * b->syn_ctas_per_sm) ctas = (long long)b->n_sms * b->syn_ctas_per_sm;
+          const int resident = b->n_sms * b->syn_ctas_per_sm;
+          p.syn_run = ns::pick_syn_run(n, nf, resident);
+          if (b->syn_run_override > 0) p.syn_run = b->syn_run_override < nf ? b->syn_run_override : nf;
+          long long ctas = (long long)n * ((nf + p.syn_run - 1) / p.syn_run);
+          if (ctas > resident) ctas = resident;
           ns_synthesis_kernel<<<(int)ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), sk>>>(p);
           break;
         }
@@ -503,6 +512,7 @@ int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_strea
   b->n_streams = n_streams;
   b->n_sms = prop.multiProcessorCount;
   b->chunk_cap = default_chunk_cap(n_streams);
+  if (const char *e = getenv("CRISPY_NS_SYN_RUN")) b->syn_run_override = atoi(e);
   if ((long long)n_streams * b->chunk_cap >= (1ll << 31)) {  // the task-loop kernels index (stream, frame) in 32 bits
     delete b;
     return fail(CRISPY_NS_EINVAL, "batch_create: n_streams x chunk frames must stay below 2^31");

@@ -218,6 +218,7 @@ struct Params {
   int chunk_cap;
   int synth_sel;          // which synthesis_mem copy this chunk reads (chunk counter & 1)
   int out_frame_offset;   // output frame t is stored at frame slot t + out_frame_offset (skipped if < 0)
+  int syn_run;            // K5: consecutive frames of one stream per task (>= 1; the host picks it per chunk)
   uint32_t flags;
   float volume;
 };

@@ -222,9 +222,9 @@ struct PitchSmem {
   float xx[R];
   float sb6[R][148];  // Syy before every coarse lag (helper warp, in the coarse search's shadow)
   int best0[R], best1[R], T0[R], nk[R];
-  // work lists of remove_doubling's inner products per window-alignment bucket: frame | lag << 3 | k << 12
+  // work lists of remove_doubling's inner products per window-alignment bucket: frame | lag << 5 | k << 14
   int n_tri[4], n_sgl[4];
-  uint16_t tri[4][R * 16], sgl[4][R * 16];  // <= 15 triples and <= 14 singles per frame
+  uint32_t tri[4][R * 16], sgl[4][R * 16];  // <= 15 triples and <= 14 singles per frame
   float dots[R][64];   // 0: T0-1, 1: T0+1; for k >= 2 at 2+4(k-2): T1-1, T1, T1+1, T1b
 };
 
@@ -674,13 +674,13 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     {
       const int bkt = (384 - Tc - 1) & 3;
       const int idx = Simt::atomic_add_shared(&sm.n_tri[bkt], 1);
-      sm.tri[bkt][idx] = (uint16_t)(f | (Tc << 3) | (k << 12));
+      sm.tri[bkt][idx] = (uint32_t)(f | (Tc << 5) | (k << 14));
     }
     if (k > 1) {
       const int T1b = rd_T1b(k, T0, Tc);
       const int bkt = (384 - T1b) & 3;
       const int idx = Simt::atomic_add_shared(&sm.n_sgl[bkt], 1);
-      sm.sgl[bkt][idx] = (uint16_t)(f | (T1b << 3) | (k << 12));
+      sm.sgl[bkt][idx] = (uint32_t)(f | (T1b << 5) | (k << 14));
     }
   }
   Simt::cta_sync();
@@ -714,7 +714,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
           const int bkt = job & 3, n = sm.n_tri[bkt];
           for (int it = (job >> 2) * 32 + lane; it < n; it += 64) {
             const int e = sm.tri[bkt][it];
-            const int f = e & 7, Tc = (e >> 3) & 0x1FF, k = e >> 12;
+            const int f = e & 31, Tc = (e >> 5) & 0x1FF, k = e >> 14;
             const float *row = sm.xlp + f * kLpStride;
             const float *ya = row + ((384 - Tc - 1) & ~3);
             float sp, sc, sm1;  // lags Tc+1, Tc, Tc-1
@@ -733,7 +733,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
           const int bkt = job - 8, n = sm.n_sgl[bkt];
           for (int it = lane; it < n; it += 32) {
             const int e = sm.sgl[bkt][it];
-            const int f = e & 7, lag = (e >> 3) & 0x1FF, k = e >> 12;
+            const int f = e & 31, lag = (e >> 5) & 0x1FF, k = e >> 14;
             const float *row = sm.xlp + f * kLpStride;
             const float *ya = row + ((384 - lag) & ~3);
             float sum;
@@ -1912,9 +1912,23 @@ NS_DEV void store_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem
   }
 }
 
-// One task = kSynRun consecutive frames of one stream.  A run that does not start the chunk first
-// re-synthesises the frame before it to recover synthesis_mem (the overlap-add halo).
-constexpr int kSynRun = 8;
+// One task = p.syn_run consecutive frames of one stream.  A run that does not start the chunk first
+// re-synthesises the frame before it to recover synthesis_mem (the overlap-add halo); the result does not
+// depend on the run length.  pick_syn_run (host): fewest task-loop rounds x frames per task, halo included.
+inline int pick_syn_run(int n_streams, int n_frames, int resident_ctas) {
+  int best = n_frames < 1 ? 1 : n_frames;
+  long long best_cost = -1;
+  for (int run = 1; run <= n_frames; run++) {
+    const long long tasks = (long long)n_streams * ((n_frames + run - 1) / run);
+    const long long rounds = (tasks + resident_ctas - 1) / resident_ctas;
+    const long long cost = rounds * (run + (run < n_frames ? 1 : 0));
+    if (best_cost < 0 || cost < best_cost || (cost == best_cost && run > best)) {
+      best_cost = cost;
+      best = run;
+    }
+  }
+  return best;
+}
 
 NS_DEV void synth_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem &s, int stream, int t, bool halo,
                         bool prefetch_next) {
@@ -1973,11 +1987,12 @@ NS_DEV void synthesis_body(const Params &p, SpecSmem &s) {
   load_tables(p, s.tab, g.tid, kGroupThreads);
   Simt::cta_sync();
   const Tables &T = s.tab;
-  const int runs = (p.n_frames + kSynRun - 1) / kSynRun;
+  const int run = p.syn_run;
+  const int runs = (p.n_frames + run - 1) / run;
   const int n_tasks = p.n_streams * runs;  // < 2^31: checked on the host
   for (int task = Simt::cta(); task < n_tasks; task += Simt::n_ctas()) {
-    const int stream = task / runs, t0 = (task - stream * runs) * kSynRun;
-    const int t1 = (t0 + kSynRun < p.n_frames) ? t0 + kSynRun : p.n_frames;
+    const int stream = task / runs, t0 = (task - stream * runs) * run;
+    const int t1 = (t0 + run < p.n_frames) ? t0 + run : p.n_frames;
     float *st = p.state + (long long)stream * kStateFloats;
     if (t0 == 0) {
       for (int i = g.tid; i < kFrame; i += kGroupThreads) s.synth[i] = st[kStSynth + p.synth_sel * kFrame + i];

@@ -160,7 +160,8 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
     if (rc) return rc;
     rc = launch(groups, ns::kMmaThreads, sizeof(ns::RnnSmem), [&](void *sm) { ns::rnn_body(p, *(ns::RnnSmem *)sm); });
     if (rc) return rc;
-    const int syn_tasks = n_streams * ((nf + ns::kSynRun - 1) / ns::kSynRun);
+    p.syn_run = nf > 5 ? 5 : nf;  // a run length that leaves a ragged last run and exercises the halo path
+    const int syn_tasks = n_streams * ((nf + p.syn_run - 1) / p.syn_run);
     rc = launch(syn_tasks < 3 ? syn_tasks : 3, ns::kGroupThreads, sizeof(ns::SpecSmem),
                 [&](void *sm) { ns::synthesis_body(p, *(ns::SpecSmem *)sm); });
     if (rc) return rc;

@@ -85,6 +85,16 @@ def test_chunk_size_variants_agree(model, chunk, monkeypatch):
     assert torch.equal(a, b) and torch.equal(va, vb)
 
 
+def test_synthesis_run_length_does_not_change_results(model, monkeypatch):
+    """K5 splits a chunk into runs of frames per task (halo = one re-synthesised frame); any split gives the same bits."""
+    x = _dev(make_signal(7, 70))
+    base, bv = cb.BatchDenoiser(7, model).process_streams(x, unit_scale=False)
+    for run in (1, 3, 8, 1000):
+        monkeypatch.setenv("CRISPY_NS_SYN_RUN", str(run))
+        out, vad = cb.BatchDenoiser(7, model).process_streams(x, unit_scale=False)
+        assert torch.equal(out, base) and torch.equal(vad, bv), run
+
+
 def test_chunking_save_load_and_reset_are_bit_exact(model):
     x = _dev(make_signal(11, 64))
     den = cb.BatchDenoiser(11, model)
