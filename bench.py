@@ -372,7 +372,41 @@ def run_b200(args):
                                "fp32_tflops": n_streams * n_out * flops / sec / 1e12}
         front_end["sinc256"]["frac_fp32_nominal"] = front_end["sinc256"]["fp32_tflops"] / FP32_PEAK_TFLOPS_NOMINAL
         front_end["linear"]["frac_hbm"] = front_end["linear"]["hbm_algorithmic_gbs"] / measured_peaks()[0]
-        del x44, y48
+        del y48
+        # ---- the other BASELINE.json configs on the same streams, 10 s each, device-resident (rank 0) ----
+        def timed(fn, reps=2):
+            fn()
+            torch.cuda.synchronize(dev)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b_.record()
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b_) / 1e3 / reps
+
+        nf10 = min(n_frames, fe_secs * 100)
+
+        def c3():
+            den.reset_async()
+            den.process_streams(x44[:, :441 * nf10], unit_scale=True, input_rate=44100, front_end="sinc")
+
+        xi16 = (x[:, :nf10 * FRAME] * 32767.0).round().clamp(-32768, 32767).to(torch.int16)
+        app = torch.roll(x[:, :nf10 * FRAME], 1, 0) * 0.5
+        mix = torch.empty((n_streams, nf10 * FRAME, 2), dtype=torch.int16, device=dev)
+
+        def c4():
+            den.reset_async()
+            den.process_streams(xi16, unit_scale=True, app=app, mix_stereo_i16=True, out=mix)
+
+        front_end["configs"] = {
+            "c3_441k_sinc_then_denoise": {"stream_seconds_per_s": n_streams * nf10 / 100.0 / timed(c3),
+                                          "what": "configs[2]: 44.1 kHz f32 in -> sinc256 -> denoise -> 48 kHz f32 out"},
+            "c4_mic_i16_plus_app_to_stereo_pcm16": {"stream_seconds_per_s": n_streams * nf10 / 100.0 / timed(c4),
+                                                    "what": "configs[3] per meeting: mic PCM16 denoised + raw app f32, "
+                                                            "clamp(mic+app) -> dual-mono stereo PCM16 (counts meetings)"},
+        }
+        del x44, xi16, app, mix
 
     if rank != 0:
         if world > 1:

@@ -41,6 +41,10 @@ extern "C" {
     fn crispy_ns_batch_save_state(b: *mut CrispyNsBatch, buf: *mut c_void, len: usize) -> c_int;
     fn crispy_ns_batch_load_state(b: *mut CrispyNsBatch, buf: *const c_void, len: usize) -> c_int;
     fn crispy_ns_batch_destroy(b: *mut CrispyNsBatch);
+    fn crispy_ns_linear_resample_count(input_rate: c_float, output_rate: c_float, n_in: i64) -> i64;
+    fn crispy_ns_sinc_resample_count(input_rate: c_int, output_rate: c_int, n_in: i64) -> i64;
+    fn crispy_ns_resample_host(device: c_int, h_in: *const c_float, h_out: *mut c_float, n_streams: c_int, n_in: i64,
+                               in_stride: i64, out_stride: i64, input_rate: c_int, output_rate: c_int, kind: c_int) -> c_int;
 }
 
 /// == nnnoiseless::FRAME_SIZE (audio.rs:4)
@@ -170,4 +174,19 @@ impl Drop for BatchDenoiser {
     fn drop(&mut self) {
         unsafe { crispy_ns_batch_destroy(self.h) }
     }
+}
+
+/// Front end for recordings that are not at 48 kHz (audio.rs:217-221 uses the linear interpolator; `sinc` selects the
+/// windowed-sinc kernel, the rubato-style alternative).  `input` holds `n_streams` rows of `n_in` samples.
+pub fn resample_to_48k(input: &[f32], n_streams: usize, n_in: usize, input_rate: u32, sinc: bool) -> Result<Vec<f32>, String> {
+    let n_out = unsafe {
+        if sinc { crispy_ns_sinc_resample_count(input_rate as c_int, 48000, n_in as i64) }
+        else { crispy_ns_linear_resample_count(input_rate as c_float, 48000.0, n_in as i64) }
+    } as usize;
+    let mut out = vec![0f32; n_streams * n_out];
+    let rc = unsafe {
+        crispy_ns_resample_host(0, input.as_ptr(), out.as_mut_ptr(), n_streams as c_int, n_in as i64, n_in as i64,
+                                n_out.max(1) as i64, input_rate as c_int, 48000, if sinc { 1 } else { 0 })
+    };
+    if rc == 0 { Ok(out) } else { Err(last_error()) }
 }

@@ -1045,6 +1045,42 @@ int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_s
   return CRISPY_NS_OK;
 }
 
+int crispy_ns_resample_host(int device, const float *h_in, float *h_out, int n_streams, int64_t n_in,
+                            int64_t in_stride, int64_t out_stride, int input_rate, int output_rate, int kind) {
+  if (!h_in || !h_out || n_streams < 1 || n_in < 0 || (kind != 0 && kind != 1))
+    return fail(CRISPY_NS_EINVAL, "resample_host: bad argument");
+  const int ndev = crispy_ns_device_count();
+  if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
+  const int64_t n_out = kind == 0 ? crispy_ns_linear_resample_count((float)input_rate, (float)output_rate, n_in)
+                                  : crispy_ns_sinc_resample_count(input_rate, output_rate, n_in);
+  if (n_in == 0 || n_out == 0) return CRISPY_NS_OK;
+  NS_CUDA(cudaSetDevice(device));
+  float *d_in = nullptr, *d_out = nullptr;
+  NS_CUDA(cudaMalloc((void **)&d_in, (size_t)n_streams * n_in * sizeof(float)));
+  if (cudaError_t e = cudaMalloc((void **)&d_out, (size_t)n_streams * n_out * sizeof(float)); e != cudaSuccess) {
+    cudaFree(d_in);
+    return fail(CRISPY_NS_ECUDA, std::string("resample_host: ") + cudaGetErrorString(e));
+  }
+  int rc = CRISPY_NS_OK;
+  cudaError_t e = cudaMemcpy2D(d_in, (size_t)n_in * 4, h_in, (size_t)in_stride * 4, (size_t)n_in * 4, n_streams,
+                               cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = kind == 0 ? crispy_ns_linear_resample(device, d_in, d_out, n_streams, n_in, n_in, n_out, (float)input_rate,
+                                               (float)output_rate, nullptr)
+                   : crispy_ns_sinc_resample(device, d_in, d_out, n_streams, n_in, n_in, n_out, input_rate, output_rate,
+                                             0, 0.f, nullptr);
+    if (rc == CRISPY_NS_OK)
+      e = cudaMemcpy2D(h_out, (size_t)out_stride * 4, d_out, (size_t)n_out * 4, (size_t)n_out * 4, n_streams,
+                       cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (rc != CRISPY_NS_OK) return rc;
+  if (e != cudaSuccess) return fail(CRISPY_NS_ECUDA, std::string("resample_host: ") + cudaGetErrorString(e));
+  return CRISPY_NS_OK;
+}
+
 // ---- f3: WAV PCM16 -------------------------------------------------------------------------------
 static void le16(uint8_t *p, uint32_t v) {
   p[0] = (uint8_t)v;

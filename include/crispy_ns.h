@@ -158,6 +158,12 @@ int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_s
                             int64_t in_stride, int64_t out_stride, int input_rate, int output_rate,
                             int sinc_len, float f_cutoff, void *cuda_stream);
 
+/* host-pointer convenience over the two front ends (what the Rust side calls for recordings in RAM):
+ * kind 0 = linear (audio.rs:108-133), 1 = windowed sinc (defaults 256 taps, cutoff 0.95).  Synchronous;
+ * h_out must hold crispy_ns_{linear,sinc}_resample_count samples per stream. */
+int crispy_ns_resample_host(int device, const float *h_in, float *h_out, int n_streams, int64_t n_in,
+                            int64_t in_stride, int64_t out_stride, int input_rate, int output_rate, int kind);
+
 /* ---- f3: RIFF/WAVE PCM16 I/O (recording.rs:83-121 writer; commands/recording.rs:385-460 parser) */
 int crispy_ns_wav_write_pcm16(const char *path, const int16_t *interleaved, int64_t n_frames,
                               int channels, int sample_rate);

@@ -203,6 +203,13 @@ def test_sinc_resample_is_bit_exact():  # north_star item 4; oracle: rno_sinc_re
     assert np.array_equal(y[2], po.sinc_resample(x[2, 100:5000], 44100, 48000, 64, 0.9))
 
 
+def test_resample_host_matches_device_paths():
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((3, 4410)).astype(np.float32)
+    assert np.array_equal(cb.resample_host(x, 44100, 48000, "sinc"), cb.sinc_resample(_dev(x), 44100, 48000).cpu().numpy())
+    assert np.array_equal(cb.resample_host(x, 44100, 48000, "linear"), cb.linear_resample(_dev(x), 44100.0, 48000.0).cpu().numpy())
+
+
 def test_sinc_resample_properties_at_full_size():
     """configs[2] geometry (1,024 streams x 10 s at 44.1 kHz): linearity in the input, exactly one frame
     per 441 samples, and time-shift invariance by whole periods (147 in -> 160 out)."""
