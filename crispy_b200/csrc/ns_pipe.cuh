@@ -48,6 +48,8 @@ constexpr int kHpTile = 96;        // samples per tile; 480 = 5 tiles
 constexpr int kHpPitch = 100;      // floats per row in shared memory: 4*lane banks apart for LDS.128
 constexpr int kHpStages = 4;
 constexpr int kHpAhead = 2;        // tiles the loader keeps in flight beyond the one it is publishing
+constexpr int kHpRaw16 = 208;      // byte offset of a row's raw PCM16 samples: 4c + 16 <= 208 + 2(c + 4) for every c < 96
+static_assert(kHpRaw16 % 16 == 0 && kHpRaw16 + 2 * kHpTile <= kHpPitch * 4 && 2 * kHpTile - 8 <= kHpRaw16, "PCM16 staging");
 struct HpSmem {
   float tile[kHpStages][32][kHpPitch];
   int landed[kHpStages], done[kHpStages], freed[kHpStages];
@@ -64,7 +66,16 @@ NS_DEV float load_sample(const Params &p, int stream, long long idx) {
 NS_DEV void hp_fetch_tile(const Params &p, HpSmem &sm, int s0, int nrows, long long in0, int n, bool fast, int lane) {
   float(*dst)[kHpPitch] = sm.tile[n % kHpStages];
   const long long idx0 = in0 + (long long)n * kHpTile;
-  if (fast) {
+  if (fast && (p.flags & kFlagInI16)) {
+    // PCM16 rows (192 B) land raw in the upper part of their float row (byte kHpRaw16 on); the recursion
+    // converts four samples at a time and writes y over the row from the front, always behind its reads
+    if (lane < kHpTile / 8) {
+      const int16_t *src = reinterpret_cast<const int16_t *>(p.in) + (long long)s0 * p.in_stride + idx0 + 8 * lane;
+      char *d = reinterpret_cast<char *>(&dst[0][0]) + kHpRaw16 + 16 * lane;
+#pragma unroll 8
+      for (int r = 0; r < nrows; r++, src += p.in_stride, d += kHpPitch * sizeof(float)) Simt::cp_async16(d, src);
+    }
+  } else if (fast) {
     if (lane < kHpTile / 4) {
       const float *src = reinterpret_cast<const float *>(p.in) + (long long)s0 * p.in_stride + idx0 + 4 * lane;
       float *d = &dst[0][4 * lane];
@@ -105,10 +116,12 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
   const bool tail_direct = nsamp >= kHist;  // the new history is the chunk's own tail
   if (tid < kHpStages) sm.landed[tid] = sm.done[tid] = sm.freed[tid] = 0;
   Simt::cta_sync();
+  const long long in0 = (long long)p.frame0 * kFrame;
+  const bool in16 = (p.flags & kFlagInI16) != 0;
+  const int amask = in16 ? 7 : 3;  // samples per 16 bytes - 1
+  const bool fast = (p.in_stride & amask) == 0 && (in0 & amask) == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
+  const bool raw16 = fast && in16;
   if (warp == 1) {  // ---- loader
-    const long long in0 = (long long)p.frame0 * kFrame;
-    const bool fast = !(p.flags & kFlagInI16) && (p.in_stride & 3) == 0 && (in0 & 3) == 0 &&
-                      (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
     for (int n = 0; n < ntiles + kHpAhead; n++) {
       if (n < ntiles) {
         if (n >= kHpStages) Simt::flag_wait(&sm.freed[n % kHpStages], n - kHpStages + 1, true);
@@ -135,8 +148,16 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
         float *row = sm.tile[slot][lane];
 #pragma unroll 2
         for (int c = 0; c < kHpTile; c += 4) {
-          const f4 xv = ld4(row + c);
-          const float x[4] = {xv.x * scale, xv.y * scale, xv.z * scale, xv.w * scale};
+          float x[4];
+          if (raw16) {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(row) + kHpRaw16 + 2 * c);
+            const uint32_t r0 = rw[0], r1 = rw[1];
+            x[0] = (float)(int16_t)(r0 & 0xFFFFu), x[1] = (float)(int16_t)(r0 >> 16);
+            x[2] = (float)(int16_t)(r1 & 0xFFFFu), x[3] = (float)(int16_t)(r1 >> 16);
+          } else {
+            const f4 xv = ld4(row + c);
+            x[0] = xv.x * scale, x[1] = xv.y * scale, x[2] = xv.z * scale, x[3] = xv.w * scale;
+          }
           float y[4];
 #pragma unroll
           for (int i = 0; i < 4; i++) {
