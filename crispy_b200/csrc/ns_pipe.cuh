@@ -895,6 +895,34 @@ NS_DEV void pitchscan_body(const Params &p, int warps_per_cta) {
 // spectra: 480-point complex FFT (forward), Stockham radices 4,4,5,6 through registers, by a
 // 128-thread group that meets on its own named barrier
 // =================================================================================================
+// K3 / K5 view of the constant tables: the FFT twiddles are indexed irregularly per lane, so they live in
+// shared memory; the window, DCT and band tables are read in order (coalesced) and come through L1 with
+// read-only loads, which frees the shared memory for the staging buffers of the next frame.
+struct SpecTw {
+  cf w480[480];
+  cf w960[244];
+};
+struct Tab {
+  const SpecTw *s;
+  const Tables *g;
+  NS_DEV cf w480(int i) const { return s->w480[i]; }
+  NS_DEV cf w960(int i) const { return s->w960[i]; }
+  NS_DEV float win(int i) const { return Simt::ldg(g->win + i); }
+  NS_DEV float dct(int i) const { return Simt::ldg(g->dct + i); }
+  NS_DEV int bin_band(int i) const { return Simt::ldg(g->bin_band + i); }
+  NS_DEV int eband(int i) const { return Simt::ldg(g->eband + i); }
+  NS_DEV f4 win4(int i) const { return ldg_f4(g->win + i); }
+  NS_DEV f4 bin_frac4(int i) const { return ldg_f4(g->bin_frac + i); }
+  static NS_DEV f4 ldg_f4(const float *p) {
+#if defined(__CUDACC__) && !defined(NS_HOST_EMU)
+    const float4 v = Simt::ldg4(p);
+    return f4{v.x, v.y, v.z, v.w};
+#else
+    return *reinterpret_cast<const f4 *>(p);
+#endif
+  }
+};
+
 struct Grp {
   int tid, lane, warp, bar;
 };
@@ -989,7 +1017,7 @@ NS_DEV void fft_store(cf *buf, int j, int k, const cf (&v)[R]) {
 }
 
 template <int R, int NS_, class Load>
-NS_DEV void fft_stage(const Grp &g, const Tables &T, cf *buf, Load load) {
+NS_DEV void fft_stage(const Grp &g, const Tab &T, cf *buf, Load load) {
   constexpr int M = 480 / R;
   constexpr int TSTEP = 480 / (NS_ * R);
   cf v[R];
@@ -1002,7 +1030,7 @@ NS_DEV void fft_stage(const Grp &g, const Tables &T, cf *buf, Load load) {
 #pragma unroll
     for (int r = 1; r < R; r++) {
       cf x = load(j + r * M);
-      v[r] = (NS_ == 1) ? x : cmul(x, T.w480[r * k * TSTEP]);
+      v[r] = (NS_ == 1) ? x : cmul(x, T.w480(r * k * TSTEP));
     }
     Dft<R>::run(v);
   }
@@ -1013,7 +1041,7 @@ NS_DEV void fft_stage(const Grp &g, const Tables &T, cf *buf, Load load) {
 
 // two independent transforms side by side (same twiddles, same barriers): K3's frame and pitch-lag spectra
 template <int R, int NS_, class Load2>
-NS_DEV void fft_stage2(const Grp &g, const Tables &T, cf *bufA, cf *bufB, Load2 load2) {
+NS_DEV void fft_stage2(const Grp &g, const Tab &T, cf *bufA, cf *bufB, Load2 load2) {
   constexpr int M = 480 / R;
   constexpr int TSTEP = 480 / (NS_ * R);
   cf va[R], vb[R];
@@ -1027,7 +1055,7 @@ NS_DEV void fft_stage2(const Grp &g, const Tables &T, cf *bufA, cf *bufB, Load2 
     for (int r = 1; r < R; r++) {
       load2(j + r * M, va[r], vb[r]);
       if (NS_ != 1) {
-        const cf w = T.w480[r * k * TSTEP];
+        const cf w = T.w480(r * k * TSTEP);
         va[r] = cmul(va[r], w);
         vb[r] = cmul(vb[r], w);
       }
@@ -1044,7 +1072,7 @@ NS_DEV void fft_stage2(const Grp &g, const Tables &T, cf *bufA, cf *bufB, Load2 
 }
 
 template <class LoadFirst>
-NS_DEV void fft480(const Grp &g, const Tables &T, cf *buf, LoadFirst load_first) {
+NS_DEV void fft480(const Grp &g, const Tab &T, cf *buf, LoadFirst load_first) {
   auto from_buf = [&](int n) -> cf { return buf[n]; };
   fft_stage<4, 1>(g, T, buf, load_first);
   fft_stage<4, 4>(g, T, buf, from_buf);
@@ -1053,17 +1081,17 @@ NS_DEV void fft480(const Grp &g, const Tables &T, cf *buf, LoadFirst load_first)
 }
 
 // a7 / a12: X <- rFFT960(window . src[0..960)) / 960   (bins 0..480); src is in HBM/L2
-NS_DEV void rfft960_windowed(const Grp &g, const Tables &T, const float *__restrict__ src, cf *X) {
+NS_DEV void rfft960_windowed(const Grp &g, const Tab &T, const float *__restrict__ src, cf *X) {
   auto load = [&](int n) -> cf {
     const int i0 = 2 * n;
-    const float w0 = (i0 < kFrame) ? T.win[i0] : T.win[kWindow - 1 - i0];
-    const float w1 = (i0 + 1 < kFrame) ? T.win[i0 + 1] : T.win[kWindow - 2 - i0];
+    const float w0 = T.win((i0 < kFrame) ? i0 : kWindow - 1 - i0);
+    const float w1 = T.win((i0 + 1 < kFrame) ? i0 + 1 : kWindow - 2 - i0);
     return cf{src[i0] * w0, src[i0 + 1] * w1};
   };
   fft480(g, T, X, load);
   const float norm = 1.0f / kWindow;
   for (int k = g.tid; k <= 240; k += kGroupThreads) {
-    const cf a = X[k], b = X[k == 0 ? 0 : 480 - k], w = T.w960[k];
+    const cf a = X[k], b = X[k == 0 ? 0 : 480 - k], w = T.w960(k);
     const float er = .5f * (a.x + b.x), ei = .5f * (a.y - b.y);
     const float orr = .5f * (a.x - b.x), oi = .5f * (a.y + b.y);
     const float tr = fmaf(orr, w.x, -(oi * w.y)), ti = fmaf(orr, w.y, oi * w.x);
@@ -1075,12 +1103,13 @@ NS_DEV void rfft960_windowed(const Grp &g, const Tables &T, const float *__restr
 
 // the same for two windows at once (X of the frame, P of the pitch-lagged window): shared window,
 // twiddle and barrier traffic
-NS_DEV void rfft960_windowed2(const Grp &g, const Tables &T, const float *__restrict__ srcA, const float *__restrict__ srcB,
-                              cf *XA, cf *XB) {
-  auto load = [&](int n, cf &a, cf &b) {
+template <class AfterFirst>
+NS_DEV void rfft960_windowed2(const Grp &g, const Tab &T, const float *win, const float *srcA, const float *srcB, cf *XA,
+                              cf *XB, AfterFirst after_first) {
+  auto load = [&](int n, cf &a, cf &b) {  // win: the half window in shared memory
     const int i0 = 2 * n;
-    const float w0 = (i0 < kFrame) ? T.win[i0] : T.win[kWindow - 1 - i0];
-    const float w1 = (i0 + 1 < kFrame) ? T.win[i0 + 1] : T.win[kWindow - 2 - i0];
+    const float w0 = win[(i0 < kFrame) ? i0 : kWindow - 1 - i0];
+    const float w1 = win[(i0 + 1 < kFrame) ? i0 + 1 : kWindow - 2 - i0];
     a = cf{srcA[i0] * w0, srcA[i0 + 1] * w1};
     b = cf{srcB[i0] * w0, srcB[i0 + 1] * w1};
   };
@@ -1089,12 +1118,13 @@ NS_DEV void rfft960_windowed2(const Grp &g, const Tables &T, const float *__rest
     b = XB[n];
   };
   fft_stage2<4, 1>(g, T, XA, XB, load);
+  after_first();  // the sources are consumed: the caller may refill them
   fft_stage2<4, 4>(g, T, XA, XB, from_buf);
   fft_stage2<5, 16>(g, T, XA, XB, from_buf);
   fft_stage2<6, 80>(g, T, XA, XB, from_buf);
   const float norm = 1.0f / kWindow;
   for (int k = g.tid; k <= 240; k += kGroupThreads) {
-    const cf w = T.w960[k];
+    const cf w = T.w960(k);
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       cf *X = q ? XB : XA;
@@ -1111,9 +1141,9 @@ NS_DEV void rfft960_windowed2(const Grp &g, const Tables &T, const float *__rest
 
 // a16: unscaled inverse of the Hermitian spectrum X[0..480]; result left in X as 480 complex
 // z[m] with x[2m] = z[m].x and x[2m+1] = -z[m].y (the conjugate of a forward FFT).
-NS_DEV void irfft960_inplace(const Grp &g, const Tables &T, cf *X) {
+NS_DEV void irfft960_inplace(const Grp &g, const Tab &T, cf *X) {
   for (int k = g.tid; k <= 240; k += kGroupThreads) {
-    const cf a = X[k], b = X[480 - k], w = T.w960[k];
+    const cf a = X[k], b = X[480 - k], w = T.w960(k);
     const float ex = a.x + b.x, ey = a.y - b.y;
     const float ox = a.x - b.x, oy = a.y + b.y;
     const float tr = fmaf(ox, w.x, oy * w.y), ti = fmaf(-ox, w.y, oy * w.x);
@@ -1135,10 +1165,10 @@ NS_DEV void irfft960_inplace(const Grp &g, const Tables &T, cf *X) {
 constexpr int kSlots = 100;
 constexpr int kPartStride = 104;
 template <int NQ, class BinVal>
-NS_DEV void band_slots(const Grp &g, const Tables &T, float *part, BinVal val) {
+NS_DEV void band_slots(const Grp &g, const Tab &T, float *part, BinVal val) {
   if (g.tid < kSlots) {
     const int k0 = 4 * g.tid;
-    const f4 fr4 = ld4(T.bin_frac + k0);
+    const f4 fr4 = T.bin_frac4(k0);
     const float fr[4] = {fr4.x, fr4.y, fr4.z, fr4.w};
     float s0[NQ], s1[NQ];
 #pragma unroll
@@ -1161,14 +1191,14 @@ NS_DEV void band_slots(const Grp &g, const Tables &T, float *part, BinVal val) {
   }
 }
 template <int NQ>
-NS_DEV void band_reduce(const Grp &g, const Tables &T, const float *part, float (&acc)[NQ]) {
+NS_DEV void band_reduce(const Grp &g, const Tab &T, const float *part, float (&acc)[NQ]) {
 #pragma unroll
   for (int q = 0; q < NQ; q++) acc[q] = 0.f;
   const int b = g.tid >> 2, sub = g.tid & 3;
   if (g.tid < 4 * kBands) {
-    const int lo = (b >= 1) ? (T.eband[b - 1] >> 2) : 0;  // slots
-    const int mid = T.eband[b] >> 2;
-    const int hi = (b <= kBands - 2) ? (T.eband[b + 1] >> 2) : mid;
+    const int lo = (b >= 1) ? (T.eband(b - 1) >> 2) : 0;  // slots
+    const int mid = T.eband(b) >> 2;
+    const int hi = (b <= kBands - 2) ? (T.eband(b + 1) >> 2) : mid;
     for (int sl = mid + sub; sl < hi; sl += 4) {  // interval b: this band is its lower one
 #pragma unroll
       for (int q = 0; q < NQ; q++) acc[q] += part[(2 * q) * kPartStride + sl];
@@ -1187,27 +1217,35 @@ NS_DEV void band_reduce(const Grp &g, const Tables &T, const float *part, float 
 }
 
 struct SpecSmem {
-  Tables tab;
-  cf X[482];
-  cf P[482];
+  SpecTw tw;
+  // K3: spec[0] = X | P of the frame in work, spec[1] = the next task's raw windows (960 + 968 floats).
+  // K5: the two halves hold X | P of the frame in work and of the next frame (double buffer by frame parity).
+  cf spec[2][2 * kSpecStride];
+  float rec_s[2][kRecFloats];  // K5: the frames' records, staged with the spectra
   float Ex[24], Ep[24], Exp[24], Ly[24], g[24], graw[24], r[24], nrm[24], newE[24];
   float synth[kFrame];
   float part[6 * kPartStride];  // band_slots -> band_reduce
   int pitch_index, silence;
+  alignas(8) uint64_t mbar;  // completion of the bulk copies that stage the next frame
 };
+static_assert(sizeof(SpecSmem) <= 28160, "eight resident CTAs per SM: 8 x (sizeof + 1 KB) <= 228 KB");
+static_assert(2 * kSpecStride * sizeof(cf) >= (960 + 968) * sizeof(float), "raw window staging fits one spectra buffer");
 
-NS_DEV void load_tables(const Params &p, Tables &dst, int tid, int nthr) {
+NS_DEV void load_twiddles(const Params &p, SpecTw &dst, int tid, int nthr) {
+  static_assert(offsetof(Tables, w480) == 0 && offsetof(Tables, w960) == sizeof(cf) * 480, "twiddles lead the tables");
   const uint32_t *src = reinterpret_cast<const uint32_t *>(p.tables);
   uint32_t *d = reinterpret_cast<uint32_t *>(&dst);
-  for (int i = tid; i < (int)(sizeof(Tables) / 4); i += nthr) d[i] = src[i];
+  for (int i = tid; i < (int)(sizeof(SpecTw) / 4); i += nthr) d[i] = src[i];
 }
 
-// spectra of frame t: X of [prev | cur], P of the window lagged by pitch_index, Ex / Ep / raw Exp
-NS_DEV void frame_spectra(const Grp &g, const Tables &T, SpecSmem &s, const float *hp_row, int t, int pitch_index) {
-  const float *cur = hp_row + kHist - kFrame + (long long)t * kFrame;  // [analysis_mem | frame]
-  rfft960_windowed2(g, T, cur, cur - pitch_index, s.X, s.P);
+// spectra of one frame from its staged raw windows: X of [prev | cur], P of the window lagged by
+// pitch_index, Ex / Ep / raw Exp.  after_first runs once the raw windows have been consumed.
+template <class AfterFirst>
+NS_DEV void frame_spectra(const Grp &g, const Tab &T, SpecSmem &s, const float *rawA, const float *rawB, AfterFirst after_first) {
+  cf *X = s.spec[0], *P = s.spec[0] + kSpecStride;
+  rfft960_windowed2(g, T, s.synth, rawA, rawB, X, P, after_first);  // K3 keeps the window where K5 keeps synthesis_mem
   band_slots<3>(g, T, s.part, [&](int k, float (&v)[3]) {
-    const cf x = s.X[k], p = s.P[k];
+    const cf x = X[k], p = P[k];
     v[0] = fmaf(x.x, x.x, x.y * x.y);
     v[1] = fmaf(p.x, p.x, p.y * p.y);
     v[2] = fmaf(x.x, p.x, x.y * p.y);
@@ -1224,7 +1262,9 @@ NS_DEV void frame_spectra(const Grp &g, const Tables &T, SpecSmem &s, const floa
 }
 
 // =================================================================================================
-// K3: per (stream, frame): spectra -> band features that do not depend on recurrent state
+// K3: per (stream, frame): spectra -> band features that do not depend on recurrent state.
+// The raw windows of a CTA's next task are fetched by TMA bulk copies into shared memory while the current
+// task is transformed (the pitch index that places the lagged window is read one task further ahead).
 // =================================================================================================
 NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
   Grp g;
@@ -1232,20 +1272,70 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
   g.lane = g.tid & 31;
   g.warp = g.tid >> 5;
   g.bar = 1;
-  load_tables(p, s.tab, g.tid, kGroupThreads);
-  Simt::cta_sync();
-  const Tables &T = s.tab;
+  load_twiddles(p, s.tw, g.tid, kGroupThreads);
+  const Tab T{&s.tw, p.tables};
   const float dct_scale = 0.30151134457776363f;  // sqrt(2/22)
-  const int n_tasks = p.n_streams * p.n_frames;  // < 2^31: checked on the host
-  for (int task = Simt::cta(); task < n_tasks; task += Simt::n_ctas()) {
-    const int stream = task / p.n_frames, t = task - stream * p.n_frames;
+  float *rawA = reinterpret_cast<float *>(s.spec[1]), *rawB = rawA + 960;
+  // a CTA's tasks are n_ctas apart: (stream, t) advance by (dq, dr) with a carry, no division per task
+  const int dq = Simt::n_ctas() / p.n_frames, dr = Simt::n_ctas() - dq * p.n_frames;
+  auto advance = [&](int &stream, int &t) {
+    stream += dq;
+    t += dr;
+    if (t >= p.n_frames) {
+      t -= p.n_frames;
+      stream += 1;
+    }
+  };
+  auto pitch_of = [&](int stream, int t) -> int {
+    return reinterpret_cast<const int *>(p.rec + ((long long)stream * p.chunk_cap + t) * kRecFloats)[kRecPitchIndex];
+  };
+  // one thread stages [analysis_mem | frame] (16-byte aligned) and the 4-float-aligned superset of the window
+  // pitch_index earlier with two bulk copies that complete on s.mbar
+  auto stage = [&](int stream, int t, int pitch_index) {
+    if (g.tid == 0) {
+      const long long cur = (long long)stream * p.hp_stride + kHist - kFrame + (long long)t * kFrame;
+      const long long lag = (cur - pitch_index) & ~3ll;
+      Simt::fence_async_proxy();
+      Simt::mbar_expect_tx(&s.mbar, (960 + 964) * sizeof(float));
+      Simt::bulk_g2s(rawA, p.hp + cur, 960 * sizeof(float), &s.mbar);
+      Simt::bulk_g2s(rawB, p.hp + lag, 964 * sizeof(float), &s.mbar);
+    }
+  };
+  if (g.tid == 0) Simt::mbar_init(&s.mbar, 1);
+  for (int i = g.tid; i < kFrame; i += kGroupThreads) s.synth[i] = p.tables->win[i];
+  Simt::cta_sync();
+  int stream = Simt::cta() / p.n_frames, t = Simt::cta() - stream * p.n_frames;
+  int stream1 = stream, t1 = t;  // the next task
+  advance(stream1, t1);
+  int stream2 = stream1, t2 = t1;  // the task after it (its pitch index is fetched one task early)
+  advance(stream2, t2);
+  int pi_cur = 0, pi_next = 0;
+  if (stream < p.n_streams) {
+    pi_cur = pitch_of(stream, t);
+    stage(stream, t, pi_cur);
+    if (stream1 < p.n_streams) pi_next = pitch_of(stream1, t1);
+  }
+  unsigned parity = 0;
+  for (; stream < p.n_streams; stream = stream1, t = t1, stream1 = stream2, t1 = t2, advance(stream2, t2)) {
     const long long fidx = (long long)stream * p.chunk_cap + t;
     float *rec = p.rec + fidx * kRecFloats;
-    const int pitch_index = reinterpret_cast<const int *>(rec)[kRecPitchIndex];
-    frame_spectra(g, T, s, p.hp + (long long)stream * p.hp_stride, t, pitch_index);
+    const int pitch_index = pi_cur;
+    const int pi_staged = pi_next;
+    if (stream2 < p.n_streams) pi_next = pitch_of(stream2, t2);  // consumed one task later
+    pi_cur = pi_staged;
+    Simt::mbar_wait(&s.mbar, parity);
+    parity ^= 1u;
+    gsync(g);
+    {
+      const long long cur = (long long)stream * p.hp_stride + kHist - kFrame + (long long)t * kFrame;
+      const int off = (int)((cur - pitch_index) & 3);
+      frame_spectra(g, T, s, rawA, rawB + off, [&]() {
+        if (stream1 < p.n_streams) stage(stream1, t1, pi_staged);
+      });
+    }
     {  // spectra -> workspace (K5 reads them back instead of redoing two FFTs)
       f4 *dst4 = reinterpret_cast<f4 *>(p.spec + fidx * (2 * kSpecStride));
-      const f4 *src4 = reinterpret_cast<const f4 *>(s.X);  // X[482] and P[482] are contiguous: 482 float4
+      const f4 *src4 = reinterpret_cast<const f4 *>(s.spec[0]);  // X[482] | P[482]: 482 float4
       for (int k = g.tid; k < kSpecStride; k += kGroupThreads) dst4[k] = src4[k];
     }
     if (g.tid < kBands) {
@@ -1270,7 +1360,7 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
     if (g.tid < kBands) {
       const int i = g.tid;
       float sum = 0.f;
-      for (int j = 0; j < kBands; j++) sum += s.Ly[j] * T.dct[j * kBands + i];
+      for (int j = 0; j < kBands; j++) sum += s.Ly[j] * T.dct(j * kBands + i);
       float c = sum * dct_scale;
       if (i == 0) c -= 12.f;
       if (i == 1) c -= 4.f;
@@ -1287,7 +1377,7 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
     } else if (g.tid >= 32 && g.tid < 32 + kDeltaCeps) {
       const int i = g.tid - 32;
       float sum = 0.f;
-      for (int j = 0; j < kBands; j++) sum += s.Exp[j] * T.dct[j * kBands + i];
+      for (int j = 0; j < kBands; j++) sum += s.Exp[j] * T.dct(j * kBands + i);
       float c = sum * dct_scale;
       if (i == 0) c -= 1.3f;
       if (i == 1) c -= 0.9f;
@@ -1783,29 +1873,29 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
 // K5: a15 pitch filter + gain interpolation, a16 synthesis; one 128-thread group per stream walks
 // the chunk's frames carrying synthesis_mem in shared memory
 // =================================================================================================
-NS_DEV void pitch_filter_and_gains(const Grp &g, const Tables &T, SpecSmem &s) {
+NS_DEV void pitch_filter_and_gains(const Grp &g, const Tab &T, SpecSmem &s, cf *X, const cf *P, const float *rc) {
   if (g.tid < kBands) {
     const int i = g.tid;
-    const float e = s.Exp[i], gi = s.graw[i];
+    const float e = rc[kRecExp + i], gi = rc[kRecGRaw + i];
     float r;
     if (e > gi)
       r = 1.f;
     else
       r = (e * e) * (1.f - gi * gi) / (.001f + (gi * gi) * (1.f - e * e));
     r = sqrtf(fminf(1.f, fmaxf(0.f, r)));
-    r *= (float)sqrt((double)s.Ex[i] / (1e-8 + (double)s.Ep[i]));
+    r *= (float)sqrt((double)rc[kRecEx + i] / (1e-8 + (double)rc[kRecEp + i]));
     s.r[i] = r;
   }
   gsync(g);
   // slot pass (four bins of one band interval per thread): X += rf P, and the filtered spectrum's band
   // energy partials in the same sweep
   if (g.tid < kSlots) {
-    const int k0 = 4 * g.tid, b = T.bin_band[k0];
-    const f4 fr4 = ld4(T.bin_frac + k0);
+    const int k0 = 4 * g.tid, b = T.bin_band(k0);
+    const f4 fr4 = T.bin_frac4(k0);
     const float fr[4] = {fr4.x, fr4.y, fr4.z, fr4.w};
     const float r0 = s.r[b], r1 = s.r[b + 1];
-    f4 *X4 = reinterpret_cast<f4 *>(s.X + k0);
-    const f4 *P4 = reinterpret_cast<const f4 *>(s.P + k0);
+    f4 *X4 = reinterpret_cast<f4 *>(X + k0);
+    const f4 *P4 = reinterpret_cast<const f4 *>(P + k0);
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -1832,16 +1922,16 @@ NS_DEV void pitch_filter_and_gains(const Grp &g, const Tables &T, SpecSmem &s) {
     band_reduce<1>(g, T, s.part, e);
     if (g.tid < 4 * kBands && (g.tid & 3) == 0) {
       const int i = g.tid >> 2;
-      s.nrm[i] = (float)sqrt((double)s.Ex[i] / (1e-8 + (double)e[0]));
+      s.nrm[i] = (float)sqrt((double)rc[kRecEx + i] / (1e-8 + (double)e[0]));
     }
   }
   gsync(g);
   if (g.tid < kSlots) {
-    const int k0 = 4 * g.tid, b = T.bin_band[k0];
-    const f4 fr4 = ld4(T.bin_frac + k0);
+    const int k0 = 4 * g.tid, b = T.bin_band(k0);
+    const f4 fr4 = T.bin_frac4(k0);
     const float fr[4] = {fr4.x, fr4.y, fr4.z, fr4.w};
-    const float n0 = s.nrm[b], n1 = s.nrm[b + 1], g0 = s.g[b], g1 = s.g[b + 1];
-    f4 *X4 = reinterpret_cast<f4 *>(s.X + k0);
+    const float n0 = s.nrm[b], n1 = s.nrm[b + 1], g0 = rc[kRecG + b], g1 = rc[kRecG + b + 1];
+    f4 *X4 = reinterpret_cast<f4 *>(X + k0);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       f4 x = X4[h];
@@ -1855,7 +1945,7 @@ NS_DEV void pitch_filter_and_gains(const Grp &g, const Tables &T, SpecSmem &s) {
       X4[h] = x;
     }
   } else {
-    for (int k = 400 + (g.tid - kSlots); k < kFreq; k += kGroupThreads - kSlots) s.X[k] = cf{0.f, 0.f};
+    for (int k = 400 + (g.tid - kSlots); k < kFreq; k += kGroupThreads - kSlots) X[k] = cf{0.f, 0.f};
   }
   gsync(g);
 }
@@ -1876,13 +1966,13 @@ NS_DEV int16_t out_mix(const Params &p, float o, float app) {
 }
 NS_DEV uint32_t pack16(int16_t lo, int16_t hi) { return (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16); }
 
-NS_DEV void store_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem &s, int stream, int t_call) {
+NS_DEV void store_frame(const Grp &g, const Tab &T, const Params &p, SpecSmem &s, const cf *X, int stream, int t_call) {
   // X holds z[m] with x[2m] = z.x, x[2m+1] = -z.y.  out[i] = x[i] w[i] + synth[i]; synth = x[480+i] w[479-i]
   const int slot = t_call + p.out_frame_offset;
-  const float *zb = reinterpret_cast<const float *>(s.X);
+  const float *zb = reinterpret_cast<const float *>(X);
   if (g.tid >= kFrame / 4) return;
   const int i = 4 * g.tid;
-  const f4 za = ld4(zb + i), zc = ld4(zb + kFrame + i), wa = ld4(T.win + i), wr = ld4(T.win + kFrame - 4 - i);
+  const f4 za = ld4(zb + i), zc = ld4(zb + kFrame + i), wa = T.win4(i), wr = T.win4(kFrame - 4 - i);
   const f4 sy = ld4(s.synth + i);
   const float o[4] = {za.x * wa.x + sy.x, (-za.y) * wa.y + sy.y, za.z * wa.z + sy.z, (-za.w) * wa.w + sy.w};
   *reinterpret_cast<f4 *>(s.synth + i) = f4{zc.x * wr.w, (-zc.y) * wr.z, zc.z * wr.y, (-zc.w) * wr.x};
@@ -1951,50 +2041,42 @@ inline int pick_syn_run(int n_streams, int n_frames, int resident_ctas) {
   return best;
 }
 
-NS_DEV void synth_frame(const Grp &g, const Tables &T, const Params &p, SpecSmem &s, int stream, int t, bool halo,
-                        bool prefetch_next) {
-  const long long fidx = (long long)stream * p.chunk_cap + t;
-  const float *rec = p.rec + fidx * kRecFloats;
-  const bool silent = reinterpret_cast<const int *>(rec)[kRecSilence] != 0;
-  const cf *src = p.spec + fidx * (2 * kSpecStride);
-  {  // X (and P unless silent) as 16-byte copies: kSpecStride cf = 241 float4 each, X and P contiguous on both sides
-    static_assert(kSpecStride % 2 == 0 && offsetof(SpecSmem, P) == offsetof(SpecSmem, X) + kSpecStride * sizeof(cf), "layout");
-    const f4 *src4 = reinterpret_cast<const f4 *>(src);
-    f4 *dst4 = reinterpret_cast<f4 *>(s.X);
-    const int n4 = silent ? kSpecStride / 2 : kSpecStride;
-    for (int k = g.tid; k < n4; k += kGroupThreads) dst4[k] = src4[k];
+// one thread stages a frame's spectra (X | P, 7,712 B) and record (576 B) into buffer b: two bulk copies on s.mbar
+NS_DEV void synth_stage(const Grp &g, const Params &p, SpecSmem &s, int stream, int t, int b) {
+  static_assert((2 * kSpecStride * sizeof(cf)) % 16 == 0 && (kRecFloats * sizeof(float)) % 16 == 0, "bulk copy sizes");
+  if (g.tid == 0) {
+    const long long fidx = (long long)stream * p.chunk_cap + t;
+    Simt::fence_async_proxy();
+    Simt::mbar_expect_tx(&s.mbar, (unsigned)(2 * kSpecStride * sizeof(cf) + kRecFloats * sizeof(float)));
+    Simt::bulk_g2s(s.spec[b], p.spec + fidx * (2 * kSpecStride), (unsigned)(2 * kSpecStride * sizeof(cf)), &s.mbar);
+    Simt::bulk_g2s(s.rec_s[b], p.rec + fidx * kRecFloats, (unsigned)(kRecFloats * sizeof(float)), &s.mbar);
   }
-  // the run's next frame is the next 7.7 KB of the same array: pull it into L2 while this one is worked on
-  if (prefetch_next && g.tid * 128 < (int)(2 * kSpecStride * sizeof(cf)))
-    Simt::prefetch_l2(reinterpret_cast<const char *>(src + 2 * kSpecStride) + g.tid * 128);
-  if (g.tid < kBands) {
-    s.g[g.tid] = rec[kRecG + g.tid];
-    s.graw[g.tid] = rec[kRecGRaw + g.tid];
-    s.Exp[g.tid] = rec[kRecExp + g.tid];
-    s.Ex[g.tid] = rec[kRecEx + g.tid];
-    s.Ep[g.tid] = rec[kRecEp + g.tid];
-  }
-  gsync(g);
-  if (!silent) pitch_filter_and_gains(g, T, s);
+}
+
+NS_DEV void synth_frame(const Grp &g, const Tab &T, const Params &p, SpecSmem &s, int stream, int t, bool halo, int b) {
+  cf *X = s.spec[b], *P = X + kSpecStride;
+  const float *rc = s.rec_s[b];
+  const bool silent = reinterpret_cast<const int *>(rc)[kRecSilence] != 0;
+  if (!silent) pitch_filter_and_gains(g, T, s, X, P, rc);
   if (p.dbg && !halo) {
     float *d = p.dbg + ((long long)stream * p.n_frames_call + p.frame0 + t) * kDbgFloats;
-    if (g.tid < kBands) d[kDbgGains + g.tid] = s.g[g.tid];
+    if (g.tid < kBands) d[kDbgGains + g.tid] = rc[kRecG + g.tid];
     if (g.tid == 0) {
-      d[kDbgPitchGain] = rec[kRecPitchGain];
-      d[kDbgVad] = rec[kRecVad];
-      d[kDbgPitchIndex] = (float)reinterpret_cast<const int *>(rec)[kRecPitchIndex];
+      d[kDbgPitchGain] = rc[kRecPitchGain];
+      d[kDbgVad] = rc[kRecVad];
+      d[kDbgPitchIndex] = (float)reinterpret_cast<const int *>(rc)[kRecPitchIndex];
       d[kDbgSilence] = silent ? 1.f : 0.f;
     }
   }
-  irfft960_inplace(g, T, s.X);
+  irfft960_inplace(g, T, X);
   if (halo) {
-    const float *zb = reinterpret_cast<const float *>(s.X);
+    const float *zb = reinterpret_cast<const float *>(X);
     for (int i = g.tid; i < kFrame; i += kGroupThreads) {
       const float x1 = (i & 1) ? -zb[kFrame + i] : zb[kFrame + i];
-      s.synth[i] = x1 * T.win[kFrame - 1 - i];
+      s.synth[i] = x1 * T.win(kFrame - 1 - i);
     }
   } else {
-    store_frame(g, T, p, s, stream, p.frame0 + t);
+    store_frame(g, T, p, s, X, stream, p.frame0 + t);
   }
   gsync(g);
 }
@@ -2005,9 +2087,11 @@ NS_DEV void synthesis_body(const Params &p, SpecSmem &s) {
   g.lane = g.tid & 31;
   g.warp = g.tid >> 5;
   g.bar = 1;
-  load_tables(p, s.tab, g.tid, kGroupThreads);
+  load_twiddles(p, s.tw, g.tid, kGroupThreads);
+  if (g.tid == 0) Simt::mbar_init(&s.mbar, 1);
   Simt::cta_sync();
-  const Tables &T = s.tab;
+  const Tab T{&s.tw, p.tables};
+  unsigned parity = 0;
   const int run = p.syn_run;
   const int runs = (p.n_frames + run - 1) / run;
   const int n_tasks = p.n_streams * runs;  // < 2^31: checked on the host
@@ -2015,13 +2099,19 @@ NS_DEV void synthesis_body(const Params &p, SpecSmem &s) {
     const int stream = task / runs, t0 = (task - stream * runs) * run;
     const int t1 = (t0 + run < p.n_frames) ? t0 + run : p.n_frames;
     float *st = p.state + (long long)stream * kStateFloats;
-    if (t0 == 0) {
+    // a run that does not start the chunk re-synthesises the frame before it (the overlap-add halo)
+    const int first = (t0 == 0) ? 0 : t0 - 1;
+    synth_stage(g, p, s, stream, first, 0);
+    if (t0 == 0)
       for (int i = g.tid; i < kFrame; i += kGroupThreads) s.synth[i] = st[kStSynth + p.synth_sel * kFrame + i];
-      gsync(g);
-    } else {
-      synth_frame(g, T, p, s, stream, t0 - 1, true, true);
+    for (int t = first; t < t1; t++) {
+      const int b = (t - first) & 1;
+      Simt::mbar_wait(&s.mbar, parity);
+      parity ^= 1u;
+      gsync(g);  // frame t has landed in buffer b; everyone is done with buffer b ^ 1
+      if (t + 1 < t1) synth_stage(g, p, s, stream, t + 1, b ^ 1);  // in flight while frame t is worked on
+      synth_frame(g, T, p, s, stream, t, t < t0, b);
     }
-    for (int t = t0; t < t1; t++) synth_frame(g, T, p, s, stream, t, false, t + 1 < t1);
     if (t1 == p.n_frames) {
       for (int i = g.tid; i < kFrame; i += kGroupThreads) st[kStSynth + (1 - p.synth_sel) * kFrame + i] = s.synth[i];
       if (g.tid == 0) reinterpret_cast<int *>(st)[kStFrameCount] += p.n_frames;

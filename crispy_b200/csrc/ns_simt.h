@@ -51,6 +51,45 @@ struct Simt {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
   }
   static NS_DEV void prefetch_l2(const void *gmem) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem)); }
+  // read-only global loads through L1 (LDG.CONSTANT): the small tables every CTA reads in order
+  static NS_DEV float ldg(const float *p) { return __ldg(p); }
+  static NS_DEV int ldg(const int *p) { return __ldg(p); }
+  static NS_DEV float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+  // ---- TMA 1-D bulk copies (cp.async.bulk, UBLKCP) completing on a shared-memory mbarrier: one thread moves a
+  // whole tile with one instruction; consumers wait on the barrier's phase parity.  dst, src and bytes are
+  // multiples of 16.
+  static NS_DEV void mbar_init(uint64_t *bar, int count) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  static NS_DEV void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+  }
+  static NS_DEV void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), a = (unsigned)__cvta_generic_to_shared(bar);
+    const unsigned long long g = (unsigned long long)__cvta_generic_to_global(gmem_src);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(g),
+                 "r"(bytes), "r"(a)
+                 : "memory");
+  }
+  static NS_DEV void mbar_wait(uint64_t *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NS_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NS_MBAR_DONE;\n"
+        "bra NS_MBAR_WAIT;\n"
+        "NS_MBAR_DONE:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
+  }
+  // orders this thread's earlier generic-proxy accesses to shared memory before its later async-proxy copies
+  static NS_DEV void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
   // shared-memory flags between the specialised warps of one CTA (no bar.sync): values only grow
   static NS_DEV void fence_cta() { __threadfence_block(); }
   static NS_DEV void flag_set(int *f, int v) {
@@ -172,6 +211,14 @@ struct Simt {
     return rn(lo) | (rn(hi) << 16);
   }
   static void prefetch_l2(const void *) {}
+  static float ldg(const float *p) { return *p; }
+  static int ldg(const int *p) { return *p; }
+  // bulk copies complete at once in the emulation; callers follow every mbar_wait with a group barrier
+  static void mbar_init(uint64_t *, int) {}
+  static void mbar_expect_tx(uint64_t *, unsigned) {}
+  static void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *) { memcpy(smem_dst, gmem_src, bytes); }
+  static void mbar_wait(uint64_t *, unsigned) {}
+  static void fence_async_proxy() {}
   static void fence_cta() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
   static void flag_set(int *f, int v) { __atomic_store_n(f, v, __ATOMIC_SEQ_CST); }
   static void flag_wait(const int *f, int v, bool) {
