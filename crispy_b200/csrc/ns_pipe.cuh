@@ -1016,7 +1016,9 @@ NS_DEV void fft_store(cf *buf, int j, int k, const cf (&v)[R]) {
   }
 }
 
-template <int R, int NS_, class Load>
+// PP ("ping-pong"): the stage stores into a buffer it does not load from, so the barrier between the loads and the
+// stores is not needed
+template <int R, int NS_, bool PP = false, class Load>
 NS_DEV void fft_stage(const Grp &g, const Tab &T, cf *buf, Load load) {
   constexpr int M = 480 / R;
   constexpr int TSTEP = 480 / (NS_ * R);
@@ -1034,13 +1036,13 @@ NS_DEV void fft_stage(const Grp &g, const Tab &T, cf *buf, Load load) {
     }
     Dft<R>::run(v);
   }
-  gsync(g);
+  if (!PP) gsync(g);
   if (act) fft_store<R, NS_>(buf, j, k, v);
   gsync(g);
 }
 
 // two independent transforms side by side (same twiddles, same barriers): K3's frame and pitch-lag spectra
-template <int R, int NS_, class Load2>
+template <int R, int NS_, bool PP = false, class Load2>
 NS_DEV void fft_stage2(const Grp &g, const Tab &T, cf *bufA, cf *bufB, Load2 load2) {
   constexpr int M = 480 / R;
   constexpr int TSTEP = 480 / (NS_ * R);
@@ -1063,7 +1065,7 @@ NS_DEV void fft_stage2(const Grp &g, const Tab &T, cf *bufA, cf *bufB, Load2 loa
     Dft<R>::run(va);
     Dft<R>::run(vb);
   }
-  gsync(g);
+  if (!PP) gsync(g);
   if (act) {
     fft_store<R, NS_>(bufA, j, k, va);
     fft_store<R, NS_>(bufB, j, k, vb);
@@ -1103,25 +1105,28 @@ NS_DEV void rfft960_windowed(const Grp &g, const Tab &T, const float *__restrict
 
 // the same for two windows at once (X of the frame, P of the pitch-lagged window): shared window,
 // twiddle and barrier traffic
-template <class AfterFirst>
-NS_DEV void rfft960_windowed2(const Grp &g, const Tab &T, const float *win, const float *srcA, const float *srcB, cf *XA,
-                              cf *XB, AfterFirst after_first) {
-  auto load = [&](int n, cf &a, cf &b) {  // win: the half window in shared memory
+// (XA, XB) receive the result; (YA, YB) are scratch of the same size: the four stages ping-pong between them
+NS_DEV void rfft960_windowed2(const Grp &g, const Tab &T, const float *win, const float *__restrict__ srcA,
+                              const float *__restrict__ srcB, cf *XA, cf *XB, cf *YA, cf *YB) {
+  auto load = [&](int n, cf &a, cf &b) {  // win: the half window in shared memory; srcA / srcB in HBM / L2
     const int i0 = 2 * n;
     const float w0 = win[(i0 < kFrame) ? i0 : kWindow - 1 - i0];
     const float w1 = win[(i0 + 1 < kFrame) ? i0 + 1 : kWindow - 2 - i0];
     a = cf{srcA[i0] * w0, srcA[i0 + 1] * w1};
     b = cf{srcB[i0] * w0, srcB[i0 + 1] * w1};
   };
-  auto from_buf = [&](int n, cf &a, cf &b) {
+  auto from_x = [&](int n, cf &a, cf &b) {
     a = XA[n];
     b = XB[n];
   };
-  fft_stage2<4, 1>(g, T, XA, XB, load);
-  after_first();  // the sources are consumed: the caller may refill them
-  fft_stage2<4, 4>(g, T, XA, XB, from_buf);
-  fft_stage2<5, 16>(g, T, XA, XB, from_buf);
-  fft_stage2<6, 80>(g, T, XA, XB, from_buf);
+  auto from_y = [&](int n, cf &a, cf &b) {
+    a = YA[n];
+    b = YB[n];
+  };
+  fft_stage2<4, 1, true>(g, T, YA, YB, load);
+  fft_stage2<4, 4, true>(g, T, XA, XB, from_y);
+  fft_stage2<5, 16, true>(g, T, YA, YB, from_x);
+  fft_stage2<6, 80, true>(g, T, XA, XB, from_y);
   const float norm = 1.0f / kWindow;
   for (int k = g.tid; k <= 240; k += kGroupThreads) {
     const cf w = T.w960(k);
@@ -1141,7 +1146,7 @@ NS_DEV void rfft960_windowed2(const Grp &g, const Tab &T, const float *win, cons
 
 // a16: unscaled inverse of the Hermitian spectrum X[0..480]; result left in X as 480 complex
 // z[m] with x[2m] = z[m].x and x[2m+1] = -z[m].y (the conjugate of a forward FFT).
-NS_DEV void irfft960_inplace(const Grp &g, const Tab &T, cf *X) {
+NS_DEV void irfft960_inplace(const Grp &g, const Tab &T, cf *X, cf *Y) {  // Y: scratch of 480 cf (ping-pong partner)
   for (int k = g.tid; k <= 240; k += kGroupThreads) {
     const cf a = X[k], b = X[480 - k], w = T.w960(k);
     const float ex = a.x + b.x, ey = a.y - b.y;
@@ -1151,8 +1156,12 @@ NS_DEV void irfft960_inplace(const Grp &g, const Tab &T, cf *X) {
     if (k != 0) X[480 - k] = cf{ex + ti, ey - tr};
   }
   gsync(g);
-  auto from_buf = [&](int n) -> cf { return X[n]; };
-  fft480(g, T, X, from_buf);
+  auto from_x = [&](int n) -> cf { return X[n]; };
+  auto from_y = [&](int n) -> cf { return Y[n]; };
+  fft_stage<4, 1, true>(g, T, Y, from_x);
+  fft_stage<4, 4, true>(g, T, X, from_y);
+  fft_stage<5, 16, true>(g, T, Y, from_x);
+  fft_stage<6, 80, true>(g, T, X, from_y);
 }
 
 // a8: 22 triangular bands over bins 0..400.  Every band edge is a multiple of four bins, so bins
@@ -1238,12 +1247,12 @@ NS_DEV void load_twiddles(const Params &p, SpecTw &dst, int tid, int nthr) {
   for (int i = tid; i < (int)(sizeof(SpecTw) / 4); i += nthr) d[i] = src[i];
 }
 
-// spectra of one frame from its staged raw windows: X of [prev | cur], P of the window lagged by
-// pitch_index, Ex / Ep / raw Exp.  after_first runs once the raw windows have been consumed.
-template <class AfterFirst>
-NS_DEV void frame_spectra(const Grp &g, const Tab &T, SpecSmem &s, const float *rawA, const float *rawB, AfterFirst after_first) {
+// spectra of frame t: X of [prev | cur], P of the window lagged by pitch_index, Ex / Ep / raw Exp
+NS_DEV void frame_spectra(const Grp &g, const Tab &T, SpecSmem &s, const float *hp_row, int t, int pitch_index) {
+  const float *cur = hp_row + kHist - kFrame + (long long)t * kFrame;  // [analysis_mem | frame]
   cf *X = s.spec[0], *P = s.spec[0] + kSpecStride;
-  rfft960_windowed2(g, T, s.synth, rawA, rawB, X, P, after_first);  // K3 keeps the window where K5 keeps synthesis_mem
+  // K3 keeps the window where K5 keeps synthesis_mem; spec[1] is the FFT's ping-pong partner
+  rfft960_windowed2(g, T, s.synth, cur, cur - pitch_index, X, P, s.spec[1], s.spec[1] + kSpecStride);
   band_slots<3>(g, T, s.part, [&](int k, float (&v)[3]) {
     const cf x = X[k], p = P[k];
     v[0] = fmaf(x.x, x.x, x.y * x.y);
@@ -1262,9 +1271,7 @@ NS_DEV void frame_spectra(const Grp &g, const Tab &T, SpecSmem &s, const float *
 }
 
 // =================================================================================================
-// K3: per (stream, frame): spectra -> band features that do not depend on recurrent state.
-// The raw windows of a CTA's next task are fetched by TMA bulk copies into shared memory while the current
-// task is transformed (the pitch index that places the lagged window is read one task further ahead).
+// K3: per (stream, frame): spectra -> band features that do not depend on recurrent state
 // =================================================================================================
 NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
   Grp g;
@@ -1273,66 +1280,23 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
   g.warp = g.tid >> 5;
   g.bar = 1;
   load_twiddles(p, s.tw, g.tid, kGroupThreads);
+  for (int i = g.tid; i < kFrame; i += kGroupThreads) s.synth[i] = p.tables->win[i];
+  Simt::cta_sync();
   const Tab T{&s.tw, p.tables};
   const float dct_scale = 0.30151134457776363f;  // sqrt(2/22)
-  float *rawA = reinterpret_cast<float *>(s.spec[1]), *rawB = rawA + 960;
   // a CTA's tasks are n_ctas apart: (stream, t) advance by (dq, dr) with a carry, no division per task
   const int dq = Simt::n_ctas() / p.n_frames, dr = Simt::n_ctas() - dq * p.n_frames;
-  auto advance = [&](int &stream, int &t) {
-    stream += dq;
-    t += dr;
+  int stream = Simt::cta() / p.n_frames, t = Simt::cta() - stream * p.n_frames;
+  for (; stream < p.n_streams; stream += dq, t += dr) {
     if (t >= p.n_frames) {
       t -= p.n_frames;
       stream += 1;
+      if (stream >= p.n_streams) break;
     }
-  };
-  auto pitch_of = [&](int stream, int t) -> int {
-    return reinterpret_cast<const int *>(p.rec + ((long long)stream * p.chunk_cap + t) * kRecFloats)[kRecPitchIndex];
-  };
-  // one thread stages [analysis_mem | frame] (16-byte aligned) and the 4-float-aligned superset of the window
-  // pitch_index earlier with two bulk copies that complete on s.mbar
-  auto stage = [&](int stream, int t, int pitch_index) {
-    if (g.tid == 0) {
-      const long long cur = (long long)stream * p.hp_stride + kHist - kFrame + (long long)t * kFrame;
-      const long long lag = (cur - pitch_index) & ~3ll;
-      Simt::fence_async_proxy();
-      Simt::mbar_expect_tx(&s.mbar, (960 + 964) * sizeof(float));
-      Simt::bulk_g2s(rawA, p.hp + cur, 960 * sizeof(float), &s.mbar);
-      Simt::bulk_g2s(rawB, p.hp + lag, 964 * sizeof(float), &s.mbar);
-    }
-  };
-  if (g.tid == 0) Simt::mbar_init(&s.mbar, 1);
-  for (int i = g.tid; i < kFrame; i += kGroupThreads) s.synth[i] = p.tables->win[i];
-  Simt::cta_sync();
-  int stream = Simt::cta() / p.n_frames, t = Simt::cta() - stream * p.n_frames;
-  int stream1 = stream, t1 = t;  // the next task
-  advance(stream1, t1);
-  int stream2 = stream1, t2 = t1;  // the task after it (its pitch index is fetched one task early)
-  advance(stream2, t2);
-  int pi_cur = 0, pi_next = 0;
-  if (stream < p.n_streams) {
-    pi_cur = pitch_of(stream, t);
-    stage(stream, t, pi_cur);
-    if (stream1 < p.n_streams) pi_next = pitch_of(stream1, t1);
-  }
-  unsigned parity = 0;
-  for (; stream < p.n_streams; stream = stream1, t = t1, stream1 = stream2, t1 = t2, advance(stream2, t2)) {
     const long long fidx = (long long)stream * p.chunk_cap + t;
     float *rec = p.rec + fidx * kRecFloats;
-    const int pitch_index = pi_cur;
-    const int pi_staged = pi_next;
-    if (stream2 < p.n_streams) pi_next = pitch_of(stream2, t2);  // consumed one task later
-    pi_cur = pi_staged;
-    Simt::mbar_wait(&s.mbar, parity);
-    parity ^= 1u;
-    gsync(g);
-    {
-      const long long cur = (long long)stream * p.hp_stride + kHist - kFrame + (long long)t * kFrame;
-      const int off = (int)((cur - pitch_index) & 3);
-      frame_spectra(g, T, s, rawA, rawB + off, [&]() {
-        if (stream1 < p.n_streams) stage(stream1, t1, pi_staged);
-      });
-    }
+    const int pitch_index = reinterpret_cast<const int *>(rec)[kRecPitchIndex];
+    frame_spectra(g, T, s, p.hp + (long long)stream * p.hp_stride, t, pitch_index);
     {  // spectra -> workspace (K5 reads them back instead of redoing two FFTs)
       f4 *dst4 = reinterpret_cast<f4 *>(p.spec + fidx * (2 * kSpecStride));
       const f4 *src4 = reinterpret_cast<const f4 *>(s.spec[0]);  // X[482] | P[482]: 482 float4
@@ -2068,7 +2032,7 @@ NS_DEV void synth_frame(const Grp &g, const Tab &T, const Params &p, SpecSmem &s
       d[kDbgSilence] = silent ? 1.f : 0.f;
     }
   }
-  irfft960_inplace(g, T, X);
+  irfft960_inplace(g, T, X, P);  // P is dead after the pitch filter
   if (halo) {
     const float *zb = reinterpret_cast<const float *>(X);
     for (int i = g.tid; i < kFrame; i += kGroupThreads) {
