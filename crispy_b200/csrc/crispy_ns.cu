@@ -1170,3 +1170,14 @@ int crispy_ns_wav_read_pcm16(const char *path, int16_t *interleaved, int64_t cap
 }
 
 }  // extern "C"
+
+#ifdef NS_PHASE_CLOCKS
+extern "C" int crispy_ns_debug_pitch_phase_cycles(unsigned long long *out16, int reset) {
+  if (out16 && cudaMemcpyFromSymbol(out16, ns::g_pitch_phase_cycles, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(ns::g_pitch_phase_cycles, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#endif

@@ -242,6 +242,10 @@ struct PitchSmem {
   int fi[R][12];
   float xx[R];
   float sb6[R][148];  // Syy before every coarse lag (helper warp, in the coarse search's shadow)
+  float s10[R][12];   // fine pass: Syy before each of the (at most ten) candidate lags (chain warp B, in P7's shadow)
+#ifdef NS_PITCH_PAD_BYTES
+  char pad[NS_PITCH_PAD_BYTES];  // measurement builds: forces fewer resident CTAs per SM
+#endif
   int best0[R], best1[R], T0[R], nk[R];
   // work lists of remove_doubling's inner products per window-alignment bucket: frame | lag << 5 | k << 14
   int n_tri[4], n_sgl[4];
@@ -425,9 +429,26 @@ NS_DEV float sumsq_from(float acc, const float *y) {
   return acc;
 }
 
+#if defined(NS_PHASE_CLOCKS) && defined(__CUDACC__) && !defined(NS_HOST_EMU)
+// measurement build only: cycles between K1's barriers, summed over CTAs (thread 0 of each CTA)
+__device__ unsigned long long g_pitch_phase_cycles[16];
+#define NS_PHASE_BEGIN() long long ns_pc_ = clock64()
+#define NS_PHASE_MARK(i)                                                       \
+  do {                                                                         \
+    if (tid == 0) {                                                            \
+      const long long now_ = clock64();                                        \
+      atomicAdd(&g_pitch_phase_cycles[i], (unsigned long long)(now_ - ns_pc_)); \
+      ns_pc_ = now_;                                                           \
+    }                                                                          \
+  } while (0)
+#else
+#define NS_PHASE_BEGIN() do {} while (0)
+#define NS_PHASE_MARK(i) do {} while (0)
+#endif
 template <int R, int NT>
 NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   const int tid = Simt::tid();
+  NS_PHASE_BEGIN();
   const int runs_per_stream = (p.n_frames + R - 1) / R;
   const int stream = Simt::cta() / runs_per_stream;
   const int t0 = (Simt::cta() % runs_per_stream) * R;
@@ -444,6 +465,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     for (int i = tid; i < n4; i += NT) dst[i] = src[i];
   }
   Simt::cta_sync();
+  NS_PHASE_MARK(1);
   // P1: a9 2x downsample, pitch_buf[j] of frame f = h[480 f + j]
   for (int it = tid; it < nfr * (kLpLen / 4); it += NT) {  // four outputs per lane from two float4s (+ one scalar)
     const int f = it / (kLpLen / 4), i0 = 4 * (it - f * (kLpLen / 4));
@@ -460,9 +482,37 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     *reinterpret_cast<f4 *>(sm.xr + f * kLpStride + i0) = v;
   }
   Simt::cta_sync();
-  // P2: _celt_autocorr, lags 0..4.  Warp k works lag k for every frame, so the window shift is a
-  // compile-time constant per warp (no selects on the 860-step serial chain).
-  if (NT >= 5 * 32 && R <= 32) {
+  NS_PHASE_MARK(2);
+  // P2: _celt_autocorr, lags 0..4.  One lane per (frame, lag) chain, twenty chains per warp (four frames x five
+  // lags: their rows sit 8 banks apart and the lags 1 bank apart, so the scalar reads of x[i + k] do not
+  // conflict and x[i] arrives as one broadcast LDS.128 per frame); operands are fetched one quad ahead of the
+  // chain of adds.
+  if (R <= 8 && NT >= 64) {
+    if (tid < 64) {
+      const int l = tid & 31, fl = l / 5, k = l - 5 * fl, f = 4 * (tid >> 5) + fl;
+      if (l < 20 && f < nfr) {
+        const float *x = sm.xr + f * kLpStride;
+        const float *y = x + k;
+        f4 xv = ld4(x);
+        float y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
+        float sum = 0.f;
+        NS_UNROLL(NS_DOT_UNROLL)
+        for (int i = 0; i < kLpLen - 4; i += 4) {  // the last trip's over-read stays inside the padded row
+          const f4 xn = ld4(x + i + 4);
+          const float n0 = y[i + 4], n1 = y[i + 5], n2 = y[i + 6], n3 = y[i + 7];
+          sum += xv.x * y0;
+          sum += xv.y * y1;
+          sum += xv.z * y2;
+          sum += xv.w * y3;
+          xv = xn;
+          y0 = n0, y1 = n1, y2 = n2, y3 = n3;
+        }
+        float d = 0.f;
+        for (int i = k + kLpLen - 4; i < kLpLen; i++) d += x[i] * x[i - k];
+        sm.ac[f][k] = sum + d;
+      }
+    }
+  } else if (NT >= 5 * 32 && R <= 32) {
     const int k = tid >> 5, f = tid & 31;
     if (k < 5 && f < nfr) {
       const float *x = sm.xr + f * kLpStride;
@@ -489,6 +539,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     }
   }
   Simt::cta_sync();
+  NS_PHASE_MARK(3);
   // P3: lag window, _celt_lpc (order 4), bandwidth expansion, the extra zero
   if (tid < nfr) {
     const int f = tid;
@@ -528,6 +579,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     sm.lpc2[f][4] = .8f * lpc[3];
   }
   Simt::cta_sync();
+  NS_PHASE_MARK(4);
   // P4: celt_fir5 with zero initial memory -> x_lp (overwrites the window h, which is dead now)
   for (int it = tid; it < nfr * (kLpLen / 4); it += NT) {  // four outputs per lane from three float4s
     const int f = it / (kLpLen / 4), i0 = 4 * (it - f * (kLpLen / 4));
@@ -551,12 +603,86 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     *reinterpret_cast<f4 *>(sm.xlp + f * kLpStride + i0) = f4{o[0], o[1], o[2], o[3]};
   }
   Simt::cta_sync();
+  NS_PHASE_MARK(5);
   // P4b: 4x-decimated copy y4[m] = x_lp[2m] (x4[j] = y4[192 + j]); zero pad to 432+8
   for (int it = tid; it < nfr * 440; it += NT) {
     const int f = it / 440, m = it - f * 440;
     sm.xr[f * kLpStride + m] = (m < 432) ? sm.xlp[f * kLpStride + 2 * m] : 0.f;
   }
   Simt::cta_sync();
+  NS_PHASE_MARK(6);
+  // ---- the two long serial chains that only need x_lp run on their own warps in the shadow of P5..P7, a
+  // budgeted number of 16-element blocks per phase (state stays in registers across the barriers):
+  //   B (warp NW-2, lane = frame): find_best_pitch's running energy of the fine pass, Syy = 1 + sum_{j<480} y[j]^2
+  //     (P5/P6), then, once P6 has named the candidate lags, Syy <- max(1, Syy + y[i+480]^2 - y[i]^2) up to the last
+  //     candidate, keeping the value before each candidate lag (sm.s10) for P8;
+  //   C (warp NW-3, lane = frame): remove_doubling's xx = sum x[j]^2 and its yy_lookup recurrence.
+  // Both are complete before their consumers: B before P8, C before P12 (the P7 call finishes both).
+  constexpr int NW = NT / 32;
+  static_assert(NW >= 4, "chain warps B and C, the coarse helper and at least one worker warp");
+  const int chain_lane = tid & 31;
+  const bool chain_b = (tid >> 5) == NW - 2 && chain_lane < nfr, chain_c = (tid >> 5) == NW - 3 && chain_lane < nfr;
+  float ch_acc = chain_b ? 1.f : 0.f;
+  int ch_blk = 0;  // blocks done: 30 for the sum of squares, then 19 (B) / 24 (C) for the recurrence
+  auto chain_run = [&](int budget, bool recur_b) {
+    if (!chain_b && !chain_c) return;
+    const int f = chain_lane;
+    const float *y = sm.xlp + f * kLpStride + (chain_c ? 384 : 0);
+    for (; budget > 0 && ch_blk < 30; budget--, ch_blk++) {
+      const float *q = y + 16 * ch_blk;
+      const f4 v0 = ld4(q), v1 = ld4(q + 4), v2 = ld4(q + 8), v3 = ld4(q + 12);
+      ch_acc += v0.x * v0.x, ch_acc += v0.y * v0.y, ch_acc += v0.z * v0.z, ch_acc += v0.w * v0.w;
+      ch_acc += v1.x * v1.x, ch_acc += v1.y * v1.y, ch_acc += v1.z * v1.z, ch_acc += v1.w * v1.w;
+      ch_acc += v2.x * v2.x, ch_acc += v2.y * v2.y, ch_acc += v2.z * v2.z, ch_acc += v2.w * v2.w;
+      ch_acc += v3.x * v3.x, ch_acc += v3.y * v3.y, ch_acc += v3.z * v3.z, ch_acc += v3.w * v3.w;
+      if (ch_blk == 29 && chain_c) {
+        sm.xx[f] = ch_acc;
+        sm.xr[f * kLpStride + 432] = ch_acc;  // yy_lookup[0]
+      }
+    }
+    if (chain_b) {
+      if (ch_blk < 30 || !recur_b) return;  // the recurrence waits for P6's candidates
+      // candidate runs exactly as P8 walks them
+      const int lo0 = 2 * sm.best0[f] - 2, lo1 = 2 * sm.best1[f] - 2;
+      const int r1 = lo0 < lo1 ? lo0 : lo1, r2 = lo0 < lo1 ? lo1 : lo0;
+      auto clampi = [](int v) { return v < 0 ? 0 : (v > 294 ? 294 : v); };
+      const int a0 = clampi(r1), b0 = clampi(r2 > r1 + 5 ? r2 : r1 + 5), last = clampi(r2 + 5);
+      float syy = ch_acc;
+      for (int i0 = 0; i0 < last; i0 += 4) {
+        const f4 ya = ld4(y + i0 + 480), yb = ld4(y + i0);
+        const float d[4] = {ya.x * ya.x - yb.x * yb.x, ya.y * ya.y - yb.y * yb.y, ya.z * ya.z - yb.z * yb.z,
+                            ya.w * ya.w - yb.w * yb.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          if ((unsigned)(i - a0) < 5u) sm.s10[f][i - a0] = syy;
+          if ((unsigned)(i - b0) < 5u) sm.s10[f][5 + i - b0] = syy;
+          syy += d[u];
+          syy = syy < 1.f ? 1.f : syy;
+        }
+      }
+      ch_blk = 1000;
+    } else {
+      float *yyl = sm.xr + f * kLpStride + 432;  // yy_lookup[0..384]
+      for (; budget > 0 && ch_blk < 30 + 24; budget--, ch_blk++) {
+        const int i1 = 1 + 16 * (ch_blk - 30);
+        float yy = ch_acc;
+#pragma unroll
+        for (int h = 0; h < 4; h++) {  // lags i0..i0+3: x[-i] and x[480-i] come as two aligned float4s
+          const int i0 = i1 + 4 * h;
+          const f4 a = ld4(y - i0 - 3), c = ld4(y + 477 - i0);
+          const float av[4] = {a.w * a.w, a.z * a.z, a.y * a.y, a.x * a.x};
+          const float cv[4] = {c.w * c.w, c.z * c.z, c.y * c.y, c.x * c.x};
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            yy = yy + av[u] - cv[u];
+            yyl[i0 + u] = yy < 0.f ? 0.f : yy;
+          }
+        }
+        ch_acc = yy;
+      }
+    }
+  };
   // P5: a10 coarse cross-correlation, 147 lags x 240 taps, eight lags per lane.  In its shadow the
   // last warp (idle when NT > 19 R + 32) runs the coarse find_best_pitch's Syy recurrence (it only needs y4).
   if (tid >= NT - 32) {
@@ -591,7 +717,9 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     *reinterpret_cast<f4 *>(dst) = f4{a[0], a[1], a[2], a[3]};
     *reinterpret_cast<f4 *>(dst + 4) = f4{a[4], a[5], a[6], a[7]};
   }
+  chain_run(25, false);
   Simt::cta_sync();
+  NS_PHASE_MARK(7);
   // P6: find_best_pitch on the coarse correlation (one lane per frame)
   if (tid < nfr) {
     const int f = tid;
@@ -612,18 +740,10 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     sm.best0[f] = b.p0;
     sm.best1[f] = b.p1;
   }
+  chain_run(20, false);  // B's sum of squares completes here; C keeps a share for P7
   Simt::cta_sync();
-  // P7: fine search, at most ten lags around 2*best0 and 2*best1.  In its shadow the last warp runs
-  // the fine pass's Syy recurrence and remove_doubling's xx (= sum x[j]^2, the same products and order as
-  // the inner product of x with itself).
-  if (tid >= NT - 32) {
-    const int l = tid - (NT - 32);
-    if (l < nfr) {  // Syy before every fine lag -> the 4x-decimated row, dead since P6
-      const float *y = sm.xlp + l * kLpStride;
-      syy_recurrence(sumsq_from<480>(1.f, y), y, 480, 294, sm.xr + l * kLpStride);
-    } else if (l >= 16 && l - 16 < nfr)
-      sm.xx[l - 16] = sumsq_from<480>(0.f, sm.xlp + (l - 16) * kLpStride + 384);
-  }
+  NS_PHASE_MARK(8);
+  // P7: fine search, at most ten lags around 2*best0 and 2*best1 (chain C finishes in its shadow)
   for (int it = tid; it < nfr * 10; it += NT) {
     const int f = it / 10, c = it - f * 10;
     const float *lp = sm.xlp + f * kLpStride;
@@ -636,7 +756,9 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     sm.fi[f][c] = ok ? i : -1;
     sm.fx[f][c] = sum < -1.f ? -1.f : sum;
   }
+  chain_run(1000, true);
   Simt::cta_sync();
+  NS_PHASE_MARK(9);
   // P8: find_best_pitch on the fine correlation (zero outside the candidates), pseudo-interpolation
   if (tid < nfr) {
     const int f = tid;
@@ -650,20 +772,19 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     };
     Best2 b;
     best_init(b);
-    // only the two runs of five candidate lags are compared; Syy before each lag is in the scratch row
-    const float *sb = sm.xr + f * kLpStride;
+    // only the two runs of five candidate lags are compared; Syy before each of them came from chain B
     const int r1 = lo0 < lo1 ? lo0 : lo1, r2 = lo0 < lo1 ? lo1 : lo0;
     auto clampi = [](int v) { return v < 0 ? 0 : (v > 294 ? 294 : v); };
     const int a0 = clampi(r1), a1 = clampi(r1 + 5), b0 = clampi(r2 > r1 + 5 ? r2 : r1 + 5), b1 = clampi(r2 + 5);
-    auto checked = [&](int from, int to) {
+    auto checked = [&](int from, int to, const float *syy) {
       for (int i = from; i < to; i++) {
         const float xc = xcorr_at(i);
         const float x16 = xc * 1e-12f;
-        best_insert_sel(b, xc > 0.f, x16 * x16, sb[i], i);
+        best_insert_sel(b, xc > 0.f, x16 * x16, syy[i - from], i);
       }
     };
-    checked(a0, a1);
-    checked(b0, b1);
+    checked(a0, a1, sm.s10[f]);
+    checked(b0, b1, sm.s10[f] + 5);
     const int bp = b.p0;
     int offset = 0;
     if (bp > 0 && bp < 293) {
@@ -679,6 +800,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     sm.T0[f] = T0;
   }
   Simt::cta_sync();
+  NS_PHASE_MARK(10);
   // P9 (a11 remove_doubling): xx came from the helper warp above; xy(T0) is one more item of the work list
   // P10: the candidate work list, one lane per (frame, k).  k is examined iff T0/k stays >= 30 (T1 is
   // non-increasing in k, so this equals upstream's break).  Every k contributes the three consecutive
@@ -705,31 +827,12 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     }
   }
   Simt::cta_sync();
-  // P11: the inner products on the worker warps; meanwhile the last warp runs the serial yy_lookup
-  // recurrence, which only P12 needs.  Jobs 0..7: triples of bucket j % 4, half j / 4; jobs 8..11:
+  NS_PHASE_MARK(11);
+  // P11: the inner products on the worker warps.  Jobs 0..7: triples of bucket j % 4, half j / 4; jobs 8..11:
   // singles of bucket j - 8.  Worker warp w takes jobs w, w + nwork, ...
   {
-    static_assert(NT >= 160, "four worker warps + the helper warp");
-    const int nwork = NT / 32 - 1, w = tid >> 5, lane = tid & 31;
-    if (w == nwork) {
-      if (lane < nfr) {
-        const int f = lane;
-        const float *x = sm.xlp + f * kLpStride + 384;
-        float *yyl = sm.xr + f * kLpStride + 432;  // yy_lookup[0..384]
-        float yy = sm.xx[f];
-        yyl[0] = yy;
-        for (int i0 = 1; i0 <= 384; i0 += 4) {  // lags i0..i0+3: x[-i] and x[480-i] come as two aligned float4s
-          const f4 a = ld4(x - i0 - 3), c = ld4(x + 477 - i0);
-          const float av[4] = {a.w * a.w, a.z * a.z, a.y * a.y, a.x * a.x};
-          const float cv[4] = {c.w * c.w, c.z * c.z, c.y * c.y, c.x * c.x};
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            yy = yy + av[u] - cv[u];
-            yyl[i0 + u] = yy < 0.f ? 0.f : yy;
-          }
-        }
-      }
-    } else {
+    const int nwork = NW > 4 ? NW - 3 : NW, w = tid >> 5, lane = tid & 31;
+    if (w < nwork) {
       for (int job = w; job < 12; job += nwork) {
         if (job < 8) {
           const int bkt = job & 3, n = sm.n_tri[bkt];
@@ -771,6 +874,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     }
   }
   Simt::cta_sync();
+  NS_PHASE_MARK(12);
   // P12: per candidate k: gain, the pitch gain it would report, refined pitch index -> table
   for (int it = tid; it < nfr * 16; it += NT) {
     const int f = it >> 4, k = it & 15;  // k == 0 writes the header
@@ -819,6 +923,7 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     e[1] = f2u(g);
     e[2] = f2u(pg);
   }
+  NS_PHASE_MARK(13);
 }
 
 // =================================================================================================
