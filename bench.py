@@ -443,6 +443,9 @@ def run_b200(args):
         tr = traffic_tab.get(name)
         if tr and tr.get("streams") == n_streams:
             ent["dram_bytes_per_launch_ncu"] = tr["dram_bytes_per_launch"] * frames_per_launch / tr["frames_per_launch"]
+            # what actually limits the kernel (ncu --set full of one isolated launch, profiles/): per cent of peak
+            ent["ncu_limiters_pct"] = {k: tr[k] for k in ("issue_active_pct", "smem_wavefronts_pct_of_peak", "fma_pipe_pct",
+                                                          "tensor_pipe_pct", "dram_throughput_pct") if tr.get(k) == tr.get(k) and tr.get(k) is not None}
         kernels.append(ent)
     kernels.sort(key=lambda e: -e["ms_total"])
     dom = kernels[0]
@@ -450,7 +453,7 @@ def run_b200(args):
                 "frac": dom["hbm_algorithmic_gbs"] / hbm_peak, "traffic": dom.get("dram_bytes_per_launch_ncu"),
                 "peak_source": peak_src, "kernel": dom["kernel"],
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_FRAME * dom["frames_per_launch"],
-                "avg_launch_us": dom["avg_launch_us"],
+                "avg_launch_us": dom["avg_launch_us"], "ncu_limiters_pct": dom.get("ncu_limiters_pct"),
                 "note": "algorithmic bytes = 3,844 B per (stream, frame) (480 f32 in + 480 f32 out + VAD) x the frames "
                         "one launch covers / that kernel's mean launch time (CUDA events on its own stream, inside the "
                         "timed region, kernels of neighbouring chunks running concurrently). No kernel of this path "

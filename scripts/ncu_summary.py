@@ -50,7 +50,12 @@ for r in rows[2:]:
                  f"{num(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
                  f"{num(r, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | {top} |")
     traffic[name] = {"dram_bytes_per_launch": rd + wr, "streams": n_streams, "frames_per_launch": frames,
-                     "gpu_time_us_isolated": t * 1e6}
+                     "gpu_time_us_isolated": t * 1e6,
+                     "issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                     "smem_wavefronts_pct_of_peak": num(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+                     "fma_pipe_pct": num(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                     "tensor_pipe_pct": num(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                     "dram_throughput_pct": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}
 open(out_md, "a").write("\n".join(lines) + "\n")
 if traffic_json:
     json.dump(traffic, open(traffic_json, "w"), indent=1)
