@@ -184,7 +184,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "stream-seconds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -484,13 +484,29 @@ def run_b200(args):
         "cpu_baseline": cpu_baseline,
         "parity_vs_oracle": parity, "wall_s_timed_region": t_wall,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the real stdout; everything else printed while the bench runs (NCCL's version
+    banner comes from C code, past sys.stdout) was routed to stderr by main()."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # stdout must hold exactly one JSON line
     if args.impl == "reference":
         run_reference(args)
     else:
