@@ -205,6 +205,14 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = []
+    if world > 1:  # one process per GPU: keep this rank's pinned host buffers on the GPU's own NUMA node
+        from crispy_b200.shard import bind_to_gpu_numa_node
+        try:
+            pr = torch.cuda.get_device_properties(local)  # CUDA's own enumeration, not NVML's
+            numa_cpus = bind_to_gpu_numa_node(f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        except Exception:
+            numa_cpus = []
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL only carries the timing barrier / max here; keep its banner ("NCCL version ...") off stdout,
@@ -318,7 +326,8 @@ def run_b200(args):
                "h2d_bytes_per_step": n_streams * e2e_frames * FRAME * 4,
                "d2h_bytes_per_step": n_streams * e2e_frames * (FRAME * 4 + 4),
                "seconds_per_stream": e2e_frames / 100.0,
-               "api": "BatchDenoiser.process_streams_host -> crispy_ns_process_streams_host (pinned host buffers)"}
+               "api": "BatchDenoiser.process_streams_host -> crispy_ns_process_streams_host (pinned host buffers)",
+               "rank0_cpus_bound": len(numa_cpus)}
         if rank == 0:
             e2e["matches_device_path"] = bool(torch.equal(hout[:4], out[:4, :e2e_frames * FRAME].cpu()))
 

@@ -58,3 +58,14 @@ def test_two_ranks_partition_and_reduce_like_bench():
     t_max, id_sum, count = q.get(timeout=10)
     assert t_max == 0.5 and count == n and id_sum == n * (n - 1) // 2
     assert job_rate([513 * 60.0, 513 * 60.0], [0.25, 0.5]) == n * 60.0 / 0.5
+
+
+def test_cpulist_parser_and_numa_binding_is_harmless():
+    from crispy_b200.shard import bind_to_gpu_numa_node, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("") == []
+    import os
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node("0000:ff:1f.7") == []  # no such device: affinity untouched
+    assert os.sched_getaffinity(0) == before
+
