@@ -330,6 +330,31 @@ def run_b200(args):
                "rank0_cpus_bound": len(numa_cpus)}
         if rank == 0:
             e2e["matches_device_path"] = bool(torch.equal(hout[:4], out[:4, :e2e_frames * FRAME].cpu()))
+        # the same leg with PCM16 on the link (CRISPY_NS_IN_I16 | CRISPY_NS_OUT_I16: what the recorder stores,
+        # recording.rs:101-121): half the bytes per stream-second, so the PCIe ceiling doubles.  Reported beside
+        # the f32 figure, not instead of it.
+        hx16 = torch.empty((n_streams, e2e_frames * FRAME), dtype=torch.int16).pin_memory()
+        hx16.copy_((hx * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+        hout16 = torch.empty_like(hx16).pin_memory()
+
+        def e2e16_step():
+            den.reset_async()
+            den.process_streams_host(hx16, unit_scale=True, out=hout16, vad=hvad, out_i16=True)
+
+        e2e16_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e16_step()
+        barrier()
+        dt16 = time.perf_counter() - t0
+        tt = torch.tensor([dt16], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e["pcm16_link"] = {"value": world * n_streams * e2e_frames / 100.0 * args.steps / float(tt.item()),
+                             "unit": "stream-seconds/s", "h2d_bytes_per_step": n_streams * e2e_frames * FRAME * 2,
+                             "d2h_bytes_per_step": n_streams * e2e_frames * (FRAME * 2 + 4)}
+        del hx16, hout16
 
     # ---- the same kernels one at a time (one stream): isolated durations, comparable with the ncu
     # launch list under profiles/ (inside the timed region above they overlap 7 deep and share SMs) ----
