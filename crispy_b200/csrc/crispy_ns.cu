@@ -90,17 +90,20 @@ __global__ void ns_linear_resample_kernel(const float *__restrict__ in, float *_
 template <int Q>
 __global__ void __launch_bounds__(1024) ns_sinc_resample_kernel(const float *__restrict__ in, float *__restrict__ out,
                                                                 const float *__restrict__ hT,  // [sinc_len][L]
-                                                                long long n_in, long long n_out, long long in_stride,
+                                                                long long n_total, long long in_first,
+                                                                long long first_out, long long n_out, long long in_stride,
                                                                 long long out_stride, int L, int M, int sinc_len,
                                                                 int span) {
+  // the recording has n_total input samples; in[0] is its sample in_first; outputs first_out .. first_out + n_out
+  // (first_out a multiple of L) are written to out[0 .. n_out)
   extern __shared__ float xs[];
   const int T = blockDim.x, t = threadIdx.x;
-  const long long n0 = (long long)blockIdx.x * T * Q;      // multiple of L
-  const long long base0 = n0 / L * M - sinc_len / 2 + 1;   // input index of xs[0]
-  const float *src = in + (long long)blockIdx.y * in_stride;
+  const long long n0 = first_out + (long long)blockIdx.x * T * Q;  // multiple of L
+  const long long base0 = n0 / L * M - sinc_len / 2 + 1;           // recording index of xs[0]
+  const float *src = in + (long long)blockIdx.y * in_stride - in_first;
   for (int i = t; i < span; i += T) {
     const long long g = base0 + i;
-    xs[i] = (g >= 0 && g < n_in) ? __ldg(src + g) : 0.f;
+    xs[i] = (g >= 0 && g < n_total) ? __ldg(src + g) : 0.f;
   }
   __syncthreads();
   const int pos = t * M;  // t < 1024, M < 2^20
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(1024) ns_sinc_resample_kernel(const float *__r
   float *dst = out + (long long)blockIdx.y * out_stride;
 #pragma unroll
   for (int q = 0; q < Q; q++) {
-    const long long n = n0 + t + (long long)q * T;
+    const long long n = n0 + t + (long long)q * T - first_out;
     if (n < n_out) dst[n] = acc[q];
   }
 }
@@ -979,10 +982,34 @@ int64_t crispy_ns_sinc_resample_count(int input_rate, int output_rate, int64_t n
   if (n_in <= 0 || !reduce_ratio(input_rate, output_rate, &L, &M)) return 0;
   return (int64_t)(((unsigned long long)n_in * (unsigned)L + (unsigned)M - 1) / (unsigned)M);
 }
-int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
-                            int64_t in_stride, int64_t out_stride, int input_rate, int output_rate,
-                            int sinc_len, float f_cutoff, void *cuda_stream) {
-  if (!d_in || !d_out || n_streams < 1 || n_in < 0) return fail(CRISPY_NS_EINVAL, "sinc_resample: bad argument");
+int crispy_ns_sinc_resample_needed(int input_rate, int output_rate, int sinc_len, int64_t n_total, int64_t first_out,
+                                   int64_t n_out, int64_t *in_first, int64_t *n_in) {
+  int L, M;
+  if (sinc_len == 0) sinc_len = 256;
+  if (!reduce_ratio(input_rate, output_rate, &L, &M) || n_total < 0 || first_out < 0 || n_out < 0 || sinc_len < 2 || (sinc_len & 1))
+    return fail(CRISPY_NS_EINVAL, "sinc_resample_needed: bad argument");
+  if (n_out == 0) {
+    if (in_first) *in_first = 0;
+    if (n_in) *n_in = 0;
+    return CRISPY_NS_OK;
+  }
+  const long long half = sinc_len / 2;
+  long long lo = (long long)((unsigned long long)first_out * (unsigned)M / (unsigned)L) - half + 1;
+  long long hi = (long long)((unsigned long long)(first_out + n_out - 1) * (unsigned)M / (unsigned)L) + half + 1;  // exclusive
+  if (lo < 0) lo = 0;
+  if (hi > n_total) hi = n_total;
+  if (hi < lo) hi = lo;
+  if (in_first) *in_first = lo;
+  if (n_in) *n_in = hi - lo;
+  return CRISPY_NS_OK;
+}
+
+int crispy_ns_sinc_resample_chunk(int device, const float *d_in, int64_t in_first, int64_t n_in, int64_t n_total,
+                                  float *d_out, int64_t first_out, int64_t n_out, int n_streams, int64_t in_stride,
+                                  int64_t out_stride, int input_rate, int output_rate, int sinc_len, float f_cutoff,
+                                  void *cuda_stream) {
+  if (!d_in || !d_out || n_streams < 1 || n_in < 0 || n_total < 0 || in_first < 0 || first_out < 0 || n_out < 0)
+    return fail(CRISPY_NS_EINVAL, "sinc_resample: bad argument");
   if (sinc_len == 0) sinc_len = 256;
   if (f_cutoff == 0.f) f_cutoff = 0.95f;
   if (sinc_len < 2 || sinc_len > 2048 || (sinc_len & 1) || !(f_cutoff > 0.f) || f_cutoff > 1.f)
@@ -991,12 +1018,21 @@ int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_s
   if (!reduce_ratio(input_rate, output_rate, &L, &M))
     return fail(CRISPY_NS_EINVAL, "sinc_resample: output_rate/input_rate must reduce to L/M with L <= 1024");
   if (M >= (1 << 20)) return fail(CRISPY_NS_EINVAL, "sinc_resample: ratio too extreme");
+  if (first_out % L) return fail(CRISPY_NS_EINVAL, "sinc_resample: first_out must be a multiple of L (a whole number of periods)");
+  if (first_out + n_out > crispy_ns_sinc_resample_count(input_rate, output_rate, n_total))
+    return fail(CRISPY_NS_EINVAL, "sinc_resample: outputs beyond the end of the recording");
+  {
+    int64_t need_first = 0, need_n = 0;
+    crispy_ns_sinc_resample_needed(input_rate, output_rate, sinc_len, n_total, first_out, n_out, &need_first, &need_n);
+    if (need_n > 0 && (need_first < in_first || need_first + need_n > in_first + n_in))
+      return fail(CRISPY_NS_EINVAL, "sinc_resample: the input window does not cover the taps of the requested outputs "
+                                    "(crispy_ns_sinc_resample_needed gives the range)");
+  }
   const int ndev = crispy_ns_device_count();
   if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
   NS_CUDA(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  const int64_t n_out = crispy_ns_sinc_resample_count(input_rate, output_rate, n_in);
   if (n_out == 0) return CRISPY_NS_OK;
   float *d_taps = nullptr;
   {
@@ -1031,8 +1067,8 @@ int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_s
     if (smem > 48 * 1024)                                                                                \
       NS_CUDA(cudaFuncSetAttribute(ns_sinc_resample_kernel<QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)smem));                                                          \
-    ns_sinc_resample_kernel<QQ><<<grid, T, smem, st>>>(d_in, d_out, d_taps, n_in, n_out, in_stride,      \
-                                                       out_stride, L, M, sinc_len, (int)span);           \
+    ns_sinc_resample_kernel<QQ><<<grid, T, smem, st>>>(d_in, d_out, d_taps, n_total, in_first, first_out, n_out, \
+                                                       in_stride, out_stride, L, M, sinc_len, (int)span); \
   } while (0)
   switch (Q) {
     case 8: NS_SINC_LAUNCH(8); break;
@@ -1043,6 +1079,18 @@ int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_s
 #undef NS_SINC_LAUNCH
   NS_CUDA(cudaGetLastError());
   return CRISPY_NS_OK;
+}
+
+int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
+                            int64_t in_stride, int64_t out_stride, int input_rate, int output_rate,
+                            int sinc_len, float f_cutoff, void *cuda_stream) {
+  if (n_in < 0) return fail(CRISPY_NS_EINVAL, "sinc_resample: bad argument");
+  int L, M;
+  if (!reduce_ratio(input_rate, output_rate, &L, &M))
+    return fail(CRISPY_NS_EINVAL, "sinc_resample: output_rate/input_rate must reduce to L/M with L <= 1024");
+  return crispy_ns_sinc_resample_chunk(device, d_in, 0, n_in, n_in, d_out, 0,
+                                       crispy_ns_sinc_resample_count(input_rate, output_rate, n_in), n_streams, in_stride,
+                                       out_stride, input_rate, output_rate, sinc_len, f_cutoff, cuda_stream);
 }
 
 int crispy_ns_resample_host(int device, const float *h_in, float *h_out, int n_streams, int64_t n_in,

@@ -172,6 +172,31 @@ def sinc_resample(x, input_rate: int, output_rate: int, sinc_len: int = 256, f_c
     return out
 
 
+def sinc_needed(input_rate: int, output_rate: int, n_total: int, first_out: int, n_out: int, sinc_len: int = 256):
+    """(in_first, n_in): the input samples the taps of outputs first_out .. first_out + n_out touch."""
+    a, b = C.c_int64(), C.c_int64()
+    check(_lib.lib().crispy_ns_sinc_resample_needed(int(input_rate), int(output_rate), int(sinc_len), int(n_total),
+                                                    int(first_out), int(n_out), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def sinc_resample_chunk(x_window, in_first: int, n_total: int, first_out: int, n_out: int, input_rate: int,
+                        output_rate: int, sinc_len: int = 256, f_cutoff: float = 0.95):
+    """Outputs first_out .. first_out + n_out of a long recording from the window of it that is on the GPU
+    (x_window[:, 0] is the recording's sample in_first).  Chunked calls reproduce sinc_resample bit for bit."""
+    import torch
+    if not x_window.is_cuda or x_window.dtype != torch.float32 or x_window.dim() != 2 or x_window.stride(1) != 1:
+        raise CrispyNsError("sinc_resample_chunk needs a CUDA float32 [n_streams, n_in] tensor")
+    n_streams, n_in = x_window.shape
+    out = torch.empty((n_streams, n_out), dtype=torch.float32, device=x_window.device)
+    st = torch.cuda.current_stream(x_window.device).cuda_stream
+    check(_lib.lib().crispy_ns_sinc_resample_chunk(x_window.device.index or 0, x_window.data_ptr(), int(in_first), n_in,
+                                                   int(n_total), out.data_ptr(), int(first_out), int(n_out), n_streams,
+                                                   x_window.stride(0), out.stride(0) if n_out else 0, int(input_rate),
+                                                   int(output_rate), int(sinc_len), float(f_cutoff), st))
+    return out
+
+
 def resample_host(x, input_rate: int, output_rate: int, kind: str = "sinc", device: int = 0):
     """Host-array front end (crispy_ns_resample_host): x is a host f32 array [n_streams, n_in]; returns a numpy
     array [n_streams, n_out].  kind: "linear" (audio.rs:108-133) or "sinc"."""

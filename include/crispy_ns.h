@@ -158,6 +158,17 @@ int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_s
                             int64_t in_stride, int64_t out_stride, int input_rate, int output_rate,
                             int sinc_len, float f_cutoff, void *cuda_stream);
 
+/* the same for a recording that does not fit one call: the recording has n_total input samples, d_in[s][0] is its
+ * sample in_first and n_in samples are present; outputs first_out .. first_out + n_out (first_out a whole number of
+ * periods, i.e. a multiple of L: any multiple of 480 for 44.1 -> 48 kHz) go to d_out[s][0 ..).  Samples outside
+ * [0, n_total) count as zeros; crispy_ns_sinc_resample_needed gives the input range the outputs' taps touch.
+ * Chunked calls reproduce the whole-recording call bit for bit. */
+int crispy_ns_sinc_resample_needed(int input_rate, int output_rate, int sinc_len, int64_t n_total, int64_t first_out,
+                                   int64_t n_out, int64_t *in_first, int64_t *n_in);
+int crispy_ns_sinc_resample_chunk(int device, const float *d_in, int64_t in_first, int64_t n_in, int64_t n_total,
+                                  float *d_out, int64_t first_out, int64_t n_out, int n_streams, int64_t in_stride,
+                                  int64_t out_stride, int input_rate, int output_rate, int sinc_len, float f_cutoff,
+                                  void *cuda_stream);
 /* host-pointer convenience over the two front ends (what the Rust side calls for recordings in RAM):
  * kind 0 = linear (audio.rs:108-133), 1 = windowed sinc (defaults 256 taps, cutoff 0.95).  Synchronous;
  * h_out must hold crispy_ns_{linear,sinc}_resample_count samples per stream. */

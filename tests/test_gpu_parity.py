@@ -203,6 +203,24 @@ def test_sinc_resample_is_bit_exact():  # north_star item 4; oracle: rno_sinc_re
     assert np.array_equal(y[2], po.sinc_resample(x[2, 100:5000], 44100, 48000, 64, 0.9))
 
 
+def test_sinc_resample_chunks_reproduce_the_whole_call():
+    """A recording too long for one call: outputs in chunks of whole periods from the input window their taps touch."""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((3, 44100)).astype(np.float32)
+    whole = cb.sinc_resample(_dev(x), 44100, 48000)
+    n_total, n_out_total = x.shape[1], whole.shape[1]
+    pieces, first = [], 0
+    for n_out in (480 * 7, 160, 480 * 40, n_out_total):  # the last one is clipped to what is left
+        n_out = min(n_out, n_out_total - first)
+        lo, n_in = cb.sinc_needed(44100, 48000, n_total, first, n_out)
+        pieces.append(cb.sinc_resample_chunk(_dev(x[:, lo:lo + n_in]), lo, n_total, first, n_out, 44100, 48000))
+        first += n_out
+    assert first == n_out_total
+    assert torch.equal(torch.cat(pieces, 1), whole)
+    with pytest.raises(cb.CrispyNsError):  # window too short for the taps
+        cb.sinc_resample_chunk(_dev(x[:, 5000:6000]), 5000, n_total, 4800, 4800, 44100, 48000)
+
+
 def test_resample_host_matches_device_paths():
     rng = np.random.default_rng(2)
     x = rng.standard_normal((3, 4410)).astype(np.float32)

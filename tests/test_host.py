@@ -90,3 +90,22 @@ def test_wav_roundtrip_and_header(tmp_path):  # recording.rs:406-480
         cb.wav_write_pcm16(p, np.zeros(3, np.int16), channels=2)
     with pytest.raises(cb.CrispyNsError):
         cb.wav_read_pcm16(str(tmp_path / "missing.wav"))
+
+
+def test_sinc_front_end_geometry_and_argument_checks():  # no device needed: validation comes first
+    L = _lib.lib()
+    assert L.crispy_ns_sinc_resample_count(44100, 48000, 441) == 480
+    assert L.crispy_ns_sinc_resample_count(48000, 16000, 300) == 100
+    assert L.crispy_ns_sinc_resample_count(44100, 48000, 0) == 0
+    assert L.crispy_ns_sinc_resample_count(44101, 48000, 100) == 0  # L = 48000 > 1024: unsupported ratio
+    assert cb.sinc_needed(44100, 48000, 441000, 4800, 4800) == (4283, 4665)
+    assert cb.sinc_needed(44100, 48000, 441000, 0, 480) == (0, 441 + 128)  # clipped at the start of the recording
+    assert cb.sinc_needed(44100, 48000, 441, 0, 480) == (0, 441)            # and at its end
+    fake = 16  # never dereferenced: the argument checks fail first
+    assert L.crispy_ns_sinc_resample_chunk(0, fake, 0, 441, 441, fake, 7, 160, 1, 441, 480, 44100, 48000, 0, 0.0, None) == -1
+    assert b"multiple of L" in L.crispy_ns_last_error()
+    assert L.crispy_ns_sinc_resample_chunk(0, fake, 0, 441, 441, fake, 0, 481, 1, 441, 481, 44100, 48000, 0, 0.0, None) == -1
+    assert L.crispy_ns_sinc_resample_chunk(0, fake, 100, 341, 441, fake, 0, 480, 1, 441, 480, 44100, 48000, 0, 0.0, None) == -1
+    assert b"window" in L.crispy_ns_last_error()
+    assert L.crispy_ns_sinc_resample(0, fake, fake, 1, 441, 441, 480, 44100, 48000, 7, 0.0, None) == -1  # odd sinc_len
+
