@@ -1407,55 +1407,59 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
       const f4 *src4 = reinterpret_cast<const f4 *>(s.spec[0]);  // X[482] | P[482]: 482 float4
       for (int k = g.tid; k < kSpecStride; k += kGroupThreads) dst4[k] = src4[k];
     }
-    if (g.tid < kBands) {
-      const int i = g.tid;
-      s.Exp[i] = s.Exp[i] / (float)sqrt(.001 + (double)(s.Ex[i] * s.Ep[i]));
-      s.Ly[i] = (float)log10(1e-2 + (double)s.Ex[i]);
-    }
-    gsync(g);
-    if (g.tid == 0) {
-      float logMax = -2.f, follow = -2.f, E = 0.f;
-      for (int i = 0; i < kBands; i++) {
-        float ly = s.Ly[i];
-        ly = fmaxf(logMax - 7.f, fmaxf(follow - 1.5f, ly));
-        logMax = fmaxf(logMax, ly);
-        follow = fmaxf(follow - 1.5f, ly);
-        s.Ly[i] = ly;
-        E += s.Ex[i];
+    // band features: warp 0 alone, meeting on warp barriers, while the other warps finish the spectra store and
+    // start on the next frame (nothing written below is touched again before several group barriers have passed,
+    // and warp 0 joins the next frame's first barrier only after it is done here)
+    if (g.warp == 0) {
+      const int i = g.lane;
+      if (i < kBands) {
+        s.Exp[i] = s.Exp[i] / (float)sqrt(.001 + (double)(s.Ex[i] * s.Ep[i]));
+        s.Ly[i] = (float)log10(1e-2 + (double)s.Ex[i]);
       }
-      s.silence = (E < 0.04f) ? 1 : 0;
-    }
-    gsync(g);
-    if (g.tid < kBands) {
-      const int i = g.tid;
-      float sum = 0.f;
-      for (int j = 0; j < kBands; j++) sum += s.Ly[j] * T.dct(j * kBands + i);
-      float c = sum * dct_scale;
-      if (i == 0) c -= 12.f;
-      if (i == 1) c -= 4.f;
-      rec[kRecCeps + i] = c;
-      rec[kRecExp + i] = s.Exp[i];
-      rec[kRecEx + i] = s.Ex[i];
-      rec[kRecEp + i] = s.Ep[i];
-      if (p.dbg) {
-        float *d = p.dbg + ((long long)stream * p.n_frames_call + p.frame0 + t) * kDbgFloats;
-        d[kDbgEx + i] = s.Ex[i];
-        d[kDbgEp + i] = s.Ep[i];
-        d[kDbgExp + i] = s.Exp[i];
+      Simt::warp_sync();
+      if (i == 0) {
+        float logMax = -2.f, follow = -2.f, E = 0.f;
+        for (int j = 0; j < kBands; j++) {
+          float ly = s.Ly[j];
+          ly = fmaxf(logMax - 7.f, fmaxf(follow - 1.5f, ly));
+          logMax = fmaxf(logMax, ly);
+          follow = fmaxf(follow - 1.5f, ly);
+          s.Ly[j] = ly;
+          E += s.Ex[j];
+        }
+        s.silence = (E < 0.04f) ? 1 : 0;
       }
-    } else if (g.tid >= 32 && g.tid < 32 + kDeltaCeps) {
-      const int i = g.tid - 32;
-      float sum = 0.f;
-      for (int j = 0; j < kBands; j++) sum += s.Exp[j] * T.dct(j * kBands + i);
-      float c = sum * dct_scale;
-      if (i == 0) c -= 1.3f;
-      if (i == 1) c -= 0.9f;
-      rec[kRecTail + i] = c;
-    } else if (g.tid == 40) {
-      rec[kRecTail + kDeltaCeps] = .01f * (float)(pitch_index - 300);
-      reinterpret_cast<int *>(rec)[kRecSilence] = s.silence;
+      Simt::warp_sync();
+      if (i < kBands) {
+        float sum = 0.f;
+        for (int j = 0; j < kBands; j++) sum += s.Ly[j] * T.dct(j * kBands + i);
+        float c = sum * dct_scale;
+        if (i == 0) c -= 12.f;
+        if (i == 1) c -= 4.f;
+        rec[kRecCeps + i] = c;
+        rec[kRecExp + i] = s.Exp[i];
+        rec[kRecEx + i] = s.Ex[i];
+        rec[kRecEp + i] = s.Ep[i];
+        if (p.dbg) {
+          float *d = p.dbg + ((long long)stream * p.n_frames_call + p.frame0 + t) * kDbgFloats;
+          d[kDbgEx + i] = s.Ex[i];
+          d[kDbgEp + i] = s.Ep[i];
+          d[kDbgExp + i] = s.Exp[i];
+        }
+      } else if (i < kBands + kDeltaCeps) {
+        const int c6 = i - kBands;
+        float sum = 0.f;
+        for (int j = 0; j < kBands; j++) sum += s.Exp[j] * T.dct(j * kBands + c6);
+        float c = sum * dct_scale;
+        if (c6 == 0) c -= 1.3f;
+        if (c6 == 1) c -= 0.9f;
+        rec[kRecTail + c6] = c;
+      } else if (i == kBands + kDeltaCeps) {
+        rec[kRecTail + kDeltaCeps] = .01f * (float)(pitch_index - 300);
+        reinterpret_cast<int *>(rec)[kRecSilence] = s.silence;
+      }
+      Simt::warp_sync();  // the next frame's band sums overwrite Ex / Ep / Exp: every lane is done reading first
     }
-    gsync(g);
   }
 }
 
