@@ -1106,12 +1106,37 @@ struct Dft<6> {
   }
 };
 
-// Stockham scatter of one butterfly's outputs; the first stage writes R consecutive bins per thread
-// and uses 16-byte stores (the 8-byte scatter is 4-way bank conflicted there)
+// Stockham scatter of one butterfly's outputs, ordered so that the lanes of one shared-memory transaction hit
+// different banks:
+//  * first stage (NS = 1, R = 4): a thread owns 32 contiguous bytes and writes them as two 16-byte stores; the
+//    upper half of every quarter-warp writes its two halves in the other order (straight order is 2-way conflicted);
+//  * second stage (R = 4, NS = 4): output r of butterfly j = 4g + k goes to bin 16g + k + 4r, so for a fixed r the
+//    sixteen lanes of a half-warp cover only four bank groups (4-way conflict); lane group g therefore writes
+//    its outputs rotated by g, r = (s + g) mod 4 at step s, which makes the sixteen addresses distinct mod 16 bins.
+// The rotations are selects on registers (no dynamic indexing).
 template <int R, int NS_>
 NS_DEV void fft_store(cf *buf, int j, int k, const cf (&v)[R]) {
   const int j0 = (j - k) * R + k;
-  if (NS_ == 1 && (R & 1) == 0) {
+  if (NS_ == 1 && R == 4) {
+    f4 *d = reinterpret_cast<f4 *>(buf + j0);
+    const bool sw = (j & 4) != 0;
+    const f4 lo = f4{v[0].x, v[0].y, v[1].x, v[1].y}, hi = f4{v[2].x, v[2].y, v[3].x, v[3].y};
+    d[sw ? 1 : 0] = sw ? hi : lo;
+    d[sw ? 0 : 1] = sw ? lo : hi;
+  } else if (NS_ == 4 && R == 4) {
+    const int rot = (j >> 2) & 3;
+    cf w[4] = {v[0], v[1], v[2], v[3]};
+    if (rot & 1) {  // w[s] <- w[s + 1]
+      const cf t0 = w[0];
+      w[0] = w[1], w[1] = w[2], w[2] = w[3], w[3] = t0;
+    }
+    if (rot & 2) {  // w[s] <- w[s + 2]
+      const cf t0 = w[0], t1 = w[1];
+      w[0] = w[2], w[1] = w[3], w[2] = t0, w[3] = t1;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++) buf[j0 + ((s + rot) & 3) * 4] = w[s];  // w[s] == v[(s + rot) & 3]
+  } else if (NS_ == 1 && (R & 1) == 0) {
     f4 *d = reinterpret_cast<f4 *>(buf + j0);
 #pragma unroll
     for (int r = 0; r < R; r += 2) d[r >> 1] = f4{v[r].x, v[r].y, v[r + 1].x, v[r + 1].y};
