@@ -1239,9 +1239,10 @@ NS_DEV void rfft960_windowed(const Grp &g, const Tab &T, const float *__restrict
 NS_DEV void rfft960_windowed2(const Grp &g, const Tab &T, const float *win, const float *__restrict__ srcA,
                               const float *__restrict__ srcB, cf *XA, cf *XB, cf *YA, cf *YB) {
   auto load = [&](int n, cf &a, cf &b) {  // win: the half window in shared memory; srcA / srcB in HBM / L2
-    const int i0 = 2 * n;
-    const float w0 = win[(i0 < kFrame) ? i0 : kWindow - 1 - i0];
-    const float w1 = win[(i0 + 1 < kFrame) ? i0 + 1 : kWindow - 2 - i0];
+    const int i0 = 2 * n;  // even: both taps sit in the same half of the symmetric window -> one 8-byte read
+    const bool up = i0 < kFrame;
+    const cf wp = *reinterpret_cast<const cf *>(win + (up ? i0 : kWindow - 2 - i0));
+    const float w0 = up ? wp.x : wp.y, w1 = up ? wp.y : wp.x;
     a = cf{srcA[i0] * w0, srcA[i0 + 1] * w1};
     b = cf{srcB[i0] * w0, srcB[i0 + 1] * w1};
   };
@@ -1302,6 +1303,19 @@ NS_DEV void irfft960_inplace(const Grp &g, const Tab &T, cf *X, cf *Y) {  // Y: 
 // lanes add the partials of the two intervals that touch the band in a fixed order; results are valid
 // in lanes with (tid & 3) == 0, tid < 88.
 constexpr int kSlots = 100;
+// a thread's slot = 32 contiguous bytes (four complex bins) as two 16-byte accesses; the upper half of every
+// quarter-warp takes them in the other order so that the eight lanes of a transaction cover all 32 banks
+NS_DEV void ld_slot(const cf *slot, bool sw, f4 &lo, f4 &hi) {
+  const f4 *q = reinterpret_cast<const f4 *>(slot);
+  const f4 a = q[sw ? 1 : 0], b = q[sw ? 0 : 1];
+  lo = sw ? b : a;
+  hi = sw ? a : b;
+}
+NS_DEV void st_slot(cf *slot, bool sw, f4 lo, f4 hi) {
+  f4 *q = reinterpret_cast<f4 *>(slot);
+  q[sw ? 1 : 0] = sw ? hi : lo;
+  q[sw ? 0 : 1] = sw ? lo : hi;
+}
 constexpr int kPartStride = 104;
 template <int NQ, class BinVal>
 NS_DEV void band_slots(const Grp &g, const Tab &T, float *part, BinVal val) {
@@ -1315,7 +1329,7 @@ NS_DEV void band_slots(const Grp &g, const Tab &T, float *part, BinVal val) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       float v[NQ];
-      val(k0 + u, v);
+      val(u, v);
 #pragma unroll
       for (int q = 0; q < NQ; q++) {
         s0[q] += v[q];
@@ -1383,12 +1397,21 @@ NS_DEV void frame_spectra(const Grp &g, const Tab &T, SpecSmem &s, const float *
   cf *X = s.spec[0], *P = s.spec[0] + kSpecStride;
   // K3 keeps the window where K5 keeps synthesis_mem; spec[1] is the FFT's ping-pong partner
   rfft960_windowed2(g, T, s.synth, cur, cur - pitch_index, X, P, s.spec[1], s.spec[1] + kSpecStride);
-  band_slots<3>(g, T, s.part, [&](int k, float (&v)[3]) {
-    const cf x = X[k], p = P[k];
-    v[0] = fmaf(x.x, x.x, x.y * x.y);
-    v[1] = fmaf(p.x, p.x, p.y * p.y);
-    v[2] = fmaf(x.x, p.x, x.y * p.y);
-  });
+  {
+    f4 xl, xh, pl, ph;
+    const int sl = g.tid < kSlots ? g.tid : 0;
+    const bool sw = (g.tid & 4) != 0;
+    ld_slot(X + 4 * sl, sw, xl, xh);
+    ld_slot(P + 4 * sl, sw, pl, ph);
+    const cf xs[4] = {cf{xl.x, xl.y}, cf{xl.z, xl.w}, cf{xh.x, xh.y}, cf{xh.z, xh.w}};
+    const cf ps[4] = {cf{pl.x, pl.y}, cf{pl.z, pl.w}, cf{ph.x, ph.y}, cf{ph.z, ph.w}};
+    band_slots<3>(g, T, s.part, [&](int u, float (&v)[3]) {  // u: bin within the slot
+      const cf x = xs[u], p = ps[u];
+      v[0] = fmaf(x.x, x.x, x.y * x.y);
+      v[1] = fmaf(p.x, p.x, p.y * p.y);
+      v[2] = fmaf(x.x, p.x, x.y * p.y);
+    });
+  }
   gsync(g);
   float acc[3];
   band_reduce<3>(g, T, s.part, acc);
@@ -1992,25 +2015,28 @@ NS_DEV void pitch_filter_and_gains(const Grp &g, const Tab &T, SpecSmem &s, cf *
     const f4 fr4 = T.bin_frac4(k0);
     const float fr[4] = {fr4.x, fr4.y, fr4.z, fr4.w};
     const float r0 = s.r[b], r1 = s.r[b + 1];
-    f4 *X4 = reinterpret_cast<f4 *>(X + k0);
-    const f4 *P4 = reinterpret_cast<const f4 *>(P + k0);
+    const bool sw = (g.tid & 4) != 0;
+    f4 xq[2], pq[2];
+    ld_slot(X + k0, sw, xq[0], xq[1]);
+    ld_slot(P + k0, sw, pq[0], pq[1]);
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      f4 x = X4[h];
-      const f4 pp = P4[h];
+      f4 x = xq[h];
+      const f4 pp = pq[h];
       const float rfa = (1.f - fr[2 * h]) * r0 + fr[2 * h] * r1, rfb = (1.f - fr[2 * h + 1]) * r0 + fr[2 * h + 1] * r1;
       x.x += rfa * pp.x;
       x.y += rfa * pp.y;
       x.z += rfb * pp.z;
       x.w += rfb * pp.w;
-      X4[h] = x;
+      xq[h] = x;
       const float va = fmaf(x.x, x.x, x.y * x.y), vb = fmaf(x.z, x.z, x.w * x.w);
       s0 += va;
       s1 = fmaf(fr[2 * h], va, s1);
       s0 += vb;
       s1 = fmaf(fr[2 * h + 1], vb, s1);
     }
+    st_slot(X + k0, sw, xq[0], xq[1]);
     s.part[g.tid] = s0 - s1;
     s.part[kPartStride + g.tid] = s1;
   }
@@ -2029,10 +2055,12 @@ NS_DEV void pitch_filter_and_gains(const Grp &g, const Tab &T, SpecSmem &s, cf *
     const f4 fr4 = T.bin_frac4(k0);
     const float fr[4] = {fr4.x, fr4.y, fr4.z, fr4.w};
     const float n0 = s.nrm[b], n1 = s.nrm[b + 1], g0 = rc[kRecG + b], g1 = rc[kRecG + b + 1];
-    f4 *X4 = reinterpret_cast<f4 *>(X + k0);
+    const bool sw = (g.tid & 4) != 0;
+    f4 xq[2];
+    ld_slot(X + k0, sw, xq[0], xq[1]);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      f4 x = X4[h];
+      f4 x = xq[h];
       const float fa = fr[2 * h], fb = fr[2 * h + 1];
       const float nfa = (1.f - fa) * n0 + fa * n1, gfa = (1.f - fa) * g0 + fa * g1;
       const float nfb = (1.f - fb) * n0 + fb * n1, gfb = (1.f - fb) * g0 + fb * g1;
@@ -2040,8 +2068,9 @@ NS_DEV void pitch_filter_and_gains(const Grp &g, const Tab &T, SpecSmem &s, cf *
       x.y = (x.y * nfa) * gfa;
       x.z = (x.z * nfb) * gfb;
       x.w = (x.w * nfb) * gfb;
-      X4[h] = x;
+      xq[h] = x;
     }
+    st_slot(X + k0, sw, xq[0], xq[1]);
   } else {
     for (int k = 400 + (g.tid - kSlots); k < kFreq; k += kGroupThreads - kSlots) X[k] = cf{0.f, 0.f};
   }
