@@ -1006,12 +1006,15 @@ NS_DEV void pitchscan_body(const Params &p, int warps_per_cta) {
 struct SpecTw {
   cf w480[480];
   cf w960[244];
+  cf tw3[64];  // third FFT stage (radix 5, 16 sub-transforms): w480[6 r k] for r = 1..4, k < 16, contiguous in k --
+               // read straight from w480 the sixteen lanes of a half-warp stride 48 r bytes (up to 8-way conflicts)
 };
 struct Tab {
   const SpecTw *s;
   const Tables *g;
   NS_DEV cf w480(int i) const { return s->w480[i]; }
   NS_DEV cf w960(int i) const { return s->w960[i]; }
+  NS_DEV cf tw3(int r, int k) const { return s->tw3[(r - 1) * 16 + k]; }
   NS_DEV float win(int i) const { return Simt::ldg(g->win + i); }
   NS_DEV float dct(int i) const { return Simt::ldg(g->dct + i); }
   NS_DEV int bin_band(int i) const { return Simt::ldg(g->bin_band + i); }
@@ -1162,7 +1165,7 @@ NS_DEV void fft_stage(const Grp &g, const Tab &T, cf *buf, Load load) {
 #pragma unroll
     for (int r = 1; r < R; r++) {
       cf x = load(j + r * M);
-      v[r] = (NS_ == 1) ? x : cmul(x, T.w480(r * k * TSTEP));
+      v[r] = (NS_ == 1) ? x : cmul(x, (R == 5 && NS_ == 16) ? T.tw3(r, k) : T.w480(r * k * TSTEP));
     }
     Dft<R>::run(v);
   }
@@ -1187,7 +1190,7 @@ NS_DEV void fft_stage2(const Grp &g, const Tab &T, cf *bufA, cf *bufB, Load2 loa
     for (int r = 1; r < R; r++) {
       load2(j + r * M, va[r], vb[r]);
       if (NS_ != 1) {
-        const cf w = T.w480(r * k * TSTEP);
+        const cf w = (R == 5 && NS_ == 16) ? T.tw3(r, k) : T.w480(r * k * TSTEP);
         va[r] = cmul(va[r], w);
         vb[r] = cmul(vb[r], w);
       }
@@ -1316,7 +1319,7 @@ NS_DEV void st_slot(cf *slot, bool sw, f4 lo, f4 hi) {
   q[sw ? 1 : 0] = sw ? hi : lo;
   q[sw ? 0 : 1] = sw ? lo : hi;
 }
-constexpr int kPartStride = 104;
+constexpr int kPartStride = 100;
 template <int NQ, class BinVal>
 NS_DEV void band_slots(const Grp &g, const Tab &T, float *part, BinVal val) {
   if (g.tid < kSlots) {
@@ -1388,7 +1391,8 @@ NS_DEV void load_twiddles(const Params &p, SpecTw &dst, int tid, int nthr) {
   static_assert(offsetof(Tables, w480) == 0 && offsetof(Tables, w960) == sizeof(cf) * 480, "twiddles lead the tables");
   const uint32_t *src = reinterpret_cast<const uint32_t *>(p.tables);
   uint32_t *d = reinterpret_cast<uint32_t *>(&dst);
-  for (int i = tid; i < (int)(sizeof(SpecTw) / 4); i += nthr) d[i] = src[i];
+  for (int i = tid; i < (int)(offsetof(SpecTw, tw3) / 4); i += nthr) d[i] = src[i];
+  for (int i = tid; i < 64; i += nthr) dst.tw3[i] = p.tables->w480[6 * ((i >> 4) + 1) * (i & 15)];
 }
 
 // spectra of frame t: X of [prev | cur], P of the window lagged by pitch_index, Ex / Ep / raw Exp
