@@ -1,7 +1,7 @@
 // ns_pipe.cuh -- device code of the phased RNNoise pipeline behind
 // nnnoiseless::DenoiseState::process_frame (/root/reference/src-tauri/src/audio.rs:268).
 //
-// One chunk of frames of every stream goes through six kernels (DESIGN.md has the data flow):
+// One chunk of frames of every stream goes through seven kernels (DESIGN.md has the data flow):
 //   K0 highpass   serial-in-time biquad, one lane per stream (f32 state, f64 intermediates: a6)
 //   K1 pitch      parallel over (stream, run of R frames): pitch_downsample, pitch_search and every
 //                 inner product remove_doubling can ask for (a9-a11) -> candidate table
@@ -9,9 +9,12 @@
 //                 warp per stream, one lane per candidate
 //   K3 spectrum   parallel over (stream, frame): windowed rFFT960 of the frame and of the
 //                 pitch-lagged window, band energies / correlation, cepstrum (a7, a8, a12, a13)
-//   K4 rnn        serial-in-time recurrent core, 8 streams per CTA: cepstral ring + delta features,
-//                 dense -> 3 GRUs -> dense, gain smoothing (a13, a14)
-//   K5 synthesis  per stream: pitch filter, gain interpolation, inverse FFT, overlap-add (a15, a16)
+//   K3b features  serial-in-time cepstral ring, delta features, spectral variability (a13), one warp per
+//                 stream; emits the 42 features as bf16 hi + lo MMA fragments
+//   K4 rnn        serial-in-time recurrent core on the tensor pipe (mma.sync bf16 hi + lo), 16 streams per
+//                 CTA: dense -> 3 GRUs -> dense, gain smoothing (a14)
+//   K5 synthesis  per (stream, run of frames): pitch filter, gain interpolation, inverse FFT, overlap-add
+//                 (a15, a16); the next frame's spectra arrive by TMA bulk copies
 //
 // EXACTNESS CONTRACT.  Everything that feeds a discrete pitch decision (K0, K1, K2) is computed
 // with the oracle's operation order and roundings: this translation unit is compiled with
@@ -1206,38 +1209,8 @@ NS_DEV void fft_stage2(const Grp &g, const Tab &T, cf *bufA, cf *bufB, Load2 loa
   gsync(g);
 }
 
-template <class LoadFirst>
-NS_DEV void fft480(const Grp &g, const Tab &T, cf *buf, LoadFirst load_first) {
-  auto from_buf = [&](int n) -> cf { return buf[n]; };
-  fft_stage<4, 1>(g, T, buf, load_first);
-  fft_stage<4, 4>(g, T, buf, from_buf);
-  fft_stage<5, 16>(g, T, buf, from_buf);
-  fft_stage<6, 80>(g, T, buf, from_buf);
-}
-
-// a7 / a12: X <- rFFT960(window . src[0..960)) / 960   (bins 0..480); src is in HBM/L2
-NS_DEV void rfft960_windowed(const Grp &g, const Tab &T, const float *__restrict__ src, cf *X) {
-  auto load = [&](int n) -> cf {
-    const int i0 = 2 * n;
-    const float w0 = T.win((i0 < kFrame) ? i0 : kWindow - 1 - i0);
-    const float w1 = T.win((i0 + 1 < kFrame) ? i0 + 1 : kWindow - 2 - i0);
-    return cf{src[i0] * w0, src[i0 + 1] * w1};
-  };
-  fft480(g, T, X, load);
-  const float norm = 1.0f / kWindow;
-  for (int k = g.tid; k <= 240; k += kGroupThreads) {
-    const cf a = X[k], b = X[k == 0 ? 0 : 480 - k], w = T.w960(k);
-    const float er = .5f * (a.x + b.x), ei = .5f * (a.y - b.y);
-    const float orr = .5f * (a.x - b.x), oi = .5f * (a.y + b.y);
-    const float tr = fmaf(orr, w.x, -(oi * w.y)), ti = fmaf(orr, w.y, oi * w.x);
-    X[k] = cf{(er + ti) * norm, (ei - tr) * norm};
-    X[480 - k] = cf{(er - ti) * norm, (-ei - tr) * norm};
-  }
-  gsync(g);
-}
-
-// the same for two windows at once (X of the frame, P of the pitch-lagged window): shared window,
-// twiddle and barrier traffic
+// a7 / a12: X <- rFFT960(window . src[0..960)) / 960 (bins 0..480) for two windows at once (X of the frame, P of the
+// pitch-lagged window): shared window, twiddle and barrier traffic
 // (XA, XB) receive the result; (YA, YB) are scratch of the same size: the four stages ping-pong between them
 NS_DEV void rfft960_windowed2(const Grp &g, const Tab &T, const float *win, const float *__restrict__ srcA,
                               const float *__restrict__ srcB, cf *XA, cf *XB, cf *YA, cf *YB) {
