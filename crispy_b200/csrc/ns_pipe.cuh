@@ -236,16 +236,16 @@ template <int R>
 struct PitchSmem {
   static constexpr int kHLen = R * kFrame + 1248;
   static constexpr int kXlpFloats = (R * kLpStride > kHLen) ? R * kLpStride : kHLen;
-  float xr[R * kLpStride];  // raw downsampled rows; after the FIR each row holds y4[432] | yy_lookup[388]
-  float xlp[kXlpFloats];    // first the high-passed window, then the whitened rows x_lp
-  float xc[R][152];
-  float ac[R][8];
-  float lpc2[R][8];
-  float fx[R][12];
-  int fi[R][12];
-  float xx[R];
-  float sb6[R][148];  // Syy before every coarse lag (helper warp, in the coarse search's shadow)
-  float s10[R][12];   // fine pass: Syy before each of the (at most ten) candidate lags (chain warp B, in P7's shadow)
+  alignas(16) float xr[R * kLpStride];  // raw downsampled rows; after the FIR each row holds y4[432] | yy_lookup[388]
+  alignas(16) float xlp[kXlpFloats];    // first the high-passed window, then the whitened rows x_lp
+  alignas(16) float xc[R][152];
+  alignas(16) float ac[R][8];
+  alignas(16) float lpc2[R][8];
+  alignas(16) float fx[R][12];
+  alignas(16) int fi[R][12];
+  alignas(16) float xx[R];
+  alignas(16) float sb6[R][148];  // Syy before every coarse lag (helper warp, in the coarse search's shadow)
+  alignas(16) float s10[R][12];   // fine pass: Syy before each of the (at most ten) candidate lags (chain warp B, in P7's shadow)
 #ifdef NS_PITCH_PAD_BYTES
   char pad[NS_PITCH_PAD_BYTES];  // measurement builds: forces fewer resident CTAs per SM
 #endif
@@ -253,7 +253,7 @@ struct PitchSmem {
   // work lists of remove_doubling's inner products per window-alignment bucket: frame | lag << 5 | k << 14
   int n_tri[4], n_sgl[4];
   uint32_t tri[4][R * 16], sgl[4][R * 16];  // <= 15 triples and <= 14 singles per frame
-  float dots[R][64];   // 0: T0-1, 1: T0+1; for k >= 2 at 2+4(k-2): T1-1, T1, T1+1, T1b
+  alignas(16) float dots[R][64];   // 0: T0-1, 1: T0+1; for k >= 2 at 2+4(k-2): T1-1, T1, T1+1, T1b
 };
 
 struct Best2 {
