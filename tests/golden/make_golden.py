@@ -22,3 +22,11 @@ if __name__ == "__main__":
                         silence=np.array([t["silence"] for t in taps], np.int32),
                         gains=np.array([t["gains"] for t in taps], np.float32))
     print("wrote c1_head.npz", out.shape)
+    # front ends: a 0.1 s chirp at 44.1 kHz through the linear (audio.rs:108-133) and the sinc resampler
+    t = np.arange(4410) / 44100.0
+    chirp = (0.5 * np.sin(2 * np.pi * (200.0 + 40000.0 * t) * t)).astype(np.float32)
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "front_end.npz"), x44=chirp,
+                        linear=po.linear_resample(chirp, 44100.0, 48000.0), sinc=po.sinc_resample(chirp, 44100, 48000),
+                        sinc_taps_phase0=po.sinc_table(44100, 48000)[0][0], sinc_taps_phase77=po.sinc_table(44100, 48000)[0][77])
+    print("wrote front_end.npz")
+

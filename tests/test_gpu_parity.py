@@ -221,6 +221,14 @@ def test_sinc_resample_chunks_reproduce_the_whole_call():
         cb.sinc_resample_chunk(_dev(x[:, 5000:6000]), 5000, n_total, 4800, 4800, 44100, 48000)
 
 
+def test_front_end_golden_fixture():
+    """The committed front-end fixture (tests/golden/front_end.npz) through the CUDA kernels: both bit-exact."""
+    g = np.load(os.path.join(GOLDEN, "front_end.npz"))
+    x = _dev(g["x44"][None, :])
+    assert np.array_equal(cb.sinc_resample(x, 44100, 48000)[0].cpu().numpy(), g["sinc"])
+    assert np.array_equal(cb.linear_resample(x, 44100.0, 48000.0)[0].cpu().numpy(), g["linear"])
+
+
 def test_resample_host_matches_device_paths():
     rng = np.random.default_rng(2)
     x = rng.standard_normal((3, 4410)).astype(np.float32)

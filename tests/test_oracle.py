@@ -236,3 +236,13 @@ def test_sinc_resample_reconstructs_a_tone_and_beats_linear():
     best = min(np.abs(lin[400:k] - 0.5 * np.sin(2 * np.pi * 5000.0 * (np.arange(400, k) / 48000.0 + d / 44100.0))).max()
                for d in (0.0, 1.0))
     assert best > 100 * err_sinc
+
+
+def test_front_end_golden_regression():
+    """tests/golden/front_end.npz (make_golden.py): the linear and sinc resamplers of the oracle on a chirp."""
+    g = np.load(os.path.join(GOLDEN, "front_end.npz"))
+    assert np.array_equal(po.linear_resample(g["x44"], 44100.0, 48000.0), g["linear"])
+    assert np.array_equal(po.sinc_resample(g["x44"], 44100, 48000), g["sinc"])
+    h, _ = po.sinc_table(44100, 48000)
+    assert np.array_equal(h[0], g["sinc_taps_phase0"]) and np.array_equal(h[77], g["sinc_taps_phase77"])
+
