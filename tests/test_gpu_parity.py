@@ -144,6 +144,23 @@ def test_host_path_equals_device_path(model, monkeypatch):
     assert torch.equal(h2, d_out.cpu()[:, 480:])
 
 
+def test_unaligned_rows_take_the_scalar_loader_and_match(model):
+    """K0 fetches 16-byte aligned rows with cp.async (f32 and PCM16) and anything else sample by sample; K5 stores
+    16 bytes at a time only into aligned rows: odd row strides and offsets must give the same bits."""
+    x = make_signal(5, 40)
+    xi = np.clip(np.rint(x), -32768, 32767).astype(np.int16)
+    for arr, kw in ((x.astype(np.float32), {}), (xi, {"out_i16": True})):
+        ref, rv = cb.BatchDenoiser(5, model).process_streams(_dev(arr), unit_scale=False, **kw)
+        wide = torch.zeros((5, arr.shape[1] + 7), dtype=_dev(arr).dtype, device="cuda")
+        view = wide[:, 3:3 + arr.shape[1]]
+        view.copy_(_dev(arr))
+        out_wide = torch.zeros((5, arr.shape[1] + 5), dtype=ref.dtype, device="cuda")
+        out_view = out_wide[:, 1:1 + arr.shape[1]]
+        out, vad = cb.BatchDenoiser(5, model).process_streams(view, unit_scale=False, out=out_view, **kw)
+        assert torch.equal(out, ref) and torch.equal(vad, rv)
+        assert float(out_wide[:, 0].abs().max()) == 0 and float(out_wide[:, 1 + arr.shape[1]:].abs().max()) == 0
+
+
 def test_i16_io_and_dual_mono_mix(oracle_model, model):
     x = make_signal(6, 50)
     xi = np.clip(np.rint(x), -32768, 32767).astype(np.int16)
