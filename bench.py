@@ -245,9 +245,10 @@ def run_b200(args):
         den.reset_async()
         den.process_streams(x, unit_scale=True, out=out, vad=vad)
 
-    # ---- parity spot-check against the oracle (rank 0, a few streams, first 2 s) ----------------
+    # ---- part of the cpu_baseline leg (the one place this arm runs the oracle, as the checker and never inside a
+    # timed region): the GPU output of a few streams' first 2 s against the CPU port's (rank 0) ----
     parity = None
-    if rank == 0 and args.parity_streams > 0:
+    if rank == 0 and args.parity_streams > 0 and not args.no_cpu_baseline:
         from oracle import pyoracle as po
         ns_p, nf_p = min(args.parity_streams, n_streams), min(200, n_frames)
         step()
