@@ -199,6 +199,10 @@ struct crispy_ns_state {
   crispy_ns_batch *b = nullptr;
   float *h_pin = nullptr;  // 480 in + 480 out + 1 vad, pinned
   float *d_io = nullptr;   // same on device
+  // the live path is launch bound (one frame through seven tiny kernels): each call replays a CUDA graph of
+  // copy-in -> K0 .. K5 -> copy-out, one graph per workspace slot the chunk counter can select
+  cudaStream_t s = nullptr;
+  cudaGraphExec_t gexec[kSlots] = {};
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -276,6 +280,42 @@ struct RunHooks {
   cudaEvent_t all_done = nullptr;  // recorded after the call's last K5
 };
 
+// one kernel of the chunk described by p (n streams x nf frames) on stream sk
+static void launch_kernel(crispy_ns_batch *b, int k, ns::Params &p, int n, int nf, int groups, cudaStream_t sk) {
+  switch (k) {
+    case 0:
+      ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem), sk>>>(p);
+      break;
+    case 1:
+      ns_pitch_kernel<<<n * ((nf + kPitchRun - 1) / kPitchRun), kPitchThreads, sizeof(ns::PitchSmem<kPitchRun>), sk>>>(p);
+      break;
+    case 2:
+      ns_pitchscan_kernel<<<(n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, sk>>>(p);
+      break;
+    case 3: {
+      long long ctas = (long long)n * nf;  // persistent task loop: exactly one resident wave
+      if (ctas > (long long)b->n_sms * b->spec_ctas_per_sm) ctas = (long long)b->n_sms * b->spec_ctas_per_sm;
+      ns_spectrum_kernel<<<(int)ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), sk>>>(p);
+      break;
+    }
+    case 4:
+      ns_features_kernel<<<(groups * ns::kMmaStreams + ns::kFeatWarps - 1) / ns::kFeatWarps, 32 * ns::kFeatWarps, 0, sk>>>(p);
+      break;
+    case 5:
+      ns_rnn_kernel<<<groups, ns::kMmaThreads, sizeof(ns::RnnSmem), sk>>>(p);
+      break;
+    default: {
+      const int resident = b->n_sms * b->syn_ctas_per_sm;
+      p.syn_run = ns::pick_syn_run(n, nf, resident);
+      if (b->syn_run_override > 0) p.syn_run = b->syn_run_override < nf ? b->syn_run_override : nf;
+      long long ctas = (long long)n * ((nf + p.syn_run - 1) / p.syn_run);
+      if (ctas > resident) ctas = resident;
+      ns_synthesis_kernel<<<(int)ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), sk>>>(p);
+      break;
+    }
+  }
+}
+
 static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad, const float *d_app,
                       float *d_taps, int n_frames, int64_t in_stride, int64_t out_stride,
                       int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume, cudaStream_t st,
@@ -341,38 +381,7 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
       cudaStream_t sk = b->s_k[k];
       if (k > 0) NS_CUDA(cudaStreamWaitEvent(sk, b->e_k[slot][k - 1], 0));
       NS_CUDA(prof_begin(b, k, sk));
-      switch (k) {
-        case 0:
-          ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem), sk>>>(p);
-          break;
-        case 1:
-          ns_pitch_kernel<<<n * ((nf + kPitchRun - 1) / kPitchRun), kPitchThreads, sizeof(ns::PitchSmem<kPitchRun>), sk>>>(p);
-          break;
-        case 2:
-          ns_pitchscan_kernel<<<(n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, sk>>>(p);
-          break;
-        case 3: {
-          long long ctas = (long long)n * nf;  // persistent task loop: exactly one resident wave
-          if (ctas > (long long)b->n_sms * b->spec_ctas_per_sm) ctas = (long long)b->n_sms * b->spec_ctas_per_sm;
-          ns_spectrum_kernel<<<(int)ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), sk>>>(p);
-          break;
-        }
-        case 4:
-          ns_features_kernel<<<(groups * ns::kMmaStreams + ns::kFeatWarps - 1) / ns::kFeatWarps, 32 * ns::kFeatWarps, 0, sk>>>(p);
-          break;
-        case 5:
-          ns_rnn_kernel<<<groups, ns::kMmaThreads, sizeof(ns::RnnSmem), sk>>>(p);
-          break;
-        default: {
-          const int resident = b->n_sms * b->syn_ctas_per_sm;
-          p.syn_run = ns::pick_syn_run(n, nf, resident);
-          if (b->syn_run_override > 0) p.syn_run = b->syn_run_override < nf ? b->syn_run_override : nf;
-          long long ctas = (long long)n * ((nf + p.syn_run - 1) / p.syn_run);
-          if (ctas > resident) ctas = resident;
-          ns_synthesis_kernel<<<(int)ctas, ns::kGroupThreads, sizeof(ns::SpecSmem), sk>>>(p);
-          break;
-        }
-      }
+      launch_kernel(b, k, p, n, nf, groups, sk);
       NS_CUDA(cudaGetLastError());
       NS_CUDA(prof_end(b, sk));
       NS_CUDA(cudaEventRecord(b->e_k[slot][k], sk));
@@ -814,6 +823,9 @@ void crispy_ns_host_free(void *ptr) {
 void crispy_ns_destroy(crispy_ns_state *st) {
   if (!st) return;
   if (st->b) cudaSetDevice(st->b->device);
+  for (int i = 0; i < kSlots; i++)
+    if (st->gexec[i]) cudaGraphExecDestroy(st->gexec[i]);
+  if (st->s) cudaStreamDestroy(st->s);
   if (st->h_pin) cudaFreeHost(st->h_pin);
   if (st->d_io) cudaFree(st->d_io);
   crispy_ns_batch_destroy(st->b);
@@ -830,6 +842,7 @@ int crispy_ns_create(const crispy_ns_model *model, int device, crispy_ns_state *
   }
   cudaError_t e = cudaHostAlloc((void **)&st->h_pin, 964 * sizeof(float), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_io, 964 * sizeof(float));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st->s, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     crispy_ns_destroy(st);
     return fail(CRISPY_NS_ECUDA, std::string("create: ") + cudaGetErrorString(e));
@@ -837,15 +850,75 @@ int crispy_ns_create(const crispy_ns_model *model, int device, crispy_ns_state *
   *out = st;
   return CRISPY_NS_OK;
 }
+// one frame of the state's single stream as a captured graph on st->s (built on the first use of each slot)
+static int frame_graph(crispy_ns_state *st, int slot) {
+  crispy_ns_batch *b = st->b;
+  ns::Params p;
+  memset(&p, 0, sizeof(p));
+  p.in = st->d_io;
+  p.out = st->d_io + 480;
+  p.vad = st->d_io + 960;
+  p.state = b->d_state;
+  p.tables = b->d_tables;
+  p.rnn_hdr = b->d_hdr;
+  p.rnn_words = b->d_words;
+  p.rnn_bias = b->d_bias;
+  p.in_stride = 480;
+  p.out_stride = 480;
+  p.vad_stride = 1;
+  p.hp_stride = ns::kHist + (long long)b->chunk_cap * ns::kFrame;
+  p.n_streams = 1;
+  p.n_frames_call = 1;
+  p.n_frames = 1;
+  p.chunk_cap = b->chunk_cap;
+  p.volume = 1.0f;
+  p.hp = b->d_hp[slot];
+  p.tab = b->d_tab[slot];
+  p.rec = b->d_rec[slot];
+  p.spec = b->d_spec[slot];
+  p.featq = b->d_featq[slot];
+  p.synth_sel = slot & 1;  // == chunk counter & 1: kSlots is even
+  static_assert(kSlots % 2 == 0, "the synthesis_mem parity follows the slot");
+  NS_CUDA(cudaStreamBeginCapture(st->s, cudaStreamCaptureModeThreadLocal));
+  cudaMemcpyAsync(st->d_io, st->h_pin, ns::kFrame * sizeof(float), cudaMemcpyHostToDevice, st->s);
+  for (int k = 0; k < kNumKernels; k++) launch_kernel(b, k, p, 1, 1, 1, st->s);
+  cudaMemcpyAsync(st->h_pin + 480, st->d_io + 480, 481 * sizeof(float), cudaMemcpyDeviceToHost, st->s);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st->s, &graph);
+  if (e != cudaSuccess || !graph) {
+    cudaGetLastError();
+    return fail(CRISPY_NS_ECUDA, std::string("process_frame: graph capture: ") + cudaGetErrorString(e));
+  }
+  const cudaError_t ei = cudaGraphInstantiate(&st->gexec[slot], graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) return fail(CRISPY_NS_ECUDA, std::string("process_frame: graph instantiate: ") + cudaGetErrorString(ei));
+  return CRISPY_NS_OK;
+}
+
 int crispy_ns_process_frame(crispy_ns_state *st, float *out480, const float *in480, float *vad) {
   if (!st || !out480 || !in480) return fail(CRISPY_NS_EINVAL, "process_frame: bad argument");
-  NS_CUDA(cudaSetDevice(st->b->device));
+  crispy_ns_batch *b = st->b;
+  NS_CUDA(cudaSetDevice(b->device));
   memcpy(st->h_pin, in480, ns::kFrame * sizeof(float));
-  NS_CUDA(cudaMemcpyAsync(st->d_io, st->h_pin, ns::kFrame * sizeof(float), cudaMemcpyHostToDevice, 0));
-  const int rc = run_device(st->b, st->d_io, st->d_io + 480, st->d_io + 960, nullptr, nullptr, 1, 480, 480, 1, 0, 0, 1.0f, 0);
-  if (rc != CRISPY_NS_OK) return rc;
-  NS_CUDA(cudaMemcpyAsync(st->h_pin + 480, st->d_io + 480, 481 * sizeof(float), cudaMemcpyDeviceToHost, 0));
-  NS_CUDA(cudaStreamSynchronize(0));
+  if (b->prof_on || b->reset_pending || getenv("CRISPY_NS_NO_GRAPH")) {  // plain launches (measurement / async reset)
+    NS_CUDA(cudaMemcpyAsync(st->d_io, st->h_pin, ns::kFrame * sizeof(float), cudaMemcpyHostToDevice, 0));
+    const int rc = run_device(b, st->d_io, st->d_io + 480, st->d_io + 960, nullptr, nullptr, 1, 480, 480, 1, 0, 0, 1.0f, 0);
+    if (rc != CRISPY_NS_OK) return rc;
+    NS_CUDA(cudaMemcpyAsync(st->h_pin + 480, st->d_io + 480, 481 * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    NS_CUDA(cudaStreamSynchronize(0));
+  } else {
+    const int slot = (int)(b->chunks_done % kSlots);
+    if (!st->gexec[slot]) {
+      NS_CUDA(configure_kernels(b->device));
+      const int rc = frame_graph(st, slot);
+      if (rc != CRISPY_NS_OK) return rc;
+    }
+    NS_CUDA(cudaGraphLaunch(st->gexec[slot], st->s));
+    NS_CUDA(cudaStreamSynchronize(st->s));
+    b->launches += kNumKernels;
+    b->chunks_done += 1;
+    b->frames_done += 1;
+  }
   memcpy(out480, st->h_pin + 480, ns::kFrame * sizeof(float));
   if (vad) *vad = st->h_pin[960];
   return CRISPY_NS_OK;

@@ -81,7 +81,8 @@ void crispy_ns_model_destroy(crispy_ns_model *m);
  * named by $CRISPY_NS_WEIGHTS if set, else synthetic seed 0. ---- */
 int crispy_ns_create(const crispy_ns_model *model, int device, crispy_ns_state **out);
 /* ---- DenoiseState::process_frame (audio.rs:268): 480 f32 in 16-bit scale in and out (host
- * pointers); *vad receives the voice-activity probability the reference discards. ---- */
+ * pointers); *vad receives the voice-activity probability the reference discards.  Synchronous; the seven
+ * kernels of the frame are replayed as a CUDA graph (about 0.1 ms per call on a B200). ---- */
 int crispy_ns_process_frame(crispy_ns_state *st, float *out480, const float *in480, float *vad);
 int crispy_ns_reset(crispy_ns_state *st); /* fresh DenoiseState (audio.rs:955-965 model switch) */
 void crispy_ns_destroy(crispy_ns_state *st);
