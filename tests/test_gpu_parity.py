@@ -41,6 +41,23 @@ def test_c1_single_stream_process_frame(oracle_model):
         st.process_frame(np.zeros(479, np.float32), np.zeros(479, np.float32))
 
 
+def test_process_frame_graph_replay_equals_plain_launches(model, monkeypatch):
+    """crispy_ns_process_frame replays a CUDA graph per workspace slot; CRISPY_NS_NO_GRAPH=1 takes the plain launches."""
+    x = make_signal(1, 40)[0].reshape(40, 480)
+    outs = []
+    for no_graph in (False, True):
+        if no_graph:
+            monkeypatch.setenv("CRISPY_NS_NO_GRAPH", "1")
+        st = cb.DenoiseState.new(model)
+        o = np.zeros(480, np.float32)
+        frames, vads = [], []
+        for t in range(40):
+            vads.append(st.process_frame(o, x[t]))
+            frames.append(o.copy())
+        outs.append((np.concatenate(frames), np.array(vads, np.float32)))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_batch_matches_oracle_with_taps(oracle_model, model):
     n_streams, n_frames = 37, 120
     x = make_signal(n_streams, n_frames)
