@@ -246,3 +246,19 @@ def test_front_end_golden_regression():
     h, _ = po.sinc_table(44100, 48000)
     assert np.array_equal(h[0], g["sinc_taps_phase0"]) and np.array_equal(h[77], g["sinc_taps_phase77"])
 
+
+
+def test_pitch_path_matches_an_independent_numpy_transliteration(oracle_model):
+    """tests/np_pitch.py restates biquad + pitch_downsample + pitch_search + remove_doubling from the published
+    algorithm (xiph/rnnoise pitch.c / celt_lpc.c), independently of the C oracle: the discrete
+    pitch decisions and the pitch gain of every frame must agree bit for bit."""
+    from tests.np_pitch import PitchTracker
+    from tests.util import make_signal
+    x = make_signal(4, 150)
+    for s in range(4):
+        _, taps = po.debug_trace(oracle_model, x[s].astype(np.float32))
+        pt = PitchTracker()
+        for t in range(150):
+            pi, g = pt.frame(x[s, t * 480:(t + 1) * 480])
+            assert pi == taps[t]["pitch_index"], (s, t)
+            assert np.float32(g) == np.float32(taps[t]["pitch_gain"]), (s, t, float(g), float(taps[t]["pitch_gain"]))
