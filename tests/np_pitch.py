@@ -202,6 +202,7 @@ class PitchTracker:
 
     def frame(self, x480):
         x = biquad(x480, self.mem)
+        self.x_hp = x
         self.pitch_buf = np.concatenate([self.pitch_buf[FRAME:], x])
         lp = pitch_downsample(self.pitch_buf)
         pitch = pitch_search(lp[MAXP >> 1:], lp, PFRAME, MAXP - 3 * MINP)

@@ -262,3 +262,35 @@ def test_pitch_path_matches_an_independent_numpy_transliteration(oracle_model):
             pi, g = pt.frame(x[s, t * 480:(t + 1) * 480])
             assert pi == taps[t]["pitch_index"], (s, t)
             assert np.float32(g) == np.float32(taps[t]["pitch_gain"]), (s, t, float(g), float(taps[t]["pitch_gain"]))
+
+
+def test_whole_frame_matches_an_independent_numpy_transliteration(oracle_model):
+    """tests/np_denoise.py restates the rest of process_frame (analysis, features, dense/GRU stack, pitch filter,
+    synthesis) in float64 from the published algorithm; the float32 C oracle must follow it: same silence decisions,
+    band energies / features / gains / VAD to float32 accuracy, output within 3e-5 of full scale and >= 80 dB (float32
+    against float64 through 150 recurrent steps)."""
+    from tests.np_denoise import NpDenoise
+    from tests.util import make_signal, snr_db
+    x = make_signal(2, 150)  # stream 1 carries a digital-silence stretch
+    blob = oracle_model.to_bytes()
+    for s in range(2):
+        out_o, taps = po.debug_trace(oracle_model, x[s].astype(np.float32))
+        ref = NpDenoise(blob)
+        outs, n_silent = [], 0
+        for t in range(150):
+            o, vad, tp = ref.process_frame(x[s, t * 480:(t + 1) * 480])
+            ot = taps[t]
+            outs.append(o)
+            assert tp["pitch_index"] == ot["pitch_index"] and tp["silence"] == ot["silence"], (s, t)
+            n_silent += tp["silence"]
+            assert np.allclose(tp["Ex"], ot["Ex"], rtol=1e-4, atol=1e-6)
+            assert np.allclose(tp["Ep"], ot["Ep"], rtol=1e-4, atol=1e-6)
+            assert np.abs(tp["Exp"] - np.array(ot["Exp"])).max() < 1e-3
+            assert np.abs(tp["features"] - np.array(ot["features"])).max() < 1e-3
+            assert abs(vad - float(ot["vad"])) < 1e-5
+            if not tp["silence"]:
+                assert np.abs(tp["gains"] - np.array(ot["gains"])).max() < 1e-4
+        out = np.concatenate(outs)
+        assert np.abs(out - out_o).max() < 1.0 and snr_db(out, out_o) >= 80.0
+        assert (n_silent > 0) == (s == 1)
+
