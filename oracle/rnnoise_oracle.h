@@ -15,7 +15,9 @@
  * sites and wrapper arithmetic (audio.rs:242-295), (b) the reference's own unit tests for the
  * neighbouring rows (LinearResampler audio.rs:1040-1096, WavWriter recording.rs:454-504), and
  * (c) algorithm-level known answers (window power-complementarity, DCT orthonormality, tanh
- * table, analysis/synthesis perfect reconstruction on the silence path).
+ * table, analysis/synthesis perfect reconstruction on the silence path), and (d) two NumPy transliterations of the
+ * published algorithm written independently of this file (tests/np_pitch.py: pitch decisions and gain bit for bit;
+ * tests/np_denoise.py: the whole frame in float64, agreement to float32 accuracy).
  */
 #ifndef RNNOISE_ORACLE_H
 #define RNNOISE_ORACLE_H
