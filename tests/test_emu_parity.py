@@ -90,3 +90,32 @@ def test_drop_first_frame_offset(model_blob, sig):
     full, _, _, _ = emu_process(model_blob, sig, chunk=8)
     dropped, _, _, _ = emu_process(model_blob, sig, chunk=8, out_frame_offset=-1)
     assert np.array_equal(dropped[:, : 19 * 480], full[:, 480:])
+
+
+def test_adversarial_inputs_keep_every_decision_bit_exact(oracle_model, model_blob):
+    """DC, impulses, loud / tiny noise, tones at and beyond the pitch range, clipping, a chirp, silence then a step:
+    pitch index, pitch gain and the silence gate equal the oracle's bit for bit, features / gains / VAD to float32
+    accuracy.  Samples meet the north_star tolerance except on two inputs where RNNoise itself is discontinuous:
+    a clipped square wave drives the band correlation Exp and the gain g both to 1.0, where the pitch filter's
+    `Exp > g ? 1 : ...` branch flips on the last bit, and sparse impulses leave bands of the lagged window at
+    rounding-noise energy under `Ex / (1e-8 + Ep)`.  There two correct implementations differ by ~1 % of full scale
+    in isolated frames -- the float32 oracle and the float64 NumPy transliteration do, too."""
+    from tests.util import adversarial_signals, parity_report
+    sigs = adversarial_signals(24)
+    names = list(sigs)
+    x = np.stack([sigs[k] for k in names])
+    out, vad, dbg, _ = emu_process(model_blob, x, chunk=8)
+    ref, rvad = po.process_streams(oracle_model, x)
+    for i, name in enumerate(names):
+        _, taps = po.debug_trace(oracle_model, x[i])
+        assert np.array_equal(dbg[i, :, 132].astype(int), np.array([t["pitch_index"] for t in taps])), name
+        assert np.array_equal(dbg[i, :, 130], np.array([t["pitch_gain"] for t in taps], dtype=np.float32)), name
+        assert np.array_equal(dbg[i, :, 133].astype(int), np.array([t["silence"] for t in taps])), name
+        assert np.max(np.abs(dbg[i, :, 0:42] - np.array([t["features"] for t in taps]))) < 2e-2, name  # log-domain
+        assert np.max(np.abs(dbg[i, :, 42:64] - np.array([t["gains"] for t in taps]))) < 5e-3, name
+        r = parity_report(ref[i], out[i], rvad[i], vad[i])
+        assert r["vad_max"] <= 1e-3, name
+        if name in ("impulses", "square_clip"):
+            assert r["max_abs"] <= 0.02 * 32768.0, (name, r)
+        else:
+            assert r["max_abs"] <= TOL_MAX_ABS and r["snr_db"] >= 60.0, (name, r)

@@ -294,3 +294,18 @@ def test_whole_frame_matches_an_independent_numpy_transliteration(oracle_model):
         assert np.abs(out - out_o).max() < 1.0 and snr_db(out, out_o) >= 80.0
         assert (n_silent > 0) == (s == 1)
 
+
+
+def test_pitch_path_numpy_cross_check_on_adversarial_inputs(oracle_model):
+    """The same bit-for-bit agreement on inputs that reach the corners of the pitch range (60 .. 767)."""
+    from tests.np_pitch import PitchTracker
+    from tests.util import adversarial_signals
+    seen = set()
+    for name, x in adversarial_signals(40).items():
+        _, taps = po.debug_trace(oracle_model, x)
+        pt = PitchTracker()
+        for t in range(40):
+            pi, g = pt.frame(x[t * 480:(t + 1) * 480])
+            assert pi == taps[t]["pitch_index"] and np.float32(g) == np.float32(taps[t]["pitch_gain"]), (name, t)
+            seen.add(pi)
+    assert min(seen) == 60 and max(seen) > 700

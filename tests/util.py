@@ -121,3 +121,24 @@ def canonical_state(state: np.ndarray) -> np.ndarray:
     st[:, ST_SYNTH + 480: ST_SYNTH + 960] = 0.0
     st.view(np.int32)[0, -1] = 0
     return st
+
+
+def adversarial_signals(n_frames: int) -> dict:
+    """Inputs that push the pitch path to its corners (16-bit scale): DC, sparse impulses, loud and tiny noise, tones
+    at and beyond the pitch range, clipping, a chirp, silence followed by a step."""
+    n = n_frames * 480
+    t = np.arange(n) / 48000.0
+    rng = np.random.default_rng(1)
+    sigs = {
+        "dc": np.full(n, 5000.0),
+        "impulses": np.where(np.arange(n) % 997 == 0, 30000.0, 0.0),
+        "white_loud": rng.standard_normal(n) * 9000,
+        "white_tiny": rng.standard_normal(n) * 0.3,
+        "sine_60hz": 8000 * np.sin(2 * np.pi * 60 * t),
+        "sine_800hz": 8000 * np.sin(2 * np.pi * 800 * t),
+        "sine_62_5hz": 8000 * np.sin(2 * np.pi * 62.5 * t),
+        "square_clip": np.clip(40000 * np.sin(2 * np.pi * 150 * t), -32768, 32767),
+        "chirp": 9000 * np.sin(2 * np.pi * (80 + 4000 * t) * t),
+        "zeros_then_step": np.concatenate([np.zeros(n // 2), np.full(n - n // 2, 12000.0)]),
+    }
+    return {k: v.astype(np.float32) for k, v in sigs.items()}
