@@ -153,7 +153,7 @@ def cpu_reference_rate(target_seconds: float = 12.0, seed_streams: int = 0):
     t0 = time.perf_counter()
     po.process_streams(model, x, unit_scale=True, n_threads=cores, native=True)
     dt = time.perf_counter() - t0
-    return {"value": n_streams * secs / dt, "unit": "stream-seconds/s", "cores": cores, "kind": "port",
+    return {"value": n_streams * secs / dt, "unit": "stream-seconds/s", "cores": cores, "kind": "port", "wall_s": dt,
             "sample": f"{n_streams} streams x {secs} s of the same synthetic workload, {cores} pthreads over "
                       f"streams, oracle C port (-O3 -march=native) of nnnoiseless 0.5.2; {dt:.2f} s wall"}
 
@@ -163,18 +163,20 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    vals, last = [], None
+    vals, walls, last = [], [], None
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_rate(target_seconds=2.0)
     for _ in range(steps):
         last = cpu_reference_rate(target_seconds=max(4.0, min(20.0, 60.0 / steps)))
         vals.append(last["value"])
+        walls.append(last["wall_s"])
     v = sum(vals) / len(vals)
     last["value"] = v
     line = {
         "impl": "reference", "metric": "stream-seconds of 48 kHz audio denoised per wall-second",
         "value": v, "unit": "stream-seconds/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": 1e3 * sum(walls) / len(walls),  # one step = one bounded sample of the workload (cpu_baseline.sample)
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.streams} independent {args.seconds:g} s 48 kHz mono streams per GPU "
                                "(BASELINE.json configs[1]); CPU arm times a bounded sample of it",
