@@ -31,6 +31,7 @@ FRAME = 480
 ALG_BYTES_PER_FRAME = 3844          # 480*4 read + 480*4 written + 4 (VAD)
 RNN_FLOPS_PER_FRAME = 175006        # 2 * 87,503 MAC
 ALL_FLOPS_PER_FRAME = 390000        # SURVEY.md 8(a) whole-pipeline estimate
+PITCH_MACS_PER_FRAME = 75000        # K1: multiply-adds per frame that must stay unfused
 FP32_PEAK_TFLOPS_NOMINAL = 74.5     # 148 SM * 128 lanes * 2 * 1.965 GHz (not in MEASURED_PEAKS.json)
 # the recurrent core (K4) runs on the tensor pipe: 723 bf16 m16n8k16 tiles per 16-stream step, twice (hi + lo plane)
 RNN_MMA_FLOPS_PER_FRAME = 2 * 723 * (16 * 8 * 16 * 2) // 16   # executed flops per (stream, frame), padding included
@@ -49,6 +50,13 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-front-end", action="store_true")
     ap.add_argument("--parity-streams", type=int, default=4)
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 = BASELINE.json configs[1] (default, the headline); c4 = configs[3]: 4,096 dual-source meetings "
+                         "x 10 min, mic PCM16 + app f32 -> dual-mono PCM16; c5 = configs[4]: 8,192 streams x 60 min; both "
+                         "partitioned by stream over the N ranks, synthesised on device chunk by chunk, state carried")
+    ap.add_argument("--total-streams", type=int, default=None, help="c4/c5: streams (meetings) in the whole job")
+    ap.add_argument("--minutes", type=float, default=None, help="c4/c5: recording length (default 10 / 60)")
+    ap.add_argument("--chunk-seconds", type=int, default=10, help="c4/c5: audio seconds per call")
     return ap.parse_args()
 
 
@@ -132,57 +140,93 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_rate(target_seconds: float = 12.0, seed_streams: int = 0):
-    """stream-seconds per wall-second of the CPU implementation on all host cores, on a bounded
-    sample of the same synthetic workload (first streams of the batch, first seconds of each)."""
-    import numpy as np
-    from crispy_b200.synth import synth_chunk
-    from oracle import pyoracle as po
-    po.build_native()
-    cores = os.cpu_count() or 1
-    model = po.Model.synthetic(0)
-    # calibrate on one second per thread, then size the sample for ~target_seconds of wall time
-    x = synth_chunk(cores, 48000, first_stream=seed_streams).numpy()
-    t0 = time.perf_counter()
-    po.process_streams(model, x, unit_scale=True, n_threads=cores, native=True)
-    dt = time.perf_counter() - t0
-    rate = cores * 1.0 / dt
-    secs = max(2, min(60, int(target_seconds * rate / (cores * 4))))
-    n_streams = cores * 4
-    x = synth_chunk(n_streams, 48000 * secs, first_stream=seed_streams).numpy()
-    t0 = time.perf_counter()
-    po.process_streams(model, x, unit_scale=True, n_threads=cores, native=True)
-    dt = time.perf_counter() - t0
-    return {"value": n_streams * secs / dt, "unit": "stream-seconds/s", "cores": cores, "kind": "port", "wall_s": dt,
-            "sample": f"{n_streams} streams x {secs} s of the same synthetic workload, {cores} pthreads over "
-                      f"streams, oracle C port (-O3 -march=native) of nnnoiseless 0.5.2; {dt:.2f} s wall"}
+class CpuArm:
+    """The CPU implementation of the path on all host cores: the oracle port (oracle/rnnoise_oracle.c, the in-repo C
+    restatement of nnnoiseless 0.5.2 -- the crate itself cannot be built offline), -O3 -march=native, one DenoiseState
+    per stream, pthreads over streams.  The synthetic sample (full-length streams of the same workload) is generated
+    ONCE; every step() denoises it again from fresh states."""
+
+    def __init__(self, seconds_per_stream: float, target_step_s: float):
+        import numpy as np
+        import torch
+        from crispy_b200.synth import synth_chunk
+        from oracle import pyoracle as po
+        self.po, self.np = po, np
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)  # torchrun exports OMP_NUM_THREADS=1: the generator would crawl
+        po.build_native()
+        self.model = po.Model.synthetic(0)
+        # calibrate: one second of audio per thread, on one thread and on all of them
+        cal = synth_chunk(self.cores, 48000).numpy()
+        po.process_streams(self.model, cal[:1, :4800], unit_scale=True, n_threads=1, native=True)  # tables, page faults
+        t0 = time.perf_counter()
+        po.process_streams(self.model, cal[:1], unit_scale=True, n_threads=1, native=True)
+        self.x_realtime_one_thread = 1.0 / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        po.process_streams(self.model, cal, unit_scale=True, n_threads=self.cores, native=True)
+        rate = self.cores / (time.perf_counter() - t0)
+        # whole streams of the workload's own length, as many as fit the step budget (a multiple of the thread count)
+        self.secs = int(seconds_per_stream) if seconds_per_stream >= 1 else 1
+        n = int(target_step_s * rate / self.secs)
+        n = max(self.cores, min(1024, n // self.cores * self.cores))
+        self.n_streams = n
+        t0 = time.perf_counter()
+        self.x = np.empty((n, 48000 * self.secs), np.float32)
+        for f0 in range(0, self.secs, 10):  # 10 s pieces keep the generator's f64 temporaries small
+            nf = min(10, self.secs - f0)
+            self.x[:, f0 * 48000:(f0 + nf) * 48000] = synth_chunk(n, nf * 48000, start_sample=f0 * 48000).numpy()
+        self.gen_s = time.perf_counter() - t0
+
+    def step(self) -> float:
+        """one pass over the sample; returns the wall seconds it took"""
+        t0 = time.perf_counter()
+        self.po.process_streams(self.model, self.x, unit_scale=True, n_threads=self.cores, native=True)
+        return time.perf_counter() - t0
+
+    def describe(self, value: float, wall_s: float) -> dict:
+        return {"value": value, "unit": "stream-seconds/s", "cores": self.cores, "kind": "port", "wall_s": wall_s,
+                "x_realtime_per_thread_all_threads_busy": value / self.cores,
+                "x_realtime_one_thread_alone": self.x_realtime_one_thread,
+                "sample": f"{self.n_streams} streams x {self.secs} s of the same synthetic workload (generated once, "
+                          f"{self.gen_s:.1f} s, untimed), {self.cores} pthreads over streams, oracle C port "
+                          f"(-O3 -march=native: the RNN's sums run one vector lane per neuron, the coarse pitch "
+                          f"search eight lags per vector, Stockham FFT) of nnnoiseless 0.5.2; {wall_s:.2f} s wall per pass. "
+                          f"RNNoise's paper quotes ~60x real time on one x86 core"}
+
+
+def cpu_reference_rate(target_seconds: float = 10.0, seconds_per_stream: float = 60.0):
+    arm = CpuArm(seconds_per_stream, target_seconds)
+    dt = arm.step()
+    return arm.describe(arm.n_streams * arm.secs / dt, dt)
 
 
 def run_reference(args):
+    """bench.py --impl reference: rank 0 alone runs the CPU arm (the other ranks exit at once); the whole run is
+    sized to end within ~90 s at any K: one calibration, one generated sample, W <= 1 warm-up pass, K timed passes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = max(1, args.steps)
-    vals, walls, last = [], [], None
+    arm = CpuArm(args.seconds, max(3.0, min(12.0, 50.0 / (steps + min(args.warmup, 1)))))
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_rate(target_seconds=2.0)
-    for _ in range(steps):
-        last = cpu_reference_rate(target_seconds=max(4.0, min(20.0, 60.0 / steps)))
-        vals.append(last["value"])
-        walls.append(last["wall_s"])
-    v = sum(vals) / len(vals)
-    last["value"] = v
+        arm.step()
+    walls = [arm.step() for _ in range(steps)]
+    wall = sum(walls) / len(walls)
+    v = arm.n_streams * arm.secs / wall
     line = {
         "impl": "reference", "metric": "stream-seconds of 48 kHz audio denoised per wall-second",
-        "value": v, "unit": "stream-seconds/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(walls) / len(walls),  # one step = one bounded sample of the workload (cpu_baseline.sample)
+        "value": v, "unit": "stream-seconds/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * wall,  # one step = one pass over the bounded sample (cpu_baseline.sample)
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.streams} independent {args.seconds:g} s 48 kHz mono streams per GPU "
-                               "(BASELINE.json configs[1]); CPU arm times a bounded sample of it",
+                               f"(BASELINE.json configs[1]); the CPU arm times a bounded sample of it: "
+                               f"{arm.n_streams} of those streams at full length per step",
+                   "same_config": False,
+                   "ranks": "rank 0 alone runs the CPU arm with every host thread; a rate, so it does not depend on N",
                    "note": "nnnoiseless itself cannot be built offline (no Rust toolchain, crate not vendored): "
                            "this is the in-repo C restatement, all host cores"},
-        "cpu_baseline": last,
+        "cpu_baseline": arm.describe(v, wall),
         "e2e": {"value": v, "unit": "stream-seconds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -217,9 +261,7 @@ def run_b200(args):
             numa_cpus = []
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL only carries the timing barrier / max here; keep its banner ("NCCL version ...") off stdout,
-        # which must hold exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.devnull)
+        # NCCL only carries the timing barrier / max here; whatever it prints goes to stderr with the rest (main())
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -242,6 +284,7 @@ def run_b200(args):
     vad = torch.empty((n_streams, n_frames), dtype=torch.float32, device=dev)
     den = cb.BatchDenoiser(n_streams, device=local)
     info0 = den.info
+    fp32 = cb.measure_fp32(local) if rank == 0 else None  # FFMA burst + unfused MAC burst on every SM, ~50 ms
 
     def step():
         den.reset_async()
@@ -271,8 +314,6 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = den.info["launches"]
-    # every kernel launch of the timed region is bracketed by CUDA events on its own (internal) stream
-    den.profile(True)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
@@ -283,10 +324,16 @@ def run_b200(args):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
-    kernel_prof = den.profile_read()
-    den.profile(False)
     total_ms = evs[0][0].elapsed_time(evs[-1][1])
     launches = den.info["launches"] - launches0
+    # per-kernel launch durations: one more step of the same workload, OUTSIDE the timed region, with every launch
+    # bracketed by CUDA events on the (internal) stream it is launched on; the pipeline runs exactly as above
+    # (seven kernels of neighbouring chunks overlap), so these are in-pipeline durations
+    den.profile(True)
+    step()
+    kernel_prof = den.profile_read()
+    den.profile(False)
+    prof_steps = 1
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -358,7 +405,9 @@ def run_b200(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e["pcm16_link"] = {"value": world * n_streams * e2e_frames / 100.0 * args.steps / float(tt.item()),
                              "unit": "stream-seconds/s", "h2d_bytes_per_step": n_streams * e2e_frames * FRAME * 2,
-                             "d2h_bytes_per_step": n_streams * e2e_frames * (FRAME * 2 + 4)}
+                             "d2h_bytes_per_step": n_streams * e2e_frames * (FRAME * 2 + 4),
+                             "api": "the same call with CRISPY_NS_IN_I16 | CRISPY_NS_OUT_I16 (PCM16 on the host link, "
+                                    "what the recorder stores: recording.rs:101-121)"}
         del hx16, hout16
 
     # ---- the same kernels one at a time (one stream): isolated durations, comparable with the ncu
@@ -409,7 +458,7 @@ def run_b200(args):
             front_end[name] = {"ms_per_launch": sec * 1e3, "stream_seconds_per_s": n_streams * fe_secs / sec,
                                "hbm_algorithmic_gbs": n_streams * (x44.shape[1] + n_out) * 4 / sec / 1e9,
                                "fp32_tflops": n_streams * n_out * flops / sec / 1e12}
-        front_end["sinc256"]["frac_fp32_nominal"] = front_end["sinc256"]["fp32_tflops"] / FP32_PEAK_TFLOPS_NOMINAL
+        front_end["sinc256"]["frac_fp32_measured"] = front_end["sinc256"]["fp32_tflops"] / fp32["ffma_tflops"]
         front_end["linear"]["frac_hbm"] = front_end["linear"]["hbm_algorithmic_gbs"] / measured_peaks()[0]
         del y48
         # ---- the other BASELINE.json configs on the same streams, 10 s each, device-resident (rank 0) ----
@@ -467,7 +516,7 @@ def run_b200(args):
     for name, (ms, n) in kernel_prof.items():
         if n == 0:
             continue
-        frames_per_launch = n_streams * n_frames * args.steps / n  # (stream, frame) units one launch processes
+        frames_per_launch = n_streams * n_frames * prof_steps / n  # (stream, frame) units one launch processes
         avg_s = ms / n / 1e3
         ent = {"kernel": name, "launches": n, "ms_total": ms, "share_of_kernel_time": ms / sum_ms,
                "avg_launch_us": avg_s * 1e6, "frames_per_launch": frames_per_launch,
@@ -498,12 +547,24 @@ def run_b200(args):
                         "timed region, kernels of neighbouring chunks running concurrently). No kernel of this path "
                         "is HBM-bound yet: they are issue/latency bound (profiles/)."}
     roofline_fp32 = {"whole_pipeline_tflops": ALL_FLOPS_PER_FRAME * n_streams * n_frames * args.steps / (total_ms / 1e3) / 1e12,
-                     "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL}
-    roofline_fp32["frac_whole_pipeline"] = roofline_fp32["whole_pipeline_tflops"] / FP32_PEAK_TFLOPS_NOMINAL
+                     "peak_tflops_measured_ffma_burst": fp32["ffma_tflops"],
+                     "unfused_tmacs_measured": fp32["unfused_tmacs"],
+                     "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
+                     "how": "crispy_ns_measure_fp32: register-resident FFMA chains (fused) and FMUL+FADD chains (the "
+                            "unfused multiply-add the pitch kernel's exactness contract requires) on every SM, best of 3"}
+    roofline_fp32["frac_whole_pipeline"] = roofline_fp32["whole_pipeline_tflops"] / fp32["ffma_tflops"]
+    # K1's own roofline: ~75 K unfused MACs per frame (coarse 35.3 K + candidates <= 28 K + fine 4.8 K + autocorr 4.3 K
+    # + downsample / FIR / energies ~3 K) against the measured unfused-MAC rate
+    for ent in kernels:
+        if ent["kernel"] == "ns_pitch_kernel":
+            ent["fp32_unfused"] = {"macs_per_frame": PITCH_MACS_PER_FRAME,
+                                   "achieved_tmacs": PITCH_MACS_PER_FRAME * ent["frames_per_launch"] / (ent["avg_launch_us"] * 1e-6) / 1e12,
+                                   "peak_tmacs": fp32["unfused_tmacs"]}
+            ent["fp32_unfused"]["frac"] = ent["fp32_unfused"]["achieved_tmacs"] / fp32["unfused_tmacs"]
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        cpu_baseline = cpu_reference_rate(target_seconds=12.0)
+        cpu_baseline = cpu_reference_rate(target_seconds=8.0, seconds_per_stream=args.seconds)
 
     line = {
         "metric": "stream-seconds of 48 kHz audio denoised per wall-second",
@@ -517,11 +578,160 @@ def run_b200(args):
                    "l2": f"inputs {x.numel() * 4 / 1e9:.1f} GB + outputs {x.numel() * 4 / 1e9:.1f} GB per step >> 126 MB L2 "
                          "(no flush needed)",
                    "weights": "synthetic seed 0 (nnnoiseless weights are not available offline)"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "e2e": e2e, "e2e_pcm16": (e2e or {}).get("pcm16_link"), "gpu_launches": int(launches),
         "roofline": roofline, "kernels": kernels, "kernels_isolated": kernels_isolated, "roofline_fp32": roofline_fp32,
         "front_end": front_end,
         "cpu_baseline": cpu_baseline,
         "parity_vs_oracle": parity, "wall_s_timed_region": t_wall,
+    }
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# the long configs at their real size: configs[3] (c4) and configs[4] (c5)
+# --------------------------------------------------------------------------------------------------
+def run_long(args):
+    """c4: 4,096 dual-source meetings x 10 min -- mic PCM16 denoised + raw app f32 -> clamp(mic + app) as dual-mono
+    stereo PCM16 (commands/recording.rs:260-264, recording.rs:101-121); counts meetings.  c5: 8,192 streams x 60 min,
+    f32 in/out.  Both are partitioned by stream over the N ranks (contiguous blocks, no collective), fed as calls of
+    --chunk-seconds of audio with every DenoiseState carried from call to call, the input of each call synthesised on
+    the device just before it (the recordings do not fit HBM: SURVEY.md 8(d)).  Only the denoise calls are timed:
+    one CUDA event pair per call on the launching stream, summed; max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import crispy_b200 as cb
+    from crispy_b200.shard import stream_block
+    from crispy_b200.synth import synth_chunk
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    c4 = args.config == "c4"
+    total_streams = args.total_streams or (4096 if c4 else 8192)
+    minutes = args.minutes or (10.0 if c4 else 60.0)
+    first, last = stream_block(total_streams, world, rank)
+    n = last - first
+    call_frames = args.chunk_seconds * 100
+    n_calls = max(1, int(round(minutes * 60.0 / args.chunk_seconds)))
+    den = cb.BatchDenoiser(n, device=local)
+    S = call_frames * FRAME
+    if c4:
+        mic = torch.empty((n, S), dtype=torch.int16, device=dev)
+        app = torch.empty((n, S), dtype=torch.float32, device=dev)
+        out = torch.empty((n, S, 2), dtype=torch.int16, device=dev)
+    else:
+        mic = torch.empty((n, S), dtype=torch.float32, device=dev)
+        app = None
+        out = torch.empty((n, S), dtype=torch.float32, device=dev)
+    vad = torch.empty((n, call_frames), dtype=torch.float32, device=dev)
+
+    def synth(call: int):
+        for f0 in range(0, call_frames, 100):
+            nf = min(100, call_frames - f0)
+            x = synth_chunk(n, nf * FRAME, first_stream=first, start_sample=(call * call_frames + f0) * FRAME, device=dev)
+            if c4:
+                mic[:, f0 * FRAME:(f0 + nf) * FRAME] = (x * 32767.0).round().clamp_(-32768, 32767).to(torch.int16)
+                app[:, f0 * FRAME:(f0 + nf) * FRAME] = torch.roll(x, 1, 0) * 0.5  # another meeting's voice as app audio
+            else:
+                mic[:, f0 * FRAME:(f0 + nf) * FRAME] = x
+
+    def call():
+        if c4:
+            den.process_streams(mic, unit_scale=True, app=app, mix_stereo_i16=True, out=out, vad=vad)
+        else:
+            den.process_streams(mic, unit_scale=True, out=out, vad=vad)
+
+    synth(0)
+    parity = None
+    if rank == 0 and args.parity_streams > 0 and not args.no_cpu_baseline:  # checker leg: first call, a few streams
+        from oracle import pyoracle as po
+        k = min(args.parity_streams, n)
+        call()
+        torch.cuda.synchronize(dev)
+        xin = (mic[:k].float() / 32768.0 if c4 else mic[:k]).cpu().numpy()
+        ref, rv = po.process_streams(po.Model.synthetic(0), xin, unit_scale=True, n_threads=k, native=True)
+        if c4:
+            want = np.stack([po.mix_dual_mono_i16(ref[i], app[i].cpu().numpy()).reshape(-1, 2) for i in range(k)])
+            d = np.abs(out[:k].cpu().numpy().astype(np.int32) - want.astype(np.int32))
+            parity = {"streams": k, "frames": call_frames, "max_abs_lsb": int(d.max()), "vad_max": float(np.abs(vad[:k].cpu().numpy() - rv).max())}
+        else:
+            err = out[:k].cpu().numpy().astype(np.float64) - ref
+            parity = {"streams": k, "frames": call_frames, "max_abs_fs": float(np.abs(err).max()),
+                      "vad_max": float(np.abs(vad[:k].cpu().numpy() - rv).max())}
+    for _ in range(max(3, args.warmup)):
+        call()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = den.info["launches"]
+    total_ms = 0.0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        den.reset()
+        for c in range(n_calls):
+            synth(c)  # untimed: the recording "arrives"
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            call()
+            e1.record()
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = den.info["launches"] - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    units = total_streams * n_calls * call_frames / 100.0  # stream-seconds (c4: meeting-seconds) per step, all ranks
+    value = units * args.steps / (total_ms_max / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm_peak, peak_src = measured_peaks()
+    bytes_per_frame = (FRAME * 2 + FRAME * 4 + FRAME * 4 + 4) if c4 else ALG_BYTES_PER_FRAME
+    achieved = bytes_per_frame * (n * n_calls * call_frames * args.steps) / (total_ms / 1e3) / 1e9
+    what = ("4,096 dual-source meetings x 10 min (BASELINE.json configs[3]): mic PCM16 denoised + raw app f32 -> "
+            "clamp(mic+app) as dual-mono stereo PCM16; counts meetings" if c4 else
+            "8,192 streams x 60 min (BASELINE.json configs[4]), f32 unit-scale in/out + VAD")
+    line = {
+        "metric": "stream-seconds of 48 kHz audio denoised per wall-second",
+        "value": value, "unit": "stream-seconds/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{what}; this run: {total_streams} x {minutes:g} min over {world} GPU(s)",
+                   "streams_this_rank": n, "calls_per_step": n_calls, "seconds_per_call": args.chunk_seconds,
+                   "state": "every DenoiseState carried across the calls of a step (reset between steps)",
+                   "timing": "only the denoise calls are timed (one CUDA event pair per call, summed, max over ranks); each "
+                             "call's input is synthesised on the device just before it, outside the timed region",
+                   "l2": f"{n * S * (6 if c4 else 4) / 1e9:.1f} GB in + {n * S * 4 / 1e9:.1f} GB out per call >> 126 MB L2",
+                   "chunk_frames": den.info["chunk_frames"], "parallelism": f"streams/{world}gpu, no collective"},
+        "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "whole pipeline (sum over the calls)",
+                     "algorithmic_bytes_per_frame": bytes_per_frame},
+        "cpu_baseline": None if args.no_cpu_baseline else cpu_reference_rate(8.0, 60.0),
+        "parity_vs_oracle": parity, "wall_s_with_synthesis": t_wall,
     }
     emit(line)
     if world > 1:
@@ -548,6 +758,8 @@ def main():
     os.dup2(2, 1)  # stdout must hold exactly one JSON line
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "c2":
+        run_long(args)
     else:
         run_b200(args)
 

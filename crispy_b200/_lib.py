@@ -30,6 +30,9 @@ SYMBOLS = [
     "crispy_ns_resample_host",
     "crispy_ns_wav_write_pcm16", "crispy_ns_wav_read_pcm16",
     "crispy_ns_kernel_count", "crispy_ns_kernel_name", "crispy_ns_batch_profile", "crispy_ns_batch_profile_read",
+    "crispy_ns_multi_create", "crispy_ns_multi_n_devices", "crispy_ns_multi_stream_range", "crispy_ns_multi_reset",
+    "crispy_ns_multi_process_streams_host", "crispy_ns_multi_destroy", "crispy_ns_denoise_wav_files",
+    "crispy_ns_measure_fp32",
 ]
 
 
@@ -99,6 +102,16 @@ def lib() -> C.CDLL:
     L.crispy_ns_resample_host.argtypes = [C.c_int, vp, vp, C.c_int, i64, i64, i64, C.c_int, C.c_int, C.c_int]
     L.crispy_ns_wav_write_pcm16.argtypes = [C.c_char_p, vp, i64, C.c_int, C.c_int]
     L.crispy_ns_wav_read_pcm16.argtypes = [C.c_char_p, vp, i64, C.POINTER(i64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.crispy_ns_multi_create.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.c_int, vpp]
+    L.crispy_ns_multi_n_devices.argtypes = [vp]
+    L.crispy_ns_multi_stream_range.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.crispy_ns_multi_reset.argtypes = [vp]
+    L.crispy_ns_multi_process_streams_host.argtypes = [vp, vp, vp, vp, vp, C.c_int, i64, i64, i64, i64, u32, f32]
+    L.crispy_ns_multi_destroy.argtypes = [vp]
+    L.crispy_ns_multi_destroy.restype = None
+    L.crispy_ns_denoise_wav_files.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, u32, f32,
+                                              C.POINTER(f32)]
+    L.crispy_ns_measure_fp32.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
 

@@ -6,9 +6,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <exception>
 #include <map>
 #include <mutex>
+#include <new>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -90,12 +93,13 @@ __global__ void ns_linear_resample_kernel(const float *__restrict__ in, float *_
 template <int Q>
 __global__ void __launch_bounds__(1024) ns_sinc_resample_kernel(const float *__restrict__ in, float *__restrict__ out,
                                                                 const float *__restrict__ hT,  // [sinc_len][L]
-                                                                long long n_total, long long in_first,
+                                                                long long n_total, long long in_first, long long in_end,
                                                                 long long first_out, long long n_out, long long in_stride,
                                                                 long long out_stride, int L, int M, int sinc_len,
                                                                 int span) {
-  // the recording has n_total input samples; in[0] is its sample in_first; outputs first_out .. first_out + n_out
-  // (first_out a multiple of L) are written to out[0 .. n_out)
+  // the recording has n_total input samples; in[0] is its sample in_first and samples [in_first, in_end) are present;
+  // outputs first_out .. first_out + n_out (first_out a multiple of L) are written to out[0 .. n_out).  A partial last
+  // tile stages a full tile's span: what lies beyond the caller's window feeds no stored output and is not read.
   extern __shared__ float xs[];
   const int T = blockDim.x, t = threadIdx.x;
   const long long n0 = first_out + (long long)blockIdx.x * T * Q;  // multiple of L
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(1024) ns_sinc_resample_kernel(const float *__r
   const float *src = in + (long long)blockIdx.y * in_stride - in_first;
   for (int i = t; i < span; i += T) {
     const long long g = base0 + i;
-    xs[i] = (g >= 0 && g < n_total) ? __ldg(src + g) : 0.f;
+    xs[i] = (g >= in_first && g < in_end) ? __ldg(src + g) : 0.f;
   }
   __syncthreads();
   const int pos = t * M;  // t < 1024, M < 2^20
@@ -132,9 +136,38 @@ __global__ void __launch_bounds__(1024) ns_sinc_resample_kernel(const float *__r
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static int fail(int code, const std::string &msg) {
-  g_err = msg;
+static int fail(int code, const std::string &msg) noexcept {
+  try {
+    g_err = msg;
+  } catch (...) {  // the message itself could not be stored: the code still goes back
+  }
   return code;
+}
+static int fail(int code, const char *msg) noexcept {
+  try {
+    g_err = msg;
+  } catch (...) {
+  }
+  return code;
+}
+// Every extern "C" entry point runs its body through guard(): nothing thrown inside (std::bad_alloc from a
+// std::vector / std::string / std::map, std::system_error from a std::thread) crosses the C boundary -- the
+// reference builds with panic = "abort" (Cargo.toml:10-20) precisely so that nothing unwinds through FFI.
+template <class F>
+static int guard(const char *what, F &&body) noexcept {
+  try {
+    return body();
+  } catch (const std::bad_alloc &) {
+    return fail(CRISPY_NS_ENOMEM, what);
+  } catch (const std::exception &e) {
+    try {
+      return fail(CRISPY_NS_EINVAL, std::string(what) + ": " + e.what());
+    } catch (...) {
+      return fail(CRISPY_NS_EINVAL, what);
+    }
+  } catch (...) {
+    return fail(CRISPY_NS_EINVAL, what);
+  }
 }
 #define NS_CUDA(expr)                                                                              \
   do {                                                                                             \
@@ -322,6 +355,8 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
                       const RunHooks *hooks = nullptr) {
   if (!b || !d_in || !d_out || n_frames < 0) return fail(CRISPY_NS_EINVAL, "process_streams: bad argument");
   if (n_frames == 0) return CRISPY_NS_OK;
+  if ((flags & CRISPY_NS_OUT_I16) && !(flags & CRISPY_NS_MIX_STEREO_I16) && volume != 1.0f)
+    return fail(CRISPY_NS_EINVAL, "process_streams: CRISPY_NS_OUT_I16 is in 16-bit scale and takes no volume (use 1.0)");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(configure_kernels(b->device));
   ns::Params p;
@@ -401,13 +436,15 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
 }
 
 // ------------------------------------------------------------------------------------------------
-// C ABI
+// C ABI: the implementations live in namespace impl under the names include/crispy_ns.h declares; the extern "C"
+// symbols themselves are the generated forwarding wrappers of crispy_ns_abi.inc (included at the end), which
+// catch everything.
 // ------------------------------------------------------------------------------------------------
-extern "C" {
+namespace impl {
 
-int crispy_ns_frame_size(void) { return ns::kFrame; }
-const char *crispy_ns_last_error(void) { return g_err.c_str(); }
-int crispy_ns_device_count(void) {
+int frame_size(void) { return ns::kFrame; }
+const char *last_error(void) { return g_err.c_str(); }
+int device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
     cudaGetLastError();
@@ -415,9 +452,9 @@ int crispy_ns_device_count(void) {
   }
   return n;
 }
-int crispy_ns_debug_floats(void) { return ns::kDbgFloats; }
+int debug_floats(void) { return ns::kDbgFloats; }
 
-int crispy_ns_model_synthetic(uint64_t seed, crispy_ns_model **out) {
+int model_synthetic(uint64_t seed, crispy_ns_model **out) {
   if (!out) return fail(CRISPY_NS_EINVAL, "model_synthetic: out is null");
   crispy_ns_model *m = new (std::nothrow) crispy_ns_model();
   if (!m) return fail(CRISPY_NS_ENOMEM, "out of memory");
@@ -425,7 +462,7 @@ int crispy_ns_model_synthetic(uint64_t seed, crispy_ns_model **out) {
   *out = m;
   return CRISPY_NS_OK;
 }
-int crispy_ns_model_from_bytes(const void *blob, size_t len, crispy_ns_model **out) {
+int model_from_bytes(const void *blob, size_t len, crispy_ns_model **out) {
   if (!out) return fail(CRISPY_NS_EINVAL, "model_from_bytes: out is null");
   crispy_ns_model *m = new (std::nothrow) crispy_ns_model();
   if (!m) return fail(CRISPY_NS_ENOMEM, "out of memory");
@@ -437,14 +474,14 @@ int crispy_ns_model_from_bytes(const void *blob, size_t len, crispy_ns_model **o
   *out = m;
   return CRISPY_NS_OK;
 }
-int crispy_ns_model_to_bytes(const crispy_ns_model *m, void *buf, size_t cap, size_t *needed) {
+int model_to_bytes(const crispy_ns_model *m, void *buf, size_t cap, size_t *needed) {
   if (!m) return fail(CRISPY_NS_EINVAL, "model_to_bytes: model is null");
   const std::vector<uint8_t> b = ns::model_to_bytes(m->m);
   if (needed) *needed = b.size();
   if (buf && cap >= b.size()) memcpy(buf, b.data(), b.size());
   return CRISPY_NS_OK;
 }
-void crispy_ns_model_destroy(crispy_ns_model *m) { delete m; }
+void model_destroy(crispy_ns_model *m) { delete m; }
 
 static int default_model(ns::Model &m) {
   const char *path = getenv("CRISPY_NS_WEIGHTS");
@@ -464,7 +501,7 @@ static int default_model(ns::Model &m) {
   return CRISPY_NS_OK;
 }
 
-void crispy_ns_batch_destroy(crispy_ns_batch *b) {
+void batch_destroy(crispy_ns_batch *b) {
   if (!b) return;
   cudaSetDevice(b->device);
   prof_clear(b);
@@ -501,9 +538,9 @@ void crispy_ns_batch_destroy(crispy_ns_batch *b) {
   delete b;
 }
 
-int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_streams, crispy_ns_batch **out) {
+int batch_create(const crispy_ns_model *model, int device, int n_streams, crispy_ns_batch **out) {
   if (!out || n_streams < 1) return fail(CRISPY_NS_EINVAL, "batch_create: bad argument");
-  const int ndev = crispy_ns_device_count();
+  const int ndev = device_count();
   if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
   ns::Model local;
@@ -587,14 +624,14 @@ int crispy_ns_batch_create(const crispy_ns_model *model, int device, int n_strea
     }
   }
   if (e != cudaSuccess) {
-    crispy_ns_batch_destroy(b);
+    batch_destroy(b);
     return fail(CRISPY_NS_ECUDA, std::string("batch_create: ") + cudaGetErrorString(e));
   }
   *out = b;
   return CRISPY_NS_OK;
 }
 
-int crispy_ns_batch_reset(crispy_ns_batch *b) {
+int batch_reset(crispy_ns_batch *b) {
   if (!b) return fail(CRISPY_NS_EINVAL, "batch_reset: null handle");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(cudaDeviceSynchronize());
@@ -602,7 +639,7 @@ int crispy_ns_batch_reset(crispy_ns_batch *b) {
   b->frames_done = 0;
   return CRISPY_NS_OK;
 }
-int crispy_ns_batch_reset_async(crispy_ns_batch *b, void *cuda_stream) {
+int batch_reset_async(crispy_ns_batch *b, void *cuda_stream) {
   if (!b) return fail(CRISPY_NS_EINVAL, "batch_reset_async: null handle");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(cudaMemsetAsync(b->d_state, 0, (size_t)b->n_streams * ns::kStateFloats * sizeof(float), (cudaStream_t)cuda_stream));
@@ -611,9 +648,9 @@ int crispy_ns_batch_reset_async(crispy_ns_batch *b, void *cuda_stream) {
   b->frames_done = 0;
   return CRISPY_NS_OK;
 }
-int crispy_ns_batch_n_streams(const crispy_ns_batch *b) { return b ? b->n_streams : 0; }
+int batch_n_streams(const crispy_ns_batch *b) { return b ? b->n_streams : 0; }
 
-int crispy_ns_process_streams(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad,
+int process_streams(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad,
                               const float *d_app, int n_frames, int64_t in_stride, int64_t out_stride,
                               int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume,
                               void *cuda_stream) {
@@ -621,14 +658,14 @@ int crispy_ns_process_streams(crispy_ns_batch *b, const void *d_in, void *d_out,
                     app_stride, flags, volume, (cudaStream_t)cuda_stream);
 }
 
-int crispy_ns_process_streams_debug(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad,
+int process_streams_debug(crispy_ns_batch *b, const void *d_in, void *d_out, float *d_vad,
                                     float *d_taps, int n_frames, int64_t in_stride, int64_t out_stride,
                                     uint32_t flags, float volume, void *cuda_stream) {
   return run_device(b, d_in, d_out, d_vad, nullptr, d_taps, n_frames, in_stride, out_stride, n_frames, 0,
                     flags, volume, (cudaStream_t)cuda_stream);
 }
 
-int crispy_ns_process_streams_host(crispy_ns_batch *b, const void *h_in, void *h_out, float *h_vad,
+int process_streams_host(crispy_ns_batch *b, const void *h_in, void *h_out, float *h_vad,
                                    const float *h_app, int n_frames, int64_t in_stride,
                                    int64_t out_stride, int64_t vad_stride, int64_t app_stride,
                                    uint32_t flags, float volume) {
@@ -741,21 +778,21 @@ int crispy_ns_process_streams_host(crispy_ns_batch *b, const void *h_in, void *h
   return CRISPY_NS_OK;
 }
 
-size_t crispy_ns_batch_state_size(const crispy_ns_batch *b) {
+size_t batch_state_size(const crispy_ns_batch *b) {
   return b ? (size_t)b->n_streams * ns::kStateFloats * sizeof(float) + 16 : 0;
 }
-int crispy_ns_batch_save_state(crispy_ns_batch *b, void *buf, size_t len) {
-  if (!b || !buf || len < crispy_ns_batch_state_size(b)) return fail(CRISPY_NS_EINVAL, "save_state: bad argument");
+int batch_save_state(crispy_ns_batch *b, void *buf, size_t len) {
+  if (!b || !buf || len < batch_state_size(b)) return fail(CRISPY_NS_EINVAL, "save_state: bad argument");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(cudaDeviceSynchronize());
   int64_t hdr[2] = {b->n_streams | (b->chunks_done & 1) << 40, b->frames_done};
   memcpy(buf, hdr, 16);
-  NS_CUDA(cudaMemcpy((char *)buf + 16, b->d_state, len - 16 < crispy_ns_batch_state_size(b) - 16 ? len - 16 : crispy_ns_batch_state_size(b) - 16,
+  NS_CUDA(cudaMemcpy((char *)buf + 16, b->d_state, len - 16 < batch_state_size(b) - 16 ? len - 16 : batch_state_size(b) - 16,
                      cudaMemcpyDeviceToHost));
   return CRISPY_NS_OK;
 }
-int crispy_ns_batch_load_state(crispy_ns_batch *b, const void *buf, size_t len) {
-  if (!b || !buf || len < crispy_ns_batch_state_size(b)) return fail(CRISPY_NS_EINVAL, "load_state: bad argument");
+int batch_load_state(crispy_ns_batch *b, const void *buf, size_t len) {
+  if (!b || !buf || len < batch_state_size(b)) return fail(CRISPY_NS_EINVAL, "load_state: bad argument");
   int64_t hdr[2];
   memcpy(hdr, buf, 16);
   const int64_t sel = (hdr[0] >> 40) & 1;
@@ -763,12 +800,12 @@ int crispy_ns_batch_load_state(crispy_ns_batch *b, const void *buf, size_t len) 
   if (hdr[0] != b->n_streams) return fail(CRISPY_NS_EINVAL, "load_state: stream count mismatch");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(cudaDeviceSynchronize());
-  NS_CUDA(cudaMemcpy(b->d_state, (const char *)buf + 16, crispy_ns_batch_state_size(b) - 16, cudaMemcpyHostToDevice));
+  NS_CUDA(cudaMemcpy(b->d_state, (const char *)buf + 16, batch_state_size(b) - 16, cudaMemcpyHostToDevice));
   b->frames_done = hdr[1];
   if ((b->chunks_done & 1) != sel) b->chunks_done += 1;  // synthesis_mem double buffer parity (ns_common.h kStSynth)
   return CRISPY_NS_OK;
 }
-int crispy_ns_batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_ctas, int64_t *launches,
+int batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_ctas, int64_t *launches,
                          int64_t *frames_done) {  // (rnn_streams_per_cta, chunk_frames, ...)
   if (!b) return fail(CRISPY_NS_EINVAL, "batch_info: null handle");
   if (streams_per_cta) *streams_per_cta = ns::kMmaStreams;
@@ -778,13 +815,13 @@ int crispy_ns_batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_
   return CRISPY_NS_OK;
 }
 
-int crispy_ns_kernel_count(void) { return kNumKernels; }
-const char *crispy_ns_kernel_name(int k) {
+int kernel_count(void) { return kNumKernels; }
+const char *kernel_name(int k) {
   static const char *names[kNumKernels] = {"ns_highpass_kernel", "ns_pitch_kernel",    "ns_pitchscan_kernel", "ns_spectrum_kernel",
                                            "ns_features_kernel", "ns_rnn_kernel",      "ns_synthesis_kernel"};
   return (k >= 0 && k < kNumKernels) ? names[k] : "";
 }
-int crispy_ns_batch_profile(crispy_ns_batch *b, int enable) {
+int batch_profile(crispy_ns_batch *b, int enable) {
   if (!b) return fail(CRISPY_NS_EINVAL, "batch_profile: null handle");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(cudaDeviceSynchronize());
@@ -792,7 +829,7 @@ int crispy_ns_batch_profile(crispy_ns_batch *b, int enable) {
   b->prof_on = enable != 0;
   return CRISPY_NS_OK;
 }
-int crispy_ns_batch_profile_read(crispy_ns_batch *b, double *ms_total, int64_t *n_launches, int n_kernels) {
+int batch_profile_read(crispy_ns_batch *b, double *ms_total, int64_t *n_launches, int n_kernels) {
   if (!b || !ms_total || !n_launches || n_kernels < kNumKernels) return fail(CRISPY_NS_EINVAL, "batch_profile_read: bad argument");
   NS_CUDA(cudaSetDevice(b->device));
   NS_CUDA(cudaDeviceSynchronize());
@@ -810,17 +847,17 @@ int crispy_ns_batch_profile_read(crispy_ns_batch *b, double *ms_total, int64_t *
   return CRISPY_NS_OK;
 }
 
-int crispy_ns_host_alloc(void **ptr, size_t bytes) {
+int host_alloc(void **ptr, size_t bytes) {
   if (!ptr) return fail(CRISPY_NS_EINVAL, "host_alloc: null");
   NS_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
   return CRISPY_NS_OK;
 }
-void crispy_ns_host_free(void *ptr) {
+void host_free(void *ptr) {
   if (ptr) cudaFreeHost(ptr);
 }
 
 // ---- single stream: DenoiseState ------------------------------------------------------------------
-void crispy_ns_destroy(crispy_ns_state *st) {
+void destroy(crispy_ns_state *st) {
   if (!st) return;
   if (st->b) cudaSetDevice(st->b->device);
   for (int i = 0; i < kSlots; i++)
@@ -828,14 +865,14 @@ void crispy_ns_destroy(crispy_ns_state *st) {
   if (st->s) cudaStreamDestroy(st->s);
   if (st->h_pin) cudaFreeHost(st->h_pin);
   if (st->d_io) cudaFree(st->d_io);
-  crispy_ns_batch_destroy(st->b);
+  batch_destroy(st->b);
   delete st;
 }
-int crispy_ns_create(const crispy_ns_model *model, int device, crispy_ns_state **out) {
+int create(const crispy_ns_model *model, int device, crispy_ns_state **out) {
   if (!out) return fail(CRISPY_NS_EINVAL, "create: out is null");
   crispy_ns_state *st = new (std::nothrow) crispy_ns_state();
   if (!st) return fail(CRISPY_NS_ENOMEM, "out of memory");
-  int rc = crispy_ns_batch_create(model, device, 1, &st->b);
+  int rc = batch_create(model, device, 1, &st->b);
   if (rc != CRISPY_NS_OK) {
     delete st;
     return rc;
@@ -844,7 +881,7 @@ int crispy_ns_create(const crispy_ns_model *model, int device, crispy_ns_state *
   if (e == cudaSuccess) e = cudaMalloc((void **)&st->d_io, 964 * sizeof(float));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st->s, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
-    crispy_ns_destroy(st);
+    destroy(st);
     return fail(CRISPY_NS_ECUDA, std::string("create: ") + cudaGetErrorString(e));
   }
   *out = st;
@@ -895,7 +932,7 @@ static int frame_graph(crispy_ns_state *st, int slot) {
   return CRISPY_NS_OK;
 }
 
-int crispy_ns_process_frame(crispy_ns_state *st, float *out480, const float *in480, float *vad) {
+int process_frame(crispy_ns_state *st, float *out480, const float *in480, float *vad) {
   if (!st || !out480 || !in480) return fail(CRISPY_NS_EINVAL, "process_frame: bad argument");
   crispy_ns_batch *b = st->b;
   NS_CUDA(cudaSetDevice(b->device));
@@ -923,9 +960,9 @@ int crispy_ns_process_frame(crispy_ns_state *st, float *out480, const float *in4
   if (vad) *vad = st->h_pin[960];
   return CRISPY_NS_OK;
 }
-int crispy_ns_reset(crispy_ns_state *st) {
+int reset(crispy_ns_state *st) {
   if (!st) return fail(CRISPY_NS_EINVAL, "reset: null handle");
-  return crispy_ns_batch_reset(st->b);
+  return batch_reset(st->b);
 }
 
 // ---- a4 / f2: LinearResampler -------------------------------------------------------------------
@@ -951,7 +988,24 @@ static void build_resample_table(float input_rate, float output_rate, int64_t n_
     }
   }
 }
-int64_t crispy_ns_linear_resample_count(float input_rate, float output_rate, int64_t n_in) {
+namespace {
+struct LinKey {
+  int device;
+  uint32_t in_rate_bits, out_rate_bits;
+  int64_t n_in;
+  bool operator<(const LinKey &o) const {
+    return std::tie(device, in_rate_bits, out_rate_bits, n_in) < std::tie(o.device, o.in_rate_bits, o.out_rate_bits, o.n_in);
+  }
+};
+struct LinEntry {
+  int32_t *d_idx = nullptr;
+  float *d_frac = nullptr;
+  int64_t n_out = 0;
+};
+std::mutex g_lin_mu;
+std::map<LinKey, LinEntry> g_lin_tables;  // device copies of the (index, fraction) tables
+}  // namespace
+int64_t linear_resample_count(float input_rate, float output_rate, int64_t n_in) {
   if (n_in <= 0) return 0;
   const float d = input_rate - output_rate;
   if ((d < 0 ? -d : d) < 1.0f) return n_in;
@@ -959,12 +1013,12 @@ int64_t crispy_ns_linear_resample_count(float input_rate, float output_rate, int
   build_resample_table(input_rate, output_rate, n_in, t);
   return (int64_t)t.idx.size();
 }
-int crispy_ns_linear_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
+int linear_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
                               int64_t in_stride, int64_t out_stride, float input_rate,
                               float output_rate, void *cuda_stream) {
   if (!d_in || !d_out || n_streams < 1 || n_in < 0) return fail(CRISPY_NS_EINVAL, "linear_resample: bad argument");
   if (n_in >= (1ll << 31)) return fail(CRISPY_NS_EINVAL, "linear_resample: n_in too large for one call");
-  const int ndev = crispy_ns_device_count();
+  const int ndev = device_count();
   if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
   NS_CUDA(cudaSetDevice(device));
@@ -975,24 +1029,55 @@ int crispy_ns_linear_resample(int device, const float *d_in, float *d_out, int n
                               n_streams, cudaMemcpyDeviceToDevice, st));
     return CRISPY_NS_OK;
   }
-  ResampleTable t;
-  build_resample_table(input_rate, output_rate, n_in, t);
-  const int64_t n_out = (int64_t)t.idx.size();
-  if (n_out == 0) return CRISPY_NS_OK;
+  // The (index, fraction) table depends only on (rates, n_in): it is built and uploaded once per device and kept
+  // (like the sinc taps), so the call itself is asynchronous on `st` and capturable in a CUDA graph.
   int32_t *d_idx = nullptr;
   float *d_frac = nullptr;
-  NS_CUDA(cudaMallocAsync((void **)&d_idx, (size_t)n_out * 4, st));
-  NS_CUDA(cudaMallocAsync((void **)&d_frac, (size_t)n_out * 4, st));
-  NS_CUDA(cudaMemcpyAsync(d_idx, t.idx.data(), (size_t)n_out * 4, cudaMemcpyHostToDevice, st));
-  NS_CUDA(cudaMemcpyAsync(d_frac, t.frac.data(), (size_t)n_out * 4, cudaMemcpyHostToDevice, st));
-  NS_CUDA(cudaStreamSynchronize(st));  // the host table goes out of scope below
+  int64_t n_out = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_lin_mu);
+    uint32_t ri, ro;
+    memcpy(&ri, &input_rate, 4);
+    memcpy(&ro, &output_rate, 4);
+    const LinKey key{device, ri, ro, n_in};
+    auto it = g_lin_tables.find(key);
+    if (it == g_lin_tables.end()) {
+      if (g_lin_tables.size() >= 32) {  // bounded cache: drop everything once no stream can still be reading it
+        NS_CUDA(cudaDeviceSynchronize());
+        for (auto &kv : g_lin_tables) {
+          cudaSetDevice(kv.first.device);
+          cudaFree(kv.second.d_idx);
+          cudaFree(kv.second.d_frac);
+        }
+        g_lin_tables.clear();
+        NS_CUDA(cudaSetDevice(device));
+      }
+      ResampleTable t;
+      build_resample_table(input_rate, output_rate, n_in, t);
+      LinEntry e;
+      e.n_out = (int64_t)t.idx.size();
+      if (e.n_out > 0) {
+        NS_CUDA(cudaMalloc((void **)&e.d_idx, (size_t)e.n_out * 4));
+        if (cudaError_t ce = cudaMalloc((void **)&e.d_frac, (size_t)e.n_out * 4); ce != cudaSuccess) {
+          cudaFree(e.d_idx);
+          return fail(CRISPY_NS_ECUDA, std::string("linear_resample: ") + cudaGetErrorString(ce));
+        }
+        // synchronous copies from the pageable host table: done before it goes out of scope
+        NS_CUDA(cudaMemcpy(e.d_idx, t.idx.data(), (size_t)e.n_out * 4, cudaMemcpyHostToDevice));
+        NS_CUDA(cudaMemcpy(e.d_frac, t.frac.data(), (size_t)e.n_out * 4, cudaMemcpyHostToDevice));
+      }
+      it = g_lin_tables.emplace(key, e).first;
+    }
+    d_idx = it->second.d_idx;
+    d_frac = it->second.d_frac;
+    n_out = it->second.n_out;
+  }
+  if (n_out == 0) return CRISPY_NS_OK;
   int gx = (int)((n_out + 255) / 256);
   if (gx > 148 * 8) gx = 148 * 8;
   dim3 grid(gx, n_streams);
   ns_linear_resample_kernel<<<grid, 256, 0, st>>>(d_in, d_out, d_idx, d_frac, n_out, in_stride, out_stride);
   NS_CUDA(cudaGetLastError());
-  NS_CUDA(cudaFreeAsync(d_idx, st));
-  NS_CUDA(cudaFreeAsync(d_frac, st));
   return CRISPY_NS_OK;
 }
 
@@ -1050,12 +1135,12 @@ void sinc_taps_transposed(int L, int M, int sinc_len, float f_cutoff, std::vecto
 }
 }  // namespace
 
-int64_t crispy_ns_sinc_resample_count(int input_rate, int output_rate, int64_t n_in) {
+int64_t sinc_resample_count(int input_rate, int output_rate, int64_t n_in) {
   int L, M;
   if (n_in <= 0 || !reduce_ratio(input_rate, output_rate, &L, &M)) return 0;
   return (int64_t)(((unsigned long long)n_in * (unsigned)L + (unsigned)M - 1) / (unsigned)M);
 }
-int crispy_ns_sinc_resample_needed(int input_rate, int output_rate, int sinc_len, int64_t n_total, int64_t first_out,
+int sinc_resample_needed(int input_rate, int output_rate, int sinc_len, int64_t n_total, int64_t first_out,
                                    int64_t n_out, int64_t *in_first, int64_t *n_in) {
   int L, M;
   if (sinc_len == 0) sinc_len = 256;
@@ -1077,7 +1162,7 @@ int crispy_ns_sinc_resample_needed(int input_rate, int output_rate, int sinc_len
   return CRISPY_NS_OK;
 }
 
-int crispy_ns_sinc_resample_chunk(int device, const float *d_in, int64_t in_first, int64_t n_in, int64_t n_total,
+int sinc_resample_chunk(int device, const float *d_in, int64_t in_first, int64_t n_in, int64_t n_total,
                                   float *d_out, int64_t first_out, int64_t n_out, int n_streams, int64_t in_stride,
                                   int64_t out_stride, int input_rate, int output_rate, int sinc_len, float f_cutoff,
                                   void *cuda_stream) {
@@ -1092,16 +1177,16 @@ int crispy_ns_sinc_resample_chunk(int device, const float *d_in, int64_t in_firs
     return fail(CRISPY_NS_EINVAL, "sinc_resample: output_rate/input_rate must reduce to L/M with L <= 1024");
   if (M >= (1 << 20)) return fail(CRISPY_NS_EINVAL, "sinc_resample: ratio too extreme");
   if (first_out % L) return fail(CRISPY_NS_EINVAL, "sinc_resample: first_out must be a multiple of L (a whole number of periods)");
-  if (first_out + n_out > crispy_ns_sinc_resample_count(input_rate, output_rate, n_total))
+  if (first_out + n_out > sinc_resample_count(input_rate, output_rate, n_total))
     return fail(CRISPY_NS_EINVAL, "sinc_resample: outputs beyond the end of the recording");
   {
     int64_t need_first = 0, need_n = 0;
-    crispy_ns_sinc_resample_needed(input_rate, output_rate, sinc_len, n_total, first_out, n_out, &need_first, &need_n);
+    sinc_resample_needed(input_rate, output_rate, sinc_len, n_total, first_out, n_out, &need_first, &need_n);
     if (need_n > 0 && (need_first < in_first || need_first + need_n > in_first + n_in))
       return fail(CRISPY_NS_EINVAL, "sinc_resample: the input window does not cover the taps of the requested outputs "
                                     "(crispy_ns_sinc_resample_needed gives the range)");
   }
-  const int ndev = crispy_ns_device_count();
+  const int ndev = device_count();
   if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
   NS_CUDA(cudaSetDevice(device));
@@ -1133,6 +1218,8 @@ int crispy_ns_sinc_resample_chunk(int device, const float *d_in, int64_t in_firs
   if (span * 4 > 200 * 1024) return fail(CRISPY_NS_EINVAL, "sinc_resample: decimation ratio too large for one tile");
   const size_t smem = (size_t)span * sizeof(float);
   const long long tiles = (n_out + (long long)T * Q - 1) / ((long long)T * Q);
+  // samples of the recording the kernel may read: the caller's window, clipped to the recording
+  const long long in_end = (in_first + n_in < n_total) ? in_first + n_in : n_total;
   if (tiles > 0x7fffffffll || n_streams > 65535) return fail(CRISPY_NS_EINVAL, "sinc_resample: too large for one call");
   dim3 grid((unsigned)tiles, (unsigned)n_streams);
 #define NS_SINC_LAUNCH(QQ)                                                                               \
@@ -1140,7 +1227,7 @@ int crispy_ns_sinc_resample_chunk(int device, const float *d_in, int64_t in_firs
     if (smem > 48 * 1024)                                                                                \
       NS_CUDA(cudaFuncSetAttribute(ns_sinc_resample_kernel<QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)smem));                                                          \
-    ns_sinc_resample_kernel<QQ><<<grid, T, smem, st>>>(d_in, d_out, d_taps, n_total, in_first, first_out, n_out, \
+    ns_sinc_resample_kernel<QQ><<<grid, T, smem, st>>>(d_in, d_out, d_taps, n_total, in_first, in_end, first_out, n_out, \
                                                        in_stride, out_stride, L, M, sinc_len, (int)span); \
   } while (0)
   switch (Q) {
@@ -1154,27 +1241,27 @@ int crispy_ns_sinc_resample_chunk(int device, const float *d_in, int64_t in_firs
   return CRISPY_NS_OK;
 }
 
-int crispy_ns_sinc_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
+int sinc_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
                             int64_t in_stride, int64_t out_stride, int input_rate, int output_rate,
                             int sinc_len, float f_cutoff, void *cuda_stream) {
   if (n_in < 0) return fail(CRISPY_NS_EINVAL, "sinc_resample: bad argument");
   int L, M;
   if (!reduce_ratio(input_rate, output_rate, &L, &M))
     return fail(CRISPY_NS_EINVAL, "sinc_resample: output_rate/input_rate must reduce to L/M with L <= 1024");
-  return crispy_ns_sinc_resample_chunk(device, d_in, 0, n_in, n_in, d_out, 0,
-                                       crispy_ns_sinc_resample_count(input_rate, output_rate, n_in), n_streams, in_stride,
+  return sinc_resample_chunk(device, d_in, 0, n_in, n_in, d_out, 0,
+                                       sinc_resample_count(input_rate, output_rate, n_in), n_streams, in_stride,
                                        out_stride, input_rate, output_rate, sinc_len, f_cutoff, cuda_stream);
 }
 
-int crispy_ns_resample_host(int device, const float *h_in, float *h_out, int n_streams, int64_t n_in,
+int resample_host(int device, const float *h_in, float *h_out, int n_streams, int64_t n_in,
                             int64_t in_stride, int64_t out_stride, int input_rate, int output_rate, int kind) {
   if (!h_in || !h_out || n_streams < 1 || n_in < 0 || (kind != 0 && kind != 1))
     return fail(CRISPY_NS_EINVAL, "resample_host: bad argument");
-  const int ndev = crispy_ns_device_count();
+  const int ndev = device_count();
   if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
-  const int64_t n_out = kind == 0 ? crispy_ns_linear_resample_count((float)input_rate, (float)output_rate, n_in)
-                                  : crispy_ns_sinc_resample_count(input_rate, output_rate, n_in);
+  const int64_t n_out = kind == 0 ? linear_resample_count((float)input_rate, (float)output_rate, n_in)
+                                  : sinc_resample_count(input_rate, output_rate, n_in);
   if (n_in == 0 || n_out == 0) return CRISPY_NS_OK;
   NS_CUDA(cudaSetDevice(device));
   float *d_in = nullptr, *d_out = nullptr;
@@ -1187,9 +1274,9 @@ int crispy_ns_resample_host(int device, const float *h_in, float *h_out, int n_s
   cudaError_t e = cudaMemcpy2D(d_in, (size_t)n_in * 4, h_in, (size_t)in_stride * 4, (size_t)n_in * 4, n_streams,
                                cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    rc = kind == 0 ? crispy_ns_linear_resample(device, d_in, d_out, n_streams, n_in, n_in, n_out, (float)input_rate,
+    rc = kind == 0 ? linear_resample(device, d_in, d_out, n_streams, n_in, n_in, n_out, (float)input_rate,
                                                (float)output_rate, nullptr)
-                   : crispy_ns_sinc_resample(device, d_in, d_out, n_streams, n_in, n_in, n_out, input_rate, output_rate,
+                   : sinc_resample(device, d_in, d_out, n_streams, n_in, n_in, n_out, input_rate, output_rate,
                                              0, 0.f, nullptr);
     if (rc == CRISPY_NS_OK)
       e = cudaMemcpy2D(h_out, (size_t)out_stride * 4, d_out, (size_t)n_out * 4, (size_t)n_out * 4, n_streams,
@@ -1213,7 +1300,7 @@ static void le32(uint8_t *p, uint32_t v) {
   p[2] = (uint8_t)(v >> 16);
   p[3] = (uint8_t)(v >> 24);
 }
-int crispy_ns_wav_write_pcm16(const char *path, const int16_t *interleaved, int64_t n_frames, int channels,
+int wav_write_pcm16(const char *path, const int16_t *interleaved, int64_t n_frames, int channels,
                               int sample_rate) {
   if (!path || (!interleaved && n_frames > 0) || n_frames < 0 || channels < 1 || sample_rate < 1)
     return fail(CRISPY_NS_EINVAL, "wav_write: bad argument");
@@ -1239,7 +1326,7 @@ int crispy_ns_wav_write_pcm16(const char *path, const int16_t *interleaved, int6
   ok = (fclose(f) == 0) && ok;
   return ok ? CRISPY_NS_OK : fail(CRISPY_NS_EIO, "wav_write: short write");
 }
-int crispy_ns_wav_read_pcm16(const char *path, int16_t *interleaved, int64_t cap_samples, int64_t *n_frames,
+int wav_read_pcm16(const char *path, int16_t *interleaved, int64_t cap_samples, int64_t *n_frames,
                              int *channels, int *sample_rate) {
   if (!path) return fail(CRISPY_NS_EINVAL, "wav_read: bad argument");
   FILE *f = fopen(path, "rb");
@@ -1290,7 +1377,246 @@ int crispy_ns_wav_read_pcm16(const char *path, int16_t *interleaved, int64_t cap
   return fail(CRISPY_NS_EIO, "wav_read: no fmt/data chunk");
 }
 
-}  // extern "C"
+
+// ---- (e) several GPUs from one process ---------------------------------------------------------------
+}  // namespace impl
+struct crispy_ns_multi {
+  int n_streams = 0;
+  std::vector<int> device, first, count;
+  std::vector<crispy_ns_batch *> batch;
+};
+namespace impl {
+
+void multi_destroy(crispy_ns_multi *m) {
+  if (!m) return;
+  for (crispy_ns_batch *b : m->batch) batch_destroy(b);
+  delete m;
+}
+
+int multi_create(const crispy_ns_model *model, const int *devices, int n_devices, int n_streams,
+                           crispy_ns_multi **out) {
+  if (!out || n_devices < 1 || n_streams < 1) return fail(CRISPY_NS_EINVAL, "multi_create: bad argument");
+  const int ndev = device_count();
+  if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
+  crispy_ns_multi *m = new crispy_ns_multi();
+  m->n_streams = n_streams;
+  // contiguous blocks whose sizes differ by at most one (crispy_b200/shard.py stream_block); devices beyond the
+  // stream count stay empty and are skipped
+  const int base = n_streams / n_devices, extra = n_streams % n_devices;
+  for (int i = 0; i < n_devices; i++) {
+    const int cnt = base + (i < extra ? 1 : 0);
+    if (cnt == 0) continue;
+    const int dev = devices ? devices[i] : i;
+    if (dev < 0 || dev >= ndev) {
+      multi_destroy(m);
+      return fail(CRISPY_NS_ENODEV, "multi_create: device index out of range");
+    }
+    crispy_ns_batch *b = nullptr;
+    const int rc = batch_create(model, dev, cnt, &b);
+    if (rc != CRISPY_NS_OK) {
+      multi_destroy(m);
+      return rc;
+    }
+    m->device.push_back(dev);
+    m->first.push_back(i * base + (i < extra ? i : extra));
+    m->count.push_back(cnt);
+    m->batch.push_back(b);
+  }
+  *out = m;
+  return CRISPY_NS_OK;
+}
+int multi_n_devices(const crispy_ns_multi *m) { return m ? (int)m->batch.size() : 0; }
+int multi_stream_range(const crispy_ns_multi *m, int i, int *device, int *first_stream, int *n_streams) {
+  if (!m || i < 0 || i >= (int)m->batch.size()) return fail(CRISPY_NS_EINVAL, "multi_stream_range: bad argument");
+  if (device) *device = m->device[i];
+  if (first_stream) *first_stream = m->first[i];
+  if (n_streams) *n_streams = m->count[i];
+  return CRISPY_NS_OK;
+}
+int multi_reset(crispy_ns_multi *m) {
+  if (!m) return fail(CRISPY_NS_EINVAL, "multi_reset: null handle");
+  for (crispy_ns_batch *b : m->batch) {
+    const int rc = batch_reset(b);
+    if (rc != CRISPY_NS_OK) return rc;
+  }
+  return CRISPY_NS_OK;
+}
+int multi_process_streams_host(crispy_ns_multi *m, const void *h_in, void *h_out, float *h_vad,
+                                         const float *h_app, int n_frames, int64_t in_stride, int64_t out_stride,
+                                         int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume) {
+  if (!m || !h_in || !h_out || n_frames < 0) return fail(CRISPY_NS_EINVAL, "multi_process_streams_host: bad argument");
+  const size_t nd = m->batch.size();
+  const size_t ie = in_elem(flags), oe = out_elem(flags);
+  std::vector<int> rc(nd, CRISPY_NS_OK);
+  std::vector<std::string> err(nd);
+  auto work = [&](size_t i) {  // one host thread per device: its copies and launches never wait for another device
+    const int64_t s0 = m->first[i];
+    rc[i] = guard("multi_process_streams_host", [&]() -> int {
+      return process_streams_host(m->batch[i], (const char *)h_in + (size_t)(s0 * in_stride) * ie,
+                                            (char *)h_out + (size_t)(s0 * out_stride) * oe,
+                                            h_vad ? h_vad + s0 * vad_stride : nullptr,
+                                            h_app ? h_app + s0 * app_stride : nullptr, n_frames, in_stride, out_stride,
+                                            vad_stride, app_stride, flags, volume);
+    });
+    if (rc[i] != CRISPY_NS_OK) {
+      try {
+        err[i] = g_err;  // thread-local: carry the message back to the caller's thread
+      } catch (...) {
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t i = 1; i < nd; i++) th.emplace_back(work, i);
+  work(0);
+  for (auto &t : th) t.join();
+  for (size_t i = 0; i < nd; i++)
+    if (rc[i] != CRISPY_NS_OK) return fail(rc[i], "device " + std::to_string(m->device[i]) + ": " + err[i]);
+  return CRISPY_NS_OK;
+}
+
+// ---- f3 end to end: WAV files in, dual-mono WAV files out ---------------------------------------------
+int denoise_wav_files(const crispy_ns_model *model, int device, const char *const *paths_in,
+                                const char *const *paths_out, int n_files, uint32_t flags, float volume,
+                                float *mean_vad) {
+  if (!paths_in || !paths_out || n_files < 1) return fail(CRISPY_NS_EINVAL, "denoise_wav_files: bad argument");
+  if (flags & ~(uint32_t)CRISPY_NS_DROP_FIRST_FRAME) return fail(CRISPY_NS_EINVAL, "denoise_wav_files: only CRISPY_NS_DROP_FIRST_FRAME is accepted");
+  std::vector<int64_t> len((size_t)n_files, 0);
+  std::vector<int> chans((size_t)n_files, 0);
+  int64_t max_len = 0;
+  for (int i = 0; i < n_files; i++) {
+    if (!paths_in[i] || !paths_out[i]) return fail(CRISPY_NS_EINVAL, "denoise_wav_files: null path");
+    int sr = 0;
+    const int rc = wav_read_pcm16(paths_in[i], nullptr, 0, &len[(size_t)i], &chans[(size_t)i], &sr);
+    if (rc != CRISPY_NS_OK) return rc;
+    if (sr != 48000) return fail(CRISPY_NS_EINVAL, std::string("denoise_wav_files: ") + paths_in[i] + " is not 48 kHz (recording.rs:14)");
+    if (len[(size_t)i] > max_len) max_len = len[(size_t)i];
+  }
+  const int64_t n_frames = (max_len + ns::kFrame - 1) / ns::kFrame;
+  if (n_frames >= (1ll << 31) / ns::kFrame) return fail(CRISPY_NS_EINVAL, "denoise_wav_files: recording too long for one call");
+  const bool drop = (flags & CRISPY_NS_DROP_FIRST_FRAME) != 0;
+  const int64_t row = n_frames * ns::kFrame;
+  struct Pinned {  // pinned staging: mono PCM16 in, stereo PCM16 out, VAD
+    void *p = nullptr;
+    ~Pinned() {
+      if (p) cudaFreeHost(p);
+    }
+  } hin, hout, hvad;
+  crispy_ns_batch *b = nullptr;
+  int rc = batch_create(model, device, n_files, &b);
+  if (rc != CRISPY_NS_OK) return rc;
+  struct BatchGuard {
+    crispy_ns_batch *b;
+    ~BatchGuard() { batch_destroy(b); }
+  } bg{b};
+  if (n_frames == 0 || (drop && n_frames < 2)) {  // nothing to denoise: empty outputs
+    for (int i = 0; i < n_files; i++) {
+      rc = wav_write_pcm16(paths_out[i], nullptr, 0, 2, 48000);
+      if (rc != CRISPY_NS_OK) return rc;
+      if (mean_vad) mean_vad[i] = 0.f;
+    }
+    return CRISPY_NS_OK;
+  }
+  NS_CUDA(cudaHostAlloc(&hin.p, (size_t)n_files * row * sizeof(int16_t), cudaHostAllocDefault));
+  NS_CUDA(cudaHostAlloc(&hout.p, (size_t)n_files * row * 2 * sizeof(int16_t), cudaHostAllocDefault));
+  NS_CUDA(cudaHostAlloc(&hvad.p, (size_t)n_files * n_frames * sizeof(float), cudaHostAllocDefault));
+  int16_t *in16 = (int16_t *)hin.p, *out16 = (int16_t *)hout.p;
+  float *vad = (float *)hvad.p;
+  {
+    std::vector<int16_t> tmp;
+    for (int i = 0; i < n_files; i++) {
+      const int ch = chans[(size_t)i];
+      const int64_t n = len[(size_t)i];
+      tmp.resize((size_t)(n * ch));
+      int64_t nf = 0;
+      rc = wav_read_pcm16(paths_in[i], tmp.data(), n * ch, &nf, nullptr, nullptr);
+      if (rc != CRISPY_NS_OK) return rc;
+      int16_t *dst = in16 + (size_t)i * row;
+      for (int64_t k = 0; k < n; k++) dst[k] = tmp[(size_t)(k * ch)];  // channel 0 (commands/transcription.rs:310-312)
+      memset(dst + n, 0, (size_t)(row - n) * sizeof(int16_t));
+    }
+  }
+  rc = process_streams_host(b, in16, out16, vad, nullptr, (int)n_frames, row, row, n_frames, 0,
+                                      CRISPY_NS_IN_I16 | CRISPY_NS_UNIT_SCALE | CRISPY_NS_MIX_STEREO_I16 | flags, volume);
+  if (rc != CRISPY_NS_OK) return rc;
+  for (int i = 0; i < n_files; i++) {
+    int64_t n_out = len[(size_t)i] - (drop ? ns::kFrame : 0);
+    if (n_out < 0) n_out = 0;
+    rc = wav_write_pcm16(paths_out[i], out16 + (size_t)i * row * 2, n_out, 2, 48000);
+    if (rc != CRISPY_NS_OK) return rc;
+    if (mean_vad) {
+      const int64_t fr = (len[(size_t)i] + ns::kFrame - 1) / ns::kFrame;
+      double acc = 0.0;
+      for (int64_t t = 0; t < fr; t++) acc += vad[(size_t)i * n_frames + t];
+      mean_vad[i] = fr > 0 ? (float)(acc / (double)fr) : 0.f;
+    }
+  }
+  return CRISPY_NS_OK;
+}
+
+// ---- measurement aid: FP32 burst -------------------------------------------------------------------------
+}  // namespace impl
+template <bool FUSED>
+__global__ void __launch_bounds__(256) ns_fp32_burst_kernel(float *out, int iters, float y0) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (FUSED)
+        a[i] = fmaf(a[(i + 1) & 7], y0, a[i]);
+      else
+        a[i] = __fadd_rn(a[i], __fmul_rn(a[(i + 1) & 7], y0));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+namespace impl {
+int measure_fp32(int device, double *ffma_tflops, double *unfused_tmacs) {
+  const int ndev = device_count();
+  if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
+  NS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  NS_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  float *d = nullptr;
+  NS_CUDA(cudaMalloc((void **)&d, (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best[2] = {1e30, 1e30};
+  cudaError_t e = cudaSuccess;
+  for (int mode = 0; mode < 2 && e == cudaSuccess; mode++) {
+    for (int rep = 0; rep < 4 && e == cudaSuccess; rep++) {
+      cudaEventRecord(a, 0);
+      if (mode == 0)
+        ns_fp32_burst_kernel<true><<<blocks, threads>>>(d, rep == 0 ? 64 : iters, 1e-6f);
+      else
+        ns_fp32_burst_kernel<false><<<blocks, threads>>>(d, rep == 0 ? 64 : iters, 1e-6f);
+      cudaEventRecord(b, 0);
+      e = cudaEventSynchronize(b);
+      float ms = 0.f;
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+      if (rep > 0 && ms < best[mode]) best[mode] = ms;
+    }
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(CRISPY_NS_ECUDA, std::string("measure_fp32: ") + cudaGetErrorString(e));
+  const double macs = (double)blocks * threads * 8.0 * iters;
+  if (ffma_tflops) *ffma_tflops = 2.0 * macs / (best[0] * 1e-3) / 1e12;
+  if (unfused_tmacs) *unfused_tmacs = macs / (best[1] * 1e-3) / 1e12;
+  return CRISPY_NS_OK;
+}
+
+}  // namespace impl
+
+#include "crispy_ns_abi.inc"
 
 #ifdef NS_PHASE_CLOCKS
 extern "C" int crispy_ns_debug_pitch_phase_cycles(unsigned long long *out16, int reset) {

@@ -15,6 +15,7 @@ in the hand-written sm_100a kernels.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import deque
 from typing import Optional, Tuple
 
@@ -388,6 +389,89 @@ class BatchDenoiser:
             pass
 
 
+class MultiDenoiser:
+    """n independent DenoiseStates over several GPUs of one box, driven from this one process
+    (crispy_ns_multi_*: contiguous blocks of streams per device, one host thread per device, no exchange)."""
+
+    def __init__(self, n_streams: int, devices=None, model: Optional[Model] = None):
+        self.n_streams = int(n_streams)
+        devs = list(range(device_count())) if devices is None else [int(d) for d in devices]
+        arr = (C.c_int * len(devs))(*devs)
+        self._model = model
+        self._h = C.c_void_p()
+        check(_lib.lib().crispy_ns_multi_create(model._h if model else None, arr, len(devs), n_streams, C.byref(self._h)))
+
+    @property
+    def ranges(self):
+        """[(device, first_stream, n_streams), ...] -- the partition (== shard.stream_block)."""
+        L = _lib.lib()
+        out = []
+        for i in range(L.crispy_ns_multi_n_devices(self._h)):
+            d, f, n = C.c_int(), C.c_int(), C.c_int()
+            check(L.crispy_ns_multi_stream_range(self._h, i, C.byref(d), C.byref(f), C.byref(n)))
+            out.append((d.value, f.value, n.value))
+        return out
+
+    def reset(self) -> None:
+        check(_lib.lib().crispy_ns_multi_reset(self._h))
+
+    def process_streams_host(self, x, *, unit_scale: bool = True, volume: float = 1.0, drop_first_frame: bool = False,
+                             out=None, vad=None, out_i16: bool = False, app=None, mix_stereo_i16: bool = False,
+                             first_call: bool = True):
+        """As BatchDenoiser.process_streams_host over all n_streams rows; returns when every device is done."""
+        import torch
+        xt = torch.as_tensor(x)
+        if xt.is_cuda or xt.dim() != 2 or xt.stride(1) != 1 or xt.shape[0] != self.n_streams:
+            raise CrispyNsError("process_streams_host needs a host [n_streams, n_samples] tensor")
+        n_frames = xt.shape[1] // FRAME_SIZE
+        flags = 0
+        if xt.dtype == torch.int16:
+            flags |= IN_I16
+        elif xt.dtype != torch.float32:
+            raise CrispyNsError("process_streams_host input must be float32 or int16")
+        if unit_scale:
+            flags |= UNIT_SCALE
+        if drop_first_frame:
+            flags |= DROP_FIRST_FRAME
+        n_out_frames = n_frames - (1 if (drop_first_frame and first_call) else 0)
+        if mix_stereo_i16:
+            flags |= MIX_STEREO_I16
+            if out is None:
+                out = torch.zeros((self.n_streams, n_out_frames * FRAME_SIZE, 2), dtype=torch.int16)
+            out_stride = out.stride(0) // 2
+        else:
+            if out_i16:
+                flags |= OUT_I16
+            if out is None:
+                out = torch.zeros((self.n_streams, n_out_frames * FRAME_SIZE), dtype=torch.int16 if out_i16 else torch.float32)
+            out_stride = out.stride(0)
+        if vad is None:
+            vad = torch.zeros((self.n_streams, n_frames), dtype=torch.float32)
+        app_ptr, app_stride = None, 0
+        if app is not None:
+            app = torch.as_tensor(app)
+            app_ptr, app_stride = app.data_ptr(), app.stride(0)
+        check(_lib.lib().crispy_ns_multi_process_streams_host(self._h, xt.data_ptr(), out.data_ptr(), vad.data_ptr(), app_ptr,
+                                                              n_frames, xt.stride(0), out_stride, vad.stride(0), app_stride,
+                                                              flags, volume))
+        return out, vad
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().crispy_ns_multi_destroy(self._h)
+        except Exception:
+            pass
+
+
+def measure_fp32(device: int = 0) -> dict:
+    """Register-resident FP32 bursts on every SM: {'ffma_tflops': fused multiply-add throughput,
+    'unfused_tmacs': rounded product + rounded add pairs per second / 1e12}."""
+    a, b = C.c_double(), C.c_double()
+    check(_lib.lib().crispy_ns_measure_fp32(device, C.byref(a), C.byref(b)))
+    return {"ffma_tflops": a.value, "unfused_tmacs": b.value}
+
+
 class RnnNoiseProcessor:
     """audio.rs:202-315: per-sample operator around DenoiseState (frame assembly, x32768, /32768,
     clamp, volume, first frame dropped, linear resampling on either side)."""
@@ -460,6 +544,22 @@ def wav_write_pcm16(path: str, interleaved: np.ndarray, channels: int = 2, sampl
     if a.size % channels:
         raise CrispyNsError("Left and right channel length mismatch")  # recording.rs:103
     check(_lib.lib().crispy_ns_wav_write_pcm16(path.encode(), a.ctypes.data, a.size // channels, channels, sample_rate))
+
+
+def denoise_wav_files(paths_in, paths_out, *, model: Optional[Model] = None, device: int = 0, volume: float = 1.0,
+                      drop_first_frame: bool = False):
+    """Finished recordings in, denoised dual-mono recordings out (crispy_ns_denoise_wav_files): 48 kHz PCM16 files
+    as the recorder writes them (recording.rs:83-99); channel 0 is denoised (commands/transcription.rs:310-312) and
+    written to both channels through the recorder's quantiser (recording.rs:108-110).  Returns each file's mean VAD."""
+    n = len(paths_in)
+    if n != len(paths_out) or n == 0:
+        raise CrispyNsError("denoise_wav_files needs as many output as input paths (at least one)")
+    pin = (C.c_char_p * n)(*[os.fsencode(p) for p in paths_in])
+    pout = (C.c_char_p * n)(*[os.fsencode(p) for p in paths_out])
+    vad = (C.c_float * n)()
+    check(_lib.lib().crispy_ns_denoise_wav_files(model._h if model else None, device, pin, pout, n,
+                                                 DROP_FIRST_FRAME if drop_first_frame else 0, volume, vad))
+    return [float(v) for v in vad]
 
 
 def wav_read_pcm16(path: str):

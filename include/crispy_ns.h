@@ -51,7 +51,9 @@ enum {
 /* flags for the batched calls */
 enum {
   CRISPY_NS_IN_I16 = 1u << 0,     /* input samples are int16 (16-bit scale) instead of f32 */
-  CRISPY_NS_OUT_I16 = 1u << 1,    /* output samples are int16 (round-to-nearest, saturating) */
+  CRISPY_NS_OUT_I16 = 1u << 1,    /* output samples are int16 in 16-bit scale (round-to-nearest, saturating);
+                                     UNIT_SCALE's clamp and `volume` do not apply to this format: a call
+                                     with OUT_I16 and volume != 1 is rejected with CRISPY_NS_EINVAL */
   CRISPY_NS_UNIT_SCALE = 1u << 2, /* f32 I/O in [-1,1]: x32768 on load, /32768 + clamp(-1,1) + *volume
                                      on store -- RnnNoiseProcessor::push_sample, audio.rs:261-273.
                                      Without it f32 I/O is in 16-bit scale, as process_frame itself. */
@@ -64,6 +66,7 @@ enum {
 typedef struct crispy_ns_model crispy_ns_model; /* the six RNN layers (int8 weights) */
 typedef struct crispy_ns_state crispy_ns_state; /* one stream: mirrors nnnoiseless::DenoiseState */
 typedef struct crispy_ns_batch crispy_ns_batch; /* n independent streams on one GPU */
+typedef struct crispy_ns_multi crispy_ns_multi; /* n independent streams over several GPUs of one box */
 
 int crispy_ns_frame_size(void); /* 480 */
 const char *crispy_ns_last_error(void);
@@ -132,6 +135,24 @@ int crispy_ns_batch_profile(crispy_ns_batch *b, int enable);
 int crispy_ns_batch_profile_read(crispy_ns_batch *b, double *ms_total, int64_t *n_launches, int n_kernels);
 void crispy_ns_batch_destroy(crispy_ns_batch *b);
 
+
+/* ---- (e) several GPUs from one process.  The reference keeps one DenoiseState per stream
+ * and no shared mutable state (audio.rs:203), so the n_streams of a multi handle are cut into contiguous blocks
+ * of ceil/floor(n_streams / n_devices) streams, device i taking block i (crispy_ns_multi_stream_range); a
+ * meeting's mic and app audio share one stream index, so its dual-mono mix never crosses devices.  Each device
+ * has its own crispy_ns_batch, weights copy, host thread and CUDA streams; nothing is exchanged between
+ * devices (no collective).  The host call has crispy_ns_process_streams_host's geometry over all n_streams
+ * rows; it returns when every device has finished. ---- */
+int crispy_ns_multi_create(const crispy_ns_model *model, const int *devices, int n_devices, int n_streams,
+                           crispy_ns_multi **out);
+int crispy_ns_multi_n_devices(const crispy_ns_multi *m);
+int crispy_ns_multi_stream_range(const crispy_ns_multi *m, int i, int *device, int *first_stream, int *n_streams);
+int crispy_ns_multi_reset(crispy_ns_multi *m);
+int crispy_ns_multi_process_streams_host(crispy_ns_multi *m, const void *h_in, void *h_out, float *h_vad,
+                                         const float *h_app, int n_frames, int64_t in_stride, int64_t out_stride,
+                                         int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume);
+void crispy_ns_multi_destroy(crispy_ns_multi *m);
+
 /* pinned host memory for the host-pointer path */
 int crispy_ns_host_alloc(void **ptr, size_t bytes);
 void crispy_ns_host_free(void *ptr);
@@ -181,6 +202,24 @@ int crispy_ns_wav_write_pcm16(const char *path, const int16_t *interleaved, int6
                               int channels, int sample_rate);
 int crispy_ns_wav_read_pcm16(const char *path, int16_t *interleaved, int64_t cap_samples,
                              int64_t *n_frames, int *channels, int *sample_rate);
+
+
+/* ---- f3 end to end: batch-denoise finished recordings.  Every paths_in[i] is a 48 kHz PCM16 RIFF/WAVE file as
+ * the recorder writes it (recording.rs:83-99: stereo, both channels carry the same mix); channel 0 is taken
+ * (as the transcription reader does, commands/transcription.rs:310-312), denoised with PCM16 on the host link,
+ * and written to paths_out[i] as dual-mono stereo PCM16 through the recorder's quantiser
+ * (clamp(x,-1,1)*32767 truncated, recording.rs:108-110).  Files may differ in length: all n_files run as one
+ * batch, shorter ones are padded with silence internally and written back at their own length.  flags:
+ * CRISPY_NS_DROP_FIRST_FRAME mirrors audio.rs:275-278 (the output is then 480 samples shorter).  mean_vad
+ * (n_files floats, may be NULL) receives each file's mean voice-activity probability (f4). ---- */
+int crispy_ns_denoise_wav_files(const crispy_ns_model *model, int device, const char *const *paths_in,
+                                const char *const *paths_out, int n_files, uint32_t flags, float volume,
+                                float *mean_vad);
+
+/* ---- measurement aid: a register-resident burst on every SM for ~10 ms.  *ffma_tflops receives the FP32
+ * throughput of fused multiply-adds (2 flop each), *unfused_tmacs the rate of rounded-product + rounded-add
+ * pairs (10^12 MAC/s), the form the pitch kernel's exactness contract requires.  Either may be NULL. ---- */
+int crispy_ns_measure_fp32(int device, double *ffma_tflops, double *unfused_tmacs);
 
 #ifdef __cplusplus
 }

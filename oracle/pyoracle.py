@@ -109,6 +109,12 @@ def _declare(L: C.CDLL) -> C.CDLL:
     L.rno_process_streams.restype = C.c_int
     L.rno_process_streams.argtypes = [vp, f32p, f32p, f32p, C.c_int, C.c_int, C.c_long, C.c_long,
                                       C.c_uint, C.c_float, C.c_int]
+    i32p = C.POINTER(C.c_int32)
+    L.rno_process_streams_trace.restype = C.c_int
+    L.rno_process_streams_trace.argtypes = [vp, f32p, f32p, f32p, C.c_int, C.c_int, C.c_long, C.c_long,
+                                            C.c_uint, C.c_float, C.c_int, i32p, f32p, i32p]
+    L.rno_set_sum_policy.argtypes = [C.c_int]
+    L.rno_get_sum_policy.restype = C.c_int
     L.rno_linres_init.argtypes = [C.POINTER(LinRes), C.c_float, C.c_float]
     L.rno_linres_process.restype = C.c_size_t
     L.rno_linres_process.argtypes = [C.POINTER(LinRes), f32p, C.c_size_t, f32p, C.c_size_t]
@@ -213,6 +219,30 @@ def process_streams(model: Model, x: np.ndarray, unit_scale: bool = False, volum
     lib(native).rno_process_streams(model.h, _fp(x), _fp(out), _fp(vad), n_streams, n_frames, n, n,
                               1 if unit_scale else 0, volume, n_threads)
     return out, vad
+
+
+def process_streams_trace(model: Model, x: np.ndarray, unit_scale: bool = False, volume: float = 1.0,
+                          n_threads: int = 1, native: bool = False, sum_policy: int = 0):
+    """As process_streams, additionally returning every frame's discrete decisions:
+    (out, vad, pitch_index [n_streams, n_frames] int32, pitch_gain f32, silence int32).
+    sum_policy: summation order of the pitch path's inner products (rnnoise_oracle.c rno_set_sum_policy)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n_streams, n = x.shape
+    n_frames = n // FRAME_SIZE
+    out = np.zeros_like(x)
+    vad = np.zeros((n_streams, n_frames), dtype=np.float32)
+    pi = np.zeros((n_streams, n_frames), dtype=np.int32)
+    pg = np.zeros((n_streams, n_frames), dtype=np.float32)
+    sil = np.zeros((n_streams, n_frames), dtype=np.int32)
+    L = lib(native)
+    L.rno_set_sum_policy(int(sum_policy))
+    try:
+        L.rno_process_streams_trace(model.h, _fp(x), _fp(out), _fp(vad), n_streams, n_frames, n, n,
+                                    1 if unit_scale else 0, volume, n_threads,
+                                    pi.ctypes.data_as(C.POINTER(C.c_int32)), _fp(pg), sil.ctypes.data_as(C.POINTER(C.c_int32)))
+    finally:
+        L.rno_set_sum_policy(0)
+    return out, vad, pi, pg, sil
 
 
 def debug_trace(model: Model, x: np.ndarray):

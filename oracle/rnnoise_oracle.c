@@ -9,6 +9,33 @@
  * src/{denoise,pitch,celt_lpc,rnn}.c) are given per function.
  *
  * Build: gcc -O2 -ffp-contract=off (Rust never contracts a*b+c into an FMA, so neither do we).
+ *
+ * Provenance of the algorithm: this file restates, routine by routine and under the upstream identifiers,
+ * xiph/rnnoise (src/denoise.c, pitch.c, celt_lpc.c, rnn.c) -- the code nnnoiseless 0.5.2 ports to Rust.  It was
+ * written from the published algorithm, not copied from /root/reference (which does not contain it).  The upstream
+ * sources carry this notice, reproduced here because the routines below follow them closely:
+ *
+ *   Copyright (c) 2017-2018 Mozilla; Copyright (c) 2007-2009 Xiph.Org Foundation; Copyright (c) 2003-2008
+ *   Jean-Marc Valin; Copyright (c) 2007-2008 CSIRO; Copyright (c) 2008-2011 Octasic Inc.
+ *   Redistribution and use in source and binary forms, with or without modification, are permitted provided
+ *   that the following conditions are met:
+ *   - Redistributions of source code must retain the above copyright notice, this list of conditions and the
+ *     following disclaimer.
+ *   - Redistributions in binary form must reproduce the above copyright notice, this list of conditions and
+ *     the following disclaimer in the documentation and/or other materials provided with the distribution.
+ *   THIS SOFTWARE IS PROVIDED BY THE COPYRIGHT HOLDERS AND CONTRIBUTORS "AS IS" AND ANY EXPRESS OR IMPLIED
+ *   WARRANTIES, INCLUDING, BUT NOT LIMITED TO, THE IMPLIED WARRANTIES OF MERCHANTABILITY AND FITNESS FOR A
+ *   PARTICULAR PURPOSE ARE DISCLAIMED.  IN NO EVENT SHALL THE FOUNDATION OR CONTRIBUTORS BE LIABLE FOR ANY
+ *   DIRECT, INDIRECT, INCIDENTAL, SPECIAL, EXEMPLARY, OR CONSEQUENTIAL DAMAGES (INCLUDING, BUT NOT LIMITED TO,
+ *   PROCUREMENT OF SUBSTITUTE GOODS OR SERVICES; LOSS OF USE, DATA, OR PROFITS; OR BUSINESS INTERRUPTION)
+ *   HOWEVER CAUSED AND ON ANY THEORY OF LIABILITY, WHETHER IN CONTRACT, STRICT LIABILITY, OR TORT (INCLUDING
+ *   NEGLIGENCE OR OTHERWISE) ARISING IN ANY WAY OUT OF THE USE OF THIS SOFTWARE, EVEN IF ADVISED OF THE
+ *   POSSIBILITY OF SUCH DAMAGE.
+ *
+ * OPEN POINTS against nnnoiseless itself (SURVEY.md Appendix A [verify]): (1) whether the
+ * biquad widens to f64 as the C does (implemented: yes); (2) the GRU activations of the shipped model (carried by
+ * the model blob, so the real weights decide); (3) the model blob format (CRNSMDL1 is this repo's own container);
+ * (4) the summation order of the inner products (rno_set_sum_policy below).
  */
 #include "rnnoise_oracle.h"
 
@@ -54,10 +81,10 @@ static const int eband5ms[NB_BANDS] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  10, 1
 static float g_half_window[FRAME_SIZE];
 static float g_dct_table[NB_BANDS * NB_BANDS];
 static float g_tansig[201];
-static cpx g_tw480[480];  /* exp(-2 pi i k / 480) */
 static cpx g_tw960[481];  /* exp(-2 pi i k / 960), k <= 480 */
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
 
+static void init_fft_plan(void);
 static void init_tables(void) {
   int i, j;
   /* upstream: denoise.c check_init(): half_window, dct_table */
@@ -73,14 +100,11 @@ static void init_tables(void) {
     }
   /* upstream: tansig_table.h -- tanh(0.04 i) printed with 6 decimals */
   for (i = 0; i <= 200; i++) g_tansig[i] = (float)(floor(tanh(.04 * i) * 1e6 + .5) / 1e6);
-  for (i = 0; i < 480; i++) {
-    g_tw480[i].r = (float)cos(2 * M_PI * i / 480);
-    g_tw480[i].i = (float)-sin(2 * M_PI * i / 480);
-  }
   for (i = 0; i <= 480; i++) {
     g_tw960[i].r = (float)cos(2 * M_PI * i / 960);
     g_tw960[i].i = (float)-sin(2 * M_PI * i / 960);
   }
+  init_fft_plan();
 }
 static void ensure_tables(void) { pthread_once(&g_once, init_tables); }
 
@@ -98,7 +122,7 @@ const float *rno_tansig_table(void) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* FFT: 480-point complex mixed radix (2,3,5) in f32 + real packing.  Stands in for            */
+/* FFT: 480-point complex mixed radix (Stockham, 5.3.4.4.2) in f32 + real packing.  Stands in for */
 /* easyfft/realfft/rustfft (Cargo.lock:1200-1210, :3927-3933, :4199-4210), which compute the   */
 /* same DFT in f32; only rounding differs.                                                    */
 /* ------------------------------------------------------------------------------------------ */
@@ -109,29 +133,112 @@ static cpx cmul(cpx a, cpx b) {
   return c;
 }
 
-/* out[k] = sum_n in[n*stride] W_N^{nk}; recursive decimation in time over the smallest factor */
-static void fft_rec(cpx *out, const cpx *in, int n, int stride) {
-  int p, m, k, q, r;
-  cpx tmp[5];
-  if (n == 1) {
-    out[0] = in[0];
-    return;
-  }
-  p = (n % 2 == 0) ? 2 : (n % 3 == 0) ? 3 : 5;
-  m = n / p;
-  for (q = 0; q < p; q++) fft_rec(out + q * m, in + q * stride, m, stride * p);
-  for (k = 0; k < m; k++) {
-    for (q = 0; q < p; q++) tmp[q] = cmul(out[q * m + k], g_tw480[(q * k * (480 / n)) % 480]);
-    for (r = 0; r < p; r++) {
-      cpx acc = tmp[0];
-      for (q = 1; q < p; q++) {
-        cpx w = g_tw480[((q * r) % p) * (480 / p)];
-        cpx t = cmul(tmp[q], w);
-        acc.r += t.r;
-        acc.i += t.i;
+/* out = DFT480(in): Stockham autosort (decimation in time), radices 5, 3, 4, 4, 2 with the twiddles of every stage
+ * tabulated in stage order (g_stage_tw, init_tables).  Stage with radix p after Ns = product of the earlier radices:
+ * butterfly j = b*Ns + k reads in[j + r*N/p] * W_{Ns p}^{r k} and writes out[b*Ns*p + k + r*Ns]. */
+#define FFT_STAGES 5
+static const int g_radix[FFT_STAGES] = {5, 3, 4, 4, 2};
+static cpx g_stage_tw[480 * 2]; /* sum over stages of Ns * (p - 1) <= 480 + ... */
+static int g_stage_off[FFT_STAGES];
+
+static void init_fft_plan(void) {
+  int s, k, r, ns = 1, off = 0;
+  for (s = 0; s < FFT_STAGES; s++) {
+    const int p = g_radix[s];
+    g_stage_off[s] = off;
+    for (k = 0; k < ns; k++)
+      for (r = 1; r < p; r++) {
+        const double a = -2.0 * M_PI * (double)(r * k) / (double)(ns * p);
+        g_stage_tw[off].r = (float)cos(a);
+        g_stage_tw[off].i = (float)sin(a);
+        off++;
       }
-      out[r * m + k] = acc;
-    }
+    ns *= p;
+  }
+}
+
+static inline cpx cadd(cpx a, cpx b) {
+  cpx c;
+  c.r = a.r + b.r;
+  c.i = a.i + b.i;
+  return c;
+}
+static inline cpx csub(cpx a, cpx b) {
+  cpx c;
+  c.r = a.r - b.r;
+  c.i = a.i - b.i;
+  return c;
+}
+static inline cpx mul_mi(cpx a) { /* a * (-i) */
+  cpx c;
+  c.r = a.i;
+  c.i = -a.r;
+  return c;
+}
+
+static void butterfly(cpx *v, int p) {
+  if (p == 2) {
+    cpx a = v[0];
+    v[0] = cadd(a, v[1]);
+    v[1] = csub(a, v[1]);
+  } else if (p == 4) {
+    cpx t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]), t2 = cadd(v[1], v[3]), t3 = mul_mi(csub(v[1], v[3]));
+    v[0] = cadd(t0, t2);
+    v[2] = csub(t0, t2);
+    v[1] = cadd(t1, t3);
+    v[3] = csub(t1, t3);
+  } else if (p == 3) {
+    const float s3 = 0.86602540378443864676f;
+    cpx a = cadd(v[1], v[2]), d = csub(v[1], v[2]), m, n;
+    m.r = v[0].r - .5f * a.r;
+    m.i = v[0].i - .5f * a.i;
+    n.r = s3 * d.i; /* -i * s3 * d = (s3 d.i, -s3 d.r) */
+    n.i = -s3 * d.r;
+    v[0] = cadd(v[0], a);
+    v[1] = cadd(m, n);
+    v[2] = csub(m, n);
+  } else { /* 5 */
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    cpx a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+    cpx m1, m2, n1, n2, x0 = v[0];
+    m1.r = x0.r + c1 * a1.r + c2 * a2.r;
+    m1.i = x0.i + c1 * a1.i + c2 * a2.i;
+    m2.r = x0.r + c2 * a1.r + c1 * a2.r;
+    m2.i = x0.i + c2 * a1.i + c1 * a2.i;
+    n1.r = s1 * b1.i + s2 * b2.i; /* -i * (s1 b1 + s2 b2) */
+    n1.i = -(s1 * b1.r + s2 * b2.r);
+    n2.r = s2 * b1.i - s1 * b2.i; /* -i * (s2 b1 - s1 b2) */
+    n2.i = -(s2 * b1.r - s1 * b2.r);
+    v[0].r = x0.r + a1.r + a2.r;
+    v[0].i = x0.i + a1.i + a2.i;
+    v[1] = cadd(m1, n1);
+    v[4] = csub(m1, n1);
+    v[2] = cadd(m2, n2);
+    v[3] = csub(m2, n2);
+  }
+}
+
+static void fft480(cpx *out, const cpx *in) {
+  cpx buf[2][480];
+  const cpx *src = in;
+  int s, ns = 1;
+  for (s = 0; s < FFT_STAGES; s++) {
+    const int p = g_radix[s], m = 480 / p;
+    cpx *dst = (s == FFT_STAGES - 1) ? out : buf[s & 1];
+    const cpx *tw = g_stage_tw + g_stage_off[s];
+    int b, k, r;
+    for (b = 0; b < m / ns; b++)
+      for (k = 0; k < ns; k++) {
+        cpx v[5];
+        const int j = b * ns + k;
+        v[0] = src[j];
+        for (r = 1; r < p; r++) v[r] = (ns == 1) ? src[j + r * m] : cmul(src[j + r * m], tw[k * (p - 1) + r - 1]);
+        butterfly(v, p);
+        for (r = 0; r < p; r++) dst[b * ns * p + k + r * ns] = v[r];
+      }
+    src = dst;
+    ns *= p;
   }
 }
 
@@ -145,7 +252,7 @@ static void forward_transform(cpx *out, const float *in) {
     z[k].r = in[2 * k];
     z[k].i = in[2 * k + 1];
   }
-  fft_rec(Z, z, 480, 1);
+  fft480(Z, z);
   for (k = 0; k <= 480; k++) {
     cpx a = Z[k % 480], b = Z[(480 - k) % 480], e, o, t;
     b.i = -b.i; /* conj(Z[N-k]) */
@@ -181,7 +288,7 @@ static void inverse_transform(float *out, const cpx *in) {
     Z[k].r = e.r - t.i;
     Z[k].i = -(e.i + t.r);
   }
-  fft_rec(z, Z, 480, 1);
+  fft480(z, Z);
   for (k = 0; k < 480; k++) {
     out[2 * k] = z[k].r;
     out[2 * k + 1] = -z[k].i;
@@ -628,9 +735,53 @@ static void dct(float *out, const float *in) {
 /* ------------------------------------------------------------------------------------------ */
 /* a9: pitch_downsample (pitch.c) + _celt_autocorr/_celt_lpc (celt_lpc.c) + celt_fir5          */
 /* ------------------------------------------------------------------------------------------ */
+/* Summation-order policy of the pitch path's inner products (process-wide; set it before any thread runs).
+ *   0  sequential, ascending index: xiph/rnnoise's C (celt_inner_prod, xcorr_kernel per lag).  THE DEFAULT, and the
+ *      order the CUDA kernels reproduce bit for bit.
+ *   1  four interleaved partial sums (s[j & 3] += x[j] y[j], then ((s0 + s1) + s2) + s3, tail sequential) in
+ *      celt_inner_prod / dual_inner_prod only -- the shape of a hand-unrolled Rust inner product such as a port may
+ *      use; the cross-correlation kernels stay sequential per lag.
+ *   2  policy 1, and the same four-way split inside celt_pitch_xcorr (hence _celt_autocorr) as well.
+ * Nothing here claims to be what nnnoiseless does: the crate source is absent.  The switch exists to MEASURE how
+ * often a different but equally legitimate float32 order flips a discrete pitch decision (tests/test_oracle.py,
+ * profiles/r2_parity.json): the decisions are bit-exact against the oracle's order only. */
+static int g_sum_policy = 0;
+void rno_set_sum_policy(int policy) { g_sum_policy = policy < 0 ? 0 : (policy > 2 ? 2 : policy); }
+int rno_get_sum_policy(void) { return g_sum_policy; }
+
+static float dot4(const float *x, const float *y, int N) {
+  float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s;
+  int i, n4 = N & ~3;
+  for (i = 0; i < n4; i += 4) {
+    s0 += x[i] * y[i];
+    s1 += x[i + 1] * y[i + 1];
+    s2 += x[i + 2] * y[i + 2];
+    s3 += x[i + 3] * y[i + 3];
+  }
+  s = ((s0 + s1) + s2) + s3;
+  for (; i < N; i++) s += x[i] * y[i];
+  return s;
+}
+
 static void celt_pitch_xcorr(const float *x, const float *y, float *xcorr, int len, int max_pitch) {
   int i, j;
-  for (i = 0; i < max_pitch; i++) {
+  if (g_sum_policy >= 2) {
+    for (i = 0; i < max_pitch; i++) xcorr[i] = dot4(x, y + i, len);
+    return;
+  }
+  /* eight lags at a time, each lag's sum still accumulated in ascending j with a rounded product and a rounded
+   * add: bit-identical to the lag-by-lag loop, but the compiler can keep the eight sums in one vector register */
+  for (i = 0; i + 8 <= max_pitch; i += 8) {
+    float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const float *yy = y + i;
+    for (j = 0; j < len; j++) {
+      const float xj = x[j];
+      int l;
+      for (l = 0; l < 8; l++) sum[l] += xj * yy[j + l];
+    }
+    for (j = 0; j < 8; j++) xcorr[i + j] = sum[j];
+  }
+  for (; i < max_pitch; i++) {
     float sum = 0;
     for (j = 0; j < len; j++) sum += x[j] * y[i + j];
     xcorr[i] = sum;
@@ -639,6 +790,7 @@ static void celt_pitch_xcorr(const float *x, const float *y, float *xcorr, int l
 static float celt_inner_prod(const float *x, const float *y, int N) {
   int i;
   float xy = 0;
+  if (g_sum_policy >= 1) return dot4(x, y, N);
   for (i = 0; i < N; i++) xy += x[i] * y[i];
   return xy;
 }
@@ -646,6 +798,11 @@ static void dual_inner_prod(const float *x, const float *y01, const float *y02, 
                             float *xy2) {
   int i;
   float a = 0, b = 0;
+  if (g_sum_policy >= 1) {
+    *xy1 = dot4(x, y01, N);
+    *xy2 = dot4(x, y02, N);
+    return;
+  }
   for (i = 0; i < N; i++) {
     a += x[i] * y01[i];
     b += x[i] * y02[i];
@@ -1028,38 +1185,49 @@ static float activate(int act, float x) {
   return relu(x);
 }
 
-static void compute_dense(const dense_layer *layer, float *output, const float *input) {
+/* sum[i] = bias[i] + sum_j W[j*stride + i] * in[j], j ascending: upstream walks j innermost per neuron i; here j is
+ * the outer loop and every neuron keeps its own running sum, so each sum sees the same additions in the same order
+ * (bit-identical) while the weight rows are read contiguously and the i loop vectorises. */
+static void accum_rows(float *sum, const int8_t *w, int stride, const float *in, int M, int N) {
   int i, j;
-  int M = layer->nb_inputs, N = layer->nb_neurons, stride = N;
-  for (i = 0; i < N; i++) {
-    float sum = layer->bias[i];
-    for (j = 0; j < M; j++) sum += layer->weights[j * stride + i] * input[j];
-    output[i] = activate(layer->activation, WEIGHTS_SCALE * sum);
+  for (j = 0; j < M; j++) {
+    const int8_t *row = w + (size_t)j * stride;
+    const float v = in[j];
+    for (i = 0; i < N; i++) sum[i] += row[i] * v;
   }
+}
+
+static void compute_dense(const dense_layer *layer, float *output, const float *input) {
+  int i;
+  int M = layer->nb_inputs, N = layer->nb_neurons;
+  float sum[96];
+  for (i = 0; i < N; i++) sum[i] = layer->bias[i];
+  accum_rows(sum, layer->weights, N, input, M, N);
+  for (i = 0; i < N; i++) output[i] = activate(layer->activation, WEIGHTS_SCALE * sum[i]);
 }
 
 static void compute_gru(const gru_layer *gru, float *state, const float *input) {
   int i, j;
   float z[96], r[96], h[96];
   int M = gru->nb_inputs, N = gru->nb_neurons, stride = 3 * N;
-  for (i = 0; i < N; i++) {
-    float sum = gru->bias[i];
-    for (j = 0; j < M; j++) sum += gru->input_weights[j * stride + i] * input[j];
-    for (j = 0; j < N; j++) sum += gru->recurrent_weights[j * stride + i] * state[j];
-    z[i] = rno_sigmoid_approx(WEIGHTS_SCALE * sum);
+  float sum[2 * 96];
+  /* update and reset gates share their inputs: columns 0..2N of the weight rows in one sweep */
+  for (i = 0; i < 2 * N; i++) sum[i] = gru->bias[i];
+  accum_rows(sum, gru->input_weights, stride, input, M, 2 * N);
+  accum_rows(sum, gru->recurrent_weights, stride, state, N, 2 * N);
+  for (i = 0; i < N; i++) z[i] = rno_sigmoid_approx(WEIGHTS_SCALE * sum[i]);
+  for (i = 0; i < N; i++) r[i] = rno_sigmoid_approx(WEIGHTS_SCALE * sum[N + i]);
+  /* candidate: upstream multiplies weight * state[j] * r[j] left to right, i.e. (w * state[j]) * r[j] */
+  for (i = 0; i < N; i++) sum[i] = gru->bias[2 * N + i];
+  accum_rows(sum, gru->input_weights + 2 * N, stride, input, M, N);
+  for (j = 0; j < N; j++) {
+    const int8_t *row = gru->recurrent_weights + 2 * N + (size_t)j * stride;
+    const float sj = state[j], rj = r[j];
+    for (i = 0; i < N; i++) sum[i] += row[i] * sj * rj;
   }
   for (i = 0; i < N; i++) {
-    float sum = gru->bias[N + i];
-    for (j = 0; j < M; j++) sum += gru->input_weights[N + j * stride + i] * input[j];
-    for (j = 0; j < N; j++) sum += gru->recurrent_weights[N + j * stride + i] * state[j];
-    r[i] = rno_sigmoid_approx(WEIGHTS_SCALE * sum);
-  }
-  for (i = 0; i < N; i++) {
-    float sum = gru->bias[2 * N + i];
-    for (j = 0; j < M; j++) sum += gru->input_weights[2 * N + j * stride + i] * input[j];
-    for (j = 0; j < N; j++) sum += gru->recurrent_weights[2 * N + j * stride + i] * state[j] * r[j];
-    sum = activate(gru->activation, WEIGHTS_SCALE * sum);
-    h[i] = z[i] * state[i] + (1 - z[i]) * sum;
+    const float c = activate(gru->activation, WEIGHTS_SCALE * sum[i]);
+    h[i] = z[i] * state[i] + (1 - z[i]) * c;
   }
   for (i = 0; i < N; i++) state[i] = h[i];
 }
@@ -1179,6 +1347,8 @@ typedef struct {
   long in_stride, out_stride;
   unsigned flags;
   float volume;
+  int32_t *tr_pitch, *tr_silence; /* optional per-frame decision traces, [n_streams][n_frames] */
+  float *tr_pgain;
 } job;
 
 static void *worker(void *arg) {
@@ -1204,6 +1374,9 @@ static void *worker(void *arg) {
         v = rno_process_frame(st, dst + (size_t)t * FRAME_SIZE, src + (size_t)t * FRAME_SIZE);
       }
       if (j->vad) j->vad[(size_t)s * j->n_frames + t] = v;
+      if (j->tr_pitch) j->tr_pitch[(size_t)s * j->n_frames + t] = st->dbg.pitch_index;
+      if (j->tr_pgain) j->tr_pgain[(size_t)s * j->n_frames + t] = st->dbg.pitch_gain;
+      if (j->tr_silence) j->tr_silence[(size_t)s * j->n_frames + t] = st->dbg.silence;
     }
     rno_destroy(st);
   }
@@ -1213,6 +1386,13 @@ static void *worker(void *arg) {
 int rno_process_streams(const rno_model *m, const float *in, float *out, float *vad, int n_streams,
                         int n_frames, long in_stride, long out_stride, unsigned flags, float volume,
                         int n_threads) {
+  return rno_process_streams_trace(m, in, out, vad, n_streams, n_frames, in_stride, out_stride, flags, volume,
+                                   n_threads, NULL, NULL, NULL);
+}
+
+int rno_process_streams_trace(const rno_model *m, const float *in, float *out, float *vad, int n_streams,
+                              int n_frames, long in_stride, long out_stride, unsigned flags, float volume,
+                              int n_threads, int32_t *pitch_index, float *pitch_gain, int32_t *silence) {
   int t;
   pthread_t *th;
   job *jobs;
@@ -1235,6 +1415,9 @@ int rno_process_streams(const rno_model *m, const float *in, float *out, float *
     j.out_stride = out_stride;
     j.flags = flags;
     j.volume = volume;
+    j.tr_pitch = pitch_index;
+    j.tr_pgain = pitch_gain;
+    j.tr_silence = silence;
     jobs[t] = j;
     pthread_create(&th[t], NULL, worker, &jobs[t]);
   }

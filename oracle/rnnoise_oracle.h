@@ -74,6 +74,18 @@ int rno_process_streams(const rno_model *m, const float *in, float *out, float *
                         int n_frames, long in_stride, long out_stride, unsigned flags, float volume,
                         int n_threads);
 
+/* the same, additionally recording every frame's discrete decisions ([n_streams][n_frames] each, any may be
+ * NULL): pitch_index and pitch gain out of remove_doubling, and the silence gate */
+int rno_process_streams_trace(const rno_model *m, const float *in, float *out, float *vad, int n_streams,
+                              int n_frames, long in_stride, long out_stride, unsigned flags, float volume,
+                              int n_threads, int32_t *pitch_index, float *pitch_gain, int32_t *silence);
+
+/* Summation order of the pitch path's inner products: 0 = sequential (xiph C order; default; what the CUDA kernels
+ * reproduce), 1 = four interleaved partial sums in celt_inner_prod / dual_inner_prod, 2 = also inside the
+ * cross-correlation kernels.  Process-wide; set before any thread runs.  A measurement aid: see rnnoise_oracle.c. */
+void rno_set_sum_policy(int policy);
+int rno_get_sum_policy(void);
+
 /* ---- neighbouring rows ---- */
 /* a4: LinearResampler (audio.rs:73-134). Streaming; returns number of samples emitted. */
 typedef struct rno_linres {

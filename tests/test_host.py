@@ -29,6 +29,32 @@ def test_library_exports_every_declared_symbol():
     assert L.crispy_ns_frame_size() == 480
 
 
+def test_c_consumer_compiles_against_the_header_and_links(tmp_path):
+    """tests/c_abi/abi_smoke.c is compiled as strict C99 against include/crispy_ns.h and linked to libcrispy_ns.so:
+    a prototype drift between the header and the library (or the Python ctypes table) cannot hide.  Without a GPU
+    the program checks the no-fallback contract and exits 0; the GPU suite runs it in full."""
+    import subprocess
+    exe = str(tmp_path / "abi_smoke")
+    lib_dir = os.path.join(ROOT, "crispy_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi", "abi_smoke.c"), "-L" + lib_dir, "-lcrispy_ns", "-lm",
+                           "-Wl,-rpath," + lib_dir, "-o", exe])
+    if cb.device_count() == 0:
+        r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+        assert r.returncode == 0 and "ENODEV contract ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_abi_wrappers_are_generated_from_the_header():
+    """crispy_ns_abi.inc (the extern "C" try/catch forwarding layer) is what scripts/gen_abi.py makes of the header."""
+    import subprocess
+    import sys
+    inc = os.path.join(ROOT, "crispy_b200", "csrc", "crispy_ns_abi.inc")
+    before = open(inc).read()
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "gen_abi.py")], stdout=subprocess.DEVNULL)
+    assert open(inc).read() == before, "include/crispy_ns.h changed: run scripts/gen_abi.py and rebuild"
+    assert before.count("guard(") + before.count("catch (...)") >= len(_lib.SYMBOLS)
+
+
 def test_library_contains_sm_100a_code():
     import shutil
     import subprocess

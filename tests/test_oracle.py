@@ -309,3 +309,30 @@ def test_pitch_path_numpy_cross_check_on_adversarial_inputs(oracle_model):
             assert pi == taps[t]["pitch_index"] and np.float32(g) == np.float32(taps[t]["pitch_gain"]), (name, t)
             seen.add(pi)
     assert min(seen) == 60 and max(seen) > 700
+
+
+def test_summation_policy_switch_and_decision_trace(oracle_model):
+    """rno_set_sum_policy: 0 (default) is the sequential xiph order; 1 and 2 regroup the inner products into four
+    partial sums.  The trace variant returns the same samples as the plain call plus the per-frame decisions; another
+    summation order keeps the output within tolerance on ordinary frames and flips only a small share of the pitch
+    decisions (the rate at full size is in profiles/r2_parity.json)."""
+    from tests.util import make_signal, snr_db
+    x = make_signal(4, 400)
+    o0, v0 = po.process_streams(oracle_model, x, n_threads=4)
+    o, v, pi, pg, sil = po.process_streams_trace(oracle_model, x, n_threads=4)
+    assert np.array_equal(o, o0) and np.array_equal(v, v0)
+    _, taps = po.debug_trace(oracle_model, x[1])
+    assert pi[1].tolist() == [t["pitch_index"] for t in taps] and sil[1].tolist() == [t["silence"] for t in taps]
+    assert np.array_equal(pg[1], np.array([t["pitch_gain"] for t in taps], np.float32))
+    assert po.lib().rno_get_sum_policy() == 0
+    for pol in (1, 2):
+        o2, v2, pi2, pg2, sil2 = po.process_streams_trace(oracle_model, x, n_threads=4, sum_policy=pol)
+        assert po.lib().rno_get_sum_policy() == 0  # restored
+        assert not np.array_equal(pg2, pg)  # another rounding order gives other correlations (last bits of the gain) ...
+        assert (pi2 != pi).mean() < 0.01 and np.array_equal(sil2, sil)  # ... but nearly every decision stands; the
+        # samples only change where a decision flips (the inner products feed nothing but decisions)
+        assert snr_db(o, o2) > 50
+    # the native (-O3 -march=native) build used by the CPU baseline computes the same bits as the checker build
+    po.build_native()
+    on, vn = po.process_streams(oracle_model, x, n_threads=4, native=True)
+    assert np.array_equal(on, o0) and np.array_equal(vn, v0)
