@@ -18,6 +18,7 @@
 #include "../../include/crispy_ns.h"
 #include "ns_host.h"
 #include "ns_pipe.cuh"
+#include "ns_pitch7.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // kernels (bodies in ns_pipe.cuh)
@@ -26,10 +27,20 @@
 #define NS_PITCH_RUN 8
 #endif
 constexpr int kPitchRun = NS_PITCH_RUN;  // frames of one stream per pitch CTA
+// K1 generations: the first (ns_pipe.cuh pitch_body: all 147 x 240 coarse sums in the oracle's order) is the product;
+// -DNS_PITCH_V7 builds the second (ns_pitch7.cuh: coarse search filtered on the tensor pipe), which is bit-exact too but
+// measured slower on B200 (profiles/r2_pitch.md): legacy HMMA latency and shared-memory wavefronts eat what the
+// 147 x 240 sums cost
+#ifndef NS_PITCH_V7
 #ifdef NS_PITCH_THREADS
 constexpr int kPitchThreads = NS_PITCH_THREADS;
 #else
 constexpr int kPitchThreads = (37 * kPitchRun + 31) / 32 * 32 + 32;
+#endif
+using PitchShared = ns::PitchSmem<kPitchRun>;
+#else
+constexpr int kPitchThreads = ns::kP7Threads;
+using PitchShared = ns::PitchSmem7<kPitchRun>;
 #endif
 //  // 37 lag-quads per frame in the coarse search + one helper warp
 constexpr int kScanWarps = 4;
@@ -40,7 +51,11 @@ __global__ void __launch_bounds__(ns::kHpThreads) ns_highpass_kernel(const __gri
 }
 __global__ void __launch_bounds__(kPitchThreads) ns_pitch_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ns::pitch_body<kPitchRun, kPitchThreads>(p, *reinterpret_cast<ns::PitchSmem<kPitchRun> *>(smem_raw));
+#ifndef NS_PITCH_V7
+  ns::pitch_body<kPitchRun, kPitchThreads>(p, *reinterpret_cast<PitchShared *>(smem_raw));
+#else
+  ns::pitch_body7<kPitchRun, kPitchThreads>(p, *reinterpret_cast<PitchShared *>(smem_raw));
+#endif
 }
 __global__ void __launch_bounds__(32 * kScanWarps) ns_pitchscan_kernel(const __grid_constant__ ns::Params p) {
   ns::pitchscan_body(p, kScanWarps);
@@ -269,7 +284,7 @@ static cudaError_t configure_kernels(int dev) {
   if (configured[dev]) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(ns_highpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::HpSmem));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ns_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(ns::PitchSmem<kPitchRun>));
+                                       (int)sizeof(PitchShared));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(ns_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::SpecSmem));
   if (e == cudaSuccess)
@@ -320,7 +335,7 @@ static void launch_kernel(crispy_ns_batch *b, int k, ns::Params &p, int n, int n
       ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem), sk>>>(p);
       break;
     case 1:
-      ns_pitch_kernel<<<n * ((nf + kPitchRun - 1) / kPitchRun), kPitchThreads, sizeof(ns::PitchSmem<kPitchRun>), sk>>>(p);
+      ns_pitch_kernel<<<n * ((nf + kPitchRun - 1) / kPitchRun), kPitchThreads, sizeof(PitchShared), sk>>>(p);
       break;
     case 2:
       ns_pitchscan_kernel<<<(n + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 0, sk>>>(p);
@@ -1619,10 +1634,10 @@ int measure_fp32(int device, double *ffma_tflops, double *unfused_tmacs) {
 #include "crispy_ns_abi.inc"
 
 #ifdef NS_PHASE_CLOCKS
-extern "C" int crispy_ns_debug_pitch_phase_cycles(unsigned long long *out16, int reset) {
-  if (out16 && cudaMemcpyFromSymbol(out16, ns::g_pitch_phase_cycles, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+extern "C" int crispy_ns_debug_pitch_phase_cycles(unsigned long long *out24, int reset) {
+  if (out24 && cudaMemcpyFromSymbol(out24, ns::g_pitch_phase_cycles, 24 * sizeof(unsigned long long)) != cudaSuccess) return -1;
   if (reset) {
-    unsigned long long z[16] = {0};
+    unsigned long long z[24] = {0};
     if (cudaMemcpyToSymbol(ns::g_pitch_phase_cycles, z, sizeof(z)) != cudaSuccess) return -1;
   }
   return 0;

@@ -250,9 +250,9 @@ struct PitchSmem {
   char pad[NS_PITCH_PAD_BYTES];  // measurement builds: forces fewer resident CTAs per SM
 #endif
   int best0[R], best1[R], T0[R], nk[R];
-  // work lists of remove_doubling's inner products per window-alignment bucket: frame | lag << 5 | k << 14
-  int n_tri[4], n_sgl[4];
-  uint32_t tri[4][R * 16], sgl[4][R * 16];  // <= 15 triples and <= 14 singles per frame
+  // work lists of remove_doubling's inner products: frame | lag << 5 | k << 14
+  int n_tri[4], n_sgl[4];                   // [0] used: one list each (the alignment buckets are gone)
+  uint32_t tri[4][R * 16], sgl[4][R * 16];  // <= 15 triples and <= 14 singles per frame, stored flat from tri[0] / sgl[0]
   alignas(16) float dots[R][64];   // 0: T0-1, 1: T0+1; for k >= 2 at 2+4(k-2): T1-1, T1, T1+1, T1b
 };
 
@@ -390,6 +390,45 @@ NS_DEV void dot3_fixed_shift(const float *x, const float *ya, float &s0, float &
   s1 = a1;
   s2 = a2;
 }
+// the same three inner products with the shift S = yoff & 3 known only at run time: the six window elements a quad of
+// taps needs come out of a two-level select network (shift by one, then by two) over the twelve loaded floats.
+// Fourteen selects per four taps buy full lanes: with compile-time shifts a warp only holds the items of one
+// alignment bucket (a quarter of a CTA's ~56 triples per warp-pass, seven active lanes on average).
+template <int N>
+NS_DEV void dot3_shifted(const float *x, const float *yrow, int yoff, float &s0, float &s1, float &s2) {
+  const float *ya = yrow + (yoff & ~3);
+  const bool p1 = (yoff & 1) != 0, p2 = (yoff & 2) != 0;
+  f4 w0 = ld4(ya), w1 = ld4(ya + 4), w2 = ld4(ya + 8), xv = ld4(x);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  NS_UNROLL(NS_DOT_UNROLL)
+  for (int j = 0; j < N; j += 4) {
+    const f4 w2_n = ld4(ya + j + 12), xv_n = ld4(x + j + 4);
+    // b[i] = w[i + (S & 1)], i < 8;  y[i] = b[i + (S & 2)], i < 6
+    const float b0 = p1 ? w0.y : w0.x, b1 = p1 ? w0.z : w0.y, b2 = p1 ? w0.w : w0.z, b3 = p1 ? w1.x : w0.w,
+                b4 = p1 ? w1.y : w1.x, b5 = p1 ? w1.z : w1.y, b6 = p1 ? w1.w : w1.z, b7 = p1 ? w2.x : w1.w;
+    const float y0 = p2 ? b2 : b0, y1 = p2 ? b3 : b1, y2 = p2 ? b4 : b2, y3 = p2 ? b5 : b3, y4 = p2 ? b6 : b4,
+                y5 = p2 ? b7 : b5;
+    a0 += xv.x * y0;
+    a1 += xv.x * y1;
+    a2 += xv.x * y2;
+    a0 += xv.y * y1;
+    a1 += xv.y * y2;
+    a2 += xv.y * y3;
+    a0 += xv.z * y2;
+    a1 += xv.z * y3;
+    a2 += xv.z * y4;
+    a0 += xv.w * y3;
+    a1 += xv.w * y4;
+    a2 += xv.w * y5;
+    w0 = w1;
+    w1 = w2;
+    w2 = w2_n;
+    xv = xv_n;
+  }
+  s0 = a0;
+  s1 = a1;
+  s2 = a2;
+}
 NS_DEV float dot480_shifted(const float *row, int yoff) { return dot_shifted<480>(row + 384, row, yoff); }
 
 // find_best_pitch's running energy: out[i] = Syy before lag i, Syy <- max(1, Syy + y[i+len]^2 - y[i]^2), for
@@ -434,7 +473,7 @@ NS_DEV float sumsq_from(float acc, const float *y) {
 
 #if defined(NS_PHASE_CLOCKS) && defined(__CUDACC__) && !defined(NS_HOST_EMU)
 // measurement build only: cycles between K1's barriers, summed over CTAs (thread 0 of each CTA)
-__device__ unsigned long long g_pitch_phase_cycles[16];
+__device__ unsigned long long g_pitch_phase_cycles[24];
 #define NS_PHASE_BEGIN() long long ns_pc_ = clock64()
 #define NS_PHASE_MARK(i)                                                       \
   do {                                                                         \
@@ -723,10 +762,103 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
   chain_run(25, false);
   Simt::cta_sync();
   NS_PHASE_MARK(7);
-  // P6: find_best_pitch on the coarse correlation (one lane per frame)
-  if (tid < nfr) {
+  // P6: find_best_pitch on the coarse correlation.  The serial scan (147 dependent insertions per frame) only has to
+  // be replayed over the lags that can end up among its two winners: warp f scores its frame's 147 lags in parallel
+  // (num / Syy, five lags per lane), takes the second best score, and runs the oracle's insertion, in lag order and
+  // with the oracle's cross-multiplied comparisons, over the lags within 2e-4 of it -- two or three on speech and on
+  // noise alike.  A lag further below loses every comparison against the two winners by a margin a thousand times
+  // the float32 rounding of either side, and a lag that cannot win does not change which lags do, so the result is
+  // the full scan's, bit for bit.  Where that margin means nothing -- the threshold lag's num = (xc 1e-12)^2 near the
+  // float32 underflow range (a signal decaying through the denormals), or more than 32 lags within the margin --
+  // lane 0 runs the full scan.
+  if (NW > R && (tid >> 5) < R) {
+    const int f = tid >> 5, lane = tid & 31;
+    if (f < nfr) {
+      float sc[5], xcv[5], syv[5];
+      float t0v = -1.f, t1v = -1.f, t1num = 0.f, t0num = 0.f;  // two best scores and their nums
+      int nvalid = 0;
+#pragma unroll
+      for (int u = 0; u < 5; u++) {
+        const int i = lane + 32 * u;
+        const bool in = i < 147;
+        xcv[u] = in ? sm.xc[f][i] : 0.f;
+        syv[u] = in ? sm.sb6[f][i] : 1.f;
+        const float x16 = xcv[u] * 1e-12f, num = x16 * x16;
+        const bool valid = in && xcv[u] > 0.f;
+        sc[u] = valid ? num / syv[u] : -1.f;
+        nvalid += valid ? 1 : 0;
+        const bool a = sc[u] > t0v, bb = sc[u] > t1v;
+        t1v = a ? t0v : (bb ? sc[u] : t1v);
+        t1num = a ? t0num : (bb ? num : t1num);
+        t0v = a ? sc[u] : t0v;
+        t0num = a ? num : t0num;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const float o0 = Simt::shfl_xor(t0v, d), o1 = Simt::shfl_xor(t1v, d), n0 = Simt::shfl_xor(t0num, d), n1 = Simt::shfl_xor(t1num, d);
+        nvalid += Simt::shfl_xor(nvalid, d);
+        // merge (o0, o1) into (t0v, t1v)
+        bool a = o0 > t0v, bb = o0 > t1v;
+        t1v = a ? t0v : (bb ? o0 : t1v);
+        t1num = a ? t0num : (bb ? n0 : t1num);
+        t0v = a ? o0 : t0v;
+        t0num = a ? n0 : t0num;
+        bb = o1 > t1v;
+        t1num = bb ? n1 : t1num;
+        t1v = bb ? o1 : t1v;
+      }
+      const float thr = nvalid >= 2 ? t1v * (1.f - 2e-4f) : -1.f;
+      unsigned mine = 0u;
+      int cnt = 0;
+#pragma unroll
+      for (int u = 0; u < 5; u++)
+        if (sc[u] >= 0.f && sc[u] >= thr) mine |= 1u << u, cnt++;
+      int total = cnt;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) total += Simt::shfl_xor(total, d);
+      Best2 b;
+      best_init(b);
+      if (total > 32 || (nvalid >= 2 && !(t1num >= 1e-30f))) {  // the margin argument does not apply: full scan
+        if (lane == 0) {
+          for (int i = 0; i < 147; i++) {
+            const float xc = sm.xc[f][i];
+            const float x16 = xc * 1e-12f;
+            best_insert_sel(b, xc > 0.f, x16 * x16, sm.sb6[f][i], i);
+          }
+        }
+      } else {
+        for (int s = 0; s < total; s++) {  // the candidates in ascending lag order: every lane replays the insertion
+          int mn = 0x7FFFFFFF;
+#pragma unroll
+          for (int u = 0; u < 5; u++)
+            if (mine & (1u << u)) {
+              const int i = lane + 32 * u;
+              mn = i < mn ? i : mn;
+            }
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            const int o = Simt::shfl_xor(mn, d);
+            mn = o < mn ? o : mn;
+          }
+          const int src = mn & 31, u = mn >> 5;
+          float xc = 0.f, sy = 1.f;
+#pragma unroll
+          for (int uu = 0; uu < 5; uu++)
+            if (uu == u) xc = xcv[uu], sy = syv[uu];
+          xc = Simt::shfl(xc, src);
+          sy = Simt::shfl(sy, src);
+          const float x16 = xc * 1e-12f;
+          best_insert_sel(b, xc > 0.f, x16 * x16, sy, mn);
+          if (lane == src) mine &= ~(1u << u);
+        }
+      }
+      if (lane == 0) {
+        sm.best0[f] = b.p0;
+        sm.best1[f] = b.p1;
+      }
+    }
+  } else if (NW <= R && tid < nfr) {  // narrow CTAs (measurement variants, the host emulation's small build): one lane per frame
     const int f = tid;
-    const float *y4 = sm.xr + f * kLpStride;
     Best2 b;
     best_init(b);
     for (int i0 = 0; i0 < 147; i0 += 4) {  // Syy per lag comes from the helper warp
@@ -818,60 +950,44 @@ NS_DEV void pitch_body(const Params &p, PitchSmem<R> &sm) {
     if (k == kMaxK || rd_T1(k + 1, T0) < 30) sm.nk[f] = k;
     const int Tc = (k == 1) ? T0 : rd_T1(k, T0);
     {
-      const int bkt = (384 - Tc - 1) & 3;
-      const int idx = Simt::atomic_add_shared(&sm.n_tri[bkt], 1);
-      sm.tri[bkt][idx] = (uint32_t)(f | (Tc << 5) | (k << 14));
+      const int idx = Simt::atomic_add_shared(&sm.n_tri[0], 1);
+      (&sm.tri[0][0])[idx] = (uint32_t)(f | (Tc << 5) | (k << 14));
     }
     if (k > 1) {
       const int T1b = rd_T1b(k, T0, Tc);
-      const int bkt = (384 - T1b) & 3;
-      const int idx = Simt::atomic_add_shared(&sm.n_sgl[bkt], 1);
-      sm.sgl[bkt][idx] = (uint32_t)(f | (T1b << 5) | (k << 14));
+      const int idx = Simt::atomic_add_shared(&sm.n_sgl[0], 1);
+      (&sm.sgl[0][0])[idx] = (uint32_t)(f | (T1b << 5) | (k << 14));
     }
   }
   Simt::cta_sync();
   NS_PHASE_MARK(11);
-  // P11: the inner products on the worker warps.  Jobs 0..7: triples of bucket j % 4, half j / 4; jobs 8..11:
-  // singles of bucket j - 8.  Worker warp w takes jobs w, w + nwork, ...
+  // P11: the inner products, one lane per item whatever its window alignment (dot3_shifted): full warps.  Triples
+  // first (three chains each), the singles on the warps after them.
   {
-    const int nwork = NW > 4 ? NW - 3 : NW, w = tid >> 5, lane = tid & 31;
-    if (w < nwork) {
-      for (int job = w; job < 12; job += nwork) {
-        if (job < 8) {
-          const int bkt = job & 3, n = sm.n_tri[bkt];
-          for (int it = (job >> 2) * 32 + lane; it < n; it += 64) {
-            const int e = sm.tri[bkt][it];
-            const int f = e & 31, Tc = (e >> 5) & 0x1FF, k = e >> 14;
-            const float *row = sm.xlp + f * kLpStride;
-            const float *ya = row + ((384 - Tc - 1) & ~3);
-            float sp, sc, sm1;  // lags Tc+1, Tc, Tc-1
-            switch (bkt) {
-              case 0: dot3_fixed_shift<480, 0>(row + 384, ya, sp, sc, sm1); break;
-              case 1: dot3_fixed_shift<480, 1>(row + 384, ya, sp, sc, sm1); break;
-              case 2: dot3_fixed_shift<480, 2>(row + 384, ya, sp, sc, sm1); break;
-              default: dot3_fixed_shift<480, 3>(row + 384, ya, sp, sc, sm1); break;
-            }
-            const int d = 2 + 4 * (k - 2);
-            sm.dots[f][k == 1 ? 0 : d] = sm1;
-            sm.dots[f][k == 1 ? kDotXy0 : d + 1] = sc;
-            sm.dots[f][k == 1 ? 1 : d + 2] = sp;
-          }
-        } else {
-          const int bkt = job - 8, n = sm.n_sgl[bkt];
-          for (int it = lane; it < n; it += 32) {
-            const int e = sm.sgl[bkt][it];
-            const int f = e & 31, lag = (e >> 5) & 0x1FF, k = e >> 14;
-            const float *row = sm.xlp + f * kLpStride;
-            const float *ya = row + ((384 - lag) & ~3);
-            float sum;
-            switch (bkt) {
-              case 0: sum = dot_fixed_shift<480, 0>(row + 384, ya); break;
-              case 1: sum = dot_fixed_shift<480, 1>(row + 384, ya); break;
-              case 2: sum = dot_fixed_shift<480, 2>(row + 384, ya); break;
-              default: sum = dot_fixed_shift<480, 3>(row + 384, ya); break;
-            }
-            sm.dots[f][2 + 4 * (k - 2) + 3] = sum;
-          }
+    const int w = tid >> 5, lane = tid & 31;
+    const int n_tri = sm.n_tri[0], n_sgl = sm.n_sgl[0];
+    const int tri_warps = (n_tri + 31) >> 5, sgl_warps = (n_sgl + 31) >> 5;
+    for (int job = w; job < tri_warps + sgl_warps; job += NW) {
+      if (job < tri_warps) {
+        const int it = job * 32 + lane;
+        if (it < n_tri) {
+          const int e = (&sm.tri[0][0])[it];
+          const int f = e & 31, Tc = (e >> 5) & 0x1FF, k = e >> 14;
+          const float *row = sm.xlp + f * kLpStride;
+          float sp, sc, sm1;  // lags Tc+1, Tc, Tc-1
+          dot3_shifted<480>(row + 384, row, 384 - Tc - 1, sp, sc, sm1);
+          const int d = 2 + 4 * (k - 2);
+          sm.dots[f][k == 1 ? 0 : d] = sm1;
+          sm.dots[f][k == 1 ? kDotXy0 : d + 1] = sc;
+          sm.dots[f][k == 1 ? 1 : d + 2] = sp;
+        }
+      } else {
+        const int it = (job - tri_warps) * 32 + lane;
+        if (it < n_sgl) {
+          const int e = (&sm.sgl[0][0])[it];
+          const int f = e & 31, lag = (e >> 5) & 0x1FF, k = e >> 14;
+          const float *row = sm.xlp + f * kLpStride;
+          sm.dots[f][2 + 4 * (k - 2) + 3] = dot_shifted<480>(row + 384, row, 384 - lag);
         }
       }
     }

@@ -112,7 +112,7 @@ def _declare(L: C.CDLL) -> C.CDLL:
     i32p = C.POINTER(C.c_int32)
     L.rno_process_streams_trace.restype = C.c_int
     L.rno_process_streams_trace.argtypes = [vp, f32p, f32p, f32p, C.c_int, C.c_int, C.c_long, C.c_long,
-                                            C.c_uint, C.c_float, C.c_int, i32p, f32p, i32p]
+                                            C.c_uint, C.c_float, C.c_int, i32p, f32p, i32p, f32p]
     L.rno_set_sum_policy.argtypes = [C.c_int]
     L.rno_get_sum_policy.restype = C.c_int
     L.rno_linres_init.argtypes = [C.POINTER(LinRes), C.c_float, C.c_float]
@@ -222,9 +222,9 @@ def process_streams(model: Model, x: np.ndarray, unit_scale: bool = False, volum
 
 
 def process_streams_trace(model: Model, x: np.ndarray, unit_scale: bool = False, volume: float = 1.0,
-                          n_threads: int = 1, native: bool = False, sum_policy: int = 0):
+                          n_threads: int = 1, native: bool = False, sum_policy: int = 0, margin: bool = False):
     """As process_streams, additionally returning every frame's discrete decisions:
-    (out, vad, pitch_index [n_streams, n_frames] int32, pitch_gain f32, silence int32).
+    (out, vad, pitch_index [n_streams, n_frames] int32, pitch_gain f32, silence int32[, branch margin f32]).
     sum_policy: summation order of the pitch path's inner products (rnnoise_oracle.c rno_set_sum_policy)."""
     x = np.ascontiguousarray(x, dtype=np.float32)
     n_streams, n = x.shape
@@ -234,14 +234,18 @@ def process_streams_trace(model: Model, x: np.ndarray, unit_scale: bool = False,
     pi = np.zeros((n_streams, n_frames), dtype=np.int32)
     pg = np.zeros((n_streams, n_frames), dtype=np.float32)
     sil = np.zeros((n_streams, n_frames), dtype=np.int32)
+    mg = np.zeros((n_streams, n_frames), dtype=np.float32) if margin else None
     L = lib(native)
     L.rno_set_sum_policy(int(sum_policy))
     try:
         L.rno_process_streams_trace(model.h, _fp(x), _fp(out), _fp(vad), n_streams, n_frames, n, n,
                                     1 if unit_scale else 0, volume, n_threads,
-                                    pi.ctypes.data_as(C.POINTER(C.c_int32)), _fp(pg), sil.ctypes.data_as(C.POINTER(C.c_int32)))
+                                    pi.ctypes.data_as(C.POINTER(C.c_int32)), _fp(pg), sil.ctypes.data_as(C.POINTER(C.c_int32)),
+                                    _fp(mg) if margin else None)
     finally:
         L.rno_set_sum_policy(0)
+    if margin:  # + the smallest |Exp - g| over the bands per frame: distance of the pitch filter's branch from flipping
+        return out, vad, pi, pg, sil, mg
     return out, vad, pi, pg, sil
 
 

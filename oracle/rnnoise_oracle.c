@@ -632,6 +632,8 @@ struct rno_state {
   float noise_gru_state[48];
   float denoise_gru_state[96];
   rno_debug dbg;
+  float graw[NB_BANDS]; /* test taps: the band gains as the RNN emitted them, and ... */
+  float branch_margin;  /* ... min over bands of |Exp - g| of the last frame (1e30 on silent frames) */
 };
 
 rno_state *rno_create(const rno_model *m) {
@@ -1313,6 +1315,7 @@ float rno_process_frame(rno_state *st, float *out, const float *in) {
   silence = compute_frame_features(st, X, P, Ex, Ep, Exp, features, x);
   if (!silence) {
     compute_rnn(st, g, &vad_prob, features);
+    memcpy(st->graw, g, sizeof(g));
     pitch_filter(X, P, Ex, Ep, Exp, g);
     for (i = 0; i < NB_BANDS; i++) {
       float alpha = .6f;
@@ -1326,6 +1329,16 @@ float rno_process_frame(rno_state *st, float *out, const float *in) {
     }
   }
   frame_synthesis(st, out, X);
+  /* distance of the pitch filter's `Exp > g ? 1 : ...` branch from flipping: the smallest |Exp - g| over the bands
+   * whose gain is not negligible (the band's output scales with g, so a flip under g <= 1e-3 is inaudible and far
+   * below tolerance).  RNNoise is discontinuous there: where the margin is within float32 noise, two correct
+   * implementations differ. */
+  st->branch_margin = 1e30f;
+  if (!silence)
+    for (i = 0; i < NB_BANDS; i++) {
+      float d = (float)fabs(Exp[i] - st->graw[i]);
+      if (st->graw[i] > 1e-3f && d < st->branch_margin) st->branch_margin = d;
+    }
   memcpy(st->dbg.features, features, sizeof(features));
   memcpy(st->dbg.gains, g, sizeof(g));
   memcpy(st->dbg.Ex, Ex, sizeof(Ex));
@@ -1348,7 +1361,7 @@ typedef struct {
   unsigned flags;
   float volume;
   int32_t *tr_pitch, *tr_silence; /* optional per-frame decision traces, [n_streams][n_frames] */
-  float *tr_pgain;
+  float *tr_pgain, *tr_margin;
 } job;
 
 static void *worker(void *arg) {
@@ -1377,6 +1390,7 @@ static void *worker(void *arg) {
       if (j->tr_pitch) j->tr_pitch[(size_t)s * j->n_frames + t] = st->dbg.pitch_index;
       if (j->tr_pgain) j->tr_pgain[(size_t)s * j->n_frames + t] = st->dbg.pitch_gain;
       if (j->tr_silence) j->tr_silence[(size_t)s * j->n_frames + t] = st->dbg.silence;
+      if (j->tr_margin) j->tr_margin[(size_t)s * j->n_frames + t] = st->branch_margin;
     }
     rno_destroy(st);
   }
@@ -1387,12 +1401,13 @@ int rno_process_streams(const rno_model *m, const float *in, float *out, float *
                         int n_frames, long in_stride, long out_stride, unsigned flags, float volume,
                         int n_threads) {
   return rno_process_streams_trace(m, in, out, vad, n_streams, n_frames, in_stride, out_stride, flags, volume,
-                                   n_threads, NULL, NULL, NULL);
+                                   n_threads, NULL, NULL, NULL, NULL);
 }
 
 int rno_process_streams_trace(const rno_model *m, const float *in, float *out, float *vad, int n_streams,
                               int n_frames, long in_stride, long out_stride, unsigned flags, float volume,
-                              int n_threads, int32_t *pitch_index, float *pitch_gain, int32_t *silence) {
+                              int n_threads, int32_t *pitch_index, float *pitch_gain, int32_t *silence,
+                              float *branch_margin) {
   int t;
   pthread_t *th;
   job *jobs;
@@ -1418,6 +1433,7 @@ int rno_process_streams_trace(const rno_model *m, const float *in, float *out, f
     j.tr_pitch = pitch_index;
     j.tr_pgain = pitch_gain;
     j.tr_silence = silence;
+    j.tr_margin = branch_margin;
     jobs[t] = j;
     pthread_create(&th[t], NULL, worker, &jobs[t]);
   }

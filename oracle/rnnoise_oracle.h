@@ -75,10 +75,13 @@ int rno_process_streams(const rno_model *m, const float *in, float *out, float *
                         int n_threads);
 
 /* the same, additionally recording every frame's discrete decisions ([n_streams][n_frames] each, any may be
- * NULL): pitch_index and pitch gain out of remove_doubling, and the silence gate */
+ * NULL): pitch_index and pitch gain out of remove_doubling, the silence gate, and branch_margin = the smallest
+ * |Exp[b] - g[b]| over the bands with g[b] > 1e-3, i.e. how far the pitch filter's discontinuous `Exp > g ? 1 : ...` branch is from
+ * flipping (1e30 on silent frames) */
 int rno_process_streams_trace(const rno_model *m, const float *in, float *out, float *vad, int n_streams,
                               int n_frames, long in_stride, long out_stride, unsigned flags, float volume,
-                              int n_threads, int32_t *pitch_index, float *pitch_gain, int32_t *silence);
+                              int n_threads, int32_t *pitch_index, float *pitch_gain, int32_t *silence,
+                              float *branch_margin);
 
 /* Summation order of the pitch path's inner products: 0 = sequential (xiph C order; default; what the CUDA kernels
  * reproduce), 1 = four interleaved partial sums in celt_inner_prod / dual_inner_prod, 2 = also inside the

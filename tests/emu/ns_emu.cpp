@@ -15,6 +15,7 @@
 
 #include "../../crispy_b200/csrc/ns_host.h"
 #include "../../crispy_b200/csrc/ns_pipe.cuh"
+#include "../../crispy_b200/csrc/ns_pitch7.cuh"
 
 namespace ns {
 thread_local EmuThread g_emu;
@@ -71,7 +72,13 @@ int launch(int n_ctas, int n_threads, size_t smem_bytes, const std::function<voi
 }
 
 constexpr int kPitchRun = 8;
-constexpr int kPitchThreads = 160;  // any multiple of 32 gives the same result; >= 160 takes the per-warp-lag autocorrelation path
+#ifndef NS_PITCH_V7
+constexpr int kPitchThreads = 352;  // as the device build: warp f < 8 replays frame f's coarse insertion, chain warps follow
+using PitchShared = ns::PitchSmem<kPitchRun>;
+#else
+constexpr int kPitchThreads = ns::kP7Threads;  // warp w < 8 owns frame w, three chain warps follow
+using PitchShared = ns::PitchSmem7<kPitchRun>;
+#endif
 constexpr int kScanWarps = 1;
 }  // namespace
 
@@ -144,8 +151,12 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
                     [&](void *sm) { ns::highpass_body(p, *(ns::HpSmem *)sm); });
     if (rc) return rc;
     const int runs = (nf + kPitchRun - 1) / kPitchRun;
-    rc = launch(n_streams * runs, kPitchThreads, sizeof(ns::PitchSmem<kPitchRun>), [&](void *sm) {
-      ns::pitch_body<kPitchRun, kPitchThreads>(p, *(ns::PitchSmem<kPitchRun> *)sm);
+    rc = launch(n_streams * runs, kPitchThreads, sizeof(PitchShared), [&](void *sm) {
+#ifndef NS_PITCH_V7
+      ns::pitch_body<kPitchRun, kPitchThreads>(p, *(PitchShared *)sm);
+#else
+      ns::pitch_body7<kPitchRun, kPitchThreads>(p, *(PitchShared *)sm);
+#endif
     });
     if (rc) return rc;
     rc = launch((n_streams + kScanWarps - 1) / kScanWarps, 32 * kScanWarps, 16,

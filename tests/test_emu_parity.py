@@ -119,3 +119,19 @@ def test_adversarial_inputs_keep_every_decision_bit_exact(oracle_model, model_bl
             assert r["max_abs"] <= 0.02 * 32768.0, (name, r)
         else:
             assert r["max_abs"] <= TOL_MAX_ABS and r["snr_db"] >= 60.0, (name, r)
+
+
+def test_second_generation_pitch_kernel_is_bit_exact_too(oracle_model, model_blob):
+    """ns_pitch7.cuh (-DNS_PITCH_V7: coarse search approximated on the tensor pipe, bracketed, and recomputed exactly
+    only for the lags that can win) names the same pitch index and gain as the oracle on speech, on silence after
+    speech (the exact path: the signal decays through the denormal range) and on the adversarial set."""
+    from tests.util import adversarial_signals
+    x = make_signal(2, 96)
+    x[:, 60 * 480:] = 0.0
+    adv = adversarial_signals(16)
+    for name, sig in (("speech then zeros", x), ("adversarial", np.stack(list(adv.values())))):
+        out, vad, dbg, _ = emu_process(model_blob, sig, chunk=8, v7=True)
+        ref, rvad, rpi, rpg, rsil = po.process_streams_trace(oracle_model, sig, n_threads=4)
+        assert np.array_equal(dbg[:, :, 132].astype(np.int32), rpi), name
+        assert not ((dbg[:, :, 130] != rpg) & ~(np.isnan(dbg[:, :, 130]) & np.isnan(rpg))).any(), name
+        assert np.array_equal(dbg[:, :, 133].astype(np.int32), rsil), name
