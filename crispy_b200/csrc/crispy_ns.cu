@@ -332,6 +332,8 @@ struct RunHooks {
 static void launch_kernel(crispy_ns_batch *b, int k, ns::Params &p, int n, int nf, int groups, cudaStream_t sk) {
   switch (k) {
     case 0:
+      // measurement aid only: skip the biquad once N chunks have run (the slots then still hold realistic signal)
+      if (getenv("CRISPY_NS_EXPERIMENT_SKIP_HP") && b->chunks_done >= atoll(getenv("CRISPY_NS_EXPERIMENT_SKIP_HP"))) break;
       ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem), sk>>>(p);
       break;
     case 1:
@@ -350,6 +352,7 @@ static void launch_kernel(crispy_ns_batch *b, int k, ns::Params &p, int n, int n
       ns_features_kernel<<<(groups * ns::kMmaStreams + ns::kFeatWarps - 1) / ns::kFeatWarps, 32 * ns::kFeatWarps, 0, sk>>>(p);
       break;
     case 5:
+      if (getenv("CRISPY_NS_EXPERIMENT_SKIP_RNN")) break;  // measurement aid only: what the recurrent core costs the pipeline (results are garbage)
       ns_rnn_kernel<<<groups, ns::kMmaThreads, sizeof(ns::RnnSmem), sk>>>(p);
       break;
     default: {

@@ -47,11 +47,19 @@ NS_DEV f4 ld4(const float *p) { return *reinterpret_cast<const f4 *>(p); }
 // Flags hold "tile index + 1" per ring slot: landed (loader -> recursion), done (recursion ->
 // storer), freed (storer -> loader).
 constexpr int kHpThreads = 96;
-constexpr int kHpTile = 96;        // samples per tile; 480 = 5 tiles
-constexpr int kHpPitch = 100;      // floats per row in shared memory: 4*lane banks apart for LDS.128
+// Tile length: 96 samples x 4 stages = 51 KB.  Smaller rings were measured (-DNS_HP_TILE=48: 27 KB, fits beside three
+// pitch CTAs; 24: 14 KB) and bought nothing -- the pipeline ran 47.15 / 51.3 ms per 1,536 frames against 46.9 -- while
+// the recursion warp pays ~500 cycles of hand-over per tile (isolated 617 -> 641 -> 790 us per chunk), so the long tile stays.
+#ifndef NS_HP_TILE
+#define NS_HP_TILE 96
+#endif
+constexpr int kHpTile = NS_HP_TILE;  // samples per tile; 480 = 5 tiles
+constexpr int kHpPitch = kHpTile + 4;  // floats per row in shared memory: rows 4 (mod 32) banks apart for LDS.128
 constexpr int kHpStages = 4;
 constexpr int kHpAhead = 2;        // tiles the loader keeps in flight beyond the one it is publishing
-constexpr int kHpRaw16 = 208;      // byte offset of a row's raw PCM16 samples: 4c + 16 <= 208 + 2(c + 4) for every c < 96
+// byte offset of a row's raw PCM16 samples: 16-byte aligned, 4c + 16 <= kHpRaw16 + 2(c + 4) for every c < kHpTile
+constexpr int kHpRaw16 = (2 * kHpTile - 8 + 15) / 16 * 16;
+static_assert(kFrame % kHpTile == 0 && kHpTile % 8 == 0 && kHpPitch % 32 != 0 && kHpPitch % 4 == 0, "tile geometry");
 static_assert(kHpRaw16 % 16 == 0 && kHpRaw16 + 2 * kHpTile <= kHpPitch * 4 && 2 * kHpTile - 8 <= kHpRaw16, "PCM16 staging");
 struct HpSmem {
   float tile[kHpStages][32][kHpPitch];
@@ -238,22 +246,29 @@ struct PitchSmem {
   static constexpr int kXlpFloats = (R * kLpStride > kHLen) ? R * kLpStride : kHLen;
   alignas(16) float xr[R * kLpStride];  // raw downsampled rows; after the FIR each row holds y4[432] | yy_lookup[388]
   alignas(16) float xlp[kXlpFloats];    // first the high-passed window, then the whitened rows x_lp
-  alignas(16) float xc[R][152];
   alignas(16) float ac[R][8];
   alignas(16) float lpc2[R][8];
   alignas(16) float fx[R][12];
   alignas(16) int fi[R][12];
   alignas(16) float xx[R];
-  alignas(16) float sb6[R][148];  // Syy before every coarse lag (helper warp, in the coarse search's shadow)
   alignas(16) float s10[R][12];   // fine pass: Syy before each of the (at most ten) candidate lags (chain warp B, in P7's shadow)
 #ifdef NS_PITCH_PAD_BYTES
   char pad[NS_PITCH_PAD_BYTES];  // measurement builds: forces fewer resident CTAs per SM
 #endif
   int best0[R], best1[R], T0[R], nk[R];
-  // work lists of remove_doubling's inner products: frame | lag << 5 | k << 14
   int n_tri[4], n_sgl[4];                   // [0] used: one list each (the alignment buckets are gone)
-  uint32_t tri[4][R * 16], sgl[4][R * 16];  // <= 15 triples and <= 14 singles per frame, stored flat from tri[0] / sgl[0]
-  alignas(16) float dots[R][64];   // 0: T0-1, 1: T0+1; for k >= 2 at 2+4(k-2): T1-1, T1, T1+1, T1b
+  // The coarse search's arrays (P5, P6) and remove_doubling's (P10 .. P12) are never live together: one region
+  union {
+    struct {
+      alignas(16) float xc[R][152];
+      alignas(16) float sb6[R][148];  // Syy before every coarse lag (helper warp, in the coarse search's shadow)
+    };
+    struct {
+      // work lists of remove_doubling's inner products: frame | lag << 5 | k << 14
+      uint32_t tri[4][R * 16], sgl[4][R * 16];  // <= 15 triples and <= 14 singles per frame, stored flat from tri[0] / sgl[0]
+      alignas(16) float dots[R][64];   // 0: T0-1, 1: T0+1; for k >= 2 at 2+4(k-2): T1-1, T1, T1+1, T1b
+    };
+  };
 };
 
 struct Best2 {
@@ -1125,15 +1140,25 @@ NS_DEV void pitchscan_body(const Params &p, int warps_per_cta) {
 struct SpecTw {
   cf w480[480];
   cf w960[244];
+#ifndef NS_FFT3  // four stages 4.4.5.6: the product.  -DNS_FFT3 builds three stages 8.10.6 (a quarter fewer trips through shared
+                 // memory, one barrier fewer, but only 60 / 48 / 80 busy lanes per stage): measured no faster on B200
+                 // (spectrum 224 vs 214 us, synthesis 171 vs 171 us per 32,768 frames), so it stays a variant
   cf tw3[64];  // third FFT stage (radix 5, 16 sub-transforms): w480[6 r k] for r = 1..4, k < 16, contiguous in k --
                // read straight from w480 the sixteen lanes of a half-warp stride 48 r bytes (up to 8-way conflicts)
+#else          // three stages 8.10.6: second stage (radix 10, 8 sub-transforms): w480[6 r k], r = 1..9, k < 8, contiguous in k
+  cf tw3[72];
+#endif
 };
 struct Tab {
   const SpecTw *s;
   const Tables *g;
   NS_DEV cf w480(int i) const { return s->w480[i]; }
   NS_DEV cf w960(int i) const { return s->w960[i]; }
+#ifndef NS_FFT3
   NS_DEV cf tw3(int r, int k) const { return s->tw3[(r - 1) * 16 + k]; }
+#else
+  NS_DEV cf tw3(int r, int k) const { return s->tw3[(r - 1) * 8 + k]; }
+#endif
   NS_DEV float win(int i) const { return Simt::ldg(g->win + i); }
   NS_DEV float dct(int i) const { return Simt::ldg(g->dct + i); }
   NS_DEV int bin_band(int i) const { return Simt::ldg(g->bin_band + i); }
@@ -1228,6 +1253,52 @@ struct Dft<6> {
   }
 };
 
+template <>
+struct Dft<8> {
+  static NS_DEV void run(cf *v) {
+    const float h = 0.70710678118654752440f;
+    cf e[4] = {v[0], v[2], v[4], v[6]};
+    cf o[4] = {v[1], v[3], v[5], v[7]};
+    Dft<4>::run(e);
+    Dft<4>::run(o);
+    // W8^1 = (1 - i) / sqrt 2, W8^2 = -i, W8^3 = (-1 - i) / sqrt 2
+    const cf o1 = cf{h * (o[1].x + o[1].y), h * (o[1].y - o[1].x)};
+    const cf o2 = mul_neg_i(o[2]);
+    const cf o3 = cf{h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y)};
+    v[0] = cadd(e[0], o[0]);
+    v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1);
+    v[5] = csub(e[1], o1);
+    v[2] = cadd(e[2], o2);
+    v[6] = csub(e[2], o2);
+    v[3] = cadd(e[3], o3);
+    v[7] = csub(e[3], o3);
+  }
+};
+template <>
+struct Dft<10> {
+  static NS_DEV void run(cf *v) {
+    cf e[5] = {v[0], v[2], v[4], v[6], v[8]};
+    cf o[5] = {v[1], v[3], v[5], v[7], v[9]};
+    Dft<5>::run(e);
+    Dft<5>::run(o);
+    // W10^k = exp(-2 pi i k / 10), k = 1..4
+    const cf w1 = cf{0.80901699437494742410f, -0.58778525229247312917f};
+    const cf w2 = cf{0.30901699437494742410f, -0.95105651629515357212f};
+    const cf w3 = cf{-0.30901699437494742410f, -0.95105651629515357212f};
+    const cf w4 = cf{-0.80901699437494742410f, -0.58778525229247312917f};
+    o[1] = cmul(o[1], w1);
+    o[2] = cmul(o[2], w2);
+    o[3] = cmul(o[3], w3);
+    o[4] = cmul(o[4], w4);
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      v[k] = cadd(e[k], o[k]);
+      v[k + 5] = csub(e[k], o[k]);
+    }
+  }
+};
+
 // Stockham scatter of one butterfly's outputs, ordered so that the lanes of one shared-memory transaction hit
 // different banks:
 //  * first stage (NS = 1, R = 4): a thread owns 32 contiguous bytes and writes them as two 16-byte stores; the
@@ -1245,6 +1316,23 @@ NS_DEV void fft_store(cf *buf, int j, int k, const cf (&v)[R]) {
     const f4 lo = f4{v[0].x, v[0].y, v[1].x, v[1].y}, hi = f4{v[2].x, v[2].y, v[3].x, v[3].y};
     d[sw ? 1 : 0] = sw ? hi : lo;
     d[sw ? 0 : 1] = sw ? lo : hi;
+  } else if (NS_ == 1 && R == 8) {
+    // a thread owns 64 contiguous bytes (four 16-byte chunks); a quarter-warp's lanes are 64 B apart, so chunk c of
+    // lane l sits in bank group (4 l + c) mod 8: lane l writes chunk (s + l / 2) mod 4 at step s -> eight distinct groups
+    f4 *d = reinterpret_cast<f4 *>(buf + j0);
+    const int rot = (j >> 1) & 3;
+    f4 c[4] = {f4{v[0].x, v[0].y, v[1].x, v[1].y}, f4{v[2].x, v[2].y, v[3].x, v[3].y}, f4{v[4].x, v[4].y, v[5].x, v[5].y},
+               f4{v[6].x, v[6].y, v[7].x, v[7].y}};
+    if (rot & 1) {
+      const f4 t0 = c[0];
+      c[0] = c[1], c[1] = c[2], c[2] = c[3], c[3] = t0;
+    }
+    if (rot & 2) {
+      const f4 t0 = c[0], t1 = c[1];
+      c[0] = c[2], c[1] = c[3], c[2] = t0, c[3] = t1;
+    }
+#pragma unroll
+    for (int st = 0; st < 4; st++) d[(st + rot) & 3] = c[st];  // c[st] holds chunk (st + rot) & 3
   } else if (NS_ == 4 && R == 4) {
     const int rot = (j >> 2) & 3;
     cf w[4] = {v[0], v[1], v[2], v[3]};
@@ -1268,6 +1356,15 @@ NS_DEV void fft_store(cf *buf, int j, int k, const cf (&v)[R]) {
   }
 }
 
+// the stage whose twiddles come from the compact table SpecTw::tw3
+#ifndef NS_FFT3
+template <int R, int NS_>
+constexpr bool kTw3Stage = (R == 5 && NS_ == 16);
+#else
+template <int R, int NS_>
+constexpr bool kTw3Stage = (R == 10 && NS_ == 8);
+#endif
+
 // PP ("ping-pong"): the stage stores into a buffer it does not load from, so the barrier between the loads and the
 // stores is not needed
 template <int R, int NS_, bool PP = false, class Load>
@@ -1284,7 +1381,7 @@ NS_DEV void fft_stage(const Grp &g, const Tab &T, cf *buf, Load load) {
 #pragma unroll
     for (int r = 1; r < R; r++) {
       cf x = load(j + r * M);
-      v[r] = (NS_ == 1) ? x : cmul(x, (R == 5 && NS_ == 16) ? T.tw3(r, k) : T.w480(r * k * TSTEP));
+      v[r] = (NS_ == 1) ? x : cmul(x, kTw3Stage<R, NS_> ? T.tw3(r, k) : T.w480(r * k * TSTEP));
     }
     Dft<R>::run(v);
   }
@@ -1309,7 +1406,7 @@ NS_DEV void fft_stage2(const Grp &g, const Tab &T, cf *bufA, cf *bufB, Load2 loa
     for (int r = 1; r < R; r++) {
       load2(j + r * M, va[r], vb[r]);
       if (NS_ != 1) {
-        const cf w = (R == 5 && NS_ == 16) ? T.tw3(r, k) : T.w480(r * k * TSTEP);
+        const cf w = kTw3Stage<R, NS_> ? T.tw3(r, k) : T.w480(r * k * TSTEP);
         va[r] = cmul(va[r], w);
         vb[r] = cmul(vb[r], w);
       }
@@ -1322,6 +1419,31 @@ NS_DEV void fft_stage2(const Grp &g, const Tab &T, cf *bufA, cf *bufB, Load2 loa
     fft_store<R, NS_>(bufA, j, k, va);
     fft_store<R, NS_>(bufB, j, k, vb);
   }
+  gsync(g);
+}
+
+// two independent transforms, one per half of the group (threads 0..63: A, 64..127: B): the stages with at most 64
+// butterflies per transform (radix 8: 60, radix 10: 48)
+template <int R, int NS_, bool PP = false, class LoadA, class LoadB>
+NS_DEV void fft_stage_split(const Grp &g, const Tab &T, cf *bufA, cf *bufB, LoadA loadA, LoadB loadB) {
+  constexpr int M = 480 / R;
+  constexpr int TSTEP = 480 / (NS_ * R);
+  static_assert(M <= 64, "one half of the group per transform");
+  cf v[R];
+  const int j = g.tid & 63;
+  const bool second = g.tid >= 64, act = j < M;
+  int k = 0;
+  if (act) {
+    k = j % NS_;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const cf x = second ? loadB(j + r * M) : loadA(j + r * M);
+      v[r] = (NS_ == 1 || r == 0) ? x : cmul(x, kTw3Stage<R, NS_> ? T.tw3(r, k) : T.w480(r * k * TSTEP));
+    }
+    Dft<R>::run(v);
+  }
+  if (!PP) gsync(g);
+  if (act) fft_store<R, NS_>(second ? bufB : bufA, j, k, v);
   gsync(g);
 }
 
@@ -1346,10 +1468,36 @@ NS_DEV void rfft960_windowed2(const Grp &g, const Tab &T, const float *win, cons
     a = YA[n];
     b = YB[n];
   };
+#ifndef NS_FFT3
   fft_stage2<4, 1, true>(g, T, YA, YB, load);
   fft_stage2<4, 4, true>(g, T, XA, XB, from_y);
   fft_stage2<5, 16, true>(g, T, YA, YB, from_x);
   fft_stage2<6, 80, true>(g, T, XA, XB, from_y);
+#else
+  // three stages 8 . 10 . 6: a quarter fewer trips of both spectra through shared memory and one barrier fewer; the
+  // first two stages have at most 60 butterflies per transform, so each half of the group takes one transform
+  auto loadA = [&](int n) -> cf {
+    cf a, b;
+    (void)b;
+    const int i0 = 2 * n;
+    const bool up = i0 < kFrame;
+    const cf wp = *reinterpret_cast<const cf *>(win + (up ? i0 : kWindow - 2 - i0));
+    const float w0 = up ? wp.x : wp.y, w1 = up ? wp.y : wp.x;
+    a = cf{srcA[i0] * w0, srcA[i0 + 1] * w1};
+    return a;
+  };
+  auto loadB = [&](int n) -> cf {
+    const int i0 = 2 * n;
+    const bool up = i0 < kFrame;
+    const cf wp = *reinterpret_cast<const cf *>(win + (up ? i0 : kWindow - 2 - i0));
+    const float w0 = up ? wp.x : wp.y, w1 = up ? wp.y : wp.x;
+    return cf{srcB[i0] * w0, srcB[i0 + 1] * w1};
+  };
+  (void)load;
+  fft_stage_split<8, 1, true>(g, T, XA, XB, loadA, loadB);
+  fft_stage_split<10, 8, true>(g, T, YA, YB, [&](int n) -> cf { return XA[n]; }, [&](int n) -> cf { return XB[n]; });
+  fft_stage2<6, 80, true>(g, T, XA, XB, from_y);
+#endif
   const float norm = 1.0f / kWindow;
   for (int k = g.tid; k <= 240; k += kGroupThreads) {
     const cf w = T.w960(k);
@@ -1369,22 +1517,33 @@ NS_DEV void rfft960_windowed2(const Grp &g, const Tab &T, const float *win, cons
 
 // a16: unscaled inverse of the Hermitian spectrum X[0..480]; result left in X as 480 complex
 // z[m] with x[2m] = z[m].x and x[2m+1] = -z[m].y (the conjugate of a forward FFT).
-NS_DEV void irfft960_inplace(const Grp &g, const Tab &T, cf *X, cf *Y) {  // Y: scratch of 480 cf (ping-pong partner)
+NS_DEV void irfft960_inplace(const Grp &g, const Tab &T, cf *X, cf *Y) {  // Y: scratch of 481 cf (ping-pong partner)
+#ifndef NS_FFT3
+  cf *Z = X;  // four stages end where they started
+#else
+  cf *Z = Y;  // three stages: the Hermitian fold goes to the partner so that the last stage lands in X
+#endif
   for (int k = g.tid; k <= 240; k += kGroupThreads) {
     const cf a = X[k], b = X[480 - k], w = T.w960(k);
     const float ex = a.x + b.x, ey = a.y - b.y;
     const float ox = a.x - b.x, oy = a.y + b.y;
     const float tr = fmaf(ox, w.x, oy * w.y), ti = fmaf(-ox, w.y, oy * w.x);
-    X[k] = cf{ex - ti, -(ey + tr)};
-    if (k != 0) X[480 - k] = cf{ex + ti, ey - tr};
+    Z[k] = cf{ex - ti, -(ey + tr)};
+    if (k != 0) Z[480 - k] = cf{ex + ti, ey - tr};
   }
   gsync(g);
   auto from_x = [&](int n) -> cf { return X[n]; };
   auto from_y = [&](int n) -> cf { return Y[n]; };
+#ifndef NS_FFT3
   fft_stage<4, 1, true>(g, T, Y, from_x);
   fft_stage<4, 4, true>(g, T, X, from_y);
   fft_stage<5, 16, true>(g, T, Y, from_x);
   fft_stage<6, 80, true>(g, T, X, from_y);
+#else
+  fft_stage<8, 1, true>(g, T, X, from_y);
+  fft_stage<10, 8, true>(g, T, Y, from_x);
+  fft_stage<6, 80, true>(g, T, X, from_y);
+#endif
 }
 
 // a8: 22 triangular bands over bins 0..400.  Every band edge is a multiple of four bins, so bins
@@ -1481,15 +1640,22 @@ NS_DEV void load_twiddles(const Params &p, SpecTw &dst, int tid, int nthr) {
   const uint32_t *src = reinterpret_cast<const uint32_t *>(p.tables);
   uint32_t *d = reinterpret_cast<uint32_t *>(&dst);
   for (int i = tid; i < (int)(offsetof(SpecTw, tw3) / 4); i += nthr) d[i] = src[i];
+#ifndef NS_FFT3
   for (int i = tid; i < 64; i += nthr) dst.tw3[i] = p.tables->w480[6 * ((i >> 4) + 1) * (i & 15)];
+#else
+  for (int i = tid; i < 72; i += nthr) dst.tw3[i] = p.tables->w480[6 * ((i >> 3) + 1) * (i & 7)];
+#endif
 }
 
 // spectra of frame t: X of [prev | cur], P of the window lagged by pitch_index, Ex / Ep / raw Exp
-NS_DEV void frame_spectra(const Grp &g, const Tab &T, SpecSmem &s, const float *hp_row, int t, int pitch_index) {
+// `res` selects the half of s.spec that receives X | P; the other half is the FFT's ping-pong partner.  With three FFT
+// stages the first one already writes the result half, so consecutive tasks alternate `res`: the threads that race
+// ahead into the next frame must not overwrite spectra the slower ones are still copying out.
+NS_DEV void frame_spectra(const Grp &g, const Tab &T, SpecSmem &s, const float *hp_row, int t, int pitch_index, int res = 0) {
   const float *cur = hp_row + kHist - kFrame + (long long)t * kFrame;  // [analysis_mem | frame]
-  cf *X = s.spec[0], *P = s.spec[0] + kSpecStride;
-  // K3 keeps the window where K5 keeps synthesis_mem; spec[1] is the FFT's ping-pong partner
-  rfft960_windowed2(g, T, s.synth, cur, cur - pitch_index, X, P, s.spec[1], s.spec[1] + kSpecStride);
+  cf *X = s.spec[res], *P = s.spec[res] + kSpecStride;
+  // K3 keeps the window where K5 keeps synthesis_mem
+  rfft960_windowed2(g, T, s.synth, cur, cur - pitch_index, X, P, s.spec[res ^ 1], s.spec[res ^ 1] + kSpecStride);
   {
     f4 xl, xh, pl, ph;
     const int sl = g.tid < kSlots ? g.tid : 0;
@@ -1533,6 +1699,8 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
   // a CTA's tasks are n_ctas apart: (stream, t) advance by (dq, dr) with a carry, no division per task
   const int dq = Simt::n_ctas() / p.n_frames, dr = Simt::n_ctas() - dq * p.n_frames;
   int stream = Simt::cta() / p.n_frames, t = Simt::cta() - stream * p.n_frames;
+  int task_parity = 0;
+  (void)task_parity;
   for (; stream < p.n_streams; stream += dq, t += dr) {
     if (t >= p.n_frames) {
       t -= p.n_frames;
@@ -1542,10 +1710,16 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
     const long long fidx = (long long)stream * p.chunk_cap + t;
     float *rec = p.rec + fidx * kRecFloats;
     const int pitch_index = reinterpret_cast<const int *>(rec)[kRecPitchIndex];
-    frame_spectra(g, T, s, p.hp + (long long)stream * p.hp_stride, t, pitch_index);
+#ifndef NS_FFT3
+    const int res = 0;
+#else
+    const int res = task_parity;
+    task_parity ^= 1;
+#endif
+    frame_spectra(g, T, s, p.hp + (long long)stream * p.hp_stride, t, pitch_index, res);
     {  // spectra -> workspace (K5 reads them back instead of redoing two FFTs)
       f4 *dst4 = reinterpret_cast<f4 *>(p.spec + fidx * (2 * kSpecStride));
-      const f4 *src4 = reinterpret_cast<const f4 *>(s.spec[0]);  // X[482] | P[482]: 482 float4
+      const f4 *src4 = reinterpret_cast<const f4 *>(s.spec[res]);  // X[482] | P[482]: 482 float4
       for (int k = g.tid; k < kSpecStride; k += kGroupThreads) dst4[k] = src4[k];
     }
     // band features: warp 0 alone, meeting on warp barriers, while the other warps finish the spectra store and
