@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcrispy_ns.so")
 SOURCES = ["crispy_ns.cu", "ns_host.cpp"]
-HEADERS = ["ns_common.h", "ns_simt.h", "ns_pipe.cuh", "ns_pitch7.cuh", "ns_host.h", "crispy_ns_abi.inc", os.path.join("..", "..", "include", "crispy_ns.h")]
+HEADERS = ["ns_common.h", "ns_simt.h", "ns_pipe.cuh", "ns_pitch7.cuh", "ns_rnn_tc5.cuh", "ns_host.h", "crispy_ns_abi.inc", os.path.join("..", "..", "include", "crispy_ns.h")]
 
 
 def nvcc_path() -> str:

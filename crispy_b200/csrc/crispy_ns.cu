@@ -19,6 +19,7 @@
 #include "ns_host.h"
 #include "ns_pipe.cuh"
 #include "ns_pitch7.cuh"
+#include "ns_rnn_tc5.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // kernels (bodies in ns_pipe.cuh)
@@ -44,6 +45,9 @@ using PitchShared = ns::PitchSmem7<kPitchRun>;
 #endif
 //  // 37 lag-quads per frame in the coarse search + one helper warp
 constexpr int kScanWarps = 4;
+#ifndef NS_RNN_TC5_MIN_STREAMS
+#define NS_RNN_TC5_MIN_STREAMS (1 << 30)  // the tcgen05 recurrent core is opt-in ($CRISPY_NS_RNN=tc5) until measured
+#endif
 
 __global__ void __launch_bounds__(ns::kHpThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -77,6 +81,11 @@ __global__ void __launch_bounds__(32 * ns::kFeatWarps) ns_features_kernel(const 
 __global__ void __launch_bounds__(ns::kMmaThreads, 1) ns_rnn_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ns::rnn_body(p, *reinterpret_cast<ns::RnnSmem *>(smem_raw));
+}
+// the same recurrent core on tcgen05 / tensor memory, 128 streams per CTA (ns_rnn_tc5.cuh)
+__global__ void __launch_bounds__(ns::tc5::kThreads, 1) ns_rnn_tc5_kernel(const __grid_constant__ ns::Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ns::tc5::rnn_tc5_body(p, *reinterpret_cast<ns::tc5::Smem *>(smem_raw));
 }
 __global__ void __launch_bounds__(ns::kGroupThreads, NS_SYN_MINB) ns_synthesis_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -212,6 +221,10 @@ struct crispy_ns_batch {
   ns::RnnHeader *d_hdr = nullptr;
   uint32_t *d_words = nullptr;
   float *d_bias = nullptr;
+  // the tcgen05 recurrent core's weight blocks and biases (ns_rnn_tc5.cuh); rnn_tc5: which core K4 launches
+  uint8_t *d_words_tc5 = nullptr;
+  float *d_bias_tc5 = nullptr;
+  bool rnn_tc5 = false;
   float *d_state = nullptr;
   // pipeline workspace + plumbing
   float *d_hp[kSlots] = {};
@@ -291,6 +304,8 @@ static cudaError_t configure_kernels(int dev) {
     e = cudaFuncSetAttribute(ns_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::SpecSmem));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(ns_rnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::RnnSmem));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(ns_rnn_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::tc5::Smem));
   if (e == cudaSuccess) configured[dev] = true;
   return e;
 }
@@ -353,7 +368,14 @@ static void launch_kernel(crispy_ns_batch *b, int k, ns::Params &p, int n, int n
       break;
     case 5:
       if (getenv("CRISPY_NS_EXPERIMENT_SKIP_RNN")) break;  // measurement aid only: what the recurrent core costs the pipeline (results are garbage)
-      ns_rnn_kernel<<<groups, ns::kMmaThreads, sizeof(ns::RnnSmem), sk>>>(p);
+      if (b->rnn_tc5) {
+        ns::Params q = p;
+        q.rnn_words = reinterpret_cast<const uint32_t *>(b->d_words_tc5);
+        q.rnn_bias = b->d_bias_tc5;
+        ns_rnn_tc5_kernel<<<(n + ns::tc5::kStreams - 1) / ns::tc5::kStreams, ns::tc5::kThreads, sizeof(ns::tc5::Smem), sk>>>(q);
+      } else {
+        ns_rnn_kernel<<<groups, ns::kMmaThreads, sizeof(ns::RnnSmem), sk>>>(p);
+      }
       break;
     default: {
       const int resident = b->n_sms * b->syn_ctas_per_sm;
@@ -527,6 +549,8 @@ void batch_destroy(crispy_ns_batch *b) {
   cudaFree(b->d_hdr);
   cudaFree(b->d_words);
   cudaFree(b->d_bias);
+  cudaFree(b->d_words_tc5);
+  cudaFree(b->d_bias_tc5);
   cudaFree(b->d_state);
   for (int i = 0; i < kSlots; i++) {
     cudaFree(b->d_hp[i]);
@@ -612,6 +636,18 @@ int batch_create(const crispy_ns_model *model, int device, int n_streams, crispy
   up((void **)&b->d_hdr, &pk.hdr, sizeof(pk.hdr));
   up((void **)&b->d_words, pk.words.data(), pk.words.size() * sizeof(uint32_t));
   up((void **)&b->d_bias, pk.bias.data(), pk.bias.size() * sizeof(float));
+  {
+    // K4 variant: $CRISPY_NS_RNN = "tc5" (tcgen05 / tensor memory, 128 streams per CTA) or "mma" (warp-level mma.sync,
+    // 16 streams per CTA).  Default: tc5 from 512 streams on -- it holds 8 SMs per 1,024 streams instead of 64, which
+    // the parallel kernels get back; below that its longer step (thirteen rounds per frame) is not worth it.
+    const char *sel = getenv("CRISPY_NS_RNN");
+    b->rnn_tc5 = sel ? (strcmp(sel, "tc5") == 0) : (n_streams >= NS_RNN_TC5_MIN_STREAMS);
+    std::vector<uint8_t> w5;
+    std::vector<float> b5;
+    ns::pack_rnn_tc5(*m, w5, b5);
+    up((void **)&b->d_words_tc5, w5.data(), w5.size());
+    up((void **)&b->d_bias_tc5, b5.data(), b5.size() * sizeof(float));
+  }
   if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_state, (size_t)n_streams * ns::kStateFloats * sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(b->d_state, 0, (size_t)n_streams * ns::kStateFloats * sizeof(float));
   for (int i = 0; i < kSlots && e == cudaSuccess; i++) {

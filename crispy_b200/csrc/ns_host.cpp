@@ -1,5 +1,6 @@
 // ns_host.cpp -- tables, model blobs, weight repacking (host only; see ns_host.h)
 #include "ns_host.h"
+#include "ns_rnn_tc5.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -373,6 +374,87 @@ void pack_rnn(const Model &m, PackedRnn &out) {
               [&](int col) { return (int)dv.bias[col]; });
   out.hdr.n_words = (int32_t)out.words.size();
   out.hdr.n_bias = (int32_t)out.bias.size();
+}
+
+// ---- repacking for the tcgen05 recurrent core (ns_rnn_tc5.cuh): per round one weight block in the canonical K-major
+// no-swizzle layout of a UMMA shared-memory descriptor, element (column n, input kk of k-tile i) at
+//   i * n_cols * 32 + (kk / 8) * (n_cols / 8) * 128 + (n / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2   bytes,
+// and the biases per (round, column).
+void pack_rnn_tc5(const Model &m, std::vector<uint8_t> &w, std::vector<float> &bias) {
+  using namespace tc5;
+  const DenseLayer &d0 = m.input_dense, &dv = m.vad_output, &dg = m.denoise_output;
+  const GruLayer &gv = m.vad_gru, &gn = m.noise_gru, &gd = m.denoise_gru;
+  auto gin = [](const GruLayer &g, int row, int col) { return (int)g.input_weights[(size_t)row * 3 * g.nb_neurons + col]; };
+  auto grec = [](const GruLayer &g, int row, int col) { return (int)g.recurrent_weights[(size_t)row * 3 * g.nb_neurons + col]; };
+  auto in_range = [](int p, int lo, int n) { return p >= lo && p < lo + n; };
+  // weight of the unit (layer, gate, unit) on the activation at A position p
+  auto weight = [&](const ColInfo &c, int p) -> int {
+    const int feat = p - kPosFeat;
+    switch (c.layer) {
+      case 0: return (feat >= 0 && feat < kFeatures) ? (int)d0.weights[(size_t)feat * 24 + c.unit] : 0;
+      case 1: {
+        const int col = 24 * c.gate + c.unit;
+        if (c.gate < 2) {
+          if (in_range(p, kPosDense, 24)) return gin(gv, p - kPosDense, col);
+          if (in_range(p, kPosVadH, 24)) return grec(gv, p - kPosVadH, col);
+        } else {
+          if (in_range(p, kPosDense2, 24)) return gin(gv, p - kPosDense2, col);
+          if (in_range(p, kPosVadR, 24)) return grec(gv, p - kPosVadR, col);
+        }
+        return 0;
+      }
+      case 2: {
+        const int col = 48 * c.gate + c.unit;
+        if (in_range(p, kPosDense, 24)) return gin(gn, p - kPosDense, col);
+        if (in_range(p, kPosVadH, 24)) return gin(gn, 24 + p - kPosVadH, col);
+        if (feat >= 0 && feat < kFeatures) return gin(gn, 48 + feat, col);
+        if (c.gate < 2 && in_range(p, kPosNoiseH, 48)) return grec(gn, p - kPosNoiseH, col);
+        if (c.gate == 2 && in_range(p, kPosNoiseR, 48)) return grec(gn, p - kPosNoiseR, col);
+        return 0;
+      }
+      case 3: {
+        const int col = 96 * c.gate + c.unit;
+        if (in_range(p, kPosVadH, 24)) return gin(gd, p - kPosVadH, col);
+        if (in_range(p, kPosNoiseH, 48)) return gin(gd, 24 + p - kPosNoiseH, col);
+        if (feat >= 0 && feat < kFeatures) return gin(gd, 72 + feat, col);
+        if (c.gate < 2 && in_range(p, kPosDenH, 96)) return grec(gd, p - kPosDenH, col);
+        if (c.gate == 2 && in_range(p, kPosDenR, 96)) return grec(gd, p - kPosDenR, col);
+        return 0;
+      }
+      case 4: return in_range(p, kPosDenH, 96) ? (int)dg.weights[(size_t)(p - kPosDenH) * 22 + c.unit] : 0;
+      case 5: return in_range(p, kPosVadH, 24) ? (int)dv.weights[p - kPosVadH] : 0;
+      default: return 0;
+    }
+  };
+  auto unit_bias = [&](const ColInfo &c) -> int {
+    switch (c.layer) {
+      case 0: return d0.bias[c.unit];
+      case 1: return gv.bias[24 * c.gate + c.unit];
+      case 2: return gn.bias[48 * c.gate + c.unit];
+      case 3: return gd.bias[96 * c.gate + c.unit];
+      case 4: return dg.bias[c.unit];
+      case 5: return dv.bias[0];
+      default: return 0;
+    }
+  };
+  w.assign(kWeightBytes, 0);
+  bias.assign((size_t)kNumRounds * kBiasPerRound, 0.f);
+  for (int r = 0; r < kNumRounds; r++) {
+    const Round &R = kRounds[r];
+    for (int n = 0; n < R.n; n++) {
+      const ColInfo c = col_info(r, n);
+      bias[(size_t)r * kBiasPerRound + n] = (float)unit_bias(c);
+      for (int i = 0; i < R.n_kt; i++)
+        for (int kk = 0; kk < 16; kk++) {
+          const int v = weight(c, 16 * R.kt[i] + kk);
+          const size_t off = (size_t)R.boff + (size_t)i * R.n * 32 + (size_t)(kk / 8) * (R.n / 8) * 128 + (size_t)(n / 8) * 128 +
+                             (size_t)(n % 8) * 16 + (size_t)(kk % 8) * 2;
+          const uint32_t bits = bf16_bits(v);
+          w[off] = (uint8_t)bits;
+          w[off + 1] = (uint8_t)(bits >> 8);
+        }
+    }
+  }
 }
 
 }  // namespace ns

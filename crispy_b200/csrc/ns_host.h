@@ -42,5 +42,7 @@ struct PackedRnn {
   std::vector<float> bias;
 };
 void pack_rnn(const Model &m, PackedRnn &out);
+// the same network for the tcgen05 recurrent core (ns_rnn_tc5.cuh): weight blocks as UMMA descriptors address them + biases
+void pack_rnn_tc5(const Model &m, std::vector<uint8_t> &w, std::vector<float> &bias);
 
 }  // namespace ns
