@@ -536,7 +536,20 @@ def run_b200(args):
                                                           "tensor_pipe_pct", "dram_throughput_pct") if tr.get(k) == tr.get(k) and tr.get(k) is not None}
         kernels.append(ent)
     kernels.sort(key=lambda e: -e["ms_total"])
-    dom = kernels[0]
+    # The dominant kernel is the one that takes the most SM-time, not the one whose launches last longest: the serial
+    # kernels (biquad, recurrent core: one lane or one CTA per group of streams) cover a fraction of the 148 SMs and
+    # stretch while they share them with the parallel kernels of the neighbouring chunks.  SM-time = summed launch time
+    # x the fraction of the SMs the kernel's grid covers.
+    n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    grid_ctas = {"ns_highpass_kernel": -(-n_streams // 32), "ns_pitchscan_kernel": -(-n_streams // 4),
+                 "ns_features_kernel": -(-n_streams // 4), "ns_rnn_kernel": -(-n_streams // info0["rnn_streams_per_cta"])}
+    for ent in kernels:
+        ent["sm_fraction"] = min(1.0, grid_ctas.get(ent["kernel"], n_sms) / n_sms)
+        ent["sm_time_ms"] = ent["ms_total"] * ent["sm_fraction"]
+    tot_sm_time = sum(e["sm_time_ms"] for e in kernels) or 1.0
+    for ent in kernels:
+        ent["share_of_sm_time"] = ent["sm_time_ms"] / tot_sm_time
+    dom = max(kernels, key=lambda e: e["sm_time_ms"])
     roofline = {"bound": "hbm", "achieved": dom["hbm_algorithmic_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": dom["hbm_algorithmic_gbs"] / hbm_peak, "traffic": dom.get("dram_bytes_per_launch_ncu"),
                 "peak_source": peak_src, "kernel": dom["kernel"],
@@ -544,8 +557,9 @@ def run_b200(args):
                 "avg_launch_us": dom["avg_launch_us"], "ncu_limiters_pct": dom.get("ncu_limiters_pct"),
                 "note": "algorithmic bytes = 3,844 B per (stream, frame) (480 f32 in + 480 f32 out + VAD) x the frames "
                         "one launch covers / that kernel's mean launch time (CUDA events on its own stream, inside the "
-                        "timed region, kernels of neighbouring chunks running concurrently). No kernel of this path "
-                        "is HBM-bound yet: they are issue/latency bound (profiles/)."}
+                        "timed region, kernels of neighbouring chunks running concurrently). The kernel named is the one "
+                        "with the largest share of SM-time (kernels[].share_of_sm_time). No kernel of this path "
+                        "is HBM-bound: they are issue/latency bound (profiles/)."}
     roofline_fp32 = {"whole_pipeline_tflops": ALL_FLOPS_PER_FRAME * n_streams * n_frames * args.steps / (total_ms / 1e3) / 1e12,
                      "peak_tflops_measured_ffma_burst": fp32["ffma_tflops"],
                      "unfused_tmacs_measured": fp32["unfused_tmacs"],

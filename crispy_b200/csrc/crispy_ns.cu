@@ -862,7 +862,7 @@ int batch_load_state(crispy_ns_batch *b, const void *buf, size_t len) {
 int batch_info(const crispy_ns_batch *b, int *streams_per_cta, int *n_ctas, int64_t *launches,
                          int64_t *frames_done) {  // (rnn_streams_per_cta, chunk_frames, ...)
   if (!b) return fail(CRISPY_NS_EINVAL, "batch_info: null handle");
-  if (streams_per_cta) *streams_per_cta = ns::kMmaStreams;
+  if (streams_per_cta) *streams_per_cta = b->rnn_tc5 ? ns::tc5::kStreams : ns::kMmaStreams;
   if (n_ctas) *n_ctas = b->chunk_cap;
   if (launches) *launches = b->launches;
   if (frames_done) *frames_done = b->frames_done;

@@ -398,7 +398,7 @@ void pack_rnn_tc5(const Model &m, std::vector<uint8_t> &w, std::vector<float> &b
           if (in_range(p, kPosDense, 24)) return gin(gv, p - kPosDense, col);
           if (in_range(p, kPosVadH, 24)) return grec(gv, p - kPosVadH, col);
         } else {
-          if (in_range(p, kPosDense2, 24)) return gin(gv, p - kPosDense2, col);
+          if (in_range(p, kPosDense, 24)) return gin(gv, p - kPosDense, col);
           if (in_range(p, kPosVadR, 24)) return grec(gv, p - kPosVadR, col);
         }
         return 0;

@@ -1798,6 +1798,21 @@ NS_DEV float activate(const float *tab, int act, float x) {
   if (act == 0) return tansig_approx(tab, x);
   return x < 0.f ? 0.f : x;
 }
+// N activations of one kind: the (uniform) choice is made once, so the N table look-ups and polynomial chains
+// interleave instead of running one after the other behind a branch each
+template <int N>
+NS_DEV void activate_n(const float *tab, int act, const float *x, float *y) {
+  if (act == 1) {
+#pragma unroll
+    for (int j = 0; j < N; j++) y[j] = sigmoid_approx(tab, x[j]);
+  } else if (act == 0) {
+#pragma unroll
+    for (int j = 0; j < N; j++) y[j] = tansig_approx(tab, x[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; j++) y[j] = x[j] < 0.f ? 0.f : x[j];
+  }
+}
 
 // bf16 (round to nearest even) bit pattern of a finite float, and the hi + lo split of an activation
 NS_DEV uint32_t bf16_rn_bits(float x) {
@@ -2090,10 +2105,11 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
             act_out = r.act[kJOut], act_vadout = r.act[kJVadOut];
   // GRU update of the four (row, neuron) elements this lane owns
   auto gru_update = [&](float (&h)[4], const float (&z)[4], const float (&x)[4], int act, const bool (&sil)[2]) {
+    float cnd[4];
+    activate_n<4>(tab, act, x, cnd);
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      const float cnd = activate(tab, act, x[e]);
-      const float hnew = z[e] * h[e] + (1.f - z[e]) * cnd;
+      const float hnew = z[e] * h[e] + (1.f - z[e]) * cnd[e];
       if (!sil[e >> 1]) h[e] = hnew;
     }
   };
@@ -2119,8 +2135,7 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
         mma_run<kJDense, 1>(r, fcur, tiles, 1, lane, acc);
         mma_pre<kJDense>(r, acc[0], warp, lane, x);
         float y[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) y[e] = activate(tab, act_dense, x[e]);
+        activate_n<4>(tab, act_dense, x, y);
         store_frag(r, kPosDense + warp * 8, lane, y);
         store_frag(r, kPosDense2 + warp * 8, lane, y);
       }
@@ -2217,10 +2232,12 @@ NS_DEV void rnn_body(const Params &p, RnnSmem &r) {
         const int tiles[1] = {warp};
         mma_run<kJOut, 1>(r, fcur, tiles, 1, lane, acc);
         mma_pre<kJOut>(r, acc[0], warp, lane, x);
+        float gact[4];
+        activate_n<4>(tab, act_out, x, gact);
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           if (!sil[e >> 1]) {
-            graw[e] = activate(tab, act_out, x[e]);
+            graw[e] = gact[e];
             gout[e] = fmaxf(graw[e], .6f * lastg[e]);
             lastg[e] = gout[e];
           }

@@ -2,16 +2,19 @@
 // denoise GRU -> dense) of 128 streams per CTA as tcgen05.mma (UTCHMMA) products with every operand where Blackwell
 // wants it:
 //   * A (activations, 128 streams x K): TENSOR MEMORY.  Lane = stream, 32-bit column c holds the bf16 pair of inputs
-//     (2c, 2c + 1); two planes, hi at columns [0, 216) and lo = bf16(x - hi) at [216, 432), so x = hi + lo to 2^-17.
+//     (2c, 2c + 1); two planes, hi at columns [0, 208) and lo = bf16(x - hi) at [208, 416), so x = hi + lo to 2^-17.
 //     The epilogue threads write them with tcgen05.st and the MMA reads them in place (the .ts form: A from TMEM).
-//   * B (weights, int8 exact in bf16): SHARED MEMORY, 187.5 KB resident for the whole launch, one block per product in
+//   * B (weights, int8 exact in bf16): SHARED MEMORY, 188.5 KB resident for the whole launch, one block per product in
 //     the canonical K-major no-swizzle layout a UMMA shared-memory descriptor addresses (8 x 16 B core matrices).
-//   * D (f32 accumulators, 128 x N): TENSOR MEMORY columns [432, 512), read back with tcgen05.ld for the epilogue.
-// One frame step is thirteen rounds (the eight products of the network, the wide ones cut into chunks of <= 64
-// columns because A fills most of tensor memory): one thread issues the round's MMAs (hi and lo plane into the same
-// accumulator) and commits them to an mbarrier; the 256 epilogue threads wait on it, load their half of the columns of
-// their stream's row, apply bias / table tanh / GRU algebra in registers (the GRU states themselves stay in f32
-// registers) and store the next products' operands straight back into tensor memory.
+//   * D (f32 accumulators, 128 x N): TENSOR MEMORY columns [416, 512), read back with tcgen05.ld for the epilogue.
+// One frame step is nine rounds.  A tcgen05.mma issued by one thread costs ~77 cycles whatever N <= 128 is
+// (scripts/micro/tc5_rate.cu: 77 cycles at N = 16 .. 128, 97 at 192, 128 at 256), so a round is made as wide as the
+// 96 accumulator columns allow (z | r of the noise GRU in one round; z, r, candidate of the denoise GRU 96 columns
+// each) and takes 2 MMAs (hi and lo plane into the same accumulator) per k-tile of its inputs: 152 MMAs per frame.
+// One thread issues the round's MMAs and commits them to an mbarrier; the 512 epilogue threads (four per stream: warp w
+// owns the tensor-memory lanes 32 (w % 4) .. + 31 and the column quarter w / 4) wait on it, load their quarter of the
+// columns of their stream's row, apply bias / table tanh / GRU algebra in registers (the GRU states themselves stay in
+// f32 registers) and store the next products' operands straight back into tensor memory.
 // 1,024 streams take 8 CTAs instead of the 64 the warp-level mma.sync core occupies (ns_pipe.cuh rnn_body).
 //
 // Device-only (no host emulation: tensor memory has no CPU stand-in); parity is checked on the GPU against the oracle
@@ -23,42 +26,49 @@ namespace ns {
 namespace tc5 {
 
 constexpr int kStreams = 128;
-constexpr int kThreads = 256;   // thread = (stream row m = tid & 127, column half hs = tid >> 7)
-constexpr int kColLo = 216;     // first column of the lo plane
-constexpr int kColD = 432;      // accumulator columns
+constexpr int kThreads = 512;   // thread = (stream row m = tid & 127, column quarter hs = tid >> 7)
+constexpr int kParts = 4;
+constexpr int kColLo = 208;     // first column of the lo plane
+constexpr int kColD = 416;      // accumulator columns
 constexpr int kTmemCols = 512;
-constexpr int kNumRounds = 13;
+constexpr int kNumRounds = 9;
 constexpr int kMaxKt = 14;
 
-// positions of the activation vectors in the A element space (k-tile v = elements 16 v .. 16 v + 15; the same tiling as
-// the mma.sync core: ns_common.h kKt*)
-constexpr int kPosDense = 0, kPosVadH = 24, kPosDense2 = 48, kPosVadR = 72, kPosNoiseH = 96, kPosNoiseR = 144,
-              kPosDenH = 192, kPosDenR = 288, kPosFeat = 384;
+// positions of the activation vectors in the A element space (k-tile v = elements 16 v .. 16 v + 15); every vector
+// starts a k-tile except the VAD state, which shares k-tiles 0..2 with the dense layer's output
+constexpr int kPosDense = 0, kPosVadH = 24, kPosVadR = 48, kPosNoiseH = 80, kPosNoiseR = 128, kPosDenH = 176,
+              kPosDenR = 272, kPosFeat = 368;
+static_assert(kPosFeat + 48 == 2 * kColLo, "the A planes");
 
 struct Round {
   int n_kt;
   int kt[kMaxKt];
-  int n;      // columns of the round (a multiple of 16): half 0 takes columns [0, n/2), half 1 the rest
+  int n;      // columns of the round (a multiple of 16): quarter h takes columns [h n/4, (h + 1) n/4)
   int boff;   // byte offset of the round's weight block
 };
 // weight block of a round: [k-tile][K half][n / 8][8 columns][8 inputs] bf16 = n * 32 bytes per k-tile
 constexpr Round kRounds[kNumRounds] = {
-    {3, {24, 25, 26}, 32, 0},                                              // 0 input_dense
-    {3, {0, 1, 2}, 48, 3072},                                              // 1 vad z | r
-    {3, {3, 4, 5}, 32, 7680},                                              // 2 vad candidate
-    {9, {0, 1, 2, 24, 25, 26, 6, 7, 8}, 48, 10752},                        // 3 noise z
-    {9, {0, 1, 2, 24, 25, 26, 6, 7, 8}, 64, 24576},                        // 4 noise r (+ vad_output)
-    {9, {0, 1, 2, 24, 25, 26, 9, 10, 11}, 48, 43008},                      // 5 noise candidate
-    {14, {1, 2, 6, 7, 8, 24, 25, 26, 12, 13, 14, 15, 16, 17}, 48, 56832},  // 6 denoise z, neurons 48 h + 0..23
-    {14, {1, 2, 6, 7, 8, 24, 25, 26, 12, 13, 14, 15, 16, 17}, 48, 78336},  // 7 denoise z, neurons 48 h + 24..47
-    {14, {1, 2, 6, 7, 8, 24, 25, 26, 12, 13, 14, 15, 16, 17}, 48, 99840},  // 8 denoise r, neurons 48 h + 0..23
-    {14, {1, 2, 6, 7, 8, 24, 25, 26, 12, 13, 14, 15, 16, 17}, 48, 121344}, // 9 denoise r, neurons 48 h + 24..47
-    {14, {1, 2, 6, 7, 8, 24, 25, 26, 18, 19, 20, 21, 22, 23}, 48, 142848}, // 10 denoise candidate, 48 h + 0..23
-    {14, {1, 2, 6, 7, 8, 24, 25, 26, 18, 19, 20, 21, 22, 23}, 48, 164352}, // 11 denoise candidate, 48 h + 24..47
-    {6, {12, 13, 14, 15, 16, 17}, 32, 185856},                             // 12 denoise_output
+    {3, {23, 24, 25}, 32, 0},                                                  // 0 input_dense
+    {3, {0, 1, 2}, 48, 3072},                                                  // 1 vad z | r
+    {4, {0, 1, 3, 4}, 32, 7680},                                               // 2 vad candidate
+    {9, {0, 1, 2, 23, 24, 25, 5, 6, 7}, 96, 11776},                            // 3 noise z | r
+    {9, {0, 1, 2, 23, 24, 25, 8, 9, 10}, 64, 39424},                           // 4 noise candidate (+ vad_output)
+    {14, {1, 2, 5, 6, 7, 23, 24, 25, 11, 12, 13, 14, 15, 16}, 96, 57856},      // 5 denoise z
+    {14, {1, 2, 5, 6, 7, 23, 24, 25, 11, 12, 13, 14, 15, 16}, 96, 100864},     // 6 denoise r
+    {14, {1, 2, 5, 6, 7, 23, 24, 25, 17, 18, 19, 20, 21, 22}, 96, 143872},     // 7 denoise candidate
+    {6, {11, 12, 13, 14, 15, 16}, 32, 186880},                                 // 8 denoise_output
 };
-constexpr int kWeightBytes = 185856 + 6 * 32 * 32;  // 192,000
-constexpr int kBiasPerRound = 64;
+constexpr int kWeightBytes = 186880 + 6 * 32 * 32;  // 193,024
+constexpr int kBiasPerRound = 96;
+constexpr bool rounds_consistent() {
+  int off = 0;
+  for (int r = 0; r < kNumRounds; r++) {
+    if (kRounds[r].boff != off || kRounds[r].n % 16 != 0 || kRounds[r].n > kBiasPerRound || kRounds[r].n > kTmemCols - kColD) return false;
+    off += kRounds[r].n_kt * kRounds[r].n * 32;
+  }
+  return off == kWeightBytes;
+}
+static_assert(rounds_consistent(), "weight block offsets");
 
 // what column `col` of round `r` computes: layer 0 dense, 1 vad GRU, 2 noise GRU, 3 denoise GRU, 4 output, 5 vad_output;
 // gate 0 z, 1 r, 2 candidate; unit index; layer -1 = padding.  Shared by the host packer and (implicitly) the epilogues.
@@ -66,21 +76,17 @@ struct ColInfo {
   int layer, gate, unit;
 };
 inline ColInfo col_info(int r, int col) {
-  const int half_n = kRounds[r].n / 2, h = col / half_n, j = col % half_n;
+  const int part_n = kRounds[r].n / kParts, h = col / part_n, j = col % part_n;
   switch (r) {
-    case 0: return j < 12 ? ColInfo{0, 0, 12 * h + j} : ColInfo{-1, 0, 0};
-    case 1: return j < 12 ? ColInfo{1, 0, 12 * h + j} : ColInfo{1, 1, 12 * h + j - 12};
-    case 2: return j < 12 ? ColInfo{1, 2, 12 * h + j} : ColInfo{-1, 0, 0};
-    case 3: return ColInfo{2, 0, 24 * h + j};
-    case 4: return j < 24 ? ColInfo{2, 1, 24 * h + j} : ((h == 0 && j == 24) ? ColInfo{5, 0, 0} : ColInfo{-1, 0, 0});
-    case 5: return ColInfo{2, 2, 24 * h + j};
-    case 6: return ColInfo{3, 0, 48 * h + j};
-    case 7: return ColInfo{3, 0, 48 * h + 24 + j};
-    case 8: return ColInfo{3, 1, 48 * h + j};
-    case 9: return ColInfo{3, 1, 48 * h + 24 + j};
-    case 10: return ColInfo{3, 2, 48 * h + j};
-    case 11: return ColInfo{3, 2, 48 * h + 24 + j};
-    default: return j < 11 ? ColInfo{4, 0, 11 * h + j} : ColInfo{-1, 0, 0};
+    case 0: return j < 6 ? ColInfo{0, 0, 6 * h + j} : ColInfo{-1, 0, 0};
+    case 1: return j < 6 ? ColInfo{1, 0, 6 * h + j} : ColInfo{1, 1, 6 * h + j - 6};
+    case 2: return j < 6 ? ColInfo{1, 2, 6 * h + j} : ColInfo{-1, 0, 0};
+    case 3: return j < 12 ? ColInfo{2, 0, 12 * h + j} : ColInfo{2, 1, 12 * h + j - 12};
+    case 4: return j < 12 ? ColInfo{2, 2, 12 * h + j} : ((h == 0 && j == 12) ? ColInfo{5, 0, 0} : ColInfo{-1, 0, 0});
+    case 5: return ColInfo{3, 0, 24 * h + j};
+    case 6: return ColInfo{3, 1, 24 * h + j};
+    case 7: return ColInfo{3, 2, 24 * h + j};
+    default: return (j < 6 && 6 * h + j < 22) ? ColInfo{4, 0, 6 * h + j} : ColInfo{-1, 0, 0};
   }
 }
 
@@ -99,6 +105,15 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 
 template <int N>
 struct TmemIo;
+template <>
+struct TmemIo<1> {
+  static __device__ __forceinline__ void ld(unsigned a, unsigned *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(a));
+  }
+  static __device__ __forceinline__ void st(unsigned a, const unsigned *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(a), "r"(v[0]));
+  }
+};
 template <>
 struct TmemIo<2> {
   static __device__ __forceinline__ void ld(unsigned a, unsigned *v) {
@@ -155,7 +170,7 @@ __device__ __forceinline__ void store_act(unsigned lane_base, int pos, const flo
 
 __device__ __forceinline__ void rnn_tc5_body(const Params &p, Smem &s) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hs = warp >> 2;        // TMEM lane quarter of this warp, column half
+  const int q = warp & 3, hs = warp >> 2;        // TMEM lane quarter of this warp, column quarter
   const int m = 32 * q + lane;                   // stream row within the CTA
   const int stream = blockIdx.x * kStreams + m;
   const bool live = stream < p.n_streams;
@@ -185,25 +200,44 @@ __device__ __forceinline__ void rnn_tc5_body(const Params &p, Smem &s) {
   const RnnHeader &H = *p.rnn_hdr;
   const int act_dense = H.activation[kJDense], act_vad = H.activation[kJVadC], act_noise = H.activation[kJNoiseC],
             act_den = H.activation[kJDenC], act_out = H.activation[kJOut], act_vadout = H.activation[kJVadOut];
-  // ---- recurrent state of this thread's units: vad 12 hs + 0..11, noise 24 hs + 0..23, denoise 48 hs + 0..47, lastg 11 hs + 0..10
-  float hv[12], hn[24], hd[48], lastg[11];
+  // ---- recurrent state of this thread's units: vad 6 hs + 0..5, noise 12 hs + 0..11, denoise 24 hs + 0..23,
+  //      lastg 6 hs + 0..5 (22 bands: the last quarter owns four)
+  float hv[6], hn[12], hd[24], lastg[6];
   {
     const float *st = p.state + (long long)(live ? stream : 0) * kStateFloats;
 #pragma unroll
-    for (int j = 0; j < 12; j++) hv[j] = live ? st[kStHVad + 12 * hs + j] : 0.f;
+    for (int j = 0; j < 6; j++) hv[j] = live ? st[kStHVad + 6 * hs + j] : 0.f;
 #pragma unroll
-    for (int j = 0; j < 24; j++) hn[j] = live ? st[kStHNoise + 24 * hs + j] : 0.f;
+    for (int j = 0; j < 12; j++) hn[j] = live ? st[kStHNoise + 12 * hs + j] : 0.f;
 #pragma unroll
-    for (int j = 0; j < 48; j++) hd[j] = live ? st[kStHDen + 48 * hs + j] : 0.f;
+    for (int j = 0; j < 24; j++) hd[j] = live ? st[kStHDen + 24 * hs + j] : 0.f;
 #pragma unroll
-    for (int j = 0; j < 11; j++) lastg[j] = live ? st[kStLastG + 11 * hs + j] : 0.f;
+    for (int j = 0; j < 6; j++) lastg[j] = (live && 6 * hs + j < kBands) ? st[kStLastG + 6 * hs + j] : 0.f;
   }
-  store_act<12, 2>(lane_base, kPosVadH + 12 * hs, hv);
-  store_act<24, 4>(lane_base, kPosNoiseH + 24 * hs, hn);
-  store_act<48, 8>(lane_base, kPosDenH + 48 * hs, hd);
-  // feature words of (16-stream group, frame): K3b's layout (ns_pipe.cuh features_body): pair q of row r at word widx
-  const int row16 = m & 15;
+  store_act<6, 1>(lane_base, kPosVadH + 6 * hs, hv);
+  store_act<12, 2>(lane_base, kPosNoiseH + 12 * hs, hn);
+  store_act<24, 4>(lane_base, kPosDenH + 24 * hs, hd);
+  if (hs == 0) {  // the padding behind r * h of the VAD GRU (elements 72..79) meets zero weights: it must be finite
+    const unsigned zero[4] = {0u, 0u, 0u, 0u};
+    tmem_st<4, 4>(lane_base + (unsigned)((kPosVadR + 24) >> 1), zero);
+    tmem_st<4, 4>(lane_base + (unsigned)(kColLo + ((kPosVadR + 24) >> 1)), zero);
+  }
+  // feature words of (16-stream group, frame): K3b's layout (ns_pipe.cuh features_body): pair qq of row r at word widx;
+  // quarter hs stores pairs 12 (hs & 1) .. + 11 of plane hs >> 1
+  const int row16 = m & 15, fplane = hs >> 1, fhalf = hs & 1;
   const uint32_t *fq_src = p.featq + (long long)(stream >> 4) * p.chunk_cap * kFeatBlockWords;
+  unsigned fw[12];
+  unsigned silw = 1u;
+  auto fetch_features = [&](int t) {  // issued a frame ahead: the loads fly under the previous frame's rounds
+    const uint32_t *blk = fq_src + (long long)t * kFeatBlockWords + fplane * (kFeatKt * kKtWords);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const int qq = 12 * fhalf + i;
+      const int widx = ((qq >> 3) * 32 + (row16 & 7) * 4 + (qq & 3)) * 4 + (row16 >> 3) + 2 * ((qq & 7) >> 2);
+      fw[i] = live ? __ldg(blk + widx) : 0u;
+    }
+    silw = live ? __ldg(fq_src + (long long)t * kFeatBlockWords + 2 * kFeatKt * kKtWords + row16) : 1u;
+  };
   unsigned parity = 0;
   unsigned err = 0;
   auto round_mma = [&](auto ri_tag) {  // one thread: every k-tile of the round, hi then lo plane, into the accumulator columns
@@ -230,13 +264,19 @@ __device__ __forceinline__ void rnn_tc5_body(const Params &p, Smem &s) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s.mbar)) : "memory");
   };
 #ifdef NS_TC5_CLOCKS
-  long long tk_issue = 0, tk_wait = 0, tk_epi = 0, tk_mark = clock64();
-#define NS_TC5_TICK(acc) do { const long long now_ = clock64(); acc += now_ - tk_mark; tk_mark = now_; } while (0)
+  // measurement build: where a frame step's cycles go, seen by the first thread of two warps
+  long long tk[6] = {0, 0, 0, 0, 0, 0}, tk_mark = clock64();
+#define NS_TC5_TICK(i) do { const long long now_ = clock64(); tk[i] += now_ - tk_mark; tk_mark = now_; } while (0)
 #else
-#define NS_TC5_TICK(acc) do {} while (0)
+#define NS_TC5_TICK(i) do {} while (0)
 #endif
-  auto wait_round = [&]() {
-    NS_TC5_TICK(tk_issue);
+  // issue the round (one thread) and wait for its accumulators (everyone)
+  auto run_round = [&](auto ri_tag) {
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      round_mma(ri_tag);
+    }
+    NS_TC5_TICK(0);
     unsigned done = 0;
     for (int spin = 0; spin < (1 << 24) && !done; spin++)
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -246,203 +286,154 @@ __device__ __forceinline__ void rnn_tc5_body(const Params &p, Smem &s) {
     if (!done) err = 1;  // a wedged tensor pipe must not hang the device: results are garbage, the host sees the flag
     parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;");
-    NS_TC5_TICK(tk_wait);
+    NS_TC5_TICK(1);
   };
-  // the accumulators of this thread's half of the round's columns, scaled: x = (acc + bias) / 256
-  auto load_pre = [&](int r, auto nc_tag, float *x) {
+  // NC accumulators of this thread's quarter of the round's columns from column offset c0 of the quarter, scaled:
+  // x = (acc + bias) / 256
+  auto load_pre = [&](int r, int part_n, int c0, auto nc_tag, float *x) {
     constexpr int NC = decltype(nc_tag)::value;
     unsigned v[NC];
-    tmem_ld<NC, 8>(lane_base + (unsigned)(kColD + hs * NC), v);
+    tmem_ld<NC, (NC % 8 == 0 ? 8 : 4)>(lane_base + (unsigned)(kColD + hs * part_n + c0), v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    const float *b = s.bias + r * kBiasPerRound + hs * NC;
+    const float *b = s.bias + r * kBiasPerRound + hs * part_n + c0;
 #pragma unroll
     for (int j = 0; j < NC; j++) x[j] = (__uint_as_float(v[j]) + b[j]) * (1.f / 256);
+    NS_TC5_TICK(2);
   };
   auto end_round = [&]() {  // operands stored, accumulators read: the next round may issue
+    NS_TC5_TICK(3);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
+    NS_TC5_TICK(4);
     __syncthreads();
-    NS_TC5_TICK(tk_epi);
+    NS_TC5_TICK(5);
   };
 
+  if (p.n_frames > 0) fetch_features(0);
   for (int t = 0; t < p.n_frames; t++) {
-    // features of this frame -> tensor memory (half 0 stores the hi plane, half 1 the lo plane)
-    bool sil = true;
-    {
-      unsigned fw[24];
-      const uint32_t *blk = fq_src + (long long)t * kFeatBlockWords + hs * (kFeatKt * kKtWords);
-#pragma unroll
-      for (int qq = 0; qq < 24; qq++) {
-        const int widx = ((qq >> 3) * 32 + (row16 & 7) * 4 + (qq & 3)) * 4 + (row16 >> 3) + 2 * ((qq & 7) >> 2);
-        fw[qq] = live ? __ldg(blk + widx) : 0u;
-      }
-      if (live) sil = __ldg(fq_src + (long long)t * kFeatBlockWords + 2 * kFeatKt * kKtWords + row16) != 0u;
-      tmem_st<24, 8>(lane_base + (unsigned)(hs * kColLo + (kPosFeat >> 1)), fw);
-    }
+    // features of this frame -> tensor memory; the next frame's are requested right away
+    const bool sil = silw != 0u;
+    tmem_st<12, 4>(lane_base + (unsigned)(fplane * kColLo + (kPosFeat >> 1) + 12 * fhalf), fw);
+    if (t + 1 < p.n_frames) fetch_features(t + 1);
     end_round();
     float vad = 0.f;
-    float x[32];
-    // 0: input_dense -> dense (both copies)
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      round_mma(IntC<0>{});
-    }
-    wait_round();
-    load_pre(0, IntC<16>{}, x);
+    float x[12];
+    // 0: input_dense -> dense
+    run_round(IntC<0>{});
+    load_pre(0, 8, 0, IntC<8>{}, x);
     {
-      float y[12];
-#pragma unroll
-      for (int j = 0; j < 12; j++) y[j] = activate(tab, act_dense, x[j]);
-      store_act<12, 2>(lane_base, kPosDense + 12 * hs, y);
-      store_act<12, 2>(lane_base, kPosDense2 + 12 * hs, y);
+      float y[6];
+      activate_n<6>(tab, act_dense, x, y);
+      store_act<6, 1>(lane_base, kPosDense + 6 * hs, y);
     }
     end_round();
     // 1: vad z | r
-    float zv[12];
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      round_mma(IntC<1>{});
-    }
-    wait_round();
-    load_pre(1, IntC<24>{}, x);
+    float zv[6];
+    run_round(IntC<1>{});
+    load_pre(1, 12, 0, IntC<12>{}, x);
     {
-      float rh[12];
+      float rh[6];
 #pragma unroll
-      for (int j = 0; j < 12; j++) {
+      for (int j = 0; j < 6; j++) {
         zv[j] = sigmoid_approx(tab, x[j]);
-        rh[j] = hv[j] * sigmoid_approx(tab, x[12 + j]);
+        rh[j] = hv[j] * sigmoid_approx(tab, x[6 + j]);
       }
-      store_act<12, 2>(lane_base, kPosVadR + 12 * hs, rh);
+      store_act<6, 1>(lane_base, kPosVadR + 6 * hs, rh);
     }
     end_round();
     // 2: vad candidate -> vad state
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      round_mma(IntC<2>{});
-    }
-    wait_round();
-    load_pre(2, IntC<16>{}, x);
+    run_round(IntC<2>{});
+    load_pre(2, 8, 0, IntC<8>{}, x);
+    activate_n<6>(tab, act_vad, x, x);
 #pragma unroll
-    for (int j = 0; j < 12; j++) {
-      const float c = activate(tab, act_vad, x[j]);
-      const float hnew = zv[j] * hv[j] + (1.f - zv[j]) * c;
+    for (int j = 0; j < 6; j++) {
+      const float hnew = zv[j] * hv[j] + (1.f - zv[j]) * x[j];
       if (!sil) hv[j] = hnew;
     }
-    store_act<12, 2>(lane_base, kPosVadH + 12 * hs, hv);
+    store_act<6, 1>(lane_base, kPosVadH + 6 * hs, hv);
     end_round();
-    // 3: noise z
-    float zn[24];
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      round_mma(IntC<3>{});
-    }
-    wait_round();
-    load_pre(3, IntC<24>{}, x);
+    // 3: noise z | r -> z, r * h
+    float zn[12];
+    run_round(IntC<3>{});
+    load_pre(3, 24, 0, IntC<12>{}, x);
 #pragma unroll
-    for (int j = 0; j < 24; j++) zn[j] = sigmoid_approx(tab, x[j]);
-    end_round();
-    // 4: noise r (+ vad_output in column 24 of half 0)
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      round_mma(IntC<4>{});
-    }
-    wait_round();
-    load_pre(4, IntC<32>{}, x);
+    for (int j = 0; j < 12; j++) zn[j] = sigmoid_approx(tab, x[j]);
+    load_pre(3, 24, 12, IntC<12>{}, x);
     {
-      float rh[24];
+      float rh[12];
 #pragma unroll
-      for (int j = 0; j < 24; j++) rh[j] = hn[j] * sigmoid_approx(tab, x[j]);
-      store_act<24, 4>(lane_base, kPosNoiseR + 24 * hs, rh);
-      if (hs == 0) vad = activate(tab, act_vadout, x[24]);
+      for (int j = 0; j < 12; j++) rh[j] = hn[j] * sigmoid_approx(tab, x[j]);
+      store_act<12, 2>(lane_base, kPosNoiseR + 12 * hs, rh);
     }
     end_round();
-    // 5: noise candidate -> noise state
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      round_mma(IntC<5>{});
-    }
-    wait_round();
-    load_pre(5, IntC<24>{}, x);
+    // 4: noise candidate -> noise state (+ vad_output in column 12 of quarter 0: the VAD state settled in round 2)
+    run_round(IntC<4>{});
+    load_pre(4, 16, 0, IntC<12>{}, x);
+    activate_n<12>(tab, act_noise, x, x);
 #pragma unroll
-    for (int j = 0; j < 24; j++) {
-      const float c = activate(tab, act_noise, x[j]);
-      const float hnew = zn[j] * hn[j] + (1.f - zn[j]) * c;
+    for (int j = 0; j < 12; j++) {
+      const float hnew = zn[j] * hn[j] + (1.f - zn[j]) * x[j];
       if (!sil) hn[j] = hnew;
     }
-    store_act<24, 4>(lane_base, kPosNoiseH + 24 * hs, hn);
-    end_round();
-    // 6, 7: denoise z
-    float zd[48];
-    auto den_z = [&](auto c_tag) {
-      constexpr int c = decltype(c_tag)::value;
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        round_mma(IntC<6 + c>{});
-      }
-      wait_round();
-      load_pre(6 + c, IntC<24>{}, x);
-#pragma unroll
-      for (int j = 0; j < 24; j++) zd[24 * c + j] = sigmoid_approx(tab, x[j]);
-      end_round();
-    };
-    den_z(IntC<0>{});
-    den_z(IntC<1>{});
-    // 8, 9: denoise r -> r * h
-    auto den_r = [&](auto c_tag) {
-      constexpr int c = decltype(c_tag)::value;
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        round_mma(IntC<8 + c>{});
-      }
-      wait_round();
-      load_pre(8 + c, IntC<24>{}, x);
-      float rh[24];
-#pragma unroll
-      for (int j = 0; j < 24; j++) rh[j] = hd[24 * c + j] * sigmoid_approx(tab, x[j]);
-      store_act<24, 4>(lane_base, kPosDenR + 48 * hs + 24 * c, rh);
-      end_round();
-    };
-    den_r(IntC<0>{});
-    den_r(IntC<1>{});
-    // 10, 11: denoise candidate -> denoise state (the r rounds above read the old state: it is replaced only here)
-    auto den_c = [&](auto c_tag) {
-      constexpr int c = decltype(c_tag)::value;
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        round_mma(IntC<10 + c>{});
-      }
-      wait_round();
-      load_pre(10 + c, IntC<24>{}, x);
-#pragma unroll
-      for (int j = 0; j < 24; j++) {
-        const float cc = activate(tab, act_den, x[j]);
-        const float hnew = zd[24 * c + j] * hd[24 * c + j] + (1.f - zd[24 * c + j]) * cc;
-        if (!sil) hd[24 * c + j] = hnew;
-      }
-      store_act<24, 4>(lane_base, kPosDenH + 48 * hs + 24 * c, hd + 24 * c);  // the second chunk's product reads r * h, not the state
-      end_round();
-    };
-    den_c(IntC<0>{});
-    den_c(IntC<1>{});
-    // 12: denoise_output -> band gains; g = max(g, 0.6 lastg)
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      round_mma(IntC<12>{});
+    store_act<12, 2>(lane_base, kPosNoiseH + 12 * hs, hn);
+    if (hs == 0) {
+      load_pre(4, 16, 12, IntC<4>{}, x);
+      vad = activate(tab, act_vadout, x[0]);
     }
-    wait_round();
-    load_pre(12, IntC<16>{}, x);
+    end_round();
+    // 5: denoise z
+    float zd[24];
+    run_round(IntC<5>{});
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      load_pre(5, 24, 12 * c, IntC<12>{}, x);
+#pragma unroll
+      for (int j = 0; j < 12; j++) zd[12 * c + j] = sigmoid_approx(tab, x[j]);
+    }
+    end_round();
+    // 6: denoise r -> r * h
+    run_round(IntC<6>{});
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      load_pre(6, 24, 12 * c, IntC<12>{}, x);
+      float rh[12];
+#pragma unroll
+      for (int j = 0; j < 12; j++) rh[j] = hd[12 * c + j] * sigmoid_approx(tab, x[j]);
+      store_act<12, 2>(lane_base, kPosDenR + 24 * hs + 12 * c, rh);
+    }
+    end_round();
+    // 7: denoise candidate -> denoise state
+    run_round(IntC<7>{});
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      load_pre(7, 24, 12 * c, IntC<12>{}, x);
+      activate_n<12>(tab, act_den, x, x);
+#pragma unroll
+      for (int j = 0; j < 12; j++) {
+        const float hnew = zd[12 * c + j] * hd[12 * c + j] + (1.f - zd[12 * c + j]) * x[j];
+        if (!sil) hd[12 * c + j] = hnew;
+      }
+      store_act<12, 2>(lane_base, kPosDenH + 24 * hs + 12 * c, hd + 12 * c);
+    }
+    end_round();
+    // 8: denoise_output -> band gains; g = max(g, 0.6 lastg)
+    run_round(IntC<8>{});
+    load_pre(8, 8, 0, IntC<8>{}, x);
+    activate_n<6>(tab, act_out, x, x);
     if (live) {
       float *rec = p.rec + ((long long)stream * p.chunk_cap + t) * kRecFloats;
 #pragma unroll
-      for (int j = 0; j < 11; j++) {
-        float graw = 0.f, g = 0.f;
-        if (!sil) {
-          graw = activate(tab, act_out, x[j]);
-          g = fmaxf(graw, .6f * lastg[j]);
-          lastg[j] = g;
+      for (int j = 0; j < 6; j++) {
+        if (6 * hs + j < kBands) {
+          float graw = 0.f, g = 0.f;
+          if (!sil) {
+            graw = x[j];
+            g = fmaxf(graw, .6f * lastg[j]);
+            lastg[j] = g;
+          }
+          rec[kRecGRaw + 6 * hs + j] = graw;
+          rec[kRecG + 6 * hs + j] = g;
         }
-        rec[kRecGRaw + 11 * hs + j] = graw;
-        rec[kRecG + 11 * hs + j] = g;
       }
       if (hs == 0) {
         const float v = sil ? 0.f : vad;
@@ -455,19 +446,21 @@ __device__ __forceinline__ void rnn_tc5_body(const Params &p, Smem &s) {
   if (live) {
     float *st = p.state + (long long)stream * kStateFloats;
 #pragma unroll
-    for (int j = 0; j < 12; j++) st[kStHVad + 12 * hs + j] = hv[j];
+    for (int j = 0; j < 6; j++) st[kStHVad + 6 * hs + j] = hv[j];
 #pragma unroll
-    for (int j = 0; j < 24; j++) st[kStHNoise + 24 * hs + j] = hn[j];
+    for (int j = 0; j < 12; j++) st[kStHNoise + 12 * hs + j] = hn[j];
 #pragma unroll
-    for (int j = 0; j < 48; j++) st[kStHDen + 48 * hs + j] = hd[j];
+    for (int j = 0; j < 24; j++) st[kStHDen + 24 * hs + j] = hd[j];
 #pragma unroll
-    for (int j = 0; j < 11; j++) st[kStLastG + 11 * hs + j] = lastg[j];
+    for (int j = 0; j < 6; j++)
+      if (6 * hs + j < kBands) st[kStLastG + 6 * hs + j] = lastg[j];
     if (err && tid == 0) reinterpret_cast<int *>(st)[kStFrameCount] = -1;  // poison the informational frame counter
   }
 #ifdef NS_TC5_CLOCKS
-  if (tid == 0 && blockIdx.x == 0)
-    printf("tc5 clocks per frame (thread 0): MMA issue %lld, wait for MMAs %lld, epilogue + stores + barrier %lld cycles\n",
-           tk_issue / p.n_frames, tk_wait / p.n_frames, tk_epi / p.n_frames);
+  if ((tid == 0 || tid == 480) && blockIdx.x == 0)
+    printf("tc5 cycles per frame (thread %d): issue %lld | wait for MMAs %lld | tcgen05.ld + bias %lld | activations + tcgen05.st %lld | "
+           "wait::st %lld | barrier %lld\n", tid, tk[0] / p.n_frames, tk[1] / p.n_frames, tk[2] / p.n_frames, tk[3] / p.n_frames,
+           tk[4] / p.n_frames, tk[5] / p.n_frames);
 #endif
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();

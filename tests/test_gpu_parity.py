@@ -81,6 +81,33 @@ def test_batch_matches_oracle_with_taps(oracle_model, model):
     assert flips == 0, "the pitch decision chain is computed bit-exactly (ns_pipe.cuh exactness contract)"
 
 
+@pytest.mark.parametrize("n_streams", [5, 128, 200])
+def test_tcgen05_recurrent_core_matches_oracle_and_mma_core(oracle_model, model, n_streams, monkeypatch):
+    """K4 on tcgen05 / tensor memory ($CRISPY_NS_RNN=tc5, ns_rnn_tc5.cuh): same tolerances against the oracle as the
+    warp-level core, band gains and VAD within 1e-4 of it, chunked calls with state carry bit-identical to one call
+    (ragged stream counts: one partly filled 128-stream CTA, exactly one, two)."""
+    n_frames = 72
+    x = make_signal(n_streams, n_frames)
+    res = {}
+    for sel in ("mma", "tc5"):
+        monkeypatch.setenv("CRISPY_NS_RNN", sel)
+        den = cb.BatchDenoiser(n_streams, model)
+        out, vad, taps = den.process_streams(_dev(x), unit_scale=False, return_taps=True)
+        res[sel] = (out.cpu().numpy(), vad.cpu().numpy(), taps.cpu().numpy())
+        if sel == "tc5":
+            den.reset()
+            a, va = den.process_streams(_dev(x[:, : 40 * 480]), unit_scale=False)
+            b, vb = den.process_streams(_dev(x[:, 40 * 480:]), unit_scale=False)
+            assert torch.equal(torch.cat([a, b], 1).cpu(), out.cpu()) and torch.equal(torch.cat([va, vb], 1).cpu(), vad.cpu())
+    k = min(n_streams, 6)
+    ref, rvad = po.process_streams(oracle_model, x[:k], n_threads=k)
+    r = assert_parity(ref, res["tc5"][0][:k], rvad, res["tc5"][1][:k], "tc5")
+    print("tcgen05 core parity", r)
+    assert np.abs(res["tc5"][1] - res["mma"][1]).max() <= 1e-4
+    assert np.abs(res["tc5"][2][:, :, 42:64] - res["mma"][2][:, :, 42:64]).max() <= 5e-4
+    assert np.array_equal(res["tc5"][2][:, :, 132], res["mma"][2][:, :, 132])  # pitch index: untouched by the core
+
+
 def test_golden_fixture(oracle_model, model):
     g = np.load(os.path.join(GOLDEN, "c1_head.npz"))
     x = g["x_i16"][None, :]

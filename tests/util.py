@@ -146,7 +146,7 @@ def adversarial_signals(n_frames: int) -> dict:
     return {k: v.astype(np.float32) for k, v in sigs.items()}
 
 
-BRANCH_EPS = 3e-5  # |Exp - g| below this: the pitch filter's branch is within float32 noise of flipping
+BRANCH_EPS = 1e-4  # |Exp - g| below this: the pitch filter's branch can flip between two implementations whose band gains agree to ~7e-5 (K4: bf16 hi+lo activations) and whose Exp agree to FFT rounding
 
 
 def long_run_parity(ref, out, rvad, vad, margin, what="") -> dict:
