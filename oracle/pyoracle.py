@@ -62,12 +62,37 @@ def build(force: bool = False) -> str:
 _NATIVE_PATH = os.path.join(_HERE, "librnnoise_oracle_native.so")
 
 
-def build_native() -> str:
-    """-O3 -march=native build of the same source for the CPU baseline.  Always rebuilt on the
-    machine that runs it (an -march=native object must not travel between hosts)."""
+def _host_stamp() -> str:
+    """Identifies the machine and the source a native build belongs to: CPU model + ISA flags + source mtime."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            cpu = "".join(l for l in f if l.startswith(("model name", "flags")) )[:20000]
+    except OSError:
+        cpu = "unknown"
     src = os.path.join(_HERE, "rnnoise_oracle.c")
+    return hashlib.sha1((cpu + str(os.path.getmtime(src))).encode()).hexdigest()
+
+
+def build_native(force: bool = True) -> str:
+    """-O3 -march=native build of the same source for the CPU baseline.  Rebuilt on every machine that runs it (an
+    -march=native object must not travel between hosts: the stamp file names the CPU and the source it was built
+    from, and a library with another stamp -- e.g. one that came along in a gpurun snapshot -- is rebuilt)."""
+    src = os.path.join(_HERE, "rnnoise_oracle.c")
+    stamp_path = _NATIVE_PATH + ".stamp"
+    stamp = _host_stamp()
+    if not force and os.path.exists(_NATIVE_PATH) and os.path.exists(stamp_path):
+        try:
+            if open(stamp_path).read().strip() == stamp:
+                return _NATIVE_PATH
+        except OSError:
+            pass
+    tmp = _NATIVE_PATH + f".{os.getpid()}.tmp"
     subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-ffp-contract=off", "-fno-fast-math",
-                           "-std=c11", "-shared", "-o", _NATIVE_PATH, src, "-lm", "-lpthread"])
+                           "-std=c11", "-shared", "-o", tmp, src, "-lm", "-lpthread"])
+    os.replace(tmp, _NATIVE_PATH)
+    with open(stamp_path, "w") as f:
+        f.write(stamp)
     return _NATIVE_PATH
 
 
@@ -79,8 +104,7 @@ def lib(native: bool = False) -> C.CDLL:
     global _lib
     if native:
         if "native" not in _libs:
-            if not os.path.exists(_NATIVE_PATH):
-                build_native()
+            build_native(force=False)
             _libs["native"] = _declare(C.CDLL(_NATIVE_PATH))
         return _libs["native"]
     if _lib is not None:
@@ -114,6 +138,8 @@ def _declare(L: C.CDLL) -> C.CDLL:
     L.rno_process_streams_trace.argtypes = [vp, f32p, f32p, f32p, C.c_int, C.c_int, C.c_long, C.c_long,
                                             C.c_uint, C.c_float, C.c_int, i32p, f32p, i32p, f32p]
     L.rno_set_sum_policy.argtypes = [C.c_int]
+    L.rno_set_pf_perturb.argtypes = [C.c_float, C.c_float]
+    L.rno_set_pf_perturb.restype = None
     L.rno_get_sum_policy.restype = C.c_int
     L.rno_linres_init.argtypes = [C.POINTER(LinRes), C.c_float, C.c_float]
     L.rno_linres_process.restype = C.c_size_t

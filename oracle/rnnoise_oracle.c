@@ -748,6 +748,15 @@ static void dct(float *out, const float *in) {
  * often a different but equally legitimate float32 order flips a discrete pitch decision (tests/test_oracle.py,
  * profiles/r2_parity.json): the decisions are bit-exact against the oracle's order only. */
 static int g_sum_policy = 0;
+/* Measurement aid (tests/tools only): perturb the pitch filter's inputs the way another float32 implementation
+ * would -- Exp relatively (Exp (1 + rel_exp)), the band gains in the logit domain (g + logit_g g (1 - g): what an error
+ * of logit_g in the output layer's pre-activation does) -- inside the pitch_filter call only, nothing that feeds the
+ * state.  Exposes the frames on which RNNoise's pitch filter is discontinuous (Exp > g ? 1 : ...). */
+static float g_pf_dexp = 0.f, g_pf_dg = 0.f;
+void rno_set_pf_perturb(float rel_exp, float logit_g) {
+  g_pf_dexp = rel_exp;
+  g_pf_dg = logit_g;
+}
 void rno_set_sum_policy(int policy) { g_sum_policy = policy < 0 ? 0 : (policy > 2 ? 2 : policy); }
 int rno_get_sum_policy(void) { return g_sum_policy; }
 
@@ -1316,7 +1325,16 @@ float rno_process_frame(rno_state *st, float *out, const float *in) {
   if (!silence) {
     compute_rnn(st, g, &vad_prob, features);
     memcpy(st->graw, g, sizeof(g));
-    pitch_filter(X, P, Ex, Ep, Exp, g);
+    if (g_pf_dexp != 0.f || g_pf_dg != 0.f) {
+      float Exp2[NB_BANDS], g2[NB_BANDS];
+      for (i = 0; i < NB_BANDS; i++) {
+        Exp2[i] = Exp[i] * (1.f + g_pf_dexp);
+        g2[i] = g[i] + g_pf_dg * g[i] * (1.f - g[i]);
+      }
+      pitch_filter(X, P, Ex, Ep, Exp2, g2);
+    } else {
+      pitch_filter(X, P, Ex, Ep, Exp, g);
+    }
     for (i = 0; i < NB_BANDS; i++) {
       float alpha = .6f;
       g[i] = fmaxf(g[i], alpha * st->lastg[i]);
@@ -1329,15 +1347,21 @@ float rno_process_frame(rno_state *st, float *out, const float *in) {
     }
   }
   frame_synthesis(st, out, X);
-  /* distance of the pitch filter's `Exp > g ? 1 : ...` branch from flipping: the smallest |Exp - g| over the bands
-   * whose gain is not negligible (the band's output scales with g, so a flip under g <= 1e-3 is inaudible and far
-   * below tolerance).  RNNoise is discontinuous there: where the margin is within float32 noise, two correct
-   * implementations differ. */
+  /* Distance of the pitch filter's `Exp > g ? 1 : ...` branch from flipping.  RNNoise is discontinuous there (r jumps
+   * to 1 from a value that is ~0 when g is small), at any magnitude: Exp = 2e-5 against g = 1e-5 takes the branch just
+   * like 0.8 against 0.7.  Two float32 implementations agree on Exp and g to ~1e-4 absolutely where they are of order
+   * one and to ~2e-3 RELATIVELY where they are tiny (a small sigmoid output carries the absolute error of its
+   * pre-activation as a relative error), so the margin of band b is |Exp - g| measured against
+   * min(1e-4, 2e-3 max(|Exp|, g)) and reported on the 1e-4 scale: margin = |Exp - g| max(1, 0.05 / max(|Exp|, g)).
+   * Only bands that reach the output count: those whose APPLIED gain max(g, 0.6 lastg) exceeds 1e-3 (a band the RNN
+   * has just switched off still plays at 0.6 of its previous gain). */
   st->branch_margin = 1e30f;
   if (!silence)
     for (i = 0; i < NB_BANDS; i++) {
       float d = (float)fabs(Exp[i] - st->graw[i]);
-      if (st->graw[i] > 1e-3f && d < st->branch_margin) st->branch_margin = d;
+      float scale = fmaxf((float)fabs(Exp[i]), st->graw[i]);
+      if (scale < .05f) d *= .05f / fmaxf(scale, 1e-30f);
+      if (g[i] > 1e-3f && d < st->branch_margin) st->branch_margin = d;
     }
   memcpy(st->dbg.features, features, sizeof(features));
   memcpy(st->dbg.gains, g, sizeof(g));

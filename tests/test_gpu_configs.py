@@ -24,7 +24,7 @@ import crispy_b200 as cb  # noqa: E402
 from crispy_b200.shard import stream_block  # noqa: E402
 from crispy_b200.synth import synth_chunk  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
-from tests.util import adversarial_signals, long_run_parity, parity_report, snr_db  # noqa: E402
+from tests.util import BRANCH_EPS, adversarial_signals, long_run_parity, parity_report, snr_db  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REPORT = os.environ.get("CRISPY_PARITY_REPORT", os.path.join(ROOT, "gpurun_out", "r2_parity.json"))
@@ -123,7 +123,7 @@ def test_c4_ten_minute_meetings_i16_in_app_dual_mono(oracle_model, model):
     r = long_run_parity(ref, o32, rvad, np.concatenate(vad_all, 1), rmargin, "c4 denoised f32")
     # the PCM16 mix against the reference's mixer/quantiser fed with the oracle's output: 1e-3 FS = 32.8 LSB + 1 LSB of
     # quantisation, outside the frames long_run_parity sets apart (RNNoise's own discontinuity, tests/util.py)
-    risky = rmargin < 3e-5
+    risky = rmargin < BRANCH_EPS
     risky[:, 1:] |= risky[:, :-1].copy()
     worst = 0
     for s in range(n):

@@ -336,3 +336,35 @@ def test_summation_policy_switch_and_decision_trace(oracle_model):
     po.build_native()
     on, vn = po.process_streams(oracle_model, x, n_threads=4, native=True)
     assert np.array_equal(on, o0) and np.array_equal(vn, v0)
+
+
+def test_branch_margin_names_the_frames_the_pitch_filter_makes_irreproducible(oracle_model):
+    """RNNoise's pitch filter is discontinuous at Exp == g (r jumps to 1).  With the pitch filter's inputs perturbed
+    the way another float32 implementation perturbs them (Exp by a relative 1e-5, the band gains by 1e-4 in the logit
+    domain; nothing that feeds the state), the output moves by ~1 % of full scale on a few frames and by < 1e-4 on all
+    others -- and the frames that move are inside the set the oracle's branch margin flags (with their successors:
+    overlap-add), which stays a fraction of a per cent.  This is the criterion the long-run GPU parity tests use
+    (tests/util.py long_run_parity); tools/pitch_filter_conditioning.py is the long version."""
+    import torch
+    from crispy_b200.synth import synth_chunk
+    from tests.util import BRANCH_EPS
+    n, nf = 4, 12000
+    x = torch.cat([synth_chunk(n, 6000 * 480, first_stream=2, start_sample=c * 6000 * 480) for c in range(nf // 6000)], 1).numpy()
+    ref, _, _, _, _, mg = po.process_streams_trace(oracle_model, x, unit_scale=True, n_threads=4, native=True, margin=True)
+    risky = mg < BRANCH_EPS
+    risky[:, 1:] |= risky[:, :-1].copy()
+    assert 0 < risky.mean() < 0.01
+    L = po.lib(True)
+    moved = 0
+    for d_exp, d_g in ((1e-5, -1e-4), (-1e-5, 1e-4)):
+        L.rno_set_pf_perturb(d_exp, d_g)
+        try:
+            out2 = po.process_streams_trace(oracle_model, x, unit_scale=True, n_threads=4, native=True)[0]
+        finally:
+            L.rno_set_pf_perturb(0.0, 0.0)
+        err = np.abs(out2.astype(np.float64) - ref).reshape(n, nf, 480).max(2)
+        assert err[~risky].max() <= 3e-4, (d_exp, d_g, err[~risky].max())
+        moved += int((err > 3e-4).sum())
+    again = po.process_streams_trace(oracle_model, x, unit_scale=True, n_threads=4, native=True)[0]
+    assert np.array_equal(again, ref)  # the hook is off again
+    print("frames moved by > 3e-4 FS under the perturbations:", moved, "flagged:", int(risky.sum()), "of", risky.size)
