@@ -86,7 +86,8 @@ constexpr int kDbgPitchGain = 130;
 constexpr int kDbgVad = 131;
 constexpr int kDbgPitchIndex = 132;  // stored as float
 constexpr int kDbgSilence = 133;
-constexpr int kDbgFloats = 136;
+constexpr int kDbgGRaw = 136;        // 22: band gains as the RNN emitted them (what the pitch filter compares Exp with)
+constexpr int kDbgFloats = 160;
 
 // ---- constant tables, generated on the host in f64 and copied to shared memory per CTA
 struct Tables {

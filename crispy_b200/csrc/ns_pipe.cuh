@@ -2472,6 +2472,7 @@ NS_DEV void synth_frame(const Grp &g, const Tab &T, const Params &p, SpecSmem &s
   if (p.dbg && !halo) {
     float *d = p.dbg + ((long long)stream * p.n_frames_call + p.frame0 + t) * kDbgFloats;
     if (g.tid < kBands) d[kDbgGains + g.tid] = rc[kRecG + g.tid];
+    if (g.tid < kBands) d[kDbgGRaw + g.tid] = rc[kRecGRaw + g.tid];
     if (g.tid == 0) {
       d[kDbgPitchGain] = rc[kRecPitchGain];
       d[kDbgVad] = rc[kRecVad];

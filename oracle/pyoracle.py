@@ -138,7 +138,7 @@ def _declare(L: C.CDLL) -> C.CDLL:
     L.rno_process_streams_trace.argtypes = [vp, f32p, f32p, f32p, C.c_int, C.c_int, C.c_long, C.c_long,
                                             C.c_uint, C.c_float, C.c_int, i32p, f32p, i32p, f32p]
     L.rno_set_sum_policy.argtypes = [C.c_int]
-    L.rno_set_pf_perturb.argtypes = [C.c_float, C.c_float]
+    L.rno_set_pf_perturb.argtypes = [C.c_float, C.c_float, C.c_float]
     L.rno_set_pf_perturb.restype = None
     L.rno_get_sum_policy.restype = C.c_int
     L.rno_linres_init.argtypes = [C.POINTER(LinRes), C.c_float, C.c_float]

@@ -749,13 +749,16 @@ static void dct(float *out, const float *in) {
  * profiles/r2_parity.json): the decisions are bit-exact against the oracle's order only. */
 static int g_sum_policy = 0;
 /* Measurement aid (tests/tools only): perturb the pitch filter's inputs the way another float32 implementation
- * would -- Exp relatively (Exp (1 + rel_exp)), the band gains in the logit domain (g + logit_g g (1 - g): what an error
+ * would -- Exp absolutely and relatively (Exp (1 + rel_exp) + abs_exp: a normalised correlation carries the rounding
+ * of a sum of positive and negative terms), the band gains in the logit domain (g + logit_g g (1 - g): what an error
  * of logit_g in the output layer's pre-activation does) -- inside the pitch_filter call only, nothing that feeds the
  * state.  Exposes the frames on which RNNoise's pitch filter is discontinuous (Exp > g ? 1 : ...). */
-static float g_pf_dexp = 0.f, g_pf_dg = 0.f;
-void rno_set_pf_perturb(float rel_exp, float logit_g) {
+static float g_pf_dexp = 0.f, g_pf_dg = 0.f, g_pf_aexp = 0.f;
+void rno_get_raw_gains(const rno_state *st, float *graw) { memcpy(graw, st->graw, sizeof(st->graw)); }
+void rno_set_pf_perturb(float rel_exp, float logit_g, float abs_exp) {
   g_pf_dexp = rel_exp;
   g_pf_dg = logit_g;
+  g_pf_aexp = abs_exp;
 }
 void rno_set_sum_policy(int policy) { g_sum_policy = policy < 0 ? 0 : (policy > 2 ? 2 : policy); }
 int rno_get_sum_policy(void) { return g_sum_policy; }
@@ -1325,10 +1328,10 @@ float rno_process_frame(rno_state *st, float *out, const float *in) {
   if (!silence) {
     compute_rnn(st, g, &vad_prob, features);
     memcpy(st->graw, g, sizeof(g));
-    if (g_pf_dexp != 0.f || g_pf_dg != 0.f) {
+    if (g_pf_dexp != 0.f || g_pf_dg != 0.f || g_pf_aexp != 0.f) {
       float Exp2[NB_BANDS], g2[NB_BANDS];
       for (i = 0; i < NB_BANDS; i++) {
-        Exp2[i] = Exp[i] * (1.f + g_pf_dexp);
+        Exp2[i] = Exp[i] * (1.f + g_pf_dexp) + g_pf_aexp;
         g2[i] = g[i] + g_pf_dg * g[i] * (1.f - g[i]);
       }
       pitch_filter(X, P, Ex, Ep, Exp2, g2);
@@ -1348,20 +1351,25 @@ float rno_process_frame(rno_state *st, float *out, const float *in) {
   }
   frame_synthesis(st, out, X);
   /* Distance of the pitch filter's `Exp > g ? 1 : ...` branch from flipping.  RNNoise is discontinuous there (r jumps
-   * to 1 from a value that is ~0 when g is small), at any magnitude: Exp = 2e-5 against g = 1e-5 takes the branch just
-   * like 0.8 against 0.7.  Two float32 implementations agree on Exp and g to ~1e-4 absolutely where they are of order
-   * one and to ~2e-3 RELATIVELY where they are tiny (a small sigmoid output carries the absolute error of its
-   * pre-activation as a relative error), so the margin of band b is |Exp - g| measured against
-   * min(1e-4, 2e-3 max(|Exp|, g)) and reported on the 1e-4 scale: margin = |Exp - g| max(1, 0.05 / max(|Exp|, g)).
-   * Only bands that reach the output count: those whose APPLIED gain max(g, 0.6 lastg) exceeds 1e-3 (a band the RNN
-   * has just switched off still plays at 0.6 of its previous gain). */
+   * to 1 from a value that is ~0 when g is small), at any magnitude: Exp = 3e-7 against g = 0 takes the branch just
+   * like 0.8 against 0.7.  Two float32 implementations agree on the two sides only up to their rounding noise:
+   *   Exp (a normalised sum of positive and negative terms): ~2e-6 absolutely + 1e-5 relatively;
+   *   g (a table sigmoid): the error of its pre-activation, ~4e-4, times g (1 - g) -- at most 1e-4, nothing where
+   *   the sigmoid saturates.
+   * margin of band b = |Exp - g| / noise_b, reported on the scale where 1e-4 means "within the noise".  Only bands
+   * that reach the output count: r is interpolated over the neighbouring bands' bins (interp_band_gain), so band b
+   * counts if the APPLIED gain max(g, 0.6 lastg) of b - 1, b or b + 1 exceeds 1e-3 (a band the RNN has just switched
+   * off still plays at 0.6 of its previous gain, and a muted band between two audible ones shapes their bins). */
   st->branch_margin = 1e30f;
   if (!silence)
     for (i = 0; i < NB_BANDS; i++) {
-      float d = (float)fabs(Exp[i] - st->graw[i]);
-      float scale = fmaxf((float)fabs(Exp[i]), st->graw[i]);
-      if (scale < .05f) d *= .05f / fmaxf(scale, 1e-30f);
-      if (g[i] > 1e-3f && d < st->branch_margin) st->branch_margin = d;
+      const float gr = st->graw[i];
+      const float noise = 2e-6f + 1e-5f * (float)fabs(Exp[i]) + 4e-4f * gr * (1.f - gr);
+      const float d = (float)fabs(Exp[i] - gr) * (1e-4f / noise);
+      float audible = g[i];
+      if (i > 0) audible = fmaxf(audible, g[i - 1]);
+      if (i + 1 < NB_BANDS) audible = fmaxf(audible, g[i + 1]);
+      if (audible > 1e-3f && d < st->branch_margin) st->branch_margin = d;
     }
   memcpy(st->dbg.features, features, sizeof(features));
   memcpy(st->dbg.gains, g, sizeof(g));

@@ -77,8 +77,8 @@ int rno_process_streams(const rno_model *m, const float *in, float *out, float *
 /* the same, additionally recording every frame's discrete decisions ([n_streams][n_frames] each, any may be
  * NULL): pitch_index and pitch gain out of remove_doubling, the silence gate, and branch_margin = how far the pitch
  * filter's discontinuous `Exp > g ? 1 : ...` branch is from flipping: the smallest |Exp[b] - g[b]| over the bands whose
- * applied gain exceeds 1e-3, on a scale where 1e-4 is what two float32 implementations can differ by (absolute where
- * Exp, g are of order one, relative where they are tiny: rnnoise_oracle.c rno_process_frame); 1e30 on silent frames */
+ * r reaches the output, in units of the rounding noise two float32 implementations carry on Exp and g, scaled so
+ * that 1e-4 means "within the noise" (rnnoise_oracle.c rno_process_frame); 1e30 on silent frames */
 int rno_process_streams_trace(const rno_model *m, const float *in, float *out, float *vad, int n_streams,
                               int n_frames, long in_stride, long out_stride, unsigned flags, float volume,
                               int n_threads, int32_t *pitch_index, float *pitch_gain, int32_t *silence,
@@ -89,8 +89,10 @@ int rno_process_streams_trace(const rno_model *m, const float *in, float *out, f
  * cross-correlation kernels.  Process-wide; set before any thread runs.  A measurement aid: see rnnoise_oracle.c. */
 void rno_set_sum_policy(int policy);
 int rno_get_sum_policy(void);
-/* Measurement aid: Exp (1 + rel_exp) and g + logit_g g (1 - g) inside the pitch_filter call only (0, 0 = off). */
-void rno_set_pf_perturb(float rel_exp, float logit_g);
+/* Measurement aid: Exp (1 + rel_exp) + abs_exp and g + logit_g g (1 - g) inside the pitch_filter call only (0, 0, 0 = off). */
+void rno_set_pf_perturb(float rel_exp, float logit_g, float abs_exp);
+/* the band gains of the last frame as the RNN produced them (before g = max(g, 0.6 lastg)): what pitch_filter compares Exp with */
+void rno_get_raw_gains(const rno_state *st, float *graw);
 
 /* ---- neighbouring rows ---- */
 /* a4: LinearResampler (audio.rs:73-134). Streaming; returns number of samples emitted. */

@@ -4,7 +4,7 @@ with the oracle alone (CPU), which frames that makes irreproducible between two 
 oracle's branch margin (rnnoise_oracle.c rno_process_frame) names exactly those frames:
 
   * the oracle runs a long synthetic recording twice, the second time with the pitch filter's inputs perturbed the way
-    another implementation would perturb them (Exp by a relative 1e-5, the band gains by 1e-4 in the logit domain;
+    another implementation would perturb them (Exp by 1e-6 and a relative 1e-5, the band gains by 1e-4 in the logit domain;
     rno_set_pf_perturb -- nothing that feeds the state is touched);
   * frames whose output moves by more than 3e-4 of full scale are listed against the margin.
 
@@ -32,12 +32,12 @@ ref, _, _, _, _, mg = po.process_streams_trace(m, x, unit_scale=True, n_threads=
 risky = mg < EPS
 risky[:, 1:] |= risky[:, :-1].copy()
 print(f"{n} streams x {minutes} min: {risky.mean() * 100:.3f} % of the frames within the branch margin (with successors)")
-for d_exp, d_g in ((1e-5, 0.0), (-1e-5, 0.0), (0.0, 1e-4), (0.0, -1e-4), (1e-5, -1e-4), (-1e-5, 1e-4)):
-    L.rno_set_pf_perturb(d_exp, d_g)
+for d_exp, d_g, a_exp in ((1e-5, 0.0, 0.0), (0.0, 0.0, 1e-6), (0.0, 0.0, -1e-6), (0.0, 1e-4, 0.0), (0.0, -1e-4, 0.0), (1e-5, -1e-4, 1e-6), (-1e-5, 1e-4, -1e-6)):
+    L.rno_set_pf_perturb(d_exp, d_g, a_exp)
     try:
         out2 = po.process_streams_trace(m, x, unit_scale=True, n_threads=os.cpu_count(), native=True)[0]
     finally:
-        L.rno_set_pf_perturb(0.0, 0.0)
+        L.rno_set_pf_perturb(0.0, 0.0, 0.0)
     err = np.abs(out2.astype(np.float64) - ref).reshape(n, nf, 480).max(2)
-    print(f"Exp (1 {d_exp:+g}), g {d_g:+g} g (1 - g): frames moved by > 1e-3 FS: {(err > 1e-3).sum()}, > 3e-4: {(err > 3e-4).sum()} "
+    print(f"Exp (1 {d_exp:+g}) {a_exp:+g}, g {d_g:+g} g (1 - g): frames moved by > 1e-3 FS: {(err > 1e-3).sum()}, > 3e-4: {(err > 3e-4).sum()} "
           f"(of them outside the margin set: {((err > 3e-4) & ~risky).sum()}); max {err.max():.2e} FS, outside the set {err[~risky].max():.2e}")
