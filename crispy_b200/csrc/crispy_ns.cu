@@ -393,8 +393,9 @@ static int run_device(crispy_ns_batch *b, const void *d_in, void *d_out, float *
                       float *d_taps, int n_frames, int64_t in_stride, int64_t out_stride,
                       int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume, cudaStream_t st,
                       const RunHooks *hooks = nullptr) {
-  if (!b || !d_in || !d_out || n_frames < 0) return fail(CRISPY_NS_EINVAL, "process_streams: bad argument");
-  if (n_frames == 0) return CRISPY_NS_OK;
+  if (!b || n_frames < 0) return fail(CRISPY_NS_EINVAL, "process_streams: bad argument");
+  if (n_frames == 0) return CRISPY_NS_OK;  // an empty call touches nothing (its pointers may be null)
+  if (!d_in || !d_out) return fail(CRISPY_NS_EINVAL, "process_streams: bad argument");
   if ((flags & CRISPY_NS_OUT_I16) && !(flags & CRISPY_NS_MIX_STEREO_I16) && volume != 1.0f)
     return fail(CRISPY_NS_EINVAL, "process_streams: CRISPY_NS_OUT_I16 is in 16-bit scale and takes no volume (use 1.0)");
   NS_CUDA(cudaSetDevice(b->device));
@@ -723,8 +724,9 @@ int process_streams_host(crispy_ns_batch *b, const void *h_in, void *h_out, floa
                                    const float *h_app, int n_frames, int64_t in_stride,
                                    int64_t out_stride, int64_t vad_stride, int64_t app_stride,
                                    uint32_t flags, float volume) {
-  if (!b || !h_in || !h_out || n_frames < 0) return fail(CRISPY_NS_EINVAL, "process_streams_host: bad argument");
-  if (n_frames == 0) return CRISPY_NS_OK;
+  if (!b || n_frames < 0) return fail(CRISPY_NS_EINVAL, "process_streams_host: bad argument");
+  if (n_frames == 0) return CRISPY_NS_OK;  // an empty call touches nothing (its pointers may be null)
+  if (!h_in || !h_out) return fail(CRISPY_NS_EINVAL, "process_streams_host: bad argument");
   NS_CUDA(cudaSetDevice(b->device));
   if (!b->s_in) {
     NS_CUDA(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
@@ -1498,7 +1500,7 @@ int multi_reset(crispy_ns_multi *m) {
 int multi_process_streams_host(crispy_ns_multi *m, const void *h_in, void *h_out, float *h_vad,
                                          const float *h_app, int n_frames, int64_t in_stride, int64_t out_stride,
                                          int64_t vad_stride, int64_t app_stride, uint32_t flags, float volume) {
-  if (!m || !h_in || !h_out || n_frames < 0) return fail(CRISPY_NS_EINVAL, "multi_process_streams_host: bad argument");
+  if (!m || n_frames < 0 || (n_frames > 0 && (!h_in || !h_out))) return fail(CRISPY_NS_EINVAL, "multi_process_streams_host: bad argument");
   const size_t nd = m->batch.size();
   const size_t ie = in_elem(flags), oe = out_elem(flags);
   std::vector<int> rc(nd, CRISPY_NS_OK);

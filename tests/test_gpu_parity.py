@@ -352,3 +352,46 @@ def test_full_size_properties(model):
     assert torch.equal(alt, out)
     # muted stretches (stream % 16 == 3, second half of every 4 s) come out as exact zeros after ring-out
     assert float(out[3, 350 * 480:400 * 480].abs().max()) < 1e-3
+
+
+def test_edge_cases_empty_single_frame_wide_batch_and_bad_arguments(oracle_model, model):
+    """Empty calls leave every state untouched; one frame of one stream; a batch far wider than the SM count (4,100
+    streams: partly filled 16- and 32-stream groups at the end) against the oracle on its first, a middle and its last
+    streams; DROP_FIRST_FRAME applies to the first call only (audio.rs:275-278); bad arguments come back as error
+    codes, never as exceptions through the C ABI."""
+    den = cb.BatchDenoiser(3, model)
+    x = _dev(make_signal(3, 20))
+    o0, v0 = den.process_streams(x[:, :0].contiguous(), unit_scale=False)
+    assert o0.shape == (3, 0) and v0.shape == (3, 0) and den.frames_done == 0
+    full, vfull = den.process_streams(x, unit_scale=False)
+    den.reset()
+    a, va = den.process_streams(x[:, :480].contiguous(), unit_scale=False)     # a single frame
+    den.process_streams(x[:, :0].contiguous(), unit_scale=False)               # an empty call in between
+    b, vb = den.process_streams(x[:, 480:].contiguous(), unit_scale=False)
+    assert torch.equal(torch.cat([a, b], 1), full) and torch.equal(torch.cat([va, vb], 1), vfull)
+    one = cb.BatchDenoiser(1, model)
+    xs = make_signal(1, 1)
+    o1, v1 = one.process_streams(_dev(xs), unit_scale=False)
+    ref, rvad = po.process_streams(oracle_model, xs)
+    assert_parity(ref, o1.cpu().numpy(), rvad, v1.cpu().numpy(), "one frame")
+    # drop_first_frame: the first call returns one frame less, later calls do not
+    den.reset()
+    d1, _ = den.process_streams(x[:, : 5 * 480].contiguous(), unit_scale=False, drop_first_frame=True)
+    d2, _ = den.process_streams(x[:, 5 * 480:].contiguous(), unit_scale=False, drop_first_frame=True)
+    assert d1.shape[1] == 4 * 480 and torch.equal(torch.cat([d1, d2], 1), full[:, 480:])
+    # wide batch
+    n_wide, nf = 4100, 12
+    xw = synth_chunk(n_wide, nf * 480, device="cuda")
+    wide = cb.BatchDenoiser(n_wide, model)
+    ow, vw = wide.process_streams(xw, unit_scale=True)
+    ids = [0, 1, 2047, 4095, 4096, 4099]
+    refw, rvw = po.process_streams(oracle_model, xw[ids].cpu().numpy(), unit_scale=True, n_threads=6)
+    err = np.abs(ow[ids].cpu().numpy().astype(np.float64) - refw).max()
+    assert err <= 1e-3 and np.abs(vw[ids].cpu().numpy() - rvw).max() <= 1e-3, err
+    # bad arguments
+    from crispy_b200 import _lib
+    L = _lib.lib()
+    assert L.crispy_ns_process_streams(None, None, None, None, None, 1, 480, 480, 1, 0, 0, 1.0, None) != 0
+    assert b"bad argument" in L.crispy_ns_last_error()
+    with pytest.raises(cb.CrispyNsError):
+        den.process_streams(x[:, :480].contiguous(), unit_scale=False, out_i16=True, volume=0.5)
