@@ -1,7 +1,7 @@
 """GPU vs oracle, band by band, at given frames of one synthetic stream (state carried from frame 0):
 the batch is synthesised exactly as tests/test_gpu_configs.py does (first_stream, n_streams, pieces of 100 frames: the
 noise draw depends on all three).
-usage: python scripts/debug/frame_compare.py <first_stream> <n_streams> <index in the batch> <frame> [more frames ...]"""
+usage: python tests/diag/frame_compare.py <first_stream> <n_streams> <index in the batch> <frame> [more frames ...]"""
 import ctypes as C
 import os
 import sys

@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """How brittle RNNoise's own pitch decisions are: the oracle against itself with the input scaled by 1 + 2^-20
 (a ~1e-6 relative perturbation, a few float32 ulps).  Counts the pitch-index flips and the frames whose output moves
-by more than 1e-3 of full scale.  CPU only.  usage: python tools/input_scale_sensitivity.py [minutes] [n_streams]"""
+by more than 1e-3 of full scale.  CPU only.  usage: python tests/diag/input_scale_sensitivity.py [minutes] [n_streams]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from crispy_b200.synth import synth_chunk  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402

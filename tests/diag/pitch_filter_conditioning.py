@@ -8,14 +8,14 @@ oracle's branch margin (rnnoise_oracle.c rno_process_frame) names exactly those 
     rno_set_pf_perturb -- nothing that feeds the state is touched);
   * frames whose output moves by more than 3e-4 of full scale are listed against the margin.
 
-usage: python tools/pitch_filter_conditioning.py [minutes] [n_streams] [first_stream]"""
+usage: python tests/diag/pitch_filter_conditioning.py [minutes] [n_streams] [first_stream]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from crispy_b200.synth import synth_chunk  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402

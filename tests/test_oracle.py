@@ -344,7 +344,7 @@ def test_branch_margin_names_the_frames_the_pitch_filter_makes_irreproducible(or
     logit domain; nothing that feeds the state), the output moves by ~1 % of full scale on a few frames and by < 1e-4 on all
     others -- and the frames that move are inside the set the oracle's branch margin flags (with their successors:
     overlap-add), which stays a fraction of a per cent.  This is the criterion the long-run GPU parity tests use
-    (tests/util.py long_run_parity); tools/pitch_filter_conditioning.py is the long version."""
+    (tests/util.py long_run_parity); tests/diag/pitch_filter_conditioning.py is the long version."""
     import torch
     from crispy_b200.synth import synth_chunk
     from tests.util import BRANCH_EPS

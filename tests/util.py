@@ -156,7 +156,7 @@ def long_run_parity(ref, out, rvad, vad, margin, what="") -> dict:
     0.9998 (mains hum), and the band still reaches the output at 0.6 of its previous gain.  Whether Exp > g holds is
     then decided by the last bits of an FFT butterfly or of the output layer's pre-activation -- two correct
     implementations differ by ~1 % of full scale in such a frame and, through the overlap-add, in the next one
-    (tools/pitch_filter_conditioning.py reproduces it with the oracle alone).  Frames whose
+    (tests/diag/pitch_filter_conditioning.py reproduces it with the oracle alone).  Frames whose
     oracle-side margin (rnnoise_oracle.c rno_process_frame: |Exp_b - g_b| against min(1e-4, 2e-3 max(|Exp_b|, g_b))
     over the audible bands) is below BRANCH_EPS, and their successors, are reported separately -- a few tenths of a
     per cent of the frames: everything else must meet north_star's max abs <= 1e-3 FS; SNR >= 60 dB and VAD within
