@@ -109,6 +109,23 @@ __global__ void ns_linear_resample_kernel(const float *__restrict__ in, float *_
 }
 
 
+// f2, app audio: resample_audio (recording.rs:13-39).  src_pos = i * ratio in f64, j = floor, frac = src_pos - j;
+// out[i] = s[j] + (s[j+1] - s[j]) * (frac as f32) without FMA contraction, or s[j] on the last sample.
+__global__ void ns_resample_audio_kernel(const float *__restrict__ in, float *__restrict__ out, long long n_in,
+                                         long long n_out, long long in_stride, long long out_stride, double ratio) {
+  const int s = blockIdx.y;
+  const float *src = in + (long long)s * in_stride;
+  float *dst = out + (long long)s * out_stride;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n_out;
+       n += (long long)gridDim.x * blockDim.x) {
+    const double pos = __dmul_rn((double)n, ratio);
+    const long long j = (long long)floor(pos);
+    const float frac = (float)(pos - (double)j);
+    const float s1 = src[j];
+    dst[n] = (j + 1 < n_in) ? __fadd_rn(s1, __fmul_rn(__fsub_rn(src[j + 1], s1), frac)) : s1;
+  }
+}
+
 // f2 (north_star item 4): windowed-sinc polyphase resampler.  out[n] = sum_k h[(n*M)%L][k] *
 // in[floor(n*M/L) - half + 1 + k].  A CTA covers T*Q consecutive outputs of one stream (T a multiple
 // of L, so thread t keeps one phase for all of its Q outputs and holds the tap h[k][phase] in a
@@ -1133,6 +1150,42 @@ int linear_resample(int device, const float *d_in, float *d_out, int n_streams, 
   if (gx > 148 * 8) gx = 148 * 8;
   dim3 grid(gx, n_streams);
   ns_linear_resample_kernel<<<grid, 256, 0, st>>>(d_in, d_out, d_idx, d_frac, n_out, in_stride, out_stride);
+  NS_CUDA(cudaGetLastError());
+  return CRISPY_NS_OK;
+}
+
+// ---- f2, app audio: resample_audio (recording.rs:13-39) ---------------------------------------------
+int64_t resample_audio_count(int64_t n_in, int from_rate, int to_rate) {
+  if (n_in <= 0 || from_rate < 1 || to_rate < 1) return 0;
+  if (from_rate == to_rate) return n_in;  // recording.rs:14-16
+  const double ratio = (double)from_rate / (double)to_rate;
+  int64_t n_out = (int64_t)ceil((double)n_in / ratio);  // recording.rs:19
+  // recording.rs:27-35 pushes nothing once floor(i * ratio) reaches the end of the input: trailing outputs only
+  while (n_out > 0 && (int64_t)floor((double)(n_out - 1) * ratio) >= n_in) n_out--;
+  return n_out;
+}
+int resample_audio(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in, int64_t in_stride,
+                   int64_t out_stride, int from_rate, int to_rate, void *cuda_stream) {
+  if (!d_in || !d_out || n_streams < 1 || n_in < 0 || from_rate < 1 || to_rate < 1)
+    return fail(CRISPY_NS_EINVAL, "resample_audio: bad argument");
+  const int ndev = device_count();
+  if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
+  if (n_streams > 65535) return fail(CRISPY_NS_EINVAL, "resample_audio: too many streams for one call");
+  NS_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (n_in == 0) return CRISPY_NS_OK;
+  if (from_rate == to_rate) {
+    NS_CUDA(cudaMemcpy2DAsync(d_out, (size_t)out_stride * 4, d_in, (size_t)in_stride * 4, (size_t)n_in * 4, n_streams,
+                              cudaMemcpyDeviceToDevice, st));
+    return CRISPY_NS_OK;
+  }
+  const int64_t n_out = resample_audio_count(n_in, from_rate, to_rate);
+  if (n_out == 0) return CRISPY_NS_OK;
+  int gx = (int)((n_out + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  ns_resample_audio_kernel<<<dim3(gx, n_streams), 256, 0, st>>>(d_in, d_out, n_in, n_out, in_stride, out_stride,
+                                                                (double)from_rate / (double)to_rate);
   NS_CUDA(cudaGetLastError());
   return CRISPY_NS_OK;
 }

@@ -156,6 +156,22 @@ def linear_resample(x, input_rate: float, output_rate: float):
     return out
 
 
+def resample_audio(x, from_rate: int, to_rate: int):
+    """recording.rs:13-39 on the device: the recorder's whole-buffer linear interpolator for captured app audio
+    (what reaches the dual-mono mix beside the denoised microphone).  x: CUDA float32 [n_streams, n_in]."""
+    import torch
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise CrispyNsError("resample_audio needs a CUDA float32 [n_streams, n_in] tensor")
+    n_streams, n_in = x.shape
+    n_out = int(_lib.lib().crispy_ns_resample_audio_count(n_in, int(from_rate), int(to_rate)))
+    out = torch.empty((n_streams, n_out), dtype=torch.float32, device=x.device)
+    if n_streams and n_out:
+        check(_lib.lib().crispy_ns_resample_audio(x.device.index or 0, x.data_ptr(), out.data_ptr(), n_streams, n_in,
+                                                  x.stride(0), out.stride(0), int(from_rate), int(to_rate),
+                                                  torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
 def sinc_resample(x, input_rate: int, output_rate: int, sinc_len: int = 256, f_cutoff: float = 0.95):
     """Batched windowed-sinc resampler on the GPU (north_star item 4: the rubato-equivalent
     44.1 -> 48 kHz front end; rubato 0.16.2 pinned at Cargo.lock:4166).  x is a CUDA f32 tensor

@@ -166,6 +166,16 @@ int crispy_ns_linear_resample(int device, const float *d_in, float *d_out, int n
                               int64_t in_stride, int64_t out_stride, float input_rate,
                               float output_rate, void *cuda_stream);
 
+/* ---- f2, the app-audio side: resample_audio (recording.rs:13-39), the whole-buffer linear interpolator the recorder
+ * applies to captured app audio before it is mixed with the denoised microphone (recording.rs:356-360):
+ * ratio = from_rate / to_rate in f64, out[i] = s[j] + (s[j + 1] - s[j]) * (frac as f32) with j = floor(i * ratio),
+ * the last sample repeated where j + 1 runs off the end.  Data-parallel and bit-identical on the device (the
+ * position of every output is one f64 multiply).  n_out = crispy_ns_resample_audio_count; equal rates copy. */
+int64_t crispy_ns_resample_audio_count(int64_t n_in, int from_rate, int to_rate);
+int crispy_ns_resample_audio(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
+                             int64_t in_stride, int64_t out_stride, int from_rate, int to_rate,
+                             void *cuda_stream);
+
 /* ---- f2 (BASELINE.json north_star item 4, configs[2]): windowed-sinc 44.1 -> 48 kHz front end,
  * "rubato-equivalent".  The reference's own front end on this path is the linear interpolator above;
  * rubato 0.16.2 (Cargo.lock:4166) is in its tree ahead of transcription

@@ -141,6 +141,8 @@ def _declare(L: C.CDLL) -> C.CDLL:
     L.rno_set_pf_perturb.argtypes = [C.c_float, C.c_float, C.c_float]
     L.rno_set_pf_perturb.restype = None
     L.rno_get_sum_policy.restype = C.c_int
+    L.rno_resample_audio.restype = C.c_size_t
+    L.rno_resample_audio.argtypes = [f32p, C.c_size_t, C.c_size_t, C.c_size_t, f32p, C.c_size_t]
     L.rno_linres_init.argtypes = [C.POINTER(LinRes), C.c_float, C.c_float]
     L.rno_linres_process.restype = C.c_size_t
     L.rno_linres_process.argtypes = [C.POINTER(LinRes), f32p, C.c_size_t, f32p, C.c_size_t]
@@ -273,6 +275,15 @@ def process_streams_trace(model: Model, x: np.ndarray, unit_scale: bool = False,
     if margin:  # + the smallest |Exp - g| over the bands per frame: distance of the pitch filter's branch from flipping
         return out, vad, pi, pg, sil, mg
     return out, vad, pi, pg, sil
+
+
+def resample_audio(x: np.ndarray, from_rate: int, to_rate: int) -> np.ndarray:
+    """recording.rs:13-39 (the recorder's app-audio resampler) on one buffer."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n = lib().rno_resample_audio(_fp(x), x.shape[0], from_rate, to_rate, None, 0)
+    out = np.zeros(n, dtype=np.float32)
+    lib().rno_resample_audio(_fp(x), x.shape[0], from_rate, to_rate, _fp(out), n)
+    return out
 
 
 def debug_trace(model: Model, x: np.ndarray):

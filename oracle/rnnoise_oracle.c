@@ -1487,6 +1487,38 @@ void rno_linres_init(rno_linres *r, float input_rate, float output_rate) {
   r->next_output_pos = 0.0;
 }
 
+/* f2, app audio: resample_audio (recording.rs:13-39), the recorder's whole-buffer linear interpolator for captured
+ * app audio (recording.rs:356-360).  Line by line: ratio = from / to in f64; output_len = ceil(len / ratio); for
+ * every i: src_pos = i * ratio, src_index = floor, frac = src_pos - src_index; two-sample interpolation with
+ * `frac as f32`, the last sample alone where src_index + 1 runs off the end, nothing beyond.  Returns the number of
+ * samples produced (all of them are written if out_cap allows). */
+size_t rno_resample_audio(const float *samples, size_t len, size_t from_rate, size_t to_rate, float *out, size_t out_cap) {
+  size_t i, k = 0, output_len;
+  double ratio;
+  if (from_rate == to_rate) { /* recording.rs:14-16 */
+    for (i = 0; i < len; i++)
+      if (i < out_cap) out[i] = samples[i];
+    return len;
+  }
+  ratio = (double)from_rate / (double)to_rate;          /* recording.rs:18 */
+  output_len = (size_t)ceil((double)len / ratio);       /* recording.rs:19 */
+  for (i = 0; i < output_len; i++) {
+    double src_pos = (double)i * ratio;                 /* recording.rs:23 */
+    size_t src_index = (size_t)floor(src_pos);
+    double frac = src_pos - (double)src_index;
+    if (src_index + 1 < len) {                          /* recording.rs:27-31 */
+      float sample1 = samples[src_index], sample2 = samples[src_index + 1];
+      float o = sample1 + (sample2 - sample1) * (float)frac;
+      if (k < out_cap) out[k] = o;
+      k++;
+    } else if (src_index < len) {                       /* recording.rs:32-35 */
+      if (k < out_cap) out[k] = samples[src_index];
+      k++;
+    }
+  }
+  return k;
+}
+
 size_t rno_linres_process(rno_linres *r, const float *in, size_t n_in, float *out, size_t out_cap) {
   size_t n, k = 0;
   for (n = 0; n < n_in; n++) {

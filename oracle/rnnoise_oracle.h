@@ -95,6 +95,9 @@ void rno_set_pf_perturb(float rel_exp, float logit_g, float abs_exp);
 void rno_get_raw_gains(const rno_state *st, float *graw);
 
 /* ---- neighbouring rows ---- */
+/* f2, app audio: resample_audio (recording.rs:13-39); returns the number of samples produced */
+size_t rno_resample_audio(const float *samples, size_t len, size_t from_rate, size_t to_rate, float *out, size_t out_cap);
+
 /* a4: LinearResampler (audio.rs:73-134). Streaming; returns number of samples emitted. */
 typedef struct rno_linres {
   float input_rate, output_rate, last_sample;

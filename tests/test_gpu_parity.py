@@ -395,3 +395,28 @@ def test_edge_cases_empty_single_frame_wide_batch_and_bad_arguments(oracle_model
     assert b"bad argument" in L.crispy_ns_last_error()
     with pytest.raises(cb.CrispyNsError):
         den.process_streams(x[:, :480].contiguous(), unit_scale=False, out_i16=True, volume=0.5)
+
+
+def test_resample_audio_is_bit_exact():  # recording.rs:13-39: the recorder's app-audio resampler
+    rng = np.random.default_rng(11)
+    for n, fr, to in ((1, 44100, 48000), (2, 44100, 48000), (441, 44100, 48000), (44101, 44100, 48000), (4800, 48000, 44100),
+                      (1000, 16000, 48000), (999, 48000, 16000), (777, 48000, 48000)):
+        x = rng.standard_normal((3, n)).astype(np.float32)
+        got = cb.resample_audio(_dev(x), fr, to).cpu().numpy()
+        for s in range(3):
+            want = po.resample_audio(x[s], fr, to)
+            assert got[s].shape == want.shape and np.array_equal(got[s], want), (n, fr, to, s)
+    # rows longer than the resampled span, odd element offset (strided, unaligned input)
+    big = torch.from_numpy(rng.standard_normal((4, 50003)).astype(np.float32)).cuda()
+    view = big[:, 1:44102]
+    got = cb.resample_audio(view, 44100, 48000).cpu().numpy()
+    assert np.array_equal(got[2], po.resample_audio(view[2].cpu().numpy(), 44100, 48000))
+    # configs[3] with a 44.1 kHz app source: resample_audio -> the dual-mono mix beside the denoised microphone
+    nf = 20
+    mic = synth_chunk(2, nf * 480, device="cuda")
+    app44 = synth_chunk(2, nf * 441, first_stream=9, device="cuda") * 0.5
+    app = cb.resample_audio(app44, 44100, 48000)
+    assert app.shape[1] == nf * 480
+    den = cb.BatchDenoiser(2, cb.Model.synthetic(0))
+    mix, _ = den.process_streams((mic * 32767.0).round().clamp(-32768, 32767).to(torch.int16), unit_scale=True, app=app, mix_stereo_i16=True)
+    assert mix.shape == (2, nf * 480, 2) and torch.equal(mix[:, :, 0], mix[:, :, 1])

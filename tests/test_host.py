@@ -135,3 +135,13 @@ def test_sinc_front_end_geometry_and_argument_checks():  # no device needed: val
     assert b"window" in L.crispy_ns_last_error()
     assert L.crispy_ns_sinc_resample(0, fake, fake, 1, 441, 441, 480, 44100, 48000, 7, 0.0, None) == -1  # odd sinc_len
 
+
+
+def test_resample_audio_count_matches_the_oracle():  # recording.rs:19, :27-35; host arithmetic only
+    import numpy as np
+    from oracle import pyoracle as po
+    L = _lib.lib()
+    for n, fr, to in ((0, 44100, 48000), (1, 44100, 48000), (441, 44100, 48000), (44101, 44100, 48000), (4800, 48000, 44100),
+                      (999, 48000, 16000), (1000, 16000, 48000), (777, 48000, 48000), (12345, 22050, 48000), (7, 8000, 48000)):
+        assert L.crispy_ns_resample_audio_count(n, fr, to) == len(po.resample_audio(np.zeros(n, np.float32), fr, to)), (n, fr, to)
+    assert L.crispy_ns_resample_audio_count(100, 0, 48000) == 0

@@ -368,3 +368,37 @@ def test_branch_margin_names_the_frames_the_pitch_filter_makes_irreproducible(or
     again = po.process_streams_trace(oracle_model, x, unit_scale=True, n_threads=4, native=True)[0]
     assert np.array_equal(again, ref)  # the hook is off again
     print("frames moved by > 3e-4 FS under the perturbations:", moved, "flagged:", int(risky.sum()), "of", risky.size)
+
+
+def _np_resample_audio(x, from_rate, to_rate):
+    """recording.rs:13-39 transliterated with NumPy (f64 positions, f32 samples), independent of the C oracle."""
+    x = np.asarray(x, np.float32)
+    if from_rate == to_rate:
+        return x.copy()
+    ratio = np.float64(from_rate) / np.float64(to_rate)
+    n_out = int(np.ceil(np.float64(len(x)) / ratio))
+    pos = np.arange(n_out, dtype=np.float64) * ratio
+    idx = np.floor(pos).astype(np.int64)
+    frac = (pos - idx).astype(np.float32)
+    keep = idx < len(x)
+    idx, frac = idx[keep], frac[keep]
+    nxt = np.minimum(idx + 1, len(x) - 1)
+    two = idx + 1 < len(x)
+    out = x[idx] + (x[nxt] - x[idx]) * frac
+    return np.where(two, out, x[idx]).astype(np.float32)
+
+
+def test_resample_audio_follows_the_recorder():  # recording.rs:13-39 (app audio ahead of the dual-mono mix)
+    rng = np.random.default_rng(7)
+    for n, fr, to in ((0, 44100, 48000), (1, 44100, 48000), (2, 44100, 48000), (441, 44100, 48000), (44101, 44100, 48000),
+                      (4800, 48000, 44100), (1000, 16000, 48000), (999, 48000, 16000), (777, 48000, 48000), (12345, 22050, 48000)):
+        x = rng.standard_normal(n).astype(np.float32)
+        got, want = po.resample_audio(x, fr, to), _np_resample_audio(x, fr, to)
+        assert got.shape == want.shape and np.array_equal(got, want), (n, fr, to)
+    # known answers: identical rates copy; a ramp stays a ramp of slope from/to; 441 samples make one 480-sample frame
+    x = np.arange(100, dtype=np.float32)
+    assert np.array_equal(po.resample_audio(x, 48000, 48000), x)
+    y = po.resample_audio(x, 44100, 48000)
+    assert len(y) == int(np.ceil(100 / (44100 / 48000))) and np.allclose(y[:-1], np.arange(len(y) - 1) * (44100 / 48000), atol=1e-4)
+    assert y[-1] == x[-1]  # the last output sits on the last sample alone (recording.rs:32-35)
+    assert len(po.resample_audio(np.zeros(441, np.float32), 44100, 48000)) == 480
