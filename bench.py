@@ -442,7 +442,8 @@ def run_b200(args):
         x44[:, :n_cp].copy_(x[:, :n_cp])  # any signal will do: the kernels are data-independent
         front_end = {"input": f"{n_streams} streams x {fe_secs} s at 44.1 kHz -> 48 kHz, device-resident, kernel alone"}
         for name, fn, flops in (("sinc256", lambda: cb.sinc_resample(x44, 44100, 48000), 2 * 256),
-                                ("linear", lambda: cb.linear_resample(x44, 44100.0, 48000.0), 3)):
+                                ("linear", lambda: cb.linear_resample(x44, 44100.0, 48000.0), 3),
+                                ("resample_audio", lambda: cb.resample_audio(x44, 44100, 48000), 3)):
             for _ in range(3):
                 y48 = fn()
             torch.cuda.synchronize(dev)
@@ -458,8 +459,32 @@ def run_b200(args):
             front_end[name] = {"ms_per_launch": sec * 1e3, "stream_seconds_per_s": n_streams * fe_secs / sec,
                                "hbm_algorithmic_gbs": n_streams * (x44.shape[1] + n_out) * 4 / sec / 1e9,
                                "fp32_tflops": n_streams * n_out * flops / sec / 1e12}
+        # the capture callbacks' downmix (audio.rs:754-755 / :816-818): stereo in, mono out -- the one kernel of the
+        # library that IS bound by HBM (12 / 8 bytes per frame, one add and one divide)
+        for name, dt, bpf in (("downmix_stereo_f32", torch.float32, 12), ("downmix_stereo_i16", torch.int16, 8)):
+            n_fr = 48000 * fe_secs
+            st2 = torch.zeros((n_streams, 2 * n_fr), dtype=dt, device=dev)
+            for _ in range(3):
+                mono = cb.downmix_mono(st2, 2)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record()
+            for _ in range(reps):
+                mono = cb.downmix_mono(st2, 2)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            sec = e0.elapsed_time(e1) / 1e3 / reps
+            front_end[name] = {"ms_per_launch": sec * 1e3, "stream_seconds_per_s": n_streams * fe_secs / sec,
+                               "hbm_algorithmic_gbs": n_streams * n_fr * bpf / sec / 1e9,
+                               "frac_hbm": n_streams * n_fr * bpf / sec / 1e9 / measured_peaks()[0],
+                               "bytes_per_launch": n_streams * n_fr * bpf,
+                               "note": "peak = the driver's copy-measured HBM figure (1 read : 1 write); this kernel reads 2 bytes "
+                                       "for every byte it writes, so it can sit above that figure and below the 7.7 TB/s nominal"}
+            del st2, mono
         front_end["sinc256"]["frac_fp32_measured"] = front_end["sinc256"]["fp32_tflops"] / fp32["ffma_tflops"]
         front_end["linear"]["frac_hbm"] = front_end["linear"]["hbm_algorithmic_gbs"] / measured_peaks()[0]
+        front_end["resample_audio"]["frac_hbm"] = front_end["resample_audio"]["hbm_algorithmic_gbs"] / measured_peaks()[0]
         del y48
         # ---- the other BASELINE.json configs on the same streams, 10 s each, device-resident (rank 0) ----
         def timed(fn, reps=2):

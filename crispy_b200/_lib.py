@@ -26,7 +26,7 @@ SYMBOLS = [
     "crispy_ns_debug_floats", "crispy_ns_batch_state_size", "crispy_ns_batch_save_state",
     "crispy_ns_batch_load_state", "crispy_ns_batch_info", "crispy_ns_batch_destroy",
     "crispy_ns_host_alloc", "crispy_ns_host_free", "crispy_ns_linear_resample_count",
-    "crispy_ns_linear_resample", "crispy_ns_resample_audio_count", "crispy_ns_resample_audio", "crispy_ns_sinc_resample_count", "crispy_ns_sinc_resample", "crispy_ns_sinc_resample_needed", "crispy_ns_sinc_resample_chunk",
+    "crispy_ns_linear_resample", "crispy_ns_resample_audio_count", "crispy_ns_resample_audio", "crispy_ns_downmix_mono", "crispy_ns_sinc_resample_count", "crispy_ns_sinc_resample", "crispy_ns_sinc_resample_needed", "crispy_ns_sinc_resample_chunk",
     "crispy_ns_resample_host",
     "crispy_ns_wav_write_pcm16", "crispy_ns_wav_read_pcm16",
     "crispy_ns_kernel_count", "crispy_ns_kernel_name", "crispy_ns_batch_profile", "crispy_ns_batch_profile_read",
@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
     L.crispy_ns_linear_resample_count.argtypes = [f32, f32, i64]
     L.crispy_ns_linear_resample_count.restype = i64
     L.crispy_ns_linear_resample.argtypes = [C.c_int, vp, vp, C.c_int, i64, i64, i64, f32, f32, vp]
+    L.crispy_ns_downmix_mono.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, i64, i64, i64, vp]
     L.crispy_ns_resample_audio_count.argtypes = [i64, C.c_int, C.c_int]
     L.crispy_ns_resample_audio_count.restype = i64
     L.crispy_ns_resample_audio.argtypes = [C.c_int, vp, vp, C.c_int, i64, i64, i64, C.c_int, C.c_int, vp]

@@ -94,35 +94,123 @@ __global__ void __launch_bounds__(ns::kGroupThreads, NS_SYN_MINB) ns_synthesis_k
 
 // a4/f2: out[s][n] = in[s][idx[n]-1] + (in[s][idx[n]] - in[s][idx[n]-1]) * frac[n], no FMA
 // contraction so the result is bit-identical to LinearResampler::process_sample (audio.rs:125-129).
-__global__ void ns_linear_resample_kernel(const float *__restrict__ in, float *__restrict__ out,
-                                          const int32_t *__restrict__ idx, const float *__restrict__ frac,
-                                          long long n_out, long long in_stride, long long out_stride) {
+__global__ void __launch_bounds__(256) ns_linear_resample_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                                 const int32_t *__restrict__ idx, const float *__restrict__ frac,
+                                                                 long long n_out, long long in_stride, long long out_stride,
+                                                                 int vec_store) {
+  // four consecutive outputs per thread and trip (their (index, fraction) entries are one 16-byte load each; the table
+  // is shared by every stream and stays in L2), a CTA covers one contiguous tile of a row
   const int s = blockIdx.y;
   const float *src = in + (long long)s * in_stride;
   float *dst = out + (long long)s * out_stride;
-  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n_out;
-       n += (long long)gridDim.x * blockDim.x) {
-    const int i = idx[n];
-    const float last = src[i - 1], cur = src[i];
-    dst[n] = __fadd_rn(last, __fmul_rn(__fsub_rn(cur, last), frac[n]));
+  for (long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; n < n_out;
+       n += (long long)gridDim.x * blockDim.x * 4) {
+    if (n + 4 <= n_out) {
+      const int4 i4 = __ldg(reinterpret_cast<const int4 *>(idx + n));
+      const float4 f4v = __ldg(reinterpret_cast<const float4 *>(frac + n));
+      const float l0 = src[i4.x - 1], c0 = src[i4.x], l1 = src[i4.y - 1], c1 = src[i4.y], l2 = src[i4.z - 1], c2 = src[i4.z],
+                  l3 = src[i4.w - 1], c3 = src[i4.w];
+      const float o0 = __fadd_rn(l0, __fmul_rn(__fsub_rn(c0, l0), f4v.x)), o1 = __fadd_rn(l1, __fmul_rn(__fsub_rn(c1, l1), f4v.y)),
+                  o2 = __fadd_rn(l2, __fmul_rn(__fsub_rn(c2, l2), f4v.z)), o3 = __fadd_rn(l3, __fmul_rn(__fsub_rn(c3, l3), f4v.w));
+      if (vec_store) {
+        *reinterpret_cast<float4 *>(dst + n) = make_float4(o0, o1, o2, o3);
+      } else {
+        dst[n] = o0, dst[n + 1] = o1, dst[n + 2] = o2, dst[n + 3] = o3;
+      }
+    } else {
+      for (long long m = n; m < n_out; m++) {
+        const int i = idx[m];
+        const float last = src[i - 1], cur = src[i];
+        dst[m] = __fadd_rn(last, __fmul_rn(__fsub_rn(cur, last), frac[m]));
+      }
+    }
   }
 }
 
+// The capture callbacks' downmix (audio.rs:754-755, :816-818, :879-884): mono = sum over the frame's channels, in
+// channel order, of the sample brought to unit scale, divided by the channel count; f32 adds, IEEE division.
+template <typename T>
+__device__ __forceinline__ float ns_unit_sample(T v);
+template <>
+__device__ __forceinline__ float ns_unit_sample<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float ns_unit_sample<int16_t>(int16_t v) { return __fmul_rn((float)v, 1.0f / 32768.0f); }  // a power of two: the same value as the division
+template <>
+__device__ __forceinline__ float ns_unit_sample<uint16_t>(uint16_t v) { return __fmul_rn(__fsub_rn((float)v, 32768.0f), 1.0f / 32768.0f); }
+template <typename T>  // any channel count, any alignment: one frame per thread and trip
+__global__ void __launch_bounds__(256) ns_downmix_kernel(const T *__restrict__ in, float *__restrict__ out, int n_channels,
+                                                         long long n_frames, long long in_stride, long long out_stride) {
+  const T *src = in + (long long)blockIdx.y * in_stride;
+  float *dst = out + (long long)blockIdx.y * out_stride;
+  const float div = (float)n_channels;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n_frames; n += (long long)gridDim.x * blockDim.x) {
+    const T *f = src + n * n_channels;
+    float sum = 0.f;
+    for (int c = 0; c < n_channels; c++) sum = __fadd_rn(sum, ns_unit_sample<T>(f[c]));
+    dst[n] = __fdiv_rn(sum, div);
+  }
+}
+// Stereo, 16-byte aligned rows: a thread turns 32 bytes of interleaved input (two 16-byte loads: 4 f32 frames or 8
+// PCM16 frames) into 16 or 32 bytes of output per trip, kDownmixTrips trips in flight per thread; a CTA covers one
+// contiguous tile of a row, so every warp reads and writes whole 128-byte lines.  The kernel is bound by HBM.
+constexpr int kDownmixTrips = 4;
+template <typename T>
+__global__ void __launch_bounds__(256) ns_downmix_stereo_kernel(const T *__restrict__ in, float *__restrict__ out, long long n_frames,
+                                                                long long in_stride, long long out_stride) {
+  constexpr int FR = 16 / (int)sizeof(T);  // frames per thread and trip: 4 (f32) or 8 (PCM16)
+  const T *src = in + (long long)blockIdx.y * in_stride;
+  float *dst = out + (long long)blockIdx.y * out_stride;
+  const long long tile0 = (long long)blockIdx.x * (256 * FR * kDownmixTrips);
+  uint4 raw[kDownmixTrips][2];
+#pragma unroll
+  for (int u = 0; u < kDownmixTrips; u++) {  // all loads first
+    const long long n = tile0 + ((long long)u * 256 + threadIdx.x) * FR;
+    if (n + FR <= n_frames) {
+      const uint4 *q = reinterpret_cast<const uint4 *>(src + 2 * n);
+      raw[u][0] = __ldg(q);
+      raw[u][1] = __ldg(q + 1);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kDownmixTrips; u++) {
+    const long long n = tile0 + ((long long)u * 256 + threadIdx.x) * FR;
+    if (n + FR <= n_frames) {
+      const T *v = reinterpret_cast<const T *>(&raw[u][0]);
+      float o[FR];
+#pragma unroll
+      for (int k = 0; k < FR; k++)
+        o[k] = __fmul_rn(__fadd_rn(__fadd_rn(0.f, ns_unit_sample<T>(v[2 * k])), ns_unit_sample<T>(v[2 * k + 1])), .5f);  // / 2, exactly
+#pragma unroll
+      for (int k = 0; k < FR; k += 4) *reinterpret_cast<float4 *>(dst + n + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+    } else {
+      for (long long m = n; m < n_frames; m++)  // the row's last, partial vector
+        dst[m] = __fmul_rn(__fadd_rn(__fadd_rn(0.f, ns_unit_sample<T>(src[2 * m])), ns_unit_sample<T>(src[2 * m + 1])), .5f);
+    }
+  }
+}
 
 // f2, app audio: resample_audio (recording.rs:13-39).  src_pos = i * ratio in f64, j = floor, frac = src_pos - j;
 // out[i] = s[j] + (s[j+1] - s[j]) * (frac as f32) without FMA contraction, or s[j] on the last sample.
-__global__ void ns_resample_audio_kernel(const float *__restrict__ in, float *__restrict__ out, long long n_in,
-                                         long long n_out, long long in_stride, long long out_stride, double ratio) {
+__global__ void __launch_bounds__(256) ns_resample_audio_kernel(const float *__restrict__ in, float *__restrict__ out, long long n_in,
+                                                                long long n_out, long long in_stride, long long out_stride, double ratio,
+                                                                int vec_store) {
   const int s = blockIdx.y;
   const float *src = in + (long long)s * in_stride;
   float *dst = out + (long long)s * out_stride;
-  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n_out;
-       n += (long long)gridDim.x * blockDim.x) {
+  auto one = [&](long long n) -> float {
     const double pos = __dmul_rn((double)n, ratio);
     const long long j = (long long)floor(pos);
     const float frac = (float)(pos - (double)j);
     const float s1 = src[j];
-    dst[n] = (j + 1 < n_in) ? __fadd_rn(s1, __fmul_rn(__fsub_rn(src[j + 1], s1), frac)) : s1;
+    return (j + 1 < n_in) ? __fadd_rn(s1, __fmul_rn(__fsub_rn(src[j + 1], s1), frac)) : s1;
+  };
+  for (long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; n < n_out;
+       n += (long long)gridDim.x * blockDim.x * 4) {
+    if (n + 4 <= n_out && vec_store) {
+      *reinterpret_cast<float4 *>(dst + n) = make_float4(one(n), one(n + 1), one(n + 2), one(n + 3));
+    } else {
+      for (long long m = n; m < n_out && m < n + 4; m++) dst[m] = one(m);
+    }
   }
 }
 
@@ -1082,9 +1170,26 @@ int64_t linear_resample_count(float input_rate, float output_rate, int64_t n_in)
   if (n_in <= 0) return 0;
   const float d = input_rate - output_rate;
   if ((d < 0 ? -d : d) < 1.0f) return n_in;
+  // the count comes out of the same f64 replay as the table; remembered per (rates, n_in) so that asking for it
+  // before every call does not replay a whole recording's positions on the host each time
+  static std::mutex mu;
+  static std::map<std::tuple<uint32_t, uint32_t, int64_t>, int64_t> counts;
+  uint32_t ri, ro;
+  memcpy(&ri, &input_rate, 4);
+  memcpy(&ro, &output_rate, 4);
+  const auto key = std::make_tuple(ri, ro, n_in);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = counts.find(key);
+    if (it != counts.end()) return it->second;
+  }
   ResampleTable t;
   build_resample_table(input_rate, output_rate, n_in, t);
-  return (int64_t)t.idx.size();
+  const int64_t n = (int64_t)t.idx.size();
+  std::lock_guard<std::mutex> lk(mu);
+  if (counts.size() >= 256) counts.clear();
+  counts[key] = n;
+  return n;
 }
 int linear_resample(int device, const float *d_in, float *d_out, int n_streams, int64_t n_in,
                               int64_t in_stride, int64_t out_stride, float input_rate,
@@ -1146,11 +1251,53 @@ int linear_resample(int device, const float *d_in, float *d_out, int n_streams, 
     n_out = it->second.n_out;
   }
   if (n_out == 0) return CRISPY_NS_OK;
-  int gx = (int)((n_out + 255) / 256);
-  if (gx > 148 * 8) gx = 148 * 8;
+  int gx = (int)((n_out + 4095) / 4096);  // 256 threads x 4 outputs x 4 trips per CTA
+  if (gx < 1) gx = 1;
   dim3 grid(gx, n_streams);
-  ns_linear_resample_kernel<<<grid, 256, 0, st>>>(d_in, d_out, d_idx, d_frac, n_out, in_stride, out_stride);
+  const int vec_store = ((uintptr_t)d_out % 16) == 0 && (out_stride % 4) == 0;
+  ns_linear_resample_kernel<<<grid, 256, 0, st>>>(d_in, d_out, d_idx, d_frac, n_out, in_stride, out_stride, vec_store);
   NS_CUDA(cudaGetLastError());
+  return CRISPY_NS_OK;
+}
+
+// ---- the capture callbacks' downmix to mono (audio.rs:754-755, :816-818, :879-884) ---------------------
+template <typename T>
+static int downmix_launch(const void *d_in, int n_channels, float *d_out, int n_streams, int64_t n_frames, int64_t in_stride,
+                          int64_t out_stride, cudaStream_t st) {
+  const T *in = static_cast<const T *>(d_in);
+  const bool vec_ok = n_channels == 2 && ((uintptr_t)d_in % 16) == 0 && ((uintptr_t)d_out % 16) == 0 &&
+                      ((in_stride * (int64_t)sizeof(T)) % 16) == 0 && (out_stride % 4) == 0;
+  if (vec_ok) {
+    constexpr int64_t tile = 256 * (16 / (int64_t)sizeof(T)) * kDownmixTrips;
+    const int64_t gx = (n_frames + tile - 1) / tile;
+    if (gx > 0x7fffffffll) return CRISPY_NS_EINVAL;
+    ns_downmix_stereo_kernel<T><<<dim3((unsigned)gx, n_streams), 256, 0, st>>>(in, d_out, n_frames, in_stride, out_stride);
+  } else {
+    int gx = (int)((n_frames + 255) / 256);
+    if (gx > 148 * 16) gx = 148 * 16;
+    ns_downmix_kernel<T><<<dim3(gx, n_streams), 256, 0, st>>>(in, d_out, n_channels, n_frames, in_stride, out_stride);
+  }
+  return cudaGetLastError() == cudaSuccess ? CRISPY_NS_OK : CRISPY_NS_ECUDA;
+}
+int downmix_mono(int device, const void *d_in, int sample_format, int n_channels, float *d_out, int n_streams,
+                 int64_t n_frames, int64_t in_stride, int64_t out_stride, void *cuda_stream) {
+  if (n_streams < 1 || n_frames < 0 || n_channels < 1 || n_channels > 64 || sample_format < 0 || sample_format > 2)
+    return fail(CRISPY_NS_EINVAL, "downmix_mono: bad argument");
+  if (n_frames == 0) return CRISPY_NS_OK;
+  if (!d_in || !d_out || n_streams > 65535) return fail(CRISPY_NS_EINVAL, "downmix_mono: bad argument");
+  const int ndev = device_count();
+  if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
+  NS_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int rc;
+  if (sample_format == CRISPY_NS_FMT_F32)
+    rc = downmix_launch<float>(d_in, n_channels, d_out, n_streams, n_frames, in_stride, out_stride, st);
+  else if (sample_format == CRISPY_NS_FMT_I16)
+    rc = downmix_launch<int16_t>(d_in, n_channels, d_out, n_streams, n_frames, in_stride, out_stride, st);
+  else
+    rc = downmix_launch<uint16_t>(d_in, n_channels, d_out, n_streams, n_frames, in_stride, out_stride, st);
+  if (rc != CRISPY_NS_OK) return fail(CRISPY_NS_ECUDA, "downmix_mono: kernel launch failed");
   return CRISPY_NS_OK;
 }
 
@@ -1182,10 +1329,10 @@ int resample_audio(int device, const float *d_in, float *d_out, int n_streams, i
   }
   const int64_t n_out = resample_audio_count(n_in, from_rate, to_rate);
   if (n_out == 0) return CRISPY_NS_OK;
-  int gx = (int)((n_out + 255) / 256);
-  if (gx > 148 * 8) gx = 148 * 8;
+  int gx = (int)((n_out + 4095) / 4096);  // 256 threads x 4 outputs x 4 trips per CTA
+  const int vec_store = ((uintptr_t)d_out % 16) == 0 && (out_stride % 4) == 0;
   ns_resample_audio_kernel<<<dim3(gx, n_streams), 256, 0, st>>>(d_in, d_out, n_in, n_out, in_stride, out_stride,
-                                                                (double)from_rate / (double)to_rate);
+                                                                (double)from_rate / (double)to_rate, vec_store);
   NS_CUDA(cudaGetLastError());
   return CRISPY_NS_OK;
 }

@@ -156,6 +156,22 @@ def linear_resample(x, input_rate: float, output_rate: float):
     return out
 
 
+def downmix_mono(x, n_channels: int):
+    """The capture callbacks' downmix (audio.rs:754-755, :816-818, :879-884) on the device.  x: CUDA tensor
+    [n_streams, n_frames * n_channels] of interleaved float32, int16 or uint16 samples -> float32 [n_streams, n_frames]."""
+    import torch
+    fmts = {torch.float32: 0, torch.int16: 1, torch.uint16: 2}
+    if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1 or x.dtype not in fmts or n_channels < 1:
+        raise CrispyNsError("downmix_mono needs a CUDA [n_streams, n_frames * n_channels] tensor of float32, int16 or uint16")
+    n_streams, n_frames = x.shape[0], x.shape[1] // int(n_channels)
+    out = torch.empty((n_streams, n_frames), dtype=torch.float32, device=x.device)
+    if n_streams and n_frames:
+        check(_lib.lib().crispy_ns_downmix_mono(x.device.index or 0, x.data_ptr(), fmts[x.dtype], int(n_channels), out.data_ptr(),
+                                                n_streams, n_frames, x.stride(0), out.stride(0),
+                                                torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
 def resample_audio(x, from_rate: int, to_rate: int):
     """recording.rs:13-39 on the device: the recorder's whole-buffer linear interpolator for captured app audio
     (what reaches the dual-mono mix beside the denoised microphone).  x: CUDA float32 [n_streams, n_in]."""

@@ -166,6 +166,16 @@ int crispy_ns_linear_resample(int device, const float *d_in, float *d_out, int n
                               int64_t in_stride, int64_t out_stride, float input_rate,
                               float output_rate, void *cuda_stream);
 
+/* ---- the caller's side of the path: the capture callbacks downmix interleaved device frames to mono before
+ * RnnNoiseProcessor::push_sample sees them -- f32: sum(frame) / channels (audio.rs:754-755); i16: sum(s / 32768) /
+ * channels (audio.rs:816-818); u16: sum((s - 32768) / 32768) / channels (audio.rs:879-884); f32 sums in channel
+ * order.  One kernel, bit-identical, bound by HBM.  d_in: [n_streams][n_frames * n_channels] interleaved samples of
+ * sample_format (strides in elements), d_out: [n_streams][n_frames] f32 unit scale. */
+enum { CRISPY_NS_FMT_F32 = 0, CRISPY_NS_FMT_I16 = 1, CRISPY_NS_FMT_U16 = 2 };
+int crispy_ns_downmix_mono(int device, const void *d_in, int sample_format, int n_channels, float *d_out,
+                           int n_streams, int64_t n_frames, int64_t in_stride, int64_t out_stride,
+                           void *cuda_stream);
+
 /* ---- f2, the app-audio side: resample_audio (recording.rs:13-39), the whole-buffer linear interpolator the recorder
  * applies to captured app audio before it is mixed with the denoised microphone (recording.rs:356-360):
  * ratio = from_rate / to_rate in f64, out[i] = s[j] + (s[j + 1] - s[j]) * (frac as f32) with j = floor(i * ratio),

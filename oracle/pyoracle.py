@@ -141,6 +141,8 @@ def _declare(L: C.CDLL) -> C.CDLL:
     L.rno_set_pf_perturb.argtypes = [C.c_float, C.c_float, C.c_float]
     L.rno_set_pf_perturb.restype = None
     L.rno_get_sum_policy.restype = C.c_int
+    L.rno_downmix_mono.restype = None
+    L.rno_downmix_mono.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, f32p]
     L.rno_resample_audio.restype = C.c_size_t
     L.rno_resample_audio.argtypes = [f32p, C.c_size_t, C.c_size_t, C.c_size_t, f32p, C.c_size_t]
     L.rno_linres_init.argtypes = [C.POINTER(LinRes), C.c_float, C.c_float]
@@ -275,6 +277,16 @@ def process_streams_trace(model: Model, x: np.ndarray, unit_scale: bool = False,
     if margin:  # + the smallest |Exp - g| over the bands per frame: distance of the pitch filter's branch from flipping
         return out, vad, pi, pg, sil, mg
     return out, vad, pi, pg, sil
+
+
+def downmix_mono(x: np.ndarray, n_channels: int) -> np.ndarray:
+    """audio.rs:754-755 / :816-818 / :879-884 on one interleaved buffer (float32, int16 or uint16)."""
+    fmt = {np.dtype(np.float32): 0, np.dtype(np.int16): 1, np.dtype(np.uint16): 2}[x.dtype]
+    x = np.ascontiguousarray(x)
+    n = x.shape[0] // n_channels
+    out = np.zeros(n, dtype=np.float32)
+    lib().rno_downmix_mono(x.ctypes.data_as(C.c_void_p), fmt, n_channels, n, _fp(out))
+    return out
 
 
 def resample_audio(x: np.ndarray, from_rate: int, to_rate: int) -> np.ndarray:

@@ -1487,6 +1487,30 @@ void rno_linres_init(rno_linres *r, float input_rate, float output_rate) {
   r->next_output_pos = 0.0;
 }
 
+/* The capture callbacks' downmix to mono (audio.rs:754-755 f32, :816-818 i16, :879-884 u16): per interleaved frame,
+ * the f32 sum in channel order of the samples brought to unit scale, divided by the channel count.  (Rust's
+ * `iter().sum::<f32>()` folds from zero; whether that zero is +0.0 or -0.0 depends on the toolchain and only shows in
+ * the sign of an all-negative-zero frame.)  fmt: 0 f32, 1 i16, 2 u16. */
+void rno_downmix_mono(const void *in, int fmt, int n_channels, size_t n_frames, float *out) {
+  size_t n;
+  int c;
+  for (n = 0; n < n_frames; n++) {
+    float sum = 0.f;
+    for (c = 0; c < n_channels; c++) {
+      size_t k = n * (size_t)n_channels + (size_t)c;
+      float v;
+      if (fmt == 0)
+        v = ((const float *)in)[k];
+      else if (fmt == 1)
+        v = (float)((const int16_t *)in)[k] / 32768.0f;
+      else
+        v = ((float)((const uint16_t *)in)[k] - 32768.0f) / 32768.0f;
+      sum = sum + v;
+    }
+    out[n] = sum / (float)n_channels;
+  }
+}
+
 /* f2, app audio: resample_audio (recording.rs:13-39), the recorder's whole-buffer linear interpolator for captured
  * app audio (recording.rs:356-360).  Line by line: ratio = from / to in f64; output_len = ceil(len / ratio); for
  * every i: src_pos = i * ratio, src_index = floor, frac = src_pos - src_index; two-sample interpolation with

@@ -95,6 +95,9 @@ void rno_set_pf_perturb(float rel_exp, float logit_g, float abs_exp);
 void rno_get_raw_gains(const rno_state *st, float *graw);
 
 /* ---- neighbouring rows ---- */
+/* capture callbacks' downmix to mono (audio.rs:754-755, :816-818, :879-884); fmt 0 f32, 1 i16, 2 u16 */
+void rno_downmix_mono(const void *in, int fmt, int n_channels, size_t n_frames, float *out);
+
 /* f2, app audio: resample_audio (recording.rs:13-39); returns the number of samples produced */
 size_t rno_resample_audio(const float *samples, size_t len, size_t from_rate, size_t to_rate, float *out, size_t out_cap);
 

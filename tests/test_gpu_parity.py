@@ -420,3 +420,31 @@ def test_resample_audio_is_bit_exact():  # recording.rs:13-39: the recorder's ap
     den = cb.BatchDenoiser(2, cb.Model.synthetic(0))
     mix, _ = den.process_streams((mic * 32767.0).round().clamp(-32768, 32767).to(torch.int16), unit_scale=True, app=app, mix_stereo_i16=True)
     assert mix.shape == (2, nf * 480, 2) and torch.equal(mix[:, :, 0], mix[:, :, 1])
+
+
+def test_downmix_mono_is_bit_exact():  # audio.rs:754-755, :816-818, :879-884: what the capture callbacks hand to push_sample
+    rng = np.random.default_rng(5)
+    n = 1003
+    for ch in (1, 2, 3, 6):
+        for dt in (np.float32, np.int16, np.uint16):
+            if dt == np.float32:
+                x = rng.standard_normal((3, n * ch)).astype(np.float32)
+            elif dt == np.int16:
+                x = rng.integers(-32768, 32768, (3, n * ch)).astype(np.int16)
+            else:
+                x = rng.integers(0, 65536, (3, n * ch)).astype(np.uint16)
+            got = cb.downmix_mono(torch.from_numpy(x).cuda(), ch).cpu().numpy()
+            for s in range(3):
+                assert np.array_equal(got[s], po.downmix_mono(x[s], ch)), (ch, dt, s)
+    # a stereo row that starts on an odd element: the scalar path
+    x = rng.standard_normal((2, 2 * n + 1)).astype(np.float32)
+    got = cb.downmix_mono(torch.from_numpy(x).cuda()[:, 1:], 2).cpu().numpy()
+    assert np.array_equal(got[1], po.downmix_mono(x[1, 1:], 2))
+    # stereo PCM16 capture -> mono -> denoise: the batched form of the i16 callback feeding push_sample
+    nf = 12
+    st = (synth_chunk(2, nf * 480, device="cuda") * 32767.0).round().clamp(-32768, 32767).to(torch.int16)
+    stereo = torch.stack([st, st], 2).reshape(2, -1).contiguous()
+    mono = cb.downmix_mono(stereo, 2)
+    assert torch.equal(mono, (st.to(torch.float32) / 32768.0 + st.to(torch.float32) / 32768.0) / 2.0)
+    out, _ = cb.BatchDenoiser(2, cb.Model.synthetic(0)).process_streams(mono, unit_scale=True)
+    assert out.shape == mono.shape and bool(torch.isfinite(out).all())

@@ -402,3 +402,25 @@ def test_resample_audio_follows_the_recorder():  # recording.rs:13-39 (app audio
     assert len(y) == int(np.ceil(100 / (44100 / 48000))) and np.allclose(y[:-1], np.arange(len(y) - 1) * (44100 / 48000), atol=1e-4)
     assert y[-1] == x[-1]  # the last output sits on the last sample alone (recording.rs:32-35)
     assert len(po.resample_audio(np.zeros(441, np.float32), 44100, 48000)) == 480
+
+
+def test_downmix_mono_follows_the_capture_callbacks():  # audio.rs:754-755 (f32), :816-818 (i16), :879-884 (u16)
+    rng = np.random.default_rng(3)
+    for ch in (1, 2, 3, 6):
+        xf = rng.standard_normal(50 * ch).astype(np.float32)
+        want = np.zeros(50, np.float32)
+        for c in range(ch):  # the f32 sum in channel order, from zero
+            want = (want + xf[c::ch]).astype(np.float32)
+        assert np.array_equal(po.downmix_mono(xf, ch), (want / np.float32(ch)).astype(np.float32))
+        xi = rng.integers(-32768, 32768, 50 * ch).astype(np.int16)
+        want = np.zeros(50, np.float32)
+        for c in range(ch):
+            want = (want + xi[c::ch].astype(np.float32) / np.float32(32768.0)).astype(np.float32)
+        assert np.array_equal(po.downmix_mono(xi, ch), (want / np.float32(ch)).astype(np.float32))
+        xu = rng.integers(0, 65536, 50 * ch).astype(np.uint16)
+        want = np.zeros(50, np.float32)
+        for c in range(ch):
+            want = (want + (xu[c::ch].astype(np.float32) - np.float32(32768.0)) / np.float32(32768.0)).astype(np.float32)
+        assert np.array_equal(po.downmix_mono(xu, ch), (want / np.float32(ch)).astype(np.float32))
+    assert po.downmix_mono(np.array([32767, 32767], np.int16), 2)[0] == np.float32(32767 / 32768)
+    assert po.downmix_mono(np.array([0, 65535], np.uint16), 2)[0] == np.float32(-1 / 65536)
