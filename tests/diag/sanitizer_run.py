@@ -35,6 +35,11 @@ y = cb.sinc_resample(x44, 44100, 48000)
 y2 = cb.linear_resample(x44, 44100.0, 48000.0)
 den = cb.BatchDenoiser(5, model)
 den.process_streams(x44[:, : 441 * 20].contiguous(), unit_scale=True, input_rate=44100, front_end="sinc")
+ya = cb.resample_audio(x44, 44100, 48000)
+ya2 = cb.resample_audio(x44[:, 1:4412], 44100, 48000)   # strided rows, scalar stores
+st16 = (torch.randn((3, 2 * 4001), device="cuda") * 8000).to(torch.int16)
+for ch, t in ((2, x44[:, :8000]), (2, st16[:, :8000]), (2, st16[:, 1:]), (3, x44[:, :9000]), (1, x44[:, :77])):
+    cb.downmix_mono(t, ch)
 hx = x.cpu().pin_memory()
 den = cb.BatchDenoiser(n, model)
 ho, hv = den.process_streams_host(hx, unit_scale=True)
