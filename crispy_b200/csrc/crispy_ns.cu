@@ -261,6 +261,88 @@ __global__ void __launch_bounds__(1024) ns_sinc_resample_kernel(const float *__r
   }
 }
 
+// Second generation for upsampling ratios with 2/3 <= M/L < 1 (44.1 -> 48 kHz: 147/160).  The first kernel reads one
+// input sample from shared memory per multiply-add, which caps it at a quarter of the FMA rate (it measures 20 %).
+// Here a thread owns FOUR ADJACENT outputs u = 4t .. 4t + 3 of a period (and Q periods of them): adjacent outputs look at
+// windows that start 0 or 1 sample apart, so sweeping over the INPUT index lets one staged sample feed all four --
+// output r meets sample i with its tap k = i - d_r, d_r = window start of r minus that of output 0 (d_r is r or r - 1).
+// The taps come from a table laid out in OUTPUT order, hs[k][u] = h[k][(u M) mod L], so the four taps of row k are one
+// 16-byte load; row i - d_r is the row loaded d_r steps ago, kept in a four-deep register delay line, and the choice
+// between "r steps ago" and "r - 1 steps ago" is one select per r and step (not per period).  Per step: Q 4-byte
+// shared-memory loads + one 16-byte table load for 4 Q multiply-adds.  Every output still accumulates
+// fmaf(h[k], x[start + k], acc) in ascending k: bit-identical to the first kernel and to the oracle's scalar loop.
+template <int Q>
+__global__ void __launch_bounds__(256) ns_sinc_resample4_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                                const float *__restrict__ hs,  // [sinc_len][L], output order
+                                                                long long n_total, long long in_first, long long in_end,
+                                                                long long first_out, long long n_out, long long in_stride,
+                                                                long long out_stride, int L, int M, int sinc_len, int span,
+                                                                int vec_store) {
+  extern __shared__ float xs[];
+  const int T = blockDim.x, t = threadIdx.x;
+  const long long tile = (long long)T * 4 * Q;
+  const long long n0 = first_out + (long long)blockIdx.x * tile;  // multiple of L
+  const long long base0 = n0 / L * M - sinc_len / 2 + 1;          // recording index of xs[0]
+  const float *src = in + (long long)blockIdx.y * in_stride - in_first;
+  for (int i = t; i < span; i += T) {
+    const long long g = base0 + i;
+    xs[i] = (g >= in_first && g < in_end) ? __ldg(src + g) : 0.f;
+  }
+  __syncthreads();
+  const int pos0 = 4 * t * M;                 // 4 t < 1024, M < L <= 1024
+  const int rb0 = pos0 / L;
+  const bool f1 = (pos0 + M) / L - rb0 == 1, f2 = (pos0 + 2 * M) / L - rb0 == 2, f3 = (pos0 + 3 * M) / L - rb0 == 3;
+  const int d1 = f1 ? 1 : 0, d2 = f2 ? 2 : 1, d3 = f3 ? 3 : 2;
+  const int step = T * 4 / L * M;             // input samples between two periods of this thread
+  const float4 *hrow = reinterpret_cast<const float4 *>(hs + (4 * t) % L);
+  const int lrow = L / 4;
+  float acc[4][Q];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int q = 0; q < Q; q++) acc[r][q] = 0.f;
+  const float *xp = xs + rb0;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 h0 = z4, h1 = z4, h2 = z4, h3 = z4;  // rows i, i - 1, i - 2, i - 3
+  // prologue (i = 0, 1, 2: taps with negative index do not exist) and epilogue (i = sinc_len .. sinc_len + 2: taps past
+  // the last do not exist) carry predicates; the main loop needs none
+  auto step_fn = [&](int i, bool edge) {
+    h3 = h2, h2 = h1, h1 = h0;
+    h0 = (i < sinc_len) ? __ldg(hrow + (long long)i * lrow) : z4;
+    const float t0 = h0.x, t1 = f1 ? h1.y : h0.y, t2 = f2 ? h2.z : h1.z, t3 = f3 ? h3.w : h2.w;
+    const bool v0 = !edge || i < sinc_len, v1 = !edge || (unsigned)(i - d1) < (unsigned)sinc_len,
+               v2 = !edge || (unsigned)(i - d2) < (unsigned)sinc_len, v3 = !edge || (unsigned)(i - d3) < (unsigned)sinc_len;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      const float x = xp[q * step + i];
+      if (v0) acc[0][q] = fmaf(t0, x, acc[0][q]);
+      if (v1) acc[1][q] = fmaf(t1, x, acc[1][q]);
+      if (v2) acc[2][q] = fmaf(t2, x, acc[2][q]);
+      if (v3) acc[3][q] = fmaf(t3, x, acc[3][q]);
+    }
+  };
+  step_fn(0, true);
+  step_fn(1, true);
+  step_fn(2, true);
+#pragma unroll 4
+  for (int i = 3; i < sinc_len; i++) step_fn(i, false);
+  step_fn(sinc_len, true);
+  step_fn(sinc_len + 1, true);
+  step_fn(sinc_len + 2, true);
+  float *dst = out + (long long)blockIdx.y * out_stride;
+#pragma unroll
+  for (int q = 0; q < Q; q++) {
+    const long long n = n0 + (long long)q * T * 4 + 4 * t - first_out;
+    if (vec_store && n + 4 <= n_out) {
+      *reinterpret_cast<float4 *>(dst + n) = make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+        if (n + r < n_out) dst[n + r] = acc[r][q];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
@@ -1352,6 +1434,7 @@ struct SincKey {
 };
 std::mutex g_sinc_mu;
 std::map<SincKey, float *> g_sinc_tables;  // device copies, [sinc_len][L]; live until process exit
+std::map<SincKey, float *> g_sinc_tables_out_order;  // the same taps with the columns in output order (ns_sinc_resample4_kernel)
 
 int reduce_ratio(int input_rate, int output_rate, int *L, int *M) {
   if (input_rate < 1 || output_rate < 1) return 0;
@@ -1461,6 +1544,49 @@ int sinc_resample_chunk(int device, const float *d_in, int64_t in_first, int64_t
       g_sinc_tables[key] = d_taps;
     } else {
       d_taps = it->second;
+    }
+  }
+  // samples of the recording the kernel may read: the caller's window, clipped to the recording
+  const long long in_end_all = (in_first + n_in < n_total) ? in_first + n_in : n_total;
+  if (n_streams > 65535) return fail(CRISPY_NS_EINVAL, "sinc_resample: too large for one call");
+  // second-generation kernel: four adjacent outputs per thread (2/3 <= M/L < 1, L a multiple of 4)
+  if (M < L && 3 * (long long)M >= 2 * (long long)L && L % 4 == 0 && !getenv("CRISPY_NS_SINC_V1")) {
+    const int unit = L / 4;                       // T * 4 must be a multiple of L
+    int T = unit * ((160 + unit - 1) / unit);
+    if (T <= 256) {
+      constexpr int Q = 8;
+      const long long tile = (long long)T * 4 * Q;
+      const long long span = tile / L * M + sinc_len + 4;
+      const size_t smem = (size_t)span * sizeof(float);
+      const long long tiles = (n_out + tile - 1) / tile;
+      if (smem <= 96 * 1024 && tiles <= 0x7fffffffll) {
+        float *d_taps4 = nullptr;
+        {
+          std::lock_guard<std::mutex> lk(g_sinc_mu);
+          const SincKey key{device, L, M, sinc_len, f_cutoff};
+          auto it = g_sinc_tables_out_order.find(key);
+          if (it == g_sinc_tables_out_order.end()) {
+            std::vector<float> taps, taps4;
+            sinc_taps_transposed(L, M, sinc_len, f_cutoff, taps);
+            taps4.resize(taps.size());
+            for (int k = 0; k < sinc_len; k++)
+              for (int u = 0; u < L; u++) taps4[(size_t)k * L + u] = taps[(size_t)k * L + (size_t)(((long long)u * M) % L)];
+            NS_CUDA(cudaMalloc((void **)&d_taps4, taps4.size() * sizeof(float)));
+            NS_CUDA(cudaMemcpy(d_taps4, taps4.data(), taps4.size() * sizeof(float), cudaMemcpyHostToDevice));
+            g_sinc_tables_out_order[key] = d_taps4;
+          } else {
+            d_taps4 = it->second;
+          }
+        }
+        if (smem > 48 * 1024)
+          NS_CUDA(cudaFuncSetAttribute(ns_sinc_resample4_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int vec_store = ((uintptr_t)d_out % 16) == 0 && (out_stride % 4) == 0;
+        ns_sinc_resample4_kernel<Q><<<dim3((unsigned)tiles, (unsigned)n_streams), T, smem, st>>>(
+            d_in, d_out, d_taps4, n_total, in_first, in_end_all, first_out, n_out, in_stride, out_stride, L, M, sinc_len, (int)span,
+            vec_store);
+        NS_CUDA(cudaGetLastError());
+        return CRISPY_NS_OK;
+      }
     }
   }
   // threads: a multiple of L near 160-256; outputs per thread Q in {8, 4, 2, 1} so the staged span fits

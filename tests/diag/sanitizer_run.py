@@ -32,6 +32,11 @@ for sel in ("mma", "tc5"):
 os.environ.pop("CRISPY_NS_RNN")
 x44 = synth_chunk(5, 44100 // 10 * 3, device="cuda")
 y = cb.sinc_resample(x44, 44100, 48000)
+os.environ["CRISPY_NS_SINC_V1"] = "1"
+y1 = cb.sinc_resample(x44, 44100, 48000)
+os.environ.pop("CRISPY_NS_SINC_V1")
+assert torch.equal(y, y1)
+y3 = cb.sinc_resample(x44[:, 1:4412], 44100, 48000)  # odd rows: scalar stores
 y2 = cb.linear_resample(x44, 44100.0, 48000.0)
 den = cb.BatchDenoiser(5, model)
 den.process_streams(x44[:, : 441 * 20].contiguous(), unit_scale=True, input_rate=44100, front_end="sinc")
