@@ -448,3 +448,22 @@ def test_downmix_mono_is_bit_exact():  # audio.rs:754-755, :816-818, :879-884: w
     assert torch.equal(mono, (st.to(torch.float32) / 32768.0 + st.to(torch.float32) / 32768.0) / 2.0)
     out, _ = cb.BatchDenoiser(2, cb.Model.synthetic(0)).process_streams(mono, unit_scale=True)
     assert out.shape == mono.shape and bool(torch.isfinite(out).all())
+
+
+def test_both_sinc_kernels_give_the_same_bits(monkeypatch):
+    """44.1 -> 48 kHz takes the second-generation kernel (four adjacent outputs per thread); CRISPY_NS_SINC_V1=1 forces
+    the first one.  Both accumulate fmaf(h[k], x[start + k], acc) in ascending k, so they agree bit for bit -- also on
+    rows that start on an odd element (scalar stores) and on a partial last tile."""
+    rng = np.random.default_rng(13)
+    x = torch.from_numpy(rng.standard_normal((5, 44100 * 2 + 17)).astype(np.float32)).cuda()
+    for view in (x, x[:, 1:4412], x[:, :441]):
+        b = cb.sinc_resample(view, 44100, 48000)
+        monkeypatch.setenv("CRISPY_NS_SINC_V1", "1")
+        a = cb.sinc_resample(view, 44100, 48000)
+        monkeypatch.delenv("CRISPY_NS_SINC_V1")
+        assert torch.equal(a, b)
+    want = po.sinc_resample(x[0, :4410].cpu().numpy(), 44100, 48000)
+    assert np.array_equal(cb.sinc_resample(x[:1, :4410].contiguous(), 44100, 48000)[0].cpu().numpy(), want)
+    # 32 kHz -> 48 kHz sits on the edge of the second kernel's range (M / L = 2 / 3)
+    y = cb.sinc_resample(x[:2, :32000].contiguous(), 32000, 48000)
+    assert np.array_equal(y[1].cpu().numpy(), po.sinc_resample(x[1, :32000].cpu().numpy(), 32000, 48000))
