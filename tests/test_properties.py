@@ -72,3 +72,40 @@ def test_sinc_oracle_is_linear_and_bounded(n, seed):
     assert len(ya) == -(-n * 160 // 147)
     if n:
         assert np.abs(yab - (ya + yb)).max() < 5e-5 * max(1.0, np.abs(yab).max())
+
+
+@settings(max_examples=150, deadline=None)
+@given(n=st.integers(0, 5000), rates=st.sampled_from([(44100, 48000), (48000, 44100), (16000, 48000), (48000, 16000), (22050, 48000),
+                                                      (8000, 48000), (48000, 48000), (47999, 48000), (96000, 48000)]))
+def test_resample_audio_count_and_shape(n, rates):  # recording.rs:19, :27-35
+    fr, to = rates
+    x = np.linspace(-1.0, 1.0, n, dtype=np.float32)
+    y = po.resample_audio(x, fr, to)
+    assert _lib.lib().crispy_ns_resample_audio_count(n, fr, to) == len(y)
+    if n:
+        assert len(y) == int(np.ceil(np.float64(n) / (np.float64(fr) / np.float64(to)))) or fr == to
+        assert y[0] == x[0] and np.all(np.diff(y.astype(np.float64)) >= -1e-6)  # an increasing ramp stays one
+        assert y.min() >= x.min() and y.max() <= x.max()  # interpolation never leaves the range of its two neighbours
+
+
+@settings(max_examples=100, deadline=None)
+@given(ch=st.integers(1, 8), n=st.integers(0, 64), seed=st.integers(0, 2 ** 31 - 1), fmt=st.sampled_from(["f32", "i16", "u16"]))
+def test_downmix_of_identical_channels_is_the_channel(ch, n, seed, fmt):  # audio.rs:754-755, :816-818, :879-884
+    rng = np.random.default_rng(seed)
+    if fmt == "f32":
+        one = rng.standard_normal(n).astype(np.float32)
+        unit = one
+    elif fmt == "i16":
+        one = rng.integers(-32768, 32768, n).astype(np.int16)
+        unit = one.astype(np.float32) / np.float32(32768.0)
+    else:
+        one = rng.integers(0, 65536, n).astype(np.uint16)
+        unit = (one.astype(np.float32) - np.float32(32768.0)) / np.float32(32768.0)
+    y = po.downmix_mono(np.repeat(one, ch), ch)
+    assert y.shape == (n,)
+    # exact where neither the running sum nor the division rounds: one or two channels; 16-bit samples (their sums fit
+    # the float32 significand) with a power-of-two channel count
+    if ch <= 2 or (fmt != "f32" and ch in (4, 8)):
+        assert np.array_equal(y, unit)
+    else:
+        assert np.allclose(y, unit, rtol=3e-7, atol=1e-12)
