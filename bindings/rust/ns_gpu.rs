@@ -69,6 +69,7 @@ extern "C" {
                                    mean_vad: *mut c_float) -> c_int;
     fn crispy_ns_linear_resample_count(input_rate: c_float, output_rate: c_float, n_in: i64) -> i64;
     fn crispy_ns_sinc_resample_count(input_rate: c_int, output_rate: c_int, n_in: i64) -> i64;
+    fn crispy_ns_resample_audio_count(n_in: i64, from_rate: c_int, to_rate: c_int) -> i64;
     fn crispy_ns_resample_host(device: c_int, h_in: *const c_float, h_out: *mut c_float, n_streams: c_int, n_in: i64,
                                in_stride: i64, out_stride: i64, input_rate: c_int, output_rate: c_int, kind: c_int) -> c_int;
 }
@@ -276,6 +277,20 @@ pub fn resample_to_48k(input: &[f32], n_streams: usize, n_in: usize, input_rate:
     let rc = unsafe {
         crispy_ns_resample_host(0, input.as_ptr(), out.as_mut_ptr(), n_streams as c_int, n_in as i64, n_in as i64,
                                 n_out.max(1) as i64, input_rate as c_int, 48000, if sinc { 1 } else { 0 })
+    };
+    if rc == 0 { Ok(out) } else { Err(last_error()) }
+}
+
+/// recording.rs:13-39 `resample_audio(samples, from_rate, to_rate)` for many buffers of one length at once
+/// (row-major `[n_streams][n_in]` in, `[n_streams][n_out]` out): bit-identical to the recorder's own loop.
+pub fn resample_audio_batch(input: &[f32], n_streams: usize, from_rate: usize, to_rate: usize) -> Result<Vec<f32>, String> {
+    assert!(n_streams > 0 && input.len() % n_streams == 0);
+    let n_in = input.len() / n_streams;
+    let n_out = unsafe { crispy_ns_resample_audio_count(n_in as i64, from_rate as c_int, to_rate as c_int) } as usize;
+    let mut out = vec![0f32; n_streams * n_out];
+    let rc = unsafe {
+        crispy_ns_resample_host(0, input.as_ptr(), out.as_mut_ptr(), n_streams as c_int, n_in as i64, n_in as i64,
+                                n_out.max(1) as i64, from_rate as c_int, to_rate as c_int, 2)
     };
     if rc == 0 { Ok(out) } else { Err(last_error()) }
 }

@@ -1637,13 +1637,14 @@ int sinc_resample(int device, const float *d_in, float *d_out, int n_streams, in
 
 int resample_host(int device, const float *h_in, float *h_out, int n_streams, int64_t n_in,
                             int64_t in_stride, int64_t out_stride, int input_rate, int output_rate, int kind) {
-  if (!h_in || !h_out || n_streams < 1 || n_in < 0 || (kind != 0 && kind != 1))
+  if (!h_in || !h_out || n_streams < 1 || n_in < 0 || kind < 0 || kind > 2)
     return fail(CRISPY_NS_EINVAL, "resample_host: bad argument");
   const int ndev = device_count();
   if (ndev == 0) return fail(CRISPY_NS_ENODEV, "no CUDA device: libcrispy_ns has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(CRISPY_NS_ENODEV, "device index out of range");
-  const int64_t n_out = kind == 0 ? linear_resample_count((float)input_rate, (float)output_rate, n_in)
-                                  : sinc_resample_count(input_rate, output_rate, n_in);
+  const int64_t n_out = kind == 0   ? linear_resample_count((float)input_rate, (float)output_rate, n_in)
+                        : kind == 1 ? sinc_resample_count(input_rate, output_rate, n_in)
+                                    : resample_audio_count(n_in, input_rate, output_rate);
   if (n_in == 0 || n_out == 0) return CRISPY_NS_OK;
   NS_CUDA(cudaSetDevice(device));
   float *d_in = nullptr, *d_out = nullptr;
@@ -1656,10 +1657,10 @@ int resample_host(int device, const float *h_in, float *h_out, int n_streams, in
   cudaError_t e = cudaMemcpy2D(d_in, (size_t)n_in * 4, h_in, (size_t)in_stride * 4, (size_t)n_in * 4, n_streams,
                                cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    rc = kind == 0 ? linear_resample(device, d_in, d_out, n_streams, n_in, n_in, n_out, (float)input_rate,
-                                               (float)output_rate, nullptr)
-                   : sinc_resample(device, d_in, d_out, n_streams, n_in, n_in, n_out, input_rate, output_rate,
-                                             0, 0.f, nullptr);
+    rc = kind == 0   ? linear_resample(device, d_in, d_out, n_streams, n_in, n_in, n_out, (float)input_rate, (float)output_rate, nullptr)
+         : kind == 1 ? sinc_resample(device, d_in, d_out, n_streams, n_in, n_in, n_out, input_rate, output_rate, 0, 0.f, nullptr)
+                     : resample_audio(device, d_in, d_out, n_streams, n_in, n_in, n_out, input_rate, output_rate, nullptr);
+    if (rc == CRISPY_NS_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) rc = fail(CRISPY_NS_ECUDA, "resample_host: kernel failed");
     if (rc == CRISPY_NS_OK)
       e = cudaMemcpy2D(h_out, (size_t)out_stride * 4, d_out, (size_t)n_out * 4, (size_t)n_out * 4, n_streams,
                        cudaMemcpyDeviceToHost);

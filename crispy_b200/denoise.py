@@ -232,15 +232,16 @@ def sinc_resample_chunk(x_window, in_first: int, n_total: int, first_out: int, n
 
 def resample_host(x, input_rate: int, output_rate: int, kind: str = "sinc", device: int = 0):
     """Host-array front end (crispy_ns_resample_host): x is a host f32 array [n_streams, n_in]; returns a numpy
-    array [n_streams, n_out].  kind: "linear" (audio.rs:108-133) or "sinc"."""
+    array [n_streams, n_out].  kind: "linear" (audio.rs:108-133), "sinc", or "audio" (recording.rs:13-39)."""
     xa = np.ascontiguousarray(x, dtype=np.float32)
     if xa.ndim != 2:
         raise CrispyNsError("resample_host needs a [n_streams, n_in] array")
     L = _lib.lib()
-    k = {"linear": 0, "sinc": 1}[kind]
+    k = {"linear": 0, "sinc": 1, "audio": 2}[kind]
     n_streams, n_in = xa.shape
     n_out = int(L.crispy_ns_linear_resample_count(float(input_rate), float(output_rate), n_in) if k == 0 else
-                L.crispy_ns_sinc_resample_count(int(input_rate), int(output_rate), n_in))
+                L.crispy_ns_sinc_resample_count(int(input_rate), int(output_rate), n_in) if k == 1 else
+                L.crispy_ns_resample_audio_count(n_in, int(input_rate), int(output_rate)))
     out = np.empty((n_streams, n_out), dtype=np.float32)
     check(L.crispy_ns_resample_host(device, xa.ctypes.data, out.ctypes.data, n_streams, n_in, n_in, max(n_out, 1),
                                     int(input_rate), int(output_rate), k))

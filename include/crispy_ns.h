@@ -212,8 +212,9 @@ int crispy_ns_sinc_resample_chunk(int device, const float *d_in, int64_t in_firs
                                   int64_t out_stride, int input_rate, int output_rate, int sinc_len, float f_cutoff,
                                   void *cuda_stream);
 /* host-pointer convenience over the two front ends (what the Rust side calls for recordings in RAM):
- * kind 0 = linear (audio.rs:108-133), 1 = windowed sinc (defaults 256 taps, cutoff 0.95).  Synchronous;
- * h_out must hold crispy_ns_{linear,sinc}_resample_count samples per stream. */
+ * kind 0 = linear (audio.rs:108-133), 1 = windowed sinc (defaults 256 taps, cutoff 0.95), 2 = the recorder's
+ * resample_audio (recording.rs:13-39).  Synchronous; h_out must hold crispy_ns_{linear,sinc}_resample_count /
+ * crispy_ns_resample_audio_count samples per stream. */
 int crispy_ns_resample_host(int device, const float *h_in, float *h_out, int n_streams, int64_t n_in,
                             int64_t in_stride, int64_t out_stride, int input_rate, int output_rate, int kind);
 

@@ -411,6 +411,10 @@ def test_resample_audio_is_bit_exact():  # recording.rs:13-39: the recorder's ap
     view = big[:, 1:44102]
     got = cb.resample_audio(view, 44100, 48000).cpu().numpy()
     assert np.array_equal(got[2], po.resample_audio(view[2].cpu().numpy(), 44100, 48000))
+    # the host-pointer entry point (what the Rust shim calls): kind 2
+    xh = rng.standard_normal((3, 4411)).astype(np.float32)
+    yh = cb.resample_host(xh, 44100, 48000, kind="audio")
+    assert np.array_equal(yh[1], po.resample_audio(xh[1], 44100, 48000))
     # configs[3] with a 44.1 kHz app source: resample_audio -> the dual-mono mix beside the denoised microphone
     nf = 20
     mic = synth_chunk(2, nf * 480, device="cuda")
