@@ -1783,16 +1783,18 @@ NS_DEV void spectrum_body(const Params &p, SpecSmem &s) {
 // =================================================================================================
 // tansig_approx without branches: |x| is clamped to 8, where the table ends at exactly 1.0 with zero
 // slope, so x >= 8 (and NaN) give +-1 as upstream's early returns do; floor(.5 + 25|x|) is a truncation.
+// The recurrent core is continuous in its inputs (no decision hangs on the last bit of an activation), so the
+// multiply-adds are fused here: 12 instead of 16 instructions per activation on the kernel's busiest path.
 NS_DEV float tansig_approx(const float *tab, float x) {
   const float ax = fminf(fabsf(x), 8.f);
-  const int i = (int)(.5f + 25.f * ax);
-  const float d = ax - .04f * i;
+  const int i = (int)fmaf(25.f, ax, .5f);
+  const float d = fmaf(-.04f, (float)i, ax);
   float y = tab[i];
-  const float dy = 1.f - y * y;
-  y = y + d * dy * (1.f - y * d);
+  const float dy = fmaf(-y, y, 1.f);
+  y = fmaf(d * dy, fmaf(-y, d, 1.f), y);
   return copysignf(y, x);
 }
-NS_DEV float sigmoid_approx(const float *tab, float x) { return .5f + .5f * tansig_approx(tab, .5f * x); }
+NS_DEV float sigmoid_approx(const float *tab, float x) { return fmaf(.5f, tansig_approx(tab, .5f * x), .5f); }
 NS_DEV float activate(const float *tab, int act, float x) {
   if (act == 1) return sigmoid_approx(tab, x);
   if (act == 0) return tansig_approx(tab, x);
