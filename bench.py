@@ -50,8 +50,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-front-end", action="store_true")
     ap.add_argument("--parity-streams", type=int, default=4)
-    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
-                    help="c2 = BASELINE.json configs[1] (default, the headline); c4 = configs[3]: 4,096 dual-source meetings "
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 = BASELINE.json configs[1] (default, the headline); c3 = configs[2]: 1,024 streams x 60 s per GPU at "
+                         "44.1 kHz through the sinc front end, then denoised; c4 = configs[3]: 4,096 dual-source meetings "
                          "x 10 min, mic PCM16 + app f32 -> dual-mono PCM16; c5 = configs[4]: 8,192 streams x 60 min; both "
                          "partitioned by stream over the N ranks, synthesised on device chunk by chunk, state carried")
     ap.add_argument("--total-streams", type=int, default=None, help="c4/c5: streams (meetings) in the whole job")
@@ -663,15 +664,23 @@ def run_long(args):
         torch.cuda.synchronize(dev)
 
     c4 = args.config == "c4"
-    total_streams = args.total_streams or (4096 if c4 else 8192)
-    minutes = args.minutes or (10.0 if c4 else 60.0)
+    c3 = args.config == "c3"
+    total_streams = args.total_streams or (4096 if c4 else (1024 * world if c3 else 8192))
+    minutes = args.minutes or (10.0 if c4 else (1.0 if c3 else 60.0))
     first, last = stream_block(total_streams, world, rank)
     n = last - first
+    if c3:
+        args.chunk_seconds = int(round(minutes * 60.0))  # the resamplers keep no state across calls: a whole recording per call
     call_frames = args.chunk_seconds * 100
     n_calls = max(1, int(round(minutes * 60.0 / args.chunk_seconds)))
     den = cb.BatchDenoiser(n, device=local)
     S = call_frames * FRAME
-    if c4:
+    in_frame = 441 if c3 else FRAME  # input samples per 10 ms
+    if c3:
+        mic = torch.empty((n, call_frames * in_frame), dtype=torch.float32, device=dev)
+        app = None
+        out = None
+    elif c4:
         mic = torch.empty((n, S), dtype=torch.int16, device=dev)
         app = torch.empty((n, S), dtype=torch.float32, device=dev)
         out = torch.empty((n, S, 2), dtype=torch.int16, device=dev)
@@ -685,14 +694,20 @@ def run_long(args):
         for f0 in range(0, call_frames, 100):
             nf = min(100, call_frames - f0)
             x = synth_chunk(n, nf * FRAME, first_stream=first, start_sample=(call * call_frames + f0) * FRAME, device=dev)
-            if c4:
+            if c3:  # the same generator read as a 44.1 kHz signal: 441 samples per 10 ms
+                mic[:, f0 * 441:(f0 + nf) * 441] = x[:, :nf * 441]
+            elif c4:
                 mic[:, f0 * FRAME:(f0 + nf) * FRAME] = (x * 32767.0).round().clamp_(-32768, 32767).to(torch.int16)
                 app[:, f0 * FRAME:(f0 + nf) * FRAME] = torch.roll(x, 1, 0) * 0.5  # another meeting's voice as app audio
             else:
                 mic[:, f0 * FRAME:(f0 + nf) * FRAME] = x
 
+    last_out = [None]
+
     def call():
-        if c4:
+        if c3:
+            last_out[0] = den.process_streams(mic, unit_scale=True, vad=vad, input_rate=44100, front_end="sinc")[0]
+        elif c4:
             den.process_streams(mic, unit_scale=True, app=app, mix_stereo_i16=True, out=out, vad=vad)
         else:
             den.process_streams(mic, unit_scale=True, out=out, vad=vad)
@@ -705,8 +720,14 @@ def run_long(args):
         call()
         torch.cuda.synchronize(dev)
         xin = (mic[:k].float() / 32768.0 if c4 else mic[:k]).cpu().numpy()
+        if c3:
+            xin = np.stack([po.sinc_resample(xin[i], 44100, 48000)[:call_frames * FRAME] for i in range(k)])
         ref, rv = po.process_streams(po.Model.synthetic(0), xin, unit_scale=True, n_threads=k, native=True)
-        if c4:
+        if c3:
+            err = last_out[0][:k].cpu().numpy().astype(np.float64) - ref
+            parity = {"streams": k, "frames": call_frames, "max_abs_fs": float(np.abs(err).max()),
+                      "vad_max": float(np.abs(vad[:k].cpu().numpy() - rv).max())}
+        elif c4:
             want = np.stack([po.mix_dual_mono_i16(ref[i], app[i].cpu().numpy()).reshape(-1, 2) for i in range(k)])
             d = np.abs(out[:k].cpu().numpy().astype(np.int32) - want.astype(np.int32))
             parity = {"streams": k, "frames": call_frames, "max_abs_lsb": int(d.max()), "vad_max": float(np.abs(vad[:k].cpu().numpy() - rv).max())}
@@ -748,22 +769,24 @@ def run_long(args):
             dist.destroy_process_group()
         return
     hbm_peak, peak_src = measured_peaks()
-    bytes_per_frame = (FRAME * 2 + FRAME * 4 + FRAME * 4 + 4) if c4 else ALG_BYTES_PER_FRAME
+    bytes_per_frame = (FRAME * 2 + FRAME * 4 + FRAME * 4 + 4) if c4 else ((441 * 4 + FRAME * 4 + 4) if c3 else ALG_BYTES_PER_FRAME)
     achieved = bytes_per_frame * (n * n_calls * call_frames * args.steps) / (total_ms / 1e3) / 1e9
     what = ("4,096 dual-source meetings x 10 min (BASELINE.json configs[3]): mic PCM16 denoised + raw app f32 -> "
             "clamp(mic+app) as dual-mono stereo PCM16; counts meetings" if c4 else
-            "8,192 streams x 60 min (BASELINE.json configs[4]), f32 unit-scale in/out + VAD")
+            ("1,024 streams x 60 s per GPU at 44.1 kHz (BASELINE.json configs[2]): windowed-sinc front end (256 taps) to 48 kHz, "
+             "then denoised; f32 unit-scale in/out + VAD" if c3 else
+             "8,192 streams x 60 min (BASELINE.json configs[4]), f32 unit-scale in/out + VAD"))
     line = {
         "metric": "stream-seconds of 48 kHz audio denoised per wall-second",
         "value": value, "unit": "stream-seconds/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak" if c3 else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{what}; this run: {total_streams} x {minutes:g} min over {world} GPU(s)",
                    "streams_this_rank": n, "calls_per_step": n_calls, "seconds_per_call": args.chunk_seconds,
                    "state": "every DenoiseState carried across the calls of a step (reset between steps)",
                    "timing": "only the denoise calls are timed (one CUDA event pair per call, summed, max over ranks); each "
                              "call's input is synthesised on the device just before it, outside the timed region",
-                   "l2": f"{n * S * (6 if c4 else 4) / 1e9:.1f} GB in + {n * S * 4 / 1e9:.1f} GB out per call >> 126 MB L2",
+                   "l2": f"{n * call_frames * in_frame * (6 if c4 else 4) / 1e9:.1f} GB in + {n * S * 4 / 1e9:.1f} GB out per call >> 126 MB L2",
                    "chunk_frames": den.info["chunk_frames"], "parallelism": f"streams/{world}gpu, no collective"},
         "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
