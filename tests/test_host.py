@@ -61,6 +61,11 @@ def test_library_contains_sm_100a_code():
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+    # the Blackwell-only instructions are really in the binary: tcgen05 mma / commit / tensor-memory load and store in
+    # the tcgen05 recurrent core, TMA bulk copies in the synthesis kernel, warp-level HMMA in the default recurrent core
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "HMMA.16816"):
+        assert mnemonic in sass, mnemonic
 
 
 def test_models_match_oracle_generator_and_loader():
