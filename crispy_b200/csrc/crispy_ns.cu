@@ -45,6 +45,9 @@ using PitchShared = ns::PitchSmem7<kPitchRun>;
 #endif
 //  // 37 lag-quads per frame in the coarse search + one helper warp
 constexpr int kScanWarps = 4;
+#ifndef NS_HP_EXCLUSIVE_MAX_STREAMS
+#define NS_HP_EXCLUSIVE_MAX_STREAMS 768
+#endif
 #ifndef NS_RNN_TC5_MIN_STREAMS
 #define NS_RNN_TC5_MIN_STREAMS (1 << 30)  // the tcgen05 recurrent core is opt-in ($CRISPY_NS_RNN=tc5) until measured
 #endif
@@ -412,6 +415,7 @@ struct crispy_ns_batch {
   uint8_t *d_words_tc5 = nullptr;
   float *d_bias_tc5 = nullptr;
   bool rnn_tc5 = false;
+  bool hp_exclusive = false;  // K0 alone on its SMs (kHpExclusiveSmem)
   float *d_state = nullptr;
   // pipeline workspace + plumbing
   float *d_hp[kSlots] = {};
@@ -477,12 +481,17 @@ static size_t out_elem(uint32_t flags) {
   return (flags & CRISPY_NS_OUT_I16) ? 2 : 4;
 }
 
+// Small batches are bound by the biquad (one lane per stream, 74 cycles per sample), and its recursion warp slows by half
+// again when it shares an SM's issue slots with the parallel kernels.  Asking for the whole shared memory of an SM keeps
+// every other CTA off the SMs the biquad runs on: it then runs at its isolated speed, at the price of streams / 32 SMs
+// that the parallel kernels lose -- a gain up to ~800 streams per GPU, a loss above (profiles/r2_small_batches.md).
+constexpr int kHpExclusiveSmem = 227 * 1024;
 static cudaError_t configure_kernels(int dev) {
   static std::mutex mu;
   static std::map<int, bool> configured;
   std::lock_guard<std::mutex> lk(mu);
   if (configured[dev]) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(ns_highpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ns::HpSmem));
+  cudaError_t e = cudaFuncSetAttribute(ns_highpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHpExclusiveSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ns_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(PitchShared));
   if (e == cudaSuccess)
@@ -536,7 +545,7 @@ static void launch_kernel(crispy_ns_batch *b, int k, ns::Params &p, int n, int n
     case 0:
       // measurement aid only: skip the biquad once N chunks have run (the slots then still hold realistic signal)
       if (getenv("CRISPY_NS_EXPERIMENT_SKIP_HP") && b->chunks_done >= atoll(getenv("CRISPY_NS_EXPERIMENT_SKIP_HP"))) break;
-      ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem), sk>>>(p);
+      ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, b->hp_exclusive ? (size_t)kHpExclusiveSmem : sizeof(ns::HpSmem), sk>>>(p);
       break;
     case 1:
       ns_pitch_kernel<<<n * ((nf + kPitchRun - 1) / kPitchRun), kPitchThreads, sizeof(PitchShared), sk>>>(p);
@@ -828,6 +837,9 @@ int batch_create(const crispy_ns_model *model, int device, int n_streams, crispy
     // K4 variant: $CRISPY_NS_RNN = "tc5" (tcgen05 / tensor memory, 128 streams per CTA) or "mma" (warp-level mma.sync,
     // 16 streams per CTA).  Default: tc5 from 512 streams on -- it holds 8 SMs per 1,024 streams instead of 64, which
     // the parallel kernels get back; below that its longer step (thirteen rounds per frame) is not worth it.
+    // K0 alone on its SMs: $CRISPY_NS_HP_EXCLUSIVE = 1 / 0, default by batch size
+    const char *hx = getenv("CRISPY_NS_HP_EXCLUSIVE");
+    b->hp_exclusive = hx ? atoi(hx) != 0 : n_streams <= NS_HP_EXCLUSIVE_MAX_STREAMS;
     const char *sel = getenv("CRISPY_NS_RNN");
     b->rnn_tc5 = sel ? (strcmp(sel, "tc5") == 0) : (n_streams >= NS_RNN_TC5_MIN_STREAMS);
     std::vector<uint8_t> w5;
