@@ -141,6 +141,22 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
       Simt::cp_async_commit();
       if (n >= kHpAhead) {  // tile n - kHpAhead has landed in every lane's view: publish it
         Simt::cp_async_wait<kHpAhead>();
+        if (raw16) {
+          // PCM16 rows were staged raw in the upper part of their float row: this warp, which only issues copies
+          // otherwise, turns them into floats in place (lane = row, four samples at a time, writing always behind its
+          // reads) so that the conversion stays off the recursion warp's chain
+          Simt::warp_sync();
+          if (lane < nrows) {
+            float *row = sm.tile[(n - kHpAhead) % kHpStages][lane];
+#pragma unroll 4
+            for (int c = 0; c < kHpTile; c += 4) {
+              const uint32_t *rw = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(row) + kHpRaw16 + 2 * c);
+              const uint32_t r0 = rw[0], r1 = rw[1];
+              *reinterpret_cast<f4 *>(row + c) = f4{(float)(int16_t)(r0 & 0xFFFFu), (float)(int16_t)(r0 >> 16),
+                                                    (float)(int16_t)(r1 & 0xFFFFu), (float)(int16_t)(r1 >> 16)};
+            }
+          }
+        }
         Simt::fence_cta();
         Simt::warp_sync();
         if (lane == 0) Simt::flag_set(&sm.landed[(n - kHpAhead) % kHpStages], n - kHpAhead + 1);
@@ -160,13 +176,8 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
 #pragma unroll 2
         for (int c = 0; c < kHpTile; c += 4) {
           float x[4];
-          if (raw16) {
-            const uint32_t *rw = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(row) + kHpRaw16 + 2 * c);
-            const uint32_t r0 = rw[0], r1 = rw[1];
-            x[0] = (float)(int16_t)(r0 & 0xFFFFu), x[1] = (float)(int16_t)(r0 >> 16);
-            x[2] = (float)(int16_t)(r1 & 0xFFFFu), x[3] = (float)(int16_t)(r1 >> 16);
-          } else {
-            const f4 xv = ld4(row + c);
+          {
+            const f4 xv = ld4(row + c);  // PCM16 input arrives here as floats too (converted by the loader warp)
             x[0] = xv.x * scale, x[1] = xv.y * scale, x[2] = xv.z * scale, x[3] = xv.w * scale;
           }
           float y[4];
