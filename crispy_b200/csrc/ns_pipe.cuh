@@ -53,6 +53,11 @@ constexpr int kHpThreads = 96;
 #ifndef NS_HP_TILE
 #define NS_HP_TILE 96
 #endif
+// 0: the recursion by upstream's f64 expression only; 1: speculated in f32 and verified in f64 off the chain
+// (TwoSum); 2: the same with the error term by a two-sided FastTwoSum.  Same bits either way.
+#ifndef NS_HP_SPEC
+#define NS_HP_SPEC 1
+#endif
 constexpr int kHpTile = NS_HP_TILE;  // samples per tile; 480 = 5 tiles
 constexpr int kHpPitch = kHpTile + 4;  // floats per row in shared memory: rows 4 (mod 32) banks apart for LDS.128
 constexpr int kHpStages = 4;
@@ -61,6 +66,13 @@ constexpr int kHpAhead = 2;        // tiles the loader keeps in flight beyond th
 constexpr int kHpRaw16 = (2 * kHpTile - 8 + 15) / 16 * 16;
 static_assert(kFrame % kHpTile == 0 && kHpTile % 8 == 0 && kHpPitch % 32 != 0 && kHpPitch % 4 == 0, "tile geometry");
 static_assert(kHpRaw16 % 16 == 0 && kHpRaw16 + 2 * kHpTile <= kHpPitch * 4 && 2 * kHpTile - 8 <= kHpRaw16, "PCM16 staging");
+#ifdef NS_HOST_EMU
+// test hook of the host emulation: groups the speculative recursion had to recompute (tests assert the path is taken)
+inline long long g_hp_respeculated = 0;
+#define NS_HP_COUNT_RESPEC() __atomic_add_fetch(&::ns::g_hp_respeculated, 1, __ATOMIC_RELAXED)
+#else
+#define NS_HP_COUNT_RESPEC() ((void)0)
+#endif
 struct HpSmem {
   float tile[kHpStages][32][kHpPitch];
   int landed[kHpStages], done[kHpStages], freed[kHpStages];
@@ -168,11 +180,110 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
     float *st = p.state + (long long)(s0 + (valid ? lane : 0)) * kStateFloats;
     float m0 = valid ? st[kStHp] : 0.f, m1 = valid ? st[kStHp + 1] : 0.f;
     const double na0 = -(double)-1.99599f, na1 = -(double)0.99600f;
+    // the four samples of one 16-byte group by upstream's own expression: the definition of the result
+    auto exact4 = [&](const float (&x)[4], float (&y)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float xi = x[i];
+        const float yi = xi + m0;
+        const double xd = (double)xi, yd = (double)yi;
+        // a0*y and a1*y are exact in f64 (24 x 24 bit), so the fused forms round exactly like
+        // upstream's  mem1 + (b0*x - a0*y)  and  b1*x - a1*y
+        m0 = (float)((double)m1 + fma(na0, yd, -2.0 * xd));
+        m1 = (float)fma(na1, yd, xd);
+        y[i] = yi;
+      }
+    };
+#if NS_HP_SPEC
+    // SPECULATE IN F32, VERIFY IN F64 OFF THE CHAIN.  The recursion's chain through mem0 is
+    // FADD -> F2F -> DFMA -> DADD -> F2F (74 cycles per sample, scripts/micro/hp_latency.cu).  The same value --
+    // RN32(m1 - 2x + a0 y) -- almost always comes out of error-free f32 arithmetic: a0 y = ph + pl exactly (FMUL +
+    // FFMA), m1 - 2x = ch + cl exactly (TwoSum, off the chain: it does not need y), ch + ph = s1 + e1 exactly, and
+    // s1 + ((cl + pl) + e1) rounds like the f64 expression unless the sum sits within ~2^-22 ulp of a rounding
+    // boundary or the low product underflows (a decaying silent stream crossing 2^-126).  That chain is FADD -> FMUL
+    // -> FADD -> TwoSum error -> FADD -> FADD, all 4-cycle operations.  mem1 needs no speculation: it is upstream's
+    // f64 expression itself, two samples away from where it is consumed.  Upstream's expression for mem0 is evaluated
+    // as well, from the speculated values, but nothing waits for it: the comparison of a 4-sample group happens after
+    // the NEXT group's chain has been issued.  A group with any bit mismatch (the sign of a zero included) and the
+    // group after it are recomputed with exact4 from the state saved at the group's start, so the results are
+    // upstream's bits BY CONSTRUCTION; the speculation only decides how fast they come.  Measured on the host over
+    // 5e8 samples of speech-like, white, DC, tonal, PCM16 and tiny inputs: no mismatch; ~100-200 per decay into
+    // digital silence; subnormal limit cycles that cross -0 mismatch once per ~800 samples.
+    const float a0f = 1.99599f;
+    float pv_x[4] = {0.f, 0.f, 0.f, 0.f}, pv_s[4] = {0.f, 0.f, 0.f, 0.f}, pv_r[4] = {0.f, 0.f, 0.f, 0.f};
+    float pv_m0 = 0.f, pv_m1 = 0.f;  // the state the pending group started from
+    float *pv_row = nullptr;
+    bool pv_have = false;
+    // speculated against upstream's values of the pending group; `dep` ties the comparison to a value that only
+    // exists after the current group's chain, so the compiler cannot place it (and its wait for the F2F) earlier
+    auto pending_bad = [&](float dep) {
+      uint32_t bad = 0u;
+#pragma unroll
+      for (int i = 0; i < 4; i++) bad |= f2u(pv_s[i]) ^ Simt::after(f2u(pv_r[i]), dep);
+      return bad != 0u;
+    };
+#endif
     for (int n = 0; n < ntiles; n++) {
       const int slot = n % kHpStages;
       Simt::flag_wait(&sm.landed[slot], n + 1, false);
       if (valid) {
         float *row = sm.tile[slot][lane];
+#if NS_HP_SPEC
+#pragma unroll 2
+        for (int c = 0; c < kHpTile; c += 4) {
+          float x[4], y[4], ms[4], mr[4];
+          {
+            const f4 xv = ld4(row + c);  // PCM16 input arrives here as floats too (converted by the loader warp)
+            x[0] = xv.x * scale, x[1] = xv.y * scale, x[2] = xv.z * scale, x[3] = xv.w * scale;
+          }
+          const float in_m0 = m0, in_m1 = m1;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float xi = x[i];
+            const float yi = xi + m0;
+            const float ph = a0f * yi, pl = fmaf(a0f, yi, -ph);
+            const float b = -2.0f * xi;
+            const float ch = m1 + b, cbb = ch - m1, cl = (m1 - (ch - cbb)) + (b - cbb);
+            const float s1 = ch + ph;
+#if NS_HP_SPEC == 2
+            // FastTwoSum both ways round: the one whose first operand is the larger is exact
+            const float e1 = (fabsf(ch) >= fabsf(ph)) ? (ph - (s1 - ch)) : (ch - (s1 - ph));
+#else
+            const float sbb = s1 - ch, e1 = (ch - (s1 - sbb)) + (ph - sbb);
+#endif
+            ms[i] = s1 + ((cl + pl) + e1);
+            const double xd = (double)xi, yd = (double)yi;
+            mr[i] = (float)((double)m1 + fma(na0, yd, -2.0 * xd));  // upstream's value, off the chain
+            m1 = (float)fma(na1, yd, xd);
+            m0 = ms[i];
+            y[i] = yi;
+          }
+          *reinterpret_cast<f4 *>(row + c) = f4{y[0], y[1], y[2], y[3]};
+          if (pv_have && pending_bad(m0)) {  // the group before this one was mis-speculated: both again, exactly
+            NS_HP_COUNT_RESPEC();
+            m0 = pv_m0, m1 = pv_m1;
+            float yy[4];
+            exact4(pv_x, yy);
+            *reinterpret_cast<f4 *>(pv_row) = f4{yy[0], yy[1], yy[2], yy[3]};
+            exact4(x, yy);
+            *reinterpret_cast<f4 *>(row + c) = f4{yy[0], yy[1], yy[2], yy[3]};
+            pv_have = false;
+          } else {
+            pv_have = true;
+            pv_m0 = in_m0, pv_m1 = in_m1, pv_row = row + c;
+#pragma unroll
+            for (int i = 0; i < 4; i++) pv_x[i] = x[i], pv_s[i] = ms[i], pv_r[i] = mr[i];
+          }
+        }
+        if (pv_have && pending_bad(m0)) {  // the tile's last group, before the tile is handed to the storer
+          NS_HP_COUNT_RESPEC();
+          m0 = pv_m0, m1 = pv_m1;
+          float yy[4];
+          exact4(pv_x, yy);
+          *reinterpret_cast<f4 *>(pv_row) = f4{yy[0], yy[1], yy[2], yy[3]};
+        }
+        pv_have = false;
+#else
 #pragma unroll 2
         for (int c = 0; c < kHpTile; c += 4) {
           float x[4];
@@ -181,19 +292,10 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
             x[0] = xv.x * scale, x[1] = xv.y * scale, x[2] = xv.z * scale, x[3] = xv.w * scale;
           }
           float y[4];
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float xi = x[i];
-            const float yi = xi + m0;
-            const double xd = (double)xi, yd = (double)yi;
-            // a0*y and a1*y are exact in f64 (24 x 24 bit), so the fused forms round exactly like
-            // upstream's  mem1 + (b0*x - a0*y)  and  b1*x - a1*y
-            m0 = (float)((double)m1 + fma(na0, yd, -2.0 * xd));
-            m1 = (float)fma(na1, yd, xd);
-            y[i] = yi;
-          }
+          exact4(x, y);
           *reinterpret_cast<f4 *>(row + c) = f4{y[0], y[1], y[2], y[3]};
         }
+#endif
       }
       Simt::fence_cta();
       Simt::warp_sync();

@@ -85,6 +85,10 @@ constexpr int kScanWarps = 1;
 extern "C" {
 int ns_emu_state_floats(void) { return ns::kStateFloats; }
 int ns_emu_dbg_floats(void) { return ns::kDbgFloats; }
+int ns_emu_state_hp_offset(void) { return ns::kStHp; }
+int ns_emu_hp_spec(void) { return NS_HP_SPEC; }
+// groups the speculative biquad recomputed with upstream's f64 expression since the last call (K0, ns_pipe.cuh)
+long long ns_emu_hp_respeculated(void) { return __atomic_exchange_n(&ns::g_hp_respeculated, 0, __ATOMIC_RELAXED); }
 
 // in/out/app use the same strides the device path uses; state is in/out ([n_streams][kStateFloats]).
 // The call is cut into chunks of `chunk_cap` frames exactly as libcrispy_ns.so does.

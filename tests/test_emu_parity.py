@@ -135,3 +135,53 @@ def test_second_generation_pitch_kernel_is_bit_exact_too(oracle_model, model_blo
         assert np.array_equal(dbg[:, :, 132].astype(np.int32), rpi), name
         assert not ((dbg[:, :, 130] != rpg) & ~(np.isnan(dbg[:, :, 130]) & np.isnan(rpg))).any(), name
         assert np.array_equal(dbg[:, :, 133].astype(np.int32), rsil), name
+
+
+def _biquad_reference(x, m0, m1):
+    """upstream denoise.c biquad(): f32 state, f64 intermediates (oracle/rnnoise_oracle.c biquad, line for line)"""
+    a0, a1 = float(np.float32(-1.99599)), float(np.float32(0.99600))
+    y = np.empty_like(x)
+    m0, m1 = np.float32(m0), np.float32(m1)
+    for i, xi in enumerate(x):
+        yi = np.float32(xi + m0)
+        m0n = np.float32(float(m1) + (-2.0 * float(xi) - a0 * float(yi)))
+        m1 = np.float32(float(xi) - a1 * float(yi))
+        m0 = m0n
+        y[i] = yi
+    return y, m0, m1
+
+
+def test_speculative_biquad_recomputes_what_it_misses(model_blob):
+    """K0 speculates mem0 in error-free f32 arithmetic and checks every value against upstream's f64 expression off
+    the critical chain; a group that differs in any bit is recomputed.  A filter state decaying into digital silence
+    crosses 2^-126, where the low half of a0*y underflows and the speculation goes wrong a few hundred times; a state
+    on a subnormal limit cycle crosses -0.  Both must leave upstream's bits, and the recomputation must have run."""
+    from tests.util import emu_lib
+    L = emu_lib()
+    if L.ns_emu_hp_spec() == 0:
+        pytest.skip("built with -DNS_HP_SPEC=0")
+    L.ns_emu_hp_respeculated.restype = __import__("ctypes").c_longlong
+    hp = L.ns_emu_state_hp_offset()
+    n_frames = 14
+    rng = np.random.default_rng(11)
+    x = np.zeros((4, n_frames * 480), np.float32)
+    x[1, :960] = (3000.0 * rng.standard_normal(960)).astype(np.float32)  # noise, then digital silence
+    x[3] = (2500.0 * rng.standard_normal(n_frames * 480)).astype(np.float32)  # ordinary input
+    state = np.zeros((4, L.ns_emu_state_floats()), np.float32)
+    state[0, hp:hp + 2] = (3.1e-36, -2.9e-36)  # decays through 2^-126 within a few thousand samples
+    state[1, hp:hp + 2] = (-120.5, 118.25)
+    state[2, hp:hp + 2] = np.array([0x80000000 | 249, 497], np.uint32).view(np.float32)  # one step from -0
+    start = state[:, hp:hp + 2].copy()
+    L.ns_emu_hp_respeculated()
+    _, _, _, st = emu_process(model_blob, x, chunk=7, state=state)
+    redone = L.ns_emu_hp_respeculated()
+    for s in range(4):
+        y, m0, m1 = _biquad_reference(x[s], *start[s])
+        got = st[s, hp:hp + 2]
+        assert got.view(np.uint32).tolist() == [np.float32(m0).view(np.uint32), np.float32(m1).view(np.uint32)], s
+        assert np.array_equal(st[s, :1440].view(np.uint32), y[-1440:].view(np.uint32)), s  # the high-passed history
+    assert redone > 50, redone
+    # ordinary input alone never takes the slow path
+    L.ns_emu_hp_respeculated()
+    emu_process(model_blob, x[3:4], chunk=7)
+    assert L.ns_emu_hp_respeculated() == 0
