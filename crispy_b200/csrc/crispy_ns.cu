@@ -52,9 +52,20 @@ constexpr int kScanWarps = 4;
 #define NS_RNN_TC5_MIN_STREAMS (1 << 30)  // the tcgen05 recurrent core is opt-in ($CRISPY_NS_RNN=tc5) until measured
 #endif
 
-__global__ void __launch_bounds__(ns::kHpThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
+#if NS_HP_PAR
+using HpShared = ns::HpParSmem;
+constexpr int kHpLaunchThreads = ns::kHpParThreads;
+#else
+using HpShared = ns::HpSmem;
+constexpr int kHpLaunchThreads = ns::kHpThreads;
+#endif
+__global__ void __launch_bounds__(kHpLaunchThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ns::highpass_body(p, *reinterpret_cast<ns::HpSmem *>(smem_raw));
+#if NS_HP_PAR
+  ns::highpass_par_body(p, *reinterpret_cast<HpShared *>(smem_raw));
+#else
+  ns::highpass_body(p, *reinterpret_cast<HpShared *>(smem_raw));
+#endif
 }
 __global__ void __launch_bounds__(kPitchThreads) ns_pitch_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -545,7 +556,7 @@ static void launch_kernel(crispy_ns_batch *b, int k, ns::Params &p, int n, int n
     case 0:
       // measurement aid only: skip the biquad once N chunks have run (the slots then still hold realistic signal)
       if (getenv("CRISPY_NS_EXPERIMENT_SKIP_HP") && b->chunks_done >= atoll(getenv("CRISPY_NS_EXPERIMENT_SKIP_HP"))) break;
-      ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, b->hp_exclusive ? (size_t)kHpExclusiveSmem : sizeof(ns::HpSmem), sk>>>(p);
+      ns_highpass_kernel<<<(n + 31) / 32, kHpLaunchThreads, b->hp_exclusive ? (size_t)kHpExclusiveSmem : sizeof(HpShared), sk>>>(p);
       break;
     case 1:
       ns_pitch_kernel<<<n * ((nf + kPitchRun - 1) / kPitchRun), kPitchThreads, sizeof(PitchShared), sk>>>(p);

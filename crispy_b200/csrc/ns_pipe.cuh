@@ -53,11 +53,6 @@ constexpr int kHpThreads = 96;
 #ifndef NS_HP_TILE
 #define NS_HP_TILE 96
 #endif
-// 0: the recursion by upstream's f64 expression only; 1: speculated in f32 and verified in f64 off the chain
-// (TwoSum); 2: the same with the error term by a two-sided FastTwoSum.  Same bits either way.
-#ifndef NS_HP_SPEC
-#define NS_HP_SPEC 1
-#endif
 constexpr int kHpTile = NS_HP_TILE;  // samples per tile; 480 = 5 tiles
 constexpr int kHpPitch = kHpTile + 4;  // floats per row in shared memory: rows 4 (mod 32) banks apart for LDS.128
 constexpr int kHpStages = 4;
@@ -66,13 +61,6 @@ constexpr int kHpAhead = 2;        // tiles the loader keeps in flight beyond th
 constexpr int kHpRaw16 = (2 * kHpTile - 8 + 15) / 16 * 16;
 static_assert(kFrame % kHpTile == 0 && kHpTile % 8 == 0 && kHpPitch % 32 != 0 && kHpPitch % 4 == 0, "tile geometry");
 static_assert(kHpRaw16 % 16 == 0 && kHpRaw16 + 2 * kHpTile <= kHpPitch * 4 && 2 * kHpTile - 8 <= kHpRaw16, "PCM16 staging");
-#ifdef NS_HOST_EMU
-// test hook of the host emulation: groups the speculative recursion had to recompute (tests assert the path is taken)
-inline long long g_hp_respeculated = 0;
-#define NS_HP_COUNT_RESPEC() __atomic_add_fetch(&::ns::g_hp_respeculated, 1, __ATOMIC_RELAXED)
-#else
-#define NS_HP_COUNT_RESPEC() ((void)0)
-#endif
 struct HpSmem {
   float tile[kHpStages][32][kHpPitch];
   int landed[kHpStages], done[kHpStages], freed[kHpStages];
@@ -180,110 +168,11 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
     float *st = p.state + (long long)(s0 + (valid ? lane : 0)) * kStateFloats;
     float m0 = valid ? st[kStHp] : 0.f, m1 = valid ? st[kStHp + 1] : 0.f;
     const double na0 = -(double)-1.99599f, na1 = -(double)0.99600f;
-    // the four samples of one 16-byte group by upstream's own expression: the definition of the result
-    auto exact4 = [&](const float (&x)[4], float (&y)[4]) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const float xi = x[i];
-        const float yi = xi + m0;
-        const double xd = (double)xi, yd = (double)yi;
-        // a0*y and a1*y are exact in f64 (24 x 24 bit), so the fused forms round exactly like
-        // upstream's  mem1 + (b0*x - a0*y)  and  b1*x - a1*y
-        m0 = (float)((double)m1 + fma(na0, yd, -2.0 * xd));
-        m1 = (float)fma(na1, yd, xd);
-        y[i] = yi;
-      }
-    };
-#if NS_HP_SPEC
-    // SPECULATE IN F32, VERIFY IN F64 OFF THE CHAIN.  The recursion's chain through mem0 is
-    // FADD -> F2F -> DFMA -> DADD -> F2F (74 cycles per sample, scripts/micro/hp_latency.cu).  The same value --
-    // RN32(m1 - 2x + a0 y) -- almost always comes out of error-free f32 arithmetic: a0 y = ph + pl exactly (FMUL +
-    // FFMA), m1 - 2x = ch + cl exactly (TwoSum, off the chain: it does not need y), ch + ph = s1 + e1 exactly, and
-    // s1 + ((cl + pl) + e1) rounds like the f64 expression unless the sum sits within ~2^-22 ulp of a rounding
-    // boundary or the low product underflows (a decaying silent stream crossing 2^-126).  That chain is FADD -> FMUL
-    // -> FADD -> TwoSum error -> FADD -> FADD, all 4-cycle operations.  mem1 needs no speculation: it is upstream's
-    // f64 expression itself, two samples away from where it is consumed.  Upstream's expression for mem0 is evaluated
-    // as well, from the speculated values, but nothing waits for it: the comparison of a 4-sample group happens after
-    // the NEXT group's chain has been issued.  A group with any bit mismatch (the sign of a zero included) and the
-    // group after it are recomputed with exact4 from the state saved at the group's start, so the results are
-    // upstream's bits BY CONSTRUCTION; the speculation only decides how fast they come.  Measured on the host over
-    // 5e8 samples of speech-like, white, DC, tonal, PCM16 and tiny inputs: no mismatch; ~100-200 per decay into
-    // digital silence; subnormal limit cycles that cross -0 mismatch once per ~800 samples.
-    const float a0f = 1.99599f;
-    float pv_x[4] = {0.f, 0.f, 0.f, 0.f}, pv_s[4] = {0.f, 0.f, 0.f, 0.f}, pv_r[4] = {0.f, 0.f, 0.f, 0.f};
-    float pv_m0 = 0.f, pv_m1 = 0.f;  // the state the pending group started from
-    float *pv_row = nullptr;
-    bool pv_have = false;
-    // speculated against upstream's values of the pending group; `dep` ties the comparison to a value that only
-    // exists after the current group's chain, so the compiler cannot place it (and its wait for the F2F) earlier
-    auto pending_bad = [&](float dep) {
-      uint32_t bad = 0u;
-#pragma unroll
-      for (int i = 0; i < 4; i++) bad |= f2u(pv_s[i]) ^ Simt::after(f2u(pv_r[i]), dep);
-      return bad != 0u;
-    };
-#endif
     for (int n = 0; n < ntiles; n++) {
       const int slot = n % kHpStages;
       Simt::flag_wait(&sm.landed[slot], n + 1, false);
       if (valid) {
         float *row = sm.tile[slot][lane];
-#if NS_HP_SPEC
-#pragma unroll 2
-        for (int c = 0; c < kHpTile; c += 4) {
-          float x[4], y[4], ms[4], mr[4];
-          {
-            const f4 xv = ld4(row + c);  // PCM16 input arrives here as floats too (converted by the loader warp)
-            x[0] = xv.x * scale, x[1] = xv.y * scale, x[2] = xv.z * scale, x[3] = xv.w * scale;
-          }
-          const float in_m0 = m0, in_m1 = m1;
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float xi = x[i];
-            const float yi = xi + m0;
-            const float ph = a0f * yi, pl = fmaf(a0f, yi, -ph);
-            const float b = -2.0f * xi;
-            const float ch = m1 + b, cbb = ch - m1, cl = (m1 - (ch - cbb)) + (b - cbb);
-            const float s1 = ch + ph;
-#if NS_HP_SPEC == 2
-            // FastTwoSum both ways round: the one whose first operand is the larger is exact
-            const float e1 = (fabsf(ch) >= fabsf(ph)) ? (ph - (s1 - ch)) : (ch - (s1 - ph));
-#else
-            const float sbb = s1 - ch, e1 = (ch - (s1 - sbb)) + (ph - sbb);
-#endif
-            ms[i] = s1 + ((cl + pl) + e1);
-            const double xd = (double)xi, yd = (double)yi;
-            mr[i] = (float)((double)m1 + fma(na0, yd, -2.0 * xd));  // upstream's value, off the chain
-            m1 = (float)fma(na1, yd, xd);
-            m0 = ms[i];
-            y[i] = yi;
-          }
-          *reinterpret_cast<f4 *>(row + c) = f4{y[0], y[1], y[2], y[3]};
-          if (pv_have && pending_bad(m0)) {  // the group before this one was mis-speculated: both again, exactly
-            NS_HP_COUNT_RESPEC();
-            m0 = pv_m0, m1 = pv_m1;
-            float yy[4];
-            exact4(pv_x, yy);
-            *reinterpret_cast<f4 *>(pv_row) = f4{yy[0], yy[1], yy[2], yy[3]};
-            exact4(x, yy);
-            *reinterpret_cast<f4 *>(row + c) = f4{yy[0], yy[1], yy[2], yy[3]};
-            pv_have = false;
-          } else {
-            pv_have = true;
-            pv_m0 = in_m0, pv_m1 = in_m1, pv_row = row + c;
-#pragma unroll
-            for (int i = 0; i < 4; i++) pv_x[i] = x[i], pv_s[i] = ms[i], pv_r[i] = mr[i];
-          }
-        }
-        if (pv_have && pending_bad(m0)) {  // the tile's last group, before the tile is handed to the storer
-          NS_HP_COUNT_RESPEC();
-          m0 = pv_m0, m1 = pv_m1;
-          float yy[4];
-          exact4(pv_x, yy);
-          *reinterpret_cast<f4 *>(pv_row) = f4{yy[0], yy[1], yy[2], yy[3]};
-        }
-        pv_have = false;
-#else
 #pragma unroll 2
         for (int c = 0; c < kHpTile; c += 4) {
           float x[4];
@@ -292,10 +181,19 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
             x[0] = xv.x * scale, x[1] = xv.y * scale, x[2] = xv.z * scale, x[3] = xv.w * scale;
           }
           float y[4];
-          exact4(x, y);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float xi = x[i];
+            const float yi = xi + m0;
+            const double xd = (double)xi, yd = (double)yi;
+            // a0*y and a1*y are exact in f64 (24 x 24 bit), so the fused forms round exactly like
+            // upstream's  mem1 + (b0*x - a0*y)  and  b1*x - a1*y
+            m0 = (float)((double)m1 + fma(na0, yd, -2.0 * xd));
+            m1 = (float)fma(na1, yd, xd);
+            y[i] = yi;
+          }
           *reinterpret_cast<f4 *>(row + c) = f4{y[0], y[1], y[2], y[3]};
         }
-#endif
       }
       Simt::fence_cta();
       Simt::warp_sync();
@@ -345,6 +243,256 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
 #pragma unroll
         for (int i = 0; i < kHist / 32; i++) dst[lane + 32 * i] = v[i];
       }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K0, second form (NS_HP_PAR, the default): THE SAME RECURSION, PARALLEL IN TIME.
+//
+// What bounds the single recursion warp above is not a latency chain but the FP64 pipe of its SM sub-partition: a
+// sample costs nine instructions there (five F2F, two DFMA, DMUL, DADD) at ~8 issue cycles each = 72 of the 74
+// cycles measured (scripts/micro/hp_latency.cu; speculating mem0 in f32 on the same warp while it still verifies
+// in f64 is therefore SLOWER: 82 cycles, variants 5 / 6).  So the f64 work is taken off the serial warp altogether
+// and spread over other sub-partitions:
+//   warp 0          : runs the recursion SPECULATIVELY in error-free f32 arithmetic, no f64 at all (~36 cycles a
+//                     sample, all 4-cycle FADD / FMUL / FFMA), and only records its state at the start of every
+//                     24-sample segment (and at the tile's end);
+//   warps 3, 5, 6, 7: segment v of every tile by upstream's own f64 expression (exact4), STARTING FROM THE RECORDED
+//                     STATE, four segments in parallel on the FP64 pipes of three other sub-partitions; they write
+//                     y, and compare the state they end in, bit for bit, with the state recorded for the next segment;
+//   warp 1 / warp 2 : loader and storer as before (y now has a ring of its own: x must survive a recomputation).
+// By induction over the segments, every y the storer sees comes out of upstream's expression from a start state that
+// is upstream's: the result is upstream's bits BY CONSTRUCTION, whatever the speculation does.  Where a segment's
+// end state differs from the record (any bit, the sign of a zero included), warp 0 takes the segment's exact end
+// state, recomputes the rest of that tile exactly, and speculates the next tile again, before the next tile is
+// released to the exact warps.
+// The f32 speculation: a0 y = ph + pl exactly (FMUL + FFMA), m1 - 2x = ch + cl exactly (TwoSum, off the chain),
+// ch + ph = s1 + e1 exactly, and RN32(s1 + ((cl + pl) + e1)) is upstream's RN32(RN53(m1 + RN53(a0 y - 2x))) unless the
+// sum sits within ~2^-22 ulp of a rounding boundary or the low product underflows; mem1 = RN32(x - a1 y) alike.  On
+// the host: no mismatch in 1e9 samples of speech-like, white, DC, tonal, PCM16 and tiny inputs; ~300 per decay into
+// digital silence (the state crossing 2^-126); subnormal limit cycles that cross -0 miss once per ~800 samples.
+// Warp 4 would share warp 0's sub-partition and exits at once.
+// -------------------------------------------------------------------------------------------------
+#ifndef NS_HP_PAR
+#define NS_HP_PAR 1
+#endif
+constexpr int kHpSeg = 4;                     // exact warps = segments per tile
+constexpr int kHpSegLen = kHpTile / kHpSeg;   // 24 samples
+constexpr int kHpYStages = 2;                 // y ring: one tile being written, one being stored
+constexpr int kHpParThreads = 256;
+static_assert(kHpTile % (4 * kHpSeg) == 0, "segments are whole 16-byte groups");
+#ifdef NS_HOST_EMU
+// test hook of the host emulation: tiles whose speculation had to be repaired (tests assert the path is taken)
+inline long long g_hp_respeculated = 0;
+#define NS_HP_COUNT_RESPEC() __atomic_add_fetch(&::ns::g_hp_respeculated, 1, __ATOMIC_RELAXED)
+#else
+#define NS_HP_COUNT_RESPEC() ((void)0)
+#endif
+struct HpParSmem {
+  HpSmem x;                                  // the x ring and the loader's flags (done[] unused)
+  float y[kHpYStages][32][kHpPitch];         // the y ring
+  float spec[2][kHpSeg + 1][32][2];          // speculated (mem0, mem1) at the start of segment v / at the tile's end
+  float exact[2][kHpSeg][32][2];             // upstream's (mem0, mem1) at the end of segment v
+  int bad[2][kHpSeg][32];                    // 1: segment v ended in a state that is not the recorded one
+  int go;                                    // tiles < go are speculated and every earlier tile is settled
+  int ver[kHpSeg];                           // tiles < ver[v] have had segment v computed
+  int ydone;                                 // tiles < ydone are final in the y ring
+  int yfreed;                                // tiles < yfreed have been stored
+};
+
+NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
+  const int tid = Simt::tid();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int s0 = Simt::cta() * 32;
+  const int nrows = (p.n_streams - s0) < 32 ? (p.n_streams - s0) : 32;
+  const int nsamp = p.n_frames * kFrame;
+  const int ntiles = nsamp / kHpTile;
+  const bool tail_direct = nsamp >= kHist;  // the new history is the chunk's own tail
+  if (tid < kHpStages) sm.x.landed[tid] = sm.x.done[tid] = sm.x.freed[tid] = 0;
+  if (tid < kHpSeg) sm.ver[tid] = 0;
+  if (tid == 0) sm.go = sm.ydone = sm.yfreed = 0;
+  Simt::cta_sync();
+  const long long in0 = (long long)p.frame0 * kFrame;
+  const bool in16 = (p.flags & kFlagInI16) != 0;
+  const int amask = in16 ? 7 : 3;  // samples per 16 bytes - 1
+  const bool fast = (p.in_stride & amask) == 0 && (in0 & amask) == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
+  const bool raw16 = fast && in16;
+  const float scale = ((p.flags & kFlagUnitScale) && !in16) ? 32768.0f : 1.0f;  // audio.rs:264
+  const bool valid = lane < nrows;
+  float m0 = 0.f, m1 = 0.f;
+  const double na0 = -(double)-1.99599f, na1 = -(double)0.99600f;
+  // n4 16-byte groups by upstream's own expression (f32 state, f64 intermediates): the definition of the result.
+  // a0*y and a1*y are exact in f64 (24 x 24 bit), so the fused forms round exactly like upstream's
+  // mem1 + (b0*x - a0*y)  and  b1*x - a1*y
+  auto exact_run = [&](const float *xrow, float *yrow, int n4) {
+#pragma unroll 2
+    for (int c = 0; c < 4 * n4; c += 4) {
+      const f4 xv = ld4(xrow + c);
+      const float x[4] = {xv.x * scale, xv.y * scale, xv.z * scale, xv.w * scale};
+      float y[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float xi = x[i];
+        const float yi = xi + m0;
+        const double xd = (double)xi, yd = (double)yi;
+        m0 = (float)((double)m1 + fma(na0, yd, -2.0 * xd));
+        m1 = (float)fma(na1, yd, xd);
+        y[i] = yi;
+      }
+      *reinterpret_cast<f4 *>(yrow + c) = f4{y[0], y[1], y[2], y[3]};
+    }
+  };
+  if (warp == 1) {  // ---- loader (as in the first form)
+    for (int n = 0; n < ntiles + kHpAhead; n++) {
+      if (n < ntiles) {
+        if (n >= kHpStages) Simt::flag_wait(&sm.x.freed[n % kHpStages], n - kHpStages + 1, true);
+        hp_fetch_tile(p, sm.x, s0, nrows, in0, n, fast, lane);
+      }
+      Simt::cp_async_commit();
+      if (n >= kHpAhead) {
+        Simt::cp_async_wait<kHpAhead>();
+        if (raw16) {
+          Simt::warp_sync();
+          if (lane < nrows) {
+            float *row = sm.x.tile[(n - kHpAhead) % kHpStages][lane];
+#pragma unroll 4
+            for (int c = 0; c < kHpTile; c += 4) {
+              const uint32_t *rw = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(row) + kHpRaw16 + 2 * c);
+              const uint32_t r0 = rw[0], r1 = rw[1];
+              *reinterpret_cast<f4 *>(row + c) = f4{(float)(int16_t)(r0 & 0xFFFFu), (float)(int16_t)(r0 >> 16),
+                                                    (float)(int16_t)(r1 & 0xFFFFu), (float)(int16_t)(r1 >> 16)};
+            }
+          }
+        }
+        Simt::fence_cta();
+        Simt::warp_sync();
+        if (lane == 0) Simt::flag_set(&sm.x.landed[(n - kHpAhead) % kHpStages], n - kHpAhead + 1);
+      }
+    }
+  } else if (warp == 0) {  // ---- speculation in f32, and the repair of what it misses
+    float *st = p.state + (long long)(s0 + (valid ? lane : 0)) * kStateFloats;
+    if (valid) m0 = st[kStHp], m1 = st[kStHp + 1];
+    const float a0f = 1.99599f, na1f = -0.99600f;
+    auto spec_tile = [&](int n) {
+      const float *row = sm.x.tile[n % kHpStages][lane];
+      float(*rec)[32][2] = sm.spec[n & 1];
+      for (int v = 0; v < kHpSeg; v++) {
+        rec[v][lane][0] = m0, rec[v][lane][1] = m1;
+#pragma unroll 2
+        for (int c = v * kHpSegLen; c < (v + 1) * kHpSegLen; c += 4) {
+          const f4 xv = ld4(row + c);
+          const float x[4] = {xv.x * scale, xv.y * scale, xv.z * scale, xv.w * scale};
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float xi = x[i];
+            const float yi = xi + m0;
+            // mem0' = RN32(m1 - 2x + a0 y)
+            const float ph = a0f * yi, pl = fmaf(a0f, yi, -ph);
+            const float b = -2.0f * xi;
+            const float ch = m1 + b, cbb = ch - m1, cl = (m1 - (ch - cbb)) + (b - cbb);
+            const float s1 = ch + ph, sbb = s1 - ch, e1 = (ch - (s1 - sbb)) + (ph - sbb);
+            // mem1' = RN32(x - a1 y)
+            const float qh = na1f * yi, ql = fmaf(na1f, yi, -qh);
+            const float s2 = xi + qh, tbb = s2 - xi, e2 = (xi - (s2 - tbb)) + (qh - tbb);
+            m0 = s1 + ((cl + pl) + e1);
+            m1 = s2 + (e2 + ql);
+          }
+        }
+      }
+      rec[kHpSeg][lane][0] = m0, rec[kHpSeg][lane][1] = m1;
+    };
+    // tile k has been through the exact warps: repair it if a segment ended off the record, then hand it on
+    auto settle = [&](int k, bool next_speculated) {
+      for (int v = 0; v < kHpSeg; v++) Simt::flag_wait(&sm.ver[v], k + 1, false);
+      if (valid) {
+        int v0 = -1;
+#pragma unroll
+        for (int v = kHpSeg - 1; v >= 0; v--)
+          if (sm.bad[k & 1][v][lane]) v0 = v;
+        if (v0 >= 0) {
+          NS_HP_COUNT_RESPEC();
+          m0 = sm.exact[k & 1][v0][lane][0], m1 = sm.exact[k & 1][v0][lane][1];  // upstream's state after segment v0
+          const int c0 = (v0 + 1) * kHpSegLen;
+          exact_run(sm.x.tile[k % kHpStages][lane] + c0, sm.y[k % kHpYStages][lane] + c0, (kHpTile - c0) / 4);
+          if (next_speculated) spec_tile(k + 1);
+        }
+      }
+      Simt::fence_cta();
+      Simt::warp_sync();
+      if (lane == 0) {
+        Simt::flag_set(&sm.ydone, k + 1);
+        Simt::flag_set(&sm.x.freed[k % kHpStages], k + 1);
+      }
+    };
+    for (int n = 0; n < ntiles; n++) {
+      Simt::flag_wait(&sm.x.landed[n % kHpStages], n + 1, false);
+      if (valid) spec_tile(n);
+      if (n >= 1) settle(n - 1, true);
+      Simt::fence_cta();
+      Simt::warp_sync();
+      if (lane == 0) Simt::flag_set(&sm.go, n + 1);
+    }
+    if (ntiles > 0) settle(ntiles - 1, false);
+    if (valid) {
+      st[kStHp] = m0;
+      st[kStHp + 1] = m1;
+    }
+  } else if (warp == 2) {  // ---- storer (as in the first form, from the y ring)
+    hp_copy_rows(p.state + (long long)s0 * kStateFloats + kStHist, kStateFloats, p.hp + (long long)s0 * p.hp_stride,
+                 p.hp_stride, nrows, lane);
+    Simt::warp_sync();  // the old history has been read: the tail tiles may overwrite it
+    for (int n = 0; n < ntiles; n++) {
+      Simt::flag_wait(&sm.ydone, n + 1, true);
+      float(*tile)[kHpPitch] = sm.y[n % kHpYStages];
+      const int base = n * kHpTile;
+      if (lane < kHpTile / 4) {
+        const int c = 4 * lane;
+        float *dsth = p.hp + (long long)s0 * p.hp_stride + kHist + base + c;
+        const int hidx = base + c - (nsamp - kHist);
+        if (tail_direct && hidx >= 0) {
+          float *dsts = p.state + (long long)s0 * kStateFloats + kStHist + hidx;
+          for (int r = 0; r < nrows; r++, dsth += p.hp_stride, dsts += kStateFloats) {
+            const f4 v = ld4(&tile[r][c]);
+            *reinterpret_cast<f4 *>(dsth) = v;
+            *reinterpret_cast<f4 *>(dsts) = v;
+          }
+        } else {
+#pragma unroll 8
+          for (int r = 0; r < nrows; r++, dsth += p.hp_stride) *reinterpret_cast<f4 *>(dsth) = ld4(&tile[r][c]);
+        }
+      }
+      Simt::warp_sync();
+      if (lane == 0) Simt::flag_set(&sm.yfreed, n + 1);
+    }
+    if (!tail_direct) {  // short chunk: last kHist samples of [history | chunk] -> state, staged through registers
+      Simt::fence_cta();
+      Simt::warp_sync();
+      for (int r = 0; r < nrows; r++) {
+        const float *src = p.hp + (long long)(s0 + r) * p.hp_stride + nsamp;
+        float *dst = p.state + (long long)(s0 + r) * kStateFloats + kStHist;
+        float v[kHist / 32];
+#pragma unroll
+        for (int i = 0; i < kHist / 32; i++) v[i] = src[lane + 32 * i];
+#pragma unroll
+        for (int i = 0; i < kHist / 32; i++) dst[lane + 32 * i] = v[i];
+      }
+    }
+  } else if (warp != 4) {  // ---- segment v of every tile by upstream's expression, from the recorded state
+    const int v = warp == 3 ? 0 : warp - 4;  // warps 3, 5, 6, 7
+    for (int n = 0; n < ntiles; n++) {
+      Simt::flag_wait(&sm.go, n + 1, true);
+      if (n >= kHpYStages) Simt::flag_wait(&sm.yfreed, n - kHpYStages + 1, true);
+      if (valid) {
+        m0 = sm.spec[n & 1][v][lane][0], m1 = sm.spec[n & 1][v][lane][1];
+        exact_run(sm.x.tile[n % kHpStages][lane] + v * kHpSegLen, sm.y[n % kHpYStages][lane] + v * kHpSegLen, kHpSegLen / 4);
+        sm.exact[n & 1][v][lane][0] = m0, sm.exact[n & 1][v][lane][1] = m1;
+        sm.bad[n & 1][v][lane] =
+            (f2u(m0) != f2u(sm.spec[n & 1][v + 1][lane][0])) | (f2u(m1) != f2u(sm.spec[n & 1][v + 1][lane][1]));
+      }
+      Simt::fence_cta();
+      Simt::warp_sync();
+      if (lane == 0) Simt::flag_set(&sm.ver[v], n + 1);
     }
   }
 }

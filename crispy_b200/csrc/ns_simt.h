@@ -28,11 +28,6 @@ struct Simt {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
   }
   static NS_DEV void warp_sync() { __syncwarp(); }
-  // v, but not before `dep` exists: a scheduling fence for the compiler (no instruction is emitted)
-  static NS_DEV uint32_t after(uint32_t v, float dep) {
-    asm volatile("" : "+r"(v) : "f"(dep));
-    return v;
-  }
   static NS_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
   static NS_DEV float shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
   static NS_DEV float shfl_up(float v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
@@ -170,7 +165,6 @@ struct Simt {
   static void cta_sync() { pthread_barrier_wait(&g_emu.cta->cta_bar); }
   static void group_sync(int id, int) { pthread_barrier_wait(&g_emu.cta->group_bar[id]); }
   static void warp_sync() { pthread_barrier_wait(&g_emu.cta->warps[g_emu.tid >> 5].bar); }
-  static uint32_t after(uint32_t v, float) { return v; }
   template <class T>
   static T xchg(T v, int src_lane) {
     EmuWarp &w = g_emu.cta->warps[g_emu.tid >> 5];

@@ -86,7 +86,7 @@ extern "C" {
 int ns_emu_state_floats(void) { return ns::kStateFloats; }
 int ns_emu_dbg_floats(void) { return ns::kDbgFloats; }
 int ns_emu_state_hp_offset(void) { return ns::kStHp; }
-int ns_emu_hp_spec(void) { return NS_HP_SPEC; }
+int ns_emu_hp_spec(void) { return NS_HP_PAR; }
 // groups the speculative biquad recomputed with upstream's f64 expression since the last call (K0, ns_pipe.cuh)
 long long ns_emu_hp_respeculated(void) { return __atomic_exchange_n(&ns::g_hp_respeculated, 0, __ATOMIC_RELAXED); }
 
@@ -151,8 +151,13 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
     int *chunk_counter = reinterpret_cast<int *>(state) + ns::kStateFloats - 1;
     p.synth_sel = *chunk_counter & 1;
     *chunk_counter += 1;
+#if NS_HP_PAR
+    int rc = launch((n_streams + 31) / 32, ns::kHpParThreads, sizeof(ns::HpParSmem),
+                    [&](void *sm) { ns::highpass_par_body(p, *(ns::HpParSmem *)sm); });
+#else
     int rc = launch((n_streams + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem),
                     [&](void *sm) { ns::highpass_body(p, *(ns::HpSmem *)sm); });
+#endif
     if (rc) return rc;
     const int runs = (nf + kPitchRun - 1) / kPitchRun;
     rc = launch(n_streams * runs, kPitchThreads, sizeof(PitchShared), [&](void *sm) {

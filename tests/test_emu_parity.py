@@ -152,22 +152,26 @@ def _biquad_reference(x, m0, m1):
 
 
 def test_speculative_biquad_recomputes_what_it_misses(model_blob):
-    """K0 speculates mem0 in error-free f32 arithmetic and checks every value against upstream's f64 expression off
-    the critical chain; a group that differs in any bit is recomputed.  A filter state decaying into digital silence
-    crosses 2^-126, where the low half of a0*y underflows and the speculation goes wrong a few hundred times; a state
-    on a subnormal limit cycle crosses -0.  Both must leave upstream's bits, and the recomputation must have run."""
+    """K0 runs the recursion speculatively in error-free f32 arithmetic on one warp, and upstream's f64 expression on
+    four others, one 24-sample segment each, from the states the first recorded; a segment that ends off the record
+    makes the first warp repair the tile and speculate the next one again.  A filter state decaying into digital
+    silence crosses 2^-126, where the low half of a0*y underflows and the speculation goes wrong a few hundred times;
+    a state on a subnormal limit cycle crosses -0; noise of ~1e-36 keeps a stream in that zone for good, so that
+    nearly every tile is repaired, in every segment position, the last tile of a launch included.  All must leave
+    upstream's bits, and the repair must have run."""
     from tests.util import emu_lib
     L = emu_lib()
     if L.ns_emu_hp_spec() == 0:
-        pytest.skip("built with -DNS_HP_SPEC=0")
+        pytest.skip("built with -DNS_HP_PAR=0")
     L.ns_emu_hp_respeculated.restype = __import__("ctypes").c_longlong
     hp = L.ns_emu_state_hp_offset()
     n_frames = 14
     rng = np.random.default_rng(11)
-    x = np.zeros((4, n_frames * 480), np.float32)
+    x = np.zeros((5, n_frames * 480), np.float32)
     x[1, :960] = (3000.0 * rng.standard_normal(960)).astype(np.float32)  # noise, then digital silence
     x[3] = (2500.0 * rng.standard_normal(n_frames * 480)).astype(np.float32)  # ordinary input
-    state = np.zeros((4, L.ns_emu_state_floats()), np.float32)
+    x[4] = (1e-36 * rng.standard_normal(n_frames * 480)).astype(np.float32)  # lives where the low product underflows
+    state = np.zeros((5, L.ns_emu_state_floats()), np.float32)
     state[0, hp:hp + 2] = (3.1e-36, -2.9e-36)  # decays through 2^-126 within a few thousand samples
     state[1, hp:hp + 2] = (-120.5, 118.25)
     state[2, hp:hp + 2] = np.array([0x80000000 | 249, 497], np.uint32).view(np.float32)  # one step from -0
@@ -175,12 +179,12 @@ def test_speculative_biquad_recomputes_what_it_misses(model_blob):
     L.ns_emu_hp_respeculated()
     _, _, _, st = emu_process(model_blob, x, chunk=7, state=state)
     redone = L.ns_emu_hp_respeculated()
-    for s in range(4):
+    for s in range(5):
         y, m0, m1 = _biquad_reference(x[s], *start[s])
         got = st[s, hp:hp + 2]
         assert got.view(np.uint32).tolist() == [np.float32(m0).view(np.uint32), np.float32(m1).view(np.uint32)], s
         assert np.array_equal(st[s, :1440].view(np.uint32), y[-1440:].view(np.uint32)), s  # the high-passed history
-    assert redone > 50, redone
+    assert redone > 2 * 7 * 5 * 0.8, redone  # stream 4 alone: nearly each of its 70 tiles
     # ordinary input alone never takes the slow path
     L.ns_emu_hp_respeculated()
     emu_process(model_blob, x[3:4], chunk=7)
