@@ -52,20 +52,17 @@ constexpr int kScanWarps = 4;
 #define NS_RNN_TC5_MIN_STREAMS (1 << 30)  // the tcgen05 recurrent core is opt-in ($CRISPY_NS_RNN=tc5) until measured
 #endif
 
-#if NS_HP_PAR
-using HpShared = ns::HpParSmem;
-constexpr int kHpLaunchThreads = ns::kHpParThreads;
-#else
-using HpShared = ns::HpSmem;
-constexpr int kHpLaunchThreads = ns::kHpThreads;
-#endif
-__global__ void __launch_bounds__(kHpLaunchThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
+// K0 in its two forms (ns_pipe.cuh): one recursion warp, and parallel in time (one speculating warp + four exact warps).
+// The second is the faster kernel (isolated 613 -> ~450 us per 32,768 frames) and wins wherever K0 bounds the pipeline
+// (small batches, where it also has its SMs to itself); beside the pitch CTAs of a full batch its eight warps cost the
+// parallel kernels what its shorter run gives back, so the first form stays there (crispy_ns_batch::hp_par).
+__global__ void __launch_bounds__(ns::kHpThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-#if NS_HP_PAR
-  ns::highpass_par_body(p, *reinterpret_cast<HpShared *>(smem_raw));
-#else
-  ns::highpass_body(p, *reinterpret_cast<HpShared *>(smem_raw));
-#endif
+  ns::highpass_body(p, *reinterpret_cast<ns::HpSmem *>(smem_raw));
+}
+__global__ void __launch_bounds__(ns::kHpParThreads) ns_highpass_par_kernel(const __grid_constant__ ns::Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ns::highpass_par_body(p, *reinterpret_cast<ns::HpParSmem *>(smem_raw));
 }
 __global__ void __launch_bounds__(kPitchThreads) ns_pitch_kernel(const __grid_constant__ ns::Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -427,6 +424,7 @@ struct crispy_ns_batch {
   float *d_bias_tc5 = nullptr;
   bool rnn_tc5 = false;
   bool hp_exclusive = false;  // K0 alone on its SMs (kHpExclusiveSmem)
+  bool hp_par = false;        // K0 parallel in time (ns_highpass_par_kernel); $CRISPY_NS_HP_PAR overrides
   float *d_state = nullptr;
   // pipeline workspace + plumbing
   float *d_hp[kSlots] = {};
@@ -503,6 +501,8 @@ static cudaError_t configure_kernels(int dev) {
   std::lock_guard<std::mutex> lk(mu);
   if (configured[dev]) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(ns_highpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHpExclusiveSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(ns_highpass_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHpExclusiveSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ns_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(PitchShared));
   if (e == cudaSuccess)
@@ -556,7 +556,10 @@ static void launch_kernel(crispy_ns_batch *b, int k, ns::Params &p, int n, int n
     case 0:
       // measurement aid only: skip the biquad once N chunks have run (the slots then still hold realistic signal)
       if (getenv("CRISPY_NS_EXPERIMENT_SKIP_HP") && b->chunks_done >= atoll(getenv("CRISPY_NS_EXPERIMENT_SKIP_HP"))) break;
-      ns_highpass_kernel<<<(n + 31) / 32, kHpLaunchThreads, b->hp_exclusive ? (size_t)kHpExclusiveSmem : sizeof(HpShared), sk>>>(p);
+      if (b->hp_par)
+        ns_highpass_par_kernel<<<(n + 31) / 32, ns::kHpParThreads, b->hp_exclusive ? (size_t)kHpExclusiveSmem : sizeof(ns::HpParSmem), sk>>>(p);
+      else
+        ns_highpass_kernel<<<(n + 31) / 32, ns::kHpThreads, b->hp_exclusive ? (size_t)kHpExclusiveSmem : sizeof(ns::HpSmem), sk>>>(p);
       break;
     case 1:
       ns_pitch_kernel<<<n * ((nf + kPitchRun - 1) / kPitchRun), kPitchThreads, sizeof(PitchShared), sk>>>(p);
@@ -851,6 +854,8 @@ int batch_create(const crispy_ns_model *model, int device, int n_streams, crispy
     // K0 alone on its SMs: $CRISPY_NS_HP_EXCLUSIVE = 1 / 0, default by batch size
     const char *hx = getenv("CRISPY_NS_HP_EXCLUSIVE");
     b->hp_exclusive = hx ? atoi(hx) != 0 : n_streams <= NS_HP_EXCLUSIVE_MAX_STREAMS;
+    const char *hpp = getenv("CRISPY_NS_HP_PAR");
+    b->hp_par = hpp ? atoi(hpp) != 0 : (NS_HP_PAR != 0 && b->hp_exclusive);
     const char *sel = getenv("CRISPY_NS_RNN");
     b->rnn_tc5 = sel ? (strcmp(sel, "tc5") == 0) : (n_streams >= NS_RNN_TC5_MIN_STREAMS);
     std::vector<uint8_t> w5;

@@ -281,6 +281,10 @@ constexpr int kHpSeg = 4;                     // exact warps = segments per tile
 constexpr int kHpSegLen = kHpTile / kHpSeg;   // 24 samples
 constexpr int kHpYStages = 2;                 // y ring: one tile being written, one being stored
 constexpr int kHpParThreads = 256;
+// The loader publishes tile n once tile n + kHpParAhead has been issued, and a ring slot is held until its tile has
+// been settled (one tile later than in the first form): with two tiles ahead the speculation warp waited ~1,000 cycles
+// per tile for `landed` (measured with -DNS_HP_CLOCKS); with one, tile n is published two tiles before it is needed.
+constexpr int kHpParAhead = 1;
 static_assert(kHpTile % (4 * kHpSeg) == 0, "segments are whole 16-byte groups");
 #ifdef NS_HOST_EMU
 // test hook of the host emulation: tiles whose speculation had to be repaired (tests assert the path is taken)
@@ -288,6 +292,13 @@ inline long long g_hp_respeculated = 0;
 #define NS_HP_COUNT_RESPEC() __atomic_add_fetch(&::ns::g_hp_respeculated, 1, __ATOMIC_RELAXED)
 #else
 #define NS_HP_COUNT_RESPEC() ((void)0)
+#endif
+#if defined(NS_HP_CLOCKS) && defined(__CUDACC__) && !defined(NS_HOST_EMU)
+#define NS_HP_T0() const long long hp_t0_ = clock64()
+#define NS_HP_ACC(var) var += clock64() - hp_t0_
+#else
+#define NS_HP_T0() ((void)0)
+#define NS_HP_ACC(var) ((void)0)
 #endif
 struct HpParSmem {
   HpSmem x;                                  // the x ring and the loader's flags (done[] unused)
@@ -300,6 +311,15 @@ struct HpParSmem {
   int ydone;                                 // tiles < ydone are final in the y ring
   int yfreed;                                // tiles < yfreed have been stored
 };
+
+// a + b - RN32(a + b), exactly: FastTwoSum with the operands ordered by magnitude first.  The ordering does not need
+// the sum, so behind s = a + b only two dependent operations remain on the recursion's chain (TwoSum: four; a
+// dependent FADD costs ~5.8 cycles on this part, scripts/micro/hp_latency.cu variants 7-9)
+NS_DEV float hp_fast_err(float a, float b, float s) {
+  const bool a_big = fabsf(a) >= fabsf(b);
+  const float big = a_big ? a : b, small = a_big ? b : a;
+  return small - (s - big);
+}
 
 NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
   const int tid = Simt::tid();
@@ -321,6 +341,10 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
   const float scale = ((p.flags & kFlagUnitScale) && !in16) ? 32768.0f : 1.0f;  // audio.rs:264
   const bool valid = lane < nrows;
   float m0 = 0.f, m1 = 0.f;
+  long long t_work = 0, t_wait = 0, t_wait2 = 0;  // -DNS_HP_CLOCKS: cycles per role (CTA 0 prints them)
+  (void)t_work, (void)t_wait, (void)t_wait2;
+  const long long t_begin = 0;
+  (void)t_begin;
   const double na0 = -(double)-1.99599f, na1 = -(double)0.99600f;
   // n4 16-byte groups by upstream's own expression (f32 state, f64 intermediates): the definition of the result.
   // a0*y and a1*y are exact in f64 (24 x 24 bit), so the fused forms round exactly like upstream's
@@ -344,18 +368,22 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
     }
   };
   if (warp == 1) {  // ---- loader (as in the first form)
-    for (int n = 0; n < ntiles + kHpAhead; n++) {
+    for (int n = 0; n < ntiles + kHpParAhead; n++) {
       if (n < ntiles) {
-        if (n >= kHpStages) Simt::flag_wait(&sm.x.freed[n % kHpStages], n - kHpStages + 1, true);
+        if (n >= kHpStages) {
+          NS_HP_T0();
+          Simt::flag_wait(&sm.x.freed[n % kHpStages], n - kHpStages + 1, true);
+          NS_HP_ACC(t_wait);
+        }
         hp_fetch_tile(p, sm.x, s0, nrows, in0, n, fast, lane);
       }
       Simt::cp_async_commit();
-      if (n >= kHpAhead) {
-        Simt::cp_async_wait<kHpAhead>();
+      if (n >= kHpParAhead) {
+        Simt::cp_async_wait<kHpParAhead>();
         if (raw16) {
           Simt::warp_sync();
           if (lane < nrows) {
-            float *row = sm.x.tile[(n - kHpAhead) % kHpStages][lane];
+            float *row = sm.x.tile[(n - kHpParAhead) % kHpStages][lane];
 #pragma unroll 4
             for (int c = 0; c < kHpTile; c += 4) {
               const uint32_t *rw = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(row) + kHpRaw16 + 2 * c);
@@ -367,7 +395,7 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
         }
         Simt::fence_cta();
         Simt::warp_sync();
-        if (lane == 0) Simt::flag_set(&sm.x.landed[(n - kHpAhead) % kHpStages], n - kHpAhead + 1);
+        if (lane == 0) Simt::flag_set(&sm.x.landed[(n - kHpParAhead) % kHpStages], n - kHpParAhead + 1);
       }
     }
   } else if (warp == 0) {  // ---- speculation in f32, and the repair of what it misses
@@ -391,10 +419,12 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
             const float ph = a0f * yi, pl = fmaf(a0f, yi, -ph);
             const float b = -2.0f * xi;
             const float ch = m1 + b, cbb = ch - m1, cl = (m1 - (ch - cbb)) + (b - cbb);
-            const float s1 = ch + ph, sbb = s1 - ch, e1 = (ch - (s1 - sbb)) + (ph - sbb);
+            const float s1 = ch + ph;
+            const float e1 = hp_fast_err(ch, ph, s1);
             // mem1' = RN32(x - a1 y)
             const float qh = na1f * yi, ql = fmaf(na1f, yi, -qh);
-            const float s2 = xi + qh, tbb = s2 - xi, e2 = (xi - (s2 - tbb)) + (qh - tbb);
+            const float s2 = xi + qh;
+            const float e2 = hp_fast_err(xi, qh, s2);
             m0 = s1 + ((cl + pl) + e1);
             m1 = s2 + (e2 + ql);
           }
@@ -404,7 +434,8 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
     };
     // tile k has been through the exact warps: repair it if a segment ended off the record, then hand it on
     auto settle = [&](int k, bool next_speculated) {
-      for (int v = 0; v < kHpSeg; v++) Simt::flag_wait(&sm.ver[v], k + 1, false);
+      for (int v = 0; v < kHpSeg; v++) Simt::flag_poll(&sm.ver[v], k + 1, false);
+      Simt::fence_cta();
       if (valid) {
         int v0 = -1;
 #pragma unroll
@@ -418,20 +449,34 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
           if (next_speculated) spec_tile(k + 1);
         }
       }
-      Simt::fence_cta();
+      Simt::fence_cta();  // one fence for the repaired y, the records of the next tile and the three flags
       Simt::warp_sync();
       if (lane == 0) {
-        Simt::flag_set(&sm.ydone, k + 1);
-        Simt::flag_set(&sm.x.freed[k % kHpStages], k + 1);
+        Simt::flag_store(&sm.ydone, k + 1);
+        Simt::flag_store(&sm.x.freed[k % kHpStages], k + 1);
+        if (next_speculated) Simt::flag_store(&sm.go, k + 2);
       }
     };
     for (int n = 0; n < ntiles; n++) {
-      Simt::flag_wait(&sm.x.landed[n % kHpStages], n + 1, false);
-      if (valid) spec_tile(n);
-      if (n >= 1) settle(n - 1, true);
-      Simt::fence_cta();
-      Simt::warp_sync();
-      if (lane == 0) Simt::flag_set(&sm.go, n + 1);
+      {
+        NS_HP_T0();
+        Simt::flag_wait(&sm.x.landed[n % kHpStages], n + 1, false);
+        NS_HP_ACC(t_wait);
+      }
+      {
+        NS_HP_T0();
+        if (valid) spec_tile(n);
+        NS_HP_ACC(t_work);
+      }
+      if (n >= 1) {
+        NS_HP_T0();
+        settle(n - 1, true);  // raises go = n + 1 as well
+        NS_HP_ACC(t_wait2);
+      } else {
+        Simt::fence_cta();
+        Simt::warp_sync();
+        if (lane == 0) Simt::flag_store(&sm.go, 1);
+      }
     }
     if (ntiles > 0) settle(ntiles - 1, false);
     if (valid) {
@@ -443,7 +488,12 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
                  p.hp_stride, nrows, lane);
     Simt::warp_sync();  // the old history has been read: the tail tiles may overwrite it
     for (int n = 0; n < ntiles; n++) {
-      Simt::flag_wait(&sm.ydone, n + 1, true);
+      {
+        NS_HP_T0();
+        Simt::flag_wait(&sm.ydone, n + 1, true);
+        NS_HP_ACC(t_wait);
+      }
+      NS_HP_T0();
       float(*tile)[kHpPitch] = sm.y[n % kHpYStages];
       const int base = n * kHpTile;
       if (lane < kHpTile / 4) {
@@ -463,6 +513,7 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
         }
       }
       Simt::warp_sync();
+      NS_HP_ACC(t_work);
       if (lane == 0) Simt::flag_set(&sm.yfreed, n + 1);
     }
     if (!tail_direct) {  // short chunk: last kHist samples of [history | chunk] -> state, staged through registers
@@ -481,8 +532,17 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
   } else if (warp != 4) {  // ---- segment v of every tile by upstream's expression, from the recorded state
     const int v = warp == 3 ? 0 : warp - 4;  // warps 3, 5, 6, 7
     for (int n = 0; n < ntiles; n++) {
-      Simt::flag_wait(&sm.go, n + 1, true);
-      if (n >= kHpYStages) Simt::flag_wait(&sm.yfreed, n - kHpYStages + 1, true);
+      {
+        NS_HP_T0();
+        Simt::flag_wait(&sm.go, n + 1, true);
+        NS_HP_ACC(t_wait);
+      }
+      if (n >= kHpYStages) {
+        NS_HP_T0();
+        Simt::flag_wait(&sm.yfreed, n - kHpYStages + 1, true);
+        NS_HP_ACC(t_wait2);
+      }
+      NS_HP_T0();
       if (valid) {
         m0 = sm.spec[n & 1][v][lane][0], m1 = sm.spec[n & 1][v][lane][1];
         exact_run(sm.x.tile[n % kHpStages][lane] + v * kHpSegLen, sm.y[n % kHpYStages][lane] + v * kHpSegLen, kHpSegLen / 4);
@@ -492,9 +552,14 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
       }
       Simt::fence_cta();
       Simt::warp_sync();
+      NS_HP_ACC(t_work);
       if (lane == 0) Simt::flag_set(&sm.ver[v], n + 1);
     }
   }
+#if defined(NS_HP_CLOCKS) && defined(__CUDACC__) && !defined(NS_HOST_EMU)
+  if (Simt::cta() == 0 && lane == 0 && warp != 4)
+    printf("K0 warp %d: %d tiles, work %lld, wait %lld, wait2 %lld cycles\n", warp, ntiles, t_work, t_wait, t_wait2);
+#endif
 }
 
 // =================================================================================================

@@ -102,6 +102,13 @@ struct Simt {
     }
     __threadfence_block();
   }
+  // the same two without their fence, for a warp that waits on / raises several flags around ONE fence_cta()
+  static NS_DEV void flag_store(int *f, int v) { *reinterpret_cast<volatile int *>(f) = v; }
+  static NS_DEV void flag_poll(const int *f, int v, bool relaxed) {
+    while (*reinterpret_cast<const volatile int *>(f) < v) {
+      if (relaxed) __nanosleep(200);
+    }
+  }
   // two floats -> packed bf16 pair, round to nearest even; `lo` lands in the low halfword
   static NS_DEV uint32_t bf16x2_rn(float lo, float hi) {
     uint32_t d;
@@ -224,6 +231,8 @@ struct Simt {
   static void flag_wait(const int *f, int v, bool) {
     while (__atomic_load_n(f, __ATOMIC_SEQ_CST) < v) sched_yield();
   }
+  static void flag_store(int *f, int v) { __atomic_store_n(f, v, __ATOMIC_SEQ_CST); }
+  static void flag_poll(const int *f, int v, bool relaxed) { flag_wait(f, v, relaxed); }
   // mma.sync.m16n8k16 (bf16 x bf16 -> f32) emulated from the lanes' fragments: A element (row, k)
   // sits in lane (row%8)*4 + (k%8)/2, word row/8 + 2*(k/8), halfword k%2; B element (k, col) in
   // lane col*4 + (k%8)/2, word k/8, halfword k%2; this lane owns D (lane/4 [+8], 2*(lane%4) [+1]).

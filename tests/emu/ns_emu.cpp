@@ -151,13 +151,13 @@ int ns_emu_process(const void *model_blob, size_t model_len, const void *in, voi
     int *chunk_counter = reinterpret_cast<int *>(state) + ns::kStateFloats - 1;
     p.synth_sel = *chunk_counter & 1;
     *chunk_counter += 1;
-#if NS_HP_PAR
-    int rc = launch((n_streams + 31) / 32, ns::kHpParThreads, sizeof(ns::HpParSmem),
-                    [&](void *sm) { ns::highpass_par_body(p, *(ns::HpParSmem *)sm); });
-#else
-    int rc = launch((n_streams + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem),
-                    [&](void *sm) { ns::highpass_body(p, *(ns::HpSmem *)sm); });
-#endif
+    // both forms of K0 (the library picks by batch size; here $CRISPY_NS_HP_PAR = 0 selects the single recursion warp)
+    const char *hpp = getenv("CRISPY_NS_HP_PAR");
+    const bool hp_par = hpp ? atoi(hpp) != 0 : NS_HP_PAR != 0;
+    int rc = hp_par ? launch((n_streams + 31) / 32, ns::kHpParThreads, sizeof(ns::HpParSmem),
+                             [&](void *sm) { ns::highpass_par_body(p, *(ns::HpParSmem *)sm); })
+                    : launch((n_streams + 31) / 32, ns::kHpThreads, sizeof(ns::HpSmem),
+                             [&](void *sm) { ns::highpass_body(p, *(ns::HpSmem *)sm); });
     if (rc) return rc;
     const int runs = (nf + kPitchRun - 1) / kPitchRun;
     rc = launch(n_streams * runs, kPitchThreads, sizeof(PitchShared), [&](void *sm) {

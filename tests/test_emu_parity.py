@@ -189,3 +189,12 @@ def test_speculative_biquad_recomputes_what_it_misses(model_blob):
     L.ns_emu_hp_respeculated()
     emu_process(model_blob, x[3:4], chunk=7)
     assert L.ns_emu_hp_respeculated() == 0
+
+
+def test_both_forms_of_the_biquad_kernel_give_the_same_bits(model_blob, sig, monkeypatch):
+    """K0 exists as one recursion warp (full batches) and parallel in time (small batches): same output, same state."""
+    a = emu_process(model_blob, sig, chunk=8)
+    monkeypatch.setenv("CRISPY_NS_HP_PAR", "0")
+    b = emu_process(model_blob, sig, chunk=8)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(canonical_state(a[3]).view(np.uint32), canonical_state(b[3]).view(np.uint32))

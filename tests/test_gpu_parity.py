@@ -471,3 +471,27 @@ def test_both_sinc_kernels_give_the_same_bits(monkeypatch):
     # 32 kHz -> 48 kHz sits on the edge of the second kernel's range (M / L = 2 / 3)
     y = cb.sinc_resample(x[:2, :32000].contiguous(), 32000, 48000)
     assert np.array_equal(y[1].cpu().numpy(), po.sinc_resample(x[1, :32000].cpu().numpy(), 32000, 48000))
+
+
+def test_both_forms_of_the_biquad_kernel_give_the_same_bits(model, monkeypatch):
+    """K0 runs as one recursion warp beside the pitch CTAs of a full batch and parallel in time (one warp speculating in
+    f32, four running upstream's f64 expression from its recorded states) on small batches; CRISPY_NS_HP_PAR forces
+    either.  Same output, VAD and state bit for bit -- also through digital silence, where the speculation is repaired
+    (a state decaying through 2^-126), on PCM16 input and with a ragged last CTA."""
+    x = make_signal(70, 120, seed=77)
+    x[3, 480 * 4:] = 0.0          # decays into digital silence: the low product underflows on the way
+    x[40] *= np.float32(3e-40)    # ~1e-36: lives where the speculation misses all the time
+    x[69, : 480 * 50] = 0.0
+    xi = np.clip(np.rint(x), -32768, 32767).astype(np.int16)
+    res = []
+    for par in ("1", "0"):
+        monkeypatch.setenv("CRISPY_NS_HP_PAR", par)
+        den = cb.BatchDenoiser(70, model)
+        out, vad = den.process_streams(_dev(x), unit_scale=False)
+        st = den.save_state()
+        den16 = cb.BatchDenoiser(70, model)
+        o16, _ = den16.process_streams(_dev(xi), unit_scale=False, out_i16=True)
+        res.append((out.cpu(), vad.cpu(), st, o16.cpu()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert res[0][2] == res[1][2]
+    assert torch.equal(res[0][3], res[1][3])
