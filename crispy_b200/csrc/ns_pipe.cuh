@@ -248,30 +248,34 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// K0, second form (NS_HP_PAR, the default): THE SAME RECURSION, PARALLEL IN TIME.
+// K0, second form (ns_highpass_par_kernel; what small batches run): THE SAME RECURSION, PARALLEL IN TIME.
 //
-// What bounds the single recursion warp above is not a latency chain but the FP64 pipe of its SM sub-partition: a
-// sample costs nine instructions there (five F2F, two DFMA, DMUL, DADD) at ~8 issue cycles each = 72 of the 74
-// cycles measured (scripts/micro/hp_latency.cu; speculating mem0 in f32 on the same warp while it still verifies
-// in f64 is therefore SLOWER: 82 cycles, variants 5 / 6).  So the f64 work is taken off the serial warp altogether
-// and spread over other sub-partitions:
-//   warp 0          : runs the recursion SPECULATIVELY in error-free f32 arithmetic, no f64 at all (~36 cycles a
-//                     sample, all 4-cycle FADD / FMUL / FFMA), and only records its state at the start of every
-//                     24-sample segment (and at the tile's end);
-//   warps 3, 5, 6, 7: segment v of every tile by upstream's own f64 expression (exact4), STARTING FROM THE RECORDED
-//                     STATE, four segments in parallel on the FP64 pipes of three other sub-partitions; they write
-//                     y, and compare the state they end in, bit for bit, with the state recorded for the next segment;
-//   warp 1 / warp 2 : loader and storer as before (y now has a ring of its own: x must survive a recomputation).
+// The single recursion warp above spends its 74 cycles per sample on the f64 side of its SM sub-partition: five F2F
+// conversions (~10 issue cycles each per warp, scripts/micro/fp64_rate.cu) and four f64 operations, on a chain of
+// FADD -> F2F -> DFMA -> DADD -> F2F (scripts/micro/hp_latency.cu; speculating mem0 in f32 on the same warp while it
+// still verifies in f64 is therefore SLOWER: 81 cycles, variants 5 / 6).  Here the f64 work leaves the serial warp:
+//   warp 0          : runs the recursion SPECULATIVELY in error-free f32 arithmetic, no f64 at all (47 cycles a
+//                     sample: ~30 FADD / FMUL / FFMA / FSEL, whose dependent latency is ~5.8 cycles on this part), and
+//                     only records its state at the start of every 24-sample segment (and at the tile's end);
+//   warps 3, 5, 6, 7: segment v of every tile by upstream's own f64 expression (exact_run), STARTING FROM THE RECORDED
+//                     STATE, four segments in parallel on the other sub-partitions; they write y, and compare the
+//                     state they end in, bit for bit, with the state recorded for the next segment;
+//   warp 1 / warp 2 : loader and storer as before (y now has a ring of its own: x must survive a repair).
 // By induction over the segments, every y the storer sees comes out of upstream's expression from a start state that
 // is upstream's: the result is upstream's bits BY CONSTRUCTION, whatever the speculation does.  Where a segment's
 // end state differs from the record (any bit, the sign of a zero included), warp 0 takes the segment's exact end
 // state, recomputes the rest of that tile exactly, and speculates the next tile again, before the next tile is
-// released to the exact warps.
-// The f32 speculation: a0 y = ph + pl exactly (FMUL + FFMA), m1 - 2x = ch + cl exactly (TwoSum, off the chain),
-// ch + ph = s1 + e1 exactly, and RN32(s1 + ((cl + pl) + e1)) is upstream's RN32(RN53(m1 + RN53(a0 y - 2x))) unless the
-// sum sits within ~2^-22 ulp of a rounding boundary or the low product underflows; mem1 = RN32(x - a1 y) alike.  On
-// the host: no mismatch in 1e9 samples of speech-like, white, DC, tonal, PCM16 and tiny inputs; ~300 per decay into
-// digital silence (the state crossing 2^-126); subnormal limit cycles that cross -0 miss once per ~800 samples.
+// released to the exact warps (`settle`).
+// The f32 speculation: a0 y = ph + pl exactly (FMUL + FFMA), m1 - 2x = ch + cl exactly, ch + ph = s1 + e1 exactly
+// (error terms by FastTwoSum on operands ordered by magnitude), and RN32(s1 + ((cl + pl) + e1)) is upstream's
+// RN32(RN53(m1 + RN53(a0 y - 2x))) unless the sum sits within ~2^-22 ulp of a rounding boundary or the low product
+// underflows; mem1 = RN32(x - a1 y) alike.  On the host: no mismatch in 1e9 samples of speech-like, white, DC, tonal,
+// PCM16 and tiny inputs; ~300 per decay into digital silence (the state crossing 2^-126); subnormal limit cycles that
+// cross -0 miss once per ~800 samples; 0.08 % of the bench workload's tiles need a repair.
+// Measured (B200, 1,024 streams x 32 frames, the kernel alone): 613 -> 475 us; per tile the speculation warp works
+// 4,550 cycles, waits 140 for the loader and spends 810 in `settle` (-DNS_HP_CLOCKS).  In the pipeline it is worth
+// +3 % at 768 streams, +11 % at 512, +17 % at 256, and nothing beside the pitch CTAs of a full batch, where K0 is not
+// the longest stage and its eight warps take issue slots from them: crispy_ns.cu picks the form by batch size.
 // Warp 4 would share warp 0's sub-partition and exits at once.
 // -------------------------------------------------------------------------------------------------
 #ifndef NS_HP_PAR
@@ -418,7 +422,7 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
             // mem0' = RN32(m1 - 2x + a0 y)
             const float ph = a0f * yi, pl = fmaf(a0f, yi, -ph);
             const float b = -2.0f * xi;
-            const float ch = m1 + b, cbb = ch - m1, cl = (m1 - (ch - cbb)) + (b - cbb);
+            const float ch = m1 + b, cl = hp_fast_err(m1, b, ch);  // m1 arrives late: the short form matters here too
             const float s1 = ch + ph;
             const float e1 = hp_fast_err(ch, ph, s1);
             // mem1' = RN32(x - a1 y)

@@ -91,16 +91,18 @@ struct Simt {
   // orders this thread's earlier generic-proxy accesses to shared memory before its later async-proxy copies
   static NS_DEV void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
   // shared-memory flags between the specialised warps of one CTA (no bar.sync): values only grow
-  static NS_DEV void fence_cta() { __threadfence_block(); }
+  // release / acquire ordering between the warps of a CTA: fence.acq_rel.cta (MEMBAR.ALL.CTA).  __threadfence_block()
+  // is the sequentially consistent fence (MEMBAR.SC.CTA), which the flag hand-overs below do not need.
+  static NS_DEV void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
   static NS_DEV void flag_set(int *f, int v) {
-    __threadfence_block();
+    fence_cta();
     *reinterpret_cast<volatile int *>(f) = v;
   }
   static NS_DEV void flag_wait(const int *f, int v, bool relaxed) {
     while (*reinterpret_cast<const volatile int *>(f) < v) {
       if (relaxed) __nanosleep(200);
     }
-    __threadfence_block();
+    fence_cta();
   }
   // the same two without their fence, for a warp that waits on / raises several flags around ONE fence_cta()
   static NS_DEV void flag_store(int *f, int v) { *reinterpret_cast<volatile int *>(f) = v; }
