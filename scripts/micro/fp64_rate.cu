@@ -22,8 +22,8 @@ __global__ void k(long long *cycles, float *sink, int iters, float seed) {
       if (OP == 2) d[i] = d[i] + 1.25;                                              // DADD
       if (OP == 3) d[i] = d[i] * 1.0000001;                                         // DMUL
       if (OP == 4) f[i] = __fadd_rn(f[i], 1.25f);                                   // FADD
-      if (OP == 5) d[i] = d[i] + (double)f[i];                                      // F2F.F64.F32 + DADD
-      if (OP == 6) f[i] = __fadd_rn(f[i], __double2float_rn(d[i]));                 // F2F.F32.F64 + FADD
+      if (OP == 5) d[i] = d[i] + (double)f[i], f[i] = __fadd_rn(f[i], 1.0f);        // F2F.F64.F32 + DADD + FADD
+      if (OP == 6) f[i] = __fadd_rn(f[i], __double2float_rn(d[i])), d[i] = d[i] + 1.25;  // F2F.F32.F64 + FADD + DADD
     }
   }
   const long long t1 = clock64();
@@ -40,7 +40,7 @@ int main() {
   cudaMalloc(&c, 8 * 16);
   cudaMalloc(&s, 4 * 1024);
   const int iters = 20000;
-  const char *names[] = {"F2F.F64.F32 + F2F.F32.F64 + FADD", "DFMA", "DADD", "DMUL", "FADD", "F2F.F64.F32 + DADD", "F2F.F32.F64 + FADD"};
+  const char *names[] = {"F2F.F64.F32 + F2F.F32.F64 + FADD", "DFMA", "DADD", "DMUL", "FADD", "F2F.F64.F32 + DADD + FADD", "F2F.F32.F64 + FADD + DADD"};
   for (int op = 0; op < 7; op++) {
     printf("%-36s", names[op]);
     for (int warps : {1, 2, 4, 8}) {
