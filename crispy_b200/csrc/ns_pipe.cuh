@@ -309,9 +309,9 @@ struct HpParSmem {
   float y[kHpYStages][32][kHpPitch];         // the y ring
   float spec[2][kHpSeg + 1][32][2];          // speculated (mem0, mem1) at the start of segment v / at the tile's end
   float exact[2][kHpSeg][32][2];             // upstream's (mem0, mem1) at the end of segment v
-  int bad[2][kHpSeg][32];                    // 1: segment v ended in a state that is not the recorded one
+  alignas(16) int bad[2][32][kHpSeg];        // 1: segment v ended in a state that is not the recorded one
   int go;                                    // tiles < go are speculated and every earlier tile is settled
-  int ver[kHpSeg];                           // tiles < ver[v] have had segment v computed
+  int ver;                                   // kHpSeg x the number of tiles every exact warp is through
   int ydone;                                 // tiles < ydone are final in the y ring
   int yfreed;                                // tiles < yfreed have been stored
 };
@@ -334,8 +334,7 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
   const int ntiles = nsamp / kHpTile;
   const bool tail_direct = nsamp >= kHist;  // the new history is the chunk's own tail
   if (tid < kHpStages) sm.x.landed[tid] = sm.x.done[tid] = sm.x.freed[tid] = 0;
-  if (tid < kHpSeg) sm.ver[tid] = 0;
-  if (tid == 0) sm.go = sm.ydone = sm.yfreed = 0;
+  if (tid == 0) sm.ver = sm.go = sm.ydone = sm.yfreed = 0;
   Simt::cta_sync();
   const long long in0 = (long long)p.frame0 * kFrame;
   const bool in16 = (p.flags & kFlagInI16) != 0;
@@ -438,13 +437,15 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
     };
     // tile k has been through the exact warps: repair it if a segment ended off the record, then hand it on
     auto settle = [&](int k, bool next_speculated) {
-      for (int v = 0; v < kHpSeg; v++) Simt::flag_poll(&sm.ver[v], k + 1, false);
+      Simt::flag_poll(&sm.ver, kHpSeg * (k + 1), false);  // the exact warps are at most one tile apart: a sum will do
       Simt::fence_cta();
       if (valid) {
-        int v0 = -1;
-#pragma unroll
-        for (int v = kHpSeg - 1; v >= 0; v--)
-          if (sm.bad[k & 1][v][lane]) v0 = v;
+        static_assert(kHpSeg == 4, "one 16-byte load fetches a lane's four flags");
+        struct alignas(16) I4 {
+          int x, y, z, w;
+        };
+        const I4 bd = *reinterpret_cast<const I4 *>(sm.bad[k & 1][lane]);
+        const int v0 = bd.x ? 0 : bd.y ? 1 : bd.z ? 2 : bd.w ? 3 : -1;
         if (v0 >= 0) {
           NS_HP_COUNT_RESPEC();
           m0 = sm.exact[k & 1][v0][lane][0], m1 = sm.exact[k & 1][v0][lane][1];  // upstream's state after segment v0
@@ -551,13 +552,13 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
         m0 = sm.spec[n & 1][v][lane][0], m1 = sm.spec[n & 1][v][lane][1];
         exact_run(sm.x.tile[n % kHpStages][lane] + v * kHpSegLen, sm.y[n % kHpYStages][lane] + v * kHpSegLen, kHpSegLen / 4);
         sm.exact[n & 1][v][lane][0] = m0, sm.exact[n & 1][v][lane][1] = m1;
-        sm.bad[n & 1][v][lane] =
+        sm.bad[n & 1][lane][v] =
             (f2u(m0) != f2u(sm.spec[n & 1][v + 1][lane][0])) | (f2u(m1) != f2u(sm.spec[n & 1][v + 1][lane][1]));
       }
       Simt::fence_cta();
       Simt::warp_sync();
       NS_HP_ACC(t_work);
-      if (lane == 0) Simt::flag_set(&sm.ver[v], n + 1);
+      if (lane == 0) Simt::atomic_add_shared(&sm.ver, 1);
     }
   }
 #if defined(NS_HP_CLOCKS) && defined(__CUDACC__) && !defined(NS_HOST_EMU)
