@@ -272,9 +272,9 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
 // underflows; mem1 = RN32(x - a1 y) alike.  On the host: no mismatch in 1e9 samples of speech-like, white, DC, tonal,
 // PCM16 and tiny inputs; ~300 per decay into digital silence (the state crossing 2^-126); subnormal limit cycles that
 // cross -0 miss once per ~800 samples; 0.08 % of the bench workload's tiles need a repair.
-// Measured (B200, 1,024 streams x 32 frames, the kernel alone): 613 -> 475 us; per tile the speculation warp works
-// 4,550 cycles, waits 140 for the loader and spends 810 in `settle` (-DNS_HP_CLOCKS).  In the pipeline it is worth
-// +3 % at 768 streams, +11 % at 512, +17 % at 256, and nothing beside the pitch CTAs of a full batch, where K0 is not
+// Measured (B200, 1,024 streams x 32 frames, the kernel alone): 613 -> 461 us; per tile the speculation warp works
+// 4,540 cycles, waits 140 for the loader and spends 630 in `settle` (-DNS_HP_CLOCKS).  In the pipeline it is worth
+// +3 % at 768 streams, +12 % at 512, +22 % at 256, and nothing beside the pitch CTAs of a full batch, where K0 is not
 // the longest stage and its eight warps take issue slots from them: crispy_ns.cu picks the form by batch size.
 // Warp 4 would share warp 0's sub-partition and exits at once.
 // -------------------------------------------------------------------------------------------------
