@@ -251,7 +251,7 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
 // K0, second form (ns_highpass_par_kernel; what small batches run): THE SAME RECURSION, PARALLEL IN TIME.
 //
 // The single recursion warp above spends its 74 cycles per sample on the f64 side of its SM sub-partition: five F2F
-// conversions (~10 issue cycles each per warp, scripts/micro/fp64_rate.cu) and four f64 operations, on a chain of
+// conversions (one warp issues one per ~13-19 cycles, scripts/micro/fp64_rate.cu) and four f64 operations, on a chain of
 // FADD -> F2F -> DFMA -> DADD -> F2F (scripts/micro/hp_latency.cu; speculating mem0 in f32 on the same warp while it
 // still verifies in f64 is therefore SLOWER: 81 cycles, variants 5 / 6).  Here the f64 work leaves the serial warp:
 //   warp 0          : runs the recursion SPECULATIVELY in error-free f32 arithmetic, no f64 at all (47 cycles a
