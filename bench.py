@@ -581,6 +581,9 @@ def run_b200(args):
                 "peak_source": peak_src, "kernel": dom["kernel"],
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_FRAME * dom["frames_per_launch"],
                 "avg_launch_us": dom["avg_launch_us"], "ncu_limiters_pct": dom.get("ncu_limiters_pct"),
+                "traffic_source": "profiles/traffic.json: dram bytes and limiter percentages of one `ncu --set full` launch of "
+                                  "this kernel at this batch size (profiles/r2_ncu_full.md), scaled to this run's frames per "
+                                  "launch; achieved / avg_launch_us are measured live in this run",
                 "note": "algorithmic bytes = 3,844 B per (stream, frame) (480 f32 in + 480 f32 out + VAD) x the frames "
                         "one launch covers / that kernel's mean launch time (CUDA events on its own stream, inside the "
                         "timed region, kernels of neighbouring chunks running concurrently). The kernel named is the one "
