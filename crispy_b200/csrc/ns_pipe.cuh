@@ -267,9 +267,9 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
 // state, recomputes the rest of that tile exactly, and speculates the next tile again, before the next tile is
 // released to the exact warps (`settle`).
 // The f32 speculation: a0 y = ph + pl exactly (FMUL + FFMA), m1 - 2x = ch + cl exactly, ch + ph = s1 + e1 exactly
-// (error terms by FastTwoSum on operands ordered by magnitude), and RN32(s1 + ((cl + pl) + e1)) is upstream's
+// (error terms by a two-sided FastTwoSum), and RN32(s1 + ((cl + pl) + e1)) is upstream's
 // RN32(RN53(m1 + RN53(a0 y - 2x))) unless the sum sits within ~2^-22 ulp of a rounding boundary or the low product
-// underflows; mem1 = RN32(x - a1 y) alike.  On the host: no mismatch in 1e9 samples of speech-like, white, DC, tonal,
+// underflows; mem1 = RN32(x - a1 y) is a single f32 FMA.  On the host: no mismatch in 1e9 samples of speech-like, white, DC, tonal,
 // PCM16 and tiny inputs; ~300 per decay into digital silence (the state crossing 2^-126); subnormal limit cycles that
 // cross -0 miss once per ~800 samples; 0.08 % of the bench workload's tiles need a repair.
 // Measured (B200, 1,024 streams x 32 frames, the kernel alone): 613 -> 461 us; per tile the speculation warp works
@@ -316,13 +316,11 @@ struct HpParSmem {
   int yfreed;                                // tiles < yfreed have been stored
 };
 
-// a + b - RN32(a + b), exactly: FastTwoSum with the operands ordered by magnitude first.  The ordering does not need
-// the sum, so behind s = a + b only two dependent operations remain on the recursion's chain (TwoSum: four; a
-// dependent FADD costs ~5.8 cycles on this part, scripts/micro/hp_latency.cu variants 7-9)
+// a + b - RN32(a + b), exactly: FastTwoSum both ways round; the one whose first operand is the larger is exact
+// (scripts/micro/hp_latency.cu variant 16: 45.8 cycles a sample; TwoSum 47.3, operands ordered first 50.3)
 NS_DEV float hp_fast_err(float a, float b, float s) {
-  const bool a_big = fabsf(a) >= fabsf(b);
-  const float big = a_big ? a : b, small = a_big ? b : a;
-  return small - (s - big);
+  const float ea = b - (s - a), eb = a - (s - b);
+  return fabsf(a) >= fabsf(b) ? ea : eb;
 }
 
 NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
@@ -418,18 +416,16 @@ NS_DEV void highpass_par_body(const Params &p, HpParSmem &sm) {
           for (int i = 0; i < 4; i++) {
             const float xi = x[i];
             const float yi = xi + m0;
-            // mem0' = RN32(m1 - 2x + a0 y)
+            // mem0' = RN32(m1 - 2x + a0 y): a0 y = ph + pl, m1 - 2x = ch + cl, ch + ph = s1 + e1, all exactly
             const float ph = a0f * yi, pl = fmaf(a0f, yi, -ph);
             const float b = -2.0f * xi;
-            const float ch = m1 + b, cl = hp_fast_err(m1, b, ch);  // m1 arrives late: the short form matters here too
+            const float ch = fmaf(-2.0f, xi, m1), cl = hp_fast_err(m1, b, ch);
             const float s1 = ch + ph;
             const float e1 = hp_fast_err(ch, ph, s1);
-            // mem1' = RN32(x - a1 y)
-            const float qh = na1f * yi, ql = fmaf(na1f, yi, -qh);
-            const float s2 = xi + qh;
-            const float e2 = hp_fast_err(xi, qh, s2);
             m0 = s1 + ((cl + pl) + e1);
-            m1 = s2 + (e2 + ql);
+            // mem1' = RN32(x - a1 y) is ONE f32 FMA: exact product, one rounding (upstream rounds to 53 bits first,
+            // which matters with probability ~2^-29 -- and then the exact warps notice)
+            m1 = fmaf(na1f, yi, xi);
           }
         }
       }

@@ -19,7 +19,7 @@ __global__ void k(const float *x, float *y, int n, long long *cycles, float *mou
   __syncwarp();
   float m0 = 0.f, m1 = 0.f;
   const double a0 = (double)-1.99599f, a1 = (double)0.99600f;
-  float acc = 0.f;
+  float acc = 0.f, acc2 = 0.f, m0_prev = 0.f;
   int bad = 0;
   long long t0 = clock64();
   for (int i = 0; i < n; i++) {
@@ -63,6 +63,52 @@ __global__ void k(const float *x, float *y, int n, long long *cycles, float *mou
       m1 = (float)fma(-a1, yd, xd);
       bad += (__float_as_uint(m0s) != __float_as_uint(m0r));
       m0 = m0s;
+    } else if (V == 15 || V == 16) {
+      // mem1 = RN32(x - a1 y) IS one f32 FMA (exact product, one rounding; upstream rounds to 53 bits first, which
+      // differs with probability ~2^-29), and -2x folds into FMAs: 19 instructions a sample instead of 30.
+      // 15: error terms by TwoSum; 16: by the two-sided FastTwoSum
+      const float a0f = 1.99599f, na1f = -0.99600f;
+      const float ph = __fmul_rn(a0f, yi), pl = __fmaf_rn(a0f, yi, -ph);
+      const float ch = __fmaf_rn(-2.0f, xi, m1);
+      const float s1 = __fadd_rn(ch, ph);
+      float cl, e1;
+      if (V == 15) {
+        const float cbb = __fsub_rn(ch, m1), sbb = __fsub_rn(s1, ch);
+        cl = __fadd_rn(__fsub_rn(m1, __fsub_rn(ch, cbb)), __fmaf_rn(-2.0f, xi, -cbb));
+        e1 = __fadd_rn(__fsub_rn(ch, __fsub_rn(s1, sbb)), __fsub_rn(ph, sbb));
+      } else {
+        const float b = -2.0f * xi;
+        cl = (fabsf(m1) >= fabsf(b)) ? __fsub_rn(b, __fsub_rn(ch, m1)) : __fsub_rn(m1, __fsub_rn(ch, b));
+        e1 = (fabsf(ch) >= fabsf(ph)) ? __fsub_rn(ph, __fsub_rn(s1, ch)) : __fsub_rn(ch, __fsub_rn(s1, ph));
+      }
+      m1 = __fmaf_rn(na1f, yi, xi);
+      m0 = __fadd_rn(s1, __fadd_rn(__fadd_rn(cl, pl), e1));
+    } else if (V >= 11 && V <= 14) {
+      // what bounds the speculation warp?  11: the head fused (s1 = fma(a0, y, ch), error two-sided); 12: as 8 with mem1
+      // taken out of the loop (main chain alone); 13: as 8 without e1 (a chain of five: NOT exact, depth probe);
+      // 14: as 8 with the chain cut (y from the state two samples back: the same instructions, issue-bound)
+      const float a0f = 1.99599f, na1f = -0.99600f;
+      const float yy = (V == 14) ? xi + m0_prev : yi;
+      const float ph = __fmul_rn(a0f, yy), pl = __fmaf_rn(a0f, yy, -ph);
+      const float b = -2.0f * xi;
+      const float ch = __fadd_rn(m1, b), cbb = __fsub_rn(ch, m1);
+      const float cl = __fadd_rn(__fsub_rn(m1, __fsub_rn(ch, cbb)), __fsub_rn(b, cbb));
+      float s1, e1;
+      if (V == 11) {
+        s1 = __fmaf_rn(a0f, yy, ch);
+        const float ea = __fadd_rn(__fsub_rn(ch, s1), ph), eb = __fadd_rn(__fsub_rn(ph, s1), ch);
+        e1 = __fadd_rn(fabsf(ch) >= fabsf(ph) ? ea : eb, pl);
+      } else {
+        s1 = __fadd_rn(ch, ph);
+        const float sbb = __fsub_rn(s1, ch);
+        e1 = (V == 13) ? 0.f : __fadd_rn(__fsub_rn(ch, __fsub_rn(s1, sbb)), __fsub_rn(ph, sbb));
+      }
+      const float qh = __fmul_rn(na1f, yy), ql = __fmaf_rn(na1f, yy, -qh);
+      const float s2 = __fadd_rn(xi, qh), tbb = __fsub_rn(s2, xi);
+      const float e2 = __fadd_rn(__fsub_rn(xi, __fsub_rn(s2, tbb)), __fsub_rn(qh, tbb));
+      m0_prev = m0;
+      m0 = (V == 11) ? __fadd_rn(s1, __fadd_rn(cl, e1)) : __fadd_rn(s1, __fadd_rn(__fadd_rn(cl, pl), e1));
+      if (V == 12) acc2 += __fadd_rn(s2, __fadd_rn(e2, ql)); else m1 = __fadd_rn(s2, __fadd_rn(e2, ql));
     } else if (V == 10) {  // as the kernel now: every error term by the ordered FastTwoSum, m1 - 2x included
       const float a0f = 1.99599f, na1f = -0.99600f;
       const float ph = __fmul_rn(a0f, yi), pl = __fmaf_rn(a0f, yi, -ph);
@@ -118,7 +164,7 @@ __global__ void k(const float *x, float *y, int n, long long *cycles, float *mou
     cycles[0] = t1 - t0;
   }
   y[threadIdx.x] = acc;
-  mout[threadIdx.x] = m0 + m1 + (float)bad;
+  mout[threadIdx.x] = m0 + m1 + (float)bad + acc2 + m0_prev;
 }
 
 int main() {
@@ -139,7 +185,7 @@ int main() {
   cudaDeviceSynchronize();                                       \
   cudaMemcpy(&hc, c, 8, cudaMemcpyDeviceToHost);                 \
   printf("variant %d: %.1f cycles/sample (%s)\n", V, (double)hc / n, cudaGetErrorString(cudaGetLastError()));
-  RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10)
+  RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10) RUN(11) RUN(12) RUN(13) RUN(14) RUN(15) RUN(16)
   {
     float hm[32];
     cudaMemcpy(hm, m, sizeof(hm), cudaMemcpyDeviceToHost);
