@@ -53,7 +53,7 @@ constexpr int kScanWarps = 4;
 #endif
 
 // K0 in its two forms (ns_pipe.cuh): one recursion warp, and parallel in time (one speculating warp + four exact warps).
-// The second is the faster kernel (isolated 613 -> 461 us per 32,768 frames) and wins wherever K0 bounds the pipeline
+// The second is the faster kernel (isolated 613 -> 424 us per 32,768 frames) and wins wherever K0 bounds the pipeline
 // (small batches, where it also has its SMs to itself); beside the pitch CTAs of a full batch its eight warps cost the
 // parallel kernels what its shorter run gives back, so the first form stays there (crispy_ns_batch::hp_par).
 __global__ void __launch_bounds__(ns::kHpThreads) ns_highpass_kernel(const __grid_constant__ ns::Params p) {

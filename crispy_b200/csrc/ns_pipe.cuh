@@ -254,8 +254,8 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
 // conversions (one warp issues one per ~13-19 cycles, scripts/micro/fp64_rate.cu) and four f64 operations, on a chain of
 // FADD -> F2F -> DFMA -> DADD -> F2F (scripts/micro/hp_latency.cu; speculating mem0 in f32 on the same warp while it
 // still verifies in f64 is therefore SLOWER: 81 cycles, variants 5 / 6).  Here the f64 work leaves the serial warp:
-//   warp 0          : runs the recursion SPECULATIVELY in error-free f32 arithmetic, no f64 at all (47 cycles a
-//                     sample: ~30 FADD / FMUL / FFMA / FSEL, whose dependent latency is ~5.8 cycles on this part), and
+//   warp 0          : runs the recursion SPECULATIVELY in error-free f32 arithmetic, no f64 at all (43 cycles a
+//                     sample: ~20 FADD / FMUL / FFMA / FSEL, whose dependent latency is ~5.8 cycles on this part), and
 //                     only records its state at the start of every 24-sample segment (and at the tile's end);
 //   warps 3, 5, 6, 7: segment v of every tile by upstream's own f64 expression (exact_run), STARTING FROM THE RECORDED
 //                     STATE, four segments in parallel on the other sub-partitions; they write y, and compare the
@@ -272,9 +272,9 @@ NS_DEV void highpass_body(const Params &p, HpSmem &sm) {
 // underflows; mem1 = RN32(x - a1 y) is a single f32 FMA.  On the host: no mismatch in 1e9 samples of speech-like, white, DC, tonal,
 // PCM16 and tiny inputs; ~300 per decay into digital silence (the state crossing 2^-126); subnormal limit cycles that
 // cross -0 miss once per ~800 samples; 0.08 % of the bench workload's tiles need a repair.
-// Measured (B200, 1,024 streams x 32 frames, the kernel alone): 613 -> 461 us; per tile the speculation warp works
-// 4,540 cycles, waits 140 for the loader and spends 630 in `settle` (-DNS_HP_CLOCKS).  In the pipeline it is worth
-// +3 % at 768 streams, +12 % at 512, +22 % at 256, and nothing beside the pitch CTAs of a full batch, where K0 is not
+// Measured (B200, 1,024 streams x 32 frames, the kernel alone): 613 -> 424 us; per tile the speculation warp works
+// 4,160 cycles, waits 130 for the loader and spends 610 in `settle` (-DNS_HP_CLOCKS).  In the pipeline it is worth
+// +3 % at 768 streams, +18 % at 512, +37 % at 256, and nothing beside the pitch CTAs of a full batch, where K0 is not
 // the longest stage and its eight warps take issue slots from them: crispy_ns.cu picks the form by batch size.
 // Warp 4 would share warp 0's sub-partition and exits at once.
 // -------------------------------------------------------------------------------------------------
