@@ -306,6 +306,17 @@ def run_b200(args):
         parity = {"streams": ns_p, "frames": nf_p, "max_abs_fs": float(np.abs(err).max()),
                   "snr_db": float(10 * np.log10((ref.astype(np.float64) ** 2).mean() / max((err ** 2).mean(), 1e-30))),
                   "vad_max": float(np.abs(gv - rv).max())}
+        # the share of frames the silence gate closes (they still ride through K4, which is batched over
+        # 16 streams; RNNoise's gate is E < 0.04 in 16-bit scale, i.e. digital silence: the synthetic streams carry
+        # noise through their pauses, so it stays at or near 0 here)
+        try:
+            den_t = cb.BatchDenoiser(ns_p, device=local)
+            _, _, taps_t = den_t.process_streams(x[:ns_p, :nf_p * FRAME], unit_scale=True, return_taps=True)
+            parity["silent_fraction"] = float((taps_t[:, :, 133] != 0).float().mean().item())
+            del den_t, taps_t
+        except Exception as e:  # a reporting extra: never take the bench line down
+            parity["silent_fraction"] = None
+            parity["silent_fraction_error"] = repr(e)[:200]
 
     # ---- device-resident timing -----------------------------------------------------------------
     for _ in range(max(3, args.warmup)):
@@ -605,6 +616,57 @@ def run_b200(args):
                                    "peak_tmacs": fp32["unfused_tmacs"]}
             ent["fp32_unfused"]["frac"] = ent["fp32_unfused"]["achieved_tmacs"] / fp32["unfused_tmacs"]
 
+    # ---- north_star: "each phase reported at a stated fraction of its roofline" -------------------------------
+    # analysis = K0 + K1 + K2 + K3 + K3b, recurrent = K4, synthesis = K5.  A phase's cost per chunk is its share of the
+    # SM-time x the pipeline's period (the kernels of neighbouring chunks overlap, so in-pipeline launch times do not
+    # add up to the period; the SM-time shares do).  HBM roofline for analysis and synthesis (algorithmic bytes:
+    # analysis reads the 480 f32 of a frame, synthesis writes them + VAD); tensor and FP32 rooflines for the
+    # recurrent phase (175,006 algorithmic flop per frame).
+    phases = None
+    try:
+        by = {e["kernel"]: e for e in kernels}
+        tpeak, tsrc = measured_tensor_peak()
+
+        fpl = dom["frames_per_launch"]
+        period_us = total_ms_max / args.steps * 1e3 / (dom["launches"] / prof_steps)  # one chunk leaves the pipeline every ...
+
+        def sm_us(names):  # the phase's share of the SM-time x the pipeline's period: the shares sum to the period
+            return sum(by[k]["share_of_sm_time"] for k in names if k in by) * period_us
+
+        ana = ("ns_highpass_kernel", "ns_highpass_par_kernel", "ns_pitch_kernel", "ns_pitchscan_kernel",
+               "ns_spectrum_kernel", "ns_features_kernel")
+        t_ana, t_rnn, t_syn = sm_us(ana), sm_us(("ns_rnn_kernel", "ns_rnn_tc5_kernel")), sm_us(("ns_synthesis_kernel",))
+        t_all = (t_ana + t_rnn + t_syn) or 1.0
+        phases = {
+            "how": "the kernels of neighbouring chunks run concurrently, so a phase's cost per chunk is its share of the "
+                   "SM-time (in-pipeline launch time x fraction of the 148 SMs its grid covers, kernels[].share_of_sm_time) "
+                   "x the pipeline's period (one chunk every period_us); the three add up to the period; achieved = "
+                   "algorithmic bytes or flops of one chunk / that time",
+            "frames_per_chunk": fpl, "period_us": period_us,
+            "analysis": {"kernels": [k for k in ana if k in by], "gpu_time_us_per_chunk": t_ana, "share": t_ana / t_all,
+                         "bound": "hbm", "algorithmic_bytes_per_frame": 1920,
+                         "achieved_gbs": 1920 * fpl / (t_ana * 1e-6) / 1e9 if t_ana else None,
+                         "frac": 1920 * fpl / (t_ana * 1e-6) / 1e9 / hbm_peak if t_ana else None,
+                         "limited_by": "issue slots and shared-memory wavefronts (K1 60 % / 64 %, K3 60 % / 58 %), "
+                                       "DRAM 2-16 % busy: profiles/r2_ncu_full.md"},
+            "recurrent": {"kernels": [k for k in ("ns_rnn_kernel", "ns_rnn_tc5_kernel") if k in by],
+                          "gpu_time_us_per_chunk": t_rnn, "share": t_rnn / t_all, "bound": "tensor",
+                          "algorithmic_flops_per_frame": RNN_FLOPS_PER_FRAME,
+                          "achieved_tflops": RNN_FLOPS_PER_FRAME * fpl / (t_rnn * 1e-6) / 1e12 if t_rnn else None,
+                          "frac_of_tensor_peak": RNN_FLOPS_PER_FRAME * fpl / (t_rnn * 1e-6) / 1e12 / tpeak if t_rnn else None,
+                          "frac_of_measured_fp32_peak": RNN_FLOPS_PER_FRAME * fpl / (t_rnn * 1e-6) / 1e12 / fp32["ffma_tflops"] if t_rnn else None,
+                          "tensor_peak_source": tsrc,
+                          "limited_by": "latency of 8 dependent matrix products per frame step, serial in time "
+                                        "(HMMA pipe 13 % busy): profiles/r2_k4_tcgen05.md"},
+            "synthesis": {"kernels": ["ns_synthesis_kernel"], "gpu_time_us_per_chunk": t_syn, "share": t_syn / t_all,
+                          "bound": "hbm", "algorithmic_bytes_per_frame": 1924,
+                          "achieved_gbs": 1924 * fpl / (t_syn * 1e-6) / 1e9 if t_syn else None,
+                          "frac": 1924 * fpl / (t_syn * 1e-6) / 1e9 / hbm_peak if t_syn else None,
+                          "limited_by": "issue slots 59 %, shared-memory wavefronts 54 %, DRAM 23 % busy"},
+        }
+    except Exception as e:  # a reporting extra: never take the bench line down
+        phases = {"error": repr(e)[:200]}
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
         cpu_baseline = cpu_reference_rate(target_seconds=8.0, seconds_per_stream=args.seconds)
@@ -623,7 +685,7 @@ def run_b200(args):
                    "weights": "synthetic seed 0 (nnnoiseless weights are not available offline)"},
         "clocks": clocks, "e2e": e2e, "e2e_pcm16": (e2e or {}).get("pcm16_link"), "gpu_launches": int(launches),
         "roofline": roofline, "kernels": kernels, "kernels_isolated": kernels_isolated, "roofline_fp32": roofline_fp32,
-        "front_end": front_end,
+        "phases": phases, "front_end": front_end,
         "cpu_baseline": cpu_baseline,
         "parity_vs_oracle": parity, "wall_s_timed_region": t_wall,
     }

@@ -849,8 +849,9 @@ int batch_create(const crispy_ns_model *model, int device, int n_streams, crispy
   up((void **)&b->d_bias, pk.bias.data(), pk.bias.size() * sizeof(float));
   {
     // K4 variant: $CRISPY_NS_RNN = "tc5" (tcgen05 / tensor memory, 128 streams per CTA) or "mma" (warp-level mma.sync,
-    // 16 streams per CTA).  Default: tc5 from 512 streams on -- it holds 8 SMs per 1,024 streams instead of 64, which
-    // the parallel kernels get back; below that its longer step (thirteen rounds per frame) is not worth it.
+    // 16 streams per CTA).  Default: mma.  tc5 holds 8 SMs per 1,024 streams instead of 64, which the parallel kernels
+    // get back, but its step is longer (thirteen rounds per frame) and the pipeline measured no faster with it
+    // (profiles/r2_k4_tcgen05.md), so it stays opt-in (NS_RNN_TC5_MIN_STREAMS).
     // K0 alone on its SMs: $CRISPY_NS_HP_EXCLUSIVE = 1 / 0, default by batch size
     const char *hx = getenv("CRISPY_NS_HP_EXCLUSIVE");
     b->hp_exclusive = hx ? atoi(hx) != 0 : n_streams <= NS_HP_EXCLUSIVE_MAX_STREAMS;
