@@ -123,6 +123,50 @@ def test_wav_roundtrip_and_header(tmp_path):  # recording.rs:406-480
         cb.wav_read_pcm16(str(tmp_path / "missing.wav"))
 
 
+def test_wav_reader_walks_chunks_like_get_wav_duration(tmp_path):  # commands/recording.rs:385-460
+    """The files either side of the path: what hound 3.5.1 writes for the recorder's spec (recording.rs:85-90: the
+    plain 44-byte PCM header), what ffmpeg's import writes (commands/convert.rs:113-127: a LIST/INFO chunk between
+    fmt and data), an 18-byte fmt chunk, an odd-sized chunk with its pad byte -- all read back sample for sample;
+    anything that is not 16-bit PCM, a truncated data chunk and a non-RIFF file are refused with CRISPY_NS_EIO; a
+    recording that never reached finalize() (hound leaves data size 0) has no frames, where the reference's walk
+    returns None."""
+    import struct
+    q = (np.arange(200, dtype=np.int16) - 100).reshape(100, 2)
+
+    def fmt(n=16, tag=1, ch=2, sr=48000, bits=16, extra=b""):
+        return b"fmt " + struct.pack("<IHHIIHH", n, tag, ch, sr, sr * ch * bits // 8, ch * bits // 8, bits) + extra
+
+    def wav(chunks, data):
+        body = b"WAVE" + b"".join(chunks) + b"data" + struct.pack("<I", len(data)) + data
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+
+    lavf = b"LIST" + struct.pack("<I", 26) + b"INFOISFT" + struct.pack("<I", 14) + b"Lavf60.16.100\0"
+    good = {"hound44": wav([fmt()], q.tobytes()),
+            "ffmpeg_list": wav([fmt(), lavf], q.tobytes()),
+            "fmt18": wav([fmt(18, extra=b"\0\0")], q.tobytes()),
+            "odd_chunk_padded": wav([fmt(), b"junk" + struct.pack("<I", 3) + b"abc\0"], q.tobytes())}
+    assert len(good["hound44"]) == 44 + 400
+    for name, blob in good.items():
+        p = tmp_path / (name + ".wav")
+        p.write_bytes(blob)
+        y, sr = cb.wav_read_pcm16(str(p))
+        assert sr == 48000 and np.array_equal(y, q), name
+    p = tmp_path / "never_finalized.wav"
+    p.write_bytes(wav([fmt()], b""))
+    y, sr = cb.wav_read_pcm16(str(p))
+    assert y.shape == (0, 2) and sr == 48000
+    bad = {"float32": wav([fmt(tag=3, bits=32)], np.zeros(200, np.float32).tobytes()),
+           "pcm24": wav([fmt(bits=24)], bytes(600)),
+           "truncated": wav([fmt()], q.tobytes())[:-50],
+           "not_riff": b"RIFX" + bytes(60),
+           "no_data_chunk": wav([fmt()], q.tobytes())[:36]}
+    for name, blob in bad.items():
+        p = tmp_path / (name + ".wav")
+        p.write_bytes(blob)
+        with pytest.raises(cb.CrispyNsError):
+            cb.wav_read_pcm16(str(p))
+
+
 def test_sinc_front_end_geometry_and_argument_checks():  # no device needed: validation comes first
     L = _lib.lib()
     assert L.crispy_ns_sinc_resample_count(44100, 48000, 441) == 480
