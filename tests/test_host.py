@@ -194,3 +194,61 @@ def test_resample_audio_count_matches_the_oracle():  # recording.rs:19, :27-35; 
                       (999, 48000, 16000), (1000, 16000, 48000), (777, 48000, 48000), (12345, 22050, 48000), (7, 8000, 48000)):
         assert L.crispy_ns_resample_audio_count(n, fr, to) == len(po.resample_audio(np.zeros(n, np.float32), fr, to)), (n, fr, to)
     assert L.crispy_ns_resample_audio_count(100, 0, 48000) == 0
+
+
+def test_rust_shim_extern_block_matches_the_header():
+    """bindings/rust/ns_gpu.rs cannot be compiled here (no rustc), so its `extern "C"` block is checked against
+    include/crispy_ns.h token by token: every function it binds is declared, with the same number of arguments and
+    the same type for each (int -> c_int, float -> c_float, int64_t -> i64, uint32_t -> u32, size_t -> usize,
+    pointers with their const-ness), and the flag constants carry the header's values."""
+    import re
+    h = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "crispy_ns.h")).read(), flags=re.S)
+    rs = open(os.path.join(ROOT, "bindings", "rust", "ns_gpu.rs")).read()
+    scalar = {"int": "c_int", "float": "c_float", "int64_t": "i64", "uint32_t": "u32", "size_t": "usize",
+              "uint64_t": "u64", "double": "f64", "void": "c_void", "char": "c_char", "int16_t": "i16"}
+    opaque = {"crispy_ns_model": "CrispyNsModel", "crispy_ns_state": "CrispyNsState",
+              "crispy_ns_batch": "CrispyNsBatch", "crispy_ns_multi": "CrispyNsMulti"}
+
+    def c_to_rust(decl: str) -> str:
+        decl = re.sub(r"\b[A-Za-z_]\w*\s*$", "", decl.strip()) if not decl.strip().endswith("*") else decl.strip()
+        toks = re.findall(r"const|\*|\w+", decl)
+        base = [t for t in toks if t not in ("const", "*", "struct")][0]
+        out = opaque.get(base) or scalar[base]
+        # walk the declarator left to right: "const T *" -> *const T, "T *" -> *mut T, "const T *const *" -> *const *const T
+        consts, stars, pending = [], 0, "const" in toks[:toks.index(base) + 1]
+        for t in toks[toks.index(base) + 1:]:
+            if t == "*":
+                consts.append(pending)
+                pending = False
+            elif t == "const":
+                pending = True
+        for is_const in consts:
+            out = ("*const " if is_const else "*mut ") + out
+        return out
+
+    protos = {}
+    for m in re.finditer(r"([\w \*]+?)\b(crispy_ns_\w+)\s*\(([^;{]*?)\)\s*;", h, flags=re.S):
+        args = " ".join(m.group(3).split())
+        protos[m.group(2)] = ([] if args in ("", "void") else [c_to_rust(a) for a in args.split(",")],
+                              " ".join(m.group(1).split()))
+    blk = rs[rs.index('extern "C" {'):]
+    blk = blk[:blk.index("\n}\n")]
+    bound = 0
+    for m in re.finditer(r"fn (crispy_ns_\w+)\s*\((.*?)\)\s*(?:->\s*([\w\* ]+?))?\s*;", blk, flags=re.S):
+        name, args, ret = m.group(1), m.group(2).strip().rstrip(","), (m.group(3) or "").strip()
+        assert name in protos, f"{name} is not declared in crispy_ns.h"
+        rust_types = [" ".join(a.split(":", 1)[1].split()) for a in args.split(",")] if args else []
+        assert rust_types == protos[name][0], (name, rust_types, protos[name][0])
+        c_ret = protos[name][1]
+        want_ret = "" if c_ret == "void" else c_to_rust(c_ret + " x" if not c_ret.endswith("*") else c_ret)
+        assert ret == want_ret, (name, ret, want_ret)
+        bound += 1
+    assert bound >= 20
+    for flag in ("IN_I16", "OUT_I16", "UNIT_SCALE", "MIX_STEREO_I16", "DROP_FIRST_FRAME"):
+        hv = re.search(rf"CRISPY_NS_{flag}\s*=\s*1u\s*<<\s*(\d+)", h).group(1)
+        rv = re.search(rf"CRISPY_NS_{flag}: u32 = 1 << (\d+)", rs).group(1)
+        assert hv == rv, flag
+    # the drop-in surface audio.rs type-checks against (audio.rs:4, :203, :229, :268)
+    assert "pub const FRAME_SIZE: usize = 480;" in rs
+    assert "pub struct DenoiseState<'model>" in rs and "pub fn new() -> Box<DenoiseState<'static>>" in rs
+    assert "pub fn process_frame(&mut self, output: &mut [f32], input: &[f32]) -> f32" in rs
