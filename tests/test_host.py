@@ -252,3 +252,42 @@ def test_rust_shim_extern_block_matches_the_header():
     assert "pub const FRAME_SIZE: usize = 480;" in rs
     assert "pub struct DenoiseState<'model>" in rs and "pub fn new() -> Box<DenoiseState<'static>>" in rs
     assert "pub fn process_frame(&mut self, output: &mut [f32], input: &[f32]) -> f32" in rs
+
+
+def test_ctypes_prototypes_match_the_header():
+    """crispy_b200/_lib.py declares argtypes by hand: every prototype in include/crispy_ns.h is compared with it,
+    argument by argument (scalar width and signedness, pointer or not) and for the return type, so a drift between
+    the header and the Python binding cannot go unseen."""
+    import ctypes as C
+    import re
+    h = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "crispy_ns.h")).read(), flags=re.S)
+    L = _lib.lib()
+    scalar = {"int": C.c_int, "float": C.c_float, "int64_t": C.c_int64, "uint32_t": C.c_uint32, "size_t": C.c_size_t,
+              "uint64_t": C.c_uint64, "double": C.c_double}
+
+    def is_pointer(t) -> bool:
+        return t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer))
+
+    seen = 0
+    for m in re.finditer(r"([\w \*]+?)\b(crispy_ns_\w+)\s*\(([^;{]*?)\)\s*;", h, flags=re.S):
+        ret, name, args = " ".join(m.group(1).split()), m.group(2), " ".join(m.group(3).split())
+        if "typedef" in ret:
+            continue
+        fn = getattr(L, name)
+        c_args = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        if c_args:
+            assert fn.argtypes is not None and len(fn.argtypes) == len(c_args), (name, fn.argtypes, c_args)
+        for a, t in zip(c_args, fn.argtypes or []):
+            if "*" in a:
+                assert is_pointer(t), (name, a, t)
+            else:
+                base = [w for w in re.findall(r"\w+", a) if w != "const"][0]
+                assert t is scalar[base], (name, a, t)
+        if ret == "void":
+            assert fn.restype is None, name
+        elif "*" in ret:
+            assert is_pointer(fn.restype), (name, fn.restype)
+        else:
+            assert fn.restype is scalar[ret], (name, ret, fn.restype)
+        seen += 1
+    assert seen == len(_lib.SYMBOLS), (seen, len(_lib.SYMBOLS))
