@@ -198,3 +198,30 @@ def test_both_forms_of_the_biquad_kernel_give_the_same_bits(model_blob, sig, mon
     b = emu_process(model_blob, sig, chunk=8)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert np.array_equal(canonical_state(a[3]).view(np.uint32), canonical_state(b[3]).view(np.uint32))
+
+
+def test_non_finite_input_poisons_only_its_own_stream(oracle_model, model_blob):
+    """NaN, Inf or near-overflow samples in one recording (a glitching capture device) must not reach its batch
+    neighbours: streams share CTAs in every kernel (32 per biquad warp, 16 per recurrent-core CTA whose matrix
+    products run one stream per accumulator row).  The neighbours' output, VAD and taps are bit-identical to a run
+    without the glitches; the glitched streams go non-finite from the same frame on as the oracle's do (upstream keeps
+    no guard either: a DenoiseState that has seen a NaN stays NaN until it is rebuilt, audio.rs:955-965)."""
+    ns, nf = 18, 6  # two recurrent-core groups
+    x = make_signal(ns, nf)
+    clean = emu_process(model_blob, x, chunk=6)
+    bad = x.copy()
+    bad[3, 480 * 2 + 17] = np.nan
+    bad[17, 480 * 1 + 5] = np.inf
+    bad[8, 480 * 3: 480 * 3 + 4] = [3e38, -3e38, 3e38, -3e38]
+    dirty = emu_process(model_blob, bad, chunk=6)
+    keep = [s for s in range(ns) if s not in (3, 17, 8)]
+    for a, b in zip(clean[:3], dirty[:3]):  # output, VAD, taps
+        assert np.array_equal(a[keep], b[keep])
+    assert np.array_equal(canonical_state(clean[3])[keep], canonical_state(dirty[3])[keep])
+    ref, _ = po.process_streams(oracle_model, bad)
+    for s in (3, 17, 8):
+        got_nan = np.isnan(dirty[0][s].reshape(nf, 480)).any(1)
+        want_nan = np.isnan(ref[s].reshape(nf, 480)).any(1)
+        assert np.array_equal(got_nan, want_nan), (s, got_nan, want_nan)
+        first = int(np.argmax(want_nan))
+        assert np.array_equal(dirty[0][s, : first * 480], clean[0][s, : first * 480])  # untouched before the glitch
