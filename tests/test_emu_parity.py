@@ -200,12 +200,14 @@ def test_both_forms_of_the_biquad_kernel_give_the_same_bits(model_blob, sig, mon
     assert np.array_equal(canonical_state(a[3]).view(np.uint32), canonical_state(b[3]).view(np.uint32))
 
 
-def test_non_finite_input_poisons_only_its_own_stream(oracle_model, model_blob):
+@pytest.mark.parametrize("hp_par", ["1", "0"])  # both forms of the biquad kernel
+def test_non_finite_input_poisons_only_its_own_stream(oracle_model, model_blob, hp_par, monkeypatch):
     """NaN, Inf or near-overflow samples in one recording (a glitching capture device) must not reach its batch
     neighbours: streams share CTAs in every kernel (32 per biquad warp, 16 per recurrent-core CTA whose matrix
     products run one stream per accumulator row).  The neighbours' output, VAD and taps are bit-identical to a run
     without the glitches; the glitched streams go non-finite from the same frame on as the oracle's do (upstream keeps
     no guard either: a DenoiseState that has seen a NaN stays NaN until it is rebuilt, audio.rs:955-965)."""
+    monkeypatch.setenv("CRISPY_NS_HP_PAR", hp_par)
     ns, nf = 18, 6  # two recurrent-core groups
     x = make_signal(ns, nf)
     clean = emu_process(model_blob, x, chunk=6)
