@@ -109,3 +109,22 @@ def test_downmix_of_identical_channels_is_the_channel(ch, n, seed, fmt):  # audi
         assert np.array_equal(y, unit)
     else:
         assert np.allclose(y, unit, rtol=3e-7, atol=1e-12)
+
+
+@settings(max_examples=150, deadline=None)
+@given(n=st.integers(0, 6000),
+       rin=st.one_of(st.sampled_from([8000.0, 11025.0, 16000.0, 22050.0, 32000.0, 44100.0, 47999.5, 48000.0, 48000.9, 88200.0,
+                                      96000.0, 192000.0]), st.floats(4000.0, 200000.0, width=32)),
+       rout=st.sampled_from([48000.0, 44100.0, 16000.0]))
+def test_linear_resampler_count_matches_the_sample_by_sample_walk(n, rin, rout):  # audio.rs:108-133
+    """LinearResampler emits while next_out_pos <= in_pos with f64 positions: the library's closed count (what sizes
+    the device output row) equals the length of the oracle's sample-by-sample walk for any device rate, including
+    the |in - out| < 1 passthrough (audio.rs:109-112), and the outputs stay inside the range of the input."""
+    x = np.linspace(-1.0, 1.0, n, dtype=np.float32)
+    y = po.linear_resample(x, rin, rout)
+    assert _lib.lib().crispy_ns_linear_resample_count(rin, rout, n) == len(y)
+    if abs(np.float32(rin) - np.float32(rout)) < 1.0:
+        assert np.array_equal(y, x)
+    elif len(y):
+        assert y.min() >= x.min() - 1e-6 and y.max() <= x.max() + 1e-6
+        assert np.all(np.diff(y.astype(np.float64)) >= -1e-6)
