@@ -291,3 +291,26 @@ def test_ctypes_prototypes_match_the_header():
             assert fn.restype is scalar[ret], (name, ret, fn.restype)
         seen += 1
     assert seen == len(_lib.SYMBOLS), (seen, len(_lib.SYMBOLS))
+
+
+def test_product_never_touches_the_oracle_and_has_no_cpu_fallback():
+    """The oracle is test infrastructure: nothing under crispy_b200/ (Python or C++/CUDA), include/ or bindings/ may
+    import, include, link or load it; importing the product must not pull the oracle's modules in either; and the
+    library links neither the oracle nor the host emulation (its only compute is the sm_100a code in it)."""
+    import re
+    import subprocess
+    import sys
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b|#\s*include\s*[<\"][^>\"]*(oracle|ns_emu)[^>\"]*[>\"])|"
+                     r"(CDLL|dlopen)\([^)]*oracle", re.M)
+    for top in ("crispy_b200", "include", "bindings"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".inc", ".rs")):
+                    src = open(os.path.join(dirpath, f), errors="replace").read()
+                    assert not pat.search(src), os.path.join(dirpath, f)
+    code = ("import sys; sys.path.insert(0, %r); import crispy_b200, crispy_b200.denoise, crispy_b200.shard; "
+            "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; print(bad); sys.exit(bool(bad))" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ldd = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "ns_emu" not in ldd, ldd
