@@ -1755,20 +1755,32 @@ int wav_read_pcm16(const char *path, int16_t *interleaved, int64_t cap_samples, 
     if (fread(c, 1, 8, f) != 8) break;
     const uint32_t sz = (uint32_t)c[4] | ((uint32_t)c[5] << 8) | ((uint32_t)c[6] << 16) | ((uint32_t)c[7] << 24);
     if (memcmp(c, "fmt ", 4) == 0) {
-      uint8_t fm[16];
-      if (sz < 16 || fread(fm, 1, 16, f) != 16) break;
+      uint8_t fm[40];
+      const size_t take = sz < 40 ? sz : 40;
+      if (sz < 16 || fread(fm, 1, take, f) != take) break;
       fmt = fm[0] | (fm[1] << 8);
       ch = fm[2] | (fm[3] << 8);
       sr = (int)((uint32_t)fm[4] | ((uint32_t)fm[5] << 8) | ((uint32_t)fm[6] << 16) | ((uint32_t)fm[7] << 24));
       bits = fm[14] | (fm[15] << 8);
+      // WAVE_FORMAT_EXTENSIBLE (what hound and ffmpeg write for more than two channels): the sample format is the
+      // first field of the sub-format GUID
+      if (fmt == 0xFFFE && take >= 26) fmt = fm[24] | (fm[25] << 8);
       have_fmt = true;
-      if (sz > 16) fseek(f, (long)(sz - 16 + (sz & 1)), SEEK_CUR);
+      if (sz + (sz & 1) > take) fseek(f, (long)(sz + (sz & 1) - take), SEEK_CUR);
     } else if (memcmp(c, "data", 4) == 0) {
       if (!have_fmt || fmt != 1 || bits != 16 || ch < 1) {
         fclose(f);
         return fail(CRISPY_NS_EIO, "wav_read: only PCM16 is supported");
       }
-      const int64_t total = (int64_t)sz / 2;
+      int64_t total = (int64_t)sz / 2;
+      if (sz == 0xFFFFFFFFu) {  // a writer that could not seek back (ffmpeg to a pipe): the data runs to the end of the file
+        const long pos = ftell(f);
+        fseek(f, 0, SEEK_END);
+        const long end = ftell(f);
+        fseek(f, pos, SEEK_SET);
+        total = (int64_t)(end > pos ? end - pos : 0) / 2;
+      }
+      total -= total % ch;
       if (n_frames) *n_frames = total / ch;
       if (channels) *channels = ch;
       if (sample_rate) *sample_rate = sr;

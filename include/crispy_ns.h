@@ -218,7 +218,12 @@ int crispy_ns_sinc_resample_chunk(int device, const float *d_in, int64_t in_firs
 int crispy_ns_resample_host(int device, const float *h_in, float *h_out, int n_streams, int64_t n_in,
                             int64_t in_stride, int64_t out_stride, int input_rate, int output_rate, int kind);
 
-/* ---- f3: RIFF/WAVE PCM16 I/O (recording.rs:83-121 writer; commands/recording.rs:385-460 parser) */
+/* ---- f3: RIFF/WAVE PCM16 I/O (recording.rs:83-121 writer; commands/recording.rs:385-460 parser).
+ * The reader walks the chunks as get_wav_duration does (unknown chunks skipped, pad bytes honoured), accepts the plain
+ * PCM header hound writes for the recorder's spec, fmt chunks of 18 or 40 bytes, WAVE_FORMAT_EXTENSIBLE with the PCM
+ * sub-format, and a data size of 0xFFFFFFFF (a writer that could not seek back: the data runs to the end of the
+ * file); anything that is not 16-bit PCM is refused with CRISPY_NS_EIO.  Call it with interleaved = NULL first to
+ * learn n_frames / channels / sample_rate. */
 int crispy_ns_wav_write_pcm16(const char *path, const int16_t *interleaved, int64_t n_frames,
                               int channels, int sample_rate);
 int crispy_ns_wav_read_pcm16(const char *path, int16_t *interleaved, int64_t cap_samples,

@@ -141,7 +141,14 @@ def test_wav_reader_walks_chunks_like_get_wav_duration(tmp_path):  # commands/re
         return b"RIFF" + struct.pack("<I", len(body)) + body
 
     lavf = b"LIST" + struct.pack("<I", 26) + b"INFOISFT" + struct.pack("<I", 14) + b"Lavf60.16.100\0"
+    guid = lambda t: struct.pack("<H", t) + bytes.fromhex("000000001000800000aa00389b71")  # KSDATAFORMAT_SUBTYPE_*
+    ext = struct.pack("<HHI", 22, 16, 3)  # cbSize, valid bits, channel mask
+    streamed = wav([fmt()], q.tobytes())
+    streamed = streamed[:40] + struct.pack("<I", 0xFFFFFFFF) + streamed[44:]  # ffmpeg to a pipe: size never patched
     good = {"hound44": wav([fmt()], q.tobytes()),
+            "extensible_pcm": wav([fmt(40, tag=0xFFFE, extra=ext + guid(1))], q.tobytes()),
+            "streamed_size": streamed,
+            "fmt17_padded": wav([fmt(17, extra=b"\0\0")], q.tobytes()),
             "ffmpeg_list": wav([fmt(), lavf], q.tobytes()),
             "fmt18": wav([fmt(18, extra=b"\0\0")], q.tobytes()),
             "odd_chunk_padded": wav([fmt(), b"junk" + struct.pack("<I", 3) + b"abc\0"], q.tobytes())}
@@ -156,6 +163,8 @@ def test_wav_reader_walks_chunks_like_get_wav_duration(tmp_path):  # commands/re
     y, sr = cb.wav_read_pcm16(str(p))
     assert y.shape == (0, 2) and sr == 48000
     bad = {"float32": wav([fmt(tag=3, bits=32)], np.zeros(200, np.float32).tobytes()),
+           "extensible_float": wav([fmt(40, tag=0xFFFE, bits=32, extra=struct.pack("<HHI", 22, 32, 3) + guid(3))],
+                                   np.zeros(200, np.float32).tobytes()),
            "pcm24": wav([fmt(bits=24)], bytes(600)),
            "truncated": wav([fmt()], q.tobytes())[:-50],
            "not_riff": b"RIFX" + bytes(60),
