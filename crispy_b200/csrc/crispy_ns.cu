@@ -1890,7 +1890,14 @@ int multi_process_streams_host(crispy_ns_multi *m, const void *h_in, void *h_out
     }
   };
   std::vector<std::thread> th;
-  for (size_t i = 1; i < nd; i++) th.emplace_back(work, i);
+  th.reserve(nd);
+  for (size_t i = 1; i < nd; i++) {
+    try {
+      th.emplace_back(work, i);
+    } catch (...) {  // no thread to be had: this device's share runs on the caller's thread (a joinable std::thread
+      work(i);       // left behind by an exception would terminate the process)
+    }
+  }
   work(0);
   for (auto &t : th) t.join();
   for (size_t i = 0; i < nd; i++)
